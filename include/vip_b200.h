@@ -1,0 +1,90 @@
+/*
+ * vip_b200 C ABI  --  B200 (sm_100a) kernels behind vip_hci.psfsub.pca / pca_annular and
+ * vip_hci.preproc.cube_derotate.
+ *
+ * The reference (vortex-exoplanet/VIP, vip_hci 2.0.1) is pure Python and has no FFI of its
+ * own; each entry point below replaces the numpy/scipy call sequence cited next to it
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes binding a VIP
+ * maintainer would add.
+ *
+ * Conventions
+ *   - all array arguments are DEVICE pointers unless the name ends in `_host`;
+ *   - matrices are dense row-major, fp32 data / fp64 small matrices as stated;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value: 0 = ok, <0 = error (message from vb_last_error(), thread-local);
+ *   - no ownership transfer: the caller allocates outputs and workspaces
+ *     (sizes from the *_workspace_bytes queries);
+ *   - calls are asynchronous on `stream` unless noted ("synchronises").
+ */
+#ifndef VIP_B200_H
+#define VIP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ABI version (major*1000 + minor). */
+int vb_version(void);
+/* Message of the last failed call on this thread ("" if none). */
+const char* vb_last_error(void);
+/* Number of kernel launches issued through this library by this process (all entry points). */
+long long vb_launch_count(void);
+
+/* ---- Gramian (PCA decomposition, O(n^2 p) part) ------------------------------------------
+ * G[n x n] (fp64) = A A^T for A[n x p] fp32.  deflate=1 routes through the mean-deflated
+ * formulation (temporal mean removed, rank-2 terms re-added in fp64).
+ * Replaces: np.linalg.svd(matrix.T) / np.dot(matrix, matrix.T)   psfsub/svd.py:466-475, 447-450 */
+size_t vb_gram_workspace_bytes(int n, size_t p);
+int vb_gram_f32(const float* A, int n, size_t p, int deflate, double* G, void* ws, size_t ws_bytes,
+                void* stream);
+/* C[na x nb] (fp64) = A B^T   (RDI / cube_sig projections: np.dot(V, matrix_emp.T), pca_fullfr.py:1728) */
+size_t vb_cross_gram_workspace_bytes(int na, int nb);
+int vb_cross_gram_f32(const float* A, int na, const float* B, int nb, size_t p, double* C, void* ws,
+                      size_t ws_bytes, void* stream);
+
+/* ---- symmetric eigensolver (fp64 block one-sided Jacobi) ----------------------------------
+ * evals[n] descending, evecs[n x n] with ROW j = eigenvector j.  G is not modified.
+ * info_host (optional, 2 ints): sweeps executed, converged flag.  Synchronises `stream`.
+ * Replaces: LAPACK dgesdd/dsyevd inside numpy                      psfsub/svd.py:450, 470 */
+size_t vb_eigh_workspace_bytes(int n);
+int vb_eigh_f64(const double* G, int n, double* evals, double* evecs, int max_sweeps, double tol,
+                void* ws, size_t ws_bytes, int* info_host, void* stream);
+
+/* ---- principal components and projection/subtraction --------------------------------------
+ * V[k x p] = Wt[k x n] . M[n x p]                                  psfsub/svd.py:451-459
+ * R[n x p] = M - C[n x k] . V[k x p]   (R may alias M)            psfsub/pca_fullfr.py:1728-1731 */
+int vb_pcs_f32(const float* Wt, const float* M, int k, int n, size_t p, float* V, void* stream);
+int vb_project_subtract_f32(const float* M, const float* C, int ldc, const float* V, int k, int n,
+                            size_t p, float* R, void* stream);
+/* out = a - b elementwise (reconstructed = matrix - residuals for full_output) */
+int vb_sub_f32(const float* a, const float* b, float* out, size_t count, void* stream);
+
+/* ---- FFT three-shear derotation of a cube --------------------------------------------------
+ * out[f] = frame f of `in` rotated exactly as frame_rotate(imlib='vip-fft', edge_blend=None)
+ * does for angle -angle_list[f]; the per-frame scalars are computed on the host with the
+ * reference's own numpy expressions: krot[f] = rint(angle/90) mod 4 (0 if angle <= 45),
+ * a[f] = tan(dangle/2), b[f] = -sin(dangle).  S = frame size (square), N = working plane size,
+ * y0 = offset of the frame in the plane (geometry of frame_pad / frame_center).
+ * mask: pixels that are NaN (mask_is_nan=1) or == mask_val are restored to mask_val in `out`;
+ * zero_masked=1 additionally feeds pixels == mask_val as 0 into the rotation.
+ * Replaces: cube_derotate -> frame_rotate -> rotate_fft -> _fft_shear
+ *           preproc/derotation.py:331-399, 51-328, 542-622, 625-640 */
+size_t vb_derotate_scratch_bytes(int nframes, int S, int N, size_t max_bytes);
+int vb_derotate_f32(const float* in, float* out, int nframes, int S, int N, int y0, const int* krot,
+                    const double* a, const double* b, float mask_val, int mask_is_nan, int zero_masked,
+                    void* scratch, size_t scratch_bytes, int force_direct, void* stream);
+
+/* ---- temporal collapse ---------------------------------------------------------------------
+ * cube[n x p] -> out[p].  mode: 0 median, 1 mean, 2 sum, 3 max, 4 absmean, 5 wmean (w: n
+ * doubles, out: double[p]), 6 trimmean (mean of sorted[trim_k : trim_k+trim_n]).  NaN-aware.
+ * Replaces: cube_collapse                                          preproc/subsampling.py:30-116 */
+int vb_collapse_f32(const float* cube, int n, size_t p, int mode, const double* w, int trim_k, int trim_n,
+                    void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIP_B200_H */

@@ -1,0 +1,87 @@
+"""Import the UNMODIFIED reference (vip_hci) from /root/reference for oracle pinning.
+
+TEST INFRASTRUCTURE.  Only usable in the build container (``/root/reference`` does not
+exist on the GPU box); used by ``tools/make_golden.py`` and
+``tests/test_oracle_vs_reference.py`` (skipped when the checkout is absent).
+
+vip_hci imports astropy / scikit-image / photutils / matplotlib / hciplot / ... at module
+scope, none of which is installed here and none of which is *called* on the default
+``pca`` / ``pca_annular`` / ``cube_derotate`` path.  A ``sys.meta_path`` finder serves
+empty stand-ins for exactly the top-level packages that are missing.
+"""
+import importlib.abc
+import importlib.machinery
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_SRC = os.environ.get("VIP_REFERENCE_SRC", "/root/reference/src")
+_OPTIONAL = ["astropy", "skimage", "photutils", "matplotlib", "hciplot", "emcee", "nestle",
+             "corner", "dataclass_builder", "pyds9", "munch", "ultranest"]
+
+
+class _Stub(types.ModuleType):
+    __path__ = []
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        modname = self.__name__
+
+        class _Missing(Warning):
+            def __init__(self, *a, **k):
+                raise ImportError(f"{modname}.{name} is not installed (stub)")
+        _Missing.__name__ = name
+        return _Missing
+
+
+class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def __init__(self, names):
+        self.names = set(names)
+
+    def find_spec(self, name, path, target=None):
+        if name.split(".")[0] in self.names:
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        return _Stub(spec.name)
+
+    def exec_module(self, module):
+        pass
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_SRC, "vip_hci"))
+
+
+_loaded = None
+
+
+def load():
+    """Return the reference ``vip_hci`` package (imported once)."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not available():
+        raise ImportError(f"reference checkout not found under {REFERENCE_SRC}")
+    missing = []
+    for m in _OPTIONAL:
+        try:
+            if importlib.util.find_spec(m) is None:
+                missing.append(m)
+        except (ImportError, ValueError):
+            missing.append(m)
+    sys.meta_path.append(_Finder(missing))
+    if REFERENCE_SRC not in sys.path:
+        sys.path.insert(0, REFERENCE_SRC)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import vip_hci  # noqa
+        import vip_hci.psfsub  # noqa
+        import vip_hci.preproc  # noqa
+        import vip_hci.var  # noqa
+    _loaded = vip_hci
+    return vip_hci

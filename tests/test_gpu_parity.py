@@ -1,0 +1,252 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+fixtures of the unmodified reference.
+
+Tolerances (north_star: "within a stated fp32 tolerance, bit-exact for indexing"):
+  * derotation:   max|out-ref| <= 2e-5 * max|ref|   (reference rotates in fp64, we in fp32)
+  * PCA residuals / final frames: <= 1e-4 * max|ref|  
+  * collapse median/mean/sum/max/absmean: bit-exact
+"""
+import numpy as np
+import pytest
+
+from oracle import vip_oracle as O
+from tools.synth import adi_cube
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+DEROT_TOL = 2e-5
+PCA_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def vb():
+    import vip_b200
+    return vip_b200
+
+
+# ------------------------------------------------------------------ derotation
+@pytest.mark.parametrize("key", ["derot32", "derot33", "derot128"])
+def test_derotate_golden(vb, golden, golden_inputs, key):
+    cube, angs = golden_inputs[key]
+    out = vb.cube_derotate(cube, angs)
+    assert out.dtype == cube.dtype and out.shape == cube.shape
+    assert rel_err(out, golden["derotate"][key]) < DEROT_TOL
+
+
+def test_derotate_mask0_golden(vb, golden, golden_inputs):
+    cube, angs = golden_inputs["derot32"]
+    cube = np.where(np.isnan(cube), 0, cube)
+    out = vb.cube_derotate(cube, angs, mask_val=0, interp_zeros=True)
+    assert rel_err(out, golden["derotate"]["derot32_mask0"]) < DEROT_TOL
+
+
+@pytest.mark.parametrize("S", [16, 17, 64, 101, 128, 256])
+def test_derotate_vs_oracle_sizes(vb, S):
+    """Generic (direct Dirichlet) path for non power-of-two planes, FFT path for S=128 (N=512) and
+    S=256 (N=1024); all rot90 quadrants and the rint() quirk angles."""
+    rng = np.random.default_rng(S)
+    angs = np.array([12.3, -33.0, 77.7, 181.0, 300.5, 135.0, 315.0, 45.0, 0.0, 360.0, 225.5, 269.9])
+    cube = rng.normal(size=(len(angs), S, S)).astype(np.float32)
+    cube[1, 2, 3] = np.nan
+    out = vb.cube_derotate(cube, angs)
+    assert rel_err(out, O.cube_derotate(cube, angs)) < DEROT_TOL
+
+
+def test_derotate_fft_and_direct_agree(vb):
+    """Same cube through the FFT kernels and through the direct kernels (S=128 -> N=512)."""
+    import torch
+    from vip_b200.preproc.derotation import derotate_device
+    cube, angs = adi_cube(6, 128, 3, 50.0, seed=2)
+    dev = torch.from_numpy(cube - cube.mean(0)).cuda()
+    a = derotate_device(dev, -angs).cpu().numpy()
+    b = derotate_device(dev, -angs, force_direct=True).cpu().numpy()
+    assert rel_err(a, b) < DEROT_TOL
+
+
+def test_derotate_float64_in_float64_out(vb):
+    rng = np.random.default_rng(5)
+    cube = rng.normal(size=(3, 20, 20))
+    out = vb.cube_derotate(cube, np.array([10.0, 100.0, 200.0]))
+    assert out.dtype == np.float64
+    assert rel_err(out, O.cube_derotate(cube, np.array([10.0, 100.0, 200.0]))) < DEROT_TOL
+
+
+def test_derotate_24x_identity(vb):
+    """Reference test tests/pre_3_10/test_preproc_rotation.py:18-69."""
+    for size, crop in ((80, 50), (81, 51)):
+        res = np.ones((4, size, size))
+        angles = np.array([120, 90, 60, 45])
+        for _ in range(24):
+            res = vb.cube_derotate(res, angles)
+        c0 = (size - crop) // 2
+        np.testing.assert_allclose(res[:, c0:c0 + crop, c0:c0 + crop], 1.0, rtol=1e-1, atol=1e-1)
+
+
+# ------------------------------------------------------------------ collapse
+def test_collapse_bit_exact(vb, golden, golden_inputs):
+    g = golden["collapse"]
+    cube = golden_inputs["small"][0].copy()
+    cube[3, 5, 5] = np.nan
+    cube[:, 7, 7] = np.nan
+    for m in ("median", "mean", "sum", "max", "absmean"):
+        out = vb.cube_collapse(cube, m)
+        assert out.dtype == np.float32
+        np.testing.assert_array_equal(out, g[m], err_msg=m)
+    np.testing.assert_array_equal(vb.cube_collapse(cube[:-1], "median"), g["median_even"])
+    assert rel_err(vb.cube_collapse(cube, "trimmean", n=10), g["trimmean"]) < 1e-6
+    w = np.random.default_rng(1).uniform(size=30)
+    out = vb.cube_collapse(cube, "wmean", w=w)
+    assert out.dtype == np.float64
+    np.testing.assert_allclose(out, g["wmean"], rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 64, 501])
+def test_collapse_median_edge_cases(vb, n):
+    rng = np.random.default_rng(n)
+    cube = rng.normal(size=(n, 9, 13)).astype(np.float32)
+    cube[rng.uniform(size=cube.shape) < 0.1] = np.nan      # ragged NaN counts per pixel
+    cube[:, 0, 0] = 3.5                                    # all ties
+    cube[:, 1, 1] = np.nan                                 # all NaN
+    cube[: n // 2, 2, 2] = -0.0                            # signed zeros / duplicates
+    cube[n // 2:, 2, 2] = 0.0
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = np.nanmedian(cube, axis=0)
+    out = vb.cube_collapse(cube, "median")
+    np.testing.assert_array_equal(out, ref)
+
+
+def test_collapse_4d(vb):
+    rng = np.random.default_rng(0)
+    cube = rng.normal(size=(3, 11, 8, 8)).astype(np.float32)
+    np.testing.assert_array_equal(vb.cube_collapse(cube, "median"), np.nanmedian(cube, axis=1))
+
+
+# ------------------------------------------------------------------ linear algebra kernels
+def test_gram_and_eigh_accuracy():
+    import torch
+    from vip_b200 import kernels
+    cube, _ = adi_cube(150, 64, 10, 60.0, seed=8)
+    M = cube.reshape(150, -1)
+    G = kernels.gram(torch.from_numpy(M).cuda()).cpu().numpy()
+    G64 = M.astype(np.float64) @ M.astype(np.float64).T
+    assert np.max(np.abs(G - G64)) / np.max(np.abs(G64)) < 1e-9
+    # deflated assembly is what keeps the small eigen-directions accurate: compare on D D^T scale
+    D = M.astype(np.float64) - M.astype(np.float64).mean(0)
+    scale = np.max(np.abs(D @ D.T))
+    assert np.max(np.abs(G - G64)) / scale < 1e-6
+    evals, evecs, info = kernels.eigh(torch.from_numpy(G64).cuda())
+    assert info["converged"]
+    w, v = np.linalg.eigh(G64)
+    np.testing.assert_allclose(evals.cpu().numpy(), w[::-1], rtol=1e-10, atol=1e-8 * w[-1])
+    E = evecs.cpu().numpy()
+    np.testing.assert_allclose(E @ E.T, np.eye(150), atol=1e-10)
+    k = 10
+    P1 = E[:k].T @ E[:k]
+    P2 = v[:, ::-1][:, :k] @ v[:, ::-1][:, :k].T
+    assert np.max(np.abs(P1 - P2)) < 1e-9
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 33, 130])
+def test_eigh_small_and_odd_sizes(n):
+    import torch
+    from vip_b200 import kernels
+    rng = np.random.default_rng(n)
+    A = rng.normal(size=(n, n + 5))
+    G = A @ A.T
+    evals, evecs, info = kernels.eigh(torch.from_numpy(G).cuda())
+    w = np.linalg.eigvalsh(G)[::-1]
+    np.testing.assert_allclose(evals.cpu().numpy(), w, rtol=1e-10, atol=1e-12 * w[0])
+    E = evecs.cpu().numpy()
+    np.testing.assert_allclose((E * evals.cpu().numpy()[:, None]).T @ E, G, atol=1e-9 * w[0])
+
+
+def test_pcs_and_project_subtract_match_numpy():
+    import torch
+    from vip_b200 import kernels
+    rng = np.random.default_rng(1)
+    for n, p, k in ((37, 1000, 5), (300, 4099, 20), (64, 513, 40)):
+        M = rng.normal(size=(n, p)).astype(np.float32)
+        Wt = rng.normal(size=(k, n)).astype(np.float32)
+        C = rng.normal(size=(n, k)).astype(np.float32)
+        dM = torch.from_numpy(M).cuda()
+        V = kernels.pcs(torch.from_numpy(Wt).cuda(), dM)
+        Vr = Wt.astype(np.float64) @ M.astype(np.float64)
+        assert np.max(np.abs(V.cpu().numpy() - Vr)) < 1e-4 * np.max(np.abs(Vr))
+        R = kernels.project_subtract(dM, torch.from_numpy(C).cuda(), V)
+        Rr = M - C.astype(np.float64) @ V.cpu().numpy().astype(np.float64)
+        assert np.max(np.abs(R.cpu().numpy() - Rr)) < 1e-4 * np.max(np.abs(Rr))
+
+
+# ------------------------------------------------------------------ pca()
+def test_pca_c1_golden(vb, golden, golden_inputs):
+    """BASELINE config 1 (50x101x101, ncomp=5, lapack) against the reference's own output."""
+    g = golden["pca_fullframe"]
+    cube, angs = golden_inputs["c1"]
+    fr, pcs, recon, res, res_ = vb.pca(cube, angs, ncomp=5, verbose=False, full_output=True)
+    assert fr.dtype == np.float32 and fr.shape == (101, 101)
+    assert pcs.shape == (5, 101, 101) and recon.shape == res.shape == res_.shape == cube.shape
+    scale = np.max(np.abs(g["c1_res_frame7"]))
+    assert np.max(np.abs(res[7] - g["c1_res_frame7"])) < PCA_TOL * scale
+    assert np.max(np.abs(res_[7] - g["c1_resder_frame7"])) < PCA_TOL * scale
+    assert rel_err(fr, g["c1_frame"]) < PCA_TOL
+    P = pcs.reshape(5, -1)
+    proj = (P.T @ P)[::97, ::89]
+    assert np.max(np.abs(proj - g["c1_proj"])) < 1e-5        # span(V) matches (sign-invariant)
+    np.testing.assert_allclose(recon + res, cube, rtol=0, atol=2e-3)
+    assert rel_err(vb.pca(cube, angs, ncomp=5, verbose=False), g["c1_frame"]) < PCA_TOL
+
+
+def test_pca_options_golden(vb, golden, golden_inputs):
+    g = golden["pca_fullframe"]
+    cube, angs = golden_inputs["small"]
+    for mode in ("lapack", "eigen", "arpack"):
+        assert rel_err(vb.pca(cube, angs, ncomp=4, svd_mode=mode, verbose=False), g["small_lapack"]) < PCA_TOL
+    for sc in ("temp-mean", "spat-mean", "temp-standard", "spat-standard"):
+        assert rel_err(vb.pca(cube, angs, ncomp=3, scaling=sc, verbose=False), g[f"small_{sc}"]) < 2e-4, sc
+    for col in ("mean", "sum"):
+        assert rel_err(vb.pca(cube, angs, ncomp=3, collapse=col, verbose=False), g[f"small_{col}"]) < PCA_TOL
+    ref = adi_cube(20, 41, 4, 60.0, seed=6)[0]
+    assert rel_err(vb.pca(cube, angs, cube_ref=ref, ncomp=4, verbose=False), g["small_rdi"]) < PCA_TOL
+    assert rel_err(vb.pca(cube, angs, cube_ref=ref, ncomp=4, ref_strategy="ARDI", verbose=False),
+                   g["small_ardi"]) < PCA_TOL
+    assert rel_err(vb.pca(cube, angs, ncomp=0.9995, verbose=False), g["small_cevr"]) < PCA_TOL
+    # positional arguments in dataclass order + algo_params object
+    fr = vb.pca(cube, angs, None, None, 4, "lapack", verbose=False)
+    assert rel_err(fr, g["small_lapack"]) < PCA_TOL
+    from vip_b200.psfsub import PCA_Params
+    fr = vb.pca(algo_params=PCA_Params(cube=cube, angle_list=angs, ncomp=4, verbose=False))
+    assert rel_err(fr, g["small_lapack"]) < PCA_TOL
+
+
+def test_pca_mask_center_and_cube_sig_vs_oracle(vb, golden_inputs):
+    cube, angs = golden_inputs["small"]
+    fr = vb.pca(cube, angs, ncomp=3, mask_center_px=4, verbose=False)
+    assert rel_err(fr, O.pca_fullframe(cube, angs, ncomp=3, mask_center_px=4)) < PCA_TOL
+    sig = np.zeros_like(cube)
+    sig[:, 30:34, 20:24] = 5.0
+    fr = vb.pca(cube, angs, ncomp=3, cube_sig=sig, verbose=False)
+    assert rel_err(fr, O.pca_fullframe(cube, angs, ncomp=3, cube_sig=sig)) < PCA_TOL
+
+
+def test_pca_errors(vb):
+    cube, angs = adi_cube(8, 16, 2, 30.0, seed=1)
+    with pytest.raises(ValueError):
+        vb.pca(cube, angs[:-1], ncomp=2, verbose=False)
+    with pytest.raises(ValueError):
+        vb.pca(cube, angs, ncomp=0, verbose=False)
+    fr = vb.pca(cube, angs, ncomp=50, verbose=False)       # clamped to n_frames like the reference
+    assert fr.shape == (16, 16)
+
+
+def test_pca_medium_vs_oracle(vb):
+    """200x128x128, ncomp=20: FFT derotation path + 2 Gram tiles; oracle finishes in ~15 s."""
+    cube, angs = adi_cube(200, 128, 20, 90.0, seed=20260103)
+    fr, pcs, recon, res, res_ = vb.pca(cube, angs, ncomp=20, verbose=False, full_output=True)
+    ofr, opcs, orecon, ores, ores_ = O.pca_fullframe(cube, angs, ncomp=20, full_output=True)
+    scale = np.max(np.abs(ores))
+    assert np.max(np.abs(res - ores)) < PCA_TOL * scale
+    assert np.max(np.abs(res_ - ores_)) < PCA_TOL * scale
+    assert rel_err(fr, ofr) < PCA_TOL

@@ -1,0 +1,87 @@
+"""Host-side behaviour of the drop-in boundary that needs no GPU: argument parsing, validation
+errors (same exception types as the reference), no silent CPU fallback."""
+import numpy as np
+import pytest
+
+import vip_b200
+from vip_b200.config import check_array, separate_kwargs_dict, setup_parameters, SvdMode
+from vip_b200.psfsub.pca_fullfr import PCA_Params
+from vip_b200.psfsub.annular import PCA_ANNULAR_Params
+
+
+def test_params_field_order_matches_reference():
+    names = list(PCA_Params.__dataclass_fields__)
+    assert names[:8] == ["cube", "angle_list", "cube_ref", "scale_list", "ncomp", "svd_mode", "scaling",
+                         "mask_center_px"]
+    assert names[-6:] == ["weights", "left_eigv", "min_frames_pca", "max_frames_pca", "cube_sig", "med_of_npcs"]
+    assert len(names) == 34
+    ann = list(PCA_ANNULAR_Params.__dataclass_fields__)
+    assert ann[:11] == ["cube", "angle_list", "cube_ref", "scale_list", "radius_int", "fwhm", "asize",
+                        "n_segments", "delta_rot", "delta_sep", "ncomp"]
+    assert len(ann) == 28
+    p = PCA_Params(None, None, None, None, 7, "eigen")
+    assert p.ncomp == 7 and p.svd_mode == SvdMode.EIGEN == "eigen"
+
+
+def test_separate_kwargs():
+    mine, rest = separate_kwargs_dict({"ncomp": 3, "mask_val": 0, "algo_params": 1, "imlib": "vip-fft"}, PCA_Params)
+    assert mine == {"ncomp": 3, "imlib": "vip-fft"} and rest == {"mask_val": 0, "algo_params": 1}
+
+    def f(cube, ncomp, full_output, other=1):
+        pass
+    got = setup_parameters(PCA_Params(cube=1, ncomp=2, full_output=False), f, full_output=True)
+    assert got == {"cube": 1, "ncomp": 2, "full_output": True}
+
+
+def test_check_array():
+    check_array(np.zeros((2, 3, 4)), (3, 4))
+    check_array([1, 2], 1)
+    with pytest.raises(TypeError):
+        check_array(np.zeros((3, 4)), (3, 4), msg="cube")
+    with pytest.raises(TypeError):
+        check_array("x", 3)
+    with pytest.raises(ValueError):
+        check_array(np.zeros(3), 7)
+
+
+def test_pca_validation_errors_before_any_gpu_work():
+    cube = np.zeros((5, 8, 8), np.float32)
+    angs = np.arange(5.0)
+    with pytest.raises(TypeError):
+        vip_b200.pca(np.zeros((8, 8)), angs)
+    with pytest.raises(NotImplementedError):
+        vip_b200.pca(cube, angs, left_eigv=True, cube_ref=cube)
+    with pytest.raises(NotImplementedError):
+        vip_b200.pca(cube, angs, imlib="opencv")
+    with pytest.raises(NotImplementedError):
+        vip_b200.pca(cube, angs, batch=2)
+    with pytest.raises(TypeError):
+        vip_b200.pca(cube, angs, cube_ref=cube, ref_strategy="XYZ")
+    with pytest.raises(TypeError):
+        vip_b200.cube_derotate(np.zeros((8, 8)), angs)
+    with pytest.raises(NotImplementedError):
+        vip_b200.cube_derotate(cube, angs, imlib="opencv")
+    with pytest.raises(ValueError):
+        vip_b200.cube_derotate(cube, angs, cxy=(1, 1))
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    cube = np.ones((5, 8, 8), np.float32)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        vip_b200.pca(cube, np.arange(5.0), ncomp=1, verbose=False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        vip_b200.cube_derotate(cube, np.arange(5.0))
+
+
+def test_product_never_imports_oracle():
+    import os
+    import re
+    root = os.path.dirname(vip_b200.__file__)
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f

@@ -1,0 +1,134 @@
+"""Known-answer vectors of the reference's own offline tests, replayed on the oracle AND on the
+host-side functions of the product (index logic must be bit-exact).
+
+Sources: tests/pre_3_10/test_preproc_rotation.py:131-186 (_define_annuli, _find_indices_adi),
+tests/pre_3_10/test_pca_svd.py:11-21 (lapack reconstruction), tests/pre_3_10/test_var_shapes.py
+(frame_center / annulus conventions), tests/pre_3_10/test_preproc_rotation.py:18-69 (24 successive
+derotations return the cube).
+"""
+import numpy as np
+import pytest
+
+from oracle import vip_oracle as O
+from vip_b200.preproc.derotation import (_compute_pa_thresh, _define_annuli, _find_indices_adi,
+                                         rotation_geometry, rotation_scalars)
+from vip_b200.preproc.parangles import check_pa_vector
+from vip_b200.var import frame_center, get_annulus_segments
+from vip_b200.var.shapes import circle_mask, mask_circle
+
+FIND_CASES = [
+    (0, None, 0, 0, 10, [3, 4, 5, 6]),
+    (1, None, 0, 0, 10, [3, 4, 5, 6]),
+    (2, None, 0, 0, 10, [4, 5, 6]),
+    (3, None, 0, 0, 10, [0, 1, 5, 6]),
+    (3, None, 1, 0, 10, (2, 4)),
+    (3, 2, 0, 0, 10, [1, 5]),
+    (3, None, 0, 1, 3, [1, 5, 6]),
+]
+
+
+@pytest.mark.parametrize("frame,nframes,out_closest,truncate,max_frames,truth", FIND_CASES)
+def test_find_indices_adi(frame, nframes, out_closest, truncate, max_frames, truth):
+    angles = np.array([130, 120, 90, 60, 30, 10, 0])
+    got = _find_indices_adi(angles, frame=frame, thr=42, nframes=nframes, out_closest=out_closest,
+                            truncate=truncate, max_frames=max_frames)
+    np.testing.assert_array_equal(np.asarray(got), np.asarray(truth))
+    if nframes is None and not out_closest:
+        np.testing.assert_array_equal(O.find_indices_adi(angles, frame, 42, truncate=bool(truncate),
+                                                         max_frames=max_frames), truth)
+
+
+def test_find_indices_random_vs_oracle():
+    rng = np.random.default_rng(3)
+    angs = np.cumsum(rng.uniform(0.2, 1.5, 120)) + 5
+    for thr in (0.5, 3.0, 11.0):
+        for fr in range(0, 120, 7):
+            for mf in (10, 50, 200):
+                a = _find_indices_adi(angs, fr, thr, truncate=True, max_frames=mf)
+                b = O.find_indices_adi(angs, fr, thr, truncate=True, max_frames=mf)
+                np.testing.assert_array_equal(a, b)
+                assert a.dtype == b.dtype
+
+
+def test_define_annuli():
+    angles = np.array([120, 90, 60, 30, 0])
+    pa, inner, centre = _define_annuli(angles, 0, 10, 4, 2, 4, 1, 1, False, strict=False)
+    np.testing.assert_allclose(pa, 53.13, rtol=1e-1, atol=1)
+    assert inner == 2 and centre == 4
+    assert (pa, inner, centre) == O.define_annuli(angles, 0, 10, 4, 2, 4, 1, strict=False)
+    # last annulus starts one pixel earlier; strict=True never clips
+    pa2, inner2, _ = _define_annuli(angles, 9, 10, 4, 2, 4, 1, 1, False, strict=True)
+    assert inner2 == 2 + 9 * 4 - 1
+    assert pa2 == _compute_pa_thresh(inner2 + 2, 4, 1) == O.compute_pa_thresh(inner2 + 2, 4, 1)
+
+
+def test_svd_recons_lapack():
+    mat = np.random.RandomState(42).randn(20, 100)
+    V = O.svd_wrapper(mat, "lapack", 20)
+    rec = (mat @ V.T) @ V
+    assert np.allclose(np.abs(mat), np.abs(rec), atol=1e-2)
+
+
+def test_frame_center_and_geometry():
+    assert frame_center(np.zeros((10, 10))) == (5, 5) == O.frame_center((10, 10))
+    assert frame_center(np.zeros((3, 11, 11))) == (5, 5) == O.frame_center((11, 11))
+    assert frame_center((4, 3, 8, 9)) == (4, 4)
+    with pytest.raises(ValueError):
+        frame_center(np.zeros(5))
+    assert rotation_geometry(512) == (2048, 768)
+    assert rotation_geometry(101) == (402, 151)
+    assert rotation_geometry(1024) == (4096, 1536)
+    # rint() quadrant quirk: exactly 135 deg uses the 180-deg quadrant, 315 deg none
+    k, a, b = rotation_scalars([135.0, 315.0, 50.0, -10.0])
+    assert list(k) == [2, 0, 1, 0]
+    np.testing.assert_allclose(a[0], np.tan(np.deg2rad(45) / 2))
+    np.testing.assert_allclose(a[2], np.tan(np.deg2rad(-40) / 2))
+    np.testing.assert_allclose(b[3], -np.sin(np.deg2rad(350 % 90 - 90)))
+
+
+def test_annulus_segments_vs_oracle():
+    for shape in ((40, 41), (33, 33), (64, 64)):
+        for ns in (1, 3, 4):
+            for th in (0, 30, 100, 359):
+                A = get_annulus_segments(shape, 5.5, 4, ns, th)
+                B = O.get_annulus_segments(shape, 5.5, 4, ns, th)
+                for (ya, xa), (yb, xb) in zip(A, B):
+                    np.testing.assert_array_equal(ya, yb)
+                    np.testing.assert_array_equal(xa, xb)
+    # small exact case: ring 1 <= r < 2 on a 5x5 grid around (2,2)
+    yy, xx = get_annulus_segments((5, 5), 1, 1)[0]
+    assert sorted(zip(yy.tolist(), xx.tolist())) == sorted(
+        [(1, 1), (1, 2), (1, 3), (2, 1), (2, 3), (3, 1), (3, 2), (3, 3)])
+
+
+def test_mask_circle_vs_oracle():
+    rng = np.random.default_rng(0)
+    for shape in ((20, 20), (21, 21)):
+        cube = rng.normal(size=(3,) + shape)
+        for r in (1, 3, 4.5):
+            np.testing.assert_array_equal(mask_circle(cube, r), O.mask_circle(cube, r))
+            np.testing.assert_array_equal(mask_circle(cube[0], r), O.mask_circle(cube[0], r))
+            np.testing.assert_array_equal(mask_circle(cube, r) == 0, np.broadcast_to(circle_mask(shape, r), cube.shape))
+
+
+def test_check_pa_vector():
+    a = np.array([350.0, 355.0, 0.0, 5.0])
+    np.testing.assert_array_equal(check_pa_vector(a), [350, 355, 360, 365])
+    np.testing.assert_array_equal(check_pa_vector(a), O.check_pa_vector(a))
+    b = np.array([-10.0, 5.0, 20.0])
+    np.testing.assert_array_equal(check_pa_vector(b), O.check_pa_vector(b))
+    with pytest.raises(ValueError):
+        check_pa_vector(a, unit="grad")
+
+
+def test_oracle_24_derotations_identity():
+    """test_preproc_rotation.py:18-69 on a reduced cube: 24 derotations by 120/90/60/45 deg = identity."""
+    for size, crop in ((40, 24), (41, 25)):
+        res = np.ones((4, size, size))
+        angles = np.array([120, 90, 60, 45])
+        for _ in range(24):
+            res = O.cube_derotate(res, angles)
+        c = size // 2
+        h = crop // 2
+        sl = slice(c - h, c - h + crop)
+        np.testing.assert_allclose(res[:, sl, sl], 1.0, rtol=1e-1, atol=1e-1)

@@ -1,0 +1,62 @@
+"""The CPU oracle against the UNMODIFIED reference imported from /root/reference (build container
+only; skipped on the GPU box where the checkout does not exist)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import ref_loader, vip_oracle as O
+from tools.synth import adi_cube
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    warnings.simplefilter("ignore")
+    ref_loader.load()
+    import vip_hci.psfsub as psfsub
+    import vip_hci.preproc as preproc
+    return psfsub, preproc
+
+
+def test_derotate_bit_identical(ref):
+    _, preproc = ref
+    rng = np.random.default_rng(1)
+    angs = np.array([12.3, -33, 77.7, 181, 300.5, 135, 315, 45, -400.2])
+    for S in (20, 21):
+        cube = rng.normal(size=(9, S, S)).astype(np.float32)
+        cube[2, 3, 4] = np.nan
+        np.testing.assert_array_equal(preproc.cube_derotate(cube, angs), O.cube_derotate(cube, angs))
+        c64 = np.nan_to_num(cube.astype(np.float64))
+        np.testing.assert_array_equal(
+            preproc.cube_derotate(c64, angs, mask_val=0, interp_zeros=True, ker=1),
+            O.cube_derotate(c64, angs, mask_val=0, interp_zeros=True))
+
+
+def test_pca_and_annular_bit_identical(ref):
+    psfsub, _ = ref
+    cube, angs = adi_cube(24, 33, 3, 60.0, seed=11)
+    for mode in ("lapack", "eigen"):
+        r = psfsub.pca(cube, angs, ncomp=3, svd_mode=mode, verbose=False, full_output=True)
+        o = O.pca_fullframe(cube, angs, ncomp=3, svd_mode=mode, full_output=True)
+        for a, b in zip(r, o):
+            np.testing.assert_array_equal(a, b)
+    np.random.seed(3)
+    r = psfsub.pca(cube, angs, ncomp=3, svd_mode="randsvd", verbose=False)
+    np.random.seed(3)
+    o = O.pca_fullframe(cube, angs, ncomp=3, svd_mode="randsvd")
+    np.testing.assert_array_equal(r, o)
+    r = psfsub.pca_annular(cube, angs, ncomp=2, asize=5, verbose=False, full_output=True)
+    o = O.pca_annular(cube, angs, ncomp=2, asize=5, full_output=True)
+    for a, b in zip(r, o):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_randsvd_restatement(ref):
+    cube, _ = adi_cube(24, 33, 3, 60.0, seed=11)
+    M = cube.reshape(24, -1)
+    om = np.random.RandomState(5).normal(size=(24, 13)).astype(np.float32)
+    V1 = O.svd_wrapper(M, "randsvd", 3, random_state=np.random.RandomState(5))
+    V2 = O.randsvd_restated(M, 3, om)
+    np.testing.assert_allclose(V1.T @ V1, V2.T @ V2, atol=1e-5)

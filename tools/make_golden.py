@@ -1,0 +1,99 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (vip_hci from /root/reference).
+
+Run in the build container only:  python tools/make_golden.py
+Inputs are regenerated from seeds by tools/synth.py (so only outputs are stored, as fp32/fp64 as the
+reference returns them).  The fixtures pin oracle/vip_oracle.py and the CUDA path.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+warnings.simplefilter("ignore")
+
+from oracle import ref_loader          # noqa: E402
+from tools.synth import adi_cube        # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_inputs():
+    """Seeded inputs shared by make_golden.py and the tests."""
+    rng = np.random.default_rng(777)
+    d = {}
+    # derotation: even/odd sizes, angles covering all rot90 quadrants, the 135/315 rint quirk, NaNs
+    angs = np.array([12.3, -33.0, 77.7, 181.0, 300.5, 135.0, 315.0, 45.0, -400.2, 90.0])
+    for S in (32, 33):
+        cube = rng.normal(size=(10, S, S)).astype(np.float32)
+        cube[2, 3, 4] = np.nan
+        cube[5, S - 1, 0] = np.nan
+        d[f"derot{S}"] = (cube, angs)
+    cube, a = adi_cube(12, 128, 4, 70.0, seed=31)          # FFT path (N=512)
+    d["derot128"] = (cube - cube.mean(0, keepdims=True), a * 3.7)
+    d["c1"] = adi_cube(50, 101, 5, 60.0, seed=20260102)    # BASELINE config 1
+    d["small"] = adi_cube(30, 41, 4, 60.0, seed=5)
+    d["ann"] = adi_cube(40, 48, 3, 80.0, seed=9)
+    return d
+
+
+def main():
+    vip = ref_loader.load()
+    from vip_hci.psfsub import pca, pca_annular
+    from vip_hci.preproc import cube_derotate, cube_collapse
+    os.makedirs(OUT, exist_ok=True)
+    inp = golden_inputs()
+    out = {}
+    for key in ("derot32", "derot33", "derot128"):
+        cube, angs = inp[key]
+        out[key] = cube_derotate(cube, angs)
+    cube, angs = inp["derot32"]
+    out["derot32_mask0"] = cube_derotate(np.where(np.isnan(cube), 0, cube), angs, mask_val=0, interp_zeros=True)
+    np.savez_compressed(os.path.join(OUT, "derotate.npz"), **out)
+
+    out = {}
+    cube, angs = inp["c1"]
+    fr, pcs, recon, res, res_ = pca(cube, angs, ncomp=5, verbose=False, full_output=True)
+    out["c1_frame"] = fr
+    out["c1_res_frame7"] = res[7]
+    out["c1_resder_frame7"] = res_[7]
+    out["c1_proj"] = (pcs.reshape(5, -1).T @ pcs.reshape(5, -1)).astype(np.float32)[::97, ::89]  # projector samples
+    cube, angs = inp["small"]
+    for mode in ("lapack", "eigen"):
+        out[f"small_{mode}"] = pca(cube, angs, ncomp=4, svd_mode=mode, verbose=False)
+    for sc in ("temp-mean", "spat-mean", "temp-standard", "spat-standard"):
+        out[f"small_{sc}"] = pca(cube, angs, ncomp=3, scaling=sc, verbose=False)
+    for col in ("mean", "sum"):
+        out[f"small_{col}"] = pca(cube, angs, ncomp=3, collapse=col, verbose=False)
+    ref = adi_cube(20, 41, 4, 60.0, seed=6)[0]
+    out["small_rdi"] = pca(cube, angs, cube_ref=ref, ncomp=4, verbose=False)
+    out["small_ardi"] = pca(cube, angs, cube_ref=ref, ncomp=4, ref_strategy="ARDI", verbose=False)
+    out["small_cevr"] = pca(cube, angs, ncomp=0.9995, verbose=False)
+    np.savez_compressed(os.path.join(OUT, "pca_fullframe.npz"), **out)
+
+    out = {}
+    cube, angs = inp["ann"]
+    co, cd, fr = pca_annular(cube, angs, ncomp=3, asize=6, verbose=False, full_output=True)
+    out["ann_frame"], out["ann_cube_out5"] = fr, co[5]
+    out["ann_seg_frame"] = pca_annular(cube, angs, ncomp=2, asize=6, n_segments=3, delta_rot=0.5,
+                                       radius_int=4, verbose=False)
+    np.savez_compressed(os.path.join(OUT, "pca_annular.npz"), **out)
+
+    out = {}
+    cube = inp["small"][0].copy()
+    cube[3, 5, 5] = np.nan
+    cube[:, 7, 7] = np.nan
+    for m in ("median", "mean", "sum", "max", "absmean", "trimmean"):
+        out[m] = cube_collapse(cube.copy(), m, n=10)
+    out["median_even"] = cube_collapse(cube[:-1].copy(), "median")
+    w = np.random.default_rng(1).uniform(size=30)
+    out["wmean"] = cube_collapse(cube.copy(), "wmean", w=w)
+    np.savez_compressed(os.path.join(OUT, "collapse.npz"), **out)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

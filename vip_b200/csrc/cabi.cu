@@ -1,0 +1,158 @@
+// C ABI of libvipb200.so (declared in include/vip_b200.h).
+#include "common.cuh"
+#include "../../include/vip_b200.h"
+#include <cstdarg>
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace vb {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- implemented in the other translation units
+size_t gram_workspace_bytes(int n, size_t p);
+int gram_f32(const float*, int, size_t, int, double*, void*, size_t, int, int*, cudaStream_t);
+int cross_gram_f32(const float*, int, const float*, int, size_t, double*, void*, size_t, int, cudaStream_t);
+size_t eigh_workspace_bytes(int n);
+int eigh_f64(const double*, int, double*, double*, int, double, void*, size_t, int*, int*, cudaStream_t);
+int pcs_f32(const float*, const float*, int, int, size_t, float*, int*, cudaStream_t);
+int project_subtract_f32(const float*, const float*, int, const float*, int, int, size_t, float*, int*,
+                         cudaStream_t);
+int sub_f32(const float*, const float*, float*, size_t, cudaStream_t);
+struct RotParams { int S; int N; int y0; int zero_masked; int mask_is_nan; float mask_val; };
+size_t derotate_scratch_bytes_per_frame(int S, int N);
+int derotate_run(const float*, float*, int, const RotParams&, const int*, const double*, const double*,
+                 const float2*, void*, size_t, int, int*, cudaStream_t);
+int collapse_f32(const float*, int, size_t, int, const double*, int, int, void*, cudaStream_t);
+
+// exp(-2 pi i j / N) tables for the FFT path, one per (device, N), built in fp64 on the host
+static const float2* twiddle_table(int N) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, float2*> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({dev, N});
+    if (it != cache.end()) return it->second;
+    std::vector<float2> h(N);
+    for (int j = 0; j < N; ++j) {
+        const double ang = -2.0 * 3.14159265358979323846 * (double)j / (double)N;
+        h[j] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    float2* d = nullptr;
+    if (cudaMalloc(&d, N * sizeof(float2)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h.data(), N * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    cache[{dev, N}] = d;
+    return d;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" {
+
+int vb_version(void) { return 1000; }
+const char* vb_last_error(void) { return g_err; }
+long long vb_launch_count(void) { return g_launches.load(); }
+
+size_t vb_gram_workspace_bytes(int n, size_t p) { return gram_workspace_bytes(n, p); }
+
+int vb_gram_f32(const float* A, int n, size_t p, int deflate, double* G, void* ws, size_t ws_bytes,
+                void* stream) {
+    int nl = 0;
+    const int rc = gram_f32(A, n, p, deflate, G, ws, ws_bytes, 0, &nl, (cudaStream_t)stream);
+    g_launches += nl;
+    return rc;
+}
+
+size_t vb_cross_gram_workspace_bytes(int na, int nb) {
+    return (size_t)ceil_div(na, 128) * ceil_div(nb, 128) * sizeof(int2) + 256;
+}
+
+int vb_cross_gram_f32(const float* A, int na, const float* B, int nb, size_t p, double* C, void* ws,
+                      size_t ws_bytes, void* stream) {
+    const int rc = cross_gram_f32(A, na, B, nb, p, C, ws, ws_bytes, 0, (cudaStream_t)stream);
+    g_launches += 1;
+    return rc;
+}
+
+size_t vb_eigh_workspace_bytes(int n) { return eigh_workspace_bytes(n); }
+
+int vb_eigh_f64(const double* G, int n, double* evals, double* evecs, int max_sweeps, double tol, void* ws,
+                size_t ws_bytes, int* info_host, void* stream) {
+    int nl = 0;
+    const int rc = eigh_f64(G, n, evals, evecs, max_sweeps, tol, ws, ws_bytes, info_host, &nl,
+                            (cudaStream_t)stream);
+    g_launches += nl;
+    return rc;
+}
+
+int vb_pcs_f32(const float* Wt, const float* M, int k, int n, size_t p, float* V, void* stream) {
+    int nl = 0;
+    const int rc = pcs_f32(Wt, M, k, n, p, V, &nl, (cudaStream_t)stream);
+    g_launches += nl;
+    return rc;
+}
+
+int vb_project_subtract_f32(const float* M, const float* C, int ldc, const float* V, int k, int n, size_t p,
+                            float* R, void* stream) {
+    int nl = 0;
+    const int rc = project_subtract_f32(M, C, ldc, V, k, n, p, R, &nl, (cudaStream_t)stream);
+    g_launches += nl;
+    return rc;
+}
+
+int vb_sub_f32(const float* a, const float* b, float* out, size_t count, void* stream) {
+    g_launches += 1;
+    return sub_f32(a, b, out, count, (cudaStream_t)stream);
+}
+
+size_t vb_derotate_scratch_bytes(int nframes, int S, int N, size_t max_bytes) {
+    const size_t per = derotate_scratch_bytes_per_frame(S, N);
+    size_t want = per * (size_t)nframes;
+    if (max_bytes && want > max_bytes) {
+        size_t frames = max_bytes / per;
+        if (frames < 1) frames = 1;
+        want = frames * per;
+    }
+    return want;
+}
+
+int vb_derotate_f32(const float* in, float* out, int nframes, int S, int N, int y0, const int* krot,
+                    const double* a, const double* b, float mask_val, int mask_is_nan, int zero_masked,
+                    void* scratch, size_t scratch_bytes, int force_direct, void* stream) {
+    VB_REQUIRE(nframes > 0 && S > 0, "derotate: empty cube");
+    VB_REQUIRE(N % 2 == 0 && N > S && y0 >= 0 && y0 + S + 1 <= N, "derotate: bad geometry S=%d N=%d y0=%d", S,
+               N, y0);
+    RotParams g{S, N, y0, zero_masked, mask_is_nan, mask_val};
+    const float2* tw = nullptr;
+    const bool pow2 = (N & (N - 1)) == 0 && N >= 512 && N <= 4096;
+    if (pow2 && !force_direct) {
+        tw = twiddle_table(N);
+        VB_REQUIRE(tw != nullptr, "derotate: could not build the twiddle table");
+    }
+    int nl = 0;
+    const int rc = derotate_run(in, out, nframes, g, krot, a, b, tw, scratch, scratch_bytes, force_direct,
+                                &nl, (cudaStream_t)stream);
+    g_launches += nl;
+    return rc;
+}
+
+int vb_collapse_f32(const float* cube, int n, size_t p, int mode, const double* w, int trim_k, int trim_n,
+                    void* out, void* stream) {
+    g_launches += 1;
+    return collapse_f32(cube, n, p, mode, w, trim_k, trim_n, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+// Gramian of the frames x pixels matrix, accumulated to fp64 (CUDA-core path).
+//
+// Role in the reference: the O(n^2 p) part of the PCA decomposition -- numpy's fp64 SVD of
+// M^T for svd_mode='lapack' (src/vip_hci/psfsub/svd.py:466-475) or  C = M.M^T  for 'eigen'
+// (svd.py:447-450).  numpy always decomposes in fp64, so to stay within fp32-level parity
+// through a (condition-squaring) Gramian we
+//   * deflate the temporal mean first:  M = 1 m^T + D,   G = D D^T + 1 (D m)^T + (D m) 1^T + (m.m) 1 1^T
+//     (D D^T has ~1e4 less dynamic range than M M^T on halo-dominated ADI cubes),
+//   * accumulate each K-chunk of 4096 pixels in fp32 FMA and reduce chunks in fp64 (atomics),
+//   * assemble G in fp64.                                             
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int GT = 128;   // output tile (GT x GT)
+constexpr int GK = 16;    // k-slab per smem stage
+constexpr int GLD = GT + 4;
+
+// temporal mean per pixel (fp64 accumulate -> fp32), one thread per pixel, coalesced over p
+__global__ void colmean_kernel(const float* __restrict__ A, int n, size_t p, float* __restrict__ mean) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += (double)A[(size_t)i * p + j];
+    mean[j] = (float)(s / n);
+}
+
+// C[na x nb] (fp64, atomics) += (A - 1 m^T)[rows] . (B - 1 m^T)[rows]^T over the K-chunk of this CTA.
+// tiles: list of (ti, tj) output tiles; blockIdx.y = K-chunk.
+__global__ void __launch_bounds__(256)
+gram_tile_kernel(const float* __restrict__ A, const float* __restrict__ B, int na, int nb, size_t p,
+                 const float* __restrict__ mean, double* __restrict__ C, int ldc,
+                 const int2* __restrict__ tiles, int kchunk) {
+    __shared__ __align__(16) float As[2][GK][GLD];
+    __shared__ __align__(16) float Bs[2][GK][GLD];
+    const int2 tile = tiles[blockIdx.x];
+    const int row0 = tile.x * GT, col0 = tile.y * GT;
+    const size_t k0 = (size_t)blockIdx.y * kchunk;
+    const size_t k1 = (k0 + kchunk < p) ? k0 + kchunk : p;
+    const int tid = threadIdx.x;
+    const int lk = tid & 15, lr = tid >> 4;   // loader: k offset, first row
+    const int ty = tid >> 4, tx = tid & 15;   // compute: 8x8 micro-tile at (ty*8, tx*8)
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    float ra[8], rb[8];
+    auto gload = [&](size_t kk) {
+        const size_t k = kk + lk;
+        const bool kin = k < k1;
+        const float m = (mean != nullptr && kin) ? __ldg(mean + k) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = lr + 16 * i;
+            ra[i] = (kin && row0 + r < na) ? __ldg(A + (size_t)(row0 + r) * p + k) - m : 0.f;
+            rb[i] = (kin && col0 + r < nb) ? __ldg(B + (size_t)(col0 + r) * p + k) - m : 0.f;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            As[buf][lk][lr + 16 * i] = ra[i];
+            Bs[buf][lk][lr + 16 * i] = rb[i];
+        }
+    };
+
+    gload(k0);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (size_t kk = k0; kk < k1; kk += GK) {
+        const bool more = kk + GK < k1;
+        if (more) gload(kk + GK);
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 8 + 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (more) {
+            sstore(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = row0 + ty * 8 + i;
+        if (r >= na) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = col0 + tx * 8 + j;
+            if (c < nb) atomicAdd(C + (size_t)r * ldc + c, (double)acc[i][j]);
+        }
+    }
+}
+
+// Dm[i] = sum_k (A[i,k] - m[k]) m[k]   (blocks 0..n-1),   mm = sum_k m[k]^2  (block n)
+__global__ void __launch_bounds__(256)
+deflate_terms_kernel(const float* __restrict__ A, int n, size_t p, const float* __restrict__ mean,
+                     double* __restrict__ Dm, double* __restrict__ mm) {
+    const int i = blockIdx.x;
+    double s = 0.0;
+    if (i < n) {
+        const float* row = A + (size_t)i * p;
+        for (size_t k = threadIdx.x; k < p; k += blockDim.x) {
+            const float m = mean[k];
+            s += (double)(row[k] - m) * (double)m;
+        }
+    } else {
+        for (size_t k = threadIdx.x; k < p; k += blockDim.x) {
+            const double m = mean[k];
+            s += m * m;
+        }
+    }
+    __shared__ double red[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        if (i < n) Dm[i] = t; else *mm = t;
+    }
+}
+
+// G = sym(Gd upper tiles) [+ deflation terms]
+__global__ void gram_assemble_kernel(const double* __restrict__ Gd, int n, const double* __restrict__ Dm,
+                                     const double* __restrict__ mm, double* __restrict__ G) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= n) return;
+    // only tiles with tile_row <= tile_col were accumulated
+    const bool upper = (i / GT) <= (j / GT);
+    double v = upper ? Gd[(size_t)i * n + j] : Gd[(size_t)j * n + i];
+    if (Dm != nullptr) v += Dm[i] + Dm[j] + *mm;
+    G[(size_t)i * n + j] = v;
+}
+
+size_t gram_workspace_bytes(int n, size_t p) {
+    const int nt = ceil_div(n, GT);
+    size_t b = 0;
+    b += ((p * sizeof(float) + 255) / 256) * 256;                  // mean
+    b += (((size_t)n * n * sizeof(double) + 255) / 256) * 256;     // Gd
+    b += (((size_t)n + 1) * sizeof(double) + 255) / 256 * 256;     // Dm, mm
+    b += ((size_t)nt * nt * sizeof(int2) + 255) / 256 * 256;       // tile list
+    return b;
+}
+
+// G (n x n fp64, row-major) = A A^T, optionally through the mean-deflated formulation.
+int gram_f32(const float* A, int n, size_t p, int deflate, double* G, void* ws, size_t ws_bytes,
+             int kchunk, int* launches, cudaStream_t st) {
+    VB_REQUIRE(n > 0 && p > 0, "gram: empty matrix");
+    VB_REQUIRE(ws_bytes >= gram_workspace_bytes(n, p), "gram: workspace too small");
+    if (kchunk <= 0) kchunk = 4096;
+    kchunk = ceil_div(kchunk, GK) * GK;
+    char* w = reinterpret_cast<char*>(ws);
+    float* mean = reinterpret_cast<float*>(w);
+    w += ((p * sizeof(float) + 255) / 256) * 256;
+    double* Gd = reinterpret_cast<double*>(w);
+    w += (((size_t)n * n * sizeof(double) + 255) / 256) * 256;
+    double* Dm = reinterpret_cast<double*>(w);
+    double* mm = Dm + n;
+    w += (((size_t)n + 1) * sizeof(double) + 255) / 256 * 256;
+    int2* tiles = reinterpret_cast<int2*>(w);
+
+    const int nt = ceil_div(n, GT);
+    int2 htiles[64 * 64];
+    VB_REQUIRE(nt <= 64, "gram: n=%d too large for the tile list (max %d)", n, 64 * GT);
+    int ntiles = 0;
+    for (int i = 0; i < nt; ++i)
+        for (int j = i; j < nt; ++j) htiles[ntiles++] = make_int2(i, j);
+    VB_CHECK_CUDA(cudaMemcpyAsync(tiles, htiles, ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
+    VB_CHECK_CUDA(cudaMemsetAsync(Gd, 0, (size_t)n * n * sizeof(double), st));
+    int nl = 0;
+    if (deflate) {
+        colmean_kernel<<<(unsigned)ceil_div(p, (size_t)256), 256, 0, st>>>(A, n, p, mean);
+        VB_CHECK_LAUNCH();
+        deflate_terms_kernel<<<n + 1, 256, 0, st>>>(A, n, p, mean, Dm, mm);
+        VB_CHECK_LAUNCH();
+        nl += 2;
+    }
+    const unsigned nchunks = (unsigned)ceil_div(p, (size_t)kchunk);
+    VB_REQUIRE(nchunks <= 65535, "gram: too many K chunks");
+    gram_tile_kernel<<<dim3(ntiles, nchunks), 256, 0, st>>>(A, A, n, n, p, deflate ? mean : nullptr, Gd, n,
+                                                            tiles, kchunk);
+    VB_CHECK_LAUNCH();
+    gram_assemble_kernel<<<dim3(ceil_div(n, 128), n), 128, 0, st>>>(Gd, n, deflate ? Dm : nullptr, mm, G);
+    VB_CHECK_LAUNCH();
+    nl += 2;
+    if (launches) *launches = nl;
+    return 0;
+}
+
+// C (na x nb fp64, row-major, overwritten) = A B^T
+int cross_gram_f32(const float* A, int na, const float* B, int nb, size_t p, double* C, void* ws,
+                   size_t ws_bytes, int kchunk, cudaStream_t st) {
+    const int nta = ceil_div(na, GT), ntb = ceil_div(nb, GT);
+    VB_REQUIRE((size_t)nta * ntb <= 4096, "cross_gram: too many tiles");
+    VB_REQUIRE(ws_bytes >= (size_t)nta * ntb * sizeof(int2), "cross_gram: workspace too small");
+    if (kchunk <= 0) kchunk = 4096;
+    kchunk = ceil_div(kchunk, GK) * GK;
+    int2 htiles[4096];
+    int ntiles = 0;
+    for (int i = 0; i < nta; ++i)
+        for (int j = 0; j < ntb; ++j) htiles[ntiles++] = make_int2(i, j);
+    int2* tiles = reinterpret_cast<int2*>(ws);
+    VB_CHECK_CUDA(cudaMemcpyAsync(tiles, htiles, ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
+    VB_CHECK_CUDA(cudaMemsetAsync(C, 0, (size_t)na * nb * sizeof(double), st));
+    const unsigned nchunks = (unsigned)ceil_div(p, (size_t)kchunk);
+    VB_REQUIRE(nchunks <= 65535, "cross_gram: too many K chunks");
+    gram_tile_kernel<<<dim3(ntiles, nchunks), 256, 0, st>>>(A, B, na, nb, p, nullptr, C, nb, tiles, kchunk);
+    VB_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace vb

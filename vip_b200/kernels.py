@@ -1,0 +1,133 @@
+"""Thin tensor-level wrappers over the C ABI (one function per ``vb_*`` entry point).
+
+Inputs/outputs are CUDA torch tensors; nothing here computes on the host.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._device import empty, ptr, stream_ptr
+
+COLLAPSE_MODES = {"median": 0, "mean": 1, "sum": 2, "max": 3, "absmean": 4, "wmean": 5, "trimmean": 6}
+
+# upper bound for the derotation scratch planes (bytes); override with VIP_B200_DEROT_SCRATCH
+_DEROT_SCRATCH_MAX = int(os.environ.get("VIP_B200_DEROT_SCRATCH", str(8 << 30)))
+
+
+def _bytes(nbytes, device):
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+def gram(M, deflate=True):
+    """G (n,n) fp64 = M M^T for a (n,p) fp32 matrix."""
+    lib = _cabi.lib()
+    n, p = M.shape
+    G = empty((n, n), torch.float64, M.device)
+    nb = lib.vb_gram_workspace_bytes(n, p)
+    ws = _bytes(nb, M.device)
+    _cabi.check(lib.vb_gram_f32(ptr(M), n, p, int(bool(deflate)), ptr(G), ptr(ws), nb, stream_ptr()),
+                "vb_gram_f32")
+    return G
+
+
+def cross_gram(A, B):
+    """C (na,nb) fp64 = A B^T for fp32 matrices sharing the pixel axis."""
+    lib = _cabi.lib()
+    na, p = A.shape
+    nb_, p2 = B.shape
+    if p != p2:
+        raise ValueError("cross_gram: pixel axes differ")
+    Cm = empty((na, nb_), torch.float64, A.device)
+    nbytes = lib.vb_cross_gram_workspace_bytes(na, nb_)
+    ws = _bytes(nbytes, A.device)
+    _cabi.check(lib.vb_cross_gram_f32(ptr(A), na, ptr(B), nb_, p, ptr(Cm), ptr(ws), nbytes, stream_ptr()),
+                "vb_cross_gram_f32")
+    return Cm
+
+
+def eigh(G, max_sweeps=0, tol=0.0):
+    """Eigen-decomposition of a symmetric PSD fp64 matrix.
+
+    Returns (evals[n] descending, evecs[n,n] with row j = eigenvector j, info dict)."""
+    lib = _cabi.lib()
+    n = G.shape[0]
+    evals = empty((n,), torch.float64, G.device)
+    evecs = empty((n, n), torch.float64, G.device)
+    nb = lib.vb_eigh_workspace_bytes(n)
+    ws = _bytes(nb, G.device)
+    info = (C.c_int * 2)()
+    _cabi.check(lib.vb_eigh_f64(ptr(G), n, ptr(evals), ptr(evecs), int(max_sweeps), float(tol), ptr(ws), nb,
+                                info, stream_ptr()), "vb_eigh_f64")
+    if n > 1 and not info[1]:
+        raise RuntimeError(f"vip_b200: Jacobi eigensolver did not converge in {info[0]} sweeps")
+    return evals, evecs, {"sweeps": int(info[0]), "converged": bool(info[1])}
+
+
+def pcs(Wt, M):
+    """V (k,p) = Wt (k,n) . M (n,p), fp32."""
+    lib = _cabi.lib()
+    k, n = Wt.shape
+    n2, p = M.shape
+    assert n == n2
+    V = empty((k, p), torch.float32, M.device)
+    _cabi.check(lib.vb_pcs_f32(ptr(Wt), ptr(M), k, n, p, ptr(V), stream_ptr()), "vb_pcs_f32")
+    return V
+
+
+def project_subtract(M, Cm, V, out=None):
+    """R (n,p) = M - Cm (n,k) . V (k,p), fp32."""
+    lib = _cabi.lib()
+    n, p = M.shape
+    k = V.shape[0]
+    assert Cm.shape == (n, k) and Cm.is_contiguous()
+    R = out if out is not None else empty((n, p), torch.float32, M.device)
+    _cabi.check(lib.vb_project_subtract_f32(ptr(M), ptr(Cm), k, ptr(V), k, n, p, ptr(R), stream_ptr()),
+                "vb_project_subtract_f32")
+    return R
+
+
+def sub(a, b):
+    lib = _cabi.lib()
+    out = torch.empty_like(a)
+    _cabi.check(lib.vb_sub_f32(ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr()), "vb_sub_f32")
+    return out
+
+
+def derotate(cube, krot, a, b, S, N, y0, mask_val=float("nan"), zero_masked=False, force_direct=False,
+             scratch_max=None):
+    """Rotate every frame of a (n,S,S) fp32 CUDA cube (vip-fft semantics); per-frame host scalars
+    krot/a/b come from ``preproc.derotation.rotation_scalars``."""
+    lib = _cabi.lib()
+    n = cube.shape[0]
+    dev = cube.device
+    out = torch.empty_like(cube)
+    d_k = torch.as_tensor(np.asarray(krot, dtype=np.int32)).to(dev)
+    d_a = torch.as_tensor(np.asarray(a, dtype=np.float64)).to(dev)
+    d_b = torch.as_tensor(np.asarray(b, dtype=np.float64)).to(dev)
+    nbytes = lib.vb_derotate_scratch_bytes(n, S, N, scratch_max or _DEROT_SCRATCH_MAX)
+    scratch = _bytes(nbytes, dev)
+    mask_is_nan = int(np.isnan(mask_val))
+    _cabi.check(lib.vb_derotate_f32(ptr(cube), ptr(out), n, S, N, y0, ptr(d_k), ptr(d_a), ptr(d_b),
+                                    float(mask_val), mask_is_nan, int(bool(zero_masked)), ptr(scratch),
+                                    nbytes, int(bool(force_direct)), stream_ptr()), "vb_derotate_f32")
+    return out
+
+
+def collapse(cube2d, mode="median", w=None, trim_k=0, trim_n=0):
+    """(n,p) fp32 -> (p,) fp32 (fp64 for 'wmean')."""
+    lib = _cabi.lib()
+    n, p = cube2d.shape
+    m = COLLAPSE_MODES[mode]
+    dev = cube2d.device
+    d_w = None
+    if mode == "wmean":
+        d_w = torch.as_tensor(np.asarray(w, dtype=np.float64)).to(dev)
+        out = empty((p,), torch.float64, dev)
+    else:
+        out = empty((p,), torch.float32, dev)
+    _cabi.check(lib.vb_collapse_f32(ptr(cube2d), n, p, m, ptr(d_w), int(trim_k), int(trim_n), ptr(out),
+                                    stream_ptr()), "vb_collapse_f32")
+    return out

@@ -1,0 +1,4 @@
+"""PSF-subtraction entry points (mirrors ``vip_hci.psfsub`` for the PCA hot path)."""
+from .pca_fullfr import pca, PCA_Params                     # noqa: F401
+from .pca_local import pca_annular, PCA_ANNULAR_Params      # noqa: F401
+from .svd import svd_wrapper                                # noqa: F401

@@ -1,0 +1,312 @@
+"""Full-frame PCA for ADI / RDI cubes on the B200 (drop-in for ``vip_hci.psfsub.pca``).
+
+Reference: ``src/vip_hci/psfsub/pca_fullfr.py`` -- ``PCA_Params`` :93-134, ``pca`` :137-798,
+``_adi_rdi_pca`` :801-1035, ``_project_subtract`` :1552-1737.
+
+The call signature, positional-argument order, ``algo_params`` / ``rot_options`` handling,
+exceptions and return layouts follow the reference.  The arithmetic runs on the GPU through
+``libvipb200.so`` only; option combinations that are not implemented on the GPU raise
+``NotImplementedError`` (there is no CPU fallback).
+"""
+from dataclasses import dataclass
+from enum import Enum
+from typing import List, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import kernels
+from .._device import require_cuda, to_device_f32, to_host
+from ..config.paramenum import ALGO_KEY, Adimsdi, Collapse, Imlib, Interpolation, SvdMode
+from ..config.utils_conf import check_array
+from ..config.utils_param import separate_kwargs_dict, setup_parameters
+from ..preproc.derotation import _check_rot_options, derotate_device
+from ..preproc.parangles import check_pa_vector
+from ..preproc.subsampling import collapse_device
+from ..var.shapes import circle_mask
+from .svd import Decomposition, _EXACT_MODES, _RAND_MODES, _mode_name, randomized_pcs
+
+
+@dataclass
+class PCA_Params:
+    """Parameters of ``pca`` in the reference's declaration order (``pca_fullfr.py:101-134``)."""
+
+    cube: np.ndarray = None
+    angle_list: np.ndarray = None
+    cube_ref: np.ndarray = None
+    scale_list: np.ndarray = None
+    ncomp: Union[Tuple, List, float, int] = 1
+    svd_mode: Enum = SvdMode.LAPACK
+    scaling: Enum = None
+    mask_center_px: int = None
+    source_xy: Tuple[int] = None
+    delta_rot: int = None
+    fwhm: float = 4
+    adimsdi: Enum = Adimsdi.SINGLE
+    crop_ifs: bool = True
+    imlib: Enum = Imlib.VIPFFT
+    imlib2: Enum = Imlib.VIPFFT
+    interpolation: Enum = Interpolation.LANCZOS4
+    collapse: Enum = Collapse.MEDIAN
+    collapse_ifs: Enum = Collapse.MEAN
+    ifs_collapse_range: Union[str, Tuple[int]] = "all"
+    smooth: float = None
+    smooth_first_pass: float = None
+    mask_rdi: np.ndarray = None
+    ref_strategy: str = "RDI"
+    check_memory: bool = True
+    batch: Union[int, float] = None
+    nproc: int = 1
+    full_output: bool = False
+    verbose: bool = True
+    weights: np.ndarray = None
+    left_eigv: bool = False
+    min_frames_pca: int = 10
+    max_frames_pca: int = None
+    cube_sig: np.ndarray = None
+    med_of_npcs: bool = False
+
+
+def _unsupported(what):
+    raise NotImplementedError(
+        f"vip_b200.pca: {what} is not implemented on the B200 path yet (no CPU fallback)")
+
+
+# --------------------------------------------------------------------------------------------------
+# device building blocks
+# --------------------------------------------------------------------------------------------------
+
+
+def scale_matrix_device(M, scaling):
+    """``matrix_scaling`` (``var/shapes.py:740-781``): sklearn ``scale`` semantics on the device --
+    mean removed along time ('temp-*', axis 0) or space ('spat-*', axis 1); '*-standard' also
+    divides by the population std, a zero std being replaced by 1."""
+    if scaling is None:
+        return M
+    scaling = _mode_name(scaling)
+    if scaling not in ("temp-mean", "spat-mean", "temp-standard", "spat-standard"):
+        raise ValueError("Scaling mode not recognized")
+    axis = 0 if scaling.startswith("temp") else 1
+    M64 = M.double()
+    mean = M64.mean(dim=axis, keepdim=True)
+    out = M64 - mean
+    if scaling.endswith("standard"):
+        std = torch.sqrt((out * out).mean(dim=axis, keepdim=True))
+        # sklearn: scales smaller than 10*eps*|mean| are treated as zero variance -> 1
+        std = torch.where(std < 10 * np.finfo(np.float64).eps * mean.abs().clamp(min=1e-300), torch.ones_like(std), std)
+        std = torch.where(std == 0, torch.ones_like(std), std)
+        out = out / std
+    return out.to(torch.float32).contiguous()
+
+
+def prepare_matrix_device(cube_dev, scaling=None, mask_center_px=None):
+    """``prepare_matrix(mode='fullfr')`` (``var/shapes.py:857-873``): optional central mask, flatten to
+    (n, H*W), optional scaling.  Returns a new tensor when anything is modified."""
+    n, H, W = cube_dev.shape
+    M = cube_dev.reshape(n, H * W)
+    if mask_center_px:
+        mask = torch.as_tensor(circle_mask((H, W), mask_center_px).reshape(-1)).to(M.device)
+        M = M.masked_fill(mask[None, :], 0.0)
+    return scale_matrix_device(M, scaling)
+
+
+def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, svd_mode="lapack",
+                            cube_ref_dev=None, cube_sig_dev=None, full_output=False, verbose=False,
+                            random_state=None):
+    """Whole-matrix branch of ``_project_subtract`` (``pca_fullfr.py:1552-1737``) on the device.
+
+    Returns residuals (n,H,W) or (residuals, reconstructed (n,p), V (k,p))."""
+    n, H, W = cube_dev.shape
+    svd_mode = _mode_name(svd_mode)
+    if not isinstance(ncomp, (int, np.integer, float, np.floating)):
+        raise TypeError("Type not recognized for ncomp, should be int or float")
+
+    matrix = prepare_matrix_device(cube_dev, scaling, mask_center_px)
+    if cube_sig_dev is None:
+        matrix_emp = matrix
+    else:
+        matrix_emp = matrix - cube_sig_dev.reshape(cube_sig_dev.shape[0], -1)
+    ref_lib = (prepare_matrix_device(cube_ref_dev, scaling, mask_center_px)
+               if cube_ref_dev is not None else matrix_emp)
+
+    dec = None
+    if isinstance(ncomp, (float, np.floating)):
+        # ncomp given as a cumulative explained variance ratio (pca_fullfr.py:1624-1637); the
+        # reference decomposes the *cube* itself for this (SVDecomposer(cube, ...))
+        if not 1 > ncomp > 0:
+            raise ValueError("if `ncomp` is float, it must lie in the interval (0,1]")
+        dec_cube = Decomposition(prepare_matrix_device(cube_dev, scaling, None))
+        ncomp = int(np.searchsorted(dec_cube.cevr(), ncomp) + 1)
+        if verbose:
+            print("Components used : {}".format(ncomp))
+        if ref_lib is matrix and not mask_center_px:
+            dec = dec_cube
+    ncomp = int(ncomp)
+
+    nr, p = ref_lib.shape
+    if ncomp > min(nr, p):
+        msg = "{} PCs cannot be obtained from a matrix with size [{},{}]."
+        msg += " Increase the size of the patches or request less PCs"
+        raise RuntimeError(msg.format(ncomp, nr, p))
+
+    if svd_mode in _EXACT_MODES:
+        if dec is None:
+            dec = Decomposition(ref_lib)
+        V = dec.pcs(ncomp)
+        if ref_lib is matrix_emp:
+            Cm = dec.coeffs(ncomp)                # = matrix_emp . V^T from the eigenpairs
+        else:
+            Cm = kernels.cross_gram(matrix_emp, V).to(torch.float32).contiguous()
+    elif svd_mode in _RAND_MODES:
+        rs = random_state
+        if rs is None:
+            rs = np.random.mtrand._rand
+        elif not isinstance(rs, np.random.RandomState):
+            rs = np.random.RandomState(rs)
+        omega = rs.normal(size=(nr, ncomp + 10))
+        V = randomized_pcs(ref_lib, ncomp, omega)
+        Cm = kernels.cross_gram(matrix_emp, V).to(torch.float32).contiguous()
+    else:
+        raise ValueError("The SVD `mode` is not recognized")
+    if verbose:
+        print("Done SVD/PCA on the GPU (vip_b200, svd_mode={})".format(svd_mode))
+
+    residuals = kernels.project_subtract(matrix, Cm, V)
+    residuals_cube = residuals.reshape(n, H, W)
+    if full_output:
+        return residuals_cube, kernels.sub(matrix, residuals), V
+    return residuals_cube
+
+
+def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_px, svd_mode, collapse,
+                        verbose, full_output, weights=None, cube_sig=None, random_state=None,
+                        keep_on_device=False, **rot_options):
+    """``_adi_rdi_pca`` (``pca_fullfr.py:801-1035``) for scalar ``ncomp`` without ``source_xy`` /
+    ``batch`` / ``mask_rdi``: PCA residuals -> derotation -> collapse."""
+    n, y, x = cube.shape
+    angle_list = check_pa_vector(np.asarray(angle_list))
+    if n != angle_list.shape[0]:
+        raise ValueError("`angle_list` vector has wrong length. It must equal the number of frames in the cube")
+    if not np.isscalar(ncomp):
+        raise TypeError("`ncomp` must be an int, float, tuple or list in the ADI case")
+    nref = cube_ref.shape[0] if cube_ref is not None else n
+    if isinstance(ncomp, (int, np.integer)) and ncomp > nref:
+        ncomp = min(ncomp, nref)
+        print("Number of PCs too high (max PCs={}), using {} PCs instead.".format(nref, ncomp))
+    elif ncomp <= 0:
+        raise ValueError("Number of PCs too low. It should be > 0.")
+
+    mask_val = float(rot_options.get("mask_val", np.nan))
+    interp_zeros = bool(rot_options.get("interp_zeros", False))
+    _check_rot_options(rot_options.get("imlib", "vip-fft"), rot_options.get("cxy"),
+                       rot_options.get("border_mode", "constant"), rot_options.get("edge_blend"), cube.shape)
+
+    dev = require_cuda()
+    as_dev = (lambda a: a.to(dev).float()) if isinstance(cube, torch.Tensor) else (lambda a: to_device_f32(a, dev))
+    cube_dev = as_dev(cube)
+    ref_dev = as_dev(cube_ref) if cube_ref is not None else None
+    sig_dev = as_dev(cube_sig) if cube_sig is not None else None
+
+    res = project_subtract_device(cube_dev, ncomp, scaling, mask_center_px, svd_mode, ref_dev, sig_dev,
+                                  full_output=full_output, verbose=verbose, random_state=random_state)
+    if full_output:
+        residuals_cube, recon, V = res
+    else:
+        residuals_cube = res
+    residuals_cube_ = derotate_device(residuals_cube, -angle_list, mask_val=mask_val, interp_zeros=interp_zeros)
+    frame = collapse_device(residuals_cube_, mode=collapse, w=weights)
+    if mask_center_px:
+        mask = torch.as_tensor(circle_mask((y, x), mask_center_px)).to(dev)
+        residuals_cube_ = residuals_cube_.masked_fill(mask[None], 0.0)
+        frame = frame.masked_fill(mask, 0.0)
+    if verbose:
+        print("Done de-rotating and combining")
+    if full_output:
+        out = (V.reshape(V.shape[0], y, x), recon.reshape(n, y, x), residuals_cube, residuals_cube_, frame)
+    else:
+        out = frame
+    return out
+
+
+def _to_numpy_like(t, ref_dtype):
+    """Device result -> numpy with the dtype the reference would return for a cube of ``ref_dtype``."""
+    a = to_host(t)
+    if a.dtype == np.float32 and ref_dtype != np.float32 and np.issubdtype(ref_dtype, np.floating):
+        a = a.astype(ref_dtype)
+    return a
+
+
+def pca(*all_args: List, **all_kwargs: dict):
+    """Full-frame PCA speckle subtraction: drop-in for ``vip_hci.psfsub.pca``.
+
+    Positional arguments map to :class:`PCA_Params` fields in declaration order; keyword arguments
+    that are not fields are the ``rot_options`` forwarded to the derotation; ``algo_params=<obj>``
+    (any object carrying the fields) bypasses the parsing (``pca_fullfr.py:398-409``).
+
+    Implemented on the GPU: 3-d ADI / ADI+RDI (``ref_strategy`` 'RDI' or 'ARDI') cubes with scalar
+    ``ncomp`` (int, or float = CEVR), every ``svd_mode`` of the reference (the deterministic ones share
+    one exact path), ``scaling``, ``mask_center_px``, ``cube_sig``, ``collapse`` modes, ``weights``,
+    ``full_output``.  Returns exactly what the reference returns for these cases
+    (``pca_fullfr.py:717-798``): ``frame`` or ``(frame, pcs, recon, residuals_cube, residuals_cube_)``.
+    """
+    class_params, rot_options = separate_kwargs_dict(initial_kwargs=all_kwargs, parent_class=PCA_Params)
+    algo_params = rot_options.pop(ALGO_KEY, None)
+    if algo_params is None:
+        algo_params = PCA_Params(*all_args, **class_params)
+    p = algo_params
+
+    if p.mask_center_px and len(rot_options) == 0:
+        rot_options["mask_val"] = 0
+        rot_options["ker"] = 1
+        rot_options["interp_zeros"] = True
+
+    if p.batch is None:
+        check_array(p.cube, (3, 4), msg="cube")
+    elif not isinstance(p.cube, (str, np.ndarray)):
+        raise TypeError("`cube` must be a numpy (3d or 4d) array or a str with the full path on disk")
+
+    if p.left_eigv and (p.batch is not None or p.mask_rdi is not None or p.cube_ref is not None):
+        raise NotImplementedError("left_eigv is not compatible with 'mask_rdi' nor 'batch'")
+
+    if p.mask_rdi is not None and p.ref_strategy in ("ARDI", "ARSDI"):
+        msg = "mask for data imputation detected. This mode can only run with "
+        msg += "a pure RDI strategy, while ref_strategy was set to {}"
+        raise TypeError(msg.format(p.ref_strategy))
+
+    if p.batch is not None:
+        _unsupported("incremental PCA (`batch`)")
+    if p.cube.ndim == 4 or p.scale_list is not None:
+        _unsupported("4-d (IFS / ADI+mSDI) input")
+    if p.left_eigv:
+        _unsupported("`left_eigv`")
+    if p.mask_rdi is not None:
+        _unsupported("`mask_rdi` (data imputation)")
+    if p.source_xy is not None:
+        _unsupported("`source_xy` (PA-threshold library / S/N optimisation)")
+    if isinstance(p.ncomp, (tuple, list)):
+        _unsupported("a tuple/list `ncomp` (pca_grid)")
+    if p.smooth is not None:
+        _unsupported("`smooth`")
+    imlib = _mode_name(p.imlib)
+    if imlib != "vip-fft":
+        _unsupported(f"imlib={imlib!r}")
+
+    # 3-D ADI or ADI+RDI (pca_fullfr.py:661-681)
+    cube_ref = p.cube_ref
+    if cube_ref is not None:
+        if p.ref_strategy == "ARDI":
+            cube_ref = np.concatenate((p.cube, cube_ref))
+            algo_params.cube_ref = cube_ref        # the reference overwrites the attribute too (:670-672)
+        elif p.ref_strategy != "RDI":
+            raise TypeError("ref_strategy argument not recognized.Should be 'RDI' or 'ARDI'")
+
+    func_params = setup_parameters(params_obj=algo_params, fkt=_adi_rdi_pca_device)
+    func_params["cube_ref"] = cube_ref
+    res = _adi_rdi_pca_device(**func_params, **rot_options)
+
+    dt = p.cube.dtype
+    if p.full_output:
+        pcs, recon, residuals_cube, residuals_cube_, frame = res
+        return (_to_numpy_like(frame, dt), _to_numpy_like(pcs, dt), _to_numpy_like(recon, dt),
+                _to_numpy_like(residuals_cube, dt), _to_numpy_like(residuals_cube_, dt))
+    return _to_numpy_like(res, dt)

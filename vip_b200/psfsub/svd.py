@@ -1,0 +1,135 @@
+"""Truncated SVD of the frames x pixels matrix on the GPU (``vip_hci/psfsub/svd.py:342-620``).
+
+All deterministic reference back-ends ('lapack', 'eigen', 'arpack' and their cupy/pytorch
+variants) return the same top-``ncomp`` right singular vectors up to sign; they are served by one
+path: fp64 Gramian of the (mean-deflated) matrix -> fp64 Jacobi eigensolver -> PCs by a skinny
+GEMM.  'randsvd' follows scikit-learn's ``randomized_svd`` (see ``randomized_pcs``).
+"""
+import numpy as np
+import torch
+
+from .. import kernels
+
+_EXACT_MODES = ("lapack", "eigen", "arpack", "cupy", "eigencupy", "pytorch", "eigenpytorch")
+_RAND_MODES = ("randsvd", "randcupy", "randpytorch")
+
+
+def _mode_name(mode):
+    return str(getattr(mode, "value", mode))
+
+
+class Decomposition:
+    """Eigen-decomposition of M M^T for a device matrix M (n,p): singular values and left vectors."""
+
+    def __init__(self, M):
+        self.M = M
+        G = kernels.gram(M, deflate=True)
+        evals, evecs, self.info = kernels.eigh(G)
+        self.evals = evals                     # (n,) descending, fp64
+        self.U = evecs                         # (n,n) fp64, row j = j-th left singular vector of M
+        self.S = torch.sqrt(torch.clamp(evals, min=0.0))
+
+    def check_rank(self, ncomp):
+        n, p = self.M.shape
+        if ncomp > min(n, p):
+            msg = "{} PCs cannot be obtained from a matrix with size [{},{}]."
+            msg += " Increase the size of the patches or request less PCs"
+            raise RuntimeError(msg.format(ncomp, n, p))
+
+    def pcs(self, ncomp):
+        """V (ncomp,p) fp32: right singular vectors = diag(1/s) U_k M."""
+        self.check_rank(ncomp)
+        s = self.S[:ncomp]
+        Wt = (self.U[:ncomp] / s[:, None]).to(torch.float32).contiguous()
+        return kernels.pcs(Wt, self.M)
+
+    def coeffs(self, ncomp):
+        """C (n,ncomp) fp32 = M V^T = U_k^T diag(s): projection of M's own rows on its PCs."""
+        return (self.U[:ncomp] * self.S[:ncomp, None]).t().to(torch.float32).contiguous()
+
+    def cevr(self):
+        """Cumulative explained variance ratio (``svd.py:256-261``)."""
+        s = self.S.cpu().numpy()
+        exp_var = s ** 2 / (s.shape[0] - 1)
+        return np.cumsum(exp_var / np.sum(exp_var))
+
+
+def orthonormalize(Yt):
+    """Rows of Yt (l,p) -> orthonormal rows spanning the same space (two Gram/eigh passes)."""
+    for _ in range(2):
+        G = kernels.cross_gram(Yt, Yt)
+        evals, evecs, _ = kernels.eigh(G)
+        keep = evals > evals[0] * 1e-30
+        Wt = (evecs / torch.sqrt(torch.clamp(evals, min=1e-300))[:, None])[keep]
+        Yt = kernels.pcs(Wt.to(torch.float32).contiguous(), Yt)
+    return Yt
+
+
+def randomized_pcs(M, ncomp, omega, n_iter=2):
+    """scikit-learn ``randomized_svd(M, ncomp, n_iter=2, transpose='auto')`` for n < p
+    (``svd.py:487-491``): with the Gaussian test matrix ``omega`` (n, ncomp+10) supplied
+    by the caller,  Y = M^T (M M^T)^n_iter omega,  Q = orth(Y),  B = Q^T M^T,  PCs = (Q U_B)[:, :k]^T.
+    Any orthonormal basis of range(Y) gives the same PCs, so orth() is Gram-based here."""
+    n, p = M.shape
+    Om = torch.as_tensor(np.asarray(omega, dtype=np.float32)).to(M.device)
+    Yt = kernels.pcs(Om.t().contiguous(), M)                    # (l,p) = omega^T M
+    for _ in range(n_iter):
+        Z = kernels.cross_gram(Yt, M)                            # (l,n) = Y^T M^T
+        Yt = kernels.pcs(Z.to(torch.float32).contiguous(), M)    # (l,p)
+    Qt = orthonormalize(Yt)
+    B = kernels.cross_gram(Qt, M)                                # (l,n) fp64
+    evals, evecs, _ = kernels.eigh((B @ B.t()).contiguous())
+    Wt = evecs[:ncomp].to(torch.float32).contiguous()            # rows = leading left vectors of B
+    return kernels.pcs(Wt, Qt)
+
+
+def svd_wrapper(matrix, mode, ncomp, verbose=False, full_output=False, random_state=None, to_numpy=True,
+                left_eigv=False):
+    """Top-``ncomp`` right singular vectors (ncomp, npix) of a 2-d matrix, computed on the GPU.
+
+    Same call signature as the reference.  ``full_output`` returns, for 'lapack', (left vectors
+    (n,ncomp), S, PCs (ncomp,p)) as the reference does; for the other exact modes (U (ncomp,n), S, V)."""
+    from .._device import to_device_f32, to_host
+    if matrix.ndim != 2:
+        raise TypeError("Input matrix is not a 2d array")
+    mode = _mode_name(mode)
+    is_tensor = isinstance(matrix, torch.Tensor)
+    M = matrix.float().contiguous() if is_tensor else to_device_f32(matrix)
+    n, p = M.shape
+    if ncomp > min(n, p):
+        msg = "{} PCs cannot be obtained from a matrix with size [{},{}]."
+        msg += " Increase the size of the patches or request less PCs"
+        raise RuntimeError(msg.format(ncomp, n, p))
+    if mode in _EXACT_MODES:
+        if n > p:
+            raise NotImplementedError("vip_b200 svd_wrapper expects n_frames <= n_pixels")
+        dec = Decomposition(M)
+        V = dec.pcs(ncomp)
+        U = dec.U[:ncomp].to(torch.float32)
+        S = dec.S[:ncomp].to(torch.float32)
+    elif mode in _RAND_MODES:
+        if full_output or left_eigv:
+            raise NotImplementedError("randsvd with full_output/left_eigv is not implemented")
+        rs = random_state
+        if rs is None:
+            rs = np.random.mtrand._rand          # numpy's global RandomState, like check_random_state(None)
+        elif not isinstance(rs, np.random.RandomState):
+            rs = np.random.RandomState(rs)
+        omega = rs.normal(size=(n, ncomp + 10))
+        V = randomized_pcs(M, ncomp, omega)
+        U = S = None
+    else:
+        raise ValueError("The SVD `mode` is not recognized")
+    if verbose:
+        print("Done SVD/PCA on the GPU (vip_b200, svd_mode={})".format(mode))
+    conv = (lambda t: t) if (is_tensor or not to_numpy) else (lambda t: to_host(t))
+    if full_output:
+        # reference, 'lapack' (svd.py:597-599): (left vectors (n,k), S, PCs (k,p))
+        if mode == "lapack":
+            return conv(U.t().contiguous()), conv(S), conv(V)
+        return conv(U), conv(S), conv(V)
+    if left_eigv:
+        if mode != "lapack":
+            raise NotImplementedError("left_eigv is only implemented for svd_mode='lapack'")
+        return conv(U.t().contiguous())
+    return conv(V)
