@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""ADI-PCA frames/s (cube -> final residual frame) on B200 -- BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c1|small]
+
+A "step" is one full pass of the hot path over one synthetic cube:
+    PCA residuals (Gramian -> eigensolve -> PCs -> projection/subtraction) -> FFT derotation ->
+    median collapse -> final frame.
+N=1 workload: BASELINE configs[1]  (500x512x512 fp32 ADI cube, full-frame PCA, ncomp=20).
+
+JSON line keys (see the task contract): value = device-resident throughput (cube already in HBM),
+e2e = the same metric through the public call ``vip_b200.pca(numpy_cube, ...)`` with the host->device
+copy of the cube (pinned) and the device->host read of the frame inside the timed region;
+roofline = derotation stage against the measured HBM peak (it is FFT-arithmetic bound);
+cpu_baseline = the numpy oracle (port of the reference algorithm) on a bounded sample.
+
+``--impl reference`` times the CPU oracle port only (bounded sample per step), no GPU needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (n_frames, size, ncomp, delta_deg, seed)
+    "c2": (500, 512, 20, 90.0, 20260102),
+    "c1": (50, 101, 5, 60.0, 20260101),
+    "small": (100, 128, 10, 60.0, 20260109),
+}
+METRIC = "ADI-PCA frames/sec (cube->final residual)"
+UNIT = "frames/s"
+
+
+def workload_name(cfg):
+    n, s, k, _, _ = CONFIGS[cfg]
+    return f"{n}x{s}x{s} fp32 ADI cube, full-frame PCA ncomp={k}, svd_mode=lapack, vip-fft derotation, median collapse"
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.thread = None
+
+    def _run(self):
+        try:
+            proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                     "--format=csv,noheader,nounits", "-lms", "100"],
+                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        while not self.stop.is_set():
+            line = proc.stdout.readline()
+            if not line:
+                break
+            self.samples.append(line.strip())
+        proc.terminate()
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline (oracle port), bounded sample extrapolated to the full workload
+# --------------------------------------------------------------------------------------------
+def cpu_sample(cube, angs, ncomp, n_rot=2, strip=8):
+    """One bounded sample of the reference algorithm on the host: PCA projection/subtraction and the
+    median on a 1/strip pixel strip of ALL frames (both scale linearly with pixels), derotation of
+    n_rot full frames (per-frame independent).  Returns extrapolated seconds for the whole cube."""
+    from oracle import vip_oracle as O
+    n, H, W = cube.shape
+    rows = max(1, H // strip)
+    sub = np.ascontiguousarray(cube[:, :rows, :])
+    t0 = time.perf_counter()
+    res = O.project_subtract(sub, ncomp)
+    t_ps = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.cube_collapse(res, "median")
+    t_col = time.perf_counter() - t0
+    fr = np.ascontiguousarray(cube[:n_rot] - cube[:n_rot].mean(0))
+    t0 = time.perf_counter()
+    O.cube_derotate(fr, angs[:n_rot])
+    t_rot = time.perf_counter() - t0
+    total = (t_ps + t_col) * (H / rows) + t_rot * (n / n_rot)
+    return total, {"project_subtract_s": t_ps * H / rows, "collapse_s": t_col * H / rows,
+                   "derotate_s": t_rot * n / n_rot}
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure Python and
+    /root/reference does not travel to the GPU box) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tools.synth import adi_cube
+    n, size, k, delta, seed = CONFIGS[args.config]
+    cube, angs = adi_cube(n, size, k, delta, seed=seed)
+    import warnings
+    warnings.simplefilter("ignore")
+    for _ in range(args.warmup):
+        cpu_sample(cube, angs, k)
+    times = []
+    for _ in range(args.steps):
+        t, parts = cpu_sample(cube, angs, k)
+        times.append(t)
+    sec = float(np.mean(times))
+    value = n / sec
+    sample = (f"per step: PCA project/subtract + nanmedian on a 1/8 pixel strip of all {n} frames (x8), "
+              f"vip-fft derotation of 2 full frames (x{n // 2}); numpy/LAPACK/pocketfft oracle port")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (fp64 FFT/SVD inside numpy)", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": workload_name(args.config), "extrapolated_from_sample": True},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                             "sample": sample, "stage_seconds_full_cube": parts},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def stage_times(cube_dev, angs, ncomp, reps=3):
+    """CUDA-event time of every stage of the pipeline (ms, best of reps) and of the three shear
+    kernels (vb_profile hooks)."""
+    import ctypes as C
+    import torch
+    from vip_b200 import kernels, _cabi
+    from vip_b200.preproc.derotation import derotate_device
+    from vip_b200.preproc.subsampling import collapse_device
+    lib = _cabi.lib()
+    n, H, W = cube_dev.shape
+    M = cube_dev.reshape(n, H * W)
+    out = {}
+
+    def timed(name, fn):
+        best = None
+        res = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            res = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        out[name] = best
+        return res
+
+    G = timed("gram_ms", lambda: kernels.gram(M))
+    evals, evecs, info = timed("eigh_ms", lambda: kernels.eigh(G))
+    S = torch.sqrt(evals[:ncomp])
+    Wt = (evecs[:ncomp] / S[:, None]).float().contiguous()
+    Cm = (evecs[:ncomp] * S[:, None]).t().float().contiguous()
+    V = timed("pcs_ms", lambda: kernels.pcs(Wt, M))
+    R = timed("project_subtract_ms", lambda: kernels.project_subtract(M, Cm, V))
+    Rc = R.reshape(n, H, W)
+    lib.vb_profile_enable(1)
+    D = timed("derotate_ms", lambda: derotate_device(Rc, -angs))
+    prof = (C.c_float * 4)()
+    lib.vb_profile_read(prof)
+    lib.vb_profile_enable(0)
+    nrep = max(1, reps)
+    out["shear_rows_first_ms"] = prof[0] / nrep
+    out["shear_cols_ms"] = prof[1] / nrep
+    out["shear_rows_last_ms"] = prof[2] / nrep
+    out["derotate_chunks"] = int(prof[3] / nrep)
+    timed("collapse_median_ms", lambda: collapse_device(D, "median"))
+    out["eigh_sweeps"] = info["sweeps"]
+    return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from tools.synth import adi_cube
+    import vip_b200
+    from vip_b200 import _cabi
+    from vip_b200.psfsub.pca_fullfr import _adi_rdi_pca_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n, size, k, delta, seed = CONFIGS[args.config]
+    # replicas: every rank processes its own cube of the same shape (different seed) -- see DESIGN.md (e)
+    cube, angs = adi_cube(n, size, k, delta, seed=seed + rank)
+    pinned = torch.from_numpy(cube).pin_memory()
+    cube_pinned_np = pinned.numpy()
+    cube_dev = pinned.cuda()
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
+    def step_dev():
+        return _adi_rdi_pca_device(cube_dev, None, angs, k, None, None, "lapack", "median", False, False)
+
+    def step_e2e():
+        return vip_b200.pca(cube_pinned_np, angs, ncomp=k, verbose=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    n0 = _cabi.launch_count()
+    with ClockSampler(local) as clk:
+        ms_dev = timed(step_dev, args.steps)
+        launches = (_cabi.launch_count() - n0) // args.steps
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+    clocks = clk.summary()
+
+    frames_total = n * world
+    value = frames_total * args.steps / (ms_dev * 1e-3)
+    e2e_value = frames_total * args.steps / (ms_e2e * 1e-3)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (Gramian/eigensolve in f64)",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.config),
+                       "l2_policy": f"inputs larger than L2 ({cube.nbytes / 1e6:.0f} MB cube vs 126 MB L2)",
+                       "multi_gpu": "one independent cube per rank (replicas, no data-path collective)"
+                       if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(cube.nbytes * world),
+                    "d2h_bytes_per_step": int(size * size * 4 * world), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
+            "clocks": clocks}
+
+    if rank == 0:
+        st = stage_times(cube_dev, angs, k)
+        p = size * size
+        derot_ms = st["derotate_ms"]
+        N = {512: 2048, 1024: 4096, 256: 1024, 128: 512}.get(size)
+        fft_flop = None
+        if N:
+            lg = int(np.log2(N))
+            fft_flop = n * (2 * size + 1 + N) * 2 * 5 * N * lg   # (rows p1 + cols p2 + rows p3) x (fwd+inv)
+        alg_bytes = 8.0 * p * n       # read residual cube + write derotated cube
+        achieved = alg_bytes / (derot_ms * 1e-3) / 1e9
+        line["roofline"] = {
+            "kernel": "vb_derotate_f32 = shear_rows_first + shear_cols + shear_rows_last (one launch each per chunk)",
+            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": None, "peak_source": peak_kind,
+            "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": derot_ms,
+            "note": "stage is fp32-FFT-arithmetic bound, not HBM bound (DESIGN.md): ~220 flop per algorithmic byte",
+            "fft_gflop": None if fft_flop is None else fft_flop / 1e9,
+            "fft_tflops_achieved": None if fft_flop is None else fft_flop / (derot_ms * 1e-3) / 1e12,
+            "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,
+        }
+        col_ms = st["collapse_median_ms"]
+        line["roofline_collapse"] = {"kernel": "collapse_median_kernel", "bound": "hbm",
+                                     "achieved": 4.0 * p * n / (col_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                     "unit": "GB/s", "frac": 4.0 * p * n / (col_ms * 1e-3) / 1e9 / hbm_peak}
+        ps_ms = st["project_subtract_ms"]
+        line["roofline_project_subtract"] = {"kernel": "subtract_kernel", "bound": "hbm",
+                                             "achieved": 8.0 * p * n / (ps_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                             "unit": "GB/s", "frac": 8.0 * p * n / (ps_ms * 1e-3) / 1e9 / hbm_peak}
+        line["stage_ms"] = st
+        if world == 1 and not args.no_cpu:
+            import warnings
+            warnings.simplefilter("ignore")
+            sec, parts = cpu_sample(cube, angs, k)
+            line["cpu_baseline"] = {
+                "value": n / sec, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                "sample": (f"PCA project/subtract + nanmedian on a 1/8 pixel strip of all {n} frames (x8), vip-fft "
+                           f"derotation of 2 full frames (x{n // 2}); numpy oracle port of the reference algorithm"),
+                "stage_seconds_full_cube": parts}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vip_b200", choices=["vip_b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

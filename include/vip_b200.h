@@ -84,6 +84,13 @@ int vb_derotate_f32(const float* in, float* out, int nframes, int S, int N, int 
 int vb_collapse_f32(const float* cube, int n, size_t p, int mode, const double* w, int trim_k, int trim_n,
                     void* out, void* stream);
 
+/* ---- measurement hook (bench.py) ----------------------------------------------------------
+ * vb_profile_enable(1): CUDA events are recorded around each of the three shear kernels of
+ * vb_derotate_f32 on its stream; vb_profile_read(out4_host) synchronises on them and returns the
+ * summed elapsed ms of pass 1 / 2 / 3 and the number of chunk launches timed. */
+void vb_profile_enable(int on);
+int vb_profile_read(float* out4_host);
+
 #ifdef __cplusplus
 }
 #endif

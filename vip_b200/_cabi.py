@@ -31,6 +31,8 @@ SIGNATURES = {
     "vb_derotate_scratch_bytes": (_sz, [_i, _i, _i, _sz]),
     "vb_derotate_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _sz, _i, _vp]),
     "vb_collapse_f32": (_i, [_vp, _i, _sz, _i, _vp, _i, _i, _vp, _vp]),
+    "vb_profile_enable": (None, [_i]),
+    "vb_profile_read": (_i, [C.POINTER(_f)]),
 }
 
 

@@ -34,6 +34,8 @@ size_t derotate_scratch_bytes_per_frame(int S, int N);
 int derotate_run(const float*, float*, int, const RotParams&, const int*, const double*, const double*,
                  const float2*, void*, size_t, int, int*, cudaStream_t);
 int collapse_f32(const float*, int, size_t, int, const double*, int, int, void*, cudaStream_t);
+void profile_enable(int on);
+int profile_read(float* out);
 
 // exp(-2 pi i j / N) tables for the FFT path, one per (device, N), built in fp64 on the host
 static const float2* twiddle_table(int N) {
@@ -154,5 +156,8 @@ int vb_collapse_f32(const float* cube, int n, size_t p, int mode, const double* 
     g_launches += 1;
     return collapse_f32(cube, n, p, mode, w, trim_k, trim_n, out, (cudaStream_t)stream);
 }
+
+void vb_profile_enable(int on) { profile_enable(on); }
+int vb_profile_read(float* out4_host) { return profile_read(out4_host); }
 
 }  // extern "C"

@@ -23,6 +23,7 @@
 //     with the closed-form Dirichlet kernel  D(t) = e^{-i pi t/N} sin(pi t) / (N sin(pi t/N)),
 //     evaluated directly on the non-zero support.
 #include "common.cuh"
+#include <vector>
 
 namespace vb {
 
@@ -572,6 +573,42 @@ shear_direct(const float* __restrict__ in, float* __restrict__ out, float2* __re
 // host side
 // =====================================================================================
 
+// Optional per-kernel timing (bench.py): when enabled, CUDA events bracket each of the three
+// shear kernels on the launching stream; vb_profile_read() sums the elapsed times.
+struct PassTimer {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;   // 4 events per chunk: before p1, after p1, after p2, after p3
+    void mark(cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+    }
+};
+static PassTimer g_timer;
+
+void profile_enable(int on) {
+    for (auto e : g_timer.ev) cudaEventDestroy(e);
+    g_timer.ev.clear();
+    g_timer.on = on != 0;
+}
+
+// out[0..2] = total ms of pass 1/2/3, out[3] = number of chunk launches timed
+int profile_read(float* out) {
+    out[0] = out[1] = out[2] = out[3] = 0.f;
+    for (size_t i = 0; i + 3 < g_timer.ev.size(); i += 4) {
+        if (cudaEventSynchronize(g_timer.ev[i + 3]) != cudaSuccess) return -1;
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, g_timer.ev[i + k], g_timer.ev[i + k + 1]);
+            out[k] += ms;
+        }
+        out[3] += 1.f;
+    }
+    return 0;
+}
+
 template <int N, int NT>
 static int launch_fft_chunk(const float* in, float* out, float2* T1, float2* T2, const RotParams& g,
                             const int* krot, const double* a, const double* b, const float2* tw,
@@ -589,14 +626,18 @@ static int launch_fft_chunk(const float* in, float* out, float2* T1, float2* T2,
         configured = true;
     }
     const int threads = NT * F::T;
+    g_timer.mark(st);
     shear_rows_first_fft<N, NT><<<dim3(ceil_div(g.S + 1, NT), nf), threads, smem, st>>>(
         in, T1, g, krot, a, tw, frame0);
     VB_CHECK_LAUNCH();
+    g_timer.mark(st);
     shear_cols_fft<N, NT><<<dim3(N / NT, nf), threads, smem, st>>>(T1, T2, g, b, tw, frame0);
     VB_CHECK_LAUNCH();
+    g_timer.mark(st);
     shear_rows_last_fft<N, NT><<<dim3(ceil_div(g.S, NT), nf), threads, smem, st>>>(
         T2, in, out, g, a, tw, frame0);
     VB_CHECK_LAUNCH();
+    g_timer.mark(st);
     return 0;
 }
 
@@ -612,12 +653,16 @@ static int launch_direct_chunk(const float* in, float* out, float2* T1, float2* 
         VB_CHECK_CUDA(cudaFuncSetAttribute(shear_direct<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
+    g_timer.mark(st);
     shear_direct<0><<<dim3(g.S + 1, nf), 128, smem, st>>>(in, out, T1, T2, g, krot, a, b, frame0);
     VB_CHECK_LAUNCH();
+    g_timer.mark(st);
     shear_direct<1><<<dim3(g.N, nf), 128, smem, st>>>(in, out, T1, T2, g, krot, a, b, frame0);
     VB_CHECK_LAUNCH();
+    g_timer.mark(st);
     shear_direct<2><<<dim3(g.S, nf), 128, smem, st>>>(in, out, T1, T2, g, krot, a, b, frame0);
     VB_CHECK_LAUNCH();
+    g_timer.mark(st);
     return 0;
 }
 

@@ -21,7 +21,7 @@ def _bytes(nbytes, device):
     return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
 
 
-def gram(M, deflate=True):
+def gram(M, deflate=False):
     """G (n,n) fp64 = M M^T for a (n,p) fp32 matrix."""
     lib = _cabi.lib()
     n, p = M.shape

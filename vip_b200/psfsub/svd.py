@@ -2,7 +2,7 @@
 
 All deterministic reference back-ends ('lapack', 'eigen', 'arpack' and their cupy/pytorch
 variants) return the same top-``ncomp`` right singular vectors up to sign; they are served by one
-path: fp64 Gramian of the (mean-deflated) matrix -> fp64 Jacobi eigensolver -> PCs by a skinny
+path: fp64 Gramian of the matrix -> fp64 Jacobi eigensolver -> PCs by a skinny
 GEMM.  'randsvd' follows scikit-learn's ``randomized_svd`` (see ``randomized_pcs``).
 """
 import numpy as np
@@ -23,7 +23,7 @@ class Decomposition:
 
     def __init__(self, M):
         self.M = M
-        G = kernels.gram(M, deflate=True)
+        G = kernels.gram(M)
         evals, evecs, self.info = kernels.eigh(G)
         self.evals = evals                     # (n,) descending, fp64
         self.U = evecs                         # (n,n) fp64, row j = j-th left singular vector of M
