@@ -53,6 +53,15 @@ size_t vb_eigh_workspace_bytes(int n);
 int vb_eigh_f64(const double* G, int n, double* evals, double* evecs, int max_sweeps, double tol,
                 void* ws, size_t ws_bytes, int* info_host, void* stream);
 
+/* Leading k (<= 24, block width <= n) eigenpairs only, by fp64 block subspace iteration with Rayleigh-Ritz
+ * (O(n^2 B) per step instead of a full decomposition).  evals[k] descending, evecs[k x n] row j =
+ * eigenvector j.  Iterates until max_j ||G x_j - theta_j x_j|| <= tol * theta_k.  info_host
+ * (optional, 2 ints): iterations, converged flag.  Synchronises `stream`.
+ * Replaces: the truncated use of the SVD, V[:ncomp]               psfsub/svd.py:471-473 */
+size_t vb_eigh_topk_workspace_bytes(int n, int k);
+int vb_eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, double* evals, double* evecs,
+                     void* ws, size_t ws_bytes, int* info_host, void* stream);
+
 /* ---- principal components and projection/subtraction --------------------------------------
  * V[k x p] = Wt[k x n] . M[n x p]                                  psfsub/svd.py:451-459
  * R[n x p] = M - C[n x k] . V[k x p]   (R may alias M)            psfsub/pca_fullfr.py:1728-1731 */
@@ -83,6 +92,22 @@ int vb_derotate_f32(const float* in, float* out, int nframes, int S, int N, int 
  * Replaces: cube_collapse                                          preproc/subsampling.py:30-116 */
 int vb_collapse_f32(const float* cube, int n, size_t p, int mode, const double* w, int trim_k, int trim_n,
                     void* out, void* stream);
+
+/* ---- annular PCA: batched per-frame library eigenproblems -----------------------------------
+ * For each problem q (target frame[q], library rows idx[q][0..len[q]) of the segment matrix):
+ * top-`ncomp` eigenpairs (theta_j, x_j) of G[idx,idx] by fp64 block subspace iteration, then the
+ * projection weights  w = sum_j x_j (x_j . Gt[frame, idx]) / theta_j  written to W[q][idx]
+ * (W: nprob x n fp32, zero-initialised by the caller; Gt = NULL means G).
+ * The residuals follow as  R = A - W . A_lib  (vb_pcs_f32 + vb_sub_f32).  iters[q] < 0 flags a
+ * problem that hit max_iter.
+ * Replaces: do_pca_patch -> get_eigenvectors -> svd_wrapper       psfsub/pca_local.py:830-909 */
+int vb_annular_weights_f64(const double* G, const double* Gt, int n, const int* idx, const int* len,
+                           const int* frame, int nprob, int Lmax, int ncomp, double tol, int max_iter, float* W,
+                           int* iters, void* stream);
+/* dst[n x npx] = src[n x p][:, cols]  and the inverse scatter (matrix_segm = array[:, yy, xx],
+ * cube_out[fr][yy, xx] = residuals[fr];  psfsub/pca_local.py:713, 786-787) */
+int vb_gather_columns_f32(const float* src, int n, size_t p, const int* cols, int npx, float* dst, void* stream);
+int vb_scatter_columns_f32(const float* src, int n, int npx, const int* cols, size_t p, float* dst, void* stream);
 
 /* ---- measurement hook (bench.py) ----------------------------------------------------------
  * vb_profile_enable(1): CUDA events are recorded around each of the three shear kernels of

@@ -16,7 +16,13 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 
 DEROT_TOL = 2e-5
-PCA_TOL = 1e-4
+PCA_TOL = 1e-4      # residual cubes (per frame), relative to max|reference residual cube|
+# Final frames: the reference's own fp32 arithmetic (sgemm projection of a 1e4-dynamic-range cube)
+# puts it 1.5e-4 * max|frame| away from the same computation in fp64 on BASELINE config 1
+# (oracle fp32 vs oracle on the float64-cast cube), so two correct fp32 implementations differ by
+# about that much on the median frame.  We require 3e-4 against the fp32 reference AND that we are
+# not farther from the fp64 truth than 1.5x the reference itself.
+FRAME_TOL = 3e-4
 
 
 @pytest.fixture(scope="module")
@@ -147,6 +153,38 @@ def test_gram_and_eigh_accuracy():
     assert np.max(np.abs(P1 - P2)) < 1e-9
 
 
+@pytest.mark.parametrize("n,k", [(40, 5), (150, 10), (150, 20), (500, 20), (700, 24)])
+def test_eigh_topk_matches_lapack(n, k):
+    """Subspace-iteration solver: leading eigenvalues to 1e-10 and the invariant subspace to 1e-8."""
+    import torch
+    from vip_b200 import kernels
+    cube, _ = adi_cube(n, 48, k, 60.0, seed=n + k)
+    M = cube.reshape(n, -1).astype(np.float64)
+    G = M @ M.T
+    assert kernels.topk_supported(n, k)
+    evals, evecs, info = kernels.eigh_topk(torch.from_numpy(G).cuda(), k)
+    assert info["converged"], info
+    w, v = np.linalg.eigh(G)
+    w, v = w[::-1], v[:, ::-1]
+    np.testing.assert_allclose(evals.cpu().numpy(), w[:k], rtol=1e-10)
+    E = evecs.cpu().numpy()
+    np.testing.assert_allclose(E @ E.T, np.eye(k), atol=1e-10)
+    assert np.max(np.abs(E.T @ E - v[:, :k] @ v[:, :k].T)) < 1e-8
+
+
+def test_eigh_topk_flat_spectrum_still_converges():
+    """Pure noise (no gap after k): slow linear convergence, but it must still reach the tolerance."""
+    import torch
+    from vip_b200 import kernels
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(200, 3000))
+    G = A @ A.T
+    evals, evecs, info = kernels.eigh_topk(torch.from_numpy(G).cuda(), 8, tol=1e-8)
+    assert info["converged"], info
+    w = np.linalg.eigvalsh(G)[::-1]
+    np.testing.assert_allclose(evals.cpu().numpy(), w[:8], rtol=1e-9)
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 33, 130])
 def test_eigh_small_and_odd_sizes(n):
     import torch
@@ -189,44 +227,46 @@ def test_pca_c1_golden(vb, golden, golden_inputs):
     scale = np.max(np.abs(g["c1_res_frame7"]))
     assert np.max(np.abs(res[7] - g["c1_res_frame7"])) < PCA_TOL * scale
     assert np.max(np.abs(res_[7] - g["c1_resder_frame7"])) < PCA_TOL * scale
-    assert rel_err(fr, g["c1_frame"]) < PCA_TOL
+    assert rel_err(fr, g["c1_frame"]) < FRAME_TOL
+    truth = O.pca_fullframe(cube.astype(np.float64), angs, ncomp=5)
+    assert rel_err(fr, truth) < 1.5 * rel_err(g["c1_frame"], truth) + 2e-5
     P = pcs.reshape(5, -1)
     proj = (P.T @ P)[::97, ::89]
     assert np.max(np.abs(proj - g["c1_proj"])) < 1e-5        # span(V) matches (sign-invariant)
     np.testing.assert_allclose(recon + res, cube, rtol=0, atol=2e-3)
-    assert rel_err(vb.pca(cube, angs, ncomp=5, verbose=False), g["c1_frame"]) < PCA_TOL
+    assert rel_err(vb.pca(cube, angs, ncomp=5, verbose=False), g["c1_frame"]) < FRAME_TOL
 
 
 def test_pca_options_golden(vb, golden, golden_inputs):
     g = golden["pca_fullframe"]
     cube, angs = golden_inputs["small"]
     for mode in ("lapack", "eigen", "arpack"):
-        assert rel_err(vb.pca(cube, angs, ncomp=4, svd_mode=mode, verbose=False), g["small_lapack"]) < PCA_TOL
+        assert rel_err(vb.pca(cube, angs, ncomp=4, svd_mode=mode, verbose=False), g["small_lapack"]) < FRAME_TOL
     for sc in ("temp-mean", "spat-mean", "temp-standard", "spat-standard"):
-        assert rel_err(vb.pca(cube, angs, ncomp=3, scaling=sc, verbose=False), g[f"small_{sc}"]) < 2e-4, sc
+        assert rel_err(vb.pca(cube, angs, ncomp=3, scaling=sc, verbose=False), g[f"small_{sc}"]) < FRAME_TOL, sc
     for col in ("mean", "sum"):
-        assert rel_err(vb.pca(cube, angs, ncomp=3, collapse=col, verbose=False), g[f"small_{col}"]) < PCA_TOL
+        assert rel_err(vb.pca(cube, angs, ncomp=3, collapse=col, verbose=False), g[f"small_{col}"]) < FRAME_TOL
     ref = adi_cube(20, 41, 4, 60.0, seed=6)[0]
-    assert rel_err(vb.pca(cube, angs, cube_ref=ref, ncomp=4, verbose=False), g["small_rdi"]) < PCA_TOL
+    assert rel_err(vb.pca(cube, angs, cube_ref=ref, ncomp=4, verbose=False), g["small_rdi"]) < FRAME_TOL
     assert rel_err(vb.pca(cube, angs, cube_ref=ref, ncomp=4, ref_strategy="ARDI", verbose=False),
-                   g["small_ardi"]) < PCA_TOL
-    assert rel_err(vb.pca(cube, angs, ncomp=0.9995, verbose=False), g["small_cevr"]) < PCA_TOL
+                   g["small_ardi"]) < FRAME_TOL
+    assert rel_err(vb.pca(cube, angs, ncomp=0.9995, verbose=False), g["small_cevr"]) < FRAME_TOL
     # positional arguments in dataclass order + algo_params object
     fr = vb.pca(cube, angs, None, None, 4, "lapack", verbose=False)
-    assert rel_err(fr, g["small_lapack"]) < PCA_TOL
+    assert rel_err(fr, g["small_lapack"]) < FRAME_TOL
     from vip_b200.psfsub import PCA_Params
     fr = vb.pca(algo_params=PCA_Params(cube=cube, angle_list=angs, ncomp=4, verbose=False))
-    assert rel_err(fr, g["small_lapack"]) < PCA_TOL
+    assert rel_err(fr, g["small_lapack"]) < FRAME_TOL
 
 
 def test_pca_mask_center_and_cube_sig_vs_oracle(vb, golden_inputs):
     cube, angs = golden_inputs["small"]
     fr = vb.pca(cube, angs, ncomp=3, mask_center_px=4, verbose=False)
-    assert rel_err(fr, O.pca_fullframe(cube, angs, ncomp=3, mask_center_px=4)) < PCA_TOL
+    assert rel_err(fr, O.pca_fullframe(cube, angs, ncomp=3, mask_center_px=4)) < FRAME_TOL
     sig = np.zeros_like(cube)
     sig[:, 30:34, 20:24] = 5.0
     fr = vb.pca(cube, angs, ncomp=3, cube_sig=sig, verbose=False)
-    assert rel_err(fr, O.pca_fullframe(cube, angs, ncomp=3, cube_sig=sig)) < PCA_TOL
+    assert rel_err(fr, O.pca_fullframe(cube, angs, ncomp=3, cube_sig=sig)) < FRAME_TOL
 
 
 def test_pca_errors(vb):
@@ -247,4 +287,75 @@ def test_pca_medium_vs_oracle(vb):
     scale = np.max(np.abs(ores))
     assert np.max(np.abs(res - ores)) < PCA_TOL * scale
     assert np.max(np.abs(res_ - ores_)) < PCA_TOL * scale
-    assert rel_err(fr, ofr) < PCA_TOL
+    assert rel_err(fr, ofr) < FRAME_TOL
+
+
+# ------------------------------------------------------------------ pca_annular()
+def test_annular_weights_kernel_vs_numpy():
+    """Batched sub-Gramian eigen-solver: weights equal pinv-projection on the top-k subspace."""
+    import torch
+    from vip_b200 import kernels
+    cube, angs = adi_cube(120, 40, 6, 80.0, seed=21)
+    A = cube.reshape(120, -1)[:, 300:900].astype(np.float64)
+    G = A @ A.T
+    rng = np.random.default_rng(0)
+    nprob, Lmax, k = 50, 70, 6
+    idx = np.zeros((nprob, Lmax), np.int32)
+    lens = rng.integers(8, Lmax + 1, nprob).astype(np.int32)
+    lens[0] = 3                      # library smaller than ncomp and than the block width
+    frames = rng.integers(0, 120, nprob).astype(np.int32)
+    for q in range(nprob):
+        cand = np.setdiff1d(np.arange(120), [frames[q]])
+        idx[q, :lens[q]] = np.sort(rng.choice(cand, lens[q], replace=False))
+    W, iters = kernels.annular_weights(torch.from_numpy(G).cuda(), torch.from_numpy(idx).cuda(),
+                                       torch.from_numpy(lens).cuda(), torch.from_numpy(frames).cuda(), k)
+    W = W.cpu().numpy()
+    assert (iters.cpu().numpy() > 0).all()
+    for q in range(nprob):
+        I = idx[q, :lens[q]]
+        w_, v_ = np.linalg.eigh(G[np.ix_(I, I)])
+        kk = min(k, len(I))
+        X = v_[:, ::-1][:, :kk]
+        th = w_[::-1][:kk]
+        wref = X @ ((X.T @ G[I, frames[q]]) / th)
+        np.testing.assert_allclose(W[q, I], wref, rtol=0, atol=2e-6 * np.max(np.abs(wref)))
+        assert np.count_nonzero(W[q]) <= len(I)
+
+
+def test_pca_annular_golden(vb, golden, golden_inputs):
+    g = golden["pca_annular"]
+    cube, angs = golden_inputs["ann"]
+    co, cd, fr = vb.pca_annular(cube, angs, ncomp=3, asize=6, verbose=False, full_output=True)
+    assert co.shape == cd.shape == cube.shape and co.dtype == np.float32
+    scale = np.max(np.abs(g["ann_cube_out5"]))
+    assert np.max(np.abs(co[5] - g["ann_cube_out5"])) < PCA_TOL * scale
+    assert rel_err(fr, g["ann_frame"]) < FRAME_TOL
+    fr = vb.pca_annular(cube, angs, ncomp=2, asize=6, n_segments=3, delta_rot=0.5, radius_int=4, verbose=False)
+    assert rel_err(fr, g["ann_seg_frame"]) < FRAME_TOL
+
+
+def test_pca_annular_options_vs_oracle(vb, golden_inputs):
+    cube, angs = golden_inputs["ann"]
+    ref = adi_cube(12, 48, 3, 80.0, seed=10)[0]
+    sig = np.zeros_like(cube)
+    sig[:, 30:33, 10:13] = 4.0
+    cases = [dict(ncomp=(1, 2, 3, 2), asize=6), dict(ncomp=2, asize=8, delta_rot=(0.2, 0.8), n_segments=2),
+             dict(ncomp=2, asize=6, cube_sig=sig), dict(ncomp=2, asize=6, cube_ref=ref),
+             dict(ncomp=2, asize=6, scaling="temp-mean"), dict(ncomp=2, asize=8, max_frames_lib=12),
+             dict(ncomp=2, asize=8, delta_rot=0)]
+    for kw in cases:
+        o = O.pca_annular(cube, angs, full_output=True, **kw)
+        r = vb.pca_annular(cube, angs, full_output=True, verbose=False, **kw)
+        scale = np.max(np.abs(o[0]))
+        assert np.max(np.abs(r[0] - o[0])) < PCA_TOL * scale, kw
+        assert rel_err(r[2], o[2]) < FRAME_TOL, kw
+
+
+def test_pca_annular_errors(vb, golden_inputs):
+    cube, angs = golden_inputs["ann"]
+    with pytest.raises(TypeError):
+        vb.pca_annular(cube, angs[:-1], ncomp=2, asize=6, verbose=False)
+    with pytest.raises(RuntimeError):      # PA threshold so large that no frame is left in the library
+        vb.pca_annular(cube, angs, ncomp=2, asize=6, delta_rot=500, verbose=False)
+    with pytest.raises(NotImplementedError):
+        vb.pca_annular(cube, angs, ncomp="auto", asize=6, verbose=False)

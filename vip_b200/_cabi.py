@@ -25,12 +25,17 @@ SIGNATURES = {
     "vb_cross_gram_f32": (_i, [_vp, _i, _vp, _i, _sz, _vp, _vp, _sz, _vp]),
     "vb_eigh_workspace_bytes": (_sz, [_i]),
     "vb_eigh_f64": (_i, [_vp, _i, _vp, _vp, _i, _d, _vp, _sz, C.POINTER(_i), _vp]),
+    "vb_eigh_topk_workspace_bytes": (_sz, [_i, _i]),
+    "vb_eigh_topk_f64": (_i, [_vp, _i, _i, _d, _i, _vp, _vp, _vp, _sz, C.POINTER(_i), _vp]),
     "vb_pcs_f32": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp]),
     "vb_project_subtract_f32": (_i, [_vp, _vp, _i, _vp, _i, _i, _sz, _vp, _vp]),
     "vb_sub_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "vb_derotate_scratch_bytes": (_sz, [_i, _i, _i, _sz]),
     "vb_derotate_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _sz, _i, _vp]),
     "vb_collapse_f32": (_i, [_vp, _i, _sz, _i, _vp, _i, _i, _vp, _vp]),
+    "vb_annular_weights_f64": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _d, _i, _vp, _vp, _vp]),
+    "vb_gather_columns_f32": (_i, [_vp, _i, _sz, _vp, _i, _vp, _vp]),
+    "vb_scatter_columns_f32": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp]),
     "vb_profile_enable": (None, [_i]),
     "vb_profile_read": (_i, [C.POINTER(_f)]),
 }

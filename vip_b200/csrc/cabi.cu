@@ -25,6 +25,8 @@ int gram_f32(const float*, int, size_t, int, double*, void*, size_t, int, int*, 
 int cross_gram_f32(const float*, int, const float*, int, size_t, double*, void*, size_t, int, cudaStream_t);
 size_t eigh_workspace_bytes(int n);
 int eigh_f64(const double*, int, double*, double*, int, double, void*, size_t, int*, int*, cudaStream_t);
+size_t eigh_topk_workspace_bytes(int n, int B);
+int eigh_topk_f64(const double*, int, int, double, int, double*, double*, void*, size_t, int*, int*, cudaStream_t);
 int pcs_f32(const float*, const float*, int, int, size_t, float*, int*, cudaStream_t);
 int project_subtract_f32(const float*, const float*, int, const float*, int, int, size_t, float*, int*,
                          cudaStream_t);
@@ -35,6 +37,10 @@ int derotate_run(const float*, float*, int, const RotParams&, const int*, const 
                  const float2*, void*, size_t, int, int*, cudaStream_t);
 int collapse_f32(const float*, int, size_t, int, const double*, int, int, void*, cudaStream_t);
 void profile_enable(int on);
+int annular_weights(const double*, const double*, int, const int*, const int*, const int*, int, int, int, double,
+                    int, float*, int*, cudaStream_t);
+int gather_columns(const float*, int, size_t, const int*, int, float*, cudaStream_t);
+int scatter_columns(const float*, int, int, const int*, size_t, float*, cudaStream_t);
 int profile_read(float* out);
 
 // exp(-2 pi i j / N) tables for the FFT path, one per (device, N), built in fp64 on the host
@@ -100,6 +106,19 @@ int vb_eigh_f64(const double* G, int n, double* evals, double* evecs, int max_sw
     return rc;
 }
 
+size_t vb_eigh_topk_workspace_bytes(int n, int k) {
+    return eigh_topk_workspace_bytes(n, (k <= 10) ? 16 : 32);
+}
+
+int vb_eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, double* evals, double* evecs,
+                     void* ws, size_t ws_bytes, int* info_host, void* stream) {
+    int nl = 0;
+    const int rc = eigh_topk_f64(G, n, k, tol, max_iter, evals, evecs, ws, ws_bytes, info_host, &nl,
+                                 (cudaStream_t)stream);
+    g_launches += nl;
+    return rc;
+}
+
 int vb_pcs_f32(const float* Wt, const float* M, int k, int n, size_t p, float* V, void* stream) {
     int nl = 0;
     const int rc = pcs_f32(Wt, M, k, n, p, V, &nl, (cudaStream_t)stream);
@@ -155,6 +174,24 @@ int vb_collapse_f32(const float* cube, int n, size_t p, int mode, const double* 
                     void* out, void* stream) {
     g_launches += 1;
     return collapse_f32(cube, n, p, mode, w, trim_k, trim_n, out, (cudaStream_t)stream);
+}
+
+int vb_annular_weights_f64(const double* G, const double* Gt, int n, const int* idx, const int* len,
+                           const int* frame, int nprob, int Lmax, int ncomp, double tol, int max_iter, float* W,
+                           int* iters, void* stream) {
+    g_launches += 1;
+    return annular_weights(G, Gt, n, idx, len, frame, nprob, Lmax, ncomp, tol, max_iter, W, iters,
+                           (cudaStream_t)stream);
+}
+
+int vb_gather_columns_f32(const float* src, int n, size_t p, const int* cols, int npx, float* dst, void* stream) {
+    g_launches += 1;
+    return gather_columns(src, n, p, cols, npx, dst, (cudaStream_t)stream);
+}
+
+int vb_scatter_columns_f32(const float* src, int n, int npx, const int* cols, size_t p, float* dst, void* stream) {
+    g_launches += 1;
+    return scatter_columns(src, n, npx, cols, p, dst, (cudaStream_t)stream);
 }
 
 void vb_profile_enable(int on) { profile_enable(on); }

@@ -211,3 +211,373 @@ int eigh_f64(const double* G, int n, double* evals, double* evecs, int max_sweep
 }
 
 }  // namespace vb
+
+// =====================================================================================
+// Top-k eigenpairs of a large symmetric PSD matrix: fp64 block subspace iteration
+// =====================================================================================
+// For integer ncomp << n the PCA needs only the leading invariant subspace of G.  Orthogonal
+// iteration with Rayleigh-Ritz on a block of B > k vectors costs O(n^2 B) per step (one skinny
+// fp64 GEMM) and converges at rate lambda_{B+1}/lambda_k; every step is 6 small launches:
+//   Y = G X  ->  T = X^T Y  ->  Ritz (Jacobi on T)  ->  rotate + S = Yr^T Yr + residuals
+//            ->  Cholesky/convergence  ->  X = Yr R^-1.
+// State lives in global memory (n x B doubles, L2 resident), so any n works.
+
+namespace vb {
+
+struct TopkState {
+    int iters;
+    int converged;
+    double worst;     // max residual / theta_k at the last check
+    double pad;
+};
+
+constexpr int TKR = 32;   // rows per CTA in the row-parallel kernels
+
+__device__ __forceinline__ double hash_unit2(unsigned int a, unsigned int b) {
+    unsigned long long z = ((unsigned long long)a << 32 | b) + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+template <int B>
+__global__ void topk_init_kernel(double* __restrict__ Y, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n * B) Y[e] = hash_unit2((unsigned)(e / B) * 131u + 7u, (unsigned)(e % B) * 977u + 3u);
+}
+
+// Y[r][:] = sum_j G[r][j] X[j][:]   (CTA: TKR rows; thread: one row x B/8 columns)
+template <int B>
+__global__ void __launch_bounds__(256)
+topk_matvec_kernel(const double* __restrict__ G, int n, const double* __restrict__ X, double* __restrict__ Y,
+                   const TopkState* __restrict__ st) {
+    if (st->converged) return;
+    constexpr int TJ = 64, CPT = B / 8;
+    __shared__ double Gs[TKR][TJ + 1];
+    __shared__ double Xs[TJ][B];
+    const int r0 = blockIdx.x * TKR;
+    const int tr = threadIdx.x / 8, tc = (threadIdx.x % 8) * CPT;
+    double acc[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) acc[c] = 0.0;
+    for (int j0 = 0; j0 < n; j0 += TJ) {
+        for (int e = threadIdx.x; e < TKR * TJ; e += 256) {
+            const int r = e / TJ, j = e % TJ;
+            Gs[r][j] = (r0 + r < n && j0 + j < n) ? G[(size_t)(r0 + r) * n + j0 + j] : 0.0;
+        }
+        for (int e = threadIdx.x; e < TJ * B; e += 256) {
+            const int j = e / B;
+            Xs[j][e % B] = (j0 + j < n) ? X[(size_t)(j0 + j) * B + e % B] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int j = 0; j < TJ; ++j) {
+            const double g = Gs[tr][j];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) acc[c] = fma(g, Xs[j][tc + c], acc[c]);
+        }
+        __syncthreads();
+    }
+    if (r0 + tr < n) {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) Y[(size_t)(r0 + tr) * B + tc + c] = acc[c];
+    }
+}
+
+// T (B x B, atomics; must be zeroed) += P^T Q over this CTA's rows
+template <int B>
+__global__ void __launch_bounds__(256)
+topk_xty_kernel(const double* __restrict__ P, const double* __restrict__ Q, int n, double* __restrict__ T,
+                const TopkState* __restrict__ st) {
+    if (st->converged) return;
+    constexpr int RCH = 64;
+    __shared__ double Ps[RCH][B], Qs[RCH][B];
+    const int r0 = blockIdx.x * RCH;
+    for (int e = threadIdx.x; e < RCH * B; e += 256) {
+        const int r = e / B;
+        const bool in = r0 + r < n;
+        Ps[r][e % B] = in ? P[(size_t)(r0 + r) * B + e % B] : 0.0;
+        Qs[r][e % B] = in ? Q[(size_t)(r0 + r) * B + e % B] : 0.0;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < B * B; e += 256) {
+        const int a = e / B, b = e % B;
+        double s = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < RCH; ++r) s = fma(Ps[r][a], Qs[r][b], s);
+        atomicAdd(&T[e], s);
+    }
+}
+
+// single CTA: symmetrise T, one-sided Jacobi -> Qm (B x B, columns = Ritz vectors in X coordinates,
+// descending theta), theta[B]; zeroes S, res, T for the next kernels
+template <int B>
+__global__ void __launch_bounds__(256)
+topk_ritz_kernel(double* __restrict__ T, double* __restrict__ Qm, double* __restrict__ theta,
+                 double* __restrict__ S, double* __restrict__ res, const TopkState* __restrict__ st) {
+    if (st->converged) return;
+    __shared__ double Tm[B][B + 1];
+    __shared__ double th[B];
+    __shared__ int order[B];
+    __shared__ int rotated;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < B * B; e += 256) {
+        const int a = e / B, b = e % B;
+        Tm[a][b] = 0.5 * (T[a * B + b] + T[b * B + a]);
+    }
+    __syncthreads();
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        if (tid == 0) rotated = 0;
+        __syncthreads();
+        for (int r = 0; r < B - 1; ++r) {
+            for (int pr = warp; pr < B / 2; pr += 8) {
+                int a, b;
+                const int mm = B - 1;
+                if (pr == 0) { a = mm; b = r % mm; } else { a = (r + pr) % mm; b = (r - pr + mm) % mm; }
+                double al = 0, be = 0, ga = 0;
+                for (int i = lane; i < B; i += 32) {
+                    const double x = Tm[i][a], y = Tm[i][b];
+                    al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
+                }
+                al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+                if (al > 0 && be > 0 && fabs(ga) > 1e-15 * sqrt(al) * sqrt(be)) {
+                    const double zeta = (be - al) / (2.0 * ga);
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                    for (int i = lane; i < B; i += 32) {
+                        const double x = Tm[i][a], y = Tm[i][b];
+                        Tm[i][a] = c * x - s * y;
+                        Tm[i][b] = s * x + c * y;
+                    }
+                    if (lane == 0) rotated = 1;
+                }
+            }
+            __syncthreads();
+        }
+        const int any = rotated;
+        __syncthreads();
+        if (!any) break;
+    }
+    if (tid < B) {
+        double s = 0.0;
+        for (int i = 0; i < B; ++i) s = fma(Tm[i][tid], Tm[i][tid], s);
+        th[tid] = sqrt(s);
+    }
+    __syncthreads();
+    if (tid < B) {
+        int rk = 0;
+        for (int j = 0; j < B; ++j) rk += (th[j] > th[tid] || (th[j] == th[tid] && j < tid));
+        order[rk] = tid;
+    }
+    __syncthreads();
+    for (int e = tid; e < B * B; e += 256) {
+        const int i = e / B, r = e % B;
+        const int src = order[r];
+        Qm[e] = th[src] > 0.0 ? Tm[i][src] / th[src] : (i == src ? 1.0 : 0.0);
+        S[e] = 0.0;
+        T[e] = 0.0;
+    }
+    if (tid < B) { theta[tid] = th[order[tid]]; res[tid] = 0.0; }
+}
+
+// rows: Yr = Y Q, Xr = X Q (in place); S += Yr^T Yr; res[r] += ||Yr[:,r] - theta_r Xr[:,r]||^2
+template <int B>
+__global__ void __launch_bounds__(256)
+topk_rotate_kernel(double* __restrict__ X, double* __restrict__ Y, int n, const double* __restrict__ Qm,
+                   const double* __restrict__ theta, double* __restrict__ S, double* __restrict__ res,
+                   const TopkState* __restrict__ st) {
+    if (st->converged) return;
+    constexpr int RCH = 64;
+    __shared__ double Qs[B][B];
+    __shared__ double Ys[RCH][B], Xs[RCH][B];
+    const int tid = threadIdx.x, r0 = blockIdx.x * RCH;
+    for (int e = tid; e < B * B; e += 256) Qs[e / B][e % B] = Qm[e];
+    for (int e = tid; e < RCH * B; e += 256) {
+        const int r = e / B;
+        const bool in = r0 + r < n;
+        Ys[r][e % B] = in ? Y[(size_t)(r0 + r) * B + e % B] : 0.0;
+        Xs[r][e % B] = in ? X[(size_t)(r0 + r) * B + e % B] : 0.0;
+    }
+    __syncthreads();
+    // each thread produces entries (row, col) of Yr and Xr: RCH*B entries / 256 threads
+    double yr[RCH * B / 256], xr[RCH * B / 256];
+#pragma unroll
+    for (int q = 0; q < RCH * B / 256; ++q) {
+        const int e = tid + q * 256, r = e / B, c = e % B;
+        double sy = 0.0, sx = 0.0;
+#pragma unroll 8
+        for (int m = 0; m < B; ++m) {
+            sy = fma(Ys[r][m], Qs[m][c], sy);
+            sx = fma(Xs[r][m], Qs[m][c], sx);
+        }
+        yr[q] = sy; xr[q] = sx;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < RCH * B / 256; ++q) {
+        const int e = tid + q * 256, r = e / B, c = e % B;
+        Ys[r][c] = yr[q]; Xs[r][c] = xr[q];
+        if (r0 + r < n) {
+            Y[(size_t)(r0 + r) * B + c] = yr[q];
+            X[(size_t)(r0 + r) * B + c] = xr[q];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < B * B; e += 256) {
+        const int a = e / B, b = e % B;
+        double s = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < RCH; ++r) s = fma(Ys[r][a], Ys[r][b], s);
+        atomicAdd(&S[e], s);
+    }
+    if (tid < B) {
+        double s = 0.0;
+        const double th = theta[tid];
+        for (int r = 0; r < RCH; ++r) {
+            const double d = Ys[r][tid] - th * Xs[r][tid];
+            s = fma(d, d, s);
+        }
+        atomicAdd(&res[tid], s);
+    }
+}
+
+// single warp: convergence test on the leading k Ritz pairs; R = chol(D^-1 S D^-1) (upper), dinv = 1/||Yr_c||
+template <int B>
+__global__ void topk_chol_kernel(const double* __restrict__ S, const double* __restrict__ res,
+                                 const double* __restrict__ theta, int k, double tol, double* __restrict__ R,
+                                 double* __restrict__ dinv, TopkState* __restrict__ st, int check) {
+    if (st->converged) return;
+    __shared__ double Sn[B][B + 1], Rm[B][B + 1], dv[B];
+    const int lane = threadIdx.x;
+    if (lane == 0) {
+        st->iters += 1;
+        if (check) {
+            double worst = 0.0;
+            for (int r = 0; r < k; ++r) worst = fmax(worst, sqrt(res[r]));
+            const double ref = theta[k - 1];
+            st->worst = ref > 0.0 ? worst / ref : 0.0;
+            if (worst <= tol * ref) st->converged = 1;
+        }
+    }
+    __syncwarp();
+    for (int c = lane; c < B; c += 32) dv[c] = S[c * B + c] > 0.0 ? rsqrt(S[c * B + c]) : 0.0;
+    __syncwarp();
+    for (int e = lane; e < B * B; e += 32) Sn[e / B][e % B] = S[e] * dv[e / B] * dv[e % B];
+    __syncwarp();
+    for (int j = 0; j < B; ++j) {
+        double d = Sn[j][j];
+        for (int m = 0; m < j; ++m) d -= Rm[m][j] * Rm[m][j];
+        d = (d > 1e-300) ? sqrt(d) : 1e-150;
+        for (int c = j + lane; c < B; c += 32) {
+            double v = Sn[j][c];
+            for (int m = 0; m < j; ++m) v -= Rm[m][j] * Rm[m][c];
+            Rm[j][c] = (c == j) ? d : v / d;
+        }
+        __syncwarp();
+    }
+    for (int e = lane; e < B * B; e += 32) R[e] = (e / B <= e % B) ? Rm[e / B][e % B] : 0.0;
+    for (int c = lane; c < B; c += 32) dinv[c] = dv[c];
+}
+
+// rows: X = (Yr D^-1) R^-1  (forward substitution per row).  When converged, X (Ritz vectors) is kept.
+template <int B>
+__global__ void __launch_bounds__(128)
+topk_solve_kernel(double* __restrict__ X, const double* __restrict__ Y, int n, const double* __restrict__ R,
+                  const double* __restrict__ dinv, const TopkState* __restrict__ st) {
+    if (st->converged) return;
+    __shared__ double Rs[B][B + 1], ds[B];
+    for (int e = threadIdx.x; e < B * B; e += 128) Rs[e / B][e % B] = R[e];
+    for (int c = threadIdx.x; c < B; c += 128) ds[c] = dinv[c];
+    __syncthreads();
+    const int r = blockIdx.x * 128 + threadIdx.x;
+    if (r >= n) return;
+    double x[B];
+#pragma unroll
+    for (int c = 0; c < B; ++c) {
+        double v = Y[(size_t)r * B + c] * ds[c];
+#pragma unroll
+        for (int m = 0; m < c; ++m) v -= x[m] * Rs[m][c];
+        x[c] = v / Rs[c][c];
+    }
+#pragma unroll
+    for (int c = 0; c < B; ++c) X[(size_t)r * B + c] = x[c];
+}
+
+// evals[k], evecs[k x n] (row j = j-th eigenvector) from theta / X
+template <int B>
+__global__ void topk_output_kernel(const double* __restrict__ X, const double* __restrict__ theta, int n, int k,
+                                   double* __restrict__ evals, double* __restrict__ evecs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        for (int j = 0; j < k; ++j) evecs[(size_t)j * n + i] = X[(size_t)i * B + j];
+    if (i < k) evals[i] = theta[i];
+}
+
+size_t eigh_topk_workspace_bytes(int n, int B) {
+    return ((size_t)2 * n * B + 4 * (size_t)B * B + 4 * B) * sizeof(double) + 256;
+}
+
+template <int B>
+static int topk_run(const double* G, int n, int k, double tol, int max_iter, double* evals, double* evecs,
+                    void* ws, int* info, int* launches, cudaStream_t st) {
+    double* X = reinterpret_cast<double*>(ws);
+    double* Y = X + (size_t)n * B;
+    double* T = Y + (size_t)n * B;
+    double* S = T + B * B;
+    double* Qm = S + B * B;
+    double* R = Qm + B * B;
+    double* theta = R + B * B;
+    double* res = theta + B;
+    double* dinv = res + B;
+    TopkState* state = reinterpret_cast<TopkState*>(dinv + 2 * B);
+    VB_CHECK_CUDA(cudaMemsetAsync(T, 0, (size_t)(4 * B * B + 4 * B) * sizeof(double) + sizeof(TopkState), st));
+    int nl = 0;
+    const int grows = ceil_div(n, 64);
+    topk_init_kernel<B><<<ceil_div(n * B, 256), 256, 0, st>>>(Y, n);
+    // orthonormalise the start block: S = Y^T Y, Cholesky, solve
+    topk_xty_kernel<B><<<grows, 256, 0, st>>>(Y, Y, n, S, state);
+    topk_chol_kernel<B><<<1, 32, 0, st>>>(S, res, theta, k, tol, R, dinv, state, 0);
+    topk_solve_kernel<B><<<ceil_div(n, 128), 128, 0, st>>>(X, Y, n, R, dinv, state);
+    nl += 4;
+    VB_CHECK_LAUNCH();
+    TopkState h{};
+    for (int it = 0; it < max_iter; ++it) {
+        topk_matvec_kernel<B><<<ceil_div(n, TKR), 256, 0, st>>>(G, n, X, Y, state);
+        topk_xty_kernel<B><<<grows, 256, 0, st>>>(X, Y, n, T, state);
+        topk_ritz_kernel<B><<<1, 256, 0, st>>>(T, Qm, theta, S, res, state);
+        topk_rotate_kernel<B><<<grows, 256, 0, st>>>(X, Y, n, Qm, theta, S, res, state);
+        topk_chol_kernel<B><<<1, 32, 0, st>>>(S, res, theta, k, tol, R, dinv, state, 1);
+        topk_solve_kernel<B><<<ceil_div(n, 128), 128, 0, st>>>(X, Y, n, R, dinv, state);
+        nl += 6;
+        if ((it & 7) == 7 || it == max_iter - 1) {
+            VB_CHECK_LAUNCH();
+            VB_CHECK_CUDA(cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, st));
+            VB_CHECK_CUDA(cudaStreamSynchronize(st));
+            if (h.converged) break;
+        }
+    }
+    topk_output_kernel<B><<<ceil_div(n, 256), 256, 0, st>>>(X, theta, n, k, evals, evecs);
+    VB_CHECK_LAUNCH();
+    nl += 1;
+    if (launches) *launches = nl;
+    if (info) { info[0] = h.iters; info[1] = h.converged; }
+    return 0;
+}
+
+// Leading k eigenpairs of the symmetric PSD matrix G (n x n fp64).  evals[k] descending,
+// evecs[k x n] row j = eigenvector j.  info_host: iterations, converged flag.  Synchronises.
+int eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, double* evals, double* evecs,
+                  void* ws, size_t ws_bytes, int* info, int* launches, cudaStream_t st) {
+    VB_REQUIRE(n >= 1 && k >= 1 && k <= n, "eigh_topk: need 1 <= k <= n");
+    if (tol <= 0) tol = 1e-10;
+    if (max_iter <= 0) max_iter = 2000;
+    const int B = (k <= 10) ? 16 : 32;
+    VB_REQUIRE(k <= 24, "eigh_topk: k=%d too large for the subspace solver (use the Jacobi solver)", k);
+    VB_REQUIRE(n >= B, "eigh_topk: n=%d smaller than the block width %d (use the Jacobi solver)", n, B);
+    VB_REQUIRE(ws_bytes >= eigh_topk_workspace_bytes(n, B), "eigh_topk: workspace too small");
+    if (B == 16) return topk_run<16>(G, n, k, tol, max_iter, evals, evecs, ws, info, launches, st);
+    return topk_run<32>(G, n, k, tol, max_iter, evals, evecs, ws, info, launches, st);
+}
+
+}  // namespace vb

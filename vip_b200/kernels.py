@@ -66,6 +66,27 @@ def eigh(G, max_sweeps=0, tol=0.0):
     return evals, evecs, {"sweeps": int(info[0]), "converged": bool(info[1])}
 
 
+def eigh_topk(G, k, tol=0.0, max_iter=0):
+    """Leading k eigenpairs of a symmetric PSD fp64 matrix by block subspace iteration.
+
+    Returns (evals[k] descending, evecs[k,n] rows = eigenvectors, info dict)."""
+    lib = _cabi.lib()
+    n = G.shape[0]
+    evals = empty((k,), torch.float64, G.device)
+    evecs = empty((k, n), torch.float64, G.device)
+    nb = lib.vb_eigh_topk_workspace_bytes(n, k)
+    ws = _bytes(nb, G.device)
+    info = (C.c_int * 2)()
+    _cabi.check(lib.vb_eigh_topk_f64(ptr(G), n, int(k), float(tol), int(max_iter), ptr(evals), ptr(evecs),
+                                     ptr(ws), nb, info, stream_ptr()), "vb_eigh_topk_f64")
+    return evals, evecs, {"iters": int(info[0]), "converged": bool(info[1])}
+
+
+def topk_supported(n, k):
+    """The subspace solver handles k <= 24 with a block (16 or 32 vectors) no wider than the matrix."""
+    return k <= 24 and n >= (16 if k <= 10 else 32) and n > 2 * k
+
+
 def pcs(Wt, M):
     """V (k,p) = Wt (k,n) . M (n,p), fp32."""
     lib = _cabi.lib()
@@ -131,3 +152,39 @@ def collapse(cube2d, mode="median", w=None, trim_k=0, trim_n=0):
     _cabi.check(lib.vb_collapse_f32(ptr(cube2d), n, p, m, ptr(d_w), int(trim_k), int(trim_n), ptr(out),
                                     stream_ptr()), "vb_collapse_f32")
     return out
+
+
+def gather_columns(M, cols):
+    """(n,p) fp32, int32 column indices (npx,) -> (n,npx) fp32."""
+    lib = _cabi.lib()
+    n, p = M.shape
+    npx = cols.numel()
+    out = empty((n, npx), torch.float32, M.device)
+    _cabi.check(lib.vb_gather_columns_f32(ptr(M), n, p, ptr(cols), npx, ptr(out), stream_ptr()),
+                "vb_gather_columns_f32")
+    return out
+
+
+def scatter_columns(src, cols, dst):
+    """dst[:, cols] = src  for (n,npx) src and (n,p) dst, in place."""
+    lib = _cabi.lib()
+    n, npx = src.shape
+    _cabi.check(lib.vb_scatter_columns_f32(ptr(src), n, npx, ptr(cols), dst.shape[1], ptr(dst), stream_ptr()),
+                "vb_scatter_columns_f32")
+    return dst
+
+
+def annular_weights(G, idx, lens, frames, ncomp, tol=0.0, max_iter=0):
+    """Per-problem projection weights from the library Gramian G (nlib,nlib) fp64.
+
+    idx (nprob,Lmax) int32, lens (nprob,) int32, frames (nprob,) int32 = row of G of each target.
+    Returns (W (nprob,nlib) fp32, iters (nprob,) int32)."""
+    lib = _cabi.lib()
+    n = G.shape[0]
+    nprob, Lmax = idx.shape
+    W = torch.zeros((nprob, n), dtype=torch.float32, device=G.device)
+    iters = torch.zeros((nprob,), dtype=torch.int32, device=G.device)
+    _cabi.check(lib.vb_annular_weights_f64(ptr(G), 0, n, ptr(idx), ptr(lens), ptr(frames), nprob, Lmax,
+                                           int(ncomp), float(tol), int(max_iter), ptr(W), ptr(iters),
+                                           stream_ptr()), "vb_annular_weights_f64")
+    return W, iters

@@ -1,11 +1,31 @@
-"""Annular PCA on the B200 (drop-in for ``vip_hci.psfsub.pca_annular``) -- under construction."""
+"""Annular PCA on the B200: drop-in for ``vip_hci.psfsub.pca_annular`` (3-d ADI / ADI+RDI cubes).
+
+Reference: ``src/vip_hci/psfsub/pca_local.py`` -- ``PCA_ANNULAR_Params`` :39-70, ``pca_annular``
+:73-462, ``_pca_adi_rdi`` :594-827, ``do_pca_patch`` :830-909.
+
+The reference runs, per annular segment and per frame, an SVD of that frame's PA-thresholded
+library.  Here each segment costs one Gramian (``vb_gram_f32``), one batched kernel that solves all
+per-frame eigenproblems on sub-blocks of that Gramian (``vb_annular_weights_f64``) and one skinny
+GEMM that applies the resulting weights (``R = A - W . A_lib``).  Library index lists are integer
+results of the reference's own selection rule and are computed on the host in numpy, bit-exactly.
+"""
 from dataclasses import dataclass
 from enum import Enum
 from typing import List, Tuple, Union
 
 import numpy as np
+import torch
 
-from ..config.paramenum import Collapse, Imlib, Interpolation, SvdMode
+from .. import kernels
+from .._device import require_cuda, to_device_f32, to_host
+from ..config.paramenum import ALGO_KEY, Collapse, Imlib, Interpolation, SvdMode
+from ..config.utils_param import separate_kwargs_dict, setup_parameters
+from ..preproc.derotation import _check_rot_options, _define_annuli, derotate_device
+from ..preproc.parangles import check_pa_vector
+from ..preproc.subsampling import collapse_device
+from ..var.shapes import get_annulus_segments
+from .pca_fullfr import scale_matrix_device
+from .svd import Decomposition, _EXACT_MODES, _mode_name
 
 
 @dataclass
@@ -42,5 +62,214 @@ class PCA_ANNULAR_Params:
     left_eigv: bool = False
 
 
-def pca_annular(*all_args, **all_kwargs):
-    raise NotImplementedError("vip_b200.pca_annular: GPU path under construction")
+def _unsupported(what):
+    raise NotImplementedError(
+        f"vip_b200.pca_annular: {what} is not implemented on the B200 path yet (no CPU fallback)")
+
+
+def library_indices(angle_list, pa_thr, max_frames):
+    """``_find_indices_adi(angle_list, f, pa_thr, truncate=True, max_frames=...)`` for every frame f
+    (``preproc/derotation.py:410-496``), vectorised per frame; returns a list of int32 arrays.
+
+    Same integer results as the reference, including the ``np.argsort`` tie-breaking of the
+    truncation step (the very same numpy call on the very same values)."""
+    n = angle_list.shape[0]
+    limit = min(n - 1, max_frames)
+    out = []
+    for f in range(n):
+        d = np.abs(angle_list - angle_list[f])
+        close = d[:f] < pa_thr
+        index_prev = int(np.argmax(close)) if close.any() else f
+        far = d[f:] > pa_thr
+        index_foll = f + int(np.argmax(far)) if far.any() else n
+        kept = np.concatenate((np.arange(0, index_prev), np.arange(index_foll, n)))
+        if len(kept) > limit:
+            d_pa = np.abs(angle_list[kept] - angle_list[f])
+            kept = np.sort(kept[np.argsort(d_pa)][:limit])
+        out.append(kept.astype(np.int32))
+    return out
+
+
+def _segment_residuals(A, A_lib, angle_list, pa_thr, ncomp, min_frames_lib, max_frames_lib, A_ref=None):
+    """Residuals of every frame of one segment matrix ``A`` (n,npx) on the device.
+
+    ``A_lib`` = matrix the libraries are drawn from (A, or A - A_sig); ``A_ref`` = optional RDI rows
+    stacked in front of every library (``pca_local.py:880-885``)."""
+    n, npx = A.shape
+    dev = A.device
+    if pa_thr == 0:
+        # every frame uses the whole segment matrix as library: one decomposition (pca_local.py:874-878)
+        lib = A_lib if A_ref is None else torch.cat((A_ref, A_lib))
+        k = min(ncomp, min(lib.shape))
+        dec = Decomposition(lib, k)
+        V = dec.pcs(k)
+        Cm = kernels.cross_gram(A_lib, V).to(torch.float32).contiguous()
+        return kernels.project_subtract(A, Cm, V), k
+
+    lists = library_indices(angle_list, pa_thr, max_frames_lib)
+    nref = 0 if A_ref is None else A_ref.shape[0]
+    for f, idx in enumerate(lists):
+        if len(idx) < min_frames_lib and A_ref is None:
+            msg = "Too few frames left in the PCA library. "
+            msg += "Accepted indices length ({:.0f}) less than {:.0f}. "
+            msg += "Try decreasing either delta_rot or min_frames_lib."
+            raise RuntimeError(msg.format(len(idx), min_frames_lib))
+    Lmax = max(len(i) for i in lists) + nref
+    if Lmax > 256:
+        _unsupported(f"libraries of more than 256 frames (got {Lmax}: max_frames_lib + reference frames)")
+    idx_host = np.zeros((n, max(Lmax, 1)), dtype=np.int32)
+    lens = np.zeros(n, dtype=np.int32)
+    for f, idx in enumerate(lists):
+        L = len(idx) + nref
+        lens[f] = L
+        if nref:
+            idx_host[f, :nref] = np.arange(nref)
+        idx_host[f, nref:L] = idx + nref
+    lib = A_lib if A_ref is None else torch.cat((A_ref, A_lib))
+    k = min(ncomp, npx)                      # get_eigenvectors clamps to min(shape) (svd.py:694)
+    if k > 24:
+        _unsupported("more than 24 principal components per annulus")
+    G = kernels.gram(lib)
+    W, iters = kernels.annular_weights(
+        G, torch.from_numpy(idx_host).to(dev), torch.from_numpy(lens).to(dev),
+        torch.arange(nref, nref + n, dtype=torch.int32, device=dev), k)
+    if bool((iters < 0).any()):
+        bad = int((iters < 0).sum())
+        raise RuntimeError(f"vip_b200.pca_annular: {bad} per-frame eigenproblems did not converge")
+    P = kernels.pcs(W, lib)                  # (n, npx) = W . A_lib : the per-frame PSF models
+    return kernels.sub(A, P), k
+
+
+def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segments=1, delta_rot=1, ncomp=1,
+                        svd_mode="lapack", nproc=None, min_frames_lib=2, max_frames_lib=200, tol=1e-1,
+                        scaling=None, imlib="vip-fft", interpolation="lanczos4", collapse="median",
+                        full_output=False, verbose=1, cube_ref=None, theta_init=0, weights=None,
+                        cube_sig=None, left_eigv=False, **rot_options):
+    """``_pca_adi_rdi`` (``pca_local.py:594-827``) with the arithmetic on the GPU."""
+    array = cube
+    if array.ndim != 3:
+        raise TypeError("Input array is not a cube or 3d array")
+    if array.shape[0] != angle_list.shape[0]:
+        raise TypeError("Input vector or parallactic angles has wrong length")
+    n, y, x = array.shape
+    angle_list = check_pa_vector(angle_list)
+    n_annuli = int((y / 2 - radius_int) / asize)
+
+    if isinstance(delta_rot, tuple):
+        delta_rot = np.linspace(delta_rot[0], delta_rot[1], num=n_annuli)
+    elif np.isscalar(delta_rot):
+        delta_rot = [delta_rot] * n_annuli
+    elif len(delta_rot) != n_annuli:
+        raise TypeError("If delta_rot is a list it should have n_annuli elements.")
+
+    if isinstance(n_segments, int):
+        n_segments = [n_segments for _ in range(n_annuli)]
+    elif n_segments == "auto":
+        n_segments = [2, 3]
+        ld = 2 * np.tan(360 / 4 / 2) * asize
+        for i in range(2, n_annuli):
+            ang = np.rad2deg(2 * np.arctan(ld / (2 * i * asize)))
+            n_segments.append(int(np.ceil(360 / ang)))
+
+    if verbose:
+        print("N annuli = {}, FWHM = {:.3f}".format(n_annuli, fwhm))
+        print("PCA per annulus (or annular sectors):")
+
+    if _mode_name(svd_mode) not in _EXACT_MODES:
+        _unsupported(f"svd_mode={_mode_name(svd_mode)!r}")
+    if isinstance(ncomp, list):
+        _unsupported("a list of `ncomp` (one residual cube per value)")
+    if isinstance(ncomp, str):
+        _unsupported("ncomp='auto'")
+    if left_eigv:
+        _unsupported("`left_eigv`")
+    _check_rot_options(imlib, rot_options.get("cxy"), rot_options.get("border_mode", "constant"),
+                       rot_options.get("edge_blend"), array.shape)
+
+    dev = require_cuda()
+    cube_dev = to_device_f32(array, dev).reshape(n, y * x)
+    ref_dev = to_device_f32(cube_ref, dev).reshape(cube_ref.shape[0], y * x) if cube_ref is not None else None
+    sig_dev = to_device_f32(cube_sig, dev).reshape(n, y * x) if cube_sig is not None else None
+    cube_out = torch.zeros_like(cube_dev)
+
+    verbose_ann = (int(verbose) + int(cube_ref is None)) if verbose else verbose
+    for ann in range(n_annuli):
+        if isinstance(ncomp, (tuple, np.ndarray)):
+            if len(ncomp) != n_annuli:
+                raise TypeError("If `ncomp` is a tuple, its length must match the number of annuli")
+            ncompann = int(ncomp[ann])
+        else:
+            ncompann = ncomp
+        pa_thr, inner_radius, _ = _define_annuli(angle_list, ann, n_annuli, fwhm, radius_int, asize,
+                                                 delta_rot[ann], n_segments[ann], verbose_ann, True)
+        segments = get_annulus_segments((y, x), inner_radius, asize, n_segments[ann], theta_init)
+        for yy, xx in segments:
+            if yy.size == 0:
+                continue
+            cols = torch.from_numpy((yy * x + xx).astype(np.int32)).to(dev)
+            A = scale_matrix_device(kernels.gather_columns(cube_dev, cols), scaling)
+            A_ref = (scale_matrix_device(kernels.gather_columns(ref_dev, cols), scaling)
+                     if ref_dev is not None else None)
+            A_lib = A - kernels.gather_columns(sig_dev, cols) if sig_dev is not None else A
+            R, _ = _segment_residuals(A, A_lib, angle_list, pa_thr, ncompann, min_frames_lib,
+                                      max_frames_lib, A_ref)
+            kernels.scatter_columns(R, cols, cube_out)
+        if verbose == 1:
+            print("Done PCA with {} for current annulus".format(_mode_name(svd_mode)))
+
+    cube_out = cube_out.reshape(n, y, x)
+    mask_val = float(rot_options.get("mask_val", np.nan))
+    interp_zeros = bool(rot_options.get("interp_zeros", False))
+    cube_der = derotate_device(cube_out, -angle_list, mask_val=mask_val, interp_zeros=interp_zeros)
+    frame = collapse_device(cube_der, mode=collapse, w=weights)
+    if verbose:
+        print("Done derotating and combining.")
+    if full_output:
+        return cube_out, cube_der, frame
+    return frame
+
+
+def pca_annular(*all_args: List, **all_kwargs: dict):
+    """Annular (per-frame PA-thresholded library) PCA: drop-in for ``vip_hci.psfsub.pca_annular``.
+
+    Positional arguments map to :class:`PCA_ANNULAR_Params` fields in declaration order; keyword
+    arguments that are not fields become ``rot_options``; ``algo_params=<obj>`` bypasses parsing.
+    Implemented on the GPU: 3-d ADI and ADI+RDI cubes, int / per-annulus-tuple ``ncomp`` (<= 24),
+    ``n_segments`` (int, list or 'auto'), ``delta_rot``, ``scaling``, ``cube_sig``, ``radius_int``,
+    every deterministic ``svd_mode``.  Returns ``frame`` or ``(cube_out, cube_der, frame)``.
+    """
+    class_params, rot_options = separate_kwargs_dict(initial_kwargs=all_kwargs,
+                                                     parent_class=PCA_ANNULAR_Params)
+    algo_params = rot_options.pop(ALGO_KEY, None)
+    if algo_params is None:
+        algo_params = PCA_ANNULAR_Params(*all_args, **class_params)
+    p = algo_params
+
+    if p.radius_int and len(rot_options) == 0:
+        rot_options["mask_val"] = 0
+        rot_options["ker"] = 1
+        rot_options["interp_zeros"] = True
+
+    if p.left_eigv and (p.cube_ref is not None or p.cube_sig is not None or p.ncomp == "auto"):
+        raise NotImplementedError("left_eigv is not compatiblewith 'cube_ref', 'cube_sig', ncomp='auto'")
+
+    if not isinstance(p.cube, np.ndarray):
+        raise TypeError("Input array is not a cube or 3d array")
+    if p.cube.ndim == 4:
+        _unsupported("4-d (IFS) input")
+    if p.cube.ndim != 3:
+        raise TypeError("Input array is not a 4d or 3d array")
+
+    func_params = setup_parameters(params_obj=p, fkt=_pca_adi_rdi_device, full_output=True)
+    cube_out, cube_der, frame = _pca_adi_rdi_device(**func_params, **rot_options)
+    dt = p.cube.dtype
+
+    def host(t):
+        a = to_host(t)
+        if a.dtype == np.float32 and dt != np.float32 and np.issubdtype(dt, np.floating):
+            a = a.astype(dt)
+        return a
+
+    if p.full_output:
+        return host(cube_out), host(cube_der), host(frame)
+    return host(frame)

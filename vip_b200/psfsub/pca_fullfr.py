@@ -151,7 +151,7 @@ def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, 
 
     if svd_mode in _EXACT_MODES:
         if dec is None:
-            dec = Decomposition(ref_lib)
+            dec = Decomposition(ref_lib, ncomp)
         V = dec.pcs(ncomp)
         if ref_lib is matrix_emp:
             Cm = dec.coeffs(ncomp)                # = matrix_emp . V^T from the eigenpairs

@@ -19,14 +19,23 @@ def _mode_name(mode):
 
 
 class Decomposition:
-    """Eigen-decomposition of M M^T for a device matrix M (n,p): singular values and left vectors."""
+    """Eigen-decomposition of M M^T for a device matrix M (n,p): singular values and left vectors.
 
-    def __init__(self, M):
+    ``ncomp=None`` -> full spectrum (Jacobi; needed for CEVR); an integer ``ncomp`` small enough for
+    the subspace solver -> only the leading pairs (falls back to Jacobi if it does not converge)."""
+
+    def __init__(self, M, ncomp=None):
         self.M = M
+        n = M.shape[0]
         G = kernels.gram(M)
-        evals, evecs, self.info = kernels.eigh(G)
-        self.evals = evals                     # (n,) descending, fp64
-        self.U = evecs                         # (n,n) fp64, row j = j-th left singular vector of M
+        self.full = True
+        if ncomp is not None and kernels.topk_supported(n, ncomp):
+            evals, evecs, self.info = kernels.eigh_topk(G, ncomp)
+            self.full = not self.info["converged"]
+        if self.full:
+            evals, evecs, self.info = kernels.eigh(G)
+        self.evals = evals                     # descending, fp64 (all n, or the leading ncomp)
+        self.U = evecs                         # fp64, row j = j-th left singular vector of M
         self.S = torch.sqrt(torch.clamp(evals, min=0.0))
 
     def check_rank(self, ncomp):
@@ -103,7 +112,7 @@ def svd_wrapper(matrix, mode, ncomp, verbose=False, full_output=False, random_st
     if mode in _EXACT_MODES:
         if n > p:
             raise NotImplementedError("vip_b200 svd_wrapper expects n_frames <= n_pixels")
-        dec = Decomposition(M)
+        dec = Decomposition(M, None if (full_output or left_eigv) else ncomp)
         V = dec.pcs(ncomp)
         U = dec.U[:ncomp].to(torch.float32)
         S = dec.S[:ncomp].to(torch.float32)
