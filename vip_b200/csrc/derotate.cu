@@ -23,6 +23,7 @@
 //     with the closed-form Dirichlet kernel  D(t) = e^{-i pi t/N} sin(pi t) / (N sin(pi t/N)),
 //     evaluated directly on the non-zero support.
 #include "common.cuh"
+#include <cstdlib>
 #include <vector>
 
 namespace vb {
@@ -210,6 +211,13 @@ __device__ __forceinline__ void phase_of(int s_int, float s_frac, int k, float& 
     sincospif(-2.0f * turns, &pi, &pr);
 }
 
+// barrier among the T threads of one transform only (transforms of a CTA do not wait for each other)
+template <int T>
+__device__ __forceinline__ void transform_sync(int tr) {
+    if (T <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(tr + 1), "r"(T) : "memory");
+}
+
 template <int N>
 struct ShearFft {
     static constexpr int T = N / 16;      // threads per transform
@@ -231,10 +239,10 @@ struct ShearFft {
     // In:  re/im[j] = x[t + j*T]  (j = 0..15).  Out: re/im[j] = y[t + j*T] where
     //   y = IFFT( FFT(x) * exp(-2 pi i s f) ),  s = s_int + s_frac pixels.
     // sre/sim: this transform's N-float exchange arrays; ph3: R3 complex per-transform phase
-    // constants in shared memory.  Must be called by all threads of the CTA (uses __syncthreads).
+    // constants in shared memory.  Must be called by all T threads of transform `tr` (named barrier tr+1).
     __device__ __forceinline__ static void run(float (&re)[16], float (&im)[16], float* sre, float* sim,
                                                float2* ph3, const float2* __restrict__ tw, int t,
-                                               int s_int, float s_frac) {
+                                               int tr, int s_int, float s_frac) {
         float wr[16], wi[16];
         const int npp = t & (L2 - 1), k1p = t >> LOG_R3;
 
@@ -259,7 +267,7 @@ struct ShearFft {
             const int a = sw1(k1 * L1 + t);
             sre[a] = yr; sim[a] = yi;
         }
-        __syncthreads();
+        transform_sync<T>(tr);
         // ---- forward stage 2: radix-16 inside each length-L1 block
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -268,7 +276,7 @@ struct ShearFft {
         }
         dif<16, -1, 0>(re, im);
         twiddle_powers<N, false>(tw, npp * 16, wr, wi);
-        __syncthreads();
+        transform_sync<T>(tr);
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) {
             const int r = brev(k2, 4);
@@ -277,7 +285,7 @@ struct ShearFft {
             const int a = sw2(k1p * L1 + k2 * L2 + npp);
             sre[a] = yr; sim[a] = yi;
         }
-        __syncthreads();
+        transform_sync<T>(tr);
         // ---- forward stage 3: radix-R3 on 16 contiguous points, phase, inverse stage 3
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
@@ -302,13 +310,13 @@ struct ShearFft {
             }
         }
         GroupFft<R3, +1, G3>::inv(re, im);
-        __syncthreads();
+        transform_sync<T>(tr);
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
             const int a = sw2(16 * t + e);
             sre[a] = re[e]; sim[a] = im[e];
         }
-        __syncthreads();
+        transform_sync<T>(tr);
         // ---- inverse stage 2
         twiddle_powers<N, true>(tw, npp * 16, wr, wi);
 #pragma unroll
@@ -318,13 +326,13 @@ struct ShearFft {
             cmul(sre[a], sim[a], wr[j], wi[j], re[r], im[r]);
         }
         dit<16, +1, 0>(re, im);
-        __syncthreads();
+        transform_sync<T>(tr);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int a = sw1(k1p * L1 + j * L2 + npp);
             sre[a] = re[j]; sim[a] = im[j];
         }
-        __syncthreads();
+        transform_sync<T>(tr);
         // ---- inverse stage 1
         twiddle_powers<N, true>(tw, t, wr, wi);
 #pragma unroll
@@ -364,7 +372,7 @@ shear_rows_first_fft(const float* __restrict__ in, float2* __restrict__ T1, RotP
     int s_int; float s_frac;
     split_shift(a_coef[f] * (double)(i - N / 2), s_int, s_frac);
     float* sre = smem + tr * F::BUF;
-    F::run(re, im, sre, sre + N, ph3s[tr], tw, t, s_int, s_frac);
+    F::run(re, im, sre, sre + N, ph3s[tr], tw, t, tr, s_int, s_frac);
     if (valid) {
         float2* dst = T1 + ((size_t)fl * (g.S + 1) + row) * N;
 #pragma unroll
@@ -408,7 +416,7 @@ shear_cols_fft(const float2* __restrict__ T1, float2* __restrict__ T2, RotParams
     __syncthreads();
     int s_int; float s_frac;
     split_shift(b_coef[f] * (double)(c0 + tr - N / 2), s_int, s_frac);
-    F::run(re, im, sre, sre + N, ph3s[tr], tw, t, s_int, s_frac);
+    F::run(re, im, sre, sre + N, ph3s[tr], tw, t, tr, s_int, s_frac);
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -457,7 +465,7 @@ shear_rows_last_fft(const float2* __restrict__ T2, const float* __restrict__ in,
     int s_int; float s_frac;
     split_shift(a_coef[f] * (double)(i - N / 2), s_int, s_frac);
     float* sre = smem + tr * F::BUF;
-    F::run(re, im, sre, sre + N, ph3s[tr], tw, t, s_int, s_frac);
+    F::run(re, im, sre, sre + N, ph3s[tr], tw, t, tr, s_int, s_frac);
     if (valid) {
         const float* src = in + ((size_t)f * g.S + row) * g.S;
         float* dst = out + ((size_t)f * g.S + row) * g.S;
@@ -666,6 +674,16 @@ static int launch_direct_chunk(const float* in, float* out, float2* T1, float2* 
     return 0;
 }
 
+// transforms per CTA for the 2048-point kernels: 2 (two 256-thread CTAs per SM, phases overlap) or 4
+static int fft_nt() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VIP_B200_FFT_NT");
+        v = (e && atoi(e) == 4) ? 4 : 2;
+    }
+    return v;
+}
+
 size_t derotate_scratch_bytes_per_frame(int S, int N) {
     return ((size_t)(S + 1) * N + (size_t)S * N) * sizeof(float2);
 }
@@ -690,7 +708,10 @@ int derotate_run(const float* in, float* out, int nframes, const RotParams& g, c
             switch (g.N) {
                 case 512:  rc = launch_fft_chunk<512, 8>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
                 case 1024: rc = launch_fft_chunk<1024, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
-                case 2048: rc = launch_fft_chunk<2048, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
+                case 2048:
+                    if (fft_nt() == 2) rc = launch_fft_chunk<2048, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    else rc = launch_fft_chunk<2048, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    break;
                 default:   rc = launch_fft_chunk<4096, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
             }
         } else {

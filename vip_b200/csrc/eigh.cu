@@ -40,11 +40,14 @@ jacobi_round_kernel(double* __restrict__ W, int n, int nblocks, int round, doubl
     // global column index of local column c (c < WB: block bi, else block bj); >= n means padding
     auto gcol = [&](int c) { return (c < WB ? bi * WB + c : bj * WB + (c - WB)); };
 
-    for (int c = 0; c < 2 * WB; ++c) {
+    // each warp streams whole columns with 8 independent loads in flight per lane
+    for (int c = warp; c < 2 * WB; c += WB) {
         const int gc = gcol(c);
         if (gc < n) {
             const double* src = W + (size_t)gc * n;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) cols[(size_t)c * n + i] = src[i];
+            double* dst = cols + (size_t)c * n;
+#pragma unroll 8
+            for (int i = lane; i < n; i += 32) dst[i] = __ldcg(src + i);
         }
     }
     __syncthreads();
@@ -56,23 +59,28 @@ jacobi_round_kernel(double* __restrict__ W, int n, int nblocks, int round, doubl
         if (gcol(ca) < n && gcol(cb) < n) {
             double* x = cols + (size_t)ca * n;
             double* y = cols + (size_t)cb * n;
-            double alpha = 0.0, beta = 0.0, gamma = 0.0;
-            for (int i = lane; i < n; i += 32) {
-                const double xv = x[i], yv = y[i];
-                alpha = fma(xv, xv, alpha);
-                beta = fma(yv, yv, beta);
-                gamma = fma(xv, yv, gamma);
+            double alpha = 0.0, beta = 0.0, gamma = 0.0, a2 = 0.0, b2 = 0.0, g2 = 0.0;
+            int i = lane;
+            for (; i + 32 < n; i += 64) {      // two independent accumulator chains
+                const double xv = x[i], yv = y[i], xw = x[i + 32], yw = y[i + 32];
+                alpha = fma(xv, xv, alpha); beta = fma(yv, yv, beta); gamma = fma(xv, yv, gamma);
+                a2 = fma(xw, xw, a2); b2 = fma(yw, yw, b2); g2 = fma(xw, yw, g2);
             }
-            alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
+            if (i < n) {
+                const double xv = x[i], yv = y[i];
+                alpha = fma(xv, xv, alpha); beta = fma(yv, yv, beta); gamma = fma(xv, yv, gamma);
+            }
+            alpha = warp_sum(alpha + a2); beta = warp_sum(beta + b2); gamma = warp_sum(gamma + g2);
             if (alpha > 0.0 && beta > 0.0 && fabs(gamma) > tol * sqrt(alpha) * sqrt(beta)) {
                 const double zeta = (beta - alpha) / (2.0 * gamma);
                 const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                 const double c = 1.0 / sqrt(1.0 + t * t);
                 const double s = c * t;
-                for (int i = lane; i < n; i += 32) {
-                    const double xv = x[i], yv = y[i];
-                    x[i] = c * xv - s * yv;
-                    y[i] = s * xv + c * yv;
+#pragma unroll 4
+                for (int j = lane; j < n; j += 32) {
+                    const double xv = x[j], yv = y[j];
+                    x[j] = c * xv - s * yv;
+                    y[j] = s * xv + c * yv;
                 }
                 ++nrot;
             }
@@ -80,11 +88,13 @@ jacobi_round_kernel(double* __restrict__ W, int n, int nblocks, int round, doubl
         __syncthreads();
     }
 
-    for (int c = 0; c < 2 * WB; ++c) {
+    for (int c = warp; c < 2 * WB; c += WB) {
         const int gc = gcol(c);
         if (gc < n) {
             double* dst = W + (size_t)gc * n;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = cols[(size_t)c * n + i];
+            const double* src = cols + (size_t)c * n;
+#pragma unroll 8
+            for (int i = lane; i < n; i += 32) __stcg(dst + i, src[i]);
         }
     }
     if (lane == 0 && nrot) atomicAdd(&state->rotations, nrot);
@@ -571,7 +581,7 @@ int eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, doubl
                   void* ws, size_t ws_bytes, int* info, int* launches, cudaStream_t st) {
     VB_REQUIRE(n >= 1 && k >= 1 && k <= n, "eigh_topk: need 1 <= k <= n");
     if (tol <= 0) tol = 1e-10;
-    if (max_iter <= 0) max_iter = 2000;
+    if (max_iter <= 0) max_iter = 400;   // beyond this the caller is better off with the Jacobi solver
     const int B = (k <= 10) ? 16 : 32;
     VB_REQUIRE(k <= 24, "eigh_topk: k=%d too large for the subspace solver (use the Jacobi solver)", k);
     VB_REQUIRE(n >= B, "eigh_topk: n=%d smaller than the block width %d (use the Jacobi solver)", n, B);
