@@ -203,7 +203,7 @@ def stage_times(cube_dev, angs, ncomp, reps=3):
     G = timed("gram_ms", lambda: kernels.gram(M))
     evals, evecs, info = timed("eigh_ms", lambda: kernels.eigh(G))
     S = torch.sqrt(evals[:ncomp])
-    Wt = (evecs[:ncomp] / S[:, None]).float().contiguous()
+    Wt = (evecs[:ncomp] / S[:, None]).contiguous()
     Cm = (evecs[:ncomp] * S[:, None]).t().float().contiguous()
     V = timed("pcs_ms", lambda: kernels.pcs(Wt, M))
     R = timed("project_subtract_ms", lambda: kernels.project_subtract(M, Cm, V))

@@ -63,9 +63,9 @@ int vb_eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, do
                      void* ws, size_t ws_bytes, int* info_host, void* stream);
 
 /* ---- principal components and projection/subtraction --------------------------------------
- * V[k x p] = Wt[k x n] . M[n x p]                                  psfsub/svd.py:451-459
+ * V[k x p] (fp32) = Wt[k x n] (fp64) . M[n x p] (fp32), accumulated in fp64   psfsub/svd.py:451-459
  * R[n x p] = M - C[n x k] . V[k x p]   (R may alias M)            psfsub/pca_fullfr.py:1728-1731 */
-int vb_pcs_f32(const float* Wt, const float* M, int k, int n, size_t p, float* V, void* stream);
+int vb_pcs_f32(const double* Wt, const float* M, int k, int n, size_t p, float* V, void* stream);
 int vb_project_subtract_f32(const float* M, const float* C, int ldc, const float* V, int k, int n,
                             size_t p, float* R, void* stream);
 /* out = a - b elementwise (reconstructed = matrix - residuals for full_output) */

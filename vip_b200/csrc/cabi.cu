@@ -27,7 +27,7 @@ size_t eigh_workspace_bytes(int n);
 int eigh_f64(const double*, int, double*, double*, int, double, void*, size_t, int*, int*, cudaStream_t);
 size_t eigh_topk_workspace_bytes(int n, int B);
 int eigh_topk_f64(const double*, int, int, double, int, double*, double*, void*, size_t, int*, int*, cudaStream_t);
-int pcs_f32(const float*, const float*, int, int, size_t, float*, int*, cudaStream_t);
+int pcs_f32(const double*, const float*, int, int, size_t, float*, int*, cudaStream_t);
 int project_subtract_f32(const float*, const float*, int, const float*, int, int, size_t, float*, int*,
                          cudaStream_t);
 int sub_f32(const float*, const float*, float*, size_t, cudaStream_t);
@@ -119,7 +119,7 @@ int vb_eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, do
     return rc;
 }
 
-int vb_pcs_f32(const float* Wt, const float* M, int k, int n, size_t p, float* V, void* stream) {
+int vb_pcs_f32(const double* Wt, const float* M, int k, int n, size_t p, float* V, void* stream) {
     int nl = 0;
     const int rc = pcs_f32(Wt, M, k, n, p, V, &nl, (cudaStream_t)stream);
     g_launches += nl;
@@ -158,7 +158,7 @@ int vb_derotate_f32(const float* in, float* out, int nframes, int S, int N, int 
                N, y0);
     RotParams g{S, N, y0, zero_masked, mask_is_nan, mask_val};
     const float2* tw = nullptr;
-    const bool pow2 = (N & (N - 1)) == 0 && N >= 512 && N <= 4096;
+    const bool pow2 = (N & (N - 1)) == 0 && N >= 512 && N <= 4096 && N == 4 * S;
     if (pow2 && !force_direct) {
         tw = twiddle_table(N);
         VB_REQUIRE(tw != nullptr, "derotate: could not build the twiddle table");

@@ -179,30 +179,7 @@ __device__ __forceinline__ void cmul(float ar, float ai, float br, float bi, flo
     ci = ar * bi + ai * br;
 }
 
-// w[k] = base^k for k = 0..15 where base^{1,2,4,8} are exact table values tw[(m * 2^b) % N]
-// (tw[j] = exp(-2 pi i j / N)); CONJ selects exp(+...).
-template <int N, bool CONJ>
-__device__ __forceinline__ void twiddle_powers(const float2* __restrict__ tw, int m, float (&wr)[16],
-                                               float (&wi)[16]) {
-    const float2 w1 = __ldg(tw + (m & (N - 1)));
-    const float2 w2 = __ldg(tw + ((2 * m) & (N - 1)));
-    const float2 w4 = __ldg(tw + ((4 * m) & (N - 1)));
-    const float2 w8 = __ldg(tw + ((8 * m) & (N - 1)));
-    const float sg = CONJ ? -1.f : 1.f;
-    wr[0] = 1.f; wi[0] = 0.f;
-    wr[1] = w1.x; wi[1] = sg * w1.y;
-    wr[2] = w2.x; wi[2] = sg * w2.y;
-    wr[4] = w4.x; wi[4] = sg * w4.y;
-    wr[8] = w8.x; wi[8] = sg * w8.y;
-    cmul(wr[1], wi[1], wr[2], wi[2], wr[3], wi[3]);
-    cmul(wr[1], wi[1], wr[4], wi[4], wr[5], wi[5]);
-    cmul(wr[2], wi[2], wr[4], wi[4], wr[6], wi[6]);
-    cmul(wr[3], wi[3], wr[4], wi[4], wr[7], wi[7]);
-#pragma unroll
-    for (int k = 1; k < 8; ++k) cmul(wr[k], wi[k], wr[8], wi[8], wr[8 + k], wi[8 + k]);
-}
-
-// exp(-2 pi i * s * k / N) / scale_den with s = s_int + s_frac, exact integer range reduction
+// exp(-2 pi i * s * k / N) with s = s_int + s_frac, exact integer range reduction
 template <int N>
 __device__ __forceinline__ void phase_of(int s_int, float s_frac, int k, float& pr, float& pi) {
     // turns = s*k/N ;  (s_int*k mod N)/N is exact, the fractional part is < 1/2 turn
@@ -218,6 +195,102 @@ __device__ __forceinline__ void transform_sync(int tr) {
     else asm volatile("bar.sync %0, %1;" ::"r"(tr + 1), "r"(T) : "memory");
 }
 
+// Inter-stage twiddles w^k, k = 0..15, for a thread-dependent base w = exp(-/+ 2 pi i m / N), applied
+// as w^(4a+b) = (w^4)^a (w)^b from six table/derived values (few live registers).
+struct Twiddle6 {
+    float b1r, b1i, b2r, b2i, b3r, b3i;   // w^1, w^2, w^3
+    float a1r, a1i, a2r, a2i, a3r, a3i;   // w^4, w^8, w^12
+    template <int N, bool CONJ>
+    __device__ __forceinline__ void load(const float2* __restrict__ tw, int m) {
+        const float2 w1 = __ldg(tw + (m & (N - 1)));
+        const float2 w2 = __ldg(tw + ((2 * m) & (N - 1)));
+        const float2 w4 = __ldg(tw + ((4 * m) & (N - 1)));
+        const float2 w8 = __ldg(tw + ((8 * m) & (N - 1)));
+        const float sg = CONJ ? -1.f : 1.f;
+        b1r = w1.x; b1i = sg * w1.y;
+        b2r = w2.x; b2i = sg * w2.y;
+        a1r = w4.x; a1i = sg * w4.y;
+        a2r = w8.x; a2i = sg * w8.y;
+        cmul(b1r, b1i, b2r, b2i, b3r, b3i);
+        cmul(a1r, a1i, a2r, a2i, a3r, a3i);
+    }
+    // (xr, xi) *= w^k, k compile-time after unrolling
+    __device__ __forceinline__ void apply(int k, float& xr, float& xi) const {
+        const int a = k >> 2, b = k & 3;
+        float tr_, ti_;
+        if (b == 1)      { cmul(xr, xi, b1r, b1i, tr_, ti_); xr = tr_; xi = ti_; }
+        else if (b == 2) { cmul(xr, xi, b2r, b2i, tr_, ti_); xr = tr_; xi = ti_; }
+        else if (b == 3) { cmul(xr, xi, b3r, b3i, tr_, ti_); xr = tr_; xi = ti_; }
+        if (a == 1)      { cmul(xr, xi, a1r, a1i, tr_, ti_); xr = tr_; xi = ti_; }
+        else if (a == 2) { cmul(xr, xi, a2r, a2i, tr_, ti_); xr = tr_; xi = ti_; }
+        else if (a == 3) { cmul(xr, xi, a3r, a3i, tr_, ti_); xr = tr_; xi = ti_; }
+    }
+};
+
+// radix-4 DFT of (x0..x3): y[a] = sum_j x_j exp(SIGN * 2 pi i j a / 4), natural order in and out
+template <int SIGN>
+__device__ __forceinline__ void dft4(float& x0r, float& x0i, float& x1r, float& x1i, float& x2r, float& x2i,
+                                     float& x3r, float& x3i) {
+    const float s0r = x0r + x2r, s0i = x0i + x2i, d0r = x0r - x2r, d0i = x0i - x2i;
+    const float s1r = x1r + x3r, s1i = x1i + x3i, d1r = x1r - x3r, d1i = x1i - x3i;
+    // SIGN * i * d1
+    const float er = -(float)SIGN * d1i, ei = (float)SIGN * d1r;
+    x0r = s0r + s1r; x0i = s0i + s1i;
+    x2r = s0r - s1r; x2i = s0i - s1i;
+    x1r = d0r + er;  x1i = d0i + ei;
+    x3r = d0r - er;  x3i = d0i - ei;
+}
+
+// Forward radix-16 DFT when only inputs 0..3 are non-zero:  y[4a+b] = sum_j (x_j w16^(-jb)) (-i)^(ja).
+// In: re/im[0..3].  Out: y[k] in register k (natural order).
+__device__ __forceinline__ void dft16_in4(float (&re)[16], float (&im)[16]) {
+    const float x0r = re[0], x0i = im[0], x1r = re[1], x1i = im[1], x2r = re[2], x2i = im[2], x3r = re[3],
+                x3i = im[3];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        float z0r = x0r, z0i = x0i, z1r, z1i, z2r, z2i, z3r, z3i;
+        // w16^(-j*b): exponents j*b in {0..9}; mul_w16<-1>(m, ...) handles m in [0,8); m = 9 -> -(m=1)
+        mul_w16<-1>((1 * b) & 7, x1r, x1i, z1r, z1i);
+        mul_w16<-1>((2 * b) & 7, x2r, x2i, z2r, z2i);
+        if (3 * b < 8) mul_w16<-1>(3 * b, x3r, x3i, z3r, z3i);
+        else { mul_w16<-1>(3 * b - 8, x3r, x3i, z3r, z3i); z3r = -z3r; z3i = -z3i; }
+        dft4<-1>(z0r, z0i, z1r, z1i, z2r, z2i, z3r, z3i);
+        re[b] = z0r; im[b] = z0i;
+        re[4 + b] = z1r; im[4 + b] = z1i;
+        re[8 + b] = z2r; im[8 + b] = z2i;
+        re[12 + b] = z3r; im[12 + b] = z3i;
+    }
+}
+
+// Inverse radix-16 DFT when only outputs 0..3 are needed:  x_j = sum_b w16^(+jb) sum_a v[4a+b] (+i)^(ja).
+// In: v[k] in register k (natural order).  Out: re/im[0..3].
+__device__ __forceinline__ void dft16_out4(float (&re)[16], float (&im)[16]) {
+    float o0r = 0.f, o0i = 0.f, o1r = 0.f, o1i = 0.f, o2r = 0.f, o2i = 0.f, o3r = 0.f, o3i = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        float u0r = re[b], u0i = im[b], u1r = re[4 + b], u1i = im[4 + b], u2r = re[8 + b], u2i = im[8 + b],
+              u3r = re[12 + b], u3i = im[12 + b];
+        dft4<+1>(u0r, u0i, u1r, u1i, u2r, u2i, u3r, u3i);      // u_j = sum_a v[4a+b] (+i)^(ja)
+        float t1r, t1i, t2r, t2i, t3r, t3i;
+        mul_w16<+1>((1 * b) & 7, u1r, u1i, t1r, t1i);
+        mul_w16<+1>((2 * b) & 7, u2r, u2i, t2r, t2i);
+        if (3 * b < 8) mul_w16<+1>(3 * b, u3r, u3i, t3r, t3i);
+        else { mul_w16<+1>(3 * b - 8, u3r, u3i, t3r, t3i); t3r = -t3r; t3i = -t3i; }
+        o0r += u0r; o0i += u0i;
+        o1r += t1r; o1i += t1i;
+        o2r += t2r; o2i += t2i;
+        o3r += t3r; o3i += t3i;
+    }
+    re[0] = o0r; im[0] = o0i; re[1] = o1r; im[1] = o1i; re[2] = o2r; im[2] = o2i; re[3] = o3r; im[3] = o3i;
+}
+
+// One 1-D shear  y = IFFT( FFT(x) * exp(-2 pi i s f) )  of length N by T = N/16 cooperating threads.
+//
+// Index convention ("re-indexed" lines): every line is stored starting at the first possibly
+// non-zero sample, i.e. position n' = n - y0 (mod N).  A circular shift commutes with the
+// (circulant) shear, so the result is the same line re-indexed the same way; with N = 4S the
+// non-zero input of passes 1/2 then lives at n' in [0, S] (thread t holds n' = t + j*T: j < 4,
+// plus the single sample n' = S owned by thread 0) and passes 2/3 only need n' in [0, S), j < 4.
 template <int N>
 struct ShearFft {
     static constexpr int T = N / 16;      // threads per transform
@@ -227,24 +300,26 @@ struct ShearFft {
     static constexpr int LOG_R3 = ilog2c(R3);
     static constexpr int LOG_L1 = ilog2c(L1);
     static constexpr int G3 = 16 / R3;    // radix-R3 butterflies per thread in stage 3
-    static constexpr int BUF = 2 * N + 8; // floats per transform buffer (re[N], im[N], stagger pad)
+    static constexpr int BUF = N + 4;     // float2 per transform buffer (+ stagger between transforms)
     static_assert(N >= 512 && N <= 4096 && (N & (N - 1)) == 0, "FFT path handles N = 512..4096");
 
-    // bank swizzles (validated conflict-free for both sides of each exchange)
+    // 64-bit shared-memory accesses are served per half-warp: 16 lanes must hit 16 distinct
+    // 8-byte banks.  XOR swizzles, validated for both sides of both exchanges (tools/fft_model.py).
     __device__ __forceinline__ static int sw1(int P) {
-        return P ^ (((P >> LOG_L1) & ((1 << (5 - LOG_R3)) - 1)) << LOG_R3);
+        if (LOG_R3 < 4) return P ^ (((P >> LOG_L1) & ((1 << (4 - LOG_R3)) - 1)) << LOG_R3);
+        return P;
     }
-    __device__ __forceinline__ static int sw2(int P) { return P ^ ((P >> 4) & 31); }
+    __device__ __forceinline__ static int sw2(int P) { return P ^ ((P >> 4) & 15); }
 
-    // In:  re/im[j] = x[t + j*T]  (j = 0..15).  Out: re/im[j] = y[t + j*T] where
-    //   y = IFFT( FFT(x) * exp(-2 pi i s f) ),  s = s_int + s_frac pixels.
-    // sre/sim: this transform's N-float exchange arrays; ph3: R3 complex per-transform phase
-    // constants in shared memory.  Must be called by all T threads of transform `tr` (named barrier tr+1).
-    __device__ __forceinline__ static void run(float (&re)[16], float (&im)[16], float* sre, float* sim,
-                                               float2* ph3, const float2* __restrict__ tw, int t,
-                                               int tr, int s_int, float s_frac) {
-        float wr[16], wi[16];
+    // IN4 : only re/im[0..3] (n' = t + j*T, j < 4) and the sample n' = 4T (x4, thread 0) are non-zero.
+    // OUT4: only outputs j < 4 are produced (re/im[0..3]).
+    // Otherwise re/im[j] <-> n' = t + j*T for j = 0..15 on input and output.
+    template <bool IN4, bool OUT4>
+    __device__ __forceinline__ static void run(float (&re)[16], float (&im)[16], float2* buf, float2* ph3,
+                                               const float2* __restrict__ tw, int t, int tr, int s_int,
+                                               float s_frac, float x4r, float x4i) {
         const int npp = t & (L2 - 1), k1p = t >> LOG_R3;
+        Twiddle6 w;
 
         // per-transform constants: exp(-2 pi i s f(256*k3)) / N, f wraps to negative for k3 >= R3/2
         if (t < R3) {
@@ -256,41 +331,49 @@ struct ShearFft {
             ph3[t] = make_float2(pr * (1.0f / N), pi * (1.0f / N));
         }
 
-        // ---- forward stage 1: radix-16 over x[t + j*T]
-        dif<16, -1, 0>(re, im);
-        twiddle_powers<N, false>(tw, t, wr, wi);
+        // ---- forward stage 1: radix-16 over n' = t + j*T; result y[k1] -> position k1*L1 + t
+        if (IN4) {
+            dft16_in4(re, im);
+            if (t == 0) {   // the lone sample at n' = 4T adds x4 * (-i)^k1 to every output of thread 0
+#pragma unroll
+                for (int k1 = 0; k1 < 16; ++k1) {
+                    const int q = k1 & 3;
+                    re[k1] += (q == 0) ? x4r : (q == 1) ? x4i : (q == 2) ? -x4r : -x4i;
+                    im[k1] += (q == 0) ? x4i : (q == 1) ? -x4r : (q == 2) ? -x4i : x4r;
+                }
+            }
+        } else {
+            dif<16, -1, 0>(re, im);
+        }
+        w.load<N, false>(tw, t);
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) {
-            const int r = brev(k1, 4);
-            float yr, yi;
-            cmul(re[r], im[r], wr[k1], wi[k1], yr, yi);
-            const int a = sw1(k1 * L1 + t);
-            sre[a] = yr; sim[a] = yi;
+            const int r = IN4 ? k1 : brev(k1, 4);
+            w.apply(k1, re[r], im[r]);
+            buf[sw1(k1 * L1 + t)] = make_float2(re[r], im[r]);
         }
         transform_sync<T>(tr);
         // ---- forward stage 2: radix-16 inside each length-L1 block
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const int a = sw1(k1p * L1 + j * L2 + npp);
-            re[j] = sre[a]; im[j] = sim[a];
+            const float2 v = buf[sw1(k1p * L1 + j * L2 + npp)];
+            re[j] = v.x; im[j] = v.y;
         }
         dif<16, -1, 0>(re, im);
-        twiddle_powers<N, false>(tw, npp * 16, wr, wi);
+        w.load<N, false>(tw, npp * 16);
         transform_sync<T>(tr);
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) {
             const int r = brev(k2, 4);
-            float yr, yi;
-            cmul(re[r], im[r], wr[k2], wi[k2], yr, yi);
-            const int a = sw2(k1p * L1 + k2 * L2 + npp);
-            sre[a] = yr; sim[a] = yi;
+            w.apply(k2, re[r], im[r]);
+            buf[sw2(k1p * L1 + k2 * L2 + npp)] = make_float2(re[r], im[r]);
         }
         transform_sync<T>(tr);
         // ---- forward stage 3: radix-R3 on 16 contiguous points, phase, inverse stage 3
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-            const int a = sw2(16 * t + e);
-            re[e] = sre[a]; im[e] = sim[a];
+            const float2 v = buf[sw2(16 * t + e)];
+            re[e] = v.x; im[e] = v.y;
         }
         GroupFft<R3, -1, G3>::fwd(re, im);
 #pragma unroll
@@ -312,48 +395,47 @@ struct ShearFft {
         GroupFft<R3, +1, G3>::inv(re, im);
         transform_sync<T>(tr);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const int a = sw2(16 * t + e);
-            sre[a] = re[e]; sim[a] = im[e];
-        }
+        for (int e = 0; e < 16; ++e) buf[sw2(16 * t + e)] = make_float2(re[e], im[e]);
         transform_sync<T>(tr);
         // ---- inverse stage 2
-        twiddle_powers<N, true>(tw, npp * 16, wr, wi);
+        w.load<N, true>(tw, npp * 16);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const int a = sw2(k1p * L1 + j * L2 + npp);
+            const float2 v = buf[sw2(k1p * L1 + j * L2 + npp)];
             const int r = brev(j, 4);
-            cmul(sre[a], sim[a], wr[j], wi[j], re[r], im[r]);
+            re[r] = v.x; im[r] = v.y;
+            w.apply(j, re[r], im[r]);
         }
         dit<16, +1, 0>(re, im);
         transform_sync<T>(tr);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int a = sw1(k1p * L1 + j * L2 + npp);
-            sre[a] = re[j]; sim[a] = im[j];
-        }
+        for (int j = 0; j < 16; ++j) buf[sw1(k1p * L1 + j * L2 + npp)] = make_float2(re[j], im[j]);
         transform_sync<T>(tr);
         // ---- inverse stage 1
-        twiddle_powers<N, true>(tw, t, wr, wi);
+        w.load<N, true>(tw, t);
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) {
-            const int a = sw1(k1 * L1 + t);
-            const int r = brev(k1, 4);
-            cmul(sre[a], sim[a], wr[k1], wi[k1], re[r], im[r]);
+            const float2 v = buf[sw1(k1 * L1 + t)];
+            const int r = OUT4 ? k1 : brev(k1, 4);
+            re[r] = v.x; im[r] = v.y;
+            w.apply(k1, re[r], im[r]);
         }
-        dit<16, +1, 0>(re, im);
-        // caller must __syncthreads() before reusing sre/sim
+        if (OUT4) dft16_out4(re, im);
+        else dit<16, +1, 0>(re, im);
+        // callers that reuse `buf` must synchronise first
     }
 };
 
-// ---- pass 1: rows [y0, y0+S], real gathered input -> T1[(S+1) x N] complex
-template <int N, int NT>
-__global__ void __launch_bounds__(NT * N / 16)
+// Column label n' of the re-indexed planes T1/T2 <-> physical plane column (n' + y0) mod N.
+
+// ---- pass 1: rows [y0, y0+S], real gathered input -> T1[(S+1) x N] complex (re-indexed columns)
+template <int N, int NT, int MINB>
+__global__ void __launch_bounds__(NT * N / 16, MINB)
 shear_rows_first_fft(const float* __restrict__ in, float2* __restrict__ T1, RotParams g,
                      const int* __restrict__ krot, const double* __restrict__ a_coef,
                      const float2* __restrict__ tw, int frame0) {
     using F = ShearFft<N>;
-    extern __shared__ float smem[];
+    extern __shared__ float2 smem2[];
     __shared__ float2 ph3s[NT][16];
     const int tr = threadIdx.x / F::T, t = threadIdx.x % F::T;
     const int fl = blockIdx.y, f = frame0 + fl;
@@ -364,15 +446,14 @@ shear_rows_first_fft(const float* __restrict__ in, float2* __restrict__ T1, RotP
     const float* frame = in + (size_t)f * g.S * g.S;
     float re[16], im[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int n = t + j * F::T;
-        re[j] = (valid && n >= g.y0 && n <= g.y0 + g.S) ? plane_sample(frame, g, k, i, n) : 0.f;
+    for (int j = 0; j < 4; ++j) {
+        re[j] = valid ? plane_sample(frame, g, k, i, g.y0 + t + j * F::T) : 0.f;
         im[j] = 0.f;
     }
+    const float x4 = (valid && t == 0) ? plane_sample(frame, g, k, i, g.y0 + g.S) : 0.f;
     int s_int; float s_frac;
     split_shift(a_coef[f] * (double)(i - N / 2), s_int, s_frac);
-    float* sre = smem + tr * F::BUF;
-    F::run(re, im, sre, sre + N, ph3s[tr], tw, t, tr, s_int, s_frac);
+    F::template run<true, false>(re, im, smem2 + tr * F::BUF, ph3s[tr], tw, t, tr, s_int, s_frac, x4, 0.f);
     if (valid) {
         float2* dst = T1 + ((size_t)fl * (g.S + 1) + row) * N;
 #pragma unroll
@@ -380,70 +461,56 @@ shear_rows_first_fft(const float* __restrict__ in, float2* __restrict__ T1, RotP
     }
 }
 
-// ---- pass 2: all N columns; input rows [y0, y0+S] of T1, output rows [y0, y0+S) -> T2[S x N]
-template <int N, int NT>
-__global__ void __launch_bounds__(NT * N / 16)
+// ---- pass 2: all N columns; input rows [0, S] of T1, output rows [0, S) -> T2[S x N]
+template <int N, int NT, int MINB>
+__global__ void __launch_bounds__(NT * N / 16, MINB)
 shear_cols_fft(const float2* __restrict__ T1, float2* __restrict__ T2, RotParams g,
                const double* __restrict__ b_coef, const float2* __restrict__ tw, int frame0) {
     using F = ShearFft<N>;
-    extern __shared__ float smem[];
+    extern __shared__ float2 smem2[];
     __shared__ float2 ph3s[NT][16];
     const int tr = threadIdx.x / F::T, t = threadIdx.x % F::T;
     const int fl = blockIdx.y, f = frame0 + fl;
     const int c0 = blockIdx.x * NT;
-    // stage the (S+1) x NT slab with columns fastest (32-byte global segments)
+    // stage the (S+1) x NT slab with columns fastest (NT*8-byte global segments)
     const float2* src = T1 + (size_t)fl * (g.S + 1) * N + c0;
     for (int idx = threadIdx.x; idx < (g.S + 1) * NT; idx += blockDim.x) {
         const int row = idx / NT, col = idx % NT;
-        const float2 v = src[(size_t)row * N + col];
-        float* b = smem + col * F::BUF;
-        const int a = F::sw1(g.y0 + row);
-        b[a] = v.x; b[N + a] = v.y;
+        smem2[col * F::BUF + F::sw1(row)] = src[(size_t)row * N + col];
     }
     __syncthreads();
-    float* sre = smem + tr * F::BUF;
+    float2* buf = smem2 + tr * F::BUF;
     float re[16], im[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int n = t + j * F::T;
-        if (n >= g.y0 && n <= g.y0 + g.S) {
-            const int a = F::sw1(n);
-            re[j] = sre[a]; im[j] = sre[N + a];
-        } else {
-            re[j] = 0.f; im[j] = 0.f;
-        }
+    for (int j = 0; j < 4; ++j) {
+        const float2 v = buf[F::sw1(t + j * F::T)];
+        re[j] = v.x; im[j] = v.y;
     }
+    const float2 v4 = buf[F::sw1(4 * F::T)];   // row S (only thread 0 uses it)
     __syncthreads();
     int s_int; float s_frac;
-    split_shift(b_coef[f] * (double)(c0 + tr - N / 2), s_int, s_frac);
-    F::run(re, im, sre, sre + N, ph3s[tr], tw, t, tr, s_int, s_frac);
+    const int col_phys = (c0 + tr + g.y0) & (N - 1);
+    split_shift(b_coef[f] * (double)(col_phys - N / 2), s_int, s_frac);
+    F::template run<true, true>(re, im, buf, ph3s[tr], tw, t, tr, s_int, s_frac, v4.x, v4.y);
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int n = t + j * F::T;
-        if (n >= g.y0 && n < g.y0 + g.S) {
-            const int a = F::sw1(n);
-            sre[a] = re[j]; sre[N + a] = im[j];
-        }
-    }
+    for (int j = 0; j < 4; ++j) buf[F::sw1(t + j * F::T)] = make_float2(re[j], im[j]);
     __syncthreads();
     float2* dst = T2 + (size_t)fl * g.S * N + c0;
     for (int idx = threadIdx.x; idx < g.S * NT; idx += blockDim.x) {
         const int row = idx / NT, col = idx % NT;
-        const float* b = smem + col * F::BUF;
-        const int a = F::sw1(g.y0 + row);
-        dst[(size_t)row * N + col] = make_float2(b[a], b[N + a]);
+        dst[(size_t)row * N + col] = smem2[col * F::BUF + F::sw1(row)];
     }
 }
 
-// ---- pass 3: rows [y0, y0+S); real part of columns [y0, y0+S) -> out, mask restored
-template <int N, int NT>
-__global__ void __launch_bounds__(NT * N / 16)
+// ---- pass 3: rows [0, S); real part of columns n' in [0, S) -> out, mask restored
+template <int N, int NT, int MINB>
+__global__ void __launch_bounds__(NT * N / 16, MINB)
 shear_rows_last_fft(const float2* __restrict__ T2, const float* __restrict__ in, float* __restrict__ out,
                     RotParams g, const double* __restrict__ a_coef, const float2* __restrict__ tw,
                     int frame0) {
     using F = ShearFft<N>;
-    extern __shared__ float smem[];
+    extern __shared__ float2 smem2[];
     __shared__ float2 ph3s[NT][16];
     const int tr = threadIdx.x / F::T, t = threadIdx.x % F::T;
     const int fl = blockIdx.y, f = frame0 + fl;
@@ -464,15 +531,14 @@ shear_rows_last_fft(const float2* __restrict__ T2, const float* __restrict__ in,
     }
     int s_int; float s_frac;
     split_shift(a_coef[f] * (double)(i - N / 2), s_int, s_frac);
-    float* sre = smem + tr * F::BUF;
-    F::run(re, im, sre, sre + N, ph3s[tr], tw, t, tr, s_int, s_frac);
+    F::template run<false, true>(re, im, smem2 + tr * F::BUF, ph3s[tr], tw, t, tr, s_int, s_frac, 0.f, 0.f);
     if (valid) {
         const float* src = in + ((size_t)f * g.S + row) * g.S;
         float* dst = out + ((size_t)f * g.S + row) * g.S;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int x = t + j * F::T - g.y0;
-            if (x >= 0 && x < g.S) dst[x] = is_masked(__ldg(src + x), g) ? g.mask_val : re[j];
+        for (int j = 0; j < 4; ++j) {
+            const int x = t + j * F::T;     // < S = 4T
+            dst[x] = is_masked(__ldg(src + x), g) ? g.mask_val : re[j];
         }
     }
 }
@@ -617,32 +683,32 @@ int profile_read(float* out) {
     return 0;
 }
 
-template <int N, int NT>
+template <int N, int NT, int MINB>
 static int launch_fft_chunk(const float* in, float* out, float2* T1, float2* T2, const RotParams& g,
                             const int* krot, const double* a, const double* b, const float2* tw,
                             int frame0, int nf, cudaStream_t st) {
     using F = ShearFft<N>;
-    const size_t smem = (size_t)NT * F::BUF * sizeof(float);
+    const size_t smem = (size_t)NT * F::BUF * sizeof(float2);
     static bool configured = false;
     if (!configured) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_first_fft<N, NT>,
+        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_first_fft<N, NT, MINB>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_cols_fft<N, NT>,
+        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_cols_fft<N, NT, MINB>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_last_fft<N, NT>,
+        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_last_fft<N, NT, MINB>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const int threads = NT * F::T;
     g_timer.mark(st);
-    shear_rows_first_fft<N, NT><<<dim3(ceil_div(g.S + 1, NT), nf), threads, smem, st>>>(
+    shear_rows_first_fft<N, NT, MINB><<<dim3(ceil_div(g.S + 1, NT), nf), threads, smem, st>>>(
         in, T1, g, krot, a, tw, frame0);
     VB_CHECK_LAUNCH();
     g_timer.mark(st);
-    shear_cols_fft<N, NT><<<dim3(N / NT, nf), threads, smem, st>>>(T1, T2, g, b, tw, frame0);
+    shear_cols_fft<N, NT, MINB><<<dim3(N / NT, nf), threads, smem, st>>>(T1, T2, g, b, tw, frame0);
     VB_CHECK_LAUNCH();
     g_timer.mark(st);
-    shear_rows_last_fft<N, NT><<<dim3(ceil_div(g.S, NT), nf), threads, smem, st>>>(
+    shear_rows_last_fft<N, NT, MINB><<<dim3(ceil_div(g.S, NT), nf), threads, smem, st>>>(
         T2, in, out, g, a, tw, frame0);
     VB_CHECK_LAUNCH();
     g_timer.mark(st);
@@ -679,7 +745,7 @@ static int fft_nt() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("VIP_B200_FFT_NT");
-        v = (e && atoi(e) == 4) ? 4 : 2;
+        v = e ? atoi(e) : 2;   // 2: NT=2 x 2 CTAs/SM (default); 3: NT=2, 85-register cap, 3 CTAs/SM; 4: NT=4
     }
     return v;
 }
@@ -699,20 +765,22 @@ int derotate_run(const float* in, float* out, int nframes, const RotParams& g, c
     if (chunk > 65535) chunk = 65535;
     float2* T1 = reinterpret_cast<float2*>(scratch);
     float2* T2 = T1 + (size_t)chunk * (g.S + 1) * g.N;
-    const bool pow2 = (g.N & (g.N - 1)) == 0 && g.N >= 512 && g.N <= 4096;
+    // the FFT kernels assume the exact 4x plane of power-of-two frames (N = 4S)
+    const bool pow2 = (g.N & (g.N - 1)) == 0 && g.N >= 512 && g.N <= 4096 && g.N == 4 * g.S;
     int nl = 0;
     for (int f0 = 0; f0 < nframes; f0 += chunk) {
         const int nf = (nframes - f0 < chunk) ? nframes - f0 : chunk;
         int rc;
         if (pow2 && !force_direct) {
             switch (g.N) {
-                case 512:  rc = launch_fft_chunk<512, 8>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
-                case 1024: rc = launch_fft_chunk<1024, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
+                case 512:  rc = launch_fft_chunk<512, 8, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
+                case 1024: rc = launch_fft_chunk<1024, 4, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
                 case 2048:
-                    if (fft_nt() == 2) rc = launch_fft_chunk<2048, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
-                    else rc = launch_fft_chunk<2048, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    if (fft_nt() == 4) rc = launch_fft_chunk<2048, 4, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    else if (fft_nt() == 3) rc = launch_fft_chunk<2048, 2, 3>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    else rc = launch_fft_chunk<2048, 2, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     break;
-                default:   rc = launch_fft_chunk<4096, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
+                default:   rc = launch_fft_chunk<4096, 2, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
             }
         } else {
             rc = launch_direct_chunk(in, out, T1, T2, g, krot, a, b, f0, nf, st);

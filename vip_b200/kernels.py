@@ -88,8 +88,9 @@ def topk_supported(n, k):
 
 
 def pcs(Wt, M):
-    """V (k,p) = Wt (k,n) . M (n,p), fp32."""
+    """V (k,p) fp32 = Wt (k,n) . M (n,p); Wt is used in fp64 and the sum is accumulated in fp64."""
     lib = _cabi.lib()
+    Wt = Wt.to(torch.float64).contiguous()
     k, n = Wt.shape
     n2, p = M.shape
     assert n == n2

@@ -49,7 +49,7 @@ class Decomposition:
         """V (ncomp,p) fp32: right singular vectors = diag(1/s) U_k M."""
         self.check_rank(ncomp)
         s = self.S[:ncomp]
-        Wt = (self.U[:ncomp] / s[:, None]).to(torch.float32).contiguous()
+        Wt = (self.U[:ncomp] / s[:, None]).contiguous()          # fp64: see csrc/proj.cu
         return kernels.pcs(Wt, self.M)
 
     def coeffs(self, ncomp):
@@ -70,7 +70,7 @@ def orthonormalize(Yt):
         evals, evecs, _ = kernels.eigh(G)
         keep = evals > evals[0] * 1e-30
         Wt = (evecs / torch.sqrt(torch.clamp(evals, min=1e-300))[:, None])[keep]
-        Yt = kernels.pcs(Wt.to(torch.float32).contiguous(), Yt)
+        Yt = kernels.pcs(Wt.contiguous(), Yt)
     return Yt
 
 
@@ -84,11 +84,11 @@ def randomized_pcs(M, ncomp, omega, n_iter=2):
     Yt = kernels.pcs(Om.t().contiguous(), M)                    # (l,p) = omega^T M
     for _ in range(n_iter):
         Z = kernels.cross_gram(Yt, M)                            # (l,n) = Y^T M^T
-        Yt = kernels.pcs(Z.to(torch.float32).contiguous(), M)    # (l,p)
+        Yt = kernels.pcs(Z.contiguous(), M)                      # (l,p)
     Qt = orthonormalize(Yt)
     B = kernels.cross_gram(Qt, M)                                # (l,n) fp64
     evals, evecs, _ = kernels.eigh((B @ B.t()).contiguous())
-    Wt = evecs[:ncomp].to(torch.float32).contiguous()            # rows = leading left vectors of B
+    Wt = evecs[:ncomp].contiguous()                              # rows = leading left vectors of B
     return kernels.pcs(Wt, Qt)
 
 
