@@ -239,11 +239,19 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n, size, k, delta, seed = CONFIGS[args.config]
-    # replicas: every rank processes its own cube of the same shape (different seed) -- see DESIGN.md (e)
-    cube, angs = adi_cube(n, size, k, delta, seed=seed + rank)
+    # N > 1: ONE cube, sharded over the ranks (vip_b200/parallel.py): total work fixed -> strong scaling
+    cube, angs = adi_cube(n, size, k, delta, seed=seed)
     pinned = torch.from_numpy(cube).pin_memory()
     cube_pinned_np = pinned.numpy()
-    cube_dev = pinned.cuda()
+    if world == 1:
+        cube_dev = pinned.cuda()
+    else:
+        from vip_b200.parallel import pca_sharded, shard_bounds
+        from vip_b200 import kernels
+        pb = shard_bounds(size * size, world)
+        shard = kernels.upload_columns(cube_pinned_np.reshape(n, -1), int(pb[rank]), int(pb[rank + 1]),
+                                       torch.device("cuda", local))
+        cube_dev = None
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
@@ -252,10 +260,14 @@ def run_gpu(args):
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
     def step_dev():
-        return _adi_rdi_pca_device(cube_dev, None, angs, k, None, None, "lapack", "median", False, False)
+        if world == 1:
+            return _adi_rdi_pca_device(cube_dev, None, angs, k, None, None, "lapack", "median", False, False)
+        return pca_sharded(cube_pinned_np, angs, k, resident_shard=shard)
 
     def step_e2e():
-        return vip_b200.pca(cube_pinned_np, angs, ncomp=k, verbose=False)
+        if world == 1:
+            return vip_b200.pca(cube_pinned_np, angs, ncomp=k, verbose=False)
+        return pca_sharded(cube_pinned_np, angs, k)
 
     def barrier():
         if world > 1:
@@ -288,24 +300,28 @@ def run_gpu(args):
         ms_e2e = timed(step_e2e, args.steps)
     clocks = clk.summary()
 
-    frames_total = n * world
+    frames_total = n          # one cube per step, whatever the number of GPUs
     value = frames_total * args.steps / (ms_dev * 1e-3)
     e2e_value = frames_total * args.steps / (ms_e2e * 1e-3)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (Gramian/eigensolve in f64)",
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+            "dtype": "f32 (Gramian/eigensolve in f64)",
             "data": "synthetic",
             "config": {"workload": workload_name(args.config),
                        "l2_policy": f"inputs larger than L2 ({cube.nbytes / 1e6:.0f} MB cube vs 126 MB L2)",
-                       "multi_gpu": "one independent cube per rank (replicas, no data-path collective)"
-                       if world > 1 else "single GPU"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(cube.nbytes * world),
-                    "d2h_bytes_per_step": int(size * size * 4 * world), "ms_per_step": ms_e2e / args.steps},
+                       "multi_gpu": ("one cube sharded over the ranks: pixel shards -> all-reduce(Gramian) -> "
+                                     "all-to-all to frame shards -> derotate -> all-to-all to pixel shards -> "
+                                     "median -> gather (NCCL)") if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(cube.nbytes),
+                    "d2h_bytes_per_step": int(size * size * 4), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
             "clocks": clocks}
 
-    if rank == 0:
+    if rank == 0 and world > 1:
+        print(json.dumps(line))
+    if rank == 0 and world == 1:
         st = stage_times(cube_dev, angs, k)
         p = size * size
         derot_ms = st["derotate_ms"]

@@ -109,6 +109,11 @@ int vb_annular_weights_f64(const double* G, const double* Gt, int n, const int* 
 int vb_gather_columns_f32(const float* src, int n, size_t p, const int* cols, int npx, float* dst, void* stream);
 int vb_scatter_columns_f32(const float* src, int n, int npx, const int* cols, size_t p, float* dst, void* stream);
 
+/* ---- host -> device upload of a pixel shard (strided rows of the host cube), one DMA ---------------
+ * dst[r][0..width) = src_host[r][0..width) for r < height, pitches in bytes (cudaMemcpy2DAsync). */
+int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitch, size_t width_bytes,
+                    size_t height, void* stream);
+
 /* ---- measurement hook (bench.py) ----------------------------------------------------------
  * vb_profile_enable(1): CUDA events are recorded around each of the three shear kernels of
  * vb_derotate_f32 on its stream; vb_profile_read(out4_host) synchronises on them and returns the

@@ -398,3 +398,27 @@ def test_pca_annular_errors(vb, golden_inputs):
         vb.pca_annular(cube, angs, ncomp=2, asize=6, delta_rot=500, verbose=False)
     with pytest.raises(NotImplementedError):
         vb.pca_annular(cube, angs, ncomp="auto", asize=6, verbose=False)
+
+
+# ------------------------------------------------------------------ sharded driver on one GPU
+def test_upload_columns_and_sharded_world1(vb, golden_inputs):
+    """The sharded driver with the CUDA ops on a 1-rank NCCL group equals pca(); the strided 2-D
+    upload equals the numpy slice."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from vip_b200 import kernels
+    from vip_b200.parallel import pca_sharded
+    cube, angs = golden_inputs["small"]
+    flat = cube.reshape(cube.shape[0], -1)
+    got = kernels.upload_columns(flat, 100, 777, torch.device("cuda")).cpu().numpy()
+    np.testing.assert_array_equal(got, flat[:, 100:777])
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        fr = pca_sharded(cube, angs, 4)
+    finally:
+        dist.destroy_process_group()
+    ref = vb.pca(cube, angs, ncomp=4, verbose=False)
+    assert rel_err(fr, ref) < 1e-5

@@ -1,0 +1,87 @@
+"""Communication logic of the sharded PCA (vip_b200/parallel.py) on CPU: gloo backend, world_size 2
+and 3, with a numpy test double for the arithmetic (the product itself only computes on the GPU).
+The sharded result must equal the single-process oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import vip_oracle as O
+from tools.synth import adi_cube
+from vip_b200.parallel import pca_sharded, shard_bounds
+
+
+class NumpyOps:
+    """Test double: the oracle's arithmetic on CPU tensors (tests only)."""
+    name = "numpy-test-double"
+
+    def upload_pixels(self, host2d, c0, c1, device):
+        return torch.from_numpy(np.ascontiguousarray(host2d[:, c0:c1], dtype=np.float32))
+
+    def gram(self, M):
+        m = M.numpy().astype(np.float64)
+        return torch.from_numpy(m @ m.T)
+
+    def leading_eig(self, G, k):
+        w, v = np.linalg.eigh(G.numpy())
+        return (torch.from_numpy(np.ascontiguousarray(w[::-1][:k])),
+                torch.from_numpy(np.ascontiguousarray(v[:, ::-1][:, :k].T)))
+
+    def pcs(self, Wt, M):
+        return torch.from_numpy((Wt.numpy() @ M.numpy().astype(np.float64)).astype(np.float32))
+
+    def project_subtract(self, M, Cm, V):
+        return torch.from_numpy(M.numpy() - Cm.numpy() @ V.numpy())
+
+    def derotate(self, cube, angles):
+        return torch.from_numpy(O.cube_derotate(cube.numpy(), -np.asarray(angles)))
+
+    def collapse(self, cube2d, mode):
+        n, p = cube2d.shape
+        return torch.from_numpy(O.cube_collapse(cube2d.numpy().reshape(n, 1, p), mode).reshape(p))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, collapse, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cube, angs = adi_cube(11, 20, 3, 70.0, seed=2)     # 11 frames / 400 px: uneven shards
+        frame, der, (f0, f1) = pca_sharded(cube, angs, 3, collapse=collapse, ops=NumpyOps(),
+                                           device=torch.device("cpu"), full_output=True)
+        assert der.shape[0] == f1 - f0
+        if rank == 0:
+            np.save(out, frame)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,collapse", [(2, "median"), (3, "mean")])
+def test_sharded_pca_matches_single_process(tmp_path, world, collapse):
+    out = str(tmp_path / "frame.npy")
+    mp.spawn(_worker, args=(world, _free_port(), collapse, out), nprocs=world, join=True)
+    frame = np.load(out)
+    cube, angs = adi_cube(11, 20, 3, 70.0, seed=2)
+    ref = O.pca_fullframe(cube, angs, ncomp=3, collapse=collapse)
+    assert frame.shape == ref.shape
+    assert np.max(np.abs(frame - ref)) < 3e-4 * np.max(np.abs(ref))
+
+
+def test_shard_bounds():
+    assert list(shard_bounds(10, 3)) == [0, 4, 7, 10]
+    assert list(shard_bounds(8, 8)) == list(range(9))
+    assert list(shard_bounds(3, 4)) == [0, 1, 2, 3, 3]       # empty last shard
+    b = shard_bounds(262144, 8)
+    assert b[-1] == 262144 and len(set(np.diff(b))) == 1

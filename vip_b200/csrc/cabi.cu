@@ -194,6 +194,13 @@ int vb_scatter_columns_f32(const float* src, int n, int npx, const int* cols, si
     return scatter_columns(src, n, npx, cols, p, dst, (cudaStream_t)stream);
 }
 
+int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitch, size_t width_bytes,
+                    size_t height, void* stream) {
+    VB_CHECK_CUDA(cudaMemcpy2DAsync(dst, dpitch, src_host, spitch, width_bytes, height, cudaMemcpyHostToDevice,
+                                    (cudaStream_t)stream));
+    return 0;
+}
+
 void vb_profile_enable(int on) { profile_enable(on); }
 int vb_profile_read(float* out4_host) { return profile_read(out4_host); }
 

@@ -189,3 +189,15 @@ def annular_weights(G, idx, lens, frames, ncomp, tol=0.0, max_iter=0):
                                            int(ncomp), float(tol), int(max_iter), ptr(W), ptr(iters),
                                            stream_ptr()), "vb_annular_weights_f64")
     return W, iters
+
+
+def upload_columns(host2d, c0, c1, device):
+    """Columns [c0, c1) of a C-contiguous fp32 host matrix -> contiguous (n, c1-c0) CUDA tensor (one 2-D DMA)."""
+    lib = _cabi.lib()
+    assert host2d.dtype == np.float32 and host2d.flags["C_CONTIGUOUS"] and host2d.ndim == 2
+    n, p = host2d.shape
+    out = empty((n, c1 - c0), torch.float32, device)
+    src = host2d.ctypes.data + c0 * 4
+    _cabi.check(lib.vb_memcpy2d_h2d(ptr(out), (c1 - c0) * 4, src, p * 4, (c1 - c0) * 4, n, stream_ptr()),
+                "vb_memcpy2d_h2d")
+    return out

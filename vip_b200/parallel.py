@@ -1,0 +1,162 @@
+"""Single-cube PCA sharded over the GPUs of one node (one process per GPU, ``torch.distributed``).
+
+SURVEY.md 8(e): the path shards with two real exchange steps and no other communication.
+
+    pixel shards  M[:, p_g]   --  G_g = M_g M_g^T  --all-reduce(sum, fp64 n x n)-->  G
+                                  top-k eigenpairs of G (replicated, broadcast from rank 0)
+                                  V_g = Wt M_g ,  R_g = M_g - C V_g                 (local)
+    all-to-all #1 (pixel -> frame shards):   R[f_g, :]
+                                  derotate own frames                               (local)
+    all-to-all #2 (frame -> pixel shards):   D[:, p_g]
+                                  collapse own pixels, gather the frame on rank 0
+
+The reference has no distributed mode (its ``nproc`` forks processes over frames,
+``preproc/derotation.py:392-397``); this module is new functionality behind the same ``pca`` semantics
+(3-d ADI cube, integer ``ncomp``, deterministic ``svd_mode``).
+
+The arithmetic goes through an ``ops`` object: :class:`CudaOps` (the CUDA kernels of this package) by
+default.  The CPU tests of the communication logic (``tests/test_parallel_gloo.py``, gloo backend,
+world_size 2) pass a numpy test double instead -- the product never computes on the CPU.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import kernels
+from .preproc.derotation import derotate_device
+from .preproc.parangles import check_pa_vector
+from .preproc.subsampling import collapse_device
+
+
+def shard_bounds(total, world):
+    """Contiguous, near-equal shards: returns world+1 offsets."""
+    base, rem = divmod(total, world)
+    sizes = [base + (1 if r < rem else 0) for r in range(world)]
+    return np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+
+
+class CudaOps:
+    """The CUDA kernels behind the distributed driver (all tensors are CUDA tensors)."""
+
+    name = "cuda"
+
+    def upload_pixels(self, host2d, c0, c1, device):
+        if host2d.dtype == np.float32 and host2d.flags["C_CONTIGUOUS"]:
+            return kernels.upload_columns(host2d, c0, c1, device)          # one strided DMA
+        return torch.from_numpy(np.ascontiguousarray(host2d[:, c0:c1], dtype=np.float32)).to(device)
+
+    def gram(self, M):
+        return kernels.gram(M)
+
+    def leading_eig(self, G, k):
+        n = G.shape[0]
+        if kernels.topk_supported(n, k):
+            evals, evecs, info = kernels.eigh_topk(G, k)
+            if info["converged"]:
+                return evals, evecs
+        evals, evecs, _ = kernels.eigh(G)
+        return evals[:k].contiguous(), evecs[:k].contiguous()
+
+    def pcs(self, Wt, M):
+        return kernels.pcs(Wt, M)
+
+    def project_subtract(self, M, Cm, V):
+        return kernels.project_subtract(M, Cm, V)
+
+    def derotate(self, cube, angles):
+        return derotate_device(cube, angles)
+
+    def collapse(self, cube2d, mode):
+        n, p = cube2d.shape
+        return collapse_device(cube2d.reshape(n, 1, p), mode).reshape(p)
+
+
+def _all_to_all(send, recv, group):
+    """Exchange lists of tensors (uneven sizes allowed)."""
+    try:
+        dist.all_to_all(recv, send, group=group)
+    except (RuntimeError, NotImplementedError):
+        # backends without all_to_all (older gloo): pairwise exchange
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        recv[rank].copy_(send[rank])
+        reqs = []
+        for peer in range(world):
+            if peer != rank:
+                reqs.append(dist.isend(send[peer], dst=dist.get_global_rank(group, peer) if group else peer,
+                                       group=group))
+                reqs.append(dist.irecv(recv[peer], src=dist.get_global_rank(group, peer) if group else peer,
+                                       group=group))
+        for r in reqs:
+            r.wait()
+
+
+def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None, device=None,
+                full_output=False, resident_shard=None):
+    """Full-frame ADI PCA of ONE cube, sharded over the ranks of ``group``.
+
+    ``cube`` (n,H,W) is the host array, visible on every rank (each rank uploads only its pixel
+    shard).  Returns the final frame (H,W) as a numpy array on rank 0 and ``None`` elsewhere; with
+    ``full_output`` every rank additionally returns its own (frames, H, W) derotated residual shard
+    as a device tensor and the frame offsets.  ``resident_shard``: this rank's pixel shard already on
+    the device (skips the upload; used by bench.py for the device-resident number)."""
+    if cube.ndim != 3:
+        raise TypeError("Input array is not a cube or 3d array")
+    ops = ops or CudaOps()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n, H, W = cube.shape
+    p = H * W
+    angle_list = check_pa_vector(np.asarray(angle_list))
+    if n != angle_list.shape[0]:
+        raise ValueError("`angle_list` vector has wrong length. It must equal the number of frames in the cube")
+    if not isinstance(ncomp, (int, np.integer)) or ncomp <= 0:
+        raise ValueError("pca_sharded needs an integer ncomp > 0")
+    ncomp = min(int(ncomp), n)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if ops.name == "cuda" else torch.device("cpu")
+
+    pb = shard_bounds(p, world)      # pixel shards
+    fb = shard_bounds(n, world)      # frame shards
+    p0, p1 = int(pb[rank]), int(pb[rank + 1])
+    f0, f1 = int(fb[rank]), int(fb[rank + 1])
+
+    # ---- pixel-sharded PCA ------------------------------------------------------------------
+    M = resident_shard if resident_shard is not None else ops.upload_pixels(cube.reshape(n, p), p0, p1, device)
+    G = ops.gram(M)
+    dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)               # exchange step 0: n x n fp64
+    evals, evecs = ops.leading_eig(G, ncomp)
+    # replicate the eigenpairs bit-identically (atomics make the solver order-dependent at 1e-16)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(evals, src=src, group=group)
+    dist.broadcast(evecs, src=src, group=group)
+    S = torch.sqrt(torch.clamp(evals, min=0.0))
+    Wt = (evecs / S[:, None]).contiguous()
+    Cm = (evecs * S[:, None]).t().to(torch.float32).contiguous()
+    V = ops.pcs(Wt, M)
+    R = ops.project_subtract(M, Cm, V)                                   # (n, p_g)
+
+    # ---- exchange 1: pixel shards -> frame shards ---------------------------------------------
+    send = [R[int(fb[h]):int(fb[h + 1])].contiguous() for h in range(world)]
+    recv = [torch.empty((f1 - f0, int(pb[h + 1] - pb[h])), dtype=R.dtype, device=device) for h in range(world)]
+    _all_to_all(send, recv, group)
+    mine = torch.cat(recv, dim=1).reshape(f1 - f0, H, W)                # my frames, all pixels
+    der = ops.derotate(mine, -angle_list[f0:f1]) if f1 > f0 else mine
+
+    # ---- exchange 2: frame shards -> pixel shards, collapse, gather --------------------------------
+    der2 = der.reshape(f1 - f0, p)
+    send = [der2[:, int(pb[h]):int(pb[h + 1])].contiguous() for h in range(world)]
+    recv = [torch.empty((int(fb[h + 1] - fb[h]), p1 - p0), dtype=der2.dtype, device=device) for h in range(world)]
+    _all_to_all(send, recv, group)
+    slab = ops.collapse(torch.cat(recv, dim=0).contiguous(), collapse)  # (p_g,)
+
+    pmax = int(np.max(np.diff(pb)))
+    padded = torch.zeros(pmax, dtype=slab.dtype, device=device)
+    padded[: p1 - p0] = slab
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)
+    frame = None
+    if rank == 0:
+        frame = torch.cat([gathered[h][: int(pb[h + 1] - pb[h])] for h in range(world)]).reshape(H, W)
+        frame = frame.cpu().numpy()
+    if full_output:
+        return frame, der, (f0, f1)
+    return frame
