@@ -109,6 +109,15 @@ int vb_annular_weights_f64(const double* G, const double* Gt, int n, const int* 
 int vb_gather_columns_f32(const float* src, int n, size_t p, const int* cols, int npx, float* dst, void* stream);
 int vb_scatter_columns_f32(const float* src, int n, int npx, const int* cols, size_t p, float* dst, void* stream);
 
+/* ---- batched fp32 GEMM ---------------------------------------------------------------------------
+ * C[b] (M x N, ldc) = alpha * A[ia] (M x K, lda) * op(B[ib]) + beta * C[b]   for b < batch, with
+ * ia = a_mod ? b % a_mod : b  (same for ib): operators that depend on the spectral channel only are
+ * shared across ADI frames.  trans_b = 0: B is K x N row-major; 1: B is N x K row-major (C = A B^T).
+ * Replaces: the FFT zoom of scale_fft, as  Re(L X L^T)            preproc/rescaling.py:1114-1217 */
+int vb_gemm_f32(const float* A, long long lda, long long strideA, int a_mod, const float* B, long long ldb,
+                long long strideB, int b_mod, int trans_b, float* C, long long ldc, long long strideC, int M,
+                int N, int K, float alpha, float beta, int batch, void* stream);
+
 /* ---- host -> device upload of a pixel shard (strided rows of the host cube), one DMA ---------------
  * dst[r][0..width) = src_host[r][0..width) for r < height, pitches in bytes (cudaMemcpy2DAsync). */
 int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitch, size_t width_bytes,

@@ -36,7 +36,26 @@ def golden_inputs():
     d["c1"] = adi_cube(50, 101, 5, 60.0, seed=20260102)    # BASELINE config 1
     d["small"] = adi_cube(30, 41, 4, 60.0, seed=5)
     d["ann"] = adi_cube(40, 48, 3, 80.0, seed=9)
+    d["ifs"] = ifs_cube()
     return d
+
+
+def ifs_cube(z=6, n=14, size=32, seed=41):
+    """Small IFS cube (z, n, size, size): each channel = the same ADI scene radially stretched by
+    lambda/lambda_min (speckles scale with wavelength), plus noise.  Returns (cube, angles, scale_list)."""
+    rng = np.random.default_rng(seed)
+    lam = np.linspace(1.0, 1.4, z)
+    scale_list = lam.max() / lam
+    base, angs = adi_cube(n, 2 * size, 3, 50.0, seed=seed)
+    from oracle import vip_oracle as O
+    cube = np.empty((z, n, size, size), dtype=np.float32)
+    c0 = size // 2
+    for c in range(z):
+        for i in range(n):
+            fr = O.frame_rescaling(base[i].astype(np.float64), lam[c] / lam[0])
+            cube[c, i] = fr[size - c0:size - c0 + size, size - c0:size - c0 + size]
+    cube += rng.normal(scale=0.5, size=cube.shape).astype(np.float32)
+    return cube, angs, scale_list
 
 
 def main():
@@ -80,6 +99,15 @@ def main():
     out["ann_seg_frame"] = pca_annular(cube, angs, ncomp=2, asize=6, n_segments=3, delta_rot=0.5,
                                        radius_int=4, verbose=False)
     np.savez_compressed(os.path.join(OUT, "pca_annular.npz"), **out)
+
+    out = {}
+    cube, angs, sl = inp["ifs"]
+    fr, rc, rd = pca(cube, angs, scale_list=sl, adimsdi="double", ncomp=(2, 3), verbose=False, full_output=True)
+    out["double_frame"], out["double_res_channels"], out["double_res_der"] = fr, rc, rd
+    out["double_skipadi"] = pca(cube, angs, scale_list=sl, adimsdi="double", ncomp=(2, None), verbose=False)
+    out["double_range"] = pca(cube, angs, scale_list=sl, adimsdi="double", ncomp=(1, 2), ifs_collapse_range=(1, 5),
+                              collapse_ifs="median", verbose=False)
+    np.savez_compressed(os.path.join(OUT, "pca_sdi.npz"), **out)
 
     out = {}
     cube = inp["small"][0].copy()

@@ -37,6 +37,14 @@ int derotate_run(const float*, float*, int, const RotParams&, const int*, const 
                  const float2*, void*, size_t, int, int*, cudaStream_t);
 int collapse_f32(const float*, int, size_t, int, const double*, int, int, void*, cudaStream_t);
 void profile_enable(int on);
+struct GemmArgs {
+    const float* A; long long lda, strideA; int a_mod;
+    const float* B; long long ldb, strideB; int b_mod;
+    float* C; long long ldc, strideC;
+    int M, N, K;
+    float alpha, beta;
+};
+int gemm_f32(const GemmArgs&, int, int, cudaStream_t);
 int annular_weights(const double*, const double*, int, const int*, const int*, const int*, int, int, int, double,
                     int, float*, int*, cudaStream_t);
 int gather_columns(const float*, int, size_t, const int*, int, float*, cudaStream_t);
@@ -192,6 +200,14 @@ int vb_gather_columns_f32(const float* src, int n, size_t p, const int* cols, in
 int vb_scatter_columns_f32(const float* src, int n, int npx, const int* cols, size_t p, float* dst, void* stream) {
     g_launches += 1;
     return scatter_columns(src, n, npx, cols, p, dst, (cudaStream_t)stream);
+}
+
+int vb_gemm_f32(const float* A, long long lda, long long strideA, int a_mod, const float* B, long long ldb,
+                long long strideB, int b_mod, int trans_b, float* C, long long ldc, long long strideC, int M,
+                int N, int K, float alpha, float beta, int batch, void* stream) {
+    GemmArgs g{A, lda, strideA, a_mod, B, ldb, strideB, b_mod, C, ldc, strideC, M, N, K, alpha, beta};
+    g_launches += 1;
+    return gemm_f32(g, trans_b, batch, (cudaStream_t)stream);
 }
 
 int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitch, size_t width_bytes,

@@ -201,3 +201,19 @@ def upload_columns(host2d, c0, c1, device):
     _cabi.check(lib.vb_memcpy2d_h2d(ptr(out), (c1 - c0) * 4, src, p * 4, (c1 - c0) * 4, n, stream_ptr()),
                 "vb_memcpy2d_h2d")
     return out
+
+
+def gemm(A, B, C, trans_b=False, alpha=1.0, beta=0.0, a_mod=0, b_mod=0):
+    """Batched fp32 GEMM on 3-d tensors: C[b] = alpha * A[b % a_mod or b] @ op(B[b % b_mod or b]) + beta * C[b].
+
+    A (Ba,M,K), B (Bb,K,N) or (Bb,N,K) if trans_b, C (batch,M,N); the last dimension of each must be
+    contiguous (row strides are passed as leading dimensions, so column-block views are fine)."""
+    lib = _cabi.lib()
+    batch, M, N = C.shape
+    K = A.shape[2]
+    for t in (A, B, C):
+        assert t.dtype == torch.float32 and t.stride(2) == 1
+    _cabi.check(lib.vb_gemm_f32(ptr(A), A.stride(1), A.stride(0), int(a_mod), ptr(B), B.stride(1), B.stride(0),
+                                int(b_mod), int(bool(trans_b)), ptr(C), C.stride(1), C.stride(0), M, N, K,
+                                float(alpha), float(beta), batch, stream_ptr()), "vb_gemm_f32")
+    return C

@@ -236,6 +236,35 @@ def _to_numpy_like(t, ref_dtype):
     return a
 
 
+def _pca_adimsdi(p, rot_options):
+    """ADI+mSDI branch of ``pca`` (``pca_fullfr.py:497-552``, returns :719-760)."""
+    from .sdi import adimsdi_doublepca_device
+    if p.cube.ndim != 4:
+        raise TypeError("Input cube is not a 4d array (required with `scale_list`)")
+    for name in ("cube_ref", "mask_rdi", "source_xy", "cube_sig", "smooth_first_pass", "smooth"):
+        if getattr(p, name) is not None:
+            _unsupported(f"`{name}` with ADI+mSDI")
+    if p.left_eigv:
+        _unsupported("`left_eigv`")
+    for lib in (p.imlib, p.imlib2):
+        if _mode_name(lib) != "vip-fft":
+            _unsupported(f"imlib={_mode_name(lib)!r}")
+    adimsdi = _mode_name(p.adimsdi)
+    if adimsdi == "double":
+        res_ch, res_der, frame = adimsdi_doublepca_device(
+            p.cube, p.angle_list, p.scale_list, p.ncomp, scaling=p.scaling, mask_center_px=p.mask_center_px,
+            svd_mode=p.svd_mode, collapse=p.collapse, collapse_ifs=p.collapse_ifs,
+            ifs_collapse_range=p.ifs_collapse_range, weights=p.weights, verbose=p.verbose, **rot_options)
+        # the reference's mSDI outputs are float64 (rescaling runs in fp64 there)
+        if p.full_output:
+            return (to_host(frame).astype(np.float64), to_host(res_ch).astype(np.float64),
+                    to_host(res_der).astype(np.float64))
+        return to_host(frame).astype(np.float64)
+    if adimsdi == "single":
+        _unsupported("adimsdi='single'")
+    raise ValueError(f"ADIMSDI value should only be {Adimsdi.SINGLE} or {Adimsdi.DOUBLE}.")
+
+
 def pca(*all_args: List, **all_kwargs: dict):
     """Full-frame PCA speckle subtraction: drop-in for ``vip_hci.psfsub.pca``.
 
@@ -275,8 +304,10 @@ def pca(*all_args: List, **all_kwargs: dict):
 
     if p.batch is not None:
         _unsupported("incremental PCA (`batch`)")
-    if p.cube.ndim == 4 or p.scale_list is not None:
-        _unsupported("4-d (IFS / ADI+mSDI) input")
+    if p.scale_list is not None:
+        return _pca_adimsdi(p, rot_options)
+    if p.cube.ndim == 4:
+        _unsupported("4-d input without `scale_list` (per-channel ADI)")
     if p.left_eigv:
         _unsupported("`left_eigv`")
     if p.mask_rdi is not None:

@@ -1,0 +1,154 @@
+"""ADI+mSDI (IFS, 4-d cubes) full-frame PCA on the B200: the ``scale_list`` branches of ``pca``.
+
+Reference: ``src/vip_hci/psfsub/pca_fullfr.py`` -- ``_adimsdi_doublepca`` :1245-1475,
+``_adimsdi_doublepca_ifs`` :1478-1549, ``_adimsdi_singlepca`` :1038-1242; rescaling through
+``cube_rescaling_wavelengths`` (``preproc/rescaling.py:324-475``).
+
+Double pass: per ADI frame, the z spectral channels are rescaled by ``scale_list`` (speckles aligned,
+planets move radially), a PCA across channels removes ``ncomp[0]`` components, the residuals are
+descaled, collapsed over channels and cropped; the resulting (n, H, W) cube then goes through the
+ordinary ADI PCA (``ncomp[1]``), derotation and collapse.  Frames are independent in stage 1 and are
+processed in chunks on the device; the (de)scaling is the separable operator of
+``preproc/rescaling.py`` applied with batched GEMMs.
+"""
+import numpy as np
+import torch
+
+from .. import kernels
+from .._device import require_cuda, to_device_f32
+from ..preproc.derotation import derotate_device
+from ..preproc.parangles import check_pa_vector
+from ..preproc.rescaling import crop_window, padded_size, rescale_operator
+from ..preproc.subsampling import collapse_device
+from ..var.coords import frame_center
+from ..var.shapes import circle_mask
+from .pca_fullfr import project_subtract_device
+
+# device memory budget (bytes) for one chunk of rescaled multispectral frames
+_CHUNK_BYTES = 2 << 30
+
+
+class RescaleOps:
+    """Forward / inverse rescaling operators of every channel, on the device.
+
+    forward:  (z, S', S')  real and imaginary parts stacked as W = [Lr; Li] (z, 2S', S')
+    inverse:  rows restricted to the final crop window -> (z, 2H, S')"""
+
+    def __init__(self, scale_list, size, device):
+        scale_list = np.asarray(scale_list, dtype=np.float64)
+        self.z = scale_list.shape[0]
+        self.size = size
+        max_sc = float(np.amax(scale_list))
+        self.big = padded_size(size, max_sc)
+        self.pad = (self.big - size) // 2
+        fwd = [rescale_operator(self.big, float(s)) for s in scale_list]
+        inv = [rescale_operator(self.big, float(1.0 / s)) for s in scale_list]
+        # inverse: collapse and crop commute (per-pixel statistics), so the crop is folded in the operator
+        if max_sc > 1 and self.big > size:
+            c = frame_center((self.big, self.big))[0]
+            y0, y1 = crop_window(self.big, size, c)
+        else:
+            y0, y1 = 0, self.big
+        self.out = y1 - y0
+        inv = [L[y0:y1] for L in inv]
+
+        def stack(ops):
+            W = np.stack([np.concatenate((L.real, L.imag), axis=0) for L in ops]).astype(np.float32)
+            return torch.from_numpy(W).to(device)
+        self.Wf = stack(fwd)          # (z, 2*big, big)
+        self.Wi = stack(inv)          # (z, 2*out, big)
+
+    @staticmethod
+    def apply(X, W, z):
+        """X (B, S, S) fp32 with B a multiple of z (channel = b % z); W (z, 2*So, S).
+        Returns Re(L X L^T) (B, So, So) with L = W[:So] + i W[So:]."""
+        B, S, _ = X.shape
+        So = W.shape[1] // 2
+        U = torch.empty((B, S, 2 * So), dtype=torch.float32, device=X.device)
+        kernels.gemm(X, W, U, trans_b=True, b_mod=z)                       # U = X [Lr; Li]^T
+        Y = torch.empty((B, So, So), dtype=torch.float32, device=X.device)
+        kernels.gemm(W[:, :So], U[:, :, :So], Y, a_mod=z)                  # Lr (X Lr^T)
+        kernels.gemm(W[:, So:], U[:, :, So:], Y, a_mod=z, alpha=-1.0, beta=1.0)   # - Li (X Li^T)
+        return Y
+
+
+def _stage1_frames(cube_dev, frames, ops, ncomp_ifs, scaling, mask_center_px, svd_mode, collapse_ifs,
+                   ifs_range):
+    """``_adimsdi_doublepca_ifs`` for a chunk of ADI frames: (z, n, H, W) device cube -> (F, H, W)."""
+    z, n, H, W = cube_dev.shape
+    F = len(frames)
+    i0, i1 = ifs_range
+    ms = cube_dev[:, frames].permute(1, 0, 2, 3).contiguous()              # (F, z, H, W)
+    if ncomp_ifs is None:
+        return torch.stack([collapse_device(ms[f, i0:i1], "median") for f in range(F)])
+    if ops.pad:
+        ms = torch.nn.functional.pad(ms, (ops.pad,) * 4, mode="reflect")   # np.pad(..., 'reflect')
+    S = ops.big
+    resc = RescaleOps.apply(ms.reshape(F * z, S, S), ops.Wf, z).reshape(F, z, S, S)
+    res = torch.empty_like(resc)
+    for f in range(F):                                                     # PCA across the z channels
+        res[f] = project_subtract_device(resc[f], ncomp_ifs, scaling, mask_center_px, svd_mode)
+    desc = RescaleOps.apply(res.reshape(F * z, S, S), ops.Wi, z).reshape(F, z, ops.out, ops.out)
+    out = torch.stack([collapse_device(desc[f, i0:i1], collapse_ifs) for f in range(F)])
+    if out.dtype != torch.float32:
+        out = out.float()
+    if mask_center_px:
+        mask = torch.as_tensor(circle_mask((ops.out, ops.out), mask_center_px)).to(out.device)
+        out = out.masked_fill(mask[None], 0.0)
+    return out
+
+
+def adimsdi_doublepca_device(cube, angle_list, scale_list, ncomp, scaling=None, mask_center_px=None,
+                             svd_mode="lapack", collapse="median", collapse_ifs="mean",
+                             ifs_collapse_range="all", weights=None, verbose=False, **rot_options):
+    """``_adimsdi_doublepca`` (``pca_fullfr.py:1245-1475``) on the device.
+    Returns (res_cube_channels (n,H,W), residuals_cube_channels_ (n,H,W), frame (H,W)) as CUDA tensors."""
+    z, n, y_in, x_in = cube.shape
+    if not isinstance(ncomp, tuple):
+        raise TypeError("`ncomp` must be a tuple when a double pass PCA is performed")
+    ncomp_ifs, ncomp_adi = ncomp
+    angle_list = check_pa_vector(np.asarray(angle_list))
+    if angle_list.shape[0] != n:
+        raise ValueError("Angle list vector has wrong length. It must equal the number frames in the cube")
+    if scale_list is None:
+        raise ValueError("Scaling factors vector must be provided")
+    scale_list = np.asarray(scale_list)
+    if scale_list.ndim > 1:
+        raise ValueError("Scaling factors vector is not 1d")
+    if scale_list.shape[0] != z:
+        raise ValueError("Scaling factors vector has wrong length")
+    if y_in != x_in:
+        raise ValueError("FFT scaling only supports square input arrays")
+    if not isinstance(scaling, tuple):
+        scaling = (scaling, scaling)
+    if ncomp_ifs is not None and ncomp_ifs > z:
+        ncomp_ifs = min(ncomp_ifs, z)
+        print("Number of PCs too high (max PCs={}), using {} PCs instead".format(z, ncomp_ifs))
+    ifs_range = (0, z) if ifs_collapse_range == "all" else (int(ifs_collapse_range[0]), int(ifs_collapse_range[1]))
+
+    dev = require_cuda()
+    cube_dev = to_device_f32(cube, dev)
+    ops = RescaleOps(scale_list, y_in, dev)
+    per_frame = 4 * z * ops.big * ops.big * 4 * 2          # rescaled + U + residuals + descaled (upper bound)
+    chunk = max(1, min(n, int(_CHUNK_BYTES // per_frame)))
+    parts = []
+    for f0 in range(0, n, chunk):
+        frames = list(range(f0, min(n, f0 + chunk)))
+        parts.append(_stage1_frames(cube_dev, frames, ops, ncomp_ifs, scaling[0], mask_center_px, svd_mode,
+                                    collapse_ifs, ifs_range))
+    res_channels = torch.cat(parts)                          # (n, H, W)
+    if verbose:
+        print("First PCA stage exploiting spectral variability done; {} ADI frames".format(n))
+
+    mask_val = float(rot_options.get("mask_val", np.nan))
+    interp_zeros = bool(rot_options.get("interp_zeros", False))
+    if ncomp_adi is None:
+        res2 = res_channels
+    else:
+        if ncomp_adi > n:
+            ncomp_adi = n
+            print("Number of PCs too high, using  maximum of {} PCs instead".format(n))
+        res2 = project_subtract_device(res_channels, ncomp_adi, scaling[1], mask_center_px, svd_mode)
+    res_der = derotate_device(res2, -angle_list, mask_val=mask_val, interp_zeros=interp_zeros)
+    frame = collapse_device(res_der, mode=collapse, w=weights)
+    return res_channels, res_der, frame
