@@ -40,6 +40,12 @@ long long vb_launch_count(void);
 size_t vb_gram_workspace_bytes(int n, size_t p);
 int vb_gram_f32(const float* A, int n, size_t p, int deflate, double* G, void* ws, size_t ws_bytes,
                 void* stream);
+/* Host cube (n x p fp32, pinned recommended) -> device matrix M AND G = M M^T in one pipelined call:
+ * `nslabs` pixel slabs are uploaded with strided 2-D DMAs on a private copy stream and the Gramian of
+ * each slab is accumulated on `stream` as soon as it has landed (SYRK hidden behind PCIe).
+ * ws: vb_gram_workspace_bytes(n, p). */
+int vb_upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, void* ws, size_t ws_bytes,
+                       int nslabs, void* stream);
 /* C[na x nb] (fp64) = A B^T   (RDI / cube_sig projections: np.dot(V, matrix_emp.T), pca_fullfr.py:1728) */
 size_t vb_cross_gram_workspace_bytes(int na, int nb);
 int vb_cross_gram_f32(const float* A, int na, const float* B, int nb, size_t p, double* C, void* ws,

@@ -1,0 +1,78 @@
+"""Time the BASELINE configs that are not the bench workload and check parity on a bounded subset.
+   python tools/run_configs.py c1|c3|c4 [...]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tools.synth import adi_cube          # noqa: E402
+from oracle import vip_oracle as O         # noqa: E402
+import vip_b200                            # noqa: E402
+from vip_b200 import _cabi                 # noqa: E402
+
+
+def timed(fn, reps=2):
+    best = None
+    out = None
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return out, best
+
+
+def c1():
+    cube, angs = adi_cube(50, 101, 5, 60.0, seed=20260101)
+    fr, dt = timed(lambda: vip_b200.pca(cube, angs, ncomp=5, verbose=False), reps=3)
+    t = time.perf_counter()
+    ref = O.pca_fullframe(cube, angs, ncomp=5)
+    cpu = time.perf_counter() - t
+    err = np.max(np.abs(fr - ref)) / np.max(np.abs(ref))
+    print(f"C1 50x101x101 ncomp=5: GPU {dt*1e3:.2f} ms ({50/dt:.0f} frames/s) | CPU oracle {cpu:.2f} s "
+          f"({50/cpu:.1f} frames/s) | rel err {err:.2e}")
+
+
+def c3(n=1000, size=512, ncomp=10, asize=32, check_frames=(0, 487, 999)):
+    cube, angs = adi_cube(n, size, ncomp, 90.0, seed=20260103)
+    n0 = _cabi.launch_count()
+    (co, cd, fr), dt = timed(lambda: vip_b200.pca_annular(cube, angs, ncomp=ncomp, asize=asize, verbose=False,
+                                                          full_output=True), reps=2)
+    nl = (_cabi.launch_count() - n0) // 2
+    print(f"C3 {n}x{size}x{size} pca_annular ncomp={ncomp} asize={asize}: GPU {dt:.3f} s ({n/dt:.0f} frames/s), "
+          f"{nl} launches")
+    t = time.perf_counter()
+    ref = O.pca_annular(cube, angs, ncomp=ncomp, asize=asize, frames=list(check_frames), derotate=False)
+    cpu = time.perf_counter() - t
+    scale = max(np.max(np.abs(ref[f])) for f in check_frames)
+    err = max(np.max(np.abs(co[f] - ref[f])) for f in check_frames) / scale
+    print(f"   parity on frames {check_frames} (PCA stage, all annuli): rel err {err:.2e}; CPU oracle "
+          f"{cpu/len(check_frames):.1f} s per frame -> {n*cpu/len(check_frames)/3600:.2f} h for the PCA stage alone")
+
+
+def c4(nframes=32):
+    rng = np.random.default_rng(0)
+    z, S = 39, 256
+    lam = np.linspace(0.95, 1.65, z)
+    sl = lam.max() / lam
+    base, angs = adi_cube(nframes, S, 10, 60.0, seed=20260104)
+    cube = np.empty((z, nframes, S, S), np.float32)
+    for c in range(z):
+        cube[c] = base * (1.0 + 0.01 * c) + rng.normal(scale=1.0, size=base.shape).astype(np.float32)
+    fr, dt = timed(lambda: vip_b200.pca(cube, angs, scale_list=sl, adimsdi="double", ncomp=(3, 10), verbose=False))
+    print(f"C4 slice 39x{nframes}x256x256 double PCA (3,10): GPU {dt:.3f} s ({nframes/dt:.1f} ADI frames/s)")
+    t = time.perf_counter()
+    ref = O.pca_adimsdi_double(cube, angs, sl, (3, 10), frames=[0])
+    cpu = time.perf_counter() - t
+    print(f"   CPU oracle stage 1: {cpu:.1f} s per ADI frame")
+
+
+if __name__ == "__main__":
+    for name in sys.argv[1:]:
+        {"c1": c1, "c3": c3, "c4": c4}[name]()

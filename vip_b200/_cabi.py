@@ -21,6 +21,7 @@ SIGNATURES = {
     "vb_launch_count": (C.c_longlong, []),
     "vb_gram_workspace_bytes": (_sz, [_i, _sz]),
     "vb_gram_f32": (_i, [_vp, _i, _sz, _i, _vp, _vp, _sz, _vp]),
+    "vb_upload_gram_f32": (_i, [_vp, _i, _sz, _vp, _vp, _vp, _sz, _i, _vp]),
     "vb_cross_gram_workspace_bytes": (_sz, [_i, _i]),
     "vb_cross_gram_f32": (_i, [_vp, _i, _vp, _i, _sz, _vp, _vp, _sz, _vp]),
     "vb_eigh_workspace_bytes": (_sz, [_i]),

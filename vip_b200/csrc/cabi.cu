@@ -23,6 +23,7 @@ void set_error(const char* fmt, ...) {
 size_t gram_workspace_bytes(int n, size_t p);
 int gram_f32(const float*, int, size_t, int, double*, void*, size_t, int, int*, cudaStream_t);
 int cross_gram_f32(const float*, int, const float*, int, size_t, double*, void*, size_t, int, cudaStream_t);
+int upload_gram_f32(const float*, int, size_t, float*, double*, void*, size_t, int, int*, cudaStream_t);
 size_t eigh_workspace_bytes(int n);
 int eigh_f64(const double*, int, double*, double*, int, double, void*, size_t, int*, int*, cudaStream_t);
 size_t eigh_topk_workspace_bytes(int n, int B);
@@ -88,6 +89,14 @@ int vb_gram_f32(const float* A, int n, size_t p, int deflate, double* G, void* w
                 void* stream) {
     int nl = 0;
     const int rc = gram_f32(A, n, p, deflate, G, ws, ws_bytes, 0, &nl, (cudaStream_t)stream);
+    g_launches += nl;
+    return rc;
+}
+
+int vb_upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, void* ws, size_t ws_bytes,
+                       int nslabs, void* stream) {
+    int nl = 0;
+    const int rc = upload_gram_f32(host, n, p, M, G, ws, ws_bytes, nslabs, &nl, (cudaStream_t)stream);
     g_launches += nl;
     return rc;
 }

@@ -745,7 +745,9 @@ static int fft_nt() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("VIP_B200_FFT_NT");
-        v = e ? atoi(e) : 2;   // 2: NT=2 x 2 CTAs/SM (default); 3: NT=2, 85-register cap, 3 CTAs/SM; 4: NT=4
+        // 1: one transform per 128-thread CTA, 4 CTAs/SM (default: measured fastest, 18.2 ms at C2);
+        // 2: NT=2 x 2 CTAs/SM (19.0 ms); 3: NT=2 with an 85-register cap (18.8 ms, spills); 4: NT=4 (21.9 ms)
+        v = e ? atoi(e) : 1;
     }
     return v;
 }
@@ -778,6 +780,8 @@ int derotate_run(const float* in, float* out, int nframes, const RotParams& g, c
                 case 2048:
                     if (fft_nt() == 4) rc = launch_fft_chunk<2048, 4, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     else if (fft_nt() == 3) rc = launch_fft_chunk<2048, 2, 3>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    else if (fft_nt() == 5) rc = launch_fft_chunk<2048, 2, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    else if (fft_nt() == 1) rc = launch_fft_chunk<2048, 1, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     else rc = launch_fft_chunk<2048, 2, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     break;
                 default:   rc = launch_fft_chunk<4096, 2, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;

@@ -30,8 +30,8 @@ __global__ void colmean_kernel(const float* __restrict__ A, int n, size_t p, flo
 // tiles: list of (ti, tj) output tiles; blockIdx.y = K-chunk.
 __global__ void __launch_bounds__(256)
 gram_tile_kernel(const float* __restrict__ A, const float* __restrict__ B, int na, int nb, size_t p,
-                 const float* __restrict__ mean, double* __restrict__ C, int ldc,
-                 const int2* __restrict__ tiles, int kchunk) {
+                 size_t ld, const float* __restrict__ mean, double* __restrict__ C, int ldc,
+                 const int2* __restrict__ tiles, int kchunk) {   // p = K extent, ld = row stride
     __shared__ __align__(16) float As[2][GK][GLD];
     __shared__ __align__(16) float Bs[2][GK][GLD];
     const int2 tile = tiles[blockIdx.x];
@@ -58,8 +58,8 @@ gram_tile_kernel(const float* __restrict__ A, const float* __restrict__ B, int n
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = lr + 16 * i;
-            ra[i] = (kin && row0 + r < na) ? __ldg(A + (size_t)(row0 + r) * p + k) - m : 0.f;
-            rb[i] = (kin && col0 + r < nb) ? __ldg(B + (size_t)(col0 + r) * p + k) - m : 0.f;
+            ra[i] = (kin && row0 + r < na) ? __ldg(A + (size_t)(row0 + r) * ld + k) - m : 0.f;
+            rb[i] = (kin && col0 + r < nb) ? __ldg(B + (size_t)(col0 + r) * ld + k) - m : 0.f;
         }
     };
     auto sstore = [&](int buf) {
@@ -150,6 +150,21 @@ __global__ void gram_assemble_kernel(const double* __restrict__ Gd, int n, const
     G[(size_t)i * n + j] = v;
 }
 
+// Split-K chunk so that (#tiles x #chunks) fills whole waves of the 148 SMs (1 CTA/SM: 250 registers)
+static int pick_kchunk(size_t p, int ntiles, int target) {
+    const int base = (int)ceil_div(p, (size_t)target);
+    int best = base;
+    double best_eff = 0.0;
+    for (int c = base; c <= base + 64; ++c) {
+        const long long total = (long long)ntiles * c;
+        const long long waves = (total + kNumSMs - 1) / kNumSMs;
+        const double eff = (double)total / (double)(waves * kNumSMs);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
+        if (eff > 0.985) break;
+    }
+    return ceil_div((int)ceil_div(p, (size_t)best), GK) * GK;
+}
+
 size_t gram_workspace_bytes(int n, size_t p) {
     const int nt = ceil_div(n, GT);
     size_t b = 0;
@@ -165,7 +180,10 @@ int gram_f32(const float* A, int n, size_t p, int deflate, double* G, void* ws, 
              int kchunk, int* launches, cudaStream_t st) {
     VB_REQUIRE(n > 0 && p > 0, "gram: empty matrix");
     VB_REQUIRE(ws_bytes >= gram_workspace_bytes(n, p), "gram: workspace too small");
-    if (kchunk <= 0) kchunk = 4096;
+    {
+        const int nt0 = ceil_div(n, GT);
+        if (kchunk <= 0) kchunk = pick_kchunk(p, nt0 * (nt0 + 1) / 2, 4096);
+    }
     kchunk = ceil_div(kchunk, GK) * GK;
     char* w = reinterpret_cast<char*>(ws);
     float* mean = reinterpret_cast<float*>(w);
@@ -195,13 +213,68 @@ int gram_f32(const float* A, int n, size_t p, int deflate, double* G, void* ws, 
     }
     const unsigned nchunks = (unsigned)ceil_div(p, (size_t)kchunk);
     VB_REQUIRE(nchunks <= 65535, "gram: too many K chunks");
-    gram_tile_kernel<<<dim3(ntiles, nchunks), 256, 0, st>>>(A, A, n, n, p, deflate ? mean : nullptr, Gd, n,
+    gram_tile_kernel<<<dim3(ntiles, nchunks), 256, 0, st>>>(A, A, n, n, p, p, deflate ? mean : nullptr, Gd, n,
                                                             tiles, kchunk);
     VB_CHECK_LAUNCH();
     gram_assemble_kernel<<<dim3(ceil_div(n, 128), n), 128, 0, st>>>(Gd, n, deflate ? Dm : nullptr, mm, G);
     VB_CHECK_LAUNCH();
     nl += 2;
     if (launches) *launches = nl;
+    return 0;
+}
+
+// Host cube -> device matrix M (n x p) AND G = M M^T, pipelined: the cube is uploaded in `nslabs` pixel
+// slabs (strided 2-D DMAs on a private copy stream) and the Gramian of each slab is accumulated on
+// `st` as soon as that slab has landed, so the fp64 SYRK hides behind the PCIe transfer.
+// `host` should be pinned (page-locked) memory for the copies to be truly asynchronous.
+int upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, void* ws, size_t ws_bytes,
+                    int nslabs, int* launches, cudaStream_t st) {
+    VB_REQUIRE(n > 0 && p > 0, "upload_gram: empty matrix");
+    VB_REQUIRE(ws_bytes >= gram_workspace_bytes(n, p), "upload_gram: workspace too small");
+    static cudaStream_t copy_stream = nullptr;
+    static cudaEvent_t ev[64], start_ev;
+    if (!copy_stream) {
+        VB_CHECK_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 64; ++i) VB_CHECK_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        VB_CHECK_CUDA(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
+    }
+    if (nslabs <= 0) nslabs = 8;
+    if (nslabs > 64) nslabs = 64;
+    char* w = reinterpret_cast<char*>(ws);
+    w += ((p * sizeof(float) + 255) / 256) * 256;                     // (mean slot, unused)
+    double* Gd = reinterpret_cast<double*>(w);
+    w += (((size_t)n * n * sizeof(double) + 255) / 256) * 256;
+    w += (((size_t)n + 1) * sizeof(double) + 255) / 256 * 256;
+    int2* tiles = reinterpret_cast<int2*>(w);
+    const int nt = ceil_div(n, GT);
+    int2 htiles[64 * 64];
+    VB_REQUIRE(nt <= 64, "upload_gram: n=%d too large for the tile list", n);
+    int ntiles = 0;
+    for (int i = 0; i < nt; ++i)
+        for (int j = i; j < nt; ++j) htiles[ntiles++] = make_int2(i, j);
+    VB_CHECK_CUDA(cudaMemcpyAsync(tiles, htiles, ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
+    VB_CHECK_CUDA(cudaMemsetAsync(Gd, 0, (size_t)n * n * sizeof(double), st));
+    // the copy stream must not start overwriting M before earlier work on `st` is done with it
+    VB_CHECK_CUDA(cudaEventRecord(start_ev, st));
+    VB_CHECK_CUDA(cudaStreamWaitEvent(copy_stream, start_ev, 0));
+    const size_t slab = ceil_div(ceil_div(p, (size_t)nslabs), (size_t)GK) * GK;
+    int nl = 0, s = 0;
+    for (size_t c0 = 0; c0 < p; c0 += slab, ++s) {
+        const size_t c1 = (c0 + slab < p) ? c0 + slab : p;
+        VB_CHECK_CUDA(cudaMemcpy2DAsync(M + c0, p * sizeof(float), host + c0, p * sizeof(float),
+                                        (c1 - c0) * sizeof(float), n, cudaMemcpyHostToDevice, copy_stream));
+        VB_CHECK_CUDA(cudaEventRecord(ev[s], copy_stream));
+        VB_CHECK_CUDA(cudaStreamWaitEvent(st, ev[s], 0));
+        const int kchunk = 1024;
+        const unsigned nchunks = (unsigned)ceil_div(c1 - c0, (size_t)kchunk);
+        gram_tile_kernel<<<dim3(ntiles, nchunks), 256, 0, st>>>(M + c0, M + c0, n, n, c1 - c0, p, nullptr, Gd, n,
+                                                                tiles, kchunk);
+        VB_CHECK_LAUNCH();
+        ++nl;
+    }
+    gram_assemble_kernel<<<dim3(ceil_div(n, 128), n), 128, 0, st>>>(Gd, n, nullptr, nullptr, G);
+    VB_CHECK_LAUNCH();
+    if (launches) *launches = nl + 1;
     return 0;
 }
 
@@ -222,7 +295,7 @@ int cross_gram_f32(const float* A, int na, const float* B, int nb, size_t p, dou
     VB_CHECK_CUDA(cudaMemsetAsync(C, 0, (size_t)na * nb * sizeof(double), st));
     const unsigned nchunks = (unsigned)ceil_div(p, (size_t)kchunk);
     VB_REQUIRE(nchunks <= 65535, "cross_gram: too many K chunks");
-    gram_tile_kernel<<<dim3(ntiles, nchunks), 256, 0, st>>>(A, B, na, nb, p, nullptr, C, nb, tiles, kchunk);
+    gram_tile_kernel<<<dim3(ntiles, nchunks), 256, 0, st>>>(A, B, na, nb, p, p, nullptr, C, nb, tiles, kchunk);
     VB_CHECK_LAUNCH();
     return 0;
 }

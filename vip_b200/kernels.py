@@ -217,3 +217,17 @@ def gemm(A, B, C, trans_b=False, alpha=1.0, beta=0.0, a_mod=0, b_mod=0):
                                 int(b_mod), int(bool(trans_b)), ptr(C), C.stride(1), C.stride(0), M, N, K,
                                 float(alpha), float(beta), batch, stream_ptr()), "vb_gemm_f32")
     return C
+
+
+def upload_and_gram(host2d, device, nslabs=8):
+    """C-contiguous fp32 host matrix (n,p) -> (M on the device, G = M M^T fp64), upload and SYRK pipelined."""
+    lib = _cabi.lib()
+    assert host2d.dtype == np.float32 and host2d.flags["C_CONTIGUOUS"] and host2d.ndim == 2
+    n, p = host2d.shape
+    M = empty((n, p), torch.float32, device)
+    G = empty((n, n), torch.float64, device)
+    nb = lib.vb_gram_workspace_bytes(n, p)
+    ws = _bytes(nb, device)
+    _cabi.check(lib.vb_upload_gram_f32(host2d.ctypes.data, n, p, ptr(M), ptr(G), ptr(ws), nb, int(nslabs),
+                                       stream_ptr()), "vb_upload_gram_f32")
+    return M, G

@@ -112,7 +112,7 @@ def prepare_matrix_device(cube_dev, scaling=None, mask_center_px=None):
 
 def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, svd_mode="lapack",
                             cube_ref_dev=None, cube_sig_dev=None, full_output=False, verbose=False,
-                            random_state=None):
+                            random_state=None, gram=None):
     """Whole-matrix branch of ``_project_subtract`` (``pca_fullfr.py:1552-1737``) on the device.
 
     Returns residuals (n,H,W) or (residuals, reconstructed (n,p), V (k,p))."""
@@ -151,7 +151,7 @@ def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, 
 
     if svd_mode in _EXACT_MODES:
         if dec is None:
-            dec = Decomposition(ref_lib, ncomp)
+            dec = Decomposition(ref_lib, ncomp, G=gram if ref_lib is matrix else None)
         V = dec.pcs(ncomp)
         if ref_lib is matrix_emp:
             Cm = dec.coeffs(ncomp)                # = matrix_emp . V^T from the eigenpairs
@@ -203,12 +203,21 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
 
     dev = require_cuda()
     as_dev = (lambda a: a.to(dev).float()) if isinstance(cube, torch.Tensor) else (lambda a: to_device_f32(a, dev))
-    cube_dev = as_dev(cube)
+    gram = None
+    plain = (cube_ref is None and cube_sig is None and scaling is None and not mask_center_px
+             and _mode_name(svd_mode) in _EXACT_MODES and isinstance(ncomp, (int, np.integer)))
+    if (plain and isinstance(cube, np.ndarray) and cube.dtype == np.float32 and cube.flags["C_CONTIGUOUS"]):
+        # host cube: upload in pixel slabs and accumulate the Gramian while the next slab is in flight
+        M, gram = kernels.upload_and_gram(cube.reshape(n, y * x), dev)
+        cube_dev = M.reshape(n, y, x)
+    else:
+        cube_dev = as_dev(cube)
     ref_dev = as_dev(cube_ref) if cube_ref is not None else None
     sig_dev = as_dev(cube_sig) if cube_sig is not None else None
 
     res = project_subtract_device(cube_dev, ncomp, scaling, mask_center_px, svd_mode, ref_dev, sig_dev,
-                                  full_output=full_output, verbose=verbose, random_state=random_state)
+                                  full_output=full_output, verbose=verbose, random_state=random_state,
+                                  gram=gram)
     if full_output:
         residuals_cube, recon, V = res
     else:

@@ -24,10 +24,11 @@ class Decomposition:
     ``ncomp=None`` -> full spectrum (Jacobi; needed for CEVR); an integer ``ncomp`` small enough for
     the subspace solver -> only the leading pairs (falls back to Jacobi if it does not converge)."""
 
-    def __init__(self, M, ncomp=None):
+    def __init__(self, M, ncomp=None, G=None):
         self.M = M
         n = M.shape[0]
-        G = kernels.gram(M)
+        if G is None:
+            G = kernels.gram(M)
         self.full = True
         if ncomp is not None and kernels.topk_supported(n, ncomp):
             evals, evecs, self.info = kernels.eigh_topk(G, ncomp)
