@@ -110,6 +110,13 @@ int vb_collapse_f32(const float* cube, int n, size_t p, int mode, const double* 
 int vb_annular_weights_f64(const double* G, const double* Gt, int n, const int* idx, const int* len,
                            const int* frame, int nprob, int Lmax, int ncomp, double tol, int max_iter, float* W,
                            int* iters, void* stream);
+/* Direct solver for the problems listed in plist[0..nlist) (those the subspace iteration left
+ * unconverged: flat, noise-dominated spectra): Householder tridiagonalisation of G[idx,idx] in the
+ * workspace ws (nlist * Lmax^2 doubles), Sturm multisection for the ncomp largest eigenvalues,
+ * simultaneous inverse iteration, back-transformation; same W/iters outputs (iters = 100000). */
+int vb_annular_direct_f64(const double* G, const double* Gt, int n, const int* idx, const int* len,
+                          const int* frame, int nprob, int Lmax, int ncomp, const int* plist, int nlist, float* W,
+                          int* iters, double* ws, void* stream);
 /* dst[n x npx] = src[n x p][:, cols]  and the inverse scatter (matrix_segm = array[:, yy, xx],
  * cube_out[fr][yy, xx] = residuals[fr];  psfsub/pca_local.py:713, 786-787) */
 int vb_gather_columns_f32(const float* src, int n, size_t p, const int* cols, int npx, float* dst, void* stream);

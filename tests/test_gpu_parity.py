@@ -361,6 +361,64 @@ def test_annular_weights_kernel_vs_numpy():
         assert np.count_nonzero(W[q]) <= len(I)
 
 
+@pytest.mark.parametrize("flat", [False, True])
+def test_annular_direct_solver_vs_numpy(flat):
+    """Direct (Householder + bisection + inverse iteration) solver, forced for every problem: gapped
+    and flat (noise-dominated, lambda_1/lambda_k ~ 1e8) sub-Gramians of 200-frame libraries."""
+    import torch
+    from vip_b200 import kernels
+    rng = np.random.default_rng(3)
+    n, npx, k, Lmax = 260, 3000, 10, 200
+    A = rng.normal(size=(n, npx)) * 3 + 1e4 / (1 + (np.arange(npx) / 300.0) ** 2)
+    if not flat:
+        for j in range(10):
+            A += np.outer(rng.normal(size=n), rng.normal(size=npx)) * 40 * 0.8 ** j
+    G = A @ A.T
+    nprob = 24
+    frames = rng.integers(0, n, nprob).astype(np.int32)
+    lens = np.full(nprob, Lmax, np.int32)
+    lens[0], lens[1] = 5, 37
+    idx = np.zeros((nprob, Lmax), np.int32)
+    for q in range(nprob):
+        idx[q, :lens[q]] = np.sort(rng.choice(np.setdiff1d(np.arange(n), [frames[q]]), lens[q], replace=False))
+    W, iters = kernels.annular_weights(torch.from_numpy(G).cuda(), torch.from_numpy(idx).cuda(),
+                                       torch.from_numpy(lens).cuda(), torch.from_numpy(frames).cuda(), k,
+                                       force_direct=True)
+    W = W.cpu().numpy()
+    assert (iters.cpu().numpy() == 100000).all()
+    for q in range(nprob):
+        I = idx[q, :lens[q]]
+        w_, v_ = np.linalg.eigh(G[np.ix_(I, I)])
+        kk = min(k, len(I))
+        X, th = v_[:, ::-1][:, :kk], w_[::-1][:kk]
+        wref = X @ ((X.T @ G[I, frames[q]]) / th)
+        # flat case: the k-th gap is ~1 % of an eigenvalue that is 1e-8 of ||G||: Gram-based accuracy limit
+        tol = (2e-4 if flat else 2e-6) * np.max(np.abs(wref))
+        np.testing.assert_allclose(W[q, I], wref, rtol=0, atol=tol, err_msg=f"problem {q} len {lens[q]}")
+
+
+def test_annular_hybrid_falls_back_on_flat_spectra():
+    import torch
+    from vip_b200 import kernels
+    rng = np.random.default_rng(4)
+    n, npx, k = 150, 2000, 6
+    A = rng.normal(size=(n, npx)) * 3 + 5e3
+    G = A @ A.T
+    idx = np.tile(np.arange(100, dtype=np.int32), (8, 1))
+    lens = np.full(8, 100, np.int32)
+    frames = np.arange(110, 118, dtype=np.int32)
+    W, iters = kernels.annular_weights(torch.from_numpy(G).cuda(), torch.from_numpy(idx).cuda(),
+                                       torch.from_numpy(lens).cuda(), torch.from_numpy(frames).cuda(), k)
+    it = iters.cpu().numpy()
+    assert (it > 0).all() and (it == 100000).any()       # flat spectrum: the direct solver had to step in
+    I = idx[0]
+    w_, v_ = np.linalg.eigh(G[np.ix_(I, I)])
+    X, th = v_[:, ::-1][:, :k], w_[::-1][:k]
+    for q in range(8):
+        wref = X @ ((X.T @ G[I, frames[q]]) / th)
+        np.testing.assert_allclose(W[q].cpu().numpy()[I], wref, rtol=0, atol=2e-4 * np.max(np.abs(wref)))
+
+
 def test_pca_annular_golden(vb, golden, golden_inputs):
     g = golden["pca_annular"]
     cube, angs = golden_inputs["ann"]

@@ -347,3 +347,336 @@ int scatter_columns(const float* src, int n, int npx, const int* cols, size_t p,
 }
 
 }  // namespace vb
+
+// =====================================================================================
+// Direct per-problem solver for (nearly) flat spectra
+// =====================================================================================
+// Subspace iteration converges at lambda_{B+1}/lambda_k per step; in noise-dominated annuli that
+// ratio is ~0.97-0.99 and it stalls.  Problems it leaves unconverged are solved directly, one CTA
+// each:  Householder tridiagonalisation of G[I,I] (workspace in global memory, L2 resident) ->
+// multisection Sturm bisection for the k largest eigenvalues -> simultaneous inverse iteration on
+// the tridiagonal (partial-pivoting solves, Gram-Schmidt between rounds) -> back-transformation ->
+// projection weights.  Same outputs as annular_weights_kernel.
+
+namespace vb {
+
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < AT / 32; ++w) t += red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(AT)
+annular_direct_kernel(AnnularArgs p, const int* __restrict__ plist, double* __restrict__ ws) {
+    extern __shared__ double sm[];
+    const int q = plist[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = p.len[q];
+    const int f = p.frame[q];
+    const int n = p.n, Lmax = p.Lmax;
+    const int* I = p.idx + (size_t)q * Lmax;
+    if (L <= 0) { if (tid == 0) p.iters[q] = 0; return; }
+    const int k = (p.ncomp < L) ? p.ncomp : L;
+    double* A = ws + (size_t)blockIdx.x * Lmax * Lmax;     // L x L, ld = L
+
+    // shared layout
+    double* d = sm;                       // [Lmax]
+    double* e = d + Lmax;                 // [Lmax]   e[j] couples j and j+1
+    double* tau = e + Lmax;               // [Lmax]
+    double* vv = tau + Lmax;              // [Lmax]
+    double* pp = vv + Lmax;               // [Lmax]
+    double* red = pp + Lmax;              // [8]
+    double* scal = red + 8;               // [8]  broadcast scalars
+    double* lam = scal + 8;               // [32]
+    double* blo = lam + 32;               // [32]
+    double* bhi = blo + 32;               // [32]
+    double* Z = bhi + 32;                 // [k][Lmax]
+    double* U0 = Z + (size_t)p.ncomp * Lmax;
+    double* U1 = U0 + (size_t)p.ncomp * Lmax;
+    double* U2 = U1 + (size_t)p.ncomp * Lmax;
+    int* cnt = reinterpret_cast<int*>(U2 + (size_t)p.ncomp * Lmax);   // [AT]
+    int* Is = cnt + AT;                   // [Lmax]
+
+    for (int i = tid; i < L; i += AT) Is[i] = I[i];
+    __syncthreads();
+    for (int el = tid; el < L * L; el += AT) {
+        const int i = el / L, j = el % L;
+        A[el] = __ldg(p.G + (size_t)Is[i] * n + Is[j]);
+    }
+    __syncthreads();
+
+    // ---- Householder tridiagonalisation (both triangles kept up to date; reflector j stored in row j)
+    for (int j = 0; j < L - 1; ++j) {
+        const int m = L - 1 - j;
+        double* x = A + (size_t)j * L + (j + 1);
+        double part = 0.0;
+        for (int i = 1 + tid; i < m; i += AT) part = fma(x[i], x[i], part);
+        const double sigma = block_sum_256(part, red);
+        if (tid == 0) {
+            const double alpha = x[0];
+            d[j] = A[(size_t)j * L + j];
+            if (sigma == 0.0) {
+                tau[j] = 0.0; e[j] = alpha; scal[0] = 0.0; scal[1] = 0.0;
+            } else {
+                const double beta = -copysign(sqrt(alpha * alpha + sigma), alpha);
+                tau[j] = (beta - alpha) / beta;
+                e[j] = beta;
+                scal[0] = tau[j];
+                scal[1] = 1.0 / (alpha - beta);
+            }
+        }
+        __syncthreads();
+        const double tj = scal[0];
+        if (tj == 0.0) {            // nothing to eliminate: v = e_1
+            if (tid == 0) x[0] = 1.0;
+            __syncthreads();
+            continue;
+        }
+        const double scale = scal[1];
+        for (int i = tid; i < m; i += AT) {
+            const double v = (i == 0) ? 1.0 : x[i] * scale;
+            vv[i] = v;
+            x[i] = v;
+        }
+        __syncthreads();
+        // p = tau * A22 v   (A22 symmetric: column i of A22 read as row-major rows l, coalesced over i)
+        const double* A22 = A + (size_t)(j + 1) * L + (j + 1);
+        if (tid < m) {
+            double acc = 0.0;
+#pragma unroll 8
+            for (int l = 0; l < m; ++l) acc = fma(A22[(size_t)l * L + tid], vv[l], acc);
+            pp[tid] = tj * acc;
+        }
+        __syncthreads();
+        double pv = (tid < m) ? pp[tid] * vv[tid] : 0.0;
+        const double K = -0.5 * tj * block_sum_256(pv, red);
+        if (tid < m) pp[tid] = fma(K, vv[tid], pp[tid]);      // w
+        __syncthreads();
+        if (tid < m) {
+            const double wi = pp[tid], vi = vv[tid];
+            double* col = A + (size_t)(j + 1) * L + (j + 1) + tid;
+#pragma unroll 8
+            for (int l = 0; l < m; ++l) col[(size_t)l * L] -= vv[l] * wi + pp[l] * vi;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { d[L - 1] = A[(size_t)(L - 1) * L + (L - 1)]; e[L - 1] = 0.0; tau[L - 1] = 0.0; }
+    __syncthreads();
+
+    // ---- k largest eigenvalues of the tridiagonal: multisection with Sturm counts
+    {
+        double gl = 1e300, gh = -1e300, e2max = 0.0;
+        for (int i = tid; i < L; i += AT) {
+            const double r = ((i > 0) ? fabs(e[i - 1]) : 0.0) + ((i < L - 1) ? fabs(e[i]) : 0.0);
+            gl = fmin(gl, d[i] - r); gh = fmax(gh, d[i] + r);
+            if (i < L - 1) e2max = fmax(e2max, e[i] * e[i]);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
+            gh = fmax(gh, __shfl_xor_sync(0xffffffffu, gh, o));
+            e2max = fmax(e2max, __shfl_xor_sync(0xffffffffu, e2max, o));
+        }
+        __syncthreads();
+        if (lane == 0) { red[warp] = gl; pp[warp] = gh; vv[warp] = e2max; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < AT / 32; ++w) { gl = fmin(gl, red[w]); gh = fmax(gh, pp[w]); e2max = fmax(e2max, vv[w]); }
+            const double pivmin = 2.2250738585072014e-308 * fmax(1.0, e2max);
+            const double span = gh - gl;
+            scal[2] = gl - (1e-3 * span + pivmin);
+            scal[3] = gh + (1e-3 * span + pivmin);
+            scal[4] = pivmin;
+        }
+        __syncthreads();
+    }
+    const double pivmin = scal[4];
+    const int P = AT / k;                 // section points per eigenvalue and round
+    if (tid < k) { blo[tid] = scal[2]; bhi[tid] = scal[3]; }
+    __syncthreads();
+    for (int round = 0; round < 64; ++round) {
+        const int r = tid / P, s = tid % P;
+        int c = 0;
+        double xs = 0.0;
+        const bool active = r < k;
+        if (active) {
+            const double lo = blo[r], hi = bhi[r];
+            xs = lo + (double)(s + 1) / (double)(P + 1) * (hi - lo);
+            double qv = d[0] - xs;
+            if (fabs(qv) < pivmin) qv = -pivmin;
+            c = qv < 0.0;
+            for (int i = 1; i < L; ++i) {
+                qv = d[i] - xs - e[i - 1] * e[i - 1] / qv;
+                if (fabs(qv) < pivmin) qv = -pivmin;
+                c += qv < 0.0;
+            }
+        }
+        cnt[tid] = c;
+        __syncthreads();
+        // per eigenvalue: new interval from the P counts (thread r)
+        __shared__ int all_done;
+        if (tid == 0) all_done = 1;
+        __syncthreads();
+        if (tid < k) {
+            const int a = L - 1 - tid;            // ascending index of the wanted eigenvalue
+            double lo = blo[tid], hi = bhi[tid];
+            const double w0 = hi - lo;
+            double nlo = lo, nhi = hi;
+            for (int s2 = 0; s2 < P; ++s2) {
+                const double x2 = lo + (double)(s2 + 1) / (double)(P + 1) * w0;
+                const int c2 = cnt[tid * P + s2];
+                if (c2 <= a) nlo = x2;
+                else { nhi = x2; break; }
+            }
+            blo[tid] = nlo; bhi[tid] = nhi;
+            const bool shrunk = (nlo > lo) || (nhi < hi);     // no progress = interval is down to a few ulps
+            if (shrunk && nhi - nlo > 4.0 * 2.220446049250313e-16 * fmax(fabs(nlo), fabs(nhi)) + 2.0 * pivmin)
+                all_done = 0;
+        }
+        __syncthreads();
+        if (all_done) break;
+    }
+    if (tid < k) lam[tid] = 0.5 * (blo[tid] + bhi[tid]);
+    __syncthreads();
+
+    // ---- simultaneous inverse iteration on the tridiagonal
+    for (int el = tid; el < k * L; el += AT) {
+        const int r = el / L, i = el % L;
+        Z[(size_t)r * Lmax + i] = hash_unit((unsigned)i * 131u + 7u, (unsigned)r * 977u + 3u);
+    }
+    __syncthreads();
+    for (int round = 0; round < 3; ++round) {
+        if (tid < k) {
+            const int r = tid;
+            double* u0 = U0 + (size_t)r * Lmax;
+            double* u1 = U1 + (size_t)r * Lmax;
+            double* u2 = U2 + (size_t)r * Lmax;
+            double* b = Z + (size_t)r * Lmax;
+            const double lr = lam[r];
+            // Gaussian elimination with partial pivoting of (T - lr I); sub-diagonal of row i+1 is e[i]
+            double diag = d[0] - lr;              // current pivot-row candidates
+            double sup = (L > 1) ? e[0] : 0.0;
+            for (int i = 0; i < L - 1; ++i) {
+                const double sub = e[i];
+                const double nd = d[i + 1] - lr;                    // next row: [sub, nd, e[i+1]]
+                const double ns = (i + 2 < L) ? e[i + 1] : 0.0;
+                if (fabs(diag) >= fabs(sub)) {
+                    const double piv = (diag != 0.0) ? diag : 1e-300;
+                    const double mlt = sub / piv;
+                    u0[i] = piv; u1[i] = sup; u2[i] = 0.0;
+                    b[i + 1] -= mlt * b[i];
+                    diag = nd - mlt * sup;
+                    sup = ns;
+                } else {
+                    const double mlt = diag / sub;
+                    u0[i] = sub; u1[i] = nd; u2[i] = ns;
+                    const double bi = b[i];
+                    b[i] = b[i + 1];
+                    b[i + 1] = bi - mlt * b[i + 1];
+                    diag = sup - mlt * nd;
+                    sup = -mlt * ns;
+                }
+            }
+            u0[L - 1] = (diag != 0.0) ? diag : 1e-300;
+            // back substitution
+            b[L - 1] = b[L - 1] / u0[L - 1];
+            if (L > 1) b[L - 2] = (b[L - 2] - u1[L - 2] * b[L - 1]) / u0[L - 2];
+            for (int i = L - 3; i >= 0; --i) b[i] = (b[i] - u1[i] * b[i + 1] - u2[i] * b[i + 2]) / u0[i];
+            // scale to avoid overflow in the next round
+            double mx = 0.0;
+            for (int i = 0; i < L; ++i) mx = fmax(mx, fabs(b[i]));
+            const double inv = (mx > 0.0) ? 1.0 / mx : 1.0;
+            for (int i = 0; i < L; ++i) b[i] *= inv;
+        }
+        __syncthreads();
+        if (warp == 0) {                  // modified Gram-Schmidt over the k vectors (one warp, no block syncs)
+            for (int r = 0; r < k; ++r) {
+                double* zr = Z + (size_t)r * Lmax;
+                for (int s2 = 0; s2 < r; ++s2) {
+                    const double* zs = Z + (size_t)s2 * Lmax;
+                    double dt = 0.0;
+                    for (int i = lane; i < L; i += 32) dt = fma(zr[i], zs[i], dt);
+                    dt = warp_sum(dt);
+                    for (int i = lane; i < L; i += 32) zr[i] -= dt * zs[i];
+                    __syncwarp();
+                }
+                double nn = 0.0;
+                for (int i = lane; i < L; i += 32) nn = fma(zr[i], zr[i], nn);
+                nn = warp_sum(nn);
+                const double inv = (nn > 0.0) ? rsqrt(nn) : 0.0;
+                for (int i = lane; i < L; i += 32) zr[i] *= inv;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- back-transformation  x = H_0 H_1 ... z  (each warp owns whole vectors: no block syncs)
+    for (int r = warp; r < k; r += AT / 32) {
+        double* z = Z + (size_t)r * Lmax;
+        for (int j = L - 2; j >= 0; --j) {
+            const double tj = tau[j];
+            if (tj == 0.0) continue;
+            const int m = L - 1 - j;
+            const double* v = A + (size_t)j * L + (j + 1);
+            double dt = 0.0;
+            for (int i = lane; i < m; i += 32) dt = fma(v[i], z[j + 1 + i], dt);
+            dt = warp_sum(dt) * tj;
+            for (int i = lane; i < m; i += 32) z[j + 1 + i] -= dt * v[i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // ---- weights  w = sum_r x_r (x_r . g) / lam_r
+    double* coef = blo;                   // (bisection intervals are no longer needed)
+    if (tid < 32) coef[tid] = 0.0;
+    __syncthreads();
+    {
+        const double g = (tid < L) ? __ldg(p.Gt + (size_t)f * n + Is[tid]) : 0.0;
+        for (int r = 0; r < k; ++r) {
+            const double v = warp_sum((tid < L) ? Z[(size_t)r * Lmax + tid] * g : 0.0);
+            if (lane == 0) atomicAdd(&coef[r], v);
+        }
+    }
+    __syncthreads();
+    if (tid < L) {
+        double w = 0.0;
+        for (int r = 0; r < k; ++r)
+            if (lam[r] > 0.0) w = fma(Z[(size_t)r * Lmax + tid], coef[r] / lam[r], w);
+        p.W[(size_t)q * n + Is[tid]] = (float)w;
+    }
+    if (tid == 0) p.iters[q] = 100000;      // marker: solved directly
+}
+
+size_t annular_direct_smem_bytes(int k, int Lmax) {
+    return ((size_t)5 * Lmax + 16 + 96 + (size_t)4 * k * Lmax) * sizeof(double) + ((size_t)AT + Lmax) * sizeof(int) + 16;
+}
+
+int annular_direct(const AnnularArgs& a, const int* plist, int nlist, double* ws, cudaStream_t st);
+
+int annular_direct_weights(const double* G, const double* Gt, int n, const int* idx, const int* len,
+                           const int* frame, int nprob, int Lmax, int ncomp, const int* plist, int nlist, float* W,
+                           int* iters, double* ws, cudaStream_t st) {
+    VB_REQUIRE(nlist > 0 && nlist <= nprob, "annular_direct: bad problem list");
+    AnnularArgs a{G, Gt ? Gt : G, n, idx, len, frame, Lmax, ncomp, 0.0, 0, W, iters};
+    return annular_direct(a, plist, nlist, ws, st);
+}
+
+// Solve the problems listed in plist (device, nlist entries) directly.  ws: nlist * Lmax^2 doubles.
+int annular_direct(const AnnularArgs& a, const int* plist, int nlist, double* ws, cudaStream_t st) {
+    VB_REQUIRE(a.ncomp <= 24 && a.ncomp >= 1, "annular_direct: ncomp must be in 1..24");
+    VB_REQUIRE(a.Lmax <= AT, "annular_direct: library too large");
+    const size_t smem = annular_direct_smem_bytes(a.ncomp, a.Lmax);
+    VB_REQUIRE(smem <= 220 * 1024, "annular_direct: %zu bytes of shared memory needed", smem);
+    VB_CHECK_CUDA(cudaFuncSetAttribute(annular_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    annular_direct_kernel<<<nlist, AT, smem, st>>>(a, plist, ws);
+    VB_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace vb

@@ -48,6 +48,8 @@ struct GemmArgs {
 int gemm_f32(const GemmArgs&, int, int, cudaStream_t);
 int annular_weights(const double*, const double*, int, const int*, const int*, const int*, int, int, int, double,
                     int, float*, int*, cudaStream_t);
+int annular_direct_weights(const double*, const double*, int, const int*, const int*, const int*, int, int, int,
+                           const int*, int, float*, int*, double*, cudaStream_t);
 int gather_columns(const float*, int, size_t, const int*, int, float*, cudaStream_t);
 int scatter_columns(const float*, int, int, const int*, size_t, float*, cudaStream_t);
 int profile_read(float* out);
@@ -199,6 +201,14 @@ int vb_annular_weights_f64(const double* G, const double* Gt, int n, const int* 
     g_launches += 1;
     return annular_weights(G, Gt, n, idx, len, frame, nprob, Lmax, ncomp, tol, max_iter, W, iters,
                            (cudaStream_t)stream);
+}
+
+int vb_annular_direct_f64(const double* G, const double* Gt, int n, const int* idx, const int* len,
+                          const int* frame, int nprob, int Lmax, int ncomp, const int* plist, int nlist, float* W,
+                          int* iters, double* ws, void* stream) {
+    g_launches += 1;
+    return annular_direct_weights(G, Gt, n, idx, len, frame, nprob, Lmax, ncomp, plist, nlist, W, iters, ws,
+                                  (cudaStream_t)stream);
 }
 
 int vb_gather_columns_f32(const float* src, int n, size_t p, const int* cols, int npx, float* dst, void* stream) {

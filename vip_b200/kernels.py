@@ -175,19 +175,35 @@ def scatter_columns(src, cols, dst):
     return dst
 
 
-def annular_weights(G, idx, lens, frames, ncomp, tol=0.0, max_iter=0):
+def annular_weights(G, idx, lens, frames, ncomp, tol=0.0, max_iter=40, direct_fallback=True, force_direct=False):
     """Per-problem projection weights from the library Gramian G (nlib,nlib) fp64.
 
     idx (nprob,Lmax) int32, lens (nprob,) int32, frames (nprob,) int32 = row of G of each target.
-    Returns (W (nprob,nlib) fp32, iters (nprob,) int32)."""
+    Block subspace iteration first (``max_iter`` steps); problems it leaves unconverged (flat,
+    noise-dominated spectra) are solved by the direct tridiagonal solver.
+    Returns (W (nprob,nlib) fp32, iters (nprob,) int32: >0 iterations, 100000 = direct, <0 = failed)."""
     lib = _cabi.lib()
     n = G.shape[0]
     nprob, Lmax = idx.shape
-    W = torch.zeros((nprob, n), dtype=torch.float32, device=G.device)
-    iters = torch.zeros((nprob,), dtype=torch.int32, device=G.device)
-    _cabi.check(lib.vb_annular_weights_f64(ptr(G), 0, n, ptr(idx), ptr(lens), ptr(frames), nprob, Lmax,
-                                           int(ncomp), float(tol), int(max_iter), ptr(W), ptr(iters),
-                                           stream_ptr()), "vb_annular_weights_f64")
+    dev = G.device
+    W = torch.zeros((nprob, n), dtype=torch.float32, device=dev)
+    iters = torch.zeros((nprob,), dtype=torch.int32, device=dev)
+    if not force_direct:
+        _cabi.check(lib.vb_annular_weights_f64(ptr(G), 0, n, ptr(idx), ptr(lens), ptr(frames), nprob, Lmax,
+                                               int(ncomp), float(tol), int(max_iter), ptr(W), ptr(iters),
+                                               stream_ptr()), "vb_annular_weights_f64")
+        if not direct_fallback:
+            return W, iters
+        todo = torch.nonzero(iters < 0).flatten().to(torch.int32)
+    else:
+        todo = torch.arange(nprob, dtype=torch.int32, device=dev)
+    chunk = max(1, min(1024, (1 << 30) // (Lmax * Lmax * 8)))      # <= 1 GiB of workspace per launch
+    for s in range(0, todo.numel(), chunk):
+        part = todo[s:s + chunk].contiguous()
+        ws = torch.empty(part.numel() * Lmax * Lmax, dtype=torch.float64, device=dev)
+        _cabi.check(lib.vb_annular_direct_f64(ptr(G), 0, n, ptr(idx), ptr(lens), ptr(frames), nprob, Lmax,
+                                              int(ncomp), ptr(part), part.numel(), ptr(W), ptr(iters), ptr(ws),
+                                              stream_ptr()), "vb_annular_direct_f64")
     return W, iters
 
 

@@ -133,7 +133,7 @@ def _segment_residuals(A, A_lib, angle_list, pa_thr, ncomp, min_frames_lib, max_
     W, iters = kernels.annular_weights(
         G, torch.from_numpy(idx_host).to(dev), torch.from_numpy(lens).to(dev),
         torch.arange(nref, nref + n, dtype=torch.int32, device=dev), k)
-    if bool((iters < 0).any()):
+    if bool((iters < 0).any()):                  # cannot happen: the direct solver always returns
         bad = int((iters < 0).sum())
         raise RuntimeError(f"vip_b200.pca_annular: {bad} per-frame eigenproblems did not converge")
     P = kernels.pcs(W, lib)                  # (n, npx) = W . A_lib : the per-frame PSF models
