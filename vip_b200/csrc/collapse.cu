@@ -11,6 +11,7 @@
 // pass finds the upper middle element for even counts.  Results are bit-exact w.r.t. numpy
 // (selection is exact; the mean of the two middle values is a single fp32 add and halving).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace vb {
 
@@ -85,6 +86,203 @@ collapse_median_kernel(const float* __restrict__ cube, int n, size_t p, float* _
     }
     const float v2 = (le >= r1 + 2) ? v1 : key2f(mingt);
     out[j] = (v1 + v2) * 0.5f;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Single-pass median: the n x PXT key tile of a CTA lives in shared memory, so the cube is read from
+// HBM exactly once (4 bytes per pixel and frame -- the algorithmic traffic).  SUB adjacent lanes share
+// one pixel (lane = pixel * SUB + s owns frames s, s+SUB, ...); every 4-bit radix pass histograms the
+// surviving candidates, merges the SUB partial histograms with shuffles, and compacts the candidates
+// of the chosen bin in place, so later passes touch ever fewer keys.  Ranks (m-1)/2 and m/2 are
+// tracked together; when they fall in different bins the answer is (max of the lower bin, min of
+// the upper bin).  NaNs are stored as key 0xFFFFFFFF (above every real key) and counted in pass 0.
+// Row stride `stride` (words) satisfies stride = odd * (32 / SUB) mod 32: the 32 lanes of a warp
+// (32/SUB pixels x SUB frames) always hit 32 distinct banks.
+// ---------------------------------------------------------------------------------------------
+template <int SUB>
+__device__ __forceinline__ unsigned int group_sum(unsigned int v) {
+#pragma unroll
+    for (int o = 1; o < SUB; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int SUB>
+__device__ __forceinline__ unsigned int group_max(unsigned int v) {
+#pragma unroll
+    for (int o = 1; o < SUB; o <<= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int SUB>
+__device__ __forceinline__ unsigned int group_min(unsigned int v) {
+#pragma unroll
+    for (int o = 1; o < SUB; o <<= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int SUB>
+__global__ void __launch_bounds__(768)
+collapse_median_smem_kernel(const float* __restrict__ cube, int n, size_t p, int pxt, int stride,
+                            float* __restrict__ out) {
+    extern __shared__ unsigned int smem_keys[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    unsigned int* K = smem_keys;
+    unsigned short* H = reinterpret_cast<unsigned short*>(smem_keys + (size_t)n * stride);   // [16][T]
+    const size_t px0 = (size_t)blockIdx.x * pxt;
+
+    // ---- load: every frame row of the tile is one contiguous pxt*4-byte segment
+    if ((p & 3) == 0 && (pxt & 3) == 0 && px0 + pxt <= p) {
+        const int q = pxt >> 2, total = n * q;
+        for (int idx = tid; idx < total; idx += T) {
+            const int row = idx / q, c4 = idx - row * q;
+            const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(cube + (size_t)row * p + px0) + c4);
+            uint4 k;
+            k.x = (v.x == v.x) ? f2key(v.x) : 0xffffffffu;
+            k.y = (v.y == v.y) ? f2key(v.y) : 0xffffffffu;
+            k.z = (v.z == v.z) ? f2key(v.z) : 0xffffffffu;
+            k.w = (v.w == v.w) ? f2key(v.w) : 0xffffffffu;
+            unsigned int* dst = K + (size_t)row * stride + 4 * c4;
+            if ((stride & 3) == 0) *reinterpret_cast<uint4*>(dst) = k;       // rows stay 16-byte aligned
+            else { dst[0] = k.x; dst[1] = k.y; dst[2] = k.z; dst[3] = k.w; }
+        }
+    } else {
+        const int total = n * pxt;
+        for (int idx = tid; idx < total; idx += T) {
+            const int row = idx / pxt, c = idx - row * pxt;
+            unsigned int k = 0xffffffffu;
+            if (px0 + c < p) {
+                const float v = __ldg(cube + (size_t)row * p + px0 + c);
+                if (v == v) k = f2key(v);
+            }
+            K[(size_t)row * stride + c] = k;
+        }
+    }
+    __syncthreads();
+
+    // ---- select
+    const int px = tid / SUB, s = tid - px * SUB;
+    unsigned int* col = K + px;                       // candidate j of this thread: col[(s + SUB*j) * stride]
+    int ncand = (n - s + SUB - 1) / SUB;
+    if (ncand < 0) ncand = 0;
+    unsigned int r1 = 0, r2 = 0, m = 0, k1 = 0, k2 = 0;
+    bool done = false;
+#pragma unroll 1
+    for (int shift = 28; shift >= 0; shift -= 4) {
+#pragma unroll
+        for (int b = 0; b < 16; ++b) H[b * T + tid] = 0;
+        unsigned int nnan = 0;
+        if (!done) {
+            for (int j = 0; j < ncand; ++j) {
+                const unsigned int key = col[(size_t)(s + SUB * j) * stride];
+                H[((key >> shift) & 15u) * T + tid] += 1;
+                if (shift == 28) nnan += (key == 0xffffffffu) ? 1u : 0u;
+            }
+        }
+        unsigned int tot[16];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) tot[b] = group_sum<SUB>((unsigned int)H[b * T + tid]);
+        if (shift == 28) {
+            m = (unsigned int)n - group_sum<SUB>(nnan);
+            if (m == 0) done = true;
+            r1 = (m - 1) >> 1;
+            r2 = m >> 1;
+        }
+        unsigned int cum = 0, b1 = 16, b2 = 16, c1 = 0, t1 = 0;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            if (b1 == 16u && r1 < cum + tot[b]) { b1 = b; c1 = cum; t1 = tot[b]; }
+            if (b2 == 16u && r2 < cum + tot[b]) { b2 = b; }
+            cum += tot[b];
+        }
+        // second scan: keep the candidates of bin b1 (compaction in place), max over bin b1, min over bin b2
+        unsigned int mx = 0u, mn = 0xffffffffu;
+        if (!done) {
+            int w = 0;
+            for (int j = 0; j < ncand; ++j) {
+                const unsigned int key = col[(size_t)(s + SUB * j) * stride];
+                const unsigned int d = (key >> shift) & 15u;
+                if (d == b1) {
+                    col[(size_t)(s + SUB * w) * stride] = key;
+                    ++w;
+                    mx = max(mx, key);
+                }
+                if (d == b2) mn = min(mn, key);
+            }
+            ncand = w;
+        }
+        mx = group_max<SUB>(mx);
+        mn = group_min<SUB>(mn);
+        if (!done) {
+            if (b1 != b2) { k1 = mx; k2 = mn; done = true; }
+            else if (t1 == 1u || shift == 0) { k1 = mx; k2 = mx; done = true; }
+            else { r1 -= c1; r2 -= c1; }
+        }
+        if (__all_sync(0xffffffffu, done)) break;      // warp-uniform: the shuffles above are warp-wide
+    }
+    if (s == 0 && px < pxt && px0 + px < p) {
+        float r;
+        if (m == 0) r = __uint_as_float(0x7fc00000u);
+        else if (m & 1u) r = key2f(k1);
+        else r = (key2f(k1) + key2f(k2)) * 0.5f;
+        out[px0 + px] = r;
+    }
+}
+
+struct MedianCfg { int sub, pxt, stride, threads; size_t smem; };
+
+// Pick (SUB, pixel tile, padded stride) maximising resident threads per SM; returns false when n is too
+// large for a shared-memory tile (the multi-pass kernel handles those).
+static bool pick_median_cfg(int n, MedianCfg* best) {
+    const size_t smem_max = 227 * 1024 - 1024;
+    // lanes per pixel: the per-pass histogram merge costs 16*log2(SUB) shuffles per lane, the scan
+    // n/SUB keys -- keep the scan the larger part (about 64 keys per lane) unless n forces more lanes
+    int sub0 = 4;
+    while (sub0 < 32 && n / sub0 > 64) sub0 <<= 1;
+    double best_score = 0.0;
+    for (int sub = sub0; sub <= 32; sub <<= 1) {
+        const int g = 32 / sub;
+        for (int pxt = 96; pxt >= 8; pxt -= 8) {
+            const int stride = ((pxt / g) & 1) ? pxt : pxt + g;
+            const int threads = pxt * sub;
+            if (threads > 768 || (threads & 31)) continue;
+            const size_t smem = (size_t)n * stride * 4 + (size_t)32 * threads;
+            if (smem > smem_max) continue;
+            int ctas = (int)((227 * 1024) / (smem + 1024));
+            if (ctas * threads > 2048) ctas = 2048 / threads;
+            if (ctas > 4) ctas = 4;
+            // resident pixels per SM decide the throughput; >= 2 CTAs/SM lets one CTA load while another selects
+            double score = (double)ctas * pxt;
+            if (ctas >= 2) score *= 1.25;
+            if (pxt < 16) score *= 0.7;
+            if (score > best_score) { best_score = score; *best = MedianCfg{sub, pxt, stride, threads, smem}; }
+        }
+        if (best_score > 0.0) break;      // the smallest SUB that fits wins
+    }
+    return best_score > 0.0;
+}
+
+static int launch_median_smem(const float* cube, int n, size_t p, float* out, const MedianCfg& c, cudaStream_t st) {
+    const unsigned grid = (unsigned)ceil_div(p, (size_t)c.pxt);
+#define VB_MEDIAN_CASE(S)                                                                              \
+    case S: {                                                                                          \
+        static size_t configured = 0;                                                                  \
+        if (c.smem > configured) {                                                                     \
+            VB_CHECK_CUDA(cudaFuncSetAttribute(collapse_median_smem_kernel<S>,                         \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))); \
+            configured = 227 * 1024;                                                                   \
+        }                                                                                              \
+        collapse_median_smem_kernel<S><<<grid, c.threads, c.smem, st>>>(cube, n, p, c.pxt, c.stride, out); \
+        break;                                                                                         \
+    }
+    switch (c.sub) {
+        VB_MEDIAN_CASE(4)
+        VB_MEDIAN_CASE(8)
+        VB_MEDIAN_CASE(16)
+        VB_MEDIAN_CASE(32)
+        default: VB_REQUIRE(false, "collapse: bad median configuration");
+    }
+#undef VB_MEDIAN_CASE
+    VB_CHECK_LAUNCH();
+    return 0;
 }
 
 // trimmed mean: mean of sorted[k : k+nn] with NaNs sorted last and skipped by the mean
@@ -173,9 +371,13 @@ int collapse_f32(const float* cube, int n, size_t p, int mode, const double* w, 
     float* fo = reinterpret_cast<float*>(out);
     const unsigned g256 = (unsigned)ceil_div(p, (size_t)256);
     switch (mode) {
-        case kMedian:
+        case kMedian: {
+            MedianCfg cfg;
+            const char* e = getenv("VIP_B200_MEDIAN_MULTIPASS");
+            if (!(e && atoi(e)) && pick_median_cfg(n, &cfg)) return launch_median_smem(cube, n, p, fo, cfg, st);
             collapse_median_kernel<<<(unsigned)ceil_div(p, (size_t)CT), CT, 0, st>>>(cube, n, p, fo);
             break;
+        }
         case kMean:    collapse_reduce_kernel<kMean><<<g256, 256, 0, st>>>(cube, n, p, fo); break;
         case kSum:     collapse_reduce_kernel<kSum><<<g256, 256, 0, st>>>(cube, n, p, fo); break;
         case kMax:     collapse_reduce_kernel<kMax><<<g256, 256, 0, st>>>(cube, n, p, fo); break;

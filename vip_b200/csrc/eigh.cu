@@ -241,7 +241,6 @@ struct TopkState {
     double pad;
 };
 
-constexpr int TKR = 32;   // rows per CTA in the row-parallel kernels
 
 __device__ __forceinline__ double hash_unit2(unsigned int a, unsigned int b) {
     unsigned long long z = ((unsigned long long)a << 32 | b) + 0x9E3779B97F4A7C15ull;
@@ -257,22 +256,21 @@ __global__ void topk_init_kernel(double* __restrict__ Y, int n) {
     if (e < n * B) Y[e] = hash_unit2((unsigned)(e / B) * 131u + 7u, (unsigned)(e % B) * 977u + 3u);
 }
 
-// Y[r][:] = sum_j G[r][j] X[j][:]   (CTA: TKR rows; thread: one row x B/8 columns)
+// Y[r][:] = sum_j G[r][j] X[j][:]   (CTA: 256/B rows x B columns, one output per thread; n/(256/B) CTAs
+// keep ~60 SMs busy on the 500 x 500 problem instead of 16)
 template <int B>
 __global__ void __launch_bounds__(256)
 topk_matvec_kernel(const double* __restrict__ G, int n, const double* __restrict__ X, double* __restrict__ Y,
                    const TopkState* __restrict__ st) {
     if (st->converged) return;
-    constexpr int TJ = 64, CPT = B / 8;
-    __shared__ double Gs[TKR][TJ + 1];
+    constexpr int TJ = 128, RPC = 256 / B;
+    __shared__ double Gs[RPC][TJ + 1];
     __shared__ double Xs[TJ][B];
-    const int r0 = blockIdx.x * TKR;
-    const int tr = threadIdx.x / 8, tc = (threadIdx.x % 8) * CPT;
-    double acc[CPT];
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) acc[c] = 0.0;
+    const int r0 = blockIdx.x * RPC;
+    const int tr = threadIdx.x / B, tc = threadIdx.x % B;
+    double acc0 = 0.0, acc1 = 0.0;
     for (int j0 = 0; j0 < n; j0 += TJ) {
-        for (int e = threadIdx.x; e < TKR * TJ; e += 256) {
+        for (int e = threadIdx.x; e < RPC * TJ; e += 256) {
             const int r = e / TJ, j = e % TJ;
             Gs[r][j] = (r0 + r < n && j0 + j < n) ? G[(size_t)(r0 + r) * n + j0 + j] : 0.0;
         }
@@ -282,17 +280,13 @@ topk_matvec_kernel(const double* __restrict__ G, int n, const double* __restrict
         }
         __syncthreads();
 #pragma unroll 8
-        for (int j = 0; j < TJ; ++j) {
-            const double g = Gs[tr][j];
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) acc[c] = fma(g, Xs[j][tc + c], acc[c]);
+        for (int j = 0; j < TJ; j += 2) {
+            acc0 = fma(Gs[tr][j], Xs[j][tc], acc0);
+            acc1 = fma(Gs[tr][j + 1], Xs[j + 1][tc], acc1);
         }
         __syncthreads();
     }
-    if (r0 + tr < n) {
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) Y[(size_t)(r0 + tr) * B + tc + c] = acc[c];
-    }
+    if (r0 + tr < n) Y[(size_t)(r0 + tr) * B + tc] = acc0 + acc1;
 }
 
 // T (B x B, atomics; must be zeroed) += P^T Q over this CTA's rows
@@ -301,7 +295,7 @@ __global__ void __launch_bounds__(256)
 topk_xty_kernel(const double* __restrict__ P, const double* __restrict__ Q, int n, double* __restrict__ T,
                 const TopkState* __restrict__ st) {
     if (st->converged) return;
-    constexpr int RCH = 64;
+    constexpr int RCH = 16;
     __shared__ double Ps[RCH][B], Qs[RCH][B];
     const int r0 = blockIdx.x * RCH;
     for (int e = threadIdx.x; e < RCH * B; e += 256) {
@@ -454,7 +448,7 @@ topk_rotate_kernel(double* __restrict__ X, double* __restrict__ Y, int n, const 
 
 // single warp: convergence test on the leading k Ritz pairs; R = chol(D^-1 S D^-1) (upper), dinv = 1/||Yr_c||
 template <int B>
-__global__ void topk_chol_kernel(const double* __restrict__ S, const double* __restrict__ res,
+__global__ void topk_chol_kernel(double* __restrict__ S, double* __restrict__ res, double* __restrict__ T,
                                  const double* __restrict__ theta, int k, double tol, double* __restrict__ R,
                                  double* __restrict__ dinv, TopkState* __restrict__ st, int check) {
     if (st->converged) return;
@@ -488,6 +482,9 @@ __global__ void topk_chol_kernel(const double* __restrict__ S, const double* __r
     }
     for (int e = lane; e < B * B; e += 32) R[e] = (e / B <= e % B) ? Rm[e / B][e % B] : 0.0;
     for (int c = lane; c < B; c += 32) dinv[c] = dv[c];
+    // leave the atomic accumulators clean for the next iteration (RR or plain orthogonalisation)
+    for (int e = lane; e < B * B; e += 32) { S[e] = 0.0; T[e] = 0.0; }
+    for (int c = lane; c < B; c += 32) res[c] = 0.0;
 }
 
 // rows: X = (Yr D^-1) R^-1  (forward substitution per row).  When converged, X (Ritz vectors) is kept.
@@ -543,23 +540,27 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
     TopkState* state = reinterpret_cast<TopkState*>(dinv + 2 * B);
     VB_CHECK_CUDA(cudaMemsetAsync(T, 0, (size_t)(4 * B * B + 4 * B) * sizeof(double) + sizeof(TopkState), st));
     int nl = 0;
-    const int grows = ceil_div(n, 64);
+    const int grows = ceil_div(n, 16);
     topk_init_kernel<B><<<ceil_div(n * B, 256), 256, 0, st>>>(Y, n);
     // orthonormalise the start block: S = Y^T Y, Cholesky, solve
     topk_xty_kernel<B><<<grows, 256, 0, st>>>(Y, Y, n, S, state);
-    topk_chol_kernel<B><<<1, 32, 0, st>>>(S, res, theta, k, tol, R, dinv, state, 0);
+    topk_chol_kernel<B><<<1, 32, 0, st>>>(S, res, T, theta, k, tol, R, dinv, state, 0);
     topk_solve_kernel<B><<<ceil_div(n, 128), 128, 0, st>>>(X, Y, n, R, dinv, state);
     nl += 4;
     VB_CHECK_LAUNCH();
     TopkState h{};
+    // Rayleigh-Ritz every iteration: without it the columns of G X all tilt towards the dominant
+    // eigenvector (lambda_0 / lambda_B ~ 1e5) and the Cholesky-QR of Y^T Y (condition number squared)
+    // loses the trailing directions -- measured: no convergence in 400 steps with RR every 4th step.
     for (int it = 0; it < max_iter; ++it) {
-        topk_matvec_kernel<B><<<ceil_div(n, TKR), 256, 0, st>>>(G, n, X, Y, state);
+        topk_matvec_kernel<B><<<ceil_div(n, 256 / B), 256, 0, st>>>(G, n, X, Y, state);
         topk_xty_kernel<B><<<grows, 256, 0, st>>>(X, Y, n, T, state);
         topk_ritz_kernel<B><<<1, 256, 0, st>>>(T, Qm, theta, S, res, state);
-        topk_rotate_kernel<B><<<grows, 256, 0, st>>>(X, Y, n, Qm, theta, S, res, state);
-        topk_chol_kernel<B><<<1, 32, 0, st>>>(S, res, theta, k, tol, R, dinv, state, 1);
+        topk_rotate_kernel<B><<<ceil_div(n, 64), 256, 0, st>>>(X, Y, n, Qm, theta, S, res, state);
+        topk_chol_kernel<B><<<1, 32, 0, st>>>(S, res, T, theta, k, tol, R, dinv, state, 1);
+        nl += 2;
         topk_solve_kernel<B><<<ceil_div(n, 128), 128, 0, st>>>(X, Y, n, R, dinv, state);
-        nl += 6;
+        nl += 4;
         if ((it & 7) == 7 || it == max_iter - 1) {
             VB_CHECK_LAUNCH();
             VB_CHECK_CUDA(cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -143,12 +143,28 @@ __global__ void gram_assemble_kernel(const double* __restrict__ Gd, int n, const
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= n) return;
-    // only tiles with tile_row <= tile_col were accumulated
-    const bool upper = (i / GT) <= (j / GT);
-    double v = upper ? Gd[(size_t)i * n + j] : Gd[(size_t)j * n + i];
+    // only tiles with tile_row <= tile_col were accumulated; mirror element-wise so that G is exactly
+    // symmetric (the two triangles of a diagonal tile are accumulated in different orders)
+    double v = (i <= j) ? Gd[(size_t)i * n + j] : Gd[(size_t)j * n + i];
     if (Dm != nullptr) v += Dm[i] + Dm[j] + *mm;
     G[(size_t)i * n + j] = v;
 }
+
+int gram_assemble(const double* Gd, int n, const double* Dm, const double* mm, double* G, cudaStream_t st) {
+    gram_assemble_kernel<<<dim3(ceil_div(n, 128), n), 128, 0, st>>>(Gd, n, Dm, mm, G);
+    VB_CHECK_LAUNCH();
+    return 0;
+}
+
+// tensor-core path (gram_tc.cu)
+size_t gram_tc_workspace_bytes(int n, size_t p);
+bool gram_tc_eligible(int n, size_t p);
+int gram_tc_begin(int n, size_t p, void* ws, size_t ws_bytes, int* ntiles_out, cudaStream_t st);
+int gram_tc_accumulate(const float* A, int n, size_t p, size_t ld, size_t c0, size_t c1, void* ws, int ntiles,
+                       int* launches, cudaStream_t st);
+int gram_tc_finish(int n, size_t p, void* ws, double* G, int* launches, cudaStream_t st);
+int gram_tc_f32(const float* A, int n, size_t p, double* G, void* ws, size_t ws_bytes, int* launches,
+                cudaStream_t st);
 
 // Split-K chunk so that (#tiles x #chunks) fills whole waves of the 148 SMs (1 CTA/SM: 250 registers)
 static int pick_kchunk(size_t p, int ntiles, int target) {
@@ -166,6 +182,7 @@ static int pick_kchunk(size_t p, int ntiles, int target) {
 }
 
 size_t gram_workspace_bytes(int n, size_t p) {
+    if (gram_tc_eligible(n, p)) return gram_tc_workspace_bytes(n, p);
     const int nt = ceil_div(n, GT);
     size_t b = 0;
     b += ((p * sizeof(float) + 255) / 256) * 256;                  // mean
@@ -180,6 +197,7 @@ int gram_f32(const float* A, int n, size_t p, int deflate, double* G, void* ws, 
              int kchunk, int* launches, cudaStream_t st) {
     VB_REQUIRE(n > 0 && p > 0, "gram: empty matrix");
     VB_REQUIRE(ws_bytes >= gram_workspace_bytes(n, p), "gram: workspace too small");
+    if (gram_tc_eligible(n, p) && kchunk <= 0) return gram_tc_f32(A, n, p, G, ws, ws_bytes, launches, st);
     {
         const int nt0 = ceil_div(n, GT);
         if (kchunk <= 0) kchunk = pick_kchunk(p, nt0 * (nt0 + 1) / 2, 4096);
@@ -240,6 +258,26 @@ int upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, voi
     }
     if (nslabs <= 0) nslabs = 8;
     if (nslabs > 64) nslabs = 64;
+    if (gram_tc_eligible(n, p)) {
+        // tensor-core SYRK per slab (split pass + tcgen05 kernel), same copy/compute pipeline
+        int ntiles = 0, nl = 0;
+        if (int rc = gram_tc_begin(n, p, ws, ws_bytes, &ntiles, st)) return rc;
+        VB_CHECK_CUDA(cudaEventRecord(start_ev, st));
+        VB_CHECK_CUDA(cudaStreamWaitEvent(copy_stream, start_ev, 0));
+        const size_t slab = ceil_div(ceil_div(p, (size_t)nslabs), (size_t)64) * 64;
+        int s = 0;
+        for (size_t c0 = 0; c0 < p; c0 += slab, ++s) {
+            const size_t c1 = (c0 + slab < p) ? c0 + slab : p;
+            VB_CHECK_CUDA(cudaMemcpy2DAsync(M + c0, p * sizeof(float), host + c0, p * sizeof(float),
+                                            (c1 - c0) * sizeof(float), n, cudaMemcpyHostToDevice, copy_stream));
+            VB_CHECK_CUDA(cudaEventRecord(ev[s], copy_stream));
+            VB_CHECK_CUDA(cudaStreamWaitEvent(st, ev[s], 0));
+            if (int rc = gram_tc_accumulate(M, n, p, p, c0, c1, ws, ntiles, &nl, st)) return rc;
+        }
+        if (int rc = gram_tc_finish(n, p, ws, G, &nl, st)) return rc;
+        if (launches) *launches = nl;
+        return 0;
+    }
     char* w = reinterpret_cast<char*>(ws);
     w += ((p * sizeof(float) + 255) / 256) * 256;                     // (mean slot, unused)
     double* Gd = reinterpret_cast<double*>(w);

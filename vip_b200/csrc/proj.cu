@@ -41,14 +41,23 @@ pcs_kernel(const double* __restrict__ Wt, const float* __restrict__ M, int n, si
         }
         __syncthreads();
         if (jin) {
-#pragma unroll 2
-            for (int i = 0; i < ni; ++i) {
-                const double m = (double)__ldg(M + (size_t)(i0 + i) * p + j);
+            // 8 independent loads in flight per thread (the kernel is latency/MLP-bound otherwise)
+            const float* src = M + (size_t)i0 * p + j;
+            for (int ib = 0; ib < ni; ib += 8) {
+                float mv[8];
 #pragma unroll
-                for (int q2 = 0; q2 < KC; q2 += 2) {
-                    const double2 w = *reinterpret_cast<const double2*>(&Ws[i][q2]);
-                    acc[q2 + 0] = fma(w.x, m, acc[q2 + 0]);
-                    acc[q2 + 1] = fma(w.y, m, acc[q2 + 1]);
+                for (int u = 0; u < 8; ++u) mv[u] = (ib + u < ni) ? __ldg(src + (size_t)(ib + u) * p) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (ib + u < ni) {
+                        const double m = (double)mv[u];
+#pragma unroll
+                        for (int q2 = 0; q2 < KC; q2 += 2) {
+                            const double2 w = *reinterpret_cast<const double2*>(&Ws[ib + u][q2]);
+                            acc[q2 + 0] = fma(w.x, m, acc[q2 + 0]);
+                            acc[q2 + 1] = fma(w.y, m, acc[q2 + 1]);
+                        }
+                    }
                 }
             }
         }
@@ -80,18 +89,28 @@ subtract_kernel(const float* Src, const float* __restrict__ C, int ldc, const fl
         }
         __syncthreads();
         if (jin) {
-            for (int i = 0; i < ni; ++i) {
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            // 8 independent loads in flight per thread; the dot products run while they land
+            const float* src = Src + (size_t)i0 * p + j;
+            float* dst = R + (size_t)i0 * p + j;
+            for (int ib = 0; ib < ni; ib += 8) {
+                float mv[8];
 #pragma unroll
-                for (int q4 = 0; q4 < KC; q4 += 4) {
-                    const float4 c = *reinterpret_cast<const float4*>(&Cs[i][q4]);
-                    s0 = fmaf(c.x, v[q4 + 0], s0);
-                    s1 = fmaf(c.y, v[q4 + 1], s1);
-                    s2 = fmaf(c.z, v[q4 + 2], s2);
-                    s3 = fmaf(c.w, v[q4 + 3], s3);
+                for (int u = 0; u < 8; ++u) mv[u] = (ib + u < ni) ? src[(size_t)(ib + u) * p] : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (ib + u < ni) {
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                        for (int q4 = 0; q4 < KC; q4 += 4) {
+                            const float4 c = *reinterpret_cast<const float4*>(&Cs[ib + u][q4]);
+                            s0 = fmaf(c.x, v[q4 + 0], s0);
+                            s1 = fmaf(c.y, v[q4 + 1], s1);
+                            s2 = fmaf(c.z, v[q4 + 2], s2);
+                            s3 = fmaf(c.w, v[q4 + 3], s3);
+                        }
+                        dst[(size_t)(ib + u) * p] = mv[u] - ((s0 + s1) + (s2 + s3));
+                    }
                 }
-                const size_t o = (size_t)(i0 + i) * p + j;
-                R[o] = Src[o] - ((s0 + s1) + (s2 + s3));
             }
         }
     }
