@@ -376,6 +376,41 @@ def test_pca_mask_center_and_cube_sig_vs_oracle(vb, golden_inputs):
     assert rel_err(fr, O.pca_fullframe(cube, angs, ncomp=3, cube_sig=sig)) < FRAME_TOL
 
 
+def test_pca_grid_and_4d_golden(vb, golden, golden_inputs):
+    """Tuple/list ncomp (one decomposition, one frame per number of PCs) and 4-d cubes without
+    scale_list (per-channel ADI + collapse_ifs), against golden outputs of the reference."""
+    g = golden["pca_grid4d"]
+    cube, angs = golden_inputs["small"]
+    fr, pcl = vb.pca(cube, angs, ncomp=(1, 4), verbose=False, full_output=True)
+    assert pcl == list(g["grid_range_pclist"]) and fr.dtype == np.float32
+    for i in range(len(pcl)):
+        assert rel_err(fr[i], g["grid_range"][i]) < FRAME_TOL, i
+    out = vb.pca(cube, angs, ncomp=[2, 4], verbose=False)
+    assert rel_err(out, g["grid_list"]) < FRAME_TOL
+    assert rel_err(vb.pca(cube, angs, ncomp=(1, 5, 2), med_of_npcs=True, verbose=False), g["grid_step_med"]) < FRAME_TOL
+    ref = adi_cube(20, 41, 4, 60.0, seed=6)[0]
+    out = vb.pca(cube, angs, cube_ref=ref, ncomp=(2, 3), scaling="temp-mean", verbose=False)
+    assert_parity(out, g["grid_rdi"],
+                  lambda: O.pca_grid(cube.astype(np.float64), angs, (2, 3), cube_ref=ref.astype(np.float64),
+                                     scaling="temp-mean")[0], FRAME_TOL, "grid rdi")
+    cube4, angs4, _ = golden_inputs["ifs"]
+    r = vb.pca(cube4, angs4, ncomp=2, verbose=False, full_output=True)
+    assert len(r) == 6 and r[0].dtype == np.float64 and r[5].dtype == np.float64 and r[1].dtype == np.float32
+    assert rel_err(r[0], g["ch_frame"]) < FRAME_TOL
+    assert rel_err(r[5], g["ch_ifs"]) < FRAME_TOL
+    assert rel_err(r[4], g["ch_res_der"]) < PCA_TOL
+    P = r[1].reshape(6, 2, -1)
+    Pg = g["ch_pcs"].reshape(6, 2, -1)
+    for ch in range(6):                                         # PCs up to sign
+        assert np.max(np.abs(np.abs(P[ch] @ Pg[ch].T) - np.eye(2))) < 1e-4
+    final, pcl4, ifs = vb.pca(cube4, angs4, ncomp=[1, 3], verbose=False, full_output=True)
+    assert pcl4 == [[1, 3]] * 6
+    assert rel_err(final, g["ch_grid"]) < FRAME_TOL and rel_err(ifs, g["ch_grid_ifs"]) < FRAME_TOL
+    assert vb.pca(cube4, angs4, ncomp=[2] * 6, collapse_ifs="median", verbose=False) == []   # reference quirk
+    with pytest.raises(ValueError):
+        vb.pca(cube4, angs4, ncomp=[1, 2, 3, 1, 2, 3], verbose=False)
+
+
 def test_pca_errors(vb):
     cube, angs = adi_cube(8, 16, 2, 30.0, seed=1)
     with pytest.raises(ValueError):
@@ -645,3 +680,24 @@ def test_pca_sdi_double_golden(vb, golden, golden_inputs):
         vb.pca(cube, angs, scale_list=sl, adimsdi="double", ncomp=3, verbose=False)
     with pytest.raises(ValueError):
         vb.pca(cube, angs, scale_list=sl[:-1], adimsdi="double", ncomp=(1, 1), verbose=False)
+
+
+def test_pca_sdi_single_golden(vb, golden, golden_inputs):
+    """ADI+mSDI single-pass PCA against golden outputs of the reference; tolerance as for the double
+    pass: 5e-6 * max|cube| (the reference runs in float64 here, our pipeline in fp32)."""
+    g = golden["pca_sdi_single"]
+    cube, angs, sl = golden_inputs["ifs"]
+    tol = 5e-6 * float(np.max(np.abs(cube)))
+    fr, allfr, desc, resadi = vb.pca(cube, angs, scale_list=sl, adimsdi="single", ncomp=3, verbose=False,
+                                     full_output=True)
+    assert fr.dtype == np.float64 and allfr.shape == (84, 32, 32) and desc.shape == cube.shape
+    assert desc.dtype == np.float32
+    assert np.max(np.abs(allfr[7] - g["single_allfr_7"])) < tol
+    assert np.max(np.abs(desc[2] - g["single_desc_ch2"])) < tol
+    assert np.max(np.abs(resadi - g["single_resadi"])) < tol
+    assert np.max(np.abs(fr - g["single_frame"])) < tol
+    out = vb.pca(cube, angs, scale_list=sl, adimsdi="single", ncomp=2, crop_ifs=False, collapse_ifs="median",
+                 verbose=False)
+    assert np.max(np.abs(out - g["single_nocrop"])) < tol
+    out = vb.pca(cube, angs, scale_list=sl, adimsdi="single", ncomp=2, ifs_collapse_range=(1, 5), verbose=False)
+    assert np.max(np.abs(out - g["single_range"])) < tol

@@ -1,3 +1,6 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_sharded.py 2>&1 | grep -v "^W\|^\*\*\*\|OMP" | tail -5
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 2>&1 | grep -v "^W\|^\*\*\*\|OMP" | tail -2 | cut -c1-900
-python -m pytest tests -m gpu -q -x -k "sharded or upload" 2>&1 | tail -3
+python tools/bench_stage.py median 500 512 2>&1 | tail -1
+python tools/bench_stage.py median 1000 512 2>&1 | tail -1
+timeout 900 python -m pytest tests -m gpu -q -x -k "collapse or single or grid" 2>&1 | tail -4
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'shear_cols_fft|collapse_median_smem' -c 2 -o gpurun_out/prof_r01e -f python bench.py --steps 1 --warmup 0 --no-cpu > gpurun_out/ncu_full_r01e.log 2>&1
+tail -3 gpurun_out/ncu_full_r01e.log
+ls -la gpurun_out/*.ncu-rep

@@ -119,8 +119,44 @@ def main():
     w = np.random.default_rng(1).uniform(size=30)
     out["wmean"] = cube_collapse(cube.copy(), "wmean", w=w)
     np.savez_compressed(os.path.join(OUT, "collapse.npz"), **out)
+    make_grid_4d(inp, pca)
+    make_sdi_single(inp, pca)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def make_sdi_single(inp, pca):
+    """ADI+mSDI single-pass PCA (one PCA over all rescaled channels of all frames)."""
+    cube, angs, sl = inp["ifs"]
+    out = {}
+    fr, allfr, desc, resadi = pca(cube, angs, scale_list=sl, adimsdi="single", ncomp=3, verbose=False,
+                                  full_output=True)
+    out["single_frame"], out["single_allfr_7"], out["single_desc_ch2"], out["single_resadi"] = \
+        fr, allfr[7], desc[2], resadi
+    out["single_nocrop"] = pca(cube, angs, scale_list=sl, adimsdi="single", ncomp=2, crop_ifs=False,
+                               collapse_ifs="median", verbose=False)
+    out["single_range"] = pca(cube, angs, scale_list=sl, adimsdi="single", ncomp=2, ifs_collapse_range=(1, 5),
+                              verbose=False)
+    np.savez_compressed(os.path.join(OUT, "pca_sdi_single.npz"), **out)
+
+
+def make_grid_4d(inp, pca):
+    """PCA grid (tuple/list ncomp -> pca_grid) and 4-d cubes without scale_list (per-channel ADI)."""
+    out = {}
+    cube, angs = inp["small"]
+    fr, pcl = pca(cube, angs, ncomp=(1, 4), verbose=False, full_output=True)
+    out["grid_range"], out["grid_range_pclist"] = fr, np.asarray(pcl)
+    out["grid_list"] = pca(cube, angs, ncomp=[2, 4], verbose=False)
+    out["grid_step_med"] = pca(cube, angs, ncomp=(1, 5, 2), med_of_npcs=True, verbose=False)
+    ref = adi_cube(20, 41, 4, 60.0, seed=6)[0]
+    out["grid_rdi"] = pca(cube, angs, cube_ref=ref, ncomp=(2, 3), scaling="temp-mean", verbose=False)
+    cube4, angs4, _ = inp["ifs"]
+    r = pca(cube4, angs4, ncomp=2, verbose=False, full_output=True)
+    out["ch_frame"], out["ch_pcs"], out["ch_res_der"], out["ch_ifs"] = r[0], r[1], r[4], r[5]
+    out["ch_list"] = pca(cube4, angs4, ncomp=[2, 2, 2, 2, 2, 2], collapse_ifs="median", verbose=False)
+    g = pca(cube4, angs4, ncomp=[1, 3], verbose=False, full_output=True)
+    out["ch_grid"], out["ch_grid_ifs"] = g[0], g[2]
+    np.savez_compressed(os.path.join(OUT, "pca_grid4d.npz"), **out)
 
 
 if __name__ == "__main__":

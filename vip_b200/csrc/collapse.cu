@@ -126,23 +126,40 @@ collapse_median_smem_kernel(const float* __restrict__ cube, int n, size_t p, int
     extern __shared__ unsigned int smem_keys[];
     const int T = blockDim.x, tid = threadIdx.x;
     unsigned int* K = smem_keys;
-    unsigned short* H = reinterpret_cast<unsigned short*>(smem_keys + (size_t)n * stride);   // [16][T]
+    // two histogram copies ([16][T] each) so that consecutive keys update independent counters
+    unsigned short* __restrict__ H = reinterpret_cast<unsigned short*>(smem_keys + (size_t)n * stride);
+    unsigned short* __restrict__ H2 = H + 16 * T;
     const size_t px0 = (size_t)blockIdx.x * pxt;
 
     // ---- load: every frame row of the tile is one contiguous pxt*4-byte segment
     if ((p & 3) == 0 && (pxt & 3) == 0 && px0 + pxt <= p) {
         const int q = pxt >> 2, total = n * q;
-        for (int idx = tid; idx < total; idx += T) {
-            const int row = idx / q, c4 = idx - row * q;
-            const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(cube + (size_t)row * p + px0) + c4);
-            uint4 k;
-            k.x = (v.x == v.x) ? f2key(v.x) : 0xffffffffu;
-            k.y = (v.y == v.y) ? f2key(v.y) : 0xffffffffu;
-            k.z = (v.z == v.z) ? f2key(v.z) : 0xffffffffu;
-            k.w = (v.w == v.w) ? f2key(v.w) : 0xffffffffu;
-            unsigned int* dst = K + (size_t)row * stride + 4 * c4;
-            if ((stride & 3) == 0) *reinterpret_cast<uint4*>(dst) = k;       // rows stay 16-byte aligned
-            else { dst[0] = k.x; dst[1] = k.y; dst[2] = k.z; dst[3] = k.w; }
+        // 8 independent 128-bit loads in flight per thread (one load at a time leaves HBM idle)
+        constexpr int U = 8;
+        for (int base = tid; base < total; base += U * T) {
+            float4 v[U];
+            int row[U], c4[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = base + u * T;
+                row[u] = idx / q;
+                c4[u] = idx - row[u] * q;
+                if (idx < total)
+                    v[u] = ld_stream_f4(reinterpret_cast<const float4*>(cube + (size_t)row[u] * p + px0) + c4[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (base + u * T < total) {
+                    uint4 k;
+                    k.x = (v[u].x == v[u].x) ? f2key(v[u].x) : 0xffffffffu;
+                    k.y = (v[u].y == v[u].y) ? f2key(v[u].y) : 0xffffffffu;
+                    k.z = (v[u].z == v[u].z) ? f2key(v[u].z) : 0xffffffffu;
+                    k.w = (v[u].w == v[u].w) ? f2key(v[u].w) : 0xffffffffu;
+                    unsigned int* dst = K + (size_t)row[u] * stride + 4 * c4[u];
+                    if ((stride & 3) == 0) *reinterpret_cast<uint4*>(dst) = k;       // rows stay 16-byte aligned
+                    else { dst[0] = k.x; dst[1] = k.y; dst[2] = k.z; dst[3] = k.w; }
+                }
+            }
         }
     } else {
         const int total = n * pxt;
@@ -168,18 +185,27 @@ collapse_median_smem_kernel(const float* __restrict__ cube, int n, size_t p, int
 #pragma unroll 1
     for (int shift = 28; shift >= 0; shift -= 4) {
 #pragma unroll
-        for (int b = 0; b < 16; ++b) H[b * T + tid] = 0;
+        for (int b = 0; b < 16; ++b) { H[b * T + tid] = 0; H2[b * T + tid] = 0; }
         unsigned int nnan = 0;
         if (!done) {
-            for (int j = 0; j < ncand; ++j) {
-                const unsigned int key = col[(size_t)(s + SUB * j) * stride];
-                H[((key >> shift) & 15u) * T + tid] += 1;
-                if (shift == 28) nnan += (key == 0xffffffffu) ? 1u : 0u;
+            int j = 0;
+            for (; j + 1 < ncand; j += 2) {
+                const unsigned int ka = col[(size_t)(s + SUB * j) * stride];
+                const unsigned int kb = col[(size_t)(s + SUB * (j + 1)) * stride];
+                H[((ka >> shift) & 15u) * T + tid] += 1;
+                H2[((kb >> shift) & 15u) * T + tid] += 1;
+                if (shift == 28) nnan += ((ka == 0xffffffffu) ? 1u : 0u) + ((kb == 0xffffffffu) ? 1u : 0u);
+            }
+            if (j < ncand) {
+                const unsigned int ka = col[(size_t)(s + SUB * j) * stride];
+                H[((ka >> shift) & 15u) * T + tid] += 1;
+                if (shift == 28) nnan += (ka == 0xffffffffu) ? 1u : 0u;
             }
         }
         unsigned int tot[16];
 #pragma unroll
-        for (int b = 0; b < 16; ++b) tot[b] = group_sum<SUB>((unsigned int)H[b * T + tid]);
+        for (int b = 0; b < 16; ++b)
+            tot[b] = group_sum<SUB>((unsigned int)H[b * T + tid] + (unsigned int)H2[b * T + tid]);
         if (shift == 28) {
             m = (unsigned int)n - group_sum<SUB>(nnan);
             if (m == 0) done = true;
@@ -196,16 +222,22 @@ collapse_median_smem_kernel(const float* __restrict__ cube, int n, size_t p, int
         // second scan: keep the candidates of bin b1 (compaction in place), max over bin b1, min over bin b2
         unsigned int mx = 0u, mn = 0xffffffffu;
         if (!done) {
-            int w = 0;
-            for (int j = 0; j < ncand; ++j) {
-                const unsigned int key = col[(size_t)(s + SUB * j) * stride];
-                const unsigned int d = (key >> shift) & 15u;
-                if (d == b1) {
-                    col[(size_t)(s + SUB * w) * stride] = key;
-                    ++w;
-                    mx = max(mx, key);
-                }
-                if (d == b2) mn = min(mn, key);
+            int w = 0, j = 0;
+            // two keys per step: both are read before either is written back (w <= j always)
+            for (; j + 1 < ncand; j += 2) {
+                const unsigned int ka = col[(size_t)(s + SUB * j) * stride];
+                const unsigned int kb = col[(size_t)(s + SUB * (j + 1)) * stride];
+                const unsigned int da = (ka >> shift) & 15u, db = (kb >> shift) & 15u;
+                if (da == b1) { col[(size_t)(s + SUB * w) * stride] = ka; ++w; mx = max(mx, ka); }
+                if (da == b2) mn = min(mn, ka);
+                if (db == b1) { col[(size_t)(s + SUB * w) * stride] = kb; ++w; mx = max(mx, kb); }
+                if (db == b2) mn = min(mn, kb);
+            }
+            if (j < ncand) {
+                const unsigned int ka = col[(size_t)(s + SUB * j) * stride];
+                const unsigned int da = (ka >> shift) & 15u;
+                if (da == b1) { col[(size_t)(s + SUB * w) * stride] = ka; ++w; mx = max(mx, ka); }
+                if (da == b2) mn = min(mn, ka);
             }
             ncand = w;
         }
@@ -237,6 +269,20 @@ static bool pick_median_cfg(int n, MedianCfg* best) {
     // n/SUB keys -- keep the scan the larger part (about 64 keys per lane) unless n forces more lanes
     int sub0 = 4;
     while (sub0 < 32 && n / sub0 > 64) sub0 <<= 1;
+    // development override: VIP_B200_MEDIAN_CFG="sub,pxt"
+    if (const char* e = getenv("VIP_B200_MEDIAN_CFG")) {
+        int sub = 0, pxt = 0;
+        if (sscanf(e, "%d,%d", &sub, &pxt) == 2 && (sub == 4 || sub == 8 || sub == 16 || sub == 32) && pxt > 0) {
+            const int g = 32 / sub;
+            const int stride = ((pxt / g) & 1) ? pxt : pxt + g;
+            const int threads = pxt * sub;
+            const size_t smem = (size_t)n * stride * 4 + (size_t)64 * threads;
+            if (pxt % g == 0 && threads <= 768 && (threads & 31) == 0 && smem <= smem_max) {
+                *best = MedianCfg{sub, pxt, stride, threads, smem};
+                return true;
+            }
+        }
+    }
     double best_score = 0.0;
     for (int sub = sub0; sub <= 32; sub <<= 1) {
         const int g = 32 / sub;
@@ -244,7 +290,7 @@ static bool pick_median_cfg(int n, MedianCfg* best) {
             const int stride = ((pxt / g) & 1) ? pxt : pxt + g;
             const int threads = pxt * sub;
             if (threads > 768 || (threads & 31)) continue;
-            const size_t smem = (size_t)n * stride * 4 + (size_t)32 * threads;
+            const size_t smem = (size_t)n * stride * 4 + (size_t)64 * threads;
             if (smem > smem_max) continue;
             int ctas = (int)((227 * 1024) / (smem + 1024));
             if (ctas * threads > 2048) ctas = 2048 / threads;

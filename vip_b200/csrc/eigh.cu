@@ -11,6 +11,7 @@
 // stages its 2*WB columns in shared memory and orthogonalises all pairs among them (one warp
 // per pair, WB disjoint pairs at a time).  Sweeps stop early through a device-side flag.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace vb {
 
@@ -317,16 +318,17 @@ topk_xty_kernel(const double* __restrict__ P, const double* __restrict__ Q, int 
 // single CTA: symmetrise T, one-sided Jacobi -> Qm (B x B, columns = Ritz vectors in X coordinates,
 // descending theta), theta[B]; zeroes S, res, T for the next kernels
 template <int B>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(16 * B)
 topk_ritz_kernel(double* __restrict__ T, double* __restrict__ Qm, double* __restrict__ theta,
-                 double* __restrict__ S, double* __restrict__ res, const TopkState* __restrict__ st) {
+                 double* __restrict__ S, double* __restrict__ res, const TopkState* __restrict__ st,
+                 double jthr) {
     if (st->converged) return;
     __shared__ double Tm[B][B + 1];
     __shared__ double th[B];
     __shared__ int order[B];
     __shared__ int rotated;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int e = tid; e < B * B; e += 256) {
+    for (int e = tid; e < B * B; e += 16 * B) {
         const int a = e / B, b = e % B;
         Tm[a][b] = 0.5 * (T[a * B + b] + T[b * B + a]);
     }
@@ -335,7 +337,8 @@ topk_ritz_kernel(double* __restrict__ T, double* __restrict__ Qm, double* __rest
         if (tid == 0) rotated = 0;
         __syncthreads();
         for (int r = 0; r < B - 1; ++r) {
-            for (int pr = warp; pr < B / 2; pr += 8) {
+            {
+                const int pr = warp;          // one column pair per warp: B/2 warps
                 int a, b;
                 const int mm = B - 1;
                 if (pr == 0) { a = mm; b = r % mm; } else { a = (r + pr) % mm; b = (r - pr + mm) % mm; }
@@ -345,7 +348,7 @@ topk_ritz_kernel(double* __restrict__ T, double* __restrict__ Qm, double* __rest
                     al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
                 }
                 al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
-                if (al > 0 && be > 0 && fabs(ga) > 1e-15 * sqrt(al) * sqrt(be)) {
+                if (al > 0 && be > 0 && fabs(ga) > jthr * sqrt(al) * sqrt(be)) {
                     const double zeta = (be - al) / (2.0 * ga);
                     const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                     const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
@@ -375,7 +378,7 @@ topk_ritz_kernel(double* __restrict__ T, double* __restrict__ Qm, double* __rest
         order[rk] = tid;
     }
     __syncthreads();
-    for (int e = tid; e < B * B; e += 256) {
+    for (int e = tid; e < B * B; e += 16 * B) {
         const int i = e / B, r = e % B;
         const int src = order[r];
         Qm[e] = th[src] > 0.0 ? Tm[i][src] / th[src] : (i == src ? 1.0 : 0.0);
@@ -549,19 +552,21 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
     nl += 4;
     VB_CHECK_LAUNCH();
     TopkState h{};
+    const char* je = getenv("VIP_B200_RITZ_THR");
+    const double jthr = je ? atof(je) : 1e-15;
     // Rayleigh-Ritz every iteration: without it the columns of G X all tilt towards the dominant
     // eigenvector (lambda_0 / lambda_B ~ 1e5) and the Cholesky-QR of Y^T Y (condition number squared)
     // loses the trailing directions -- measured: no convergence in 400 steps with RR every 4th step.
     for (int it = 0; it < max_iter; ++it) {
         topk_matvec_kernel<B><<<ceil_div(n, 256 / B), 256, 0, st>>>(G, n, X, Y, state);
         topk_xty_kernel<B><<<grows, 256, 0, st>>>(X, Y, n, T, state);
-        topk_ritz_kernel<B><<<1, 256, 0, st>>>(T, Qm, theta, S, res, state);
+        topk_ritz_kernel<B><<<1, 16 * B, 0, st>>>(T, Qm, theta, S, res, state, jthr);
         topk_rotate_kernel<B><<<ceil_div(n, 64), 256, 0, st>>>(X, Y, n, Qm, theta, S, res, state);
         topk_chol_kernel<B><<<1, 32, 0, st>>>(S, res, T, theta, k, tol, R, dinv, state, 1);
         nl += 2;
         topk_solve_kernel<B><<<ceil_div(n, 128), 128, 0, st>>>(X, Y, n, R, dinv, state);
         nl += 4;
-        if ((it & 7) == 7 || it == max_iter - 1) {
+        if ((it >= 7 && (it & 3) == 3) || it == max_iter - 1) {
             VB_CHECK_LAUNCH();
             VB_CHECK_CUDA(cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, st));
             VB_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -581,7 +586,7 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
 int eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, double* evals, double* evecs,
                   void* ws, size_t ws_bytes, int* info, int* launches, cudaStream_t st) {
     VB_REQUIRE(n >= 1 && k >= 1 && k <= n, "eigh_topk: need 1 <= k <= n");
-    if (tol <= 0) tol = 1e-10;
+    if (tol <= 0) tol = 1e-9;    // residual / lambda_k; eigenvector error ~ tol / relative gap
     if (max_iter <= 0) max_iter = 400;   // beyond this the caller is better off with the Jacobi solver
     const int B = (k <= 10) ? 16 : 32;
     VB_REQUIRE(k <= 24, "eigh_topk: k=%d too large for the subspace solver (use the Jacobi solver)", k);

@@ -237,6 +237,127 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
     return out
 
 
+def _grid_pclist(range_pcs, n):
+    """``pca_grid`` PC list (``utils_pca.py:284-305``)."""
+    if isinstance(range_pcs, list):
+        return list(range_pcs)
+    if range_pcs is None:
+        pcmin, pcmax, step = 1, n - 1, 1
+    elif len(range_pcs) == 2:
+        pcmin, pcmax = range_pcs
+        pcmax = min(pcmax, n)
+        step = 1
+    elif len(range_pcs) == 3:
+        pcmin, pcmax, step = range_pcs
+        pcmax = min(pcmax, n)
+    else:
+        raise TypeError("`range_pcs` must be None or a tuple, corresponding"
+                        "to (PC_INI, PC_MAX) or (PC_INI, PC_MAX, STEP)")
+    return list(range(pcmin, pcmax + 1, step))
+
+
+def _pca_grid_device(cube, cube_ref, rot_angles, range_pcs, scaling, mask_center_px, svd_mode, collapse,
+                     weights=None, **rot_options):
+    """``pca_grid(mode='fullfr', source_xy=None)`` (``utils_pca.py:25-428``) as reached from
+    ``_adi_rdi_pca`` (``pca_fullfr.py:1010-1035``): ONE decomposition with max(pclist) components, then
+    for every entry of the list the truncated projection/subtraction, derotation and collapse.
+    Returns (cubeout (len(pclist),H,W) device tensor, pclist)."""
+    n, y, x = cube.shape
+    rot_angles = np.asarray(rot_angles)          # = -angle_list (cube_derotate convention)
+    if _mode_name(svd_mode) not in _EXACT_MODES:
+        _unsupported(f"svd_mode={_mode_name(svd_mode)!r} with a tuple/list `ncomp`")
+    pclist = _grid_pclist(range_pcs, n)
+    pcmax = max(pclist)
+    mask_val = float(rot_options.get("mask_val", np.nan))
+    interp_zeros = bool(rot_options.get("interp_zeros", False))
+    _check_rot_options(rot_options.get("imlib", "vip-fft"), rot_options.get("cxy"),
+                       rot_options.get("border_mode", "constant"), rot_options.get("edge_blend"), cube.shape)
+    dev = require_cuda()
+    matrix = prepare_matrix_device(to_device_f32(cube, dev), scaling, mask_center_px)
+    ref_lib = (prepare_matrix_device(to_device_f32(cube_ref, dev), scaling, mask_center_px)
+               if cube_ref is not None else matrix)
+    nr, p = ref_lib.shape
+    if pcmax > min(nr, p):
+        msg = "{} PCs cannot be obtained from a matrix with size [{},{}]."
+        msg += " Increase the size of the patches or request less PCs"
+        raise RuntimeError(msg.format(pcmax, nr, p))
+    dec = Decomposition(ref_lib, pcmax)
+    V = dec.pcs(pcmax)
+    if ref_lib is matrix:
+        Cm = dec.coeffs(pcmax)
+    else:
+        Cm = kernels.cross_gram(matrix, V).to(torch.float32).contiguous()
+    frames = []
+    for pc in pclist:
+        residuals = kernels.project_subtract(matrix, Cm[:, :pc].contiguous(), V[:pc])
+        der = derotate_device(residuals.reshape(n, y, x), rot_angles, mask_val=mask_val,
+                              interp_zeros=interp_zeros)
+        frames.append(collapse_device(der, mode=collapse, w=weights))
+    return torch.stack(frames), pclist
+
+
+def _pca_4d_channels(p, rot_options):
+    """4-d input without ``scale_list``: independent ADI/RDI PCA per spectral channel, then
+    ``cube_collapse(ifs_adi_frames, collapse_ifs)`` (``pca_fullfr.py:543-658``, returns :762-783)."""
+    nch, nz, ny, nx = p.cube.shape
+    for name in ("mask_rdi", "source_xy", "batch", "smooth", "cube_sig"):
+        if getattr(p, name) is not None:
+            _unsupported(f"`{name}` with a 4-d cube")
+    if p.left_eigv:
+        _unsupported("`left_eigv`")
+    if _mode_name(p.imlib) != "vip-fft":
+        _unsupported(f"imlib={_mode_name(p.imlib)!r}")
+    grid_len = None
+    if not isinstance(p.ncomp, list):
+        ncomp = [p.ncomp] * nch
+    elif len(p.ncomp) != nch:
+        grid_len = len(p.ncomp)
+        ncomp = [p.ncomp] * nch
+    else:
+        ncomp = p.ncomp
+    if np.isscalar(p.fwhm):
+        p.fwhm = [p.fwhm] * nch                 # the reference rewrites the attribute too (:555-556)
+    dev = require_cuda()
+    pcs, recon, res, res_, frames, pclist = [], [], [], [], [], []
+    grid_case = False
+    for ch in range(nch):
+        cube_ref = None
+        if p.cube_ref is not None:
+            if p.cube_ref[ch].ndim != 3:
+                raise TypeError("Ref cube has wrong format for 4d input cube")
+            if p.ref_strategy == "RDI":
+                cube_ref = p.cube_ref[ch]
+            elif p.ref_strategy == "ARDI":
+                cube_ref = np.concatenate((p.cube[ch], p.cube_ref[ch]))
+            else:
+                raise TypeError("ref_strategy argument not recognized.Should be 'RDI' or 'ARDI'")
+        if isinstance(ncomp[ch], (tuple, list)):
+            grid_case = True
+            cubeout, pcl = _pca_grid_device(p.cube[ch], cube_ref, -check_pa_vector(np.asarray(p.angle_list)),
+                                            ncomp[ch], p.scaling, p.mask_center_px, p.svd_mode, p.collapse,
+                                            weights=p.weights, **rot_options)
+            frames.append(cubeout)
+            pclist.append(pcl)
+        else:
+            out = _adi_rdi_pca_device(p.cube[ch], cube_ref, p.angle_list, ncomp[ch], p.scaling, p.mask_center_px,
+                                      p.svd_mode, p.collapse, p.verbose, True, weights=p.weights,
+                                      **rot_options)
+            pcs.append(out[0]); recon.append(out[1]); res.append(out[2]); res_.append(out[3])
+            frames.append(out[4])
+    ifs_adi_frames = torch.stack(frames)                     # (nch, H, W) or (nch, npc, H, W)
+    if grid_case:
+        final = torch.stack([collapse_device(ifs_adi_frames[:, i].contiguous(), mode=p.collapse_ifs)
+                             for i in range(ifs_adi_frames.shape[1])])
+        return dict(grid=True, final=final, pclist=pclist, ifs=ifs_adi_frames)
+    frame = collapse_device(ifs_adi_frames, mode=p.collapse_ifs)
+    if len({tuple(t.shape) for t in pcs}) > 1:
+        # np.array(pcs) in the reference (:646) for channels with different numbers of components
+        raise ValueError("setting an array element with a sequence. The requested array has an inhomogeneous "
+                         "shape after 1 dimensions.")
+    return dict(grid=False, frame=frame, pcs=torch.stack(pcs), recon=torch.stack(recon), res=torch.stack(res),
+                res_=torch.stack(res_), ifs=ifs_adi_frames)
+
+
 def _to_numpy_like(t, ref_dtype):
     """Device result -> numpy with the dtype the reference would return for a cube of ``ref_dtype``."""
     a = to_host(t)
@@ -250,7 +371,7 @@ def _pca_adimsdi(p, rot_options):
     from .sdi import adimsdi_doublepca_device
     if p.cube.ndim != 4:
         raise TypeError("Input cube is not a 4d array (required with `scale_list`)")
-    for name in ("cube_ref", "mask_rdi", "source_xy", "cube_sig", "smooth_first_pass", "smooth"):
+    for name in ("cube_ref", "mask_rdi", "source_xy", "cube_sig", "smooth_first_pass", "smooth", "batch"):
         if getattr(p, name) is not None:
             _unsupported(f"`{name}` with ADI+mSDI")
     if p.left_eigv:
@@ -270,7 +391,20 @@ def _pca_adimsdi(p, rot_options):
                     to_host(res_der).astype(np.float64))
         return to_host(frame).astype(np.float64)
     if adimsdi == "single":
-        _unsupported("adimsdi='single'")
+        from .sdi import adimsdi_singlepca_device
+        if isinstance(p.ncomp, (tuple, list)):
+            _unsupported("adimsdi='single' with a tuple/list `ncomp` (pca_grid on the rescaled cube)")
+        allfr, desc, resadi, frame = adimsdi_singlepca_device(
+            p.cube, p.angle_list, p.scale_list, p.ncomp, scaling=p.scaling, mask_center_px=p.mask_center_px,
+            svd_mode=p.svd_mode, collapse=p.collapse, collapse_ifs=p.collapse_ifs,
+            ifs_collapse_range=p.ifs_collapse_range, crop_ifs=p.crop_ifs, weights=p.weights, verbose=p.verbose,
+            **rot_options)
+        # reference dtypes: the rescaled cube and every np.zeros buffer are float64; cube_desc_residuals
+        # is np.zeros_like(cube) (pca_fullfr.py:1159-1170)
+        f64 = lambda t: to_host(t).astype(np.float64)
+        if p.full_output:
+            return f64(frame), f64(allfr), to_host(desc).astype(p.cube.dtype), f64(resadi)
+        return f64(frame)
     raise ValueError(f"ADIMSDI value should only be {Adimsdi.SINGLE} or {Adimsdi.DOUBLE}.")
 
 
@@ -316,15 +450,31 @@ def pca(*all_args: List, **all_kwargs: dict):
     if p.scale_list is not None:
         return _pca_adimsdi(p, rot_options)
     if p.cube.ndim == 4:
-        _unsupported("4-d input without `scale_list` (per-channel ADI)")
+        r = _pca_4d_channels(p, rot_options)
+        dt = p.cube.dtype
+        # the reference gathers the channel frames in a float64 np.zeros buffer (:545): float64 outputs
+        ifs = to_host(r["ifs"]).astype(np.float64)
+        if r["grid"]:
+            final = to_host(r["final"]).astype(np.float64)
+            if p.med_of_npcs:
+                final = np.median(final, axis=0)
+            return (final, r["pclist"], ifs) if p.full_output else final
+        if isinstance(p.ncomp, (tuple, list)):
+            # reference quirk (:766-790): a per-channel list of scalar ncomp is treated as a "grid" by the
+            # return logic although no grid was computed -> the (empty) final_residuals_cube list comes back
+            final = np.median([], axis=0) if p.med_of_npcs else []
+            return (final, [], ifs) if p.full_output else final
+        frame = to_host(r["frame"]).astype(np.float64)
+        if p.full_output:
+            return (frame, _to_numpy_like(r["pcs"], dt), _to_numpy_like(r["recon"], dt),
+                    _to_numpy_like(r["res"], dt), _to_numpy_like(r["res_"], dt), ifs)
+        return frame
     if p.left_eigv:
         _unsupported("`left_eigv`")
     if p.mask_rdi is not None:
         _unsupported("`mask_rdi` (data imputation)")
     if p.source_xy is not None:
         _unsupported("`source_xy` (PA-threshold library / S/N optimisation)")
-    if isinstance(p.ncomp, (tuple, list)):
-        _unsupported("a tuple/list `ncomp` (pca_grid)")
     if p.smooth is not None:
         _unsupported("`smooth`")
     imlib = _mode_name(p.imlib)
@@ -339,6 +489,20 @@ def pca(*all_args: List, **all_kwargs: dict):
             algo_params.cube_ref = cube_ref        # the reference overwrites the attribute too (:670-672)
         elif p.ref_strategy != "RDI":
             raise TypeError("ref_strategy argument not recognized.Should be 'RDI' or 'ARDI'")
+
+    if isinstance(p.ncomp, (tuple, list)):
+        # PCA grid: one residual frame per number of components (pca_fullfr.py:1010-1035, returns :766-790)
+        if p.cube_sig is not None:
+            _unsupported("`cube_sig` with a tuple/list `ncomp`")
+        angs = check_pa_vector(np.asarray(p.angle_list))
+        if p.cube.shape[0] != angs.shape[0]:
+            raise ValueError("`angle_list` vector has wrong length. It must equal the number of frames in the cube")
+        cubeout, pclist = _pca_grid_device(p.cube, cube_ref, -angs, p.ncomp, p.scaling, p.mask_center_px,
+                                           p.svd_mode, p.collapse, weights=p.weights, **rot_options)
+        final = _to_numpy_like(cubeout, p.cube.dtype)
+        if p.med_of_npcs:
+            final = np.median(final, axis=0)
+        return (final, pclist) if p.full_output else final
 
     func_params = setup_parameters(params_obj=algo_params, fkt=_adi_rdi_pca_device)
     func_params["cube_ref"] = cube_ref

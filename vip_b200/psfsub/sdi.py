@@ -152,3 +152,83 @@ def adimsdi_doublepca_device(cube, angle_list, scale_list, ncomp, scaling=None, 
     res_der = derotate_device(res2, -angle_list, mask_val=mask_val, interp_zeros=interp_zeros)
     frame = collapse_device(res_der, mode=collapse, w=weights)
     return res_channels, res_der, frame
+
+
+def adimsdi_singlepca_device(cube, angle_list, scale_list, ncomp, scaling=None, mask_center_px=None,
+                             svd_mode="lapack", collapse="median", collapse_ifs="mean",
+                             ifs_collapse_range="all", crop_ifs=True, weights=None, verbose=False,
+                             **rot_options):
+    """``_adimsdi_singlepca`` (``pca_fullfr.py:1038-1242``) for a scalar ``ncomp`` on the device: every
+    channel of every ADI frame is rescaled (speckles aligned), ONE PCA runs over the z*n rescaled frames,
+    the residuals are descaled and collapsed over the channels of each ADI frame, then derotated and
+    collapsed over time.  Returns (cube_allfr_residuals (z*n,S,S), cube_desc_residuals (zr,n,H,W),
+    cube_adi_residuals (n,H,W), frame (H,W)) as CUDA tensors (frame index of the big cube = i*z + channel)."""
+    z, n, y_in, x_in = cube.shape
+    angle_list = check_pa_vector(np.asarray(angle_list))
+    if angle_list.shape[0] != n:
+        raise ValueError("Angle list vector has wrong length. It must equal the number frames in the cube")
+    if scale_list is None:
+        raise ValueError("`scale_list` must be provided")
+    scale_list = np.asarray(scale_list)
+    if scale_list.ndim != 1:
+        raise TypeError("Input array (scale_list) is not a 1d array")
+    if scale_list.shape[0] != z:
+        raise ValueError("`scale_list` has wrong length")
+    if y_in != x_in:
+        raise ValueError("FFT scaling only supports square input arrays")
+    if not np.isscalar(ncomp):
+        raise TypeError("`ncomp` must be an int, float, tuple or list for single-pass PCA")
+    i0, i1 = (0, z) if ifs_collapse_range == "all" else (int(ifs_collapse_range[0]), int(ifs_collapse_range[1]))
+
+    dev = require_cuda()
+    cube_dev = to_device_f32(cube, dev)
+    ops = RescaleOps(scale_list, y_in, dev)
+    S = ops.big
+    # crop_ifs: cube_crop_frames(cube_resc, size=y_in) about the centre of the padded frame
+    if crop_ifs and S > y_in:
+        c = frame_center((S, S))[0]
+        c0, c1 = crop_window(S, y_in, c)
+    else:
+        c0, c1 = 0, S
+    Sc = c1 - c0
+    big = torch.empty((n * z, Sc, Sc), dtype=torch.float32, device=dev)
+    per_frame = 3 * z * S * S * 4 * 2
+    chunk = max(1, min(n, int(_CHUNK_BYTES // per_frame)))
+    for f0 in range(0, n, chunk):
+        f1 = min(n, f0 + chunk)
+        ms = cube_dev[:, f0:f1].permute(1, 0, 2, 3).contiguous()                # (F, z, H, W)
+        if ops.pad:
+            ms = torch.nn.functional.pad(ms, (ops.pad,) * 4, mode="reflect")
+        resc = RescaleOps.apply(ms.reshape((f1 - f0) * z, S, S), ops.Wf, z)
+        big[f0 * z:f1 * z] = resc[:, c0:c1, c0:c1]
+    if verbose:
+        print("{} total frames".format(n * z))
+        print("Performing single-pass PCA")
+    res_cube = project_subtract_device(big, ncomp, scaling, mask_center_px, svd_mode)
+
+    # inverse rescaling acts on the (possibly cropped) frames: operators of size Sc, crop to the input size
+    inv = [rescale_operator(Sc, float(1.0 / s)) for s in scale_list[i0:i1]]
+    if Sc > y_in:
+        c = frame_center((Sc, Sc))[0]
+        r0, r1 = crop_window(Sc, y_in, c)
+        inv = [L[r0:r1] for L in inv]
+    Wi = torch.from_numpy(np.stack([np.concatenate((L.real, L.imag), axis=0) for L in inv]).astype(np.float32)).to(dev)
+    zr = i1 - i0
+    desc = torch.empty((zr, n, y_in, x_in), dtype=torch.float32, device=dev)
+    resadi = torch.empty((n, y_in, x_in), dtype=torch.float32, device=dev)
+    for f0 in range(0, n, chunk):
+        f1 = min(n, f0 + chunk)
+        F = f1 - f0
+        sel = res_cube[f0 * z:f1 * z].reshape(F, z, Sc, Sc)[:, i0:i1].reshape(F * zr, Sc, Sc).contiguous()
+        d = RescaleOps.apply(sel, Wi, zr).reshape(F, zr, y_in, x_in)
+        desc[:, f0:f1] = d.permute(1, 0, 2, 3)
+        for f in range(F):
+            resadi[f0 + f] = collapse_device(d[f], collapse_ifs).float()
+    mask_val = float(rot_options.get("mask_val", np.nan))
+    interp_zeros = bool(rot_options.get("interp_zeros", False))
+    der = derotate_device(resadi, -angle_list, mask_val=mask_val, interp_zeros=interp_zeros)
+    if mask_center_px:
+        mask = torch.as_tensor(circle_mask((y_in, x_in), mask_center_px)).to(dev)
+        der = der.masked_fill(mask[None], 0.0)
+    frame = collapse_device(der, mode=collapse, w=weights)
+    return res_cube, desc, resadi, frame
