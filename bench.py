@@ -128,6 +128,11 @@ def cpu_sample(cube, angs, ncomp, n_rot=2, strip=8):
                    "derotate_s": t_rot * n / n_rot}
 
 
+def n_tiles_upper(n, tile=128):
+    nt = (n + tile - 1) // tile
+    return nt * (nt + 1) // 2
+
+
 def cpu_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -201,7 +206,11 @@ def stage_times(cube_dev, angs, ncomp, reps=3):
         return res
 
     G = timed("gram_ms", lambda: kernels.gram(M))
-    evals, evecs, info = timed("eigh_ms", lambda: kernels.eigh(G))
+    if kernels.topk_supported(n, ncomp):
+        evals, evecs, info = timed("eigh_topk_ms", lambda: kernels.eigh_topk(G, ncomp))
+        out["eigh_topk_iters"] = info["iters"]
+    else:
+        evals, evecs, info = timed("eigh_jacobi_ms", lambda: kernels.eigh(G))
     S = torch.sqrt(evals[:ncomp])
     Wt = (evecs[:ncomp] / S[:, None]).contiguous()
     Cm = (evecs[:ncomp] * S[:, None]).t().float().contiguous()
@@ -219,7 +228,6 @@ def stage_times(cube_dev, angs, ncomp, reps=3):
     out["shear_rows_last_ms"] = prof[2] / nrep
     out["derotate_chunks"] = int(prof[3] / nrep)
     timed("collapse_median_ms", lambda: collapse_device(D, "median"))
-    out["eigh_sweeps"] = info["sweeps"]
     return out
 
 
@@ -332,18 +340,33 @@ def run_gpu(args):
             fft_flop = n * (2 * size + 1 + N) * 2 * 5 * N * lg   # (rows p1 + cols p2 + rows p3) x (fwd+inv)
         alg_bytes = 8.0 * p * n       # read residual cube + write derotated cube
         achieved = alg_bytes / (derot_ms * 1e-3) / 1e9
+        # DRAM bytes of the three shear kernels for one 500x512x512 step, from the committed ncu --set full
+        # captures (profiles/r01a_ncu_full_c2.md rows kernels, profiles/r01e_ncu_full_c2.md columns kernel):
+        # the complex planes T1/T2 between the passes (the transposition of the 3-shear algorithm) make it
+        # 17x the algorithmic 8p bytes/frame
+        traffic = 18.27e9 if (n, size) == (500, 512) else None
         line["roofline"] = {
             "kernel": "vb_derotate_f32 = shear_rows_first + shear_cols + shear_rows_last (one launch each per chunk)",
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": None, "peak_source": peak_kind,
+            "traffic": traffic, "peak_source": peak_kind,
             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": derot_ms,
             "note": "stage is fp32-FFT-arithmetic bound, not HBM bound (DESIGN.md): ~220 flop per algorithmic byte",
             "fft_gflop": None if fft_flop is None else fft_flop / 1e9,
             "fft_tflops_achieved": None if fft_flop is None else fft_flop / (derot_ms * 1e-3) / 1e12,
             "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,
         }
+        gram_ms = st["gram_ms"]
+        tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+        gram_flop = float(n) * n * p                 # symmetric half of the 2 n^2 p SYRK
+        line["roofline_gram"] = {
+            "kernel": "vb_gram_f32 = slab_mean + split_planes<3> + gram_umma_kernel<64,3> (tcgen05) + assemble",
+            "bound": "tensor", "achieved": gram_flop / (gram_ms * 1e-3) / 1e12, "peak": tf_peak,
+            "unit": "TFLOP/s", "frac": gram_flop / (gram_ms * 1e-3) / 1e12 / tf_peak,
+            "note": ("algorithmic n^2 p flop of the exact product; the kernel issues 6 bf16 MMAs per product "
+                     "(error-free bf16x3 split) on 10 of 16 tiles: 0.52 PFLOP of tensor work per step"),
+            "issued_bf16_tflops": 6.0 * 2.0 * (n_tiles_upper(n) * 128.0 * 128.0) * p / (gram_ms * 1e-3) / 1e12}
         col_ms = st["collapse_median_ms"]
-        line["roofline_collapse"] = {"kernel": "collapse_median_kernel", "bound": "hbm",
+        line["roofline_collapse"] = {"kernel": "collapse_median_smem_kernel", "bound": "hbm",
                                      "achieved": 4.0 * p * n / (col_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                      "unit": "GB/s", "frac": 4.0 * p * n / (col_ms * 1e-3) / 1e9 / hbm_peak}
         ps_ms = st["project_subtract_ms"]

@@ -151,3 +151,10 @@ def test_vectorised_library_indices_match_reference_rule():
     lists = library_indices(angs, 42, 3)
     for f in range(7):
         np.testing.assert_array_equal(lists[f], O.find_indices_adi(angs, f, 42, truncate=True, max_frames=3))
+    # uniformly spaced / duplicated angles: |dPA| ties at the truncation boundary take the exact argsort path
+    for angs in (np.linspace(0.0, 80.0, 120), np.round(np.linspace(0.0, 40.0, 90))):
+        for thr, mf in ((0.5, 7), (3.0, 50), (2.0, 20)):
+            lists = library_indices(angs, thr, mf)
+            for f in range(len(angs)):
+                np.testing.assert_array_equal(lists[f], O.find_indices_adi(angs, f, thr, truncate=True,
+                                                                            max_frames=mf))

@@ -503,6 +503,61 @@ shear_cols_fft(const float2* __restrict__ T1, float2* __restrict__ T2, RotParams
     }
 }
 
+// ---- pass 2, persistent variant (one transform per CTA at a time, CTAs loop over the columns) -------
+// ncu on the one-shot kernel above shows the long scoreboard (global loads: the strided column gather)
+// as the top stall.  Here each CTA prefetches the NEXT column with cp.async into a staging line while
+// the current transform runs, and writes its S outputs straight from registers.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int N, int MINB>
+__global__ void __launch_bounds__(N / 16, MINB)
+shear_cols_fft_persist(const float2* __restrict__ T1, float2* __restrict__ T2, RotParams g,
+                       const double* __restrict__ b_coef, const float2* __restrict__ tw, int frame0, int nf) {
+    using F = ShearFft<N>;
+    constexpr int T = F::T;
+    extern __shared__ float2 smem2[];
+    __shared__ float2 ph3s[16];
+    float2* buf = smem2;                 // F::BUF exchange buffer
+    float2* stage = smem2 + F::BUF;      // S+1 input samples of the prefetched column
+    const int t = threadIdx.x;
+    const int S = g.S;
+    const long long total = (long long)nf * N;
+    long long item = blockIdx.x;
+    auto prefetch = [&](long long it) {
+        const int fl = (int)(it / N), c = (int)(it % N);
+        const float2* src = T1 + (size_t)fl * (S + 1) * N + c;
+        for (int row = t; row <= S; row += T) cp_async8(stage + row, src + (size_t)row * N);
+        cp_async_commit();
+    };
+    if (item < total) prefetch(item);
+    for (; item < total; item += gridDim.x) {
+        cp_async_wait_all();
+        __syncthreads();                 // staged column visible; previous transform done with buf
+        float re[16], im[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 v = stage[t + j * T];
+            re[j] = v.x; im[j] = v.y;
+        }
+        const float2 v4 = stage[4 * T];  // row S (only thread 0 uses it)
+        __syncthreads();                 // everyone has read the staging line
+        if (item + gridDim.x < total) prefetch(item + gridDim.x);
+        const int fl = (int)(item / N), c = (int)(item % N);
+        int s_int; float s_frac;
+        const int col_phys = (c + g.y0) & (N - 1);
+        split_shift(b_coef[frame0 + fl] * (double)(col_phys - N / 2), s_int, s_frac);
+        F::template run<true, true>(re, im, buf, ph3s, tw, t, 0, s_int, s_frac, v4.x, v4.y);
+        float2* dst = T2 + (size_t)fl * S * N + c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[(size_t)(t + j * T) * N] = make_float2(re[j], im[j]);
+    }
+}
+
 // ---- pass 3: rows [0, S); real part of columns n' in [0, S) -> out, mask restored
 template <int N, int NT, int MINB>
 __global__ void __launch_bounds__(NT * N / 16, MINB)
@@ -683,6 +738,15 @@ int profile_read(float* out) {
     return 0;
 }
 
+static int fft_persist() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VIP_B200_FFT_PERSIST");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 template <int N, int NT, int MINB>
 static int launch_fft_chunk(const float* in, float* out, float2* T1, float2* T2, const RotParams& g,
                             const int* krot, const double* a, const double* b, const float2* tw,
@@ -705,7 +769,20 @@ static int launch_fft_chunk(const float* in, float* out, float2* T1, float2* T2,
         in, T1, g, krot, a, tw, frame0);
     VB_CHECK_LAUNCH();
     g_timer.mark(st);
-    shear_cols_fft<N, NT, MINB><<<dim3(N / NT, nf), threads, smem, st>>>(T1, T2, g, b, tw, frame0);
+    if (NT == 1 && N >= 2048 && fft_persist()) {
+        static bool cfg2 = false;
+        const size_t smem2 = (size_t)(F::BUF + g.S + 8) * sizeof(float2);
+        if (!cfg2) {
+            VB_CHECK_CUDA(cudaFuncSetAttribute(shear_cols_fft_persist<N, MINB>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            cfg2 = true;
+        }
+        const long long total = (long long)nf * N;
+        const int grid = (int)((total < (long long)kNumSMs * MINB) ? total : (long long)kNumSMs * MINB);
+        shear_cols_fft_persist<N, MINB><<<grid, F::T, smem2, st>>>(T1, T2, g, b, tw, frame0, nf);
+    } else {
+        shear_cols_fft<N, NT, MINB><<<dim3(N / NT, nf), threads, smem, st>>>(T1, T2, g, b, tw, frame0);
+    }
     VB_CHECK_LAUNCH();
     g_timer.mark(st);
     shear_rows_last_fft<N, NT, MINB><<<dim3(ceil_div(g.S, NT), nf), threads, smem, st>>>(
@@ -782,6 +859,8 @@ int derotate_run(const float* in, float* out, int nframes, const RotParams& g, c
                     else if (fft_nt() == 3) rc = launch_fft_chunk<2048, 2, 3>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     else if (fft_nt() == 5) rc = launch_fft_chunk<2048, 2, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     else if (fft_nt() == 1) rc = launch_fft_chunk<2048, 1, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    else if (fft_nt() == 6) rc = launch_fft_chunk<2048, 1, 5>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    else if (fft_nt() == 7) rc = launch_fft_chunk<2048, 1, 6>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     else rc = launch_fft_chunk<2048, 2, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     break;
                 default:   rc = launch_fft_chunk<4096, 2, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;

@@ -13,6 +13,9 @@ from dataclasses import dataclass
 from enum import Enum
 from typing import List, Tuple, Union
 
+import os
+import time
+
 import numpy as np
 import torch
 
@@ -62,17 +65,26 @@ class PCA_ANNULAR_Params:
     left_eigv: bool = False
 
 
+_TIMING = bool(int(os.environ.get("VIP_B200_TIMING", "0")))
+_T = {}
+
+
+def _tick(name, t0):
+    """Development aid (VIP_B200_TIMING=1): accumulate synchronised wall time per section."""
+    if _TIMING:
+        torch.cuda.synchronize()
+        _T[name] = _T.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+    return t0
+
+
 def _unsupported(what):
     raise NotImplementedError(
         f"vip_b200.pca_annular: {what} is not implemented on the B200 path yet (no CPU fallback)")
 
 
-def library_indices(angle_list, pa_thr, max_frames):
-    """``_find_indices_adi(angle_list, f, pa_thr, truncate=True, max_frames=...)`` for every frame f
-    (``preproc/derotation.py:410-496``), vectorised per frame; returns a list of int32 arrays.
-
-    Same integer results as the reference, including the ``np.argsort`` tie-breaking of the
-    truncation step (the very same numpy call on the very same values)."""
+def _library_indices_loop(angle_list, pa_thr, max_frames):
+    """Frame-by-frame restatement of ``_find_indices_adi`` (kept as the exact fallback and test reference)."""
     n = angle_list.shape[0]
     limit = min(n - 1, max_frames)
     out = []
@@ -90,7 +102,48 @@ def library_indices(angle_list, pa_thr, max_frames):
     return out
 
 
-def _segment_residuals(A, A_lib, angle_list, pa_thr, ncomp, min_frames_lib, max_frames_lib, A_ref=None):
+def library_indices(angle_list, pa_thr, max_frames):
+    """``_find_indices_adi(angle_list, f, pa_thr, truncate=True, max_frames=...)`` for every frame f
+    (``preproc/derotation.py:410-496``); returns a list of int32 arrays.
+
+    Vectorised over frames.  The reference keeps the ``limit`` library frames closest in |dPA| through
+    ``np.argsort`` and re-sorts them by index, so only the SET matters: it is unambiguous unless the
+    limit-th and (limit+1)-th smallest |dPA| are equal; those rows (and only those) go through the very
+    same ``np.argsort`` call as the reference, which reproduces its tie-breaking bit-exactly."""
+    ang = np.asarray(angle_list)
+    n = ang.shape[0]
+    limit = min(n - 1, max_frames)
+    D = np.abs(ang[None, :] - ang[:, None])                     # D[f, i] = |ang[i] - ang[f]|
+    col = np.arange(n)[None, :]
+    row = np.arange(n)[:, None]
+    close = (D < pa_thr) & (col < row)
+    index_prev = np.where(close.any(1), close.argmax(1), np.arange(n))
+    far = (D > pa_thr) & (col >= row)
+    index_foll = np.where(far.any(1), far.argmax(1), n)
+    kept = (col < index_prev[:, None]) | (col >= index_foll[:, None])
+    nkept = kept.sum(1)
+    out = [None] * n
+    over = nkept > limit
+    if over.any():
+        rows = np.nonzero(over)[0]
+        Dm = np.where(kept[rows], D[rows], np.inf)
+        v = np.partition(Dm, limit - 1, axis=1)[:, limit - 1]
+        sel = Dm <= v[:, None]
+        exact = sel.sum(1) == limit
+        cols = np.nonzero(sel[exact])[1].reshape(-1, limit).astype(np.int32)
+        for r, c in zip(rows[exact], cols):
+            out[r] = c
+        for r in rows[~exact]:                                    # tie at the truncation boundary
+            k = np.nonzero(kept[r])[0]
+            d_pa = np.abs(ang[k] - ang[r])
+            out[r] = np.sort(k[np.argsort(d_pa)][:limit]).astype(np.int32)
+    for r in np.nonzero(~over)[0]:
+        out[r] = np.nonzero(kept[r])[0].astype(np.int32)
+    return out
+
+
+def _segment_residuals(A, A_lib, angle_list, pa_thr, ncomp, min_frames_lib, max_frames_lib, A_ref=None,
+                       lists=None):
     """Residuals of every frame of one segment matrix ``A`` (n,npx) on the device.
 
     ``A_lib`` = matrix the libraries are drawn from (A, or A - A_sig); ``A_ref`` = optional RDI rows
@@ -106,7 +159,9 @@ def _segment_residuals(A, A_lib, angle_list, pa_thr, ncomp, min_frames_lib, max_
         Cm = kernels.cross_gram(A_lib, V).to(torch.float32).contiguous()
         return kernels.project_subtract(A, Cm, V), k
 
-    lists = library_indices(angle_list, pa_thr, max_frames_lib)
+    t0 = time.perf_counter()
+    if lists is None:
+        lists = library_indices(angle_list, pa_thr, max_frames_lib)
     nref = 0 if A_ref is None else A_ref.shape[0]
     for f, idx in enumerate(lists):
         if len(idx) < min_frames_lib and A_ref is None:
@@ -130,14 +185,19 @@ def _segment_residuals(A, A_lib, angle_list, pa_thr, ncomp, min_frames_lib, max_
     if k > 24:
         _unsupported("more than 24 principal components per annulus")
     G = kernels.gram(lib)
+    t0 = _tick("gram", t0)
     W, iters = kernels.annular_weights(
         G, torch.from_numpy(idx_host).to(dev), torch.from_numpy(lens).to(dev),
         torch.arange(nref, nref + n, dtype=torch.int32, device=dev), k)
     if bool((iters < 0).any()):                  # cannot happen: the direct solver always returns
         bad = int((iters < 0).sum())
         raise RuntimeError(f"vip_b200.pca_annular: {bad} per-frame eigenproblems did not converge")
-    P = kernels.pcs(W, lib)                  # (n, npx) = W . A_lib : the per-frame PSF models
-    return kernels.sub(A, P), k
+    t0 = _tick("weights (batched eigenproblems)", t0)
+    # R = A - W . A_lib  (the per-frame PSF models) as one fp32 GEMM with alpha = -1, beta = 1
+    R = A.clone()
+    kernels.gemm(W.unsqueeze(0), lib.unsqueeze(0), R.unsqueeze(0), alpha=-1.0, beta=1.0)
+    _tick("apply W.A_lib and subtract", t0)
+    return R, k
 
 
 def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segments=1, delta_rot=1, ncomp=1,
@@ -186,13 +246,24 @@ def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segme
     _check_rot_options(imlib, rot_options.get("cxy"), rot_options.get("border_mode", "constant"),
                        rot_options.get("edge_blend"), array.shape)
 
+    t0 = time.perf_counter()
     dev = require_cuda()
     cube_dev = to_device_f32(array, dev).reshape(n, y * x)
     ref_dev = to_device_f32(cube_ref, dev).reshape(cube_ref.shape[0], y * x) if cube_ref is not None else None
     sig_dev = to_device_f32(cube_sig, dev).reshape(n, y * x) if cube_sig is not None else None
     cube_out = torch.zeros_like(cube_dev)
+    t0 = _tick("upload", t0)
 
     verbose_ann = (int(verbose) + int(cube_ref is None)) if verbose else verbose
+    # library index lists of every annulus (host integer logic, independent of the pixel data): computed
+    # up-front on a few host threads so that they do not serialise with the GPU work of each annulus
+    thresholds = [_define_annuli(angle_list, ann, n_annuli, fwhm, radius_int, asize, delta_rot[ann],
+                                 n_segments[ann], False, True)[0] for ann in range(n_annuli)]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, max(1, n_annuli))) as pool:
+        all_lists = list(pool.map(lambda thr: library_indices(angle_list, thr, max_frames_lib) if thr != 0 else None,
+                                  thresholds))
+    t0 = _tick("index lists (host)", t0)
     for ann in range(n_annuli):
         if isinstance(ncomp, (tuple, np.ndarray)):
             if len(ncomp) != n_annuli:
@@ -212,16 +283,21 @@ def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segme
                      if ref_dev is not None else None)
             A_lib = A - kernels.gather_columns(sig_dev, cols) if sig_dev is not None else A
             R, _ = _segment_residuals(A, A_lib, angle_list, pa_thr, ncompann, min_frames_lib,
-                                      max_frames_lib, A_ref)
+                                      max_frames_lib, A_ref, lists=all_lists[ann])
             kernels.scatter_columns(R, cols, cube_out)
         if verbose == 1:
             print("Done PCA with {} for current annulus".format(_mode_name(svd_mode)))
 
+    t0 = time.perf_counter()
     cube_out = cube_out.reshape(n, y, x)
     mask_val = float(rot_options.get("mask_val", np.nan))
     interp_zeros = bool(rot_options.get("interp_zeros", False))
     cube_der = derotate_device(cube_out, -angle_list, mask_val=mask_val, interp_zeros=interp_zeros)
     frame = collapse_device(cube_der, mode=collapse, w=weights)
+    _tick("derotate + collapse", t0)
+    if _TIMING:
+        print("vip_b200.pca_annular timing:", {k_: round(v_, 4) for k_, v_ in _T.items()})
+        _T.clear()
     if verbose:
         print("Done derotating and combining.")
     if full_output:
