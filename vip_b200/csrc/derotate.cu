@@ -396,9 +396,10 @@ struct ShearFft {
         transform_sync<T>(tr);
 #pragma unroll
         for (int e = 0; e < 16; ++e) buf[sw2(16 * t + e)] = make_float2(re[e], im[e]);
+        // twiddles of the next stage are fetched BEFORE the barrier so that the load latency hides behind it
+        w.load<N, true>(tw, npp * 16);
         transform_sync<T>(tr);
         // ---- inverse stage 2
-        w.load<N, true>(tw, npp * 16);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const float2 v = buf[sw2(k1p * L1 + j * L2 + npp)];
@@ -410,9 +411,9 @@ struct ShearFft {
         transform_sync<T>(tr);
 #pragma unroll
         for (int j = 0; j < 16; ++j) buf[sw1(k1p * L1 + j * L2 + npp)] = make_float2(re[j], im[j]);
+        w.load<N, true>(tw, t);
         transform_sync<T>(tr);
         // ---- inverse stage 1
-        w.load<N, true>(tw, t);
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) {
             const float2 v = buf[sw1(k1 * L1 + t)];
@@ -742,7 +743,7 @@ static int fft_persist() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("VIP_B200_FFT_PERSIST");
-        v = e ? atoi(e) : 1;
+        v = e ? atoi(e) : 0;       // measured: 12.3 ms vs 11.9 ms for the one-shot kernel at config 2
     }
     return v;
 }
