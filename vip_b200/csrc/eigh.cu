@@ -524,8 +524,286 @@ __global__ void topk_output_kernel(const double* __restrict__ X, const double* _
     if (i < k) evals[i] = theta[i];
 }
 
+// =====================================================================================
+// Fused persistent variant of the subspace iteration (one cooperative launch for all iterations)
+// =====================================================================================
+// The six kernels above are latency-bound (n x 32 blocks on a 500 x 500 matrix): a launch per phase
+// costs more than the phase.  Here ceil(n / RPC) co-resident CTAs keep their RPC rows of X and Y in
+// shared memory across the phases of an iteration and meet at a grid barrier between phases:
+//   A  Y_rows = G_rows X  (+ partial X^T Y or Y^T Y)      all CTAs
+//   B  Rayleigh-Ritz (Jacobi on the B x B matrix)          CTA 0, RR iterations only
+//   C  rotate own rows, partial Gram of the rotated block  all CTAs, RR iterations only
+//   D  Cholesky of the (column-normalised) Gram, convergence test     CTA 0, warp 0
+//   E  own rows  X = Y D^-1 R^-1                           all CTAs
+// Rayleigh-Ritz runs every `rr_every`-th iteration; the iteration before it orthonormalises twice
+// (CholeskyQR2) so that the Ritz step sees an orthonormal X (a single Cholesky-QR of G X leaves
+// 1e-4 of non-orthogonality when lambda_0 / lambda_B ~ 1e6, which stalls the residual test).
+
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const unsigned int target = (epoch + 1u) * gridDim.x;
+        const long long t0 = clock64();
+        while (*((volatile unsigned int*)bar) < target) {
+            if (clock64() - t0 > 4000000000LL) __trap();      // never hang the GPU on a protocol bug
+        }
+        __threadfence();
+    }
+    ++epoch;
+    __syncthreads();
+}
+
+template <int B>
+struct FusedSmem {
+    static constexpr int RPC = 512 / B, TJ = 64;
+    struct PhaseA { double Gs[RPC][TJ + 1]; double Xt[TJ][B]; };
+    struct PhaseB { double Tm[B][B + 1]; double th[B]; int order[B]; int rotated; };
+    struct PhaseD { double Sn[B][B + 1]; double Rm[B][B + 1]; };
+    union U { PhaseA a; PhaseB b; PhaseD d; };
+};
+
+template <int B>
+__global__ void __launch_bounds__(512, 1)
+topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int max_iter, double jthr, int rr_every,
+                  double* X, double* T, double* S, double* Qm, double* R, double* theta, double* res, double* dinv,
+                  TopkState* st, unsigned int* bar) {
+    using FS = FusedSmem<B>;
+    constexpr int RPC = FS::RPC, TJ = FS::TJ;
+    __shared__ typename FS::U u;
+    __shared__ double Ys[RPC][B + 1], Xm[RPC][B + 1], Qs[B][B + 1], dv[B];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tr = tid / B, tc = tid % B;
+    const int r0 = blockIdx.x * RPC, r = r0 + tr;
+    unsigned int epoch = 0;
+
+    // partial Gram  out[a][b] += sum_rows P[row][a] Q[row][b]  (atomics into a zeroed B x B accumulator)
+    auto partial_gram = [&](const double (*P)[B + 1], const double (*Q)[B + 1], double* out) {
+        for (int e = tid; e < B * B; e += 512) {
+            const int a = e / B, b = e % B;
+            double s = 0.0;
+#pragma unroll 8
+            for (int q = 0; q < RPC; ++q) s = fma(P[q][a], Q[q][b], s);
+            atomicAdd(&out[e], s);
+        }
+    };
+    // phase D on CTA 0 / warp 0
+    auto cholesky_phase = [&](int check, int count_iter) {
+        if (blockIdx.x == 0 && warp == 0) {
+            if (lane == 0) {
+                if (count_iter) st->iters += 1;
+                if (check) {
+                    double worst = 0.0;
+                    for (int q = 0; q < k; ++q) worst = fmax(worst, sqrt(__ldcg(&res[q])));
+                    const double ref = __ldcg(&theta[k - 1]);
+                    st->worst = ref > 0.0 ? worst / ref : 0.0;
+                    if (worst <= tol * ref) st->converged = 1;
+                }
+            }
+            __syncwarp();
+            for (int c = lane; c < B; c += 32) {
+                const double d = __ldcg(&S[c * B + c]);
+                dv[c] = d > 0.0 ? rsqrt(d) : 0.0;
+            }
+            __syncwarp();
+            for (int e = lane; e < B * B; e += 32) u.d.Sn[e / B][e % B] = __ldcg(&S[e]) * dv[e / B] * dv[e % B];
+            __syncwarp();
+            for (int j = 0; j < B; ++j) {
+                double d = u.d.Sn[j][j];
+                for (int m = 0; m < j; ++m) d -= u.d.Rm[m][j] * u.d.Rm[m][j];
+                d = (d > 1e-300) ? sqrt(d) : 1e-150;
+                for (int c = j + lane; c < B; c += 32) {
+                    double v = u.d.Sn[j][c];
+                    for (int m = 0; m < j; ++m) v -= u.d.Rm[m][j] * u.d.Rm[m][c];
+                    u.d.Rm[j][c] = (c == j) ? d : v / d;
+                }
+                __syncwarp();
+            }
+            for (int e = lane; e < B * B; e += 32) {
+                R[e] = (e / B <= e % B) ? u.d.Rm[e / B][e % B] : 0.0;
+                S[e] = 0.0;
+                T[e] = 0.0;
+            }
+            for (int c = lane; c < B; c += 32) { dinv[c] = dv[c]; res[c] = 0.0; }
+        }
+    };
+    // phase E: own rows  X = src D^-1 R^-1  (one thread per row), result to global X and to Xm
+    auto solve_phase = [&](double (*src)[B + 1]) {
+        for (int e = tid; e < B * B; e += 512) Qs[e / B][e % B] = __ldcg(&R[e]);
+        if (tid < B) dv[tid] = __ldcg(&dinv[tid]);
+        __syncthreads();
+        if (tid < RPC) {
+            double x[B];
+#pragma unroll
+            for (int c = 0; c < B; ++c) {
+                double v = src[tid][c] * dv[c];
+#pragma unroll
+                for (int m = 0; m < c; ++m) v -= x[m] * Qs[m][c];
+                x[c] = v / Qs[c][c];
+            }
+#pragma unroll
+            for (int c = 0; c < B; ++c) {
+                Xm[tid][c] = x[c];
+                if (r0 + tid < n) X[(size_t)(r0 + tid) * B + c] = x[c];
+            }
+        }
+        __syncthreads();
+    };
+
+    for (int it = 0; it < max_iter; ++it) {
+        const int ph = it % rr_every;
+        const bool rr = ph == rr_every - 1;
+        const bool qr2 = !rr && ph == rr_every - 2;
+
+        // ---- A: Y rows = G rows . X
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int j0 = 0; j0 < n; j0 += TJ) {
+            for (int e = tid; e < RPC * TJ; e += 512) {
+                const int q = e / TJ, j = e % TJ;
+                u.a.Gs[q][j] = (r0 + q < n && j0 + j < n) ? G[(size_t)(r0 + q) * n + j0 + j] : 0.0;
+            }
+            for (int e = tid; e < TJ * B; e += 512) {
+                const int j = e / B;
+                u.a.Xt[j][e % B] = (j0 + j < n) ? __ldcg(&X[(size_t)(j0 + j) * B + e % B]) : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int j = 0; j < TJ; j += 2) {
+                acc0 = fma(u.a.Gs[tr][j], u.a.Xt[j][tc], acc0);
+                acc1 = fma(u.a.Gs[tr][j + 1], u.a.Xt[j + 1][tc], acc1);
+            }
+            __syncthreads();
+        }
+        Ys[tr][tc] = (r < n) ? acc0 + acc1 : 0.0;
+        if (rr) Xm[tr][tc] = (r < n) ? __ldcg(&X[(size_t)r * B + tc]) : 0.0;
+        __syncthreads();
+        if (rr) partial_gram(Xm, Ys, T); else partial_gram(Ys, Ys, S);
+        grid_barrier(bar, epoch);
+
+        if (rr) {
+            // ---- B: Rayleigh-Ritz on CTA 0 (one-sided Jacobi on the columns of T, one column pair per warp)
+            if (blockIdx.x == 0) {
+                for (int e = tid; e < B * B; e += 512) {
+                    const int a = e / B, b = e % B;
+                    u.b.Tm[a][b] = 0.5 * (__ldcg(&T[a * B + b]) + __ldcg(&T[b * B + a]));
+                }
+                __syncthreads();
+                for (int sweep = 0; sweep < 40; ++sweep) {
+                    if (tid == 0) u.b.rotated = 0;
+                    // squared column norms, refreshed once per sweep and updated analytically per rotation
+                    // (al' = al - t ga, be' = be + t ga), so a rotation needs ONE shuffle reduction, not three
+                    if (tid < B) {
+                        double sq = 0.0;
+                        for (int i = 0; i < B; ++i) sq = fma(u.b.Tm[i][tid], u.b.Tm[i][tid], sq);
+                        u.b.th[tid] = sq;
+                    }
+                    __syncthreads();
+                    for (int rd = 0; rd < B - 1; ++rd) {
+                        if (warp < B / 2) {
+                            const int pr = warp, mm = B - 1;
+                            int a, b;
+                            if (pr == 0) { a = mm; b = rd % mm; } else { a = (rd + pr) % mm; b = (rd - pr + mm) % mm; }
+                            double ga = 0;
+                            for (int i = lane; i < B; i += 32) ga = fma(u.b.Tm[i][a], u.b.Tm[i][b], ga);
+                            ga = warp_sum(ga);
+                            const double al = u.b.th[a], be = u.b.th[b];
+                            if (al > 0 && be > 0 && ga * ga > jthr * jthr * al * be) {
+                                // t = tan(theta) = sign(d) 2ga / (|d| + sqrt(d^2 + 4 ga^2)),  d = be - al
+                                const double d = be - al, g2 = 2.0 * ga;
+                                const double t = copysign(g2, d * g2) / (fabs(d) + sqrt(fma(d, d, g2 * g2)));
+                                const double c = rsqrt(fma(t, t, 1.0)), sn = c * t;
+                                for (int i = lane; i < B; i += 32) {
+                                    const double x = u.b.Tm[i][a], y = u.b.Tm[i][b];
+                                    u.b.Tm[i][a] = c * x - sn * y;
+                                    u.b.Tm[i][b] = sn * x + c * y;
+                                }
+                                if (lane == 0) {
+                                    u.b.th[a] = al - t * ga;
+                                    u.b.th[b] = be + t * ga;
+                                    u.b.rotated = 1;
+                                }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                    const int any = u.b.rotated;
+                    __syncthreads();
+                    if (!any) break;
+                }
+                if (tid < B) {
+                    double sq = 0.0;
+                    for (int i = 0; i < B; ++i) sq = fma(u.b.Tm[i][tid], u.b.Tm[i][tid], sq);
+                    u.b.th[tid] = sqrt(sq);
+                }
+                __syncthreads();
+                if (tid < B) {
+                    int rk = 0;
+                    for (int j = 0; j < B; ++j)
+                        rk += (u.b.th[j] > u.b.th[tid] || (u.b.th[j] == u.b.th[tid] && j < tid));
+                    u.b.order[rk] = tid;
+                }
+                __syncthreads();
+                for (int e = tid; e < B * B; e += 512) {
+                    const int i = e / B, q = e % B;
+                    const int src = u.b.order[q];
+                    Qm[e] = u.b.th[src] > 0.0 ? u.b.Tm[i][src] / u.b.th[src] : (i == src ? 1.0 : 0.0);
+                }
+                if (tid < B) theta[tid] = u.b.th[u.b.order[tid]];
+            }
+            grid_barrier(bar, epoch);
+
+            // ---- C: rotate own rows, partial Gram of the rotated Y, residuals
+            for (int e = tid; e < B * B; e += 512) Qs[e / B][e % B] = __ldcg(&Qm[e]);
+            if (tid < B) dv[tid] = __ldcg(&theta[tid]);
+            __syncthreads();
+            double yr = 0.0, xr = 0.0;
+#pragma unroll 8
+            for (int m = 0; m < B; ++m) {
+                yr = fma(Ys[tr][m], Qs[m][tc], yr);
+                xr = fma(Xm[tr][m], Qs[m][tc], xr);
+            }
+            __syncthreads();
+            Ys[tr][tc] = yr;
+            Xm[tr][tc] = xr;
+            if (r < n) X[(size_t)r * B + tc] = xr;            // Ritz vectors (kept if this step converges)
+            __syncthreads();
+            partial_gram(Ys, Ys, S);
+            if (tid < B) {
+                double sq = 0.0;
+                const double th = dv[tid];
+                for (int q = 0; q < RPC; ++q) {
+                    const double d = Ys[q][tid] - th * Xm[q][tid];
+                    sq = fma(d, d, sq);
+                }
+                atomicAdd(&res[tid], sq);
+            }
+            grid_barrier(bar, epoch);
+        }
+
+        // ---- D: Cholesky (+ convergence test after a Ritz step)
+        cholesky_phase(rr ? 1 : 0, 1);
+        grid_barrier(bar, epoch);
+        if (rr && __ldcg(&st->converged)) break;
+
+        // ---- E: own rows X = Y D^-1 R^-1
+        solve_phase(Ys);
+        if (qr2) {
+            // second Cholesky-QR pass on the freshly orthogonalised block
+            partial_gram(Xm, Xm, S);
+            grid_barrier(bar, epoch);
+            cholesky_phase(0, 0);
+            grid_barrier(bar, epoch);
+            for (int e = tid; e < RPC * B; e += 512) Ys[e / B][e % B] = Xm[e / B][e % B];
+            __syncthreads();
+            solve_phase(Ys);
+        }
+        grid_barrier(bar, epoch);
+    }
+}
+
 size_t eigh_topk_workspace_bytes(int n, int B) {
-    return ((size_t)2 * n * B + 4 * (size_t)B * B + 4 * B) * sizeof(double) + 256;
+    return ((size_t)2 * n * B + 4 * (size_t)B * B + 4 * B) * sizeof(double) + 512;
 }
 
 template <int B>
@@ -541,7 +819,7 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
     double* res = theta + B;
     double* dinv = res + B;
     TopkState* state = reinterpret_cast<TopkState*>(dinv + 2 * B);
-    VB_CHECK_CUDA(cudaMemsetAsync(T, 0, (size_t)(4 * B * B + 4 * B) * sizeof(double) + sizeof(TopkState), st));
+    VB_CHECK_CUDA(cudaMemsetAsync(T, 0, (size_t)(4 * B * B + 4 * B) * sizeof(double) + sizeof(TopkState) + 128, st));
     int nl = 0;
     const int grows = ceil_div(n, 16);
     topk_init_kernel<B><<<ceil_div(n * B, 256), 256, 0, st>>>(Y, n);
@@ -553,7 +831,29 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
     VB_CHECK_LAUNCH();
     TopkState h{};
     const char* je = getenv("VIP_B200_RITZ_THR");
-    const double jthr = je ? atof(je) : 1e-15;
+    double jthr = je ? atof(je) : 1e-15;
+    // fused persistent kernel: all iterations in one cooperative launch (grid = ceil(n / rows-per-CTA) <= #SMs)
+    const char* fe = getenv("VIP_B200_TOPK_FUSED");
+    const int fused_grid = ceil_div(n, 512 / B);
+    if ((fe ? atoi(fe) : 1) && fused_grid <= kNumSMs) {
+        const char* re = getenv("VIP_B200_TOPK_RR");
+        int rr_every = re ? atoi(re) : 4;
+        if (rr_every < 1) rr_every = 1;
+        unsigned int* bar = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(state) + 64);
+        int fmax = ceil_div(max_iter, rr_every) * rr_every;
+        void* args[] = {(void*)&G, (void*)&n, (void*)&k, (void*)&tol, (void*)&fmax, (void*)&jthr, (void*)&rr_every,
+                        (void*)&X, (void*)&T, (void*)&S, (void*)&Qm, (void*)&R, (void*)&theta, (void*)&res,
+                        (void*)&dinv, (void*)&state, (void*)&bar};
+        VB_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)topk_fused_kernel<B>, dim3(fused_grid), dim3(512), args,
+                                                  0, st));
+        topk_output_kernel<B><<<ceil_div(n, 256), 256, 0, st>>>(X, theta, n, k, evals, evecs);
+        VB_CHECK_LAUNCH();
+        VB_CHECK_CUDA(cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, st));
+        VB_CHECK_CUDA(cudaStreamSynchronize(st));
+        if (launches) *launches = nl + 2;
+        if (info) { info[0] = h.iters; info[1] = h.converged; }
+        return 0;
+    }
     // Rayleigh-Ritz every iteration: without it the columns of G X all tilt towards the dominant
     // eigenvector (lambda_0 / lambda_B ~ 1e5) and the Cholesky-QR of Y^T Y (condition number squared)
     // loses the trailing directions -- measured: no convergence in 400 steps with RR every 4th step.
