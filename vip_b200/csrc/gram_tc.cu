@@ -474,7 +474,7 @@ size_t gram_tc_workspace_bytes(int n, size_t p) { return gram_tc_plan(n, p).tota
 // the tensor-core path pays off (and its tolerances were validated) for large problems only
 bool gram_tc_eligible(int n, size_t p) {
     if (tc::env_int("VIP_B200_GRAM_TC", 1) == 0) return false;
-    return n >= 32 && n <= 64 * tc::TM && (size_t)n * p >= ((size_t)1 << 24);
+    return n >= 32 && n <= 64 * tc::TM && (size_t)n * p >= ((size_t)1 << 22);
 }
 
 // zero the accumulators and upload the upper-triangular tile list
