@@ -862,6 +862,8 @@ int derotate_run(const float* in, float* out, int nframes, const RotParams& g, c
                     else if (fft_nt() == 1) rc = launch_fft_chunk<2048, 1, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     else if (fft_nt() == 6) rc = launch_fft_chunk<2048, 1, 5>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     else if (fft_nt() == 7) rc = launch_fft_chunk<2048, 1, 6>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    else if (fft_nt() == 8) rc = launch_fft_chunk<2048, 1, 3>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    else if (fft_nt() == 9) rc = launch_fft_chunk<2048, 1, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     else rc = launch_fft_chunk<2048, 2, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     break;
                 default:   rc = launch_fft_chunk<4096, 2, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;

@@ -10,6 +10,7 @@
 // Optional mean deflation (M = 1 m^T + D, G = D D^T + rank-2 terms in fp64) is kept for
 // callers that want it; it is not needed for accuracy any more.
 #include "common.cuh"
+#include <vector>
 
 namespace vb {
 
@@ -214,12 +215,13 @@ int gram_f32(const float* A, int n, size_t p, int deflate, double* G, void* ws, 
     int2* tiles = reinterpret_cast<int2*>(w);
 
     const int nt = ceil_div(n, GT);
-    int2 htiles[64 * 64];
-    VB_REQUIRE(nt <= 64, "gram: n=%d too large for the tile list (max %d)", n, 64 * GT);
-    int ntiles = 0;
+    VB_REQUIRE(nt <= 512, "gram: n=%d too large (max %d)", n, 512 * GT);
+    std::vector<int2> htiles;
     for (int i = 0; i < nt; ++i)
-        for (int j = i; j < nt; ++j) htiles[ntiles++] = make_int2(i, j);
-    VB_CHECK_CUDA(cudaMemcpyAsync(tiles, htiles, ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
+        for (int j = i; j < nt; ++j) htiles.push_back(make_int2(i, j));
+    const int ntiles = (int)htiles.size();
+    // pageable source: the runtime stages the data before returning, so the vector may go out of scope
+    VB_CHECK_CUDA(cudaMemcpyAsync(tiles, htiles.data(), ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
     VB_CHECK_CUDA(cudaMemsetAsync(Gd, 0, (size_t)n * n * sizeof(double), st));
     int nl = 0;
     if (deflate) {
@@ -285,12 +287,12 @@ int upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, voi
     w += (((size_t)n + 1) * sizeof(double) + 255) / 256 * 256;
     int2* tiles = reinterpret_cast<int2*>(w);
     const int nt = ceil_div(n, GT);
-    int2 htiles[64 * 64];
-    VB_REQUIRE(nt <= 64, "upload_gram: n=%d too large for the tile list", n);
-    int ntiles = 0;
+    VB_REQUIRE(nt <= 512, "upload_gram: n=%d too large (max %d)", n, 512 * GT);
+    std::vector<int2> htiles;
     for (int i = 0; i < nt; ++i)
-        for (int j = i; j < nt; ++j) htiles[ntiles++] = make_int2(i, j);
-    VB_CHECK_CUDA(cudaMemcpyAsync(tiles, htiles, ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
+        for (int j = i; j < nt; ++j) htiles.push_back(make_int2(i, j));
+    const int ntiles = (int)htiles.size();
+    VB_CHECK_CUDA(cudaMemcpyAsync(tiles, htiles.data(), ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
     VB_CHECK_CUDA(cudaMemsetAsync(Gd, 0, (size_t)n * n * sizeof(double), st));
     // the copy stream must not start overwriting M before earlier work on `st` is done with it
     VB_CHECK_CUDA(cudaEventRecord(start_ev, st));
@@ -320,16 +322,16 @@ int upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, voi
 int cross_gram_f32(const float* A, int na, const float* B, int nb, size_t p, double* C, void* ws,
                    size_t ws_bytes, int kchunk, cudaStream_t st) {
     const int nta = ceil_div(na, GT), ntb = ceil_div(nb, GT);
-    VB_REQUIRE((size_t)nta * ntb <= 4096, "cross_gram: too many tiles");
+    VB_REQUIRE((size_t)nta * ntb <= 65535, "cross_gram: too many tiles");
     VB_REQUIRE(ws_bytes >= (size_t)nta * ntb * sizeof(int2), "cross_gram: workspace too small");
     if (kchunk <= 0) kchunk = 4096;
     kchunk = ceil_div(kchunk, GK) * GK;
-    int2 htiles[4096];
-    int ntiles = 0;
+    std::vector<int2> htiles;
     for (int i = 0; i < nta; ++i)
-        for (int j = 0; j < ntb; ++j) htiles[ntiles++] = make_int2(i, j);
+        for (int j = 0; j < ntb; ++j) htiles.push_back(make_int2(i, j));
+    const int ntiles = (int)htiles.size();
     int2* tiles = reinterpret_cast<int2*>(ws);
-    VB_CHECK_CUDA(cudaMemcpyAsync(tiles, htiles, ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
+    VB_CHECK_CUDA(cudaMemcpyAsync(tiles, htiles.data(), ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
     VB_CHECK_CUDA(cudaMemsetAsync(C, 0, (size_t)na * nb * sizeof(double), st));
     const unsigned nchunks = (unsigned)ceil_div(p, (size_t)kchunk);
     VB_REQUIRE(nchunks <= 65535, "cross_gram: too many K chunks");

@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdlib>
+#include <vector>
 
 namespace vb {
 
@@ -474,7 +475,7 @@ size_t gram_tc_workspace_bytes(int n, size_t p) { return gram_tc_plan(n, p).tota
 // the tensor-core path pays off (and its tolerances were validated) for large problems only
 bool gram_tc_eligible(int n, size_t p) {
     if (tc::env_int("VIP_B200_GRAM_TC", 1) == 0) return false;
-    return n >= 32 && n <= 64 * tc::TM && (size_t)n * p >= ((size_t)1 << 22);
+    return n >= 32 && n <= 512 * tc::TM && (size_t)n * p >= ((size_t)1 << 22);
 }
 
 // zero the accumulators and upload the upper-triangular tile list
@@ -483,12 +484,13 @@ int gram_tc_begin(int n, size_t p, void* ws, size_t ws_bytes, int* ntiles_out, c
     VB_REQUIRE(ws_bytes >= pl.total, "gram_tc: workspace too small (%zu < %zu)", ws_bytes, pl.total);
     char* w = reinterpret_cast<char*>(ws);
     const int nt = ceil_div(n, tc::TM);
-    VB_REQUIRE(nt <= 64, "gram_tc: n=%d too large for the tile list", n);
-    int2 htiles[64 * 65 / 2];
-    int ntiles = 0;
+    VB_REQUIRE(nt <= 512, "gram_tc: n=%d too large (max %d)", n, 512 * tc::TM);
+    std::vector<int2> htiles;
     for (int i = 0; i < nt; ++i)
-        for (int j = i; j < nt; ++j) htiles[ntiles++] = make_int2(i, j);
-    VB_CHECK_CUDA(cudaMemcpyAsync(w + pl.off_tiles, htiles, ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
+        for (int j = i; j < nt; ++j) htiles.push_back(make_int2(i, j));
+    const int ntiles = (int)htiles.size();
+    // pageable source: the runtime stages the data before returning, so the vector may go out of scope
+    VB_CHECK_CUDA(cudaMemcpyAsync(w + pl.off_tiles, htiles.data(), ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
     VB_CHECK_CUDA(cudaMemsetAsync(w + pl.off_Gd, 0, (size_t)n * n * sizeof(double), st));
     VB_CHECK_CUDA(cudaMemsetAsync(w + pl.off_Dm, 0, ((size_t)n + 1) * sizeof(double), st));
     *ntiles_out = ntiles;
