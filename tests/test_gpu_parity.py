@@ -539,6 +539,12 @@ def test_pca_annular_golden(vb, golden, golden_inputs):
     assert rel_err(fr, g["ann_frame"]) < FRAME_TOL
     fr = vb.pca_annular(cube, angs, ncomp=2, asize=6, n_segments=3, delta_rot=0.5, radius_int=4, verbose=False)
     assert rel_err(fr, g["ann_seg_frame"]) < FRAME_TOL
+    # list ncomp: 4-d residual cubes (float64 like the reference's np.zeros buffers) and a list of frames
+    co4, cd4, frl = vb.pca_annular(cube, angs, ncomp=[1, 3], asize=6, verbose=False, full_output=True)
+    assert co4.shape == (2,) + cube.shape and co4.dtype == np.float64 and isinstance(frl, list) and len(frl) == 2
+    assert np.max(np.abs(co4[1, 5] - g["ann_list_cube_out_1_5"])) < PCA_TOL * scale
+    for i in range(2):
+        assert rel_err(frl[i], g["ann_list_frames"][i]) < FRAME_TOL
 
 
 def test_pca_annular_options_vs_oracle(vb, golden_inputs):
@@ -556,6 +562,22 @@ def test_pca_annular_options_vs_oracle(vb, golden_inputs):
         scale = np.max(np.abs(o[0]))
         assert np.max(np.abs(r[0] - o[0])) < PCA_TOL * scale, kw
         assert rel_err(r[2], o[2]) < FRAME_TOL, kw
+
+
+def test_pca_annular_4d_golden(vb, golden, golden_inputs):
+    """pca_annular on a 4-d cube without scale_list: per-channel annular PCA + collapse_ifs (float64 frame)."""
+    g = golden["pca_annular_4d"]
+    cube4, angs4, _ = golden_inputs["ifs"]
+    cube4 = cube4[:3]
+    co, cd, fr = vb.pca_annular(cube4, angs4, ncomp=2, asize=5, delta_rot=(0.05, 0.2), verbose=False,
+                                full_output=True)
+    assert co.shape == cube4.shape and co.dtype == np.float32 and fr.dtype == np.float64
+    scale = np.max(np.abs(co))
+    assert np.max(np.abs(co[1, 3] - g["ann4d_cube_out_ch1_fr3"])) < PCA_TOL * scale
+    assert np.max(np.abs(cd[2, 5] - g["ann4d_cube_der_ch2_fr5"])) < PCA_TOL * scale
+    assert rel_err(fr, g["ann4d_frame"]) < FRAME_TOL
+    fr = vb.pca_annular(cube4, angs4, ncomp=[1, 2, 3], asize=5, delta_rot=0.1, collapse_ifs="median", verbose=False)
+    assert rel_err(fr, g["ann4d_list_median"]) < FRAME_TOL
 
 
 def test_pca_annular_errors(vb, golden_inputs):

@@ -98,6 +98,8 @@ def main():
     out["ann_frame"], out["ann_cube_out5"] = fr, co[5]
     out["ann_seg_frame"] = pca_annular(cube, angs, ncomp=2, asize=6, n_segments=3, delta_rot=0.5,
                                        radius_int=4, verbose=False)
+    co, cd, frl = pca_annular(cube, angs, ncomp=[1, 3], asize=6, verbose=False, full_output=True)
+    out["ann_list_frames"], out["ann_list_cube_out_1_5"] = np.array(frl), co[1, 5]
     np.savez_compressed(os.path.join(OUT, "pca_annular.npz"), **out)
 
     out = {}
@@ -121,8 +123,21 @@ def main():
     np.savez_compressed(os.path.join(OUT, "collapse.npz"), **out)
     make_grid_4d(inp, pca)
     make_sdi_single(inp, pca)
+    make_annular_4d(inp, pca_annular)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def make_annular_4d(inp, pca_annular):
+    """pca_annular on a 4-d cube without scale_list (per-channel annular ADI + collapse_ifs)."""
+    cube4, angs4, _ = inp["ifs"]
+    cube4 = cube4[:3]
+    out = {}
+    co, cd, fr = pca_annular(cube4, angs4, ncomp=2, asize=5, delta_rot=(0.05, 0.2), verbose=False, full_output=True)
+    out["ann4d_frame"], out["ann4d_cube_out_ch1_fr3"], out["ann4d_cube_der_ch2_fr5"] = fr, co[1, 3], cd[2, 5]
+    out["ann4d_list_median"] = pca_annular(cube4, angs4, ncomp=[1, 2, 3], asize=5, delta_rot=0.1,
+                                           collapse_ifs="median", verbose=False)
+    np.savez_compressed(os.path.join(OUT, "pca_annular_4d.npz"), **out)
 
 
 def make_sdi_single(inp, pca):

@@ -311,6 +311,11 @@ struct ShearFft {
     }
     __device__ __forceinline__ static int sw2(int P) { return P ^ ((P >> 4) & 15); }
 
+    // Stages 2 and 3 (forward and inverse) only exchange data inside one length-L1 block of the buffer,
+    // i.e. among the N/256 consecutive threads (<= 16, same warp) that own it: a warp-level barrier
+    // orders those exchanges, and only the two stage-1 transposes need all T threads.
+    __device__ __forceinline__ static void group_sync() { __syncwarp(); }
+
     // IN4 : only re/im[0..3] (n' = t + j*T, j < 4) and the sample n' = 4T (x4, thread 0) are non-zero.
     // OUT4: only outputs j < 4 are produced (re/im[0..3]).
     // Otherwise re/im[j] <-> n' = t + j*T for j = 0..15 on input and output.
@@ -361,14 +366,14 @@ struct ShearFft {
         }
         dif<16, -1, 0>(re, im);
         w.load<N, false>(tw, npp * 16);
-        transform_sync<T>(tr);
+        group_sync();
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) {
             const int r = brev(k2, 4);
             w.apply(k2, re[r], im[r]);
             buf[sw2(k1p * L1 + k2 * L2 + npp)] = make_float2(re[r], im[r]);
         }
-        transform_sync<T>(tr);
+        group_sync();
         // ---- forward stage 3: radix-R3 on 16 contiguous points, phase, inverse stage 3
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
@@ -393,12 +398,12 @@ struct ShearFft {
             }
         }
         GroupFft<R3, +1, G3>::inv(re, im);
-        transform_sync<T>(tr);
+        group_sync();
 #pragma unroll
         for (int e = 0; e < 16; ++e) buf[sw2(16 * t + e)] = make_float2(re[e], im[e]);
         // twiddles of the next stage are fetched BEFORE the barrier so that the load latency hides behind it
         w.load<N, true>(tw, npp * 16);
-        transform_sync<T>(tr);
+        group_sync();
         // ---- inverse stage 2
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -408,7 +413,7 @@ struct ShearFft {
             w.apply(j, re[r], im[r]);
         }
         dit<16, +1, 0>(re, im);
-        transform_sync<T>(tr);
+        group_sync();
 #pragma unroll
         for (int j = 0; j < 16; ++j) buf[sw1(k1p * L1 + j * L2 + npp)] = make_float2(re[j], im[j]);
         w.load<N, true>(tw, t);

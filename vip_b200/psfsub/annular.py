@@ -238,7 +238,20 @@ def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segme
     if _mode_name(svd_mode) not in _EXACT_MODES:
         _unsupported(f"svd_mode={_mode_name(svd_mode)!r}")
     if isinstance(ncomp, list):
-        _unsupported("a list of `ncomp` (one residual cube per value)")
+        # one residual cube per number of components (pca_local.py:665-668, 799-807).  do_pca_patch
+        # truncates the SVD of max(ncomp) components (:893-903), which equals one run per value.
+        kw = dict(radius_int=radius_int, fwhm=fwhm, asize=asize, n_segments=n_segments, delta_rot=delta_rot,
+                  svd_mode=svd_mode, nproc=nproc, min_frames_lib=min_frames_lib, max_frames_lib=max_frames_lib,
+                  tol=tol, scaling=scaling, imlib=imlib, interpolation=interpolation, collapse=collapse,
+                  full_output=True, verbose=verbose, cube_ref=cube_ref, theta_init=theta_init, weights=weights,
+                  cube_sig=cube_sig, left_eigv=left_eigv)
+        runs = [_pca_adi_rdi_device(cube, angle_list, ncomp=int(v), **kw, **rot_options) for v in ncomp]
+        cube_out = torch.stack([r[0] for r in runs])
+        cube_der = torch.stack([r[1] for r in runs])
+        frames = [r[2] for r in runs]
+        if full_output:
+            return cube_out, cube_der, frames
+        return frames
     if isinstance(ncomp, str):
         _unsupported("ncomp='auto'")
     if left_eigv:
@@ -331,13 +344,10 @@ def pca_annular(*all_args: List, **all_kwargs: dict):
 
     if not isinstance(p.cube, np.ndarray):
         raise TypeError("Input array is not a cube or 3d array")
-    if p.cube.ndim == 4:
-        _unsupported("4-d (IFS) input")
-    if p.cube.ndim != 3:
+    if p.cube.ndim == 4 and p.scale_list is not None:
+        _unsupported("4-d input with `scale_list` (annular ADI+mSDI)")
+    if p.cube.ndim not in (3, 4):
         raise TypeError("Input array is not a 4d or 3d array")
-
-    func_params = setup_parameters(params_obj=p, fkt=_pca_adi_rdi_device, full_output=True)
-    cube_out, cube_der, frame = _pca_adi_rdi_device(**func_params, **rot_options)
     dt = p.cube.dtype
 
     def host(t):
@@ -346,6 +356,43 @@ def pca_annular(*all_args: List, **all_kwargs: dict):
             a = a.astype(dt)
         return a
 
+    if p.cube.ndim == 4:
+        # 4-d cube without mSDI: annular ADI/RDI per spectral channel, channel frames combined with
+        # `collapse_ifs` (pca_local.py:280-330); the reference rewrites ncomp / fwhm into per-channel lists
+        nch = p.cube.shape[0]
+        if not isinstance(p.ncomp, list) or len(p.ncomp) != nch:
+            p.ncomp = [p.ncomp] * nch
+        if np.isscalar(p.fwhm):
+            p.fwhm = [p.fwhm] * nch
+        outs, ders, frames = [], [], []
+        for ch in range(nch):
+            cube_ref = None
+            if p.cube_ref is not None:
+                if p.cube_ref[ch].ndim != 3:
+                    raise TypeError("Ref cube has wrong format for 4d input cube")
+                cube_ref = p.cube_ref[ch]
+            func_params = setup_parameters(params_obj=p, fkt=_pca_adi_rdi_device, cube=p.cube[ch],
+                                           fwhm=p.fwhm[ch], ncomp=p.ncomp[ch], full_output=True, cube_ref=cube_ref)
+            co, cd, fr = _pca_adi_rdi_device(**func_params, **rot_options)
+            outs.append(co); ders.append(cd); frames.append(fr)
+        ifs = torch.stack(frames)
+        # the channel frames live in a float64 np.zeros buffer in the reference (:282): float64 frame
+        if p.collapse_ifs is not None:
+            frame = to_host(collapse_device(ifs, mode=p.collapse_ifs)).astype(np.float64)
+        else:
+            frame = to_host(ifs).astype(np.float64)
+        if p.full_output:
+            return host(torch.stack(outs)), host(torch.stack(ders)), frame
+        return frame
+
+    func_params = setup_parameters(params_obj=p, fkt=_pca_adi_rdi_device, full_output=True)
+    cube_out, cube_der, frame = _pca_adi_rdi_device(**func_params, **rot_options)
+    if isinstance(frame, list):
+        # list `ncomp`: the reference allocates these buffers with np.zeros (float64) and returns a list of frames
+        frames = [to_host(f).astype(np.float64) for f in frame]
+        if p.full_output:
+            return to_host(cube_out).astype(np.float64), to_host(cube_der).astype(np.float64), frames
+        return frames
     if p.full_output:
         return host(cube_out), host(cube_der), host(frame)
     return host(frame)
