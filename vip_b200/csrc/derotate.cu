@@ -478,6 +478,27 @@ shear_cols_fft(const float2* __restrict__ T1, float2* __restrict__ T2, RotParams
     const int tr = threadIdx.x / F::T, t = threadIdx.x % F::T;
     const int fl = blockIdx.y, f = frame0 + fl;
     const int c0 = blockIdx.x * NT;
+    if (NT == 1) {
+        // one column per CTA: every thread gathers its own four samples (and thread 0 the extra row S)
+        // straight into registers and scatters its four results -- no staging pass, no CTA-wide barriers
+        const float2* src1 = T1 + (size_t)fl * (g.S + 1) * N + c0;
+        float re[16], im[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 v = __ldg(src1 + (size_t)(t + j * F::T) * N);
+            re[j] = v.x; im[j] = v.y;
+        }
+        float2 v4 = make_float2(0.f, 0.f);
+        if (t == 0) v4 = __ldg(src1 + (size_t)(4 * F::T) * N);
+        int s_int; float s_frac;
+        const int col_phys = (c0 + g.y0) & (N - 1);
+        split_shift(b_coef[f] * (double)(col_phys - N / 2), s_int, s_frac);
+        F::template run<true, true>(re, im, smem2, ph3s[0], tw, t, 0, s_int, s_frac, v4.x, v4.y);
+        float2* dst1 = T2 + (size_t)fl * g.S * N + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst1[(size_t)(t + j * F::T) * N] = make_float2(re[j], im[j]);
+        return;
+    }
     // stage the (S+1) x NT slab with columns fastest (NT*8-byte global segments)
     const float2* src = T1 + (size_t)fl * (g.S + 1) * N + c0;
     for (int idx = threadIdx.x; idx < (g.S + 1) * NT; idx += blockDim.x) {
@@ -871,7 +892,10 @@ int derotate_run(const float* in, float* out, int nframes, const RotParams& g, c
                     else if (fft_nt() == 9) rc = launch_fft_chunk<2048, 1, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     else rc = launch_fft_chunk<2048, 2, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     break;
-                default:   rc = launch_fft_chunk<4096, 2, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
+                default:
+                    if (fft_nt() == 2) rc = launch_fft_chunk<4096, 2, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    else rc = launch_fft_chunk<4096, 1, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    break;
             }
         } else {
             rc = launch_direct_chunk(in, out, T1, T2, g, krot, a, b, f0, nf, st);
