@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/vip_b200.h"
 #include <cstdarg>
+#include <cstdlib>
 #include <atomic>
 #include <map>
 #include <mutex>

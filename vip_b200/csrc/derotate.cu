@@ -585,6 +585,58 @@ shear_cols_fft_persist(const float2* __restrict__ T1, float2* __restrict__ T2, R
     }
 }
 
+// ---- pass 2, slab variant: one CTA owns NC adjacent columns and transforms them one after the other.
+// A single-column gather touches one 32-byte DRAM/L2 sector per 8-byte sample; measured (config 2) that
+// costs 3.5 ms of the 11 ms of this pass.  Here the (S+1) x NC input slab is loaded with NC*8-byte
+// segments (one full sector per row for NC = 4), kept column-major in shared memory (pitch = 4 mod 16
+// complex words: conflict-free both for the segment-wise fill and for the per-thread column reads),
+// every result overwrites its own input slot, and the S x NC output slab leaves with the same segments.
+template <int N, int NC, int MINB>
+__global__ void __launch_bounds__(N / 16, MINB)
+shear_cols_fft_slab(const float2* __restrict__ T1, float2* __restrict__ T2, RotParams g,
+                    const double* __restrict__ b_coef, const float2* __restrict__ tw, int frame0, int pitch) {
+    using F = ShearFft<N>;
+    constexpr int T = F::T;
+    extern __shared__ float2 smem2[];
+    __shared__ float2 ph3s[16];
+    float2* buf = smem2;
+    float2* slab = smem2 + F::BUF;
+    const int t = threadIdx.x;
+    const int fl = blockIdx.y, f = frame0 + fl;
+    const int c0 = blockIdx.x * NC;
+    const int S = g.S;
+    const float2* src = T1 + (size_t)fl * (S + 1) * N + c0;
+    for (int idx = t; idx < (S + 1) * NC; idx += T) {
+        const int row = idx / NC, c = idx % NC;
+        slab[c * pitch + row] = __ldg(src + (size_t)row * N + c);
+    }
+    __syncthreads();
+    const double bc = b_coef[f];
+#pragma unroll 1
+    for (int c = 0; c < NC; ++c) {
+        float2* col = slab + c * pitch;
+        float re[16], im[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 v = col[t + j * T];
+            re[j] = v.x; im[j] = v.y;
+        }
+        const float2 v4 = col[4 * T];      // row S (only thread 0 uses it)
+        int s_int; float s_frac;
+        const int col_phys = (c0 + c + g.y0) & (N - 1);
+        split_shift(bc * (double)(col_phys - N / 2), s_int, s_frac);
+        F::template run<true, true>(re, im, buf, ph3s, tw, t, 0, s_int, s_frac, v4.x, v4.y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) col[t + j * T] = make_float2(re[j], im[j]);
+        __syncthreads();                   // buf (and ph3s) are reused by the next column
+    }
+    float2* dst = T2 + (size_t)fl * S * N + c0;
+    for (int idx = t; idx < S * NC; idx += T) {
+        const int row = idx / NC, c = idx % NC;
+        dst[(size_t)row * N + c] = slab[c * pitch + row];
+    }
+}
+
 // ---- pass 3: rows [0, S); real part of columns n' in [0, S) -> out, mask restored
 template <int N, int NT, int MINB>
 __global__ void __launch_bounds__(NT * N / 16, MINB)
@@ -765,6 +817,15 @@ int profile_read(float* out) {
     return 0;
 }
 
+static int fft_slab() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VIP_B200_FFT_SLAB");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 static int fft_persist() {
     static int v = -1;
     if (v < 0) {
@@ -796,7 +857,29 @@ static int launch_fft_chunk(const float* in, float* out, float2* T1, float2* T2,
         in, T1, g, krot, a, tw, frame0);
     VB_CHECK_LAUNCH();
     g_timer.mark(st);
-    if (NT == 1 && N >= 2048 && fft_persist()) {
+    if (NT == 1 && N >= 2048 && fft_slab() == 8) {
+        constexpr int NC = 8;
+        static bool cfg4 = false;
+        const int pitch = ((g.S + 1 + 15) / 16) * 16 + 2;      // 8 columns x 2 rows per half-warp: pitch = 2 mod 16
+        const size_t smem3 = (size_t)(F::BUF + NC * pitch) * sizeof(float2);
+        if (!cfg4) {
+            VB_CHECK_CUDA(cudaFuncSetAttribute(shear_cols_fft_slab<N, NC, MINB>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            cfg4 = true;
+        }
+        shear_cols_fft_slab<N, NC, MINB><<<dim3(N / NC, nf), F::T, smem3, st>>>(T1, T2, g, b, tw, frame0, pitch);
+    } else if (NT == 1 && N >= 2048 && fft_slab() > 0) {
+        constexpr int NC = 4;
+        static bool cfg3 = false;
+        const int pitch = ((g.S + 1 + 15) / 16) * 16 + 4;
+        const size_t smem3 = (size_t)(F::BUF + NC * pitch) * sizeof(float2);
+        if (!cfg3) {
+            VB_CHECK_CUDA(cudaFuncSetAttribute(shear_cols_fft_slab<N, NC, MINB>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            cfg3 = true;
+        }
+        shear_cols_fft_slab<N, NC, MINB><<<dim3(N / NC, nf), F::T, smem3, st>>>(T1, T2, g, b, tw, frame0, pitch);
+    } else if (NT == 1 && N >= 2048 && fft_persist()) {
         static bool cfg2 = false;
         const size_t smem2 = (size_t)(F::BUF + g.S + 8) * sizeof(float2);
         if (!cfg2) {

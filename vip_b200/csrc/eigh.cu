@@ -844,15 +844,18 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
         void* args[] = {(void*)&G, (void*)&n, (void*)&k, (void*)&tol, (void*)&fmax, (void*)&jthr, (void*)&rr_every,
                         (void*)&X, (void*)&T, (void*)&S, (void*)&Qm, (void*)&R, (void*)&theta, (void*)&res,
                         (void*)&dinv, (void*)&state, (void*)&bar};
-        VB_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)topk_fused_kernel<B>, dim3(fused_grid), dim3(512), args,
-                                                  0, st));
-        topk_output_kernel<B><<<ceil_div(n, 256), 256, 0, st>>>(X, theta, n, k, evals, evecs);
-        VB_CHECK_LAUNCH();
-        VB_CHECK_CUDA(cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, st));
-        VB_CHECK_CUDA(cudaStreamSynchronize(st));
-        if (launches) *launches = nl + 2;
-        if (info) { info[0] = h.iters; info[1] = h.converged; }
-        return 0;
+        const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)topk_fused_kernel<B>, dim3(fused_grid),
+                                                           dim3(512), args, 0, st);
+        if (ce == cudaSuccess) {
+            topk_output_kernel<B><<<ceil_div(n, 256), 256, 0, st>>>(X, theta, n, k, evals, evecs);
+            VB_CHECK_LAUNCH();
+            VB_CHECK_CUDA(cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, st));
+            VB_CHECK_CUDA(cudaStreamSynchronize(st));
+            if (launches) *launches = nl + 2;
+            if (info) { info[0] = h.iters; info[1] = h.converged; }
+            return 0;
+        }
+        (void)cudaGetLastError();     // cooperative launch unavailable (e.g. MPS): use the per-phase kernels below
     }
     // Rayleigh-Ritz every iteration: without it the columns of G X all tilt towards the dominant
     // eigenvector (lambda_0 / lambda_B ~ 1e5) and the Cholesky-QR of Y^T Y (condition number squared)
