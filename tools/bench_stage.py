@@ -40,7 +40,8 @@ def main():
     lib = _cabi.lib()
     if what == "derotate":
         cube = torch.randn((n, size, size), device="cuda", generator=g)
-        angs = np.linspace(3.0, 93.0, n)
+        amax = float(os.environ.get("BENCH_ANGLE_MAX", "93.0"))
+        angs = np.linspace(3.0, amax, n)
         lib.vb_profile_enable(0)
         ms = timeit(lambda: derotate_device(cube, -angs))
         lib.vb_profile_enable(1)

@@ -13,7 +13,7 @@
 
 namespace vb {
 
-constexpr int KCMAX = 32;     // components per pass (kernels are instantiated for 8/16/24/32)
+constexpr int KCMAX = 32;     // components per pass (kernels are instantiated for 8/16/20/24/32)
 constexpr int ROWS = 256;     // rows of the small matrix staged in shared memory per step
 constexpr int PT = 256;       // threads (= pixels) per CTA
 
@@ -132,6 +132,7 @@ int pcs_f32(const double* Wt, const float* M, int k, int n, size_t p, float* V, 
         const int kc = (k - k0 < KCMAX) ? k - k0 : KCMAX;
         if (kc <= 8)       pcs_kernel<8><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V);
         else if (kc <= 16) pcs_kernel<16><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V);
+        else if (kc <= 20) pcs_kernel<20><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V);
         else if (kc <= 24) pcs_kernel<24><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V);
         else               pcs_kernel<32><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V);
         VB_CHECK_LAUNCH();
@@ -152,6 +153,7 @@ int project_subtract_f32(const float* M, const float* C, int ldc, const float* V
         const float* src = (k0 == 0) ? M : R;
         if (kc <= 8)       subtract_kernel<8><<<grid, PT, 0, st>>>(src, C, ldc, V, n, p, k0, kc, R);
         else if (kc <= 16) subtract_kernel<16><<<grid, PT, 0, st>>>(src, C, ldc, V, n, p, k0, kc, R);
+        else if (kc <= 20) subtract_kernel<20><<<grid, PT, 0, st>>>(src, C, ldc, V, n, p, k0, kc, R);
         else if (kc <= 24) subtract_kernel<24><<<grid, PT, 0, st>>>(src, C, ldc, V, n, p, k0, kc, R);
         else               subtract_kernel<32><<<grid, PT, 0, st>>>(src, C, ldc, V, n, p, k0, kc, R);
         VB_CHECK_LAUNCH();
