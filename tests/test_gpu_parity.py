@@ -82,6 +82,40 @@ def test_derotate_fft_and_direct_agree(vb):
     assert rel_err(a, b) < DEROT_TOL
 
 
+@pytest.mark.parametrize("S", [128, 256, 512])
+def test_derotate_nyquist_content(vb, S):
+    """Checkerboard-dominated frames: the Nyquist bin (f = -1/2) is the one place where a shear of a
+    real line is not real; the packed real-plane kernels carry it through per-line scalars
+    (csrc/derotate.cu, tools/shear_real_model.py).  Large Nyquist content makes those terms first order."""
+    rng = np.random.default_rng(100 + S)
+    angs = np.array([12.3, 100.2, 315.0, -44.0]) if S < 512 else np.array([-27.7, 158.4])
+    board = ((np.add.outer(np.arange(S), np.arange(S)) % 2) * 2.0 - 1.0)
+    cube = (rng.normal(size=(len(angs), S, S)) + 5.0 * board).astype(np.float32)
+    cube[0, :, ::2] += 3.0           # Nyquist content along one axis only
+    out = vb.cube_derotate(cube, angs)
+    assert rel_err(out, O.cube_derotate(cube, angs)) < DEROT_TOL
+
+
+def test_derotate_chunked_scratch_is_identical(vb):
+    """Frames are processed in chunks sized by the scratch budget: same bits whatever the chunking."""
+    import torch
+    from vip_b200 import kernels
+    from vip_b200.preproc.derotation import rotation_geometry, rotation_scalars
+    cube, angs = adi_cube(5, 128, 3, 50.0, seed=7)
+    dev = torch.from_numpy(cube).cuda()
+    N, y0 = rotation_geometry(128)
+    k, a, b = rotation_scalars(-angs)
+    full = kernels.derotate(dev, k, a, b, 128, N, y0).cpu().numpy()
+    per_frame = _cabi_lib().vb_derotate_scratch_bytes(1, 128, N, 0)
+    part = kernels.derotate(dev, k, a, b, 128, N, y0, scratch_max=2 * per_frame + 1024).cpu().numpy()
+    np.testing.assert_array_equal(full, part)
+
+
+def _cabi_lib():
+    from vip_b200 import _cabi
+    return _cabi.lib()
+
+
 def test_derotate_float64_in_float64_out(vb):
     rng = np.random.default_rng(5)
     cube = rng.normal(size=(3, 20, 20))

@@ -35,6 +35,7 @@ int project_subtract_f32(const float*, const float*, int, const float*, int, int
 int sub_f32(const float*, const float*, float*, size_t, cudaStream_t);
 struct RotParams { int S; int N; int y0; int zero_masked; int mask_is_nan; float mask_val; };
 size_t derotate_scratch_bytes_per_frame(int S, int N);
+size_t derotate_scratch_bytes_min(int S, int N);
 int derotate_run(const float*, float*, int, const RotParams&, const int*, const double*, const double*,
                  const float2*, void*, size_t, int, int*, cudaStream_t);
 int collapse_f32(const float*, int, size_t, int, const double*, int, int, void*, cudaStream_t);
@@ -167,7 +168,8 @@ size_t vb_derotate_scratch_bytes(int nframes, int S, int N, size_t max_bytes) {
         if (frames < 1) frames = 1;
         want = frames * per;
     }
-    return want;
+    const size_t floor_bytes = derotate_scratch_bytes_min(S, N);   // one frame on any path (force_direct)
+    return want < floor_bytes ? floor_bytes : want;
 }
 
 int vb_derotate_f32(const float* in, float* out, int nframes, int S, int N, int y0, const int* krot,

@@ -319,23 +319,15 @@ struct ShearFft {
     // IN4 : only re/im[0..3] (n' = t + j*T, j < 4) and the sample n' = 4T (x4, thread 0) are non-zero.
     // OUT4: only outputs j < 4 are produced (re/im[0..3]).
     // Otherwise re/im[j] <-> n' = t + j*T for j = 0..15 on input and output.
-    template <bool IN4, bool OUT4>
-    __device__ __forceinline__ static void run(float (&re)[16], float (&im)[16], float2* buf, float2* ph3,
-                                               const float2* __restrict__ tw, int t, int tr, int s_int,
-                                               float s_frac, float x4r, float x4i) {
+    //
+    // forward(): stages 1-3; on return register g*R3 + brev(k3) of thread t holds the spectrum at
+    //   k = kb + 256*k3,  kb = (q >> 4) + 16*(q & 15),  q = t*G3 + g.
+    template <bool IN4>
+    __device__ __forceinline__ static void forward(float (&re)[16], float (&im)[16], float2* buf,
+                                                   const float2* __restrict__ tw, int t, int tr, float x4r,
+                                                   float x4i) {
         const int npp = t & (L2 - 1), k1p = t >> LOG_R3;
         Twiddle6 w;
-
-        // per-transform constants: exp(-2 pi i s f(256*k3)) / N, f wraps to negative for k3 >= R3/2
-        if (t < R3) {
-            const int k3s = (t >= R3 / 2) ? t - R3 : t;          // signed multiple of N/R3
-            const int ik = (int)(((long long)s_int * k3s) % R3); // may be negative: fine for sincospi
-            const float turns = (float)ik * (1.0f / R3) + s_frac * ((float)k3s * (1.0f / R3));
-            float pr, pi;
-            sincospif(-2.0f * turns, &pi, &pr);
-            ph3[t] = make_float2(pr * (1.0f / N), pi * (1.0f / N));
-        }
-
         // ---- forward stage 1: radix-16 over n' = t + j*T; result y[k1] -> position k1*L1 + t
         if (IN4) {
             dft16_in4(re, im);
@@ -374,29 +366,21 @@ struct ShearFft {
             buf[sw2(k1p * L1 + k2 * L2 + npp)] = make_float2(re[r], im[r]);
         }
         group_sync();
-        // ---- forward stage 3: radix-R3 on 16 contiguous points, phase, inverse stage 3
+        // ---- forward stage 3: radix-R3 on 16 contiguous points
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
             const float2 v = buf[sw2(16 * t + e)];
             re[e] = v.x; im[e] = v.y;
         }
         GroupFft<R3, -1, G3>::fwd(re, im);
-#pragma unroll
-        for (int g = 0; g < G3; ++g) {
-            const int q = t * G3 + g;               // = k1*16 + k2
-            const int kb = (q >> 4) + 16 * (q & 15);  // k1 + 16*k2  (< 256)
-            float er, ei;
-            phase_of<N>(s_int, s_frac, kb, er, ei);
-#pragma unroll
-            for (int k3 = 0; k3 < R3; ++k3) {
-                const int r = g * R3 + brev(k3, LOG_R3);
-                const float2 p3 = ph3[k3];
-                float pr, pi;
-                cmul(er, ei, p3.x, p3.y, pr, pi);
-                const float xr = re[r], xi = im[r];
-                cmul(xr, xi, pr, pi, re[r], im[r]);
-            }
-        }
+    }
+
+    // inverse(): undoes forward() (unnormalised); callers that reuse `buf` must synchronise first
+    template <bool OUT4>
+    __device__ __forceinline__ static void inverse(float (&re)[16], float (&im)[16], float2* buf,
+                                                   const float2* __restrict__ tw, int t, int tr) {
+        const int npp = t & (L2 - 1), k1p = t >> LOG_R3;
+        Twiddle6 w;
         GroupFft<R3, +1, G3>::inv(re, im);
         group_sync();
 #pragma unroll
@@ -428,7 +412,128 @@ struct ShearFft {
         }
         if (OUT4) dft16_out4(re, im);
         else dit<16, +1, 0>(re, im);
-        // callers that reuse `buf` must synchronise first
+    }
+
+    // exp(-2 pi i s f(256*k3)) * scale, f wraps to negative for k3 >= R3/2 (Nyquist bin = -1/2)
+    __device__ __forceinline__ static float2 phase3(int k3, int s_int, float s_frac, float scale) {
+        const int k3s = (k3 >= R3 / 2) ? k3 - R3 : k3;          // signed multiple of N/R3
+        const int ik = (int)(((long long)s_int * k3s) % R3);     // may be negative: fine for sincospi
+        const float turns = (float)ik * (1.0f / R3) + s_frac * ((float)k3s * (1.0f / R3));
+        float pr, pi;
+        sincospif(-2.0f * turns, &pi, &pr);
+        return make_float2(pr * scale, pi * scale);
+    }
+
+    // One complex line:  y = IFFT( FFT(x) * exp(-2 pi i s f) ).
+    template <bool IN4, bool OUT4>
+    __device__ __forceinline__ static void run(float (&re)[16], float (&im)[16], float2* buf, float2* ph3,
+                                               const float2* __restrict__ tw, int t, int tr, int s_int,
+                                               float s_frac, float x4r, float x4i) {
+        if (t < R3) ph3[t] = phase3(t, s_int, s_frac, 1.0f / N);   // visible after the stage-1 barrier
+        forward<IN4>(re, im, buf, tw, t, tr, x4r, x4i);
+#pragma unroll
+        for (int g = 0; g < G3; ++g) {
+            const int q = t * G3 + g;               // = k1*16 + k2
+            const int kb = (q >> 4) + 16 * (q & 15);  // k1 + 16*k2  (< 256)
+            float er, ei;
+            phase_of<N>(s_int, s_frac, kb, er, ei);
+#pragma unroll
+            for (int k3 = 0; k3 < R3; ++k3) {
+                const int r = g * R3 + brev(k3, LOG_R3);
+                const float2 p3 = ph3[k3];
+                float pr, pi;
+                cmul(er, ei, p3.x, p3.y, pr, pi);
+                const float xr = re[r], xi = im[r];
+                cmul(xr, xi, pr, pi, re[r], im[r]);
+            }
+        }
+        inverse<OUT4>(re, im, buf, tw, t, tr);
+    }
+
+    // Two REAL lines a (in re[]) and b (in im[]) with their own shifts through ONE complex transform:
+    //   Z = FFT(a + i b),  A[k] = (Z[k] + conj Z[N-k]) / 2,  B[k] = (Z[k] - conj Z[N-k]) / (2i),
+    //   W[k] = A[k] Pa[k] + i B[k] Pb[k] = Z[k] (Pa+Pb)/2 + conj(Z[N-k]) (Pa-Pb)/2,   w = IFFT(W),
+    // so that re[] = Re shear_a(a), im[] = Re shear_b(b) on return.  A shear of a real line is real except
+    // for the Nyquist bin (f = -1/2, multiplier e^{i pi s}): its imaginary part is nyq * (-1)^n' with
+    // nyq = X[N/2] sin(pi s) / N, returned for both lines (thread 0 only); Pa/Pb carry cos(pi s) at k = N/2.
+    // The mirrored bins live in other threads: one extra exchange through `zbuf` (N+4 float2).
+    // tools/shear_real_model.py proves the bookkeeping against the oracle in fp64.
+    template <bool IN4, bool OUT4>
+    __device__ __forceinline__ static void run_pair(float (&re)[16], float (&im)[16], float2* buf, float2* zbuf,
+                                                    float2* ph3, const float2* __restrict__ tw, int t, int tr,
+                                                    int sa_int, float sa_frac, int sb_int, float sb_frac,
+                                                    float x4r, float x4i, float& nyq_a, float& nyq_b) {
+        if (t < 2 * R3) {
+            const bool second = t >= R3;
+            ph3[t] = phase3(second ? t - R3 : t, second ? sb_int : sa_int, second ? sb_frac : sa_frac,
+                            0.5f / N);
+        }
+        forward<IN4>(re, im, buf, tw, t, tr, x4r, x4i);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) zbuf[sw2(16 * t + e)] = make_float2(re[e], im[e]);
+        transform_sync<T>(tr);
+        nyq_a = 0.f; nyq_b = 0.f;
+#pragma unroll
+        for (int g = 0; g < G3; ++g) {
+            const int q = t * G3 + g;
+            const int kb = (q >> 4) + 16 * (q & 15);
+            float ear, eai, ebr, ebi;
+            phase_of<N>(sa_int, sa_frac, kb, ear, eai);
+            phase_of<N>(sb_int, sb_frac, kb, ebr, ebi);
+            // bin N-k: kb' = (256 - kb) mod 256 and k3' = R3-1-k3 (kb != 0) or (R3 - k3) mod R3 (kb == 0)
+            const int kbp = (256 - kb) & 255;
+            const int basep = R3 * (((kbp & 15) << 4) | (kbp >> 4));
+#pragma unroll
+            for (int k3 = 0; k3 < R3; ++k3) {
+                const int r = g * R3 + brev(k3, LOG_R3);
+                const int i1 = brev(R3 - 1 - k3, LOG_R3), i0 = brev((R3 - k3) & (R3 - 1), LOG_R3);
+                const float2 zp = zbuf[sw2(basep + (kb != 0 ? i1 : i0))];
+                const float2 p3a = ph3[k3], p3b = ph3[R3 + k3];
+                float par, pai, pbr, pbi;
+                cmul(ear, eai, p3a.x, p3a.y, par, pai);
+                cmul(ebr, ebi, p3b.x, p3b.y, pbr, pbi);
+                if (k3 == R3 / 2 && kb == 0) {      // Nyquist bin (thread 0 only)
+                    nyq_a = 2.f * re[r] * pai;
+                    nyq_b = 2.f * im[r] * pbi;
+                    pai = 0.f; pbi = 0.f;
+                }
+                const float hsr = par + pbr, hsi = pai + pbi, hdr = par - pbr, hdi = pai - pbi;
+                const float zr = re[r], zi = im[r];
+                re[r] = zr * hsr - zi * hsi + zp.x * hdr + zp.y * hdi;
+                im[r] = zr * hsi + zi * hsr + zp.x * hdi - zp.y * hdr;
+            }
+        }
+        inverse<OUT4>(re, im, buf, tw, t, tr);
+    }
+
+    // One complex line with the multiplier  M[k] = sum_{u=-N/2}^{N/2-1} exp(-2 pi i c u f_k)
+    //   = e^{i pi c f} sin(pi c f N) / sin(pi c f)   (the sum of the N column shears of pass 2), fp64 evaluation.
+    template <bool IN4, bool OUT4>
+    __device__ __forceinline__ static void run_mult(float (&re)[16], float (&im)[16], float2* buf,
+                                                    const float2* __restrict__ tw, int t, int tr, double c,
+                                                    float x4r, float x4i) {
+        forward<IN4>(re, im, buf, tw, t, tr, x4r, x4i);
+#pragma unroll
+        for (int g = 0; g < G3; ++g) {
+            const int q = t * G3 + g;
+            const int kb = (q >> 4) + 16 * (q & 15);
+#pragma unroll
+            for (int k3 = 0; k3 < R3; ++k3) {
+                const int r = g * R3 + brev(k3, LOG_R3);
+                const int ks = kb + 256 * ((k3 >= R3 / 2) ? k3 - R3 : k3);
+                const double cf = c * (double)ks * (1.0 / N);
+                double mr = 1.0, mi = 0.0;             // M / N
+                double sden, cden;
+                sincospi(cf, &sden, &cden);
+                if (fabs(sden) > 1e-14) {
+                    const double ratio = sinpi(c * (double)ks) / (sden * (double)N);
+                    mr = cden * ratio; mi = sden * ratio;
+                }
+                const float xr = re[r], xi = im[r];
+                cmul(xr, xi, (float)mr, (float)mi, re[r], im[r]);
+            }
+        }
+        inverse<OUT4>(re, im, buf, tw, t, tr);
     }
 };
 
@@ -678,6 +783,278 @@ shear_rows_last_fft(const float2* __restrict__ T2, const float* __restrict__ in,
 }
 
 // =====================================================================================
+// Packed REAL-plane kernels (default for the power-of-two path)
+// =====================================================================================
+// A shear of a real line is real up to its Nyquist bin, so the planes between the passes are stored as
+// REAL planes  T1r[(S+1) x N], T2r[S x N]  plus a few per-frame scalars, and every complex transform carries
+// two adjacent real lines (ShearFft::run_pair): half the transforms and half the plane traffic of the
+// complex formulation above, same result.  With primed (re-indexed) coordinates r', n' throughout:
+//   pass 1  T1 = A + i beta_r' (-1)^n'                       -> A (real plane), beta[r'] (S+1 scalars)
+//   aux 1   sigma = sum_r' (-1)^r' beta_r';  Cs[r'] = Re sum_n' shear_{s_n'}(beta)[r']  (one transform, run_mult)
+//   pass 2  column n': Re T2 = B_n'[r'] - (-1)^(n'+r') sigma sin(pi s_n')/N -> P (real plane);  gamma[n'] = Nyquist
+//           scalar of column n'.  Im T2 = gamma_n' (-1)^r' + (-1)^n' C_n'[r'] is never formed: pass 3 only
+//           needs its alternating row sums  q_r' = (-1)^r' Gamma + Cs[r'],  Gamma = sum_n' (-1)^n' gamma_n'.
+//   aux 2   Gamma, corr[r'] = q_r' sin(pi s_r') / N
+//   pass 3  out[r'][n'] = Re shear(P_r')[n'] - (-1)^n' corr[r']
+// Per-frame scalars live in `aux` (2N floats per frame): beta [0,S], sigma [2S-1], Cs [2S,3S), corr [3S,4S),
+// gamma [N,2N).
+struct AuxLayout {
+    __host__ __device__ static size_t stride(int N) { return (size_t)2 * N; }
+    __host__ __device__ static int beta(int) { return 0; }
+    __host__ __device__ static int sigma(int S) { return 2 * S - 1; }
+    __host__ __device__ static int cs(int S) { return 2 * S; }
+    __host__ __device__ static int corr(int S) { return 3 * S; }
+    __host__ __device__ static int gamma(int S) { return 4 * S; }
+};
+
+// sin(pi s) for s = s_int + s_frac
+__device__ __forceinline__ float sinpi_split(int s_int, float s_frac) {
+    const float v = sinpif(s_frac);
+    return (s_int & 1) ? -v : v;
+}
+
+// ---- pass 1 (packed): rows 2m, 2m+1 of [0, S] per transform
+template <int N, int NT, int MINB>
+__global__ void __launch_bounds__(NT * N / 16, MINB)
+shear_rows_first_pk(const float* __restrict__ in, float* __restrict__ T1, float* __restrict__ aux, RotParams g,
+                    const int* __restrict__ krot, const double* __restrict__ a_coef,
+                    const float2* __restrict__ tw, int frame0) {
+    using F = ShearFft<N>;
+    extern __shared__ float2 smem2[];
+    __shared__ float2 ph3s[NT][32];
+    const int tr = threadIdx.x / F::T, t = threadIdx.x % F::T;
+    const int fl = blockIdx.y, f = frame0 + fl;
+    const int row = 2 * (blockIdx.x * NT + tr);
+    const bool va = row <= g.S, vb_ = row + 1 <= g.S;
+    const int i = g.y0 + row;
+    const int k = krot[f];
+    const float* frame = in + (size_t)f * g.S * g.S;
+    float re[16], im[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        re[j] = va ? plane_sample(frame, g, k, i, g.y0 + t + j * F::T) : 0.f;
+        im[j] = vb_ ? plane_sample(frame, g, k, i + 1, g.y0 + t + j * F::T) : 0.f;
+    }
+    const float x4r = (va && t == 0) ? plane_sample(frame, g, k, i, g.y0 + g.S) : 0.f;
+    const float x4i = (vb_ && t == 0) ? plane_sample(frame, g, k, i + 1, g.y0 + g.S) : 0.f;
+    int sa_int, sb_int; float sa_frac, sb_frac;
+    const double ac = a_coef[f];
+    split_shift(ac * (double)(i - N / 2), sa_int, sa_frac);
+    split_shift(ac * (double)(i + 1 - N / 2), sb_int, sb_frac);
+    float nya, nyb;
+    float2* buf = smem2 + (size_t)tr * 2 * F::BUF;
+    F::template run_pair<true, false>(re, im, buf, buf + F::BUF, ph3s[tr], tw, t, tr, sa_int, sa_frac, sb_int,
+                                      sb_frac, x4r, x4i, nya, nyb);
+    float* dst = T1 + ((size_t)fl * (g.S + 1) + row) * N;
+    if (va) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[t + j * F::T] = re[j];
+    }
+    if (vb_) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[N + t + j * F::T] = im[j];
+    }
+    if (t == 0) {
+        float* beta = aux + (size_t)fl * AuxLayout::stride(N) + AuxLayout::beta(g.S);
+        if (va) beta[row] = nya;
+        if (vb_) beta[row + 1] = nyb;
+    }
+}
+
+// ---- aux 1: sigma and Cs of one frame (one CTA of N/16 threads per frame)
+template <int N>
+__global__ void __launch_bounds__(N / 16)
+shear_aux_beta(float* __restrict__ aux, RotParams g, const double* __restrict__ b_coef,
+               const float2* __restrict__ tw, int frame0) {
+    using F = ShearFft<N>;
+    constexpr int T = F::T;
+    extern __shared__ float2 smem2[];
+    __shared__ float red[T / 32];
+    const int t = threadIdx.x;
+    const int fl = blockIdx.x, f = frame0 + fl;
+    const int S = g.S;
+    float* ax = aux + (size_t)fl * AuxLayout::stride(N);
+    const float* beta = ax + AuxLayout::beta(S);
+    float re[16], im[16];
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        re[j] = beta[t + j * T];
+        im[j] = 0.f;
+        part += re[j];
+    }
+    if (t & 1) part = -part;               // (-1)^r', r' = t + j*T with T even
+    const float x4 = (t == 0) ? beta[S] : 0.f;
+    part += x4;                            // r' = S is even
+    part = warp_sum(part);
+    if ((t & 31) == 0) red[t >> 5] = part;
+    __syncthreads();
+    if (t == 0) {
+        float sg = 0.f;
+        for (int w = 0; w < T / 32; ++w) sg += red[w];
+        ax[AuxLayout::sigma(S)] = sg;
+    }
+    F::template run_mult<true, true>(re, im, smem2, tw, t, 0, b_coef[f], x4, 0.f);
+    float* cs = ax + AuxLayout::cs(S);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cs[t + j * T] = re[j];
+}
+
+// ---- pass 2 (packed): one CTA owns NC adjacent columns = NC/2 transforms, run one after the other.
+// The (S+1) x NC real slab is loaded with 16-byte vectors (NC*4-byte segments per row), kept column-major
+// in shared memory (pitch = 4 mod 32 words: conflict-free fill and column reads); results overwrite their
+// inputs and the S x NC output slab leaves the same way.
+template <int N, int NC, int MINB>
+__global__ void __launch_bounds__(N / 16, MINB)
+shear_cols_pk(const float* __restrict__ T1, float* __restrict__ T2, float* __restrict__ aux, RotParams g,
+              const double* __restrict__ b_coef, const float2* __restrict__ tw, int frame0, int pitch) {
+    using F = ShearFft<N>;
+    constexpr int T = F::T;
+    constexpr int V = NC / 4;               // float4 vectors per row
+    extern __shared__ float2 smem2[];
+    __shared__ float2 ph3s[32];
+    float2* buf = smem2;
+    float2* zbuf = smem2 + F::BUF;
+    float* slab = reinterpret_cast<float*>(smem2 + 2 * F::BUF);
+    const int t = threadIdx.x;
+    const int fl = blockIdx.y, f = frame0 + fl;
+    const int c0 = blockIdx.x * NC;
+    const int S = g.S;
+    const float* src = T1 + (size_t)fl * (S + 1) * N + c0;
+    for (int idx = t; idx < (S + 1) * V; idx += T) {
+        const int row = idx / V, h = idx % V;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * N) + h);
+        float* d = slab + (4 * h) * pitch + row;
+        d[0] = v.x; d[pitch] = v.y; d[2 * pitch] = v.z; d[3 * pitch] = v.w;
+    }
+    __syncthreads();
+    float* ax = aux + (size_t)fl * AuxLayout::stride(N);
+    const float sigma = ax[AuxLayout::sigma(S)] * (1.0f / N);
+    float* gamma = ax + AuxLayout::gamma(S);
+    const double bc = b_coef[f];
+    const float sgn_t = (t & 1) ? -1.f : 1.f;   // (-1)^r' for r' = t + j*T
+#pragma unroll 1
+    for (int c = 0; c < NC; c += 2) {
+        float* ca = slab + c * pitch;
+        float* cb = ca + pitch;
+        float re[16], im[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            re[j] = ca[t + j * T];
+            im[j] = cb[t + j * T];
+        }
+        const float x4r = ca[4 * T], x4i = cb[4 * T];      // row S (only thread 0 uses them)
+        int sa_int, sb_int; float sa_frac, sb_frac;
+        const int pa = (c0 + c + g.y0) & (N - 1), pb = (c0 + c + 1 + g.y0) & (N - 1);
+        split_shift(bc * (double)(pa - N / 2), sa_int, sa_frac);
+        split_shift(bc * (double)(pb - N / 2), sb_int, sb_frac);
+        float nya, nyb;
+        F::template run_pair<true, true>(re, im, buf, zbuf, ph3s, tw, t, 0, sa_int, sa_frac, sb_int, sb_frac,
+                                         x4r, x4i, nya, nyb);
+        // Re T2 = B - (-1)^(n'+r') sigma sin(pi s)/N ; n' = c0 + c is even for line a, odd for line b
+        const float da = sgn_t * sigma * sinpi_split(sa_int, sa_frac);
+        const float db = sgn_t * sigma * sinpi_split(sb_int, sb_frac);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ca[t + j * T] = re[j] - da;
+            cb[t + j * T] = im[j] + db;
+        }
+        if (t == 0) { gamma[c0 + c] = nya; gamma[c0 + c + 1] = nyb; }
+        __syncthreads();                   // buf / zbuf / ph3s are reused by the next pair
+    }
+    float* dst = T2 + (size_t)fl * S * N + c0;
+    for (int idx = t; idx < S * V; idx += T) {
+        const int row = idx / V, h = idx % V;
+        const float* d = slab + (4 * h) * pitch + row;
+        const float4 v = make_float4(d[0], d[pitch], d[2 * pitch], d[3 * pitch]);
+        *(reinterpret_cast<float4*>(dst + (size_t)row * N) + h) = v;
+    }
+}
+
+// ---- aux 2: Gamma and the per-row Nyquist correction of pass 3 (one CTA per frame)
+__global__ void __launch_bounds__(256)
+shear_aux_gamma(float* __restrict__ aux, RotParams g, const double* __restrict__ a_coef, int frame0) {
+    __shared__ float red[8];
+    __shared__ float Gs;
+    const int t = threadIdx.x;
+    const int fl = blockIdx.x, f = frame0 + fl;
+    const int S = g.S, N = g.N;
+    float* ax = aux + (size_t)fl * AuxLayout::stride(N);
+    const float* gamma = ax + AuxLayout::gamma(S);
+    float part = 0.f;
+    for (int n = t; n < N; n += 256) part += gamma[n];      // n = t mod 2 for every term
+    if (t & 1) part = -part;
+    part = warp_sum(part);
+    if ((t & 31) == 0) red[t >> 5] = part;
+    __syncthreads();
+    if (t == 0) {
+        float G = 0.f;
+        for (int w = 0; w < 8; ++w) G += red[w];
+        Gs = G;
+    }
+    __syncthreads();
+    const float G = Gs;
+    const float* cs = ax + AuxLayout::cs(S);
+    float* corr = ax + AuxLayout::corr(S);
+    const double ac = a_coef[f];
+    for (int r = t; r < S; r += 256) {
+        int s_int; float s_frac;
+        split_shift(ac * (double)(g.y0 + r - N / 2), s_int, s_frac);
+        const float q = ((r & 1) ? -G : G) + cs[r];
+        corr[r] = q * sinpi_split(s_int, s_frac) * (1.0f / (float)N);
+    }
+}
+
+// ---- pass 3 (packed): rows 2m, 2m+1 of [0, S); columns n' in [0, S) -> out, mask restored
+template <int N, int NT, int MINB>
+__global__ void __launch_bounds__(NT * N / 16, MINB)
+shear_rows_last_pk(const float* __restrict__ T2, const float* __restrict__ aux, const float* __restrict__ in,
+                   float* __restrict__ out, RotParams g, const double* __restrict__ a_coef,
+                   const float2* __restrict__ tw, int frame0) {
+    using F = ShearFft<N>;
+    extern __shared__ float2 smem2[];
+    __shared__ float2 ph3s[NT][32];
+    const int tr = threadIdx.x / F::T, t = threadIdx.x % F::T;
+    const int fl = blockIdx.y, f = frame0 + fl;
+    const int row = 2 * (blockIdx.x * NT + tr);
+    const bool valid = row < g.S;           // S is even on this path: both rows or none
+    const int i = g.y0 + row;
+    float re[16], im[16];
+    if (valid) {
+        const float* src = T2 + ((size_t)fl * g.S + row) * N;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            re[j] = __ldg(src + t + j * F::T);
+            im[j] = __ldg(src + N + t + j * F::T);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { re[j] = 0.f; im[j] = 0.f; }
+    }
+    int sa_int, sb_int; float sa_frac, sb_frac;
+    const double ac = a_coef[f];
+    split_shift(ac * (double)(i - N / 2), sa_int, sa_frac);
+    split_shift(ac * (double)(i + 1 - N / 2), sb_int, sb_frac);
+    float nya, nyb;
+    float2* buf = smem2 + (size_t)tr * 2 * F::BUF;
+    F::template run_pair<false, true>(re, im, buf, buf + F::BUF, ph3s[tr], tw, t, tr, sa_int, sa_frac, sb_int,
+                                      sb_frac, 0.f, 0.f, nya, nyb);
+    if (valid) {
+        const float* corr = aux + (size_t)fl * AuxLayout::stride(N) + AuxLayout::corr(g.S);
+        const float sgn_t = (t & 1) ? -1.f : 1.f;      // (-1)^n' for n' = t + j*T
+        const float ca = sgn_t * corr[row], cb = sgn_t * corr[row + 1];
+        const float* src = in + ((size_t)f * g.S + row) * g.S;
+        float* dst = out + ((size_t)f * g.S + row) * g.S;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = t + j * F::T;     // < S = 4T
+            dst[x] = is_masked(__ldg(src + x), g) ? g.mask_val : re[j] - ca;
+            dst[g.S + x] = is_masked(__ldg(src + g.S + x), g) ? g.mask_val : im[j] - cb;
+        }
+    }
+}
+
+// =====================================================================================
 // Generic path (any even N): direct circular convolution with the Dirichlet kernel
 // =====================================================================================
 
@@ -902,6 +1279,92 @@ static int launch_fft_chunk(const float* in, float* out, float2* T1, float2* T2,
     return 0;
 }
 
+static int fft_packed() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VIP_B200_FFT_PACKED");
+        v = e ? atoi(e) : 1;       // 0: complex-plane kernels (one line per transform), kept for A/B runs
+    }
+    return v;
+}
+
+static size_t packed_bytes_per_frame(int S, int N) {
+    return ((size_t)(S + 1) * N + (size_t)S * N + AuxLayout::stride(N)) * sizeof(float);
+}
+
+// pass-2 variant: 0 = 8 columns per CTA at the row kernels' occupancy, 1 = 8 columns, one CTA per SM less
+// (no register spills), 2 = 16 columns (64-byte segments), one CTA per SM less
+static int fft_cols_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VIP_B200_FFT_COLS");
+        v = e ? atoi(e) : 2;       // measured at C2 (pass 2): 5.84 / 5.46 / 5.21 ms for 0 / 1 / 2
+    }
+    return v;
+}
+
+template <int N, int NC, int MINB>
+static int launch_cols_pk(const float* T1, float* T2, float* aux, const RotParams& g, const double* b,
+                          const float2* tw, int frame0, int nf, cudaStream_t st) {
+    using F = ShearFft<N>;
+    // conflict-free vector fill: a warp covers 32/(NC/4) rows x NC/4 vectors -> pitch = 4 (NC=8) or 2 (NC=16) mod 32
+    const int pitch = ((g.S + 1 + 31) / 32) * 32 + (NC == 16 ? 2 : 4);
+    const size_t smem_cols = (size_t)2 * F::BUF * sizeof(float2) + (size_t)NC * pitch * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_cols_pk<N, NC, MINB>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    shear_cols_pk<N, NC, MINB><<<dim3(N / NC, nf), F::T, smem_cols, st>>>(T1, T2, aux, g, b, tw, frame0, pitch);
+    VB_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int N, int NT, int MINB>
+static int launch_fft_chunk_pk(const float* in, float* out, float* T1, float* T2, float* aux, const RotParams& g,
+                               const int* krot, const double* a, const double* b, const float2* tw,
+                               int frame0, int nf, cudaStream_t st) {
+    using F = ShearFft<N>;
+    const size_t smem_rows = (size_t)NT * 2 * F::BUF * sizeof(float2);
+    const size_t smem_aux = (size_t)F::BUF * sizeof(float2);
+    static bool configured = false;
+    if (!configured) {
+        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_first_pk<N, NT, MINB>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_last_pk<N, NT, MINB>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_aux_beta<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem_aux));
+        configured = true;
+    }
+    const int threads = NT * F::T;
+    const int pairs1 = (g.S + 2) / 2, pairs3 = g.S / 2;
+    g_timer.mark(st);
+    shear_rows_first_pk<N, NT, MINB><<<dim3(ceil_div(pairs1, NT), nf), threads, smem_rows, st>>>(
+        in, T1, aux, g, krot, a, tw, frame0);
+    VB_CHECK_LAUNCH();
+    g_timer.mark(st);
+    shear_aux_beta<N><<<nf, F::T, smem_aux, st>>>(aux, g, b, tw, frame0);
+    VB_CHECK_LAUNCH();
+    {
+        constexpr int MC = MINB > 1 ? MINB - 1 : 1;
+        const int cv = fft_cols_variant();
+        const int rc = cv == 2 ? launch_cols_pk<N, 16, MC>(T1, T2, aux, g, b, tw, frame0, nf, st)
+                     : cv == 1 ? launch_cols_pk<N, 8, MC>(T1, T2, aux, g, b, tw, frame0, nf, st)
+                               : launch_cols_pk<N, 8, MINB>(T1, T2, aux, g, b, tw, frame0, nf, st);
+        if (rc) return rc;
+    }
+    g_timer.mark(st);
+    shear_aux_gamma<<<nf, 256, 0, st>>>(aux, g, a, frame0);
+    VB_CHECK_LAUNCH();
+    shear_rows_last_pk<N, NT, MINB><<<dim3(ceil_div(pairs3, NT), nf), threads, smem_rows, st>>>(
+        T2, aux, in, out, g, a, tw, frame0);
+    VB_CHECK_LAUNCH();
+    g_timer.mark(st);
+    return 0;
+}
+
 static int launch_direct_chunk(const float* in, float* out, float2* T1, float2* T2, const RotParams& g,
                                const int* krot, const double* a, const double* b, int frame0, int nf,
                                cudaStream_t st) {
@@ -932,21 +1395,38 @@ static int fft_nt() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("VIP_B200_FFT_NT");
-        // 1: one transform per 128-thread CTA, 4 CTAs/SM (default: measured fastest, 18.2 ms at C2);
-        // 2: NT=2 x 2 CTAs/SM (19.0 ms); 3: NT=2 with an 85-register cap (18.8 ms, spills); 4: NT=4 (21.9 ms)
+        // 1: one transform per 128-thread CTA, 4 CTAs/SM (default: measured fastest at C2); 2: NT=2 x 2 CTAs/SM;
+        // 8 (packed only): NT=1 with 3 CTAs/SM (168 registers).  Measured and dropped on the complex kernels:
+        // NT=4 (21.9 vs 18.2 ms), 5 or 6 CTAs/SM (spills).
         v = e ? atoi(e) : 1;
     }
     return v;
 }
 
-size_t derotate_scratch_bytes_per_frame(int S, int N) {
+static bool fft_path(int S, int N) {
+    // the FFT kernels assume the exact 4x plane of power-of-two frames (N = 4S)
+    return (N & (N - 1)) == 0 && N >= 512 && N <= 4096 && N == 4 * S;
+}
+
+// complex planes T1[(S+1) x N], T2[S x N] (direct path, unpacked FFT path)
+static size_t complex_bytes_per_frame(int S, int N) {
     return ((size_t)(S + 1) * N + (size_t)S * N) * sizeof(float2);
 }
+
+size_t derotate_scratch_bytes_per_frame(int S, int N) {
+    if (fft_path(S, N) && fft_packed()) return packed_bytes_per_frame(S, N);
+    return complex_bytes_per_frame(S, N);
+}
+
+// smallest scratch any path accepts for this geometry (force_direct on a power-of-two plane included)
+size_t derotate_scratch_bytes_min(int S, int N) { return complex_bytes_per_frame(S, N); }
 
 int derotate_run(const float* in, float* out, int nframes, const RotParams& g, const int* krot,
                  const double* a, const double* b, const float2* tw, void* scratch,
                  size_t scratch_bytes, int force_direct, int* launches, cudaStream_t st) {
-    const size_t per_frame = derotate_scratch_bytes_per_frame(g.S, g.N);
+    const bool use_fft = fft_path(g.S, g.N) && !force_direct;
+    const bool packed = use_fft && fft_packed();
+    const size_t per_frame = packed ? packed_bytes_per_frame(g.S, g.N) : complex_bytes_per_frame(g.S, g.N);
     VB_REQUIRE(scratch_bytes >= per_frame, "derotate: scratch too small (%zu < %zu)", scratch_bytes,
                per_frame);
     int chunk = (int)(scratch_bytes / per_frame);
@@ -954,37 +1434,40 @@ int derotate_run(const float* in, float* out, int nframes, const RotParams& g, c
     if (chunk > 65535) chunk = 65535;
     float2* T1 = reinterpret_cast<float2*>(scratch);
     float2* T2 = T1 + (size_t)chunk * (g.S + 1) * g.N;
-    // the FFT kernels assume the exact 4x plane of power-of-two frames (N = 4S)
-    const bool pow2 = (g.N & (g.N - 1)) == 0 && g.N >= 512 && g.N <= 4096 && g.N == 4 * g.S;
+    float* T1r = reinterpret_cast<float*>(scratch);
+    float* T2r = T1r + (size_t)chunk * (g.S + 1) * g.N;
+    float* aux = T2r + (size_t)chunk * g.S * g.N;
     int nl = 0;
     for (int f0 = 0; f0 < nframes; f0 += chunk) {
         const int nf = (nframes - f0 < chunk) ? nframes - f0 : chunk;
         int rc;
-        if (pow2 && !force_direct) {
+        if (packed) {
+            switch (g.N) {
+                case 512:  rc = launch_fft_chunk_pk<512, 8, 1>(in, out, T1r, T2r, aux, g, krot, a, b, tw, f0, nf, st); break;
+                case 1024: rc = launch_fft_chunk_pk<1024, 4, 1>(in, out, T1r, T2r, aux, g, krot, a, b, tw, f0, nf, st); break;
+                case 2048:
+                    if (fft_nt() == 2) rc = launch_fft_chunk_pk<2048, 2, 2>(in, out, T1r, T2r, aux, g, krot, a, b, tw, f0, nf, st);
+                    else rc = launch_fft_chunk_pk<2048, 1, 4>(in, out, T1r, T2r, aux, g, krot, a, b, tw, f0, nf, st);
+                    break;
+                default:   rc = launch_fft_chunk_pk<4096, 1, 2>(in, out, T1r, T2r, aux, g, krot, a, b, tw, f0, nf, st); break;
+            }
+            nl += 5;
+        } else if (use_fft) {
             switch (g.N) {
                 case 512:  rc = launch_fft_chunk<512, 8, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
                 case 1024: rc = launch_fft_chunk<1024, 4, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
                 case 2048:
-                    if (fft_nt() == 4) rc = launch_fft_chunk<2048, 4, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
-                    else if (fft_nt() == 3) rc = launch_fft_chunk<2048, 2, 3>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
-                    else if (fft_nt() == 5) rc = launch_fft_chunk<2048, 2, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
-                    else if (fft_nt() == 1) rc = launch_fft_chunk<2048, 1, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
-                    else if (fft_nt() == 6) rc = launch_fft_chunk<2048, 1, 5>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
-                    else if (fft_nt() == 7) rc = launch_fft_chunk<2048, 1, 6>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
-                    else if (fft_nt() == 8) rc = launch_fft_chunk<2048, 1, 3>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
-                    else if (fft_nt() == 9) rc = launch_fft_chunk<2048, 1, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
-                    else rc = launch_fft_chunk<2048, 2, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    if (fft_nt() == 2) rc = launch_fft_chunk<2048, 2, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
+                    else rc = launch_fft_chunk<2048, 1, 4>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
                     break;
-                default:
-                    if (fft_nt() == 2) rc = launch_fft_chunk<4096, 2, 1>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
-                    else rc = launch_fft_chunk<4096, 1, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st);
-                    break;
+                default:   rc = launch_fft_chunk<4096, 1, 2>(in, out, T1, T2, g, krot, a, b, tw, f0, nf, st); break;
             }
+            nl += 3;
         } else {
             rc = launch_direct_chunk(in, out, T1, T2, g, krot, a, b, f0, nf, st);
+            nl += 3;
         }
         if (rc) return rc;
-        nl += 3;
     }
     if (launches) *launches = nl;
     return 0;
