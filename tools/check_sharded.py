@@ -23,5 +23,14 @@ for collapse in ("median", "mean"):
         err = float(np.max(np.abs(fr - ref)) / np.max(np.abs(ref)))
         print(f"sharded world={world} collapse={collapse}: rel err vs single-GPU pca = {err:.2e}")
         assert err < 1e-5, err
+# BASELINE config 5's mode: randomized SVD on pixel shards (sketch all-reduces) == single-GPU randsvd, same omega
+np.random.seed(5)
+fr = pca_sharded(cube, angs, 10, svd_mode="randsvd")
+if rank == 0:
+    np.random.seed(5)
+    ref = vip_b200.pca(cube, angs, ncomp=10, svd_mode="randsvd", verbose=False)
+    err = float(np.max(np.abs(fr - ref)) / np.max(np.abs(ref)))
+    print(f"sharded world={world} randsvd: rel err vs single-GPU pca(randsvd) = {err:.2e}")
+    assert err < 1e-4, err
 dist.barrier()
 dist.destroy_process_group()

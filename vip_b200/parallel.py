@@ -60,6 +60,14 @@ class CudaOps:
     def pcs(self, Wt, M):
         return kernels.pcs(Wt, M)
 
+    def randomized_pcs(self, M, ncomp, omega, reduce):
+        from .psfsub.svd import randomized_pcs
+        return randomized_pcs(M, ncomp, omega, reduce=reduce)
+
+    def coeffs(self, M, V, reduce):
+        """C (n,k) fp32 = M V^T, the pixel axis summed over the shards."""
+        return reduce(kernels.cross_gram(M, V)).to(torch.float32).contiguous()
+
     def project_subtract(self, M, Cm, V):
         return kernels.project_subtract(M, Cm, V)
 
@@ -91,14 +99,20 @@ def _all_to_all(send, recv, group):
 
 
 def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None, device=None,
-                full_output=False, resident_shard=None):
+                full_output=False, resident_shard=None, svd_mode="lapack", random_state=None):
     """Full-frame ADI PCA of ONE cube, sharded over the ranks of ``group``.
 
     ``cube`` (n,H,W) is the host array, visible on every rank (each rank uploads only its pixel
     shard).  Returns the final frame (H,W) as a numpy array on rank 0 and ``None`` elsewhere; with
     ``full_output`` every rank additionally returns its own (frames, H, W) derotated residual shard
     as a device tensor and the frame offsets.  ``resident_shard``: this rank's pixel shard already on
-    the device (skips the upload; used by bench.py for the device-resident number)."""
+    the device (skips the upload; used by bench.py for the device-resident number).
+
+    ``svd_mode``: any deterministic mode (exact path: all-reduce of the n x n Gramian) or 'randsvd'
+    (BASELINE config 5): scikit-learn's randomized SVD on pixel shards, whose only communication is
+    the all-reduce of the (ncomp+10) x n sketches and (ncomp+10)^2 Gramians
+    (``psfsub.svd.randomized_pcs``); the Gaussian test matrix is drawn on rank 0 from
+    ``random_state`` (default: numpy's global RandomState, as the reference does) and broadcast."""
     if cube.ndim != 3:
         raise TypeError("Input array is not a cube or 3d array")
     ops = ops or CudaOps()
@@ -121,17 +135,36 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
 
     # ---- pixel-sharded PCA ------------------------------------------------------------------
     M = resident_shard if resident_shard is not None else ops.upload_pixels(cube.reshape(n, p), p0, p1, device)
-    G = ops.gram(M)
-    dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)               # exchange step 0: n x n fp64
-    evals, evecs = ops.leading_eig(G, ncomp)
-    # replicate the eigenpairs bit-identically (atomics make the solver order-dependent at 1e-16)
     src = dist.get_global_rank(group, 0) if group is not None else 0
-    dist.broadcast(evals, src=src, group=group)
-    dist.broadcast(evecs, src=src, group=group)
-    S = torch.sqrt(torch.clamp(evals, min=0.0))
-    Wt = (evecs / S[:, None]).contiguous()
-    Cm = (evecs * S[:, None]).t().to(torch.float32).contiguous()
-    V = ops.pcs(Wt, M)
+    mode = str(getattr(svd_mode, "value", svd_mode))
+    if mode in ("randsvd", "randcupy", "randpytorch"):
+        def reduce(t):                                                   # exchange step 0: sketches
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return t
+        ell = ncomp + 10
+        if rank == 0:
+            rs = random_state
+            if rs is None:
+                rs = np.random.mtrand._rand
+            elif not isinstance(rs, np.random.RandomState):
+                rs = np.random.RandomState(rs)
+            omega = torch.from_numpy(rs.normal(size=(n, ell))).to(device)
+        else:
+            omega = torch.empty((n, ell), dtype=torch.float64, device=device)
+        dist.broadcast(omega, src=src, group=group)
+        V = ops.randomized_pcs(M, ncomp, omega.cpu().numpy(), reduce)
+        Cm = ops.coeffs(M, V, reduce)
+    else:
+        G = ops.gram(M)
+        dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)           # exchange step 0: n x n fp64
+        evals, evecs = ops.leading_eig(G, ncomp)
+        # replicate the eigenpairs bit-identically (atomics make the solver order-dependent at 1e-16)
+        dist.broadcast(evals, src=src, group=group)
+        dist.broadcast(evecs, src=src, group=group)
+        S = torch.sqrt(torch.clamp(evals, min=0.0))
+        Wt = (evecs / S[:, None]).contiguous()
+        Cm = (evecs * S[:, None]).t().to(torch.float32).contiguous()
+        V = ops.pcs(Wt, M)
     R = ops.project_subtract(M, Cm, V)                                   # (n, p_g)
 
     # ---- exchange 1: pixel shards -> frame shards ---------------------------------------------

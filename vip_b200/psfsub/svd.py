@@ -64,10 +64,13 @@ class Decomposition:
         return np.cumsum(exp_var / np.sum(exp_var))
 
 
-def orthonormalize(Yt):
-    """Rows of Yt (l,p) -> orthonormal rows spanning the same space (two Gram/eigh passes)."""
+def orthonormalize(Yt, reduce=None):
+    """Rows of Yt (l,p) -> orthonormal rows spanning the same space (two Gram/eigh passes).
+    ``reduce``: see :func:`randomized_pcs`."""
     for _ in range(2):
         G = kernels.cross_gram(Yt, Yt)
+        if reduce is not None:
+            G = reduce(G)
         evals, evecs, _ = kernels.eigh(G)
         keep = evals > evals[0] * 1e-30
         Wt = (evecs / torch.sqrt(torch.clamp(evals, min=1e-300))[:, None])[keep]
@@ -75,19 +78,25 @@ def orthonormalize(Yt):
     return Yt
 
 
-def randomized_pcs(M, ncomp, omega, n_iter=2):
+def randomized_pcs(M, ncomp, omega, n_iter=2, reduce=None):
     """scikit-learn ``randomized_svd(M, ncomp, n_iter=2, transpose='auto')`` for n < p
     (``svd.py:487-491``): with the Gaussian test matrix ``omega`` (n, ncomp+10) supplied
     by the caller,  Y = M^T (M M^T)^n_iter omega,  Q = orth(Y),  B = Q^T M^T,  PCs = (Q U_B)[:, :k]^T.
-    Any orthonormal basis of range(Y) gives the same PCs, so orth() is Gram-based here."""
+    Any orthonormal basis of range(Y) gives the same PCs, so orth() is Gram-based here.
+
+    Pixel-sharded use (``vip_b200/parallel.py``): ``M`` is this rank's column block and
+    ``reduce`` sums a small fp64 matrix over the ranks in place (NCCL all-reduce).  Every product
+    with the pixel axis contracted -- the (l,n) sketches ``Y^T M^T``, ``Q^T M^T`` and the (l,l) Gramians
+    of the orthonormalisation -- is a sum over pixel shards; everything else is local."""
     n, p = M.shape
+    red = reduce if reduce is not None else (lambda t: t)
     Om = torch.as_tensor(np.asarray(omega, dtype=np.float32)).to(M.device)
     Yt = kernels.pcs(Om.t().contiguous(), M)                    # (l,p) = omega^T M
     for _ in range(n_iter):
-        Z = kernels.cross_gram(Yt, M)                            # (l,n) = Y^T M^T
+        Z = red(kernels.cross_gram(Yt, M))                       # (l,n) = Y^T M^T
         Yt = kernels.pcs(Z.contiguous(), M)                      # (l,p)
-    Qt = orthonormalize(Yt)
-    B = kernels.cross_gram(Qt, M)                                # (l,n) fp64
+    Qt = orthonormalize(Yt, reduce)
+    B = red(kernels.cross_gram(Qt, M))                           # (l,n) fp64
     evals, evecs, _ = kernels.eigh((B @ B.t()).contiguous())
     Wt = evecs[:ncomp].contiguous()                              # rows = leading left vectors of B
     return kernels.pcs(Wt, Qt)
