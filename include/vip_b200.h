@@ -131,6 +131,18 @@ int vb_gemm_f32(const float* A, long long lda, long long strideA, int a_mod, con
                 long long strideB, int b_mod, int trans_b, float* C, long long ldc, long long strideC, int M,
                 int N, int K, float alpha, float beta, int batch, void* stream);
 
+/* ---- Fourier sub-pixel shift (frame recentring, fake-companion injection) -------------------------
+ * The vip-fft shift of a frame is  out = Ty X Tx^T - checkerboard term  with real Toeplitz operators
+ * T[m][n] = Re D_N(m - n - s) of the zero-padded even plane of N pixels (csrc/shift.cu).
+ * vb_shift_operators_f32: T[f] (L x L, fp32) for shift[f] (pixels, fp64) and plane size nplane[f];
+ * the two products are vb_gemm_f32 calls; vb_checker_correct_f32 then applies the Nyquist term
+ * out[f][r][c] -= (-1)^(r+c) coef[f] sum_{r',c'} (-1)^(r'+c') in[f][r'][c'],  coef = sin(pi sx) sin(pi sy) / N^2
+ * (kappa_ws: nframes doubles).
+ * Replaces: cube_shift -> frame_shift(imlib='vip-fft')             preproc/recentering.py:257-305, 122-189 */
+int vb_shift_operators_f32(const double* shift, const int* nplane, int nframes, int L, float* T, void* stream);
+int vb_checker_correct_f32(const float* in, float* out, int nframes, int ny, int nx, const double* coef,
+                           double* kappa_ws, void* stream);
+
 /* ---- host -> device upload of a pixel shard (strided rows of the host cube), one DMA ---------------
  * dst[r][0..width) = src_host[r][0..width) for r < height, pitches in bytes (cudaMemcpy2DAsync). */
 int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitch, size_t width_bytes,

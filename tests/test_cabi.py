@@ -34,7 +34,10 @@ def test_library_exports_all_declared_symbols():
     lib = _cabi.lib()
     assert lib.vb_version() >= 1000
     assert lib.vb_gram_workspace_bytes(500, 262144) > 500 * 500 * 8
-    assert lib.vb_derotate_scratch_bytes(2, 512, 2048, 0) == 2 * (513 + 512) * 2048 * 8
+    # packed real planes T1[(S+1) x N], T2[S x N] + 2N per-frame scalars, fp32 (csrc/derotate.cu)
+    assert lib.vb_derotate_scratch_bytes(2, 512, 2048, 0) == 2 * ((513 + 512) * 2048 + 2 * 2048) * 4
+    # generic (direct) path: complex planes
+    assert lib.vb_derotate_scratch_bytes(2, 101, 402, 0) == 2 * (102 + 101) * 402 * 8
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -757,3 +757,74 @@ def test_pca_sdi_single_golden(vb, golden, golden_inputs):
     assert np.max(np.abs(out - g["single_nocrop"])) < tol
     out = vb.pca(cube, angs, scale_list=sl, adimsdi="single", ncomp=2, ifs_collapse_range=(1, 5), verbose=False)
     assert np.max(np.abs(out - g["single_range"])) < tol
+
+
+# ------------------------------------------------------------------ Fourier shift, median subtraction
+SHIFT_TOL = 2e-5
+
+
+def test_cube_shift_golden(vb, golden):
+    from tools.make_golden import shift_inputs
+    g = golden["shift_medsub"]
+    for key, (cube, sy, sx) in shift_inputs().items():
+        out = vb.cube_shift(cube, sy, sx)
+        assert out.dtype == cube.dtype and out.shape == cube.shape
+        assert rel_err(out, g[f"shift_{key}"]) < SHIFT_TOL, key
+    assert rel_err(vb.cube_shift(shift_inputs()["even"][0], 1.25, -0.75), g["shift_scalar"]) < SHIFT_TOL
+
+
+@pytest.mark.parametrize("S", [64, 101, 256])
+def test_cube_shift_vs_oracle_sizes(vb, S):
+    """Checkerboard-heavy frames (large Nyquist term), shifts up to +-7 px, integer and zero shifts."""
+    rng = np.random.default_rng(S)
+    n = 6
+    board = ((np.add.outer(np.arange(S), np.arange(S)) % 2) * 2.0 - 1.0)
+    cube = (rng.normal(size=(n, S, S)) + 4.0 * board).astype(np.float32)
+    sy = np.array([0.0, 2.0, -6.5, 0.31, 3.999, -0.5])
+    sx = np.array([0.0, -3.0, 1.5, -7.0, 0.5, 0.5])
+    assert rel_err(vb.cube_shift(cube, sy, sx), O.cube_shift(cube, sy, sx)) < SHIFT_TOL
+    fr = vb.frame_shift(cube[2], -6.5, 1.5)
+    ref = O.frame_shift(cube[2], -6.5, 1.5)
+    assert fr.dtype == ref.dtype and rel_err(fr, ref) < SHIFT_TOL
+
+
+def test_cube_shift_errors(vb):
+    with pytest.raises(TypeError):
+        vb.cube_shift(np.zeros((4, 4)), 1, 1)
+    with pytest.raises(TypeError):
+        vb.frame_shift(np.zeros((2, 4, 4)), 1, 1)
+    with pytest.raises(NotImplementedError):
+        vb.cube_shift(np.zeros((2, 4, 4)), 1, 1, imlib="opencv")
+    with pytest.raises(ValueError):
+        vb.cube_shift(np.zeros((2, 4, 4)), 1, 1, imlib="nope")
+
+
+def test_median_sub_golden(vb, golden, golden_inputs):
+    g = golden["shift_medsub"]
+    cube, angs = golden_inputs["small"]
+    co, cd, fr = vb.median_sub(cube, angs, verbose=False, full_output=True)
+    np.testing.assert_array_equal(co[3], g["med_cube_out3"])          # exact median, exact subtraction
+    scale = np.max(np.abs(cd))
+    assert np.max(np.abs(cd[3] - g["med_cube_der3"])) < DEROT_TOL * scale
+    assert np.max(np.abs(fr - g["med_frame"])) < DEROT_TOL * scale
+    assert fr.dtype == np.float32
+    assert np.max(np.abs(vb.median_sub(cube, angs, collapse="mean", verbose=False) - g["med_mean"])) < DEROT_TOL * scale
+    ref = adi_cube(20, 41, 4, 60.0, seed=6)[0]
+    assert np.max(np.abs(vb.median_sub(cube, angs, cube_ref=ref, verbose=False) - g["med_rdi_median"])) \
+        < DEROT_TOL * scale
+    assert np.max(np.abs(vb.median_sub(cube, angs, cube_ref=ref, collapse_ref="mean", verbose=False)
+                         - g["med_rdi_mean"])) < 2 * DEROT_TOL * scale
+
+
+def test_median_sub_radius_int_and_errors(vb, golden_inputs):
+    cube, angs = golden_inputs["small"]
+    co, cd, fr = vb.median_sub(cube, angs, radius_int=5, verbose=False, full_output=True)
+    ro, rd, rf = O.median_sub_fullframe(cube, angs, radius_int=5, full_output=True)
+    np.testing.assert_array_equal(co, ro)
+    assert np.max(np.abs(fr - rf)) < DEROT_TOL * np.max(np.abs(rd))
+    with pytest.raises(TypeError):
+        vb.median_sub(cube, angs[:-1], verbose=False)
+    with pytest.raises(NotImplementedError):
+        vb.median_sub(cube, angs, mode="annular", verbose=False)
+    with pytest.raises(RuntimeError):
+        vb.median_sub(cube, angs, mode="nope", verbose=False)

@@ -60,3 +60,22 @@ def test_randsvd_restatement(ref):
     V1 = O.svd_wrapper(M, "randsvd", 3, random_state=np.random.RandomState(5))
     V2 = O.randsvd_restated(M, 3, om)
     np.testing.assert_allclose(V1.T @ V1, V2.T @ V2, atol=1e-5)
+
+
+def test_shift_and_median_sub_bit_identical(ref):
+    _, preproc = ref
+    from vip_hci.psfsub import median_sub
+    rng = np.random.default_rng(0)
+    for (ny, nx) in ((20, 20), (21, 21), (20, 24), (25, 20)):
+        for dt in (np.float32, np.float64):
+            fr = rng.normal(size=(ny, nx)).astype(dt)
+            for sy, sx in ((1.3, -2.7), (-0.4, 0.2), (3.0, 1.0), (0.0, 0.0), (-5.5, 4.49)):
+                a, b = preproc.frame_shift(fr, sy, sx), O.frame_shift(fr, sy, sx)
+                assert a.dtype == b.dtype
+                np.testing.assert_array_equal(a, b)
+    cube, angs = adi_cube(12, 32, 3, 60.0, seed=3)
+    for kw in (dict(), dict(collapse="mean")):
+        r = median_sub(cube, angs, verbose=False, full_output=True, **kw)
+        o = O.median_sub_fullframe(cube, angs, full_output=True, **kw)
+        for x, y in zip(r, o):
+            np.testing.assert_array_equal(x, y)

@@ -121,11 +121,43 @@ def main():
     w = np.random.default_rng(1).uniform(size=30)
     out["wmean"] = cube_collapse(cube.copy(), "wmean", w=w)
     np.savez_compressed(os.path.join(OUT, "collapse.npz"), **out)
+    make_shift_medsub(inp)
     make_grid_4d(inp, pca)
     make_sdi_single(inp, pca)
     make_annular_4d(inp, pca_annular)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def shift_inputs():
+    """Seeded shift vectors / cubes shared by make_golden.py and the tests."""
+    rng = np.random.default_rng(4242)
+    d = {}
+    d["odd"] = (rng.normal(size=(7, 41, 41)).astype(np.float32), rng.uniform(-4, 4, 7), rng.uniform(-4, 4, 7))
+    sy = np.array([0.0, 1.0, -2.5, 0.3, 3.999, -0.001])
+    sx = np.array([0.0, -3.0, 1.5, -0.7, 0.5, 2.2])
+    d["even"] = (rng.normal(size=(6, 32, 32)).astype(np.float32), sy, sx)
+    d["rect"] = (rng.normal(size=(4, 20, 24)), rng.uniform(-2, 2, 4), rng.uniform(-2, 2, 4))     # float64
+    return d
+
+
+def make_shift_medsub(inp):
+    """cube_shift (vip-fft) and full-frame median_sub."""
+    ref_loader.load()
+    from vip_hci.preproc import cube_shift
+    from vip_hci.psfsub import median_sub
+    out = {}
+    for key, (cube, sy, sx) in shift_inputs().items():
+        out[f"shift_{key}"] = cube_shift(cube, sy, sx, nproc=1)
+    out["shift_scalar"] = cube_shift(shift_inputs()["even"][0], 1.25, -0.75, nproc=1)
+    cube, angs = inp["small"]
+    co, cd, fr = median_sub(cube, angs, verbose=False, full_output=True)
+    out["med_cube_out3"], out["med_cube_der3"], out["med_frame"] = co[3], cd[3], fr
+    out["med_mean"] = median_sub(cube, angs, collapse="mean", verbose=False)
+    ref = adi_cube(20, 41, 4, 60.0, seed=6)[0]
+    out["med_rdi_median"] = median_sub(cube, angs, cube_ref=ref, verbose=False)
+    out["med_rdi_mean"] = median_sub(cube, angs, cube_ref=ref, collapse_ref="mean", verbose=False)
+    np.savez_compressed(os.path.join(OUT, "shift_medsub.npz"), **out)
 
 
 def make_annular_4d(inp, pca_annular):
@@ -175,4 +207,8 @@ def make_grid_4d(inp, pca):
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "shift_medsub":      # regenerate one fixture file only
+        os.makedirs(OUT, exist_ok=True)
+        make_shift_medsub(golden_inputs())
+    else:
+        main()

@@ -40,6 +40,8 @@ SIGNATURES = {
     "vb_scatter_columns_f32": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp]),
     "vb_gemm_f32": (_i, [_vp, C.c_longlong, C.c_longlong, _i, _vp, C.c_longlong, C.c_longlong, _i, _i, _vp,
                         C.c_longlong, C.c_longlong, _i, _i, _i, _f, _f, _i, _vp]),
+    "vb_shift_operators_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "vb_checker_correct_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "vb_memcpy2d_h2d": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
     "vb_profile_enable": (None, [_i]),
     "vb_profile_read": (_i, [C.POINTER(_f)]),

@@ -36,6 +36,8 @@ int sub_f32(const float*, const float*, float*, size_t, cudaStream_t);
 struct RotParams { int S; int N; int y0; int zero_masked; int mask_is_nan; float mask_val; };
 size_t derotate_scratch_bytes_per_frame(int S, int N);
 size_t derotate_scratch_bytes_min(int S, int N);
+int shift_operators(const double*, const int*, int, int, float*, cudaStream_t);
+int checker_correct(const float*, float*, int, int, int, const double*, double*, cudaStream_t);
 int derotate_run(const float*, float*, int, const RotParams&, const int*, const double*, const double*,
                  const float2*, void*, size_t, int, int*, cudaStream_t);
 int collapse_f32(const float*, int, size_t, int, const double*, int, int, void*, cudaStream_t);
@@ -190,6 +192,17 @@ int vb_derotate_f32(const float* in, float* out, int nframes, int S, int N, int 
                                 &nl, (cudaStream_t)stream);
     g_launches += nl;
     return rc;
+}
+
+int vb_shift_operators_f32(const double* shift, const int* nplane, int nframes, int L, float* T, void* stream) {
+    g_launches += 1;
+    return shift_operators(shift, nplane, nframes, L, T, (cudaStream_t)stream);
+}
+
+int vb_checker_correct_f32(const float* in, float* out, int nframes, int ny, int nx, const double* coef,
+                           double* kappa_ws, void* stream) {
+    g_launches += 2;
+    return checker_correct(in, out, nframes, ny, nx, coef, kappa_ws, (cudaStream_t)stream);
 }
 
 int vb_collapse_f32(const float* cube, int n, size_t p, int mode, const double* w, int trim_k, int trim_n,

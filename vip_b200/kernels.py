@@ -235,6 +235,29 @@ def gemm(A, B, C, trans_b=False, alpha=1.0, beta=0.0, a_mod=0, b_mod=0):
     return C
 
 
+def shift_operators(shifts, nplane, L, device):
+    """(nf, L, L) fp32 Toeplitz operators of the vip-fft shift: T[f][m][n] = Re D_N(m - n - shift[f])."""
+    lib = _cabi.lib()
+    nf = len(shifts)
+    d_s = torch.as_tensor(np.asarray(shifts, dtype=np.float64)).to(device)
+    d_n = torch.as_tensor(np.asarray(nplane, dtype=np.int32)).to(device)
+    T = empty((nf, L, L), torch.float32, device)
+    _cabi.check(lib.vb_shift_operators_f32(ptr(d_s), ptr(d_n), nf, L, ptr(T), stream_ptr()), "vb_shift_operators_f32")
+    return T
+
+
+def checker_correct(X, out, coef):
+    """out[f] -= (-1)^(r+c) coef[f] sum_{r',c'} (-1)^(r'+c') X[f]  (Nyquist term of the separable shift)."""
+    lib = _cabi.lib()
+    nf, ny, nx = X.shape
+    assert X.is_contiguous() and out.is_contiguous()
+    d_c = torch.as_tensor(np.asarray(coef, dtype=np.float64)).to(X.device)
+    ws = empty((nf,), torch.float64, X.device)
+    _cabi.check(lib.vb_checker_correct_f32(ptr(X), ptr(out), nf, ny, nx, ptr(d_c), ptr(ws), stream_ptr()),
+                "vb_checker_correct_f32")
+    return out
+
+
 def upload_and_gram(host2d, device, nslabs=8):
     """C-contiguous fp32 host matrix (n,p) -> (M on the device, G = M M^T fp64), upload and SYRK pipelined."""
     lib = _cabi.lib()
