@@ -828,3 +828,38 @@ def test_median_sub_radius_int_and_errors(vb, golden_inputs):
         vb.median_sub(cube, angs, mode="annular", verbose=False)
     with pytest.raises(RuntimeError):
         vb.median_sub(cube, angs, mode="nope", verbose=False)
+
+
+# ------------------------------------------------------------------ pca with source_xy (PA-rejection libraries)
+def test_pca_source_xy_golden(vb, golden, golden_inputs):
+    from tools.make_golden import SOURCE_XY_CASES
+    g = golden["pca_source_xy"]
+    cube, angs = golden_inputs["small"]
+    ref = adi_cube(20, 41, 4, 60.0, seed=6)[0]
+    for key, kw in SOURCE_XY_CASES.items():
+        extra = dict(cube_ref=ref) if key == "rdi" else {}
+        fr, recon, res, res_ = vb.pca(cube, angs, verbose=False, full_output=True, **kw, **extra)
+        assert fr.dtype == np.float32 and recon.shape == cube.shape and res_.shape == cube.shape
+        assert rel_err(res, g[f"{key}_res"]) < PCA_TOL, key
+        scale = np.max(np.abs(g[f"{key}_res"]))
+        assert np.max(np.abs(recon[7] - g[f"{key}_recon7"])) < PCA_TOL * np.max(np.abs(cube)), key
+        c64 = cube.astype(np.float64)
+        e64 = {k: v.astype(np.float64) for k, v in extra.items()}
+        assert_parity(fr, g[f"{key}_frame"], lambda: O.pca_fullframe(c64, angs, **kw, **e64), FRAME_TOL, key)
+        np.testing.assert_array_equal(vb.pca(cube, angs, verbose=False, **kw, **extra), fr)
+
+
+def test_pca_source_xy_large_libraries_and_errors(vb):
+    """Libraries of more than 256 frames go through the full-size eigensolvers, frame by frame."""
+    cube, angs = adi_cube(300, 24, 3, 90.0, seed=12)
+    kw = dict(source_xy=(18, 14), delta_rot=0.5, fwhm=4, ncomp=3)
+    fr = vb.pca(cube, angs, verbose=False, **kw)
+    ref = O.pca_fullframe(cube, angs, **kw)
+    assert_parity(fr, ref, lambda: O.pca_fullframe(cube.astype(np.float64), angs, **kw), FRAME_TOL)
+    small, a = adi_cube(30, 41, 4, 60.0, seed=5)
+    with pytest.raises(RuntimeError, match="min_frames_pca"):
+        vb.pca(small, a, source_xy=(30, 25), delta_rot=1, fwhm=4, ncomp=3, verbose=False)
+    with pytest.raises(TypeError):
+        vb.pca(small, a, source_xy=(30, 25), ncomp=3, verbose=False)          # delta_rot missing
+    with pytest.raises(NotImplementedError):
+        vb.pca(small, a, source_xy=(30, 25), delta_rot=0.5, ncomp=(1, 3), verbose=False)

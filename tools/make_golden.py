@@ -122,6 +122,7 @@ def main():
     out["wmean"] = cube_collapse(cube.copy(), "wmean", w=w)
     np.savez_compressed(os.path.join(OUT, "collapse.npz"), **out)
     make_shift_medsub(inp)
+    make_source_xy(inp, pca)
     make_grid_4d(inp, pca)
     make_sdi_single(inp, pca)
     make_annular_4d(inp, pca_annular)
@@ -158,6 +159,26 @@ def make_shift_medsub(inp):
     out["med_rdi_median"] = median_sub(cube, angs, cube_ref=ref, verbose=False)
     out["med_rdi_mean"] = median_sub(cube, angs, cube_ref=ref, collapse_ref="mean", verbose=False)
     np.savez_compressed(os.path.join(OUT, "shift_medsub.npz"), **out)
+
+
+SOURCE_XY_CASES = {
+    "plain": dict(source_xy=(33, 28), delta_rot=0.5, fwhm=4, ncomp=3, min_frames_pca=5),
+    "trunc": dict(source_xy=(33, 28), delta_rot=0.3, fwhm=4, ncomp=3, max_frames_pca=12, min_frames_pca=5),
+    "rdi": dict(source_xy=(28, 12), delta_rot=1, fwhm=4, ncomp=4),          # + cube_ref
+    "scaled": dict(source_xy=(33, 28), delta_rot=0.5, fwhm=4, ncomp=2, scaling="temp-mean", min_frames_pca=5),
+}
+
+
+def make_source_xy(inp, pca):
+    """pca(..., source_xy=..., delta_rot=...): frame-by-frame PCA with a PA-rejection library."""
+    cube, angs = inp["small"]
+    ref = adi_cube(20, 41, 4, 60.0, seed=6)[0]
+    out = {}
+    for key, kw in SOURCE_XY_CASES.items():
+        extra = dict(cube_ref=ref) if key == "rdi" else {}
+        fr, recon, res, res_ = pca(cube, angs, verbose=False, full_output=True, **kw, **extra)
+        out[f"{key}_frame"], out[f"{key}_res"], out[f"{key}_recon7"] = fr, res, recon[7]
+    np.savez_compressed(os.path.join(OUT, "pca_source_xy.npz"), **out)
 
 
 def make_annular_4d(inp, pca_annular):
@@ -210,5 +231,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "shift_medsub":      # regenerate one fixture file only
         os.makedirs(OUT, exist_ok=True)
         make_shift_medsub(golden_inputs())
+    elif len(sys.argv) > 1 and sys.argv[1] == "source_xy":
+        ref_loader.load()
+        from vip_hci.psfsub import pca as _pca
+        make_source_xy(golden_inputs(), _pca)
     else:
         main()

@@ -180,9 +180,11 @@ def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, 
 
 def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_px, svd_mode, collapse,
                         verbose, full_output, weights=None, cube_sig=None, random_state=None,
-                        keep_on_device=False, **rot_options):
-    """``_adi_rdi_pca`` (``pca_fullfr.py:801-1035``) for scalar ``ncomp`` without ``source_xy`` /
-    ``batch`` / ``mask_rdi``: PCA residuals -> derotation -> collapse."""
+                        keep_on_device=False, source_xy=None, delta_rot=None, fwhm=4, min_frames_pca=10,
+                        max_frames_pca=None, **rot_options):
+    """``_adi_rdi_pca`` (``pca_fullfr.py:801-1035``) for scalar ``ncomp`` without ``batch`` /
+    ``mask_rdi``: PCA residuals (whole matrix, or frame by frame with a PA-rejection library when
+    ``source_xy`` is given) -> derotation -> collapse."""
     n, y, x = cube.shape
     angle_list = check_pa_vector(np.asarray(angle_list))
     if n != angle_list.shape[0]:
@@ -205,6 +207,7 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
     as_dev = (lambda a: a.to(dev).float()) if isinstance(cube, torch.Tensor) else (lambda a: to_device_f32(a, dev))
     gram = None
     plain = (cube_ref is None and cube_sig is None and scaling is None and not mask_center_px
+             and source_xy is None
              and _mode_name(svd_mode) in _EXACT_MODES and isinstance(ncomp, (int, np.integer)))
     if (plain and isinstance(cube, np.ndarray) and cube.dtype == np.float32 and cube.flags["C_CONTIGUOUS"]):
         # host cube: upload in pixel slabs and accumulate the Gramian while the next slab is in flight
@@ -215,13 +218,23 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
     ref_dev = as_dev(cube_ref) if cube_ref is not None else None
     sig_dev = as_dev(cube_sig) if cube_sig is not None else None
 
-    res = project_subtract_device(cube_dev, ncomp, scaling, mask_center_px, svd_mode, ref_dev, sig_dev,
-                                  full_output=full_output, verbose=verbose, random_state=random_state,
-                                  gram=gram)
-    if full_output:
-        residuals_cube, recon, V = res
+    if source_xy is not None:
+        residuals_cube, recon, nfrslib = pa_rejection_residuals_device(
+            cube_dev, ref_dev, sig_dev, angle_list, ncomp, scaling, mask_center_px, svd_mode, source_xy,
+            delta_rot, fwhm, min_frames_pca, max_frames_pca, full_output)
+        V = None
+        if verbose:
+            print("Size LIB: min={:.1f} / 10th perc.={:.1f} / median={:.1f} / 90th perc.={:.1f} / max={:.1f}".format(
+                np.min(nfrslib), np.percentile(nfrslib, 10), np.median(nfrslib), np.percentile(nfrslib, 90),
+                np.max(nfrslib)))
     else:
-        residuals_cube = res
+        res = project_subtract_device(cube_dev, ncomp, scaling, mask_center_px, svd_mode, ref_dev, sig_dev,
+                                      full_output=full_output, verbose=verbose, random_state=random_state,
+                                      gram=gram)
+        if full_output:
+            residuals_cube, recon, V = res
+        else:
+            residuals_cube = res
     residuals_cube_ = derotate_device(residuals_cube, -angle_list, mask_val=mask_val, interp_zeros=interp_zeros)
     frame = collapse_device(residuals_cube_, mode=collapse, w=weights)
     if mask_center_px:
@@ -230,11 +243,114 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
         frame = frame.masked_fill(mask, 0.0)
     if verbose:
         print("Done de-rotating and combining")
-    if full_output:
+    if full_output and source_xy is not None:
+        out = (recon.reshape(n, y, x), residuals_cube, residuals_cube_, frame)       # pca_fullfr.py:996-1000
+    elif full_output:
         out = (V.reshape(V.shape[0], y, x), recon.reshape(n, y, x), residuals_cube, residuals_cube_, frame)
     else:
         out = frame
     return out
+
+
+def pa_rejection_residuals_device(cube_dev, ref_dev, sig_dev, angle_list, ncomp, scaling, mask_center_px,
+                                  svd_mode, source_xy, delta_rot, fwhm, min_frames_pca, max_frames_pca,
+                                  full_output=False):
+    """The ``source_xy`` branch of ``_adi_rdi_pca`` (``pca_fullfr.py:911-965``) with ``_project_subtract``'s
+    frame-by-frame mode (:1640-1710): frame f is projected on the PCs of the library of frames whose
+    parallactic angle differs from PA_f by more than the threshold set by ``delta_rot`` x ``fwhm`` at the
+    separation of ``source_xy`` (+ all reference frames).
+
+    The reference runs n SVDs of (library x pixels) matrices.  Here: ONE Gramian of the stacked matrix,
+    then per frame the leading eigenpairs of the library's sub-block:
+    ``(lambda, E) = eig_k(G[I,I])``, ``w = E diag(1/lambda) E^T G[I,f]``, residual ``= M_f - w^T M_emp[I]``.
+    Libraries of up to 256 frames with ncomp <= 24 go through the batched kernel of the annular path
+    (``vb_annular_weights_f64``); larger ones through the full-size eigensolvers, one frame at a time.
+    Returns (residuals (n,H,W), reconstruction (n,p) or None, library sizes)."""
+    from ..preproc.derotation import _compute_pa_thresh, _find_indices_adi
+    from ..var.coords import dist, frame_center
+    n, y, x = cube_dev.shape
+    dev = cube_dev.device
+    svd_mode = _mode_name(svd_mode)
+    if svd_mode not in _EXACT_MODES:
+        _unsupported(f"svd_mode={svd_mode!r} with `source_xy`")
+    if delta_rot is None or fwhm is None:
+        raise TypeError("Delta_rot or fwhm parameters missing. Needed forPA-based rejection of frames from the "
+                        "library")
+    if not isinstance(ncomp, (int, np.integer, float, np.floating)):
+        raise TypeError("Type not recognized for ncomp, should be int or float")
+    matrix = prepare_matrix_device(cube_dev, scaling, mask_center_px)
+    if isinstance(ncomp, (float, np.floating)):
+        # CEVR of the whole cube -> ncomp (pca_fullfr.py:1624-1637)
+        if not 1 > ncomp > 0:
+            raise ValueError("if `ncomp` is float, it must lie in the interval (0,1]")
+        ncomp = int(np.searchsorted(Decomposition(matrix, None).cevr(), ncomp) + 1)
+    ncomp = int(ncomp)
+    matrix_emp = matrix if sig_dev is None else matrix - sig_dev.reshape(sig_dev.shape[0], -1)
+    matrix_ref = prepare_matrix_device(ref_dev, scaling, mask_center_px) if ref_dev is not None else None
+    nref = 0 if matrix_ref is None else matrix_ref.shape[0]
+
+    yc, xc = frame_center((y, x))
+    x1, y1 = source_xy
+    pa_thr = _compute_pa_thresh(dist(yc, xc, y1, x1), fwhm, delta_rot)
+    truncate = max_frames_pca is not None
+    lists = [_find_indices_adi(angle_list, f, pa_thr, truncate=truncate, max_frames=max_frames_pca)
+             for f in range(n)]
+    msg = "{} frames comply to delta_rot condition < less than "
+    msg1 = msg + "min_frames_pca ({}). Try decreasing delta_rot or min_frames_pca"
+    msg2 = msg + "ncomp ({}). Try decreasing the parameter delta_rot or ncomp"
+    nfrslib = []
+    for idx in lists:
+        L = len(idx) + nref
+        if L < min_frames_pca:
+            raise RuntimeError(msg1.format(L, min_frames_pca))
+        if L < ncomp:
+            raise RuntimeError(msg2.format(L, ncomp))
+        nfrslib.append(L)
+    p = y * x
+    if ncomp > p:
+        raise RuntimeError("{} PCs cannot be obtained from a matrix with size [{},{}]. Increase the size of the "
+                           "patches or request less PCs".format(ncomp, max(nfrslib), p))
+
+    lib = matrix_emp if matrix_ref is None else torch.cat((matrix_emp, matrix_ref))     # library rows after the cube
+    ntot = n + nref
+    G = kernels.gram(lib)
+    Lmax = max(nfrslib)
+    ref_rows = np.arange(n, ntot, dtype=np.int32)
+    if Lmax <= 256 and ncomp <= 24:
+        idx_host = np.zeros((n, Lmax), dtype=np.int32)
+        lens = np.asarray(nfrslib, dtype=np.int32)
+        for f, idx in enumerate(lists):
+            idx_host[f, :len(idx)] = idx
+            idx_host[f, len(idx):lens[f]] = ref_rows
+        W, iters = kernels.annular_weights(G, torch.from_numpy(idx_host).to(dev), torch.from_numpy(lens).to(dev),
+                                           torch.arange(n, dtype=torch.int32, device=dev), ncomp)
+        if bool((iters < 0).any()):
+            raise RuntimeError("vip_b200.pca: per-frame eigenproblems did not converge")
+    else:
+        W = torch.zeros((n, ntot), dtype=torch.float32, device=dev)
+        for f, idx in enumerate(lists):
+            I = torch.from_numpy(np.concatenate((idx, ref_rows)).astype(np.int64)).to(dev)
+            Gs = G.index_select(0, I).index_select(1, I).contiguous()
+            L = I.numel()
+            if kernels.topk_supported(L, ncomp):
+                lam, E, info = kernels.eigh_topk(Gs, ncomp)
+                if not info["converged"]:
+                    lam, E, _ = kernels.eigh(Gs)
+            else:
+                lam, E, _ = kernels.eigh(Gs)
+            lam, E = lam[:ncomp], E[:ncomp]                        # E rows = eigenvectors of G[I,I]
+            g = G[f].index_select(0, I)                             # M_emp[f] . M_emp[I]^T
+            w = E.t() @ ((E @ g) / lam)
+            W[f, I] = w.to(torch.float32)
+    recon = None
+    if full_output:
+        recon = torch.zeros_like(matrix)
+        kernels.gemm(W.unsqueeze(0), lib.unsqueeze(0), recon.unsqueeze(0))
+        R = kernels.sub(matrix, recon)
+    else:
+        R = matrix.clone()
+        kernels.gemm(W.unsqueeze(0), lib.unsqueeze(0), R.unsqueeze(0), alpha=-1.0, beta=1.0)
+    return R.reshape(n, y, x), recon, nfrslib
 
 
 def _grid_pclist(range_pcs, n):
@@ -473,8 +589,8 @@ def pca(*all_args: List, **all_kwargs: dict):
         _unsupported("`left_eigv`")
     if p.mask_rdi is not None:
         _unsupported("`mask_rdi` (data imputation)")
-    if p.source_xy is not None:
-        _unsupported("`source_xy` (PA-threshold library / S/N optimisation)")
+    if p.source_xy is not None and isinstance(p.ncomp, (tuple, list)):
+        _unsupported("`source_xy` with a tuple/list `ncomp` (S/N-optimised number of components)")
     if p.smooth is not None:
         _unsupported("`smooth`")
     imlib = _mode_name(p.imlib)
@@ -509,6 +625,10 @@ def pca(*all_args: List, **all_kwargs: dict):
     res = _adi_rdi_pca_device(**func_params, **rot_options)
 
     dt = p.cube.dtype
+    if p.full_output and p.source_xy is not None:
+        recon_cube, residuals_cube, residuals_cube_, frame = res                      # pca_fullfr.py:781
+        return (_to_numpy_like(frame, dt), _to_numpy_like(recon_cube, dt), _to_numpy_like(residuals_cube, dt),
+                _to_numpy_like(residuals_cube_, dt))
     if p.full_output:
         pcs, recon, residuals_cube, residuals_cube_, frame = res
         return (_to_numpy_like(frame, dt), _to_numpy_like(pcs, dt), _to_numpy_like(recon, dt),
