@@ -61,12 +61,9 @@ def frame_shift(array, shift_y, shift_x, imlib="vip-fft", interpolation="lanczos
     if not isinstance(array, np.ndarray) or array.ndim != 2:
         raise TypeError("Input array is not a frame or 2d array")
     _check_imlib(imlib)
-    ny, nx = array.shape
     out = cube_shift_device(to_device_f32(array[None]), [shift_y], [shift_x])[0]
-    # the reference keeps the input dtype only while the padded plane is already square and even
-    npad = int(np.ceil(np.amax(np.abs([shift_y, shift_x]))))
-    keep = ny == nx and (ny + 2 * npad) % 2 == 0 and array.dtype == np.float32
-    return to_host(out, dtype=np.float32 if keep else np.float64)
+    # the reference multiplies the spectrum by a complex128 ramp: float64 out whatever the input dtype
+    return to_host(out, dtype=np.float64)
 
 
 def cube_shift(cube, shift_y, shift_x, imlib="vip-fft", interpolation="lanczos4", border_mode="reflect",

@@ -346,10 +346,8 @@ def pa_rejection_residuals_device(cube_dev, ref_dev, sig_dev, angle_list, ncomp,
     if full_output:
         recon = torch.zeros_like(matrix)
         kernels.gemm(W.unsqueeze(0), lib.unsqueeze(0), recon.unsqueeze(0))
-        R = kernels.sub(matrix, recon)
-    else:
-        R = matrix.clone()
-        kernels.gemm(W.unsqueeze(0), lib.unsqueeze(0), R.unsqueeze(0), alpha=-1.0, beta=1.0)
+    R = matrix.clone()                                   # same bits with and without full_output
+    kernels.gemm(W.unsqueeze(0), lib.unsqueeze(0), R.unsqueeze(0), alpha=-1.0, beta=1.0)
     return R.reshape(n, y, x), recon, nfrslib
 
 
