@@ -54,6 +54,25 @@ __device__ __forceinline__ float plane_sample(const float* __restrict__ frame, c
     return v;
 }
 
+// Offset of plane pixel (i, j) inside the frame (same mapping as plane_sample), or -1 outside the frame.
+__device__ __forceinline__ int plane_offset(const RotParams& g, int k, int i, int j) {
+    int r, c;
+    if (k == 0)      { r = i;       c = j; }
+    else if (k == 1) { r = j;       c = g.N - i; }
+    else if (k == 2) { r = g.N - i; c = g.N - j; }
+    else             { r = g.N - j; c = i; }
+    const int fy = r - g.y0, fx = c - g.y0;
+    if (fy < 0 || fy >= g.S || fx < 0 || fx >= g.S) return -1;
+    return fy * g.S + fx;
+}
+
+// what enters the rotation for a raw frame sample (NaNs and, optionally, masked pixels count as 0)
+__device__ __forceinline__ float clean_sample(float v, const RotParams& g) {
+    if (isnan(v)) return 0.f;
+    if (g.zero_masked && v == g.mask_val) return 0.f;
+    return v;
+}
+
 __device__ __forceinline__ bool is_masked(float v, const RotParams& g) {
     return g.mask_is_nan ? isnan(v) : (v == g.mask_val);
 }
@@ -861,6 +880,100 @@ shear_rows_first_pk(const float* __restrict__ in, float* __restrict__ T1, float*
     }
 }
 
+// ---- pass 1 (packed), looped: every CTA walks PP consecutive row pairs and fetches the samples of the NEXT
+// pair with 4-byte cp.async (zero-fill outside the frame) into per-thread staging slots while the current
+// transform runs.  The one-shot kernel above starts every CTA with two dependent global round trips
+// (krot[f] -> gather; strided by S floats for odd rot90 counts): ncu r01k shows long_scoreboard as its top
+// stall (2.5 warps per issue) and 56 % issue-active against 78 % for pass 3.  Staging slots are private to
+// the thread that filled them, so no barrier is needed for them.
+__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gsrc, bool pred) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
+template <int N, int NT, int MINB, int PP>
+__global__ void __launch_bounds__(NT * N / 16, MINB)
+shear_rows_first_pk_loop(const float* __restrict__ in, float* __restrict__ T1, float* __restrict__ aux,
+                         RotParams g, const int* __restrict__ krot, const double* __restrict__ a_coef,
+                         const float2* __restrict__ tw, int frame0) {
+    using F = ShearFft<N>;
+    constexpr int T = F::T;
+    extern __shared__ float2 smem2[];
+    __shared__ float2 ph3s[NT][32];
+    __shared__ float stage[NT][2][5][T];          // [row a/b][j = 0..3 and the lone sample n' = S][t]
+    const int tr = threadIdx.x / T, t = threadIdx.x % T;
+    const int fl = blockIdx.y, f = frame0 + fl;
+    const int k = krot[f];
+    const double ac = a_coef[f];
+    const float* frame = in + (size_t)f * g.S * g.S;
+    float2* buf = smem2 + (size_t)tr * 2 * F::BUF;
+    float* beta = aux + (size_t)fl * AuxLayout::stride(N) + AuxLayout::beta(g.S);
+
+    auto prefetch = [&](int it) {
+        const int row = 2 * ((blockIdx.x * PP + it) * NT + tr);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool v = row + h <= g.S;
+            const int i = g.y0 + row + h;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int off = v ? plane_offset(g, k, i, g.y0 + t + j * T) : -1;
+                cp_async4_zfill(&stage[tr][h][j][t], frame + (off < 0 ? 0 : off), off >= 0);
+            }
+            if (t == 0) {
+                const int off = v ? plane_offset(g, k, i, g.y0 + g.S) : -1;
+                cp_async4_zfill(&stage[tr][h][4][0], frame + (off < 0 ? 0 : off), off >= 0);
+            }
+        }
+        cp_async_commit();
+    };
+
+    prefetch(0);
+#pragma unroll 1
+    for (int it = 0; it < PP; ++it) {
+        const int row0 = 2 * (blockIdx.x * PP + it) * NT;          // first row of this iteration (CTA-uniform)
+        if (row0 > g.S) break;
+        const int row = row0 + 2 * tr;
+        const bool va = row <= g.S, vb_ = row + 1 <= g.S;
+        const int i = g.y0 + row;
+        cp_async_wait_all();
+        float re[16], im[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            re[j] = clean_sample(stage[tr][0][j][t], g);
+            im[j] = clean_sample(stage[tr][1][j][t], g);
+        }
+        float x4r = 0.f, x4i = 0.f;
+        if (t == 0) {
+            x4r = clean_sample(stage[tr][0][4][0], g);
+            x4i = clean_sample(stage[tr][1][4][0], g);
+        }
+        if (it + 1 < PP) prefetch(it + 1);       // own slots only: already consumed above
+        int sa_int, sb_int; float sa_frac, sb_frac;
+        split_shift(ac * (double)(i - N / 2), sa_int, sa_frac);
+        split_shift(ac * (double)(i + 1 - N / 2), sb_int, sb_frac);
+        float nya, nyb;
+        F::template run_pair<true, false>(re, im, buf, buf + F::BUF, ph3s[tr], tw, t, tr, sa_int, sa_frac,
+                                          sb_int, sb_frac, x4r, x4i, nya, nyb);
+        float* dst = T1 + ((size_t)fl * (g.S + 1) + row) * N;
+        if (va) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[t + j * T] = re[j];
+        }
+        if (vb_) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[N + t + j * T] = im[j];
+        }
+        if (t == 0) {
+            if (va) beta[row] = nya;
+            if (vb_) beta[row + 1] = nyb;
+        }
+        __syncthreads();                         // buf / zbuf / ph3s are reused by the next pair
+    }
+    cp_async_wait_all();
+}
+
 // ---- aux 1: sigma and Cs of one frame (one CTA of N/16 threads per frame)
 template <int N>
 __global__ void __launch_bounds__(N / 16)
@@ -1288,6 +1401,16 @@ static int fft_packed() {
     return v;
 }
 
+// pass 1: 1 = looped kernel with cp.async prefetch of the next row pair (default), 0 = one pair per CTA
+static int fft_rows_loop() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VIP_B200_FFT_ROWS_LOOP");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 static size_t packed_bytes_per_frame(int S, int N) {
     return ((size_t)(S + 1) * N + (size_t)S * N + AuxLayout::stride(N)) * sizeof(float);
 }
@@ -1332,6 +1455,8 @@ static int launch_fft_chunk_pk(const float* in, float* out, float* T1, float* T2
     if (!configured) {
         VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_first_pk<N, NT, MINB>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_first_pk_loop<N, NT, MINB, 4>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
         VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_last_pk<N, NT, MINB>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
         VB_CHECK_CUDA(cudaFuncSetAttribute(shear_aux_beta<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1341,8 +1466,14 @@ static int launch_fft_chunk_pk(const float* in, float* out, float* T1, float* T2
     const int threads = NT * F::T;
     const int pairs1 = (g.S + 2) / 2, pairs3 = g.S / 2;
     g_timer.mark(st);
-    shear_rows_first_pk<N, NT, MINB><<<dim3(ceil_div(pairs1, NT), nf), threads, smem_rows, st>>>(
-        in, T1, aux, g, krot, a, tw, frame0);
+    if (fft_rows_loop()) {
+        constexpr int PP = 4;
+        shear_rows_first_pk_loop<N, NT, MINB, PP><<<dim3(ceil_div(pairs1, NT * PP), nf), threads, smem_rows, st>>>(
+            in, T1, aux, g, krot, a, tw, frame0);
+    } else {
+        shear_rows_first_pk<N, NT, MINB><<<dim3(ceil_div(pairs1, NT), nf), threads, smem_rows, st>>>(
+            in, T1, aux, g, krot, a, tw, frame0);
+    }
     VB_CHECK_LAUNCH();
     g_timer.mark(st);
     shear_aux_beta<N><<<nf, F::T, smem_aux, st>>>(aux, g, b, tw, frame0);
