@@ -341,16 +341,19 @@ def run_gpu(args):
         alg_bytes = 8.0 * p * n       # read residual cube + write derotated cube
         achieved = alg_bytes / (derot_ms * 1e-3) / 1e9
         # DRAM bytes of the three shear kernels for one 500x512x512 step, from the committed ncu --set full
-        # captures (profiles/r01a_ncu_full_c2.md rows kernels, profiles/r01e_ncu_full_c2.md columns kernel):
-        # the complex planes T1/T2 between the passes (the transposition of the 3-shear algorithm) make it
-        # 17x the algorithmic 8p bytes/frame
-        traffic = 18.27e9 if (n, size) == (500, 512) else None
+        # capture of the packed real-plane kernels (profiles/r01k_ncu_pk.md, 100 frames, scaled x5): the real
+        # planes T1/T2 between the passes (the transposition of the 3-shear algorithm) make it 9x the
+        # algorithmic 8p bytes/frame (18.3 GB with the complex planes of r01j)
+        traffic = 9.45e9 if (n, size) == (500, 512) else None
         line["roofline"] = {
-            "kernel": "vb_derotate_f32 = shear_rows_first + shear_cols + shear_rows_last (one launch each per chunk)",
+            "kernel": ("vb_derotate_f32 = shear_rows_first_pk_loop + shear_cols_pk + shear_rows_last_pk (+ two "
+                       "per-frame scalar kernels), one launch each per chunk; two real lines per complex transform"),
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": traffic, "peak_source": peak_kind,
             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": derot_ms,
-            "note": "stage is fp32-FFT-arithmetic bound, not HBM bound (DESIGN.md): ~220 flop per algorithmic byte",
+            "note": ("stage is fp32-FFT-arithmetic bound, not HBM bound (DESIGN.md): ~330 flop per algorithmic byte; "
+                     "fft_gflop counts the reference's pruned complex transforms (2S+1+N per frame, forward + "
+                     "inverse), the kernels run half as many by packing two real lines per transform"),
             "fft_gflop": None if fft_flop is None else fft_flop / 1e9,
             "fft_tflops_achieved": None if fft_flop is None else fft_flop / (derot_ms * 1e-3) / 1e12,
             "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,

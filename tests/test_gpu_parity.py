@@ -863,3 +863,20 @@ def test_pca_source_xy_large_libraries_and_errors(vb):
         vb.pca(small, a, source_xy=(30, 25), ncomp=3, verbose=False)          # delta_rot missing
     with pytest.raises(NotImplementedError):
         vb.pca(small, a, source_xy=(30, 25), delta_rot=0.5, ncomp=(1, 3), verbose=False)
+
+
+def test_pca_left_eigv_golden(vb, golden, golden_inputs):
+    """left_eigv: same reconstruction as the pixel-space projection; 'pcs' are the temporal vectors (k, n)."""
+    g = golden["pca_left_eigv"]
+    cube, angs = golden_inputs["small"]
+    fr, pcs, recon, res, res_ = vb.pca(cube, angs, ncomp=4, left_eigv=True, verbose=False, full_output=True)
+    assert pcs.shape == (4, cube.shape[0])
+    assert rel_err(res, g["left_res"]) < PCA_TOL
+    assert np.max(np.abs(np.abs(pcs @ g["left_pcs"].T) - np.eye(4))) < 1e-4        # same vectors up to sign
+    c64 = cube.astype(np.float64)
+    assert_parity(fr, g["left_frame"], lambda: O.pca_fullframe(c64, angs, ncomp=4, left_eigv=True), FRAME_TOL)
+    fr2 = vb.pca(cube, angs, ncomp=3, left_eigv=True, scaling="spat-mean", verbose=False)
+    assert_parity(fr2, g["left_scaled_frame"],
+                  lambda: O.pca_fullframe(c64, angs, ncomp=3, left_eigv=True, scaling="spat-mean"), FRAME_TOL)
+    with pytest.raises(NotImplementedError):
+        vb.pca(cube, angs, ncomp=3, left_eigv=True, mask_center_px=3, verbose=False)

@@ -91,6 +91,7 @@ def main():
     out["small_ardi"] = pca(cube, angs, cube_ref=ref, ncomp=4, ref_strategy="ARDI", verbose=False)
     out["small_cevr"] = pca(cube, angs, ncomp=0.9995, verbose=False)
     np.savez_compressed(os.path.join(OUT, "pca_fullframe.npz"), **out)
+    make_left_eigv(inp, pca)
 
     out = {}
     cube, angs = inp["ann"]
@@ -159,6 +160,15 @@ def make_shift_medsub(inp):
     out["med_rdi_median"] = median_sub(cube, angs, cube_ref=ref, verbose=False)
     out["med_rdi_mean"] = median_sub(cube, angs, cube_ref=ref, collapse_ref="mean", verbose=False)
     np.savez_compressed(os.path.join(OUT, "shift_medsub.npz"), **out)
+
+
+def make_left_eigv(inp, pca):
+    """pca(..., left_eigv=True): projection on the temporal singular vectors."""
+    cube, angs = inp["small"]
+    fr, pcs, recon, res, res_ = pca(cube, angs, ncomp=4, left_eigv=True, verbose=False, full_output=True)
+    out = {"left_frame": fr, "left_pcs": pcs, "left_res": res}
+    out["left_scaled_frame"] = pca(cube, angs, ncomp=3, left_eigv=True, scaling="spat-mean", verbose=False)
+    np.savez_compressed(os.path.join(OUT, "pca_left_eigv.npz"), **out)
 
 
 SOURCE_XY_CASES = {
@@ -231,6 +241,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "shift_medsub":      # regenerate one fixture file only
         os.makedirs(OUT, exist_ok=True)
         make_shift_medsub(golden_inputs())
+    elif len(sys.argv) > 1 and sys.argv[1] == "left_eigv":
+        ref_loader.load()
+        from vip_hci.psfsub import pca as _pca
+        make_left_eigv(golden_inputs(), _pca)
     elif len(sys.argv) > 1 and sys.argv[1] == "source_xy":
         ref_loader.load()
         from vip_hci.psfsub import pca as _pca

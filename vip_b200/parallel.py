@@ -9,6 +9,8 @@ SURVEY.md 8(e): the path shards with two real exchange steps and no other commun
                                   derotate own frames                               (local)
     all-to-all #2 (frame -> pixel shards):   D[:, p_g]
                                   collapse own pixels, gather the frame on rank 0
+    (collapse 'mean' / 'sum' are reducible: instead of all-to-all #2, partial sums over the own frames and
+     one NCCL reduce of the (H,W) frame to rank 0)
 
 The reference has no distributed mode (its ``nproc`` forks processes over frames,
 ``preproc/derotation.py:392-397``); this module is new functionality behind the same ``pca`` semantics
@@ -173,6 +175,22 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
     _all_to_all(send, recv, group)
     mine = torch.cat(recv, dim=1).reshape(f1 - f0, H, W)                # my frames, all pixels
     der = ops.derotate(mine, -angle_list[f0:f1]) if f1 > f0 else mine
+
+    if collapse in ("mean", "sum"):
+        # ---- reducible collapse: partial sums over the own frames, one NCCL reduce of an (H,W) frame ------
+        # (PCA residuals hold no NaNs -- a NaN in the cube would already have poisoned the Gramian -- so
+        # nanmean == sum / n here; the non-reducible modes take the all-to-all below)
+        part = ops.collapse(der.reshape(f1 - f0, p), "sum") if f1 > f0 else torch.zeros(p, device=device)
+        part = part.to(torch.float32).contiguous()
+        dist.reduce(part, dst=src, op=dist.ReduceOp.SUM, group=group)
+        frame = None
+        if rank == 0:
+            if collapse == "mean":
+                part = part / n
+            frame = part.reshape(H, W).cpu().numpy()
+        if full_output:
+            return frame, der, (f0, f1)
+        return frame
 
     # ---- exchange 2: frame shards -> pixel shards, collapse, gather --------------------------------
     der2 = der.reshape(f1 - f0, p)

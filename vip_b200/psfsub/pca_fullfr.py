@@ -181,7 +181,7 @@ def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, 
 def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_px, svd_mode, collapse,
                         verbose, full_output, weights=None, cube_sig=None, random_state=None,
                         keep_on_device=False, source_xy=None, delta_rot=None, fwhm=4, min_frames_pca=10,
-                        max_frames_pca=None, **rot_options):
+                        max_frames_pca=None, left_eigv=False, **rot_options):
     """``_adi_rdi_pca`` (``pca_fullfr.py:801-1035``) for scalar ``ncomp`` without ``batch`` /
     ``mask_rdi``: PCA residuals (whole matrix, or frame by frame with a PA-rejection library when
     ``source_xy`` is given) -> derotation -> collapse."""
@@ -245,6 +245,13 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
         print("Done de-rotating and combining")
     if full_output and source_xy is not None:
         out = (recon.reshape(n, y, x), residuals_cube, residuals_cube_, frame)       # pca_fullfr.py:996-1000
+    elif full_output and left_eigv:
+        # `left_eigv` projects on the temporal (left) singular vectors U_k: U_k U_k^T M = M V_k^T V_k, the same
+        # reconstruction as the pixel-space projection (pca_fullfr.py:1697-1700, 1723-1726); only the returned
+        # "pcs" differ: V.T of the reference = U_k^T, shape (k, n) (:905).  U_k S_k = M_emp V_k^T.
+        US = kernels.cross_gram(V, scale_matrix_device(cube_dev.reshape(n, y * x), scaling))   # (k, n) = S_k U_k^T
+        pcs_left = (US / torch.linalg.vector_norm(US, dim=1, keepdim=True)).to(torch.float32)
+        out = (pcs_left, recon.reshape(n, y, x), residuals_cube, residuals_cube_, frame)
     elif full_output:
         out = (V.reshape(V.shape[0], y, x), recon.reshape(n, y, x), residuals_cube, residuals_cube_, frame)
     else:
@@ -583,8 +590,10 @@ def pca(*all_args: List, **all_kwargs: dict):
             return (frame, _to_numpy_like(r["pcs"], dt), _to_numpy_like(r["recon"], dt),
                     _to_numpy_like(r["res"], dt), _to_numpy_like(r["res_"], dt), ifs)
         return frame
-    if p.left_eigv:
-        _unsupported("`left_eigv`")
+    if p.left_eigv and (p.mask_center_px or p.source_xy is not None or isinstance(p.ncomp, (tuple, list))
+                        or p.cube_sig is not None or _mode_name(p.svd_mode) not in _EXACT_MODES):
+        _unsupported("`left_eigv` together with mask_center_px / source_xy / cube_sig / tuple ncomp / "
+                     "randomized SVD")
     if p.mask_rdi is not None:
         _unsupported("`mask_rdi` (data imputation)")
     if p.source_xy is not None and isinstance(p.ncomp, (tuple, list)):
