@@ -56,6 +56,14 @@ class NumpyOps:
         c = M.numpy().astype(np.float64) @ V.numpy().astype(np.float64).T
         return reduce(torch.from_numpy(c)).to(torch.float32)
 
+    def sdi_stage1(self, cube4d, frames, scale_list, ncomp_ifs, collapse_ifs, device):
+        fr = O.pca_adimsdi_double(cube4d, np.zeros(cube4d.shape[1]), scale_list, (ncomp_ifs, None),
+                                  collapse_ifs=collapse_ifs, frames=frames)
+        return torch.from_numpy(fr.astype(np.float32))
+
+    def project_subtract_cube(self, cube_dev, ncomp):
+        return torch.from_numpy(O.project_subtract(cube_dev.numpy(), ncomp))
+
     def derotate(self, cube, angles):
         return torch.from_numpy(O.cube_derotate(cube.numpy(), -np.asarray(angles)))
 
@@ -125,6 +133,36 @@ def test_sharded_randsvd_matches_reference_algorithm(tmp_path):
     V = O.randsvd_restated(M, 3, np.random.RandomState(11).normal(size=(24, 13)))
     res = (M - (M @ V.T) @ V).reshape(cube.shape).astype(np.float32)
     ref = O.cube_collapse(O.cube_derotate(res, angs), "median")
+    assert np.max(np.abs(frame - ref)) < 3e-4 * np.max(np.abs(ref))
+
+
+def _worker_sdi(rank, world, port, collapse, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tools.make_golden import ifs_cube
+        from vip_b200.parallel import pca_adimsdi_double_sharded
+        cube, angs, sl = ifs_cube(z=4, n=7, size=24, seed=8)        # 7 frames: uneven shards
+        frame, res_ch, der = pca_adimsdi_double_sharded(cube, angs, sl, (1, 2), collapse=collapse, ops=NumpyOps(),
+                                                        device=torch.device("cpu"), full_output=True)
+        assert res_ch.shape == (7, 24, 24)
+        if rank == 0:
+            np.save(out, frame)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("collapse", ["median", "mean"])
+def test_sharded_sdi_double_matches_single_process(tmp_path, collapse):
+    """BASELINE config 4's shape of work: ADI+mSDI double PCA sharded by ADI frame (world_size 2)."""
+    from tools.make_golden import ifs_cube
+    out = str(tmp_path / "frame.npy")
+    mp.spawn(_worker_sdi, args=(2, _free_port(), collapse, out), nprocs=2, join=True)
+    frame = np.load(out)
+    cube, angs, sl = ifs_cube(z=4, n=7, size=24, seed=8)
+    ref = O.pca_adimsdi_double(cube, angs, sl, (1, 2), collapse=collapse)
+    assert frame.shape == ref.shape
     assert np.max(np.abs(frame - ref)) < 3e-4 * np.max(np.abs(ref))
 
 

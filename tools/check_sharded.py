@@ -32,5 +32,17 @@ if rank == 0:
     err = float(np.max(np.abs(fr - ref)) / np.max(np.abs(ref)))
     print(f"sharded world={world} randsvd: rel err vs single-GPU pca(randsvd) = {err:.2e}")
     assert err < 1e-4, err
+# BASELINE config 4's mode: ADI+mSDI double PCA sharded by ADI frame == single-GPU pca(adimsdi='double')
+from tools.make_golden import ifs_cube                                   # noqa: E402
+from vip_b200.parallel import pca_adimsdi_double_sharded                  # noqa: E402
+cube4, angs4, sl = ifs_cube(z=6, n=21, size=64, seed=3)
+for collapse in ("median", "mean"):
+    fr = pca_adimsdi_double_sharded(cube4, angs4, sl, (2, 3), collapse=collapse)
+    if rank == 0:
+        ref = vip_b200.pca(cube4, angs4, scale_list=sl, adimsdi="double", ncomp=(2, 3), collapse=collapse,
+                           verbose=False)
+        err = float(np.max(np.abs(fr - ref)) / np.max(np.abs(ref)))
+        print(f"sharded world={world} ADI+mSDI double collapse={collapse}: rel err vs single-GPU pca = {err:.2e}")
+        assert err < 1e-4, err
 dist.barrier()
 dist.destroy_process_group()

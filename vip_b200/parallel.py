@@ -76,6 +76,24 @@ class CudaOps:
     def derotate(self, cube, angles):
         return derotate_device(cube, angles)
 
+    def sdi_stage1(self, cube4d, frames, scale_list, ncomp_ifs, collapse_ifs, device):
+        """Stage 1 of the ADI+mSDI double PCA for the ADI frames ``frames`` of a host (z,n,H,W) cube:
+        only those frames are uploaded.  Returns (len(frames), H, W) fp32."""
+        from ._device import to_device_f32
+        from .psfsub.sdi import RescaleOps, _stage1_frames, _CHUNK_BYTES
+        z, n, H, W = cube4d.shape
+        sub = to_device_f32(np.ascontiguousarray(cube4d[:, frames]), device)      # (z, F, H, W)
+        rops = RescaleOps(scale_list, H, device)
+        per_frame = 4 * z * rops.big * rops.big * 4 * 2
+        chunk = max(1, int(_CHUNK_BYTES // per_frame))
+        parts = [_stage1_frames(sub, list(range(c0, min(len(frames), c0 + chunk))), rops, ncomp_ifs, None, None,
+                                "lapack", collapse_ifs, (0, z)) for c0 in range(0, len(frames), chunk)]
+        return torch.cat(parts)
+
+    def project_subtract_cube(self, cube_dev, ncomp):
+        from .psfsub.pca_fullfr import project_subtract_device
+        return project_subtract_device(cube_dev, ncomp)
+
     def collapse(self, cube2d, mode):
         n, p = cube2d.shape
         return collapse_device(cube2d.reshape(n, 1, p), mode).reshape(p)
@@ -98,6 +116,53 @@ def _all_to_all(send, recv, group):
                                        group=group))
         for r in reqs:
             r.wait()
+
+
+def _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, ops, device):
+    """Tail of the sharded paths: this rank's residual frames ``mine`` (f1-f0, H, W) -> derotation (local) ->
+    temporal collapse across the ranks.  'mean' / 'sum' are reducible (partial sums + one NCCL reduce of an
+    (H,W) frame); the other modes need every frame of a pixel on one rank: all-to-all to pixel shards, local
+    collapse, gather.  Returns (frame on rank 0 / None elsewhere, own derotated frames)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    n = int(fb[-1])
+    p = int(pb[-1])
+    H, W = mine.shape[1], mine.shape[2]
+    p0, p1 = int(pb[rank]), int(pb[rank + 1])
+    f0, f1 = int(fb[rank]), int(fb[rank + 1])
+    der = ops.derotate(mine, -angle_list[f0:f1]) if f1 > f0 else mine
+
+    if collapse in ("mean", "sum"):
+        # ---- reducible collapse: partial sums over the own frames, one NCCL reduce of an (H,W) frame ------
+        # (PCA residuals hold no NaNs -- a NaN in the cube would already have poisoned the Gramian -- so
+        # nanmean == sum / n here; the non-reducible modes take the all-to-all below)
+        part = ops.collapse(der.reshape(f1 - f0, p), "sum") if f1 > f0 else torch.zeros(p, device=device)
+        part = part.to(torch.float32).contiguous()
+        dist.reduce(part, dst=src, op=dist.ReduceOp.SUM, group=group)
+        frame = None
+        if rank == 0:
+            if collapse == "mean":
+                part = part / n
+            frame = part.reshape(H, W).cpu().numpy()
+        return frame, der
+
+    # ---- exchange 2: frame shards -> pixel shards, collapse, gather --------------------------------
+    der2 = der.reshape(f1 - f0, p)
+    send = [der2[:, int(pb[h]):int(pb[h + 1])].contiguous() for h in range(world)]
+    recv = [torch.empty((int(fb[h + 1] - fb[h]), p1 - p0), dtype=der2.dtype, device=device) for h in range(world)]
+    _all_to_all(send, recv, group)
+    slab = ops.collapse(torch.cat(recv, dim=0).contiguous(), collapse)  # (p_g,)
+
+    pmax = int(np.max(np.diff(pb)))
+    padded = torch.zeros(pmax, dtype=slab.dtype, device=device)
+    padded[: p1 - p0] = slab
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)
+    frame = None
+    if rank == 0:
+        frame = torch.cat([gathered[h][: int(pb[h + 1] - pb[h])] for h in range(world)]).reshape(H, W)
+        frame = frame.cpu().numpy()
+    return frame, der
 
 
 def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None, device=None,
@@ -174,40 +239,61 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
     recv = [torch.empty((f1 - f0, int(pb[h + 1] - pb[h])), dtype=R.dtype, device=device) for h in range(world)]
     _all_to_all(send, recv, group)
     mine = torch.cat(recv, dim=1).reshape(f1 - f0, H, W)                # my frames, all pixels
-    der = ops.derotate(mine, -angle_list[f0:f1]) if f1 > f0 else mine
-
-    if collapse in ("mean", "sum"):
-        # ---- reducible collapse: partial sums over the own frames, one NCCL reduce of an (H,W) frame ------
-        # (PCA residuals hold no NaNs -- a NaN in the cube would already have poisoned the Gramian -- so
-        # nanmean == sum / n here; the non-reducible modes take the all-to-all below)
-        part = ops.collapse(der.reshape(f1 - f0, p), "sum") if f1 > f0 else torch.zeros(p, device=device)
-        part = part.to(torch.float32).contiguous()
-        dist.reduce(part, dst=src, op=dist.ReduceOp.SUM, group=group)
-        frame = None
-        if rank == 0:
-            if collapse == "mean":
-                part = part / n
-            frame = part.reshape(H, W).cpu().numpy()
-        if full_output:
-            return frame, der, (f0, f1)
-        return frame
-
-    # ---- exchange 2: frame shards -> pixel shards, collapse, gather --------------------------------
-    der2 = der.reshape(f1 - f0, p)
-    send = [der2[:, int(pb[h]):int(pb[h + 1])].contiguous() for h in range(world)]
-    recv = [torch.empty((int(fb[h + 1] - fb[h]), p1 - p0), dtype=der2.dtype, device=device) for h in range(world)]
-    _all_to_all(send, recv, group)
-    slab = ops.collapse(torch.cat(recv, dim=0).contiguous(), collapse)  # (p_g,)
-
-    pmax = int(np.max(np.diff(pb)))
-    padded = torch.zeros(pmax, dtype=slab.dtype, device=device)
-    padded[: p1 - p0] = slab
-    gathered = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(gathered, padded, group=group)
-    frame = None
-    if rank == 0:
-        frame = torch.cat([gathered[h][: int(pb[h + 1] - pb[h])] for h in range(world)]).reshape(H, W)
-        frame = frame.cpu().numpy()
+    frame, der = _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, ops, device)
     if full_output:
         return frame, der, (f0, f1)
+    return frame
+
+
+def pca_adimsdi_double_sharded(cube, angle_list, scale_list, ncomp, collapse="median", collapse_ifs="mean",
+                               group=None, ops=None, device=None, full_output=False):
+    """ADI+mSDI double-pass PCA of ONE IFS cube (z,n,H,W), sharded BY ADI FRAME over the ranks (BASELINE
+    config 4): ``pca(cube, angs, scale_list=s, adimsdi='double', ncomp=(k_ifs, k_adi))``.
+
+        stage 1 (per ADI frame: rescale the z channels, PCA across them, descale, collapse)    local, own frames
+        all-gather of the stage-1 frames (n x H x W, 78 MB at config 4)                          NCCL
+        stage 2 ADI PCA on the gathered (n, H*W) matrix (300 x 65 536: tiny)                     replicated
+        derotation of the own frames, temporal collapse                          reduce / all-to-all + gather
+
+    Each rank uploads only its own frames of the host cube.  Returns the final frame on rank 0 (None
+    elsewhere); with ``full_output`` also the (n,H,W) stage-1 cube and the own derotated frames."""
+    if cube.ndim != 4:
+        raise TypeError("Input cube is not a 4d array (required with `scale_list`)")
+    if not isinstance(ncomp, tuple) or len(ncomp) != 2:
+        raise TypeError("`ncomp` must be a tuple when a double pass PCA is performed")
+    ops = ops or CudaOps()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    z, n, H, W = cube.shape
+    k_ifs, k_adi = ncomp
+    angle_list = check_pa_vector(np.asarray(angle_list))
+    if angle_list.shape[0] != n:
+        raise ValueError("Angle list vector has wrong length. It must equal the number frames in the cube")
+    scale_list = np.asarray(scale_list)
+    if scale_list.ndim != 1 or scale_list.shape[0] != z:
+        raise ValueError("Scaling factors vector has wrong length")
+    if k_ifs is not None:
+        k_ifs = min(int(k_ifs), z)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if ops.name == "cuda" else torch.device("cpu")
+    fb = shard_bounds(n, world)
+    pb = shard_bounds(H * W, world)
+    f0, f1 = int(fb[rank]), int(fb[rank + 1])
+
+    own = ops.sdi_stage1(cube, list(range(f0, f1)), scale_list, k_ifs, collapse_ifs, device) if f1 > f0 \
+        else torch.zeros((0, H, W), dtype=torch.float32, device=device)
+    fmax = int(np.max(np.diff(fb)))
+    padded = torch.zeros((fmax, H, W), dtype=torch.float32, device=device)
+    padded[: f1 - f0] = own
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)                              # exchange: stage-1 frames
+    res_channels = torch.cat([gathered[h][: int(fb[h + 1] - fb[h])] for h in range(world)])     # (n, H, W)
+
+    if k_adi is None:
+        res2 = res_channels
+    else:
+        res2 = ops.project_subtract_cube(res_channels, min(int(k_adi), n))       # replicated, 300 x 65 536
+    frame, der = _derotate_collapse_frame_shards(res2[f0:f1].contiguous(), angle_list, fb, pb, collapse, group,
+                                                 ops, device)
+    if full_output:
+        return frame, res_channels, der
     return frame
