@@ -1167,6 +1167,76 @@ shear_rows_last_pk(const float* __restrict__ T2, const float* __restrict__ aux, 
     }
 }
 
+// ---- pass 3 (packed), looped: PP consecutive row pairs per CTA; the 32 samples per thread of the NEXT pair are
+// fetched with 4-byte cp.async into thread-private staging slots while the current transform runs (same idea
+// as shear_rows_first_pk_loop: the one-shot kernel opens every CTA with a DRAM round trip).
+template <int N, int NT, int MINB, int PP>
+__global__ void __launch_bounds__(NT * N / 16, MINB)
+shear_rows_last_pk_loop(const float* __restrict__ T2, const float* __restrict__ aux, const float* __restrict__ in,
+                        float* __restrict__ out, RotParams g, const double* __restrict__ a_coef,
+                        const float2* __restrict__ tw, int frame0) {
+    using F = ShearFft<N>;
+    constexpr int T = F::T;
+    extern __shared__ float2 smem2[];
+    __shared__ float2 ph3s[NT][32];
+    const int tr = threadIdx.x / T, t = threadIdx.x % T;
+    const int fl = blockIdx.y, f = frame0 + fl;
+    float2* buf = smem2 + (size_t)tr * 2 * F::BUF;
+    float* stage = reinterpret_cast<float*>(smem2 + (size_t)NT * 2 * F::BUF) + (size_t)tr * 32 * T;   // [h][j][t]
+    const double ac = a_coef[f];
+    const float* corr = aux + (size_t)fl * AuxLayout::stride(N) + AuxLayout::corr(g.S);
+    const float sgn_t = (t & 1) ? -1.f : 1.f;      // (-1)^n' for n' = t + j*T
+
+    auto prefetch = [&](int it) {
+        const int row = 2 * ((blockIdx.x * PP + it) * NT + tr);
+        const bool v = row < g.S;                   // S is even on this path: both rows or none
+        const float* src = T2 + ((size_t)fl * g.S + (v ? row : 0)) * N;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                cp_async4_zfill(stage + (h * 16 + j) * T + t, src + (size_t)h * N + t + j * T, v);
+        cp_async_commit();
+    };
+
+    prefetch(0);
+#pragma unroll 1
+    for (int it = 0; it < PP; ++it) {
+        const int row0 = 2 * (blockIdx.x * PP + it) * NT;
+        if (row0 >= g.S) break;                     // CTA-uniform
+        const int row = row0 + 2 * tr;
+        const bool valid = row < g.S;
+        const int i = g.y0 + row;
+        cp_async_wait_all();
+        float re[16], im[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            re[j] = stage[j * T + t];
+            im[j] = stage[(16 + j) * T + t];
+        }
+        if (it + 1 < PP) prefetch(it + 1);          // own slots only: already consumed above
+        int sa_int, sb_int; float sa_frac, sb_frac;
+        split_shift(ac * (double)(i - N / 2), sa_int, sa_frac);
+        split_shift(ac * (double)(i + 1 - N / 2), sb_int, sb_frac);
+        float nya, nyb;
+        F::template run_pair<false, true>(re, im, buf, buf + F::BUF, ph3s[tr], tw, t, tr, sa_int, sa_frac, sb_int,
+                                          sb_frac, 0.f, 0.f, nya, nyb);
+        if (valid) {
+            const float ca = sgn_t * corr[row], cb = sgn_t * corr[row + 1];
+            const float* src = in + ((size_t)f * g.S + row) * g.S;
+            float* dst = out + ((size_t)f * g.S + row) * g.S;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x = t + j * T;            // < S = 4T
+                dst[x] = is_masked(__ldg(src + x), g) ? g.mask_val : re[j] - ca;
+                dst[g.S + x] = is_masked(__ldg(src + g.S + x), g) ? g.mask_val : im[j] - cb;
+            }
+        }
+        __syncthreads();                            // buf / zbuf / ph3s are reused by the next pair
+    }
+    cp_async_wait_all();
+}
+
 // =====================================================================================
 // Generic path (any even N): direct circular convolution with the Dirichlet kernel
 // =====================================================================================
@@ -1401,7 +1471,8 @@ static int fft_packed() {
     return v;
 }
 
-// pass 1: 1 = looped kernel with cp.async prefetch of the next row pair (default), 0 = one pair per CTA
+// passes 1 / 3: 0 = one row pair per CTA; 1 = looped pass-1 kernel with cp.async prefetch of the next row pair
+// (default); 2 = looped pass 1 and pass 3
 static int fft_rows_loop() {
     static int v = -1;
     if (v < 0) {
@@ -1489,8 +1560,21 @@ static int launch_fft_chunk_pk(const float* in, float* out, float* T1, float* T2
     g_timer.mark(st);
     shear_aux_gamma<<<nf, 256, 0, st>>>(aux, g, a, frame0);
     VB_CHECK_LAUNCH();
-    shear_rows_last_pk<N, NT, MINB><<<dim3(ceil_div(pairs3, NT), nf), threads, smem_rows, st>>>(
-        T2, aux, in, out, g, a, tw, frame0);
+    if (fft_rows_loop() >= 2) {
+        constexpr int PP = 4;
+        const size_t smem_last = smem_rows + (size_t)NT * 32 * F::T * sizeof(float);
+        static bool cfg_last = false;
+        if (!cfg_last) {
+            VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_last_pk_loop<N, NT, MINB, PP>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_last));
+            cfg_last = true;
+        }
+        shear_rows_last_pk_loop<N, NT, MINB, PP><<<dim3(ceil_div(pairs3, NT * PP), nf), threads, smem_last, st>>>(
+            T2, aux, in, out, g, a, tw, frame0);
+    } else {
+        shear_rows_last_pk<N, NT, MINB><<<dim3(ceil_div(pairs3, NT), nf), threads, smem_rows, st>>>(
+            T2, aux, in, out, g, a, tw, frame0);
+    }
     VB_CHECK_LAUNCH();
     g_timer.mark(st);
     return 0;
