@@ -67,6 +67,11 @@ int vb_eigh_f64(const double* G, int n, double* evals, double* evecs, int max_sw
 size_t vb_eigh_topk_workspace_bytes(int n, int k);
 int vb_eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, double* evals, double* evecs,
                      void* ws, size_t ws_bytes, int* info_host, void* stream);
+/* Same solver without the host synchronisation: {iterations, converged} are copied to `info_pinned_host`
+ * (two ints in PINNED host memory, valid until the stream has passed this call) by an async copy on `stream`;
+ * the caller keeps enqueueing dependent work and checks the flag after its own synchronisation. */
+int vb_eigh_topk_async_f64(const double* G, int n, int k, double tol, int max_iter, double* evals, double* evecs,
+                           void* ws, size_t ws_bytes, int* info_pinned_host, void* stream);
 
 /* ---- principal components and projection/subtraction --------------------------------------
  * V[k x p] (fp32) = Wt[k x n] (fp64) . M[n x p] (fp32), accumulated in fp64   psfsub/svd.py:451-459

@@ -310,6 +310,29 @@ def test_decomposition_falls_back_to_jacobi_when_subspace_iteration_stalls():
         np.testing.assert_allclose(dec.evals.cpu().numpy()[:24], w[:24], rtol=1e-9)
 
 
+def test_pca_deferred_convergence_check_falls_back(vb, golden, golden_inputs, monkeypatch):
+    """pca() enqueues its whole pipeline behind the NON-synchronising eigensolver and reads the convergence
+    record once at the end; a record that says 'not converged' must trigger the synchronous redo (Jacobi
+    fallback) and still give the reference's frame."""
+    import torch
+    from vip_b200 import kernels
+    cube, angs = golden_inputs["c1"]
+    calls = {"async": 0}
+    real = kernels.eigh_topk_async
+
+    def stalled(G, k, tol=0.0, max_iter=0):
+        calls["async"] += 1
+        evals, evecs, rec = real(G, k, tol, max_iter)
+        torch.cuda.synchronize()
+        rec[1] = 0                                   # pretend the subspace iteration stalled
+        return evals * 0 + 1.0, torch.zeros_like(evecs), rec      # and produced garbage
+    monkeypatch.setattr(kernels, "eigh_topk_async", stalled)
+    fr = vb.pca(cube, angs, ncomp=5, verbose=False)
+    assert calls["async"] == 1
+    ref = golden["pca_fullframe"]["c1_frame"]
+    assert_parity(fr, ref, lambda: O.pca_fullframe(cube.astype(np.float64), angs, ncomp=5), FRAME_TOL)
+
+
 def test_eigh_topk_flat_spectrum_still_converges():
     """Pure noise (no gap after k): slow linear convergence, but it must still reach the tolerance."""
     import torch

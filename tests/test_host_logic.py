@@ -85,3 +85,17 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_rotation_scalars_vectorised_equals_scalar_form():
+    """Per-frame rot90 count and shear coefficients: the vectorised host code gives the bits of the
+    reference's frame-by-frame expressions (derotation.py:570-603), quirk angles included."""
+    from vip_b200.preproc.derotation import rotation_scalars, _rotation_scalars_loop
+    rng = np.random.default_rng(0)
+    angs = np.concatenate([rng.uniform(-800, 800, 5000),
+                           [0, 45, 90, 135, 180, 225, 270, 315, 360, -45, -90, 44.999999, 45.0000001, 720, -720]])
+    k0, a0, b0 = _rotation_scalars_loop(angs)
+    k1, a1, b1 = rotation_scalars(angs)
+    np.testing.assert_array_equal(k0, k1)
+    np.testing.assert_array_equal(a0, a1)
+    np.testing.assert_array_equal(b0, b1)

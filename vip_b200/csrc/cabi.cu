@@ -28,7 +28,8 @@ int upload_gram_f32(const float*, int, size_t, float*, double*, void*, size_t, i
 size_t eigh_workspace_bytes(int n);
 int eigh_f64(const double*, int, double*, double*, int, double, void*, size_t, int*, int*, cudaStream_t);
 size_t eigh_topk_workspace_bytes(int n, int B);
-int eigh_topk_f64(const double*, int, int, double, int, double*, double*, void*, size_t, int*, int*, cudaStream_t);
+int eigh_topk_f64(const double*, int, int, double, int, double*, double*, void*, size_t, int*, int*, cudaStream_t,
+                  int* async_info = nullptr);
 int pcs_f32(const double*, const float*, int, int, size_t, float*, int*, cudaStream_t);
 int project_subtract_f32(const float*, const float*, int, const float*, int, int, size_t, float*, int*,
                          cudaStream_t);
@@ -138,6 +139,16 @@ int vb_eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, do
     int nl = 0;
     const int rc = eigh_topk_f64(G, n, k, tol, max_iter, evals, evecs, ws, ws_bytes, info_host, &nl,
                                  (cudaStream_t)stream);
+    g_launches += nl;
+    return rc;
+}
+
+int vb_eigh_topk_async_f64(const double* G, int n, int k, double tol, int max_iter, double* evals, double* evecs,
+                           void* ws, size_t ws_bytes, int* info_pinned_host, void* stream) {
+    VB_REQUIRE(info_pinned_host != nullptr, "eigh_topk_async: info_pinned_host is required");
+    int nl = 0;
+    const int rc = eigh_topk_f64(G, n, k, tol, max_iter, evals, evecs, ws, ws_bytes, nullptr, &nl,
+                                 (cudaStream_t)stream, info_pinned_host);
     g_launches += nl;
     return rc;
 }

@@ -808,7 +808,7 @@ size_t eigh_topk_workspace_bytes(int n, int B) {
 
 template <int B>
 static int topk_run(const double* G, int n, int k, double tol, int max_iter, double* evals, double* evecs,
-                    void* ws, int* info, int* launches, cudaStream_t st) {
+                    void* ws, int* info, int* launches, cudaStream_t st, int* async_info) {
     double* X = reinterpret_cast<double*>(ws);
     double* Y = X + (size_t)n * B;
     double* T = Y + (size_t)n * B;
@@ -849,9 +849,15 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
         if (ce == cudaSuccess) {
             topk_output_kernel<B><<<ceil_div(n, 256), 256, 0, st>>>(X, theta, n, k, evals, evecs);
             VB_CHECK_LAUNCH();
+            if (launches) *launches = nl + 2;
+            if (async_info) {
+                // deferred check: {iters, converged} land in the caller's PINNED buffer when the stream gets
+                // there; no host synchronisation, the caller's pipeline keeps running ahead
+                VB_CHECK_CUDA(cudaMemcpyAsync(async_info, state, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+                return 0;
+            }
             VB_CHECK_CUDA(cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, st));
             VB_CHECK_CUDA(cudaStreamSynchronize(st));
-            if (launches) *launches = nl + 2;
             if (info) { info[0] = h.iters; info[1] = h.converged; }
             return 0;
         }
@@ -881,13 +887,14 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
     nl += 1;
     if (launches) *launches = nl;
     if (info) { info[0] = h.iters; info[1] = h.converged; }
+    if (async_info) { async_info[0] = h.iters; async_info[1] = h.converged; }   // this path synchronised anyway
     return 0;
 }
 
 // Leading k eigenpairs of the symmetric PSD matrix G (n x n fp64).  evals[k] descending,
 // evecs[k x n] row j = eigenvector j.  info_host: iterations, converged flag.  Synchronises.
 int eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, double* evals, double* evecs,
-                  void* ws, size_t ws_bytes, int* info, int* launches, cudaStream_t st) {
+                  void* ws, size_t ws_bytes, int* info, int* launches, cudaStream_t st, int* async_info) {
     VB_REQUIRE(n >= 1 && k >= 1 && k <= n, "eigh_topk: need 1 <= k <= n");
     if (tol <= 0) tol = 1e-9;    // residual / lambda_k; eigenvector error ~ tol / relative gap
     if (max_iter <= 0) max_iter = 400;   // beyond this the caller is better off with the Jacobi solver
@@ -895,8 +902,8 @@ int eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, doubl
     VB_REQUIRE(k <= 24, "eigh_topk: k=%d too large for the subspace solver (use the Jacobi solver)", k);
     VB_REQUIRE(n >= B, "eigh_topk: n=%d smaller than the block width %d (use the Jacobi solver)", n, B);
     VB_REQUIRE(ws_bytes >= eigh_topk_workspace_bytes(n, B), "eigh_topk: workspace too small");
-    if (B == 16) return topk_run<16>(G, n, k, tol, max_iter, evals, evecs, ws, info, launches, st);
-    return topk_run<32>(G, n, k, tol, max_iter, evals, evecs, ws, info, launches, st);
+    if (B == 16) return topk_run<16>(G, n, k, tol, max_iter, evals, evecs, ws, info, launches, st, async_info);
+    return topk_run<32>(G, n, k, tol, max_iter, evals, evecs, ws, info, launches, st, async_info);
 }
 
 }  // namespace vb

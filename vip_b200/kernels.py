@@ -82,6 +82,22 @@ def eigh_topk(G, k, tol=0.0, max_iter=0):
     return evals, evecs, {"iters": int(info[0]), "converged": bool(info[1])}
 
 
+def eigh_topk_async(G, k, tol=0.0, max_iter=0):
+    """``eigh_topk`` without the host synchronisation.  Returns (evals, evecs, info) where ``info`` is a pinned
+    int32[2] tensor {iterations, converged} that is valid once the current stream has been synchronised;
+    the workspace is returned inside ``info.ws`` to keep it alive until then."""
+    lib = _cabi.lib()
+    n = G.shape[0]
+    evals = empty((k,), torch.float64, G.device)
+    evecs = empty((k, n), torch.float64, G.device)
+    nb = lib.vb_eigh_topk_workspace_bytes(n, k)
+    ws = _bytes(nb, G.device)
+    info = torch.zeros(2, dtype=torch.int32).pin_memory()
+    _cabi.check(lib.vb_eigh_topk_async_f64(ptr(G), n, int(k), float(tol), int(max_iter), ptr(evals), ptr(evecs),
+                                           ptr(ws), nb, info.data_ptr(), stream_ptr()), "vb_eigh_topk_async_f64")
+    return evals, evecs, info
+
+
 def topk_supported(n, k):
     """The subspace solver handles k <= 24 with a block (16 or 32 vectors) no wider than the matrix."""
     return k <= 24 and n >= (16 if k <= 10 else 32) and n > 2 * k

@@ -38,7 +38,27 @@ def rotation_geometry(size):
 def rotation_scalars(angles):
     """Per-frame (krot, a, b) for rotation angles in degrees (``derotation.py:570-603``): the angle
     is wrapped to [0, 360]; above 45 deg the plane is first rot90'ed ``rint(angle/90)`` times and
-    the residual angle lies in [-45, 45]; a = tan(residual/2), b = -sin(residual)."""
+    the residual angle lies in [-45, 45]; a = tan(residual/2), b = -sin(residual).
+
+    Vectorised over frames with the reference's own fp64 expressions (same ufuncs, so the same bits as
+    the frame-by-frame form ``_rotation_scalars_loop``; tests/test_host_logic.py)."""
+    ang = np.array(angles, dtype=np.float64)
+    while np.any(ang < 0):                       # the reference wraps with repeated +-360, not with fmod
+        ang = np.where(ang < 0, ang + 360, ang)
+    while np.any(ang > 360):
+        ang = np.where(ang > 360, ang - 360, ang)
+    big = ang > 45
+    d = ang % 90
+    d = np.where(d > 45, -(90 - d), d)
+    dangle = np.where(big, d, ang)
+    krot = np.where(big, np.rint(ang / 90).astype(np.int64) % 4, 0).astype(np.int32)
+    a = np.tan(np.deg2rad(dangle) / 2)
+    b = -np.sin(np.deg2rad(dangle))
+    return krot, a, b
+
+
+def _rotation_scalars_loop(angles):
+    """Frame-by-frame statement of :func:`rotation_scalars` (the reference's scalar code path)."""
     angles = np.asarray(angles, dtype=np.float64)
     krot = np.zeros(angles.shape[0], dtype=np.int32)
     a = np.zeros(angles.shape[0], dtype=np.float64)

@@ -112,7 +112,7 @@ def prepare_matrix_device(cube_dev, scaling=None, mask_center_px=None):
 
 def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, svd_mode="lapack",
                             cube_ref_dev=None, cube_sig_dev=None, full_output=False, verbose=False,
-                            random_state=None, gram=None):
+                            random_state=None, gram=None, pending=None):
     """Whole-matrix branch of ``_project_subtract`` (``pca_fullfr.py:1552-1737``) on the device.
 
     Returns residuals (n,H,W) or (residuals, reconstructed (n,p), V (k,p))."""
@@ -151,7 +151,7 @@ def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, 
 
     if svd_mode in _EXACT_MODES:
         if dec is None:
-            dec = Decomposition(ref_lib, ncomp, G=gram if ref_lib is matrix else None)
+            dec = Decomposition(ref_lib, ncomp, G=gram if ref_lib is matrix else None, pending=pending)
         V = dec.pcs(ncomp)
         if ref_lib is matrix_emp:
             Cm = dec.coeffs(ncomp)                # = matrix_emp . V^T from the eigenpairs
@@ -181,7 +181,7 @@ def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, 
 def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_px, svd_mode, collapse,
                         verbose, full_output, weights=None, cube_sig=None, random_state=None,
                         keep_on_device=False, source_xy=None, delta_rot=None, fwhm=4, min_frames_pca=10,
-                        max_frames_pca=None, left_eigv=False, **rot_options):
+                        max_frames_pca=None, left_eigv=False, _defer_check=True, **rot_options):
     """``_adi_rdi_pca`` (``pca_fullfr.py:801-1035``) for scalar ``ncomp`` without ``batch`` /
     ``mask_rdi``: PCA residuals (whole matrix, or frame by frame with a PA-rejection library when
     ``source_xy`` is given) -> derotation -> collapse."""
@@ -228,9 +228,13 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
                 np.min(nfrslib), np.percentile(nfrslib, 10), np.median(nfrslib), np.percentile(nfrslib, 90),
                 np.max(nfrslib)))
     else:
+        # The convergence flag of the subspace eigensolver is checked AFTER the whole pipeline has been
+        # enqueued (one synchronisation at the end instead of a pipeline bubble behind the eigensolver: the
+        # host would otherwise sit idle for 1.6 ms at config 2 and only then start launching the rest)
+        pending = [] if _defer_check else None
         res = project_subtract_device(cube_dev, ncomp, scaling, mask_center_px, svd_mode, ref_dev, sig_dev,
                                       full_output=full_output, verbose=verbose, random_state=random_state,
-                                      gram=gram)
+                                      gram=gram, pending=pending)
         if full_output:
             residuals_cube, recon, V = res
         else:
@@ -241,6 +245,15 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
         mask = torch.as_tensor(circle_mask((y, x), mask_center_px)).to(dev)
         residuals_cube_ = residuals_cube_.masked_fill(mask[None], 0.0)
         frame = frame.masked_fill(mask, 0.0)
+    if source_xy is None and pending:
+        torch.cuda.current_stream().synchronize()
+        if any(int(rec[1]) == 0 for rec in pending):
+            # rare: subspace iteration stalled (flat spectrum) -> redo with the synchronous path, which falls
+            # back to the full Jacobi solver
+            return _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_px, svd_mode,
+                                       collapse, verbose, full_output, weights=weights, cube_sig=cube_sig,
+                                       random_state=random_state, keep_on_device=keep_on_device,
+                                       left_eigv=left_eigv, _defer_check=False, **rot_options)
     if verbose:
         print("Done de-rotating and combining")
     if full_output and source_xy is not None:

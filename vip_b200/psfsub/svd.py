@@ -24,15 +24,25 @@ class Decomposition:
     ``ncomp=None`` -> full spectrum (Jacobi; needed for CEVR); an integer ``ncomp`` small enough for
     the subspace solver -> only the leading pairs (falls back to Jacobi if it does not converge)."""
 
-    def __init__(self, M, ncomp=None, G=None):
+    def __init__(self, M, ncomp=None, G=None, pending=None):
+        """``pending``: a list.  When given and the subspace solver applies, it runs WITHOUT the host
+        synchronisation of its convergence check: the pinned {iterations, converged} record is appended to
+        ``pending`` and the caller, after enqueueing the rest of its pipeline and synchronising once at the
+        end, must verify ``converged`` (and redo the work with ``pending=None`` if it is 0)."""
         self.M = M
         n = M.shape[0]
         if G is None:
             G = kernels.gram(M)
         self.full = True
         if ncomp is not None and kernels.topk_supported(n, ncomp):
-            evals, evecs, self.info = kernels.eigh_topk(G, ncomp)
-            self.full = not self.info["converged"]
+            if pending is not None:
+                evals, evecs, rec = kernels.eigh_topk_async(G, ncomp)
+                pending.append(rec)
+                self.info = {"deferred": True}
+                self.full = False
+            else:
+                evals, evecs, self.info = kernels.eigh_topk(G, ncomp)
+                self.full = not self.info["converged"]
         if self.full:
             evals, evecs, self.info = kernels.eigh(G)
         self.evals = evals                     # descending, fp64 (all n, or the leading ncomp)
