@@ -31,6 +31,17 @@ class NumpyOps:
         return (torch.from_numpy(np.ascontiguousarray(w[::-1][:k])),
                 torch.from_numpy(np.ascontiguousarray(v[:, ::-1][:, :k].T)))
 
+    stall_once = False      # class-level switch for the deferred-convergence-check test
+
+    def leading_eig_async(self, G, k):
+        """Deferred-check variant: record = {iterations, converged}.  With ``stall_once`` the first call
+        reports a stalled solver and returns garbage, as a non-converged subspace iteration would."""
+        evals, evecs = self.leading_eig(G, k)
+        if NumpyOps.stall_once:
+            NumpyOps.stall_once = False
+            return evals, torch.zeros_like(evecs), torch.tensor([400, 0], dtype=torch.int32)
+        return evals, evecs, torch.tensor([7, 1], dtype=torch.int32)
+
     def pcs(self, Wt, M):
         return torch.from_numpy((Wt.numpy() @ M.numpy().astype(np.float64)).astype(np.float32))
 
@@ -85,6 +96,9 @@ def _worker(rank, world, port, collapse, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        # world 3: rank 1 alone sees a stalled eigensolver -> the MIN all-reduce of the convergence records
+        # must send EVERY rank through the synchronous redo (a lone rank re-entering the collectives would hang)
+        NumpyOps.stall_once = (world == 3 and rank == 1)
         cube, angs = adi_cube(11, 20, 3, 70.0, seed=2)     # 11 frames / 400 px: uneven shards
         frame, der, (f0, f1) = pca_sharded(cube, angs, 3, collapse=collapse, ops=NumpyOps(),
                                            device=torch.device("cpu"), full_output=True)

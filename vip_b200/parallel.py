@@ -59,6 +59,13 @@ class CudaOps:
         evals, evecs, _ = kernels.eigh(G)
         return evals[:k].contiguous(), evecs[:k].contiguous()
 
+    def leading_eig_async(self, G, k):
+        """Non-synchronising variant: (evals, evecs, record) with record = pinned int32 {iterations, converged},
+        valid after the stream has been synchronised; None when the subspace solver does not apply."""
+        if not kernels.topk_supported(G.shape[0], k):
+            return None
+        return kernels.eigh_topk_async(G, k)
+
     def pcs(self, Wt, M):
         return kernels.pcs(Wt, M)
 
@@ -166,7 +173,7 @@ def _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, o
 
 
 def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None, device=None,
-                full_output=False, resident_shard=None, svd_mode="lapack", random_state=None):
+                full_output=False, resident_shard=None, svd_mode="lapack", random_state=None, _defer_check=True):
     """Full-frame ADI PCA of ONE cube, sharded over the ranks of ``group``.
 
     ``cube`` (n,H,W) is the host array, visible on every rank (each rank uploads only its pixel
@@ -203,6 +210,7 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
     # ---- pixel-sharded PCA ------------------------------------------------------------------
     M = resident_shard if resident_shard is not None else ops.upload_pixels(cube.reshape(n, p), p0, p1, device)
     src = dist.get_global_rank(group, 0) if group is not None else 0
+    record = None
     mode = str(getattr(svd_mode, "value", svd_mode))
     if mode in ("randsvd", "randcupy", "randpytorch"):
         def reduce(t):                                                   # exchange step 0: sketches
@@ -224,7 +232,13 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
     else:
         G = ops.gram(M)
         dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)           # exchange step 0: n x n fp64
-        evals, evecs = ops.leading_eig(G, ncomp)
+        # the convergence record of the subspace solver is read once, after the whole pipeline has been
+        # enqueued (no host stall behind the eigensolver); see the check before the return
+        deferred = ops.leading_eig_async(G, ncomp) if (_defer_check and hasattr(ops, "leading_eig_async")) else None
+        if deferred is not None:
+            evals, evecs, record = deferred
+        else:
+            evals, evecs = ops.leading_eig(G, ncomp)
         # replicate the eigenpairs bit-identically (atomics make the solver order-dependent at 1e-16)
         dist.broadcast(evals, src=src, group=group)
         dist.broadcast(evecs, src=src, group=group)
@@ -240,6 +254,16 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
     _all_to_all(send, recv, group)
     mine = torch.cat(recv, dim=1).reshape(f1 - f0, H, W)                # my frames, all pixels
     frame, der = _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, ops, device)
+    if record is not None:
+        if device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        ok = torch.tensor([int(record[1])], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)            # one decision for all ranks
+        if int(ok.item()) == 0:
+            # rare: the subspace iteration stalled -> redo with the synchronous solver (Jacobi fallback)
+            return pca_sharded(cube, angle_list, ncomp, collapse=collapse, group=group, ops=ops, device=device,
+                               full_output=full_output, resident_shard=resident_shard, svd_mode=svd_mode,
+                               random_state=random_state, _defer_check=False)
     if full_output:
         return frame, der, (f0, f1)
     return frame
