@@ -346,7 +346,7 @@ def test_eigh_topk_flat_spectrum_still_converges():
     np.testing.assert_allclose(evals.cpu().numpy(), w[:8], rtol=1e-9)
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 33, 130])
+@pytest.mark.parametrize("n", [1, 2, 3, 33, 60, 64, 127, 128, 130])
 def test_eigh_small_and_odd_sizes(n):
     import torch
     from vip_b200 import kernels
@@ -358,6 +358,39 @@ def test_eigh_small_and_odd_sizes(n):
     np.testing.assert_allclose(evals.cpu().numpy(), w, rtol=1e-10, atol=1e-12 * w[0])
     E = evecs.cpu().numpy()
     np.testing.assert_allclose((E * evals.cpu().numpy()[:, None]).T @ E, G, atol=1e-9 * w[0])
+
+
+def test_eigh_small_rank_deficient():
+    """Single-launch solver (n <= 128) on a rank-deficient Gramian: zero eigenvalues come last, the leading
+    eigenvectors span the range."""
+    import torch
+    from vip_b200 import kernels
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(60, 12))
+    G = A @ A.T
+    evals, evecs, info = kernels.eigh(torch.from_numpy(G).cuda())
+    assert info["converged"]
+    w = np.linalg.eigvalsh(G)[::-1]
+    np.testing.assert_allclose(evals.cpu().numpy()[:12], w[:12], rtol=1e-10)
+    assert np.all(np.abs(evals.cpu().numpy()[12:]) < 1e-10 * w[0])
+    E = evecs.cpu().numpy()[:12]
+    np.testing.assert_allclose((E * w[:12, None]).T @ E, G, atol=1e-9 * w[0])
+
+
+@pytest.mark.parametrize("na,nb,p", [(60, 300, 20001), (300, 20, 4099), (5, 7, 1000), (130, 70, 3000),
+                                     (200, 200, 2048), (64, 129, 777), (1, 1, 17), (30, 30, 65536)])
+def test_cross_gram_shapes(na, nb, p):
+    """A B^T in fp64 for every tile layout of the CUDA-core kernel (64- or 128-row tiles, either operand on
+    the skinny side, ragged edges, K not a multiple of the slab)."""
+    import torch
+    from vip_b200 import kernels
+    rng = np.random.default_rng(na * 1000 + nb)
+    A = (rng.normal(size=(na, p)) * 100).astype(np.float32)
+    B = (rng.normal(size=(nb, p)) + 50).astype(np.float32)
+    Cm = kernels.cross_gram(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()).cpu().numpy()
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    assert Cm.shape == (na, nb)
+    assert np.max(np.abs(Cm - ref)) <= 1e-12 * np.max(np.abs(ref))
 
 
 def test_pcs_and_project_subtract_match_numpy():

@@ -109,7 +109,7 @@ int vb_upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, 
 }
 
 size_t vb_cross_gram_workspace_bytes(int na, int nb) {
-    return (size_t)ceil_div(na, 128) * ceil_div(nb, 128) * sizeof(int2) + 256;
+    return (size_t)ceil_div(na, 64) * ceil_div(nb, 64) * sizeof(int2) + 256;   // upper bound: 64- or 128-row tiles
 }
 
 int vb_cross_gram_f32(const float* A, int na, const float* B, int nb, size_t p, double* C, void* ws,

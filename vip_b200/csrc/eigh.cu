@@ -145,6 +145,90 @@ jacobi_sort_kernel(const double* __restrict__ W, int n, const double* __restrict
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = w[i] * inv;
 }
 
+// Whole eigensolver in ONE launch for small matrices (n <= 128; the (ncomp+10)^2 problems of the randomized SVD
+// and its orthonormalisation, small libraries): the matrix lives in shared memory, the 32 warps of a single CTA
+// take the disjoint column pairs of a round, and sweeps repeat in-kernel until one applies no rotation.  The
+// per-round launches of the block kernel above cost ~450 launches (4 ms) for a 60 x 60 matrix -- 12 % of a
+// config-5 step (profiles/r01m_launches_c5.md).  Same rotations, same stopping rule, then norms / ranks / output.
+__global__ void __launch_bounds__(1024, 1)
+jacobi_small_kernel(const double* __restrict__ G, int n, int max_sweeps, double tol, double* __restrict__ evals,
+                    double* __restrict__ evecs, JacobiState* __restrict__ state) {
+    extern __shared__ double cols[];            // [n][n]: column c at cols + c*n (G is symmetric)
+    __shared__ double norms[128];
+    __shared__ unsigned int nrot_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int e = tid; e < n * n; e += blockDim.x) cols[e] = G[e];
+    const int m = (n + 1) & ~1;                 // players of the tournament; an odd n gets one idle slot
+    if (tid == 0) nrot_s = 0;
+    __syncthreads();
+    unsigned int sweeps = 0, conv = (n < 2) ? 1u : 0u;
+    for (int sweep = 0; sweep < max_sweeps && !conv; ++sweep) {
+        unsigned int nrot = 0;
+        for (int r = 0; r < m - 1; ++r) {
+            for (int pr = warp; pr < m / 2; pr += nwarps) {
+                int ca, cb;
+                rr_pair(m, r, pr, ca, cb);
+                if (ca < n && cb < n) {
+                    double* x = cols + (size_t)ca * n;
+                    double* y = cols + (size_t)cb * n;
+                    double alpha = 0.0, beta = 0.0, gamma = 0.0;
+                    for (int i = lane; i < n; i += 32) {
+                        const double xv = x[i], yv = y[i];
+                        alpha = fma(xv, xv, alpha); beta = fma(yv, yv, beta); gamma = fma(xv, yv, gamma);
+                    }
+                    alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
+                    if (alpha > 0.0 && beta > 0.0 && fabs(gamma) > tol * sqrt(alpha) * sqrt(beta)) {
+                        const double zeta = (beta - alpha) / (2.0 * gamma);
+                        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        const double c = 1.0 / sqrt(1.0 + t * t);
+                        const double s = c * t;
+                        for (int j = lane; j < n; j += 32) {
+                            const double xv = x[j], yv = y[j];
+                            x[j] = c * xv - s * yv;
+                            y[j] = s * xv + c * yv;
+                        }
+                        ++nrot;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (lane == 0 && nrot) atomicAdd(&nrot_s, nrot);
+        __syncthreads();
+        const unsigned int any = nrot_s;
+        __syncthreads();
+        if (tid == 0) nrot_s = 0;
+        ++sweeps;
+        if (!any) conv = 1;
+    }
+    __syncthreads();
+    for (int c = warp; c < n; c += nwarps) {
+        double sq = 0.0;
+        for (int i = lane; i < n; i += 32) sq = fma(cols[(size_t)c * n + i], cols[(size_t)c * n + i], sq);
+        sq = warp_sum(sq);
+        if (lane == 0) norms[c] = sqrt(sq);
+    }
+    __syncthreads();
+    for (int j = warp; j < n; j += nwarps) {
+        const double lj = norms[j];
+        int cnt = 0;
+        for (int i = lane; i < n; i += 32) {
+            const double li = norms[i];
+            cnt += (li > lj || (li == lj && i < j)) ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) evals[cnt] = lj;
+        const double inv = lj > 0.0 ? 1.0 / lj : 0.0;
+        for (int i = lane; i < n; i += 32) evecs[(size_t)cnt * n + i] = cols[(size_t)j * n + i] * inv;
+    }
+    if (tid == 0) {
+        state->sweeps = sweeps;
+        state->converged = conv;
+        state->rotations = 0;
+    }
+}
+
 size_t eigh_workspace_bytes(int n) {
     return (size_t)n * n * sizeof(double) + (size_t)n * sizeof(double) + 256;
 }
@@ -196,6 +280,29 @@ int eigh_f64(const double* G, int n, double* evals, double* evecs, int max_sweep
     VB_CHECK_CUDA(cudaMemcpyAsync(W, G, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     VB_CHECK_CUDA(cudaMemsetAsync(state, 0, sizeof(JacobiState), st));
     int nl = 0;
+    static const int use_small = [] { const char* e = getenv("VIP_B200_JACOBI_SMALL"); return e ? atoi(e) : 1; }();
+    if (use_small && n <= 128) {
+        // single-CTA solver: reads G directly, writes evals/evecs, records {sweeps, converged} in `state`
+        const size_t smem = (size_t)n * n * sizeof(double);
+        static bool attr = false;
+        if (!attr) {
+            VB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               128 * 128 * (int)sizeof(double)));
+            attr = true;
+        }
+        const int threads = (n <= 32) ? 512 : 1024;
+        jacobi_small_kernel<<<1, threads, smem, st>>>(G, n, max_sweeps, tol, evals, evecs, state);
+        VB_CHECK_LAUNCH();
+        if (launches) *launches = 1;
+        if (info) {
+            JacobiState h;
+            VB_CHECK_CUDA(cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, st));
+            VB_CHECK_CUDA(cudaStreamSynchronize(st));
+            info[0] = (int)h.sweeps;
+            info[1] = (int)h.converged;
+        }
+        return 0;
+    }
     if (n > 1) {
         int rc;
         // wider blocks = fewer launches; narrower = more CTAs per round and less shared memory

@@ -10,6 +10,7 @@
 // Optional mean deflation (M = 1 m^T + D, G = D D^T + rank-2 terms in fp64) is kept for
 // callers that want it; it is not needed for accuracy any more.
 #include "common.cuh"
+#include <cstdlib>
 #include <vector>
 
 namespace vb {
@@ -107,6 +108,145 @@ gram_tile_kernel(const float* __restrict__ A, const float* __restrict__ B, int n
             if (c < nb) atomicAdd(C + (size_t)r * ldc + c, acc[i][j]);
         }
     }
+}
+
+// Second-generation tile kernel (default; VIP_B200_GRAM_V1=1 selects the kernel above).
+// The first kernel keeps fp32 operands in shared memory and widens them in every thread that uses them: 16
+// F2F.F64.F32 per 64 DFMA per k-step, and on B200 the conversion pipe is as narrow as the fp64 pipe -- the ncu
+// launch list of the config-5 slice (profiles/r01m_launches_c5.md) shows it at 31 % of the DFMA peak.  Here every
+// operand is widened ONCE, when it is stored to shared memory (16 conversions per thread per 16-deep slab), and
+// the inner loop is LDS.128 + DFMA only.  The B micro-tile is interleaved (column pairs tx*2 + 32 h) so that the
+// sixteen 16-byte reads of a half warp are contiguous (no bank conflicts); the A micro-tile is a broadcast.
+// TA = rows of the A tile: 128 for square Gramian tiles, 64 for skinny products (the (ncomp+10) x n sketches of
+// the randomized SVD and the n x ncomp projection coefficients, which would waste half of a 128-row tile).
+// trans = 1 writes C^T (used to put the skinny operand on the A side whichever argument it is).
+template <int TA>
+__global__ void __launch_bounds__(256, (TA == 64) ? 2 : 1)
+gram_tile2_kernel(const float* __restrict__ A, const float* __restrict__ B, int na, int nb, size_t p,
+                  size_t ld, const float* __restrict__ mean, double* __restrict__ C, int ldc, int trans,
+                  const int2* __restrict__ tiles, int kchunk) {
+    constexpr int MI = TA / 16;                 // micro-tile rows per thread
+    constexpr int LDA = TA + 2, LDB = GT + 2;   // even pitches keep the 16-byte alignment of the double2 reads
+    extern __shared__ __align__(16) double gsm[];
+    double* As = gsm;                           // [2][GK][LDA]
+    double* Bs = gsm + 2 * GK * LDA;            // [2][GK][LDB]
+    const int2 tile = tiles[blockIdx.x];
+    const int row0 = tile.x * TA, col0 = tile.y * GT;
+    const size_t k0 = (size_t)blockIdx.y * kchunk;
+    const size_t k1 = (k0 + kchunk < p) ? k0 + kchunk : p;
+    const int tid = threadIdx.x;
+    const int lk = tid & 15, lr = tid >> 4;     // loader: k offset, first row
+    const int ty = tid >> 4, tx = tid & 15;     // compute: rows ty*MI.., column pairs tx*2 + 32 h
+
+    double acc[MI][8];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+
+    float ra[MI], rb[8];
+    auto gload = [&](size_t kk) {
+        const size_t k = kk + lk;
+        const bool kin = k < k1;
+        const float m = (mean != nullptr && kin) ? __ldg(mean + k) : 0.f;
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const int r = lr + 16 * i;
+            ra[i] = (kin && row0 + r < na) ? __ldg(A + (size_t)(row0 + r) * ld + k) - m : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = lr + 16 * i;
+            rb[i] = (kin && col0 + r < nb) ? __ldg(B + (size_t)(col0 + r) * ld + k) - m : 0.f;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < MI; ++i) As[(buf * GK + lk) * LDA + lr + 16 * i] = (double)ra[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Bs[(buf * GK + lk) * LDB + lr + 16 * i] = (double)rb[i];
+    };
+
+    gload(k0);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (size_t kk = k0; kk < k1; kk += GK) {
+        const bool more = kk + GK < k1;
+        if (more) gload(kk + GK);
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            const double* arow = As + (buf * GK + k) * LDA + ty * MI;
+            const double* brow = Bs + (buf * GK + k) * LDB + tx * 2;
+            double av[MI], bv[8];
+#pragma unroll
+            for (int h = 0; h < MI / 2; ++h) {
+                const double2 a2 = *reinterpret_cast<const double2*>(arow + 2 * h);
+                av[2 * h] = a2.x; av[2 * h + 1] = a2.y;
+            }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const double2 b2 = *reinterpret_cast<const double2*>(brow + 32 * h);
+                bv[2 * h] = b2.x; bv[2 * h + 1] = b2.y;
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+        if (more) {
+            sstore(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int r = row0 + ty * MI + i;
+        if (r >= na) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = col0 + (j >> 1) * 32 + tx * 2 + (j & 1);
+            if (c < nb) atomicAdd(trans ? C + (size_t)c * ldc + r : C + (size_t)r * ldc + c, acc[i][j]);
+        }
+    }
+}
+
+template <int TA>
+static size_t gram_tile2_smem() { return (size_t)2 * GK * ((TA + 2) + (GT + 2)) * sizeof(double); }
+
+static bool gram_use_v1() {
+    static const int v1 = [] { const char* e = getenv("VIP_B200_GRAM_V1"); return (e && atoi(e)) ? 1 : 0; }();
+    return v1 != 0;
+}
+
+// one launch of the tile kernel (ta = 128 or 64 rows per A tile; tiles were listed for that height)
+static int launch_gram_tiles(int ta, const float* A, const float* B, int na, int nb, size_t p, size_t ld,
+                             const float* mean, double* C, int ldc, int trans, const int2* tiles, int ntiles,
+                             unsigned nchunks, int kchunk, cudaStream_t st) {
+    if (ta == 128 && !trans && gram_use_v1()) {
+        gram_tile_kernel<<<dim3(ntiles, nchunks), 256, 0, st>>>(A, B, na, nb, p, ld, mean, C, ldc, tiles, kchunk);
+    } else if (ta == 128) {
+        static bool attr = false;
+        if (!attr) {
+            VB_CHECK_CUDA(cudaFuncSetAttribute(gram_tile2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)gram_tile2_smem<128>()));
+            attr = true;
+        }
+        gram_tile2_kernel<128><<<dim3(ntiles, nchunks), 256, gram_tile2_smem<128>(), st>>>(
+            A, B, na, nb, p, ld, mean, C, ldc, trans, tiles, kchunk);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            VB_CHECK_CUDA(cudaFuncSetAttribute(gram_tile2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)gram_tile2_smem<64>()));
+            attr = true;
+        }
+        gram_tile2_kernel<64><<<dim3(ntiles, nchunks), 256, gram_tile2_smem<64>(), st>>>(
+            A, B, na, nb, p, ld, mean, C, ldc, trans, tiles, kchunk);
+    }
+    VB_CHECK_LAUNCH();
+    return 0;
 }
 
 // Dm[i] = sum_k (A[i,k] - m[k]) m[k]   (blocks 0..n-1),   mm = sum_k m[k]^2  (block n)
@@ -233,9 +373,8 @@ int gram_f32(const float* A, int n, size_t p, int deflate, double* G, void* ws, 
     }
     const unsigned nchunks = (unsigned)ceil_div(p, (size_t)kchunk);
     VB_REQUIRE(nchunks <= 65535, "gram: too many K chunks");
-    gram_tile_kernel<<<dim3(ntiles, nchunks), 256, 0, st>>>(A, A, n, n, p, p, deflate ? mean : nullptr, Gd, n,
-                                                            tiles, kchunk);
-    VB_CHECK_LAUNCH();
+    if (int rc = launch_gram_tiles(128, A, A, n, n, p, p, deflate ? mean : nullptr, Gd, n, 0, tiles, ntiles, nchunks,
+                                   kchunk, st)) return rc;
     gram_assemble_kernel<<<dim3(ceil_div(n, 128), n), 128, 0, st>>>(Gd, n, deflate ? Dm : nullptr, mm, G);
     VB_CHECK_LAUNCH();
     nl += 2;
@@ -307,9 +446,8 @@ int upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, voi
         VB_CHECK_CUDA(cudaStreamWaitEvent(st, ev[s], 0));
         const int kchunk = 1024;
         const unsigned nchunks = (unsigned)ceil_div(c1 - c0, (size_t)kchunk);
-        gram_tile_kernel<<<dim3(ntiles, nchunks), 256, 0, st>>>(M + c0, M + c0, n, n, c1 - c0, p, nullptr, Gd, n,
-                                                                tiles, kchunk);
-        VB_CHECK_LAUNCH();
+        if (int rc = launch_gram_tiles(128, M + c0, M + c0, n, n, c1 - c0, p, nullptr, Gd, n, 0, tiles, ntiles,
+                                       nchunks, kchunk, st)) return rc;
         ++nl;
     }
     gram_assemble_kernel<<<dim3(ceil_div(n, 128), n), 128, 0, st>>>(Gd, n, nullptr, nullptr, G);
@@ -318,26 +456,48 @@ int upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, voi
     return 0;
 }
 
-// C (na x nb fp64, row-major, overwritten) = A B^T
+// C (na x nb fp64, row-major, overwritten) = A B^T.  The operand with the fewer padded rows goes on the A side of
+// the tile kernel (64-row tiles when that saves work): sketches (l x n), coefficients (n x k).
 int cross_gram_f32(const float* A, int na, const float* B, int nb, size_t p, double* C, void* ws,
                    size_t ws_bytes, int kchunk, cudaStream_t st) {
-    const int nta = ceil_div(na, GT), ntb = ceil_div(nb, GT);
+    VB_REQUIRE(na > 0 && nb > 0 && p > 0, "cross_gram: empty problem");
+    auto padded = [](int rows, int t) { return ceil_div(rows, t) * t; };
+    // candidate layouts: (A side, tile height); cost = padded rows of A side x padded (128) rows of the B side
+    int trans = 0, ta = 128;
+    if (!gram_use_v1()) {
+        long long best = (long long)padded(na, 128) * padded(nb, 128);
+        const long long c64 = (long long)padded(na, 64) * padded(nb, 128);
+        const long long t64 = (long long)padded(nb, 64) * padded(na, 128);
+        if (c64 < best) { best = c64; ta = 64; trans = 0; }
+        if (t64 < best) { best = t64; ta = 64; trans = 1; }
+    }
+    const float* Pa = trans ? B : A;
+    const float* Pb = trans ? A : B;
+    const int ra = trans ? nb : na, rb = trans ? na : nb;
+    const int nta = ceil_div(ra, ta), ntb = ceil_div(rb, GT);
     VB_REQUIRE((size_t)nta * ntb <= 65535, "cross_gram: too many tiles");
     VB_REQUIRE(ws_bytes >= (size_t)nta * ntb * sizeof(int2), "cross_gram: workspace too small");
-    if (kchunk <= 0) kchunk = 4096;
-    kchunk = ceil_div(kchunk, GK) * GK;
     std::vector<int2> htiles;
     for (int i = 0; i < nta; ++i)
         for (int j = 0; j < ntb; ++j) htiles.push_back(make_int2(i, j));
     const int ntiles = (int)htiles.size();
+    if (kchunk <= 0) {
+        // fill whole waves of the resident CTA slots (2 per SM for 64-row tiles, 1 otherwise) with ~4096-deep chunks
+        const int slots = kNumSMs * ((ta == 64) ? 2 : 1);
+        const long long want = (long long)ntiles * (long long)ceil_div(p, (size_t)4096);
+        const long long waves = (want + slots - 1) / slots;
+        long long nch = (waves * slots) / ntiles;
+        if (nch < 1) nch = 1;
+        if (nch > 65535) nch = 65535;
+        kchunk = (int)ceil_div(p, (size_t)nch);
+    }
+    kchunk = ceil_div(kchunk, GK) * GK;
     int2* tiles = reinterpret_cast<int2*>(ws);
     VB_CHECK_CUDA(cudaMemcpyAsync(tiles, htiles.data(), ntiles * sizeof(int2), cudaMemcpyHostToDevice, st));
     VB_CHECK_CUDA(cudaMemsetAsync(C, 0, (size_t)na * nb * sizeof(double), st));
     const unsigned nchunks = (unsigned)ceil_div(p, (size_t)kchunk);
     VB_REQUIRE(nchunks <= 65535, "cross_gram: too many K chunks");
-    gram_tile_kernel<<<dim3(ntiles, nchunks), 256, 0, st>>>(A, B, na, nb, p, p, nullptr, C, nb, tiles, kchunk);
-    VB_CHECK_LAUNCH();
-    return 0;
+    return launch_gram_tiles(ta, Pa, Pb, ra, rb, p, p, nullptr, C, nb, trans, tiles, ntiles, nchunks, kchunk, st);
 }
 
 }  // namespace vb

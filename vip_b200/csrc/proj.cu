@@ -10,6 +10,7 @@
 // pixel axis: one thread owns one pixel column and keeps KC accumulators in registers, the
 // small coefficient matrix sits in shared memory and is read by warp-wide broadcasts.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace vb {
 
@@ -21,21 +22,29 @@ constexpr int PT = 256;       // threads (= pixels) per CTA
 // Coefficients and accumulation are fp64: Wt = diag(1/sigma) E_k^T has rows that nearly annihilate the
 // (huge) stellar halo, and the reference's V is an fp64 LAPACK result rounded once to fp32.  Rounding Wt
 // to fp32 first was measured to cost 3e-4 of final-frame parity in RDI/ARDI (tests).
-template <int KC>
-__global__ void __launch_bounds__(PT)
+// PX = pixels per thread.  With one pixel per thread every DFMA pair needs its own 16-byte broadcast read of the
+// coefficients (16 LDS.128 per 32 DFMA at KC = 32): the shared-memory pipe is as loaded as the fp64 pipe and the
+// kernel sat at 34 % of the DFMA rate (ncu launch list of the config-5 slice).  Two adjacent pixels per thread
+// (one float2 load per frame) share each coefficient read; the per-pixel summation order is unchanged, so the
+// result is bit-identical to PX = 1.
+template <int KC, int PX>
+__global__ void __launch_bounds__(PT / PX)
 pcs_kernel(const double* __restrict__ Wt, const float* __restrict__ M, int n, size_t p, int k0, int kc,
            float* __restrict__ V) {
     constexpr int WROWS = 128;
+    constexpr int NT = PT / PX;
     __shared__ __align__(16) double Ws[WROWS][KC];
-    const size_t j = (size_t)blockIdx.x * PT + threadIdx.x;
-    const bool jin = j < p;
-    double acc[KC];
+    const size_t j = ((size_t)blockIdx.x * NT + threadIdx.x) * PX;
+    const bool jin = j < p;                      // PX = 2 is only launched for even p: j + 1 < p as well
+    double acc[PX][KC];
 #pragma unroll
-    for (int q = 0; q < KC; ++q) acc[q] = 0.0;
+    for (int x = 0; x < PX; ++x)
+#pragma unroll
+        for (int q = 0; q < KC; ++q) acc[x][q] = 0.0;
     for (int i0 = 0; i0 < n; i0 += WROWS) {
         const int ni = (n - i0 < WROWS) ? n - i0 : WROWS;
         __syncthreads();
-        for (int idx = threadIdx.x; idx < ni * KC; idx += PT) {
+        for (int idx = threadIdx.x; idx < ni * KC; idx += NT) {
             const int i = idx / KC, q = idx % KC;
             Ws[i][q] = (q < kc) ? Wt[(size_t)(k0 + q) * n + i0 + i] : 0.0;
         }
@@ -44,18 +53,32 @@ pcs_kernel(const double* __restrict__ Wt, const float* __restrict__ M, int n, si
             // 8 independent loads in flight per thread (the kernel is latency/MLP-bound otherwise)
             const float* src = M + (size_t)i0 * p + j;
             for (int ib = 0; ib < ni; ib += 8) {
-                float mv[8];
+                float mv[8][PX];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) mv[u] = (ib + u < ni) ? __ldg(src + (size_t)(ib + u) * p) : 0.f;
+                for (int u = 0; u < 8; ++u) {
+                    if (PX == 2) {
+                        const float2 t = (ib + u < ni)
+                            ? __ldg(reinterpret_cast<const float2*>(src + (size_t)(ib + u) * p)) : make_float2(0.f, 0.f);
+                        mv[u][0] = t.x;
+                        mv[u][PX - 1] = t.y;
+                    } else {
+                        mv[u][0] = (ib + u < ni) ? __ldg(src + (size_t)(ib + u) * p) : 0.f;
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     if (ib + u < ni) {
-                        const double m = (double)mv[u];
+                        double m[PX];
+#pragma unroll
+                        for (int x = 0; x < PX; ++x) m[x] = (double)mv[u][x];
 #pragma unroll
                         for (int q2 = 0; q2 < KC; q2 += 2) {
                             const double2 w = *reinterpret_cast<const double2*>(&Ws[ib + u][q2]);
-                            acc[q2 + 0] = fma(w.x, m, acc[q2 + 0]);
-                            acc[q2 + 1] = fma(w.y, m, acc[q2 + 1]);
+#pragma unroll
+                            for (int x = 0; x < PX; ++x) {
+                                acc[x][q2 + 0] = fma(w.x, m[x], acc[x][q2 + 0]);
+                                acc[x][q2 + 1] = fma(w.y, m[x], acc[x][q2 + 1]);
+                            }
                         }
                     }
                 }
@@ -64,26 +87,45 @@ pcs_kernel(const double* __restrict__ Wt, const float* __restrict__ M, int n, si
     }
     if (jin) {
 #pragma unroll
-        for (int q = 0; q < KC; ++q)
-            if (q < kc) V[(size_t)(k0 + q) * p + j] = (float)acc[q];
+        for (int q = 0; q < KC; ++q) {
+            if (q < kc) {
+                if (PX == 2)
+                    *reinterpret_cast<float2*>(V + (size_t)(k0 + q) * p + j) =
+                        make_float2((float)acc[0][q], (float)acc[PX - 1][q]);
+                else
+                    V[(size_t)(k0 + q) * p + j] = (float)acc[0][q];
+            }
+        }
     }
 }
 
 // R[i][j] = Src[i][j] - sum_{kk in [k0,k0+kc)} C[i][kk] * V[kk][j]
-template <int KC>
-__global__ void __launch_bounds__(PT)
+// PX = 2: two adjacent pixels per thread (float2 loads and stores): twice the bytes in flight per thread for this
+// HBM-bound pass (2.8 TB/s with one pixel per thread), same arithmetic per pixel (bit-identical).
+template <int KC, int PX>
+__global__ void __launch_bounds__(PT / PX)
 subtract_kernel(const float* Src, const float* __restrict__ C, int ldc, const float* __restrict__ V,
                 int n, size_t p, int k0, int kc, float* R) {  // Src may alias R
+    constexpr int NT = PT / PX;
     __shared__ __align__(16) float Cs[ROWS][KC];
-    const size_t j = (size_t)blockIdx.x * PT + threadIdx.x;
+    const size_t j = ((size_t)blockIdx.x * NT + threadIdx.x) * PX;
     const bool jin = j < p;
-    float v[KC];
+    float v[PX][KC];
 #pragma unroll
-    for (int q = 0; q < KC; ++q) v[q] = (jin && q < kc) ? V[(size_t)(k0 + q) * p + j] : 0.f;
+    for (int q = 0; q < KC; ++q) {
+        if (PX == 2) {
+            const float2 t = (jin && q < kc) ? *reinterpret_cast<const float2*>(V + (size_t)(k0 + q) * p + j)
+                                             : make_float2(0.f, 0.f);
+            v[0][q] = t.x;
+            v[PX - 1][q] = t.y;
+        } else {
+            v[0][q] = (jin && q < kc) ? V[(size_t)(k0 + q) * p + j] : 0.f;
+        }
+    }
     for (int i0 = 0; i0 < n; i0 += ROWS) {
         const int ni = (n - i0 < ROWS) ? n - i0 : ROWS;
         __syncthreads();
-        for (int idx = threadIdx.x; idx < ni * KC; idx += PT) {
+        for (int idx = threadIdx.x; idx < ni * KC; idx += NT) {
             const int i = idx / KC, q = idx % KC;
             Cs[i][q] = (q < kc) ? C[(size_t)(i0 + i) * ldc + k0 + q] : 0.f;
         }
@@ -93,22 +135,43 @@ subtract_kernel(const float* Src, const float* __restrict__ C, int ldc, const fl
             const float* src = Src + (size_t)i0 * p + j;
             float* dst = R + (size_t)i0 * p + j;
             for (int ib = 0; ib < ni; ib += 8) {
-                float mv[8];
+                float mv[8][PX];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) mv[u] = (ib + u < ni) ? src[(size_t)(ib + u) * p] : 0.f;
+                for (int u = 0; u < 8; ++u) {
+                    if (PX == 2) {
+                        const float2 t = (ib + u < ni) ? *reinterpret_cast<const float2*>(src + (size_t)(ib + u) * p)
+                                                       : make_float2(0.f, 0.f);
+                        mv[u][0] = t.x;
+                        mv[u][PX - 1] = t.y;
+                    } else {
+                        mv[u][0] = (ib + u < ni) ? src[(size_t)(ib + u) * p] : 0.f;
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     if (ib + u < ni) {
-                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                        float s[PX][4];
+#pragma unroll
+                        for (int x = 0; x < PX; ++x) s[x][0] = s[x][1] = s[x][2] = s[x][3] = 0.f;
 #pragma unroll
                         for (int q4 = 0; q4 < KC; q4 += 4) {
                             const float4 c = *reinterpret_cast<const float4*>(&Cs[ib + u][q4]);
-                            s0 = fmaf(c.x, v[q4 + 0], s0);
-                            s1 = fmaf(c.y, v[q4 + 1], s1);
-                            s2 = fmaf(c.z, v[q4 + 2], s2);
-                            s3 = fmaf(c.w, v[q4 + 3], s3);
+#pragma unroll
+                            for (int x = 0; x < PX; ++x) {
+                                s[x][0] = fmaf(c.x, v[x][q4 + 0], s[x][0]);
+                                s[x][1] = fmaf(c.y, v[x][q4 + 1], s[x][1]);
+                                s[x][2] = fmaf(c.z, v[x][q4 + 2], s[x][2]);
+                                s[x][3] = fmaf(c.w, v[x][q4 + 3], s[x][3]);
+                            }
                         }
-                        dst[(size_t)(ib + u) * p] = mv[u] - ((s0 + s1) + (s2 + s3));
+                        const float r0 = mv[u][0] - ((s[0][0] + s[0][1]) + (s[0][2] + s[0][3]));
+                        if (PX == 2) {
+                            const float r1 = mv[u][PX - 1] -
+                                             ((s[PX - 1][0] + s[PX - 1][1]) + (s[PX - 1][2] + s[PX - 1][3]));
+                            *reinterpret_cast<float2*>(dst + (size_t)(ib + u) * p) = make_float2(r0, r1);
+                        } else {
+                            dst[(size_t)(ib + u) * p] = r0;
+                        }
                     }
                 }
             }
@@ -126,15 +189,24 @@ __global__ void sub_kernel(const float* __restrict__ a, const float* __restrict_
 // V (k x p, fp32) = Wt (k x n, row-major, fp64) . M (n x p, fp32), fp64 accumulation
 int pcs_f32(const double* Wt, const float* M, int k, int n, size_t p, float* V, int* launches, cudaStream_t st) {
     VB_REQUIRE(k > 0 && n > 0 && p > 0, "pcs: empty problem");
-    const unsigned grid = (unsigned)ceil_div(p, (size_t)PT);
+    static const int px_env = [] { const char* e = getenv("VIP_B200_PCS_PX"); return e ? atoi(e) : 2; }();
+    const bool two = px_env == 2 && (p % 2 == 0) && (reinterpret_cast<uintptr_t>(M) % 8 == 0) &&
+                     (reinterpret_cast<uintptr_t>(V) % 8 == 0);
+    const unsigned grid = (unsigned)ceil_div(p, (size_t)PT);      // PT pixels per CTA for both variants
     int nl = 0;
     for (int k0 = 0; k0 < k; k0 += KCMAX) {
         const int kc = (k - k0 < KCMAX) ? k - k0 : KCMAX;
-        if (kc <= 8)       pcs_kernel<8><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V);
-        else if (kc <= 16) pcs_kernel<16><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V);
-        else if (kc <= 20) pcs_kernel<20><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V);
-        else if (kc <= 24) pcs_kernel<24><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V);
-        else               pcs_kernel<32><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V);
+#define VB_PCS_LAUNCH(KCV)                                                                           \
+        do {                                                                                         \
+            if (two) pcs_kernel<KCV, 2><<<grid, PT / 2, 0, st>>>(Wt, M, n, p, k0, kc, V);            \
+            else     pcs_kernel<KCV, 1><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V);                \
+        } while (0)
+        if (kc <= 8)       VB_PCS_LAUNCH(8);
+        else if (kc <= 16) VB_PCS_LAUNCH(16);
+        else if (kc <= 20) VB_PCS_LAUNCH(20);
+        else if (kc <= 24) VB_PCS_LAUNCH(24);
+        else               VB_PCS_LAUNCH(32);
+#undef VB_PCS_LAUNCH
         VB_CHECK_LAUNCH();
         ++nl;
     }
@@ -146,16 +218,25 @@ int pcs_f32(const double* Wt, const float* M, int k, int n, size_t p, float* V, 
 int project_subtract_f32(const float* M, const float* C, int ldc, const float* V, int k, int n, size_t p,
                          float* R, int* launches, cudaStream_t st) {
     VB_REQUIRE(k > 0 && n > 0 && p > 0, "project_subtract: empty problem");
-    const unsigned grid = (unsigned)ceil_div(p, (size_t)PT);
+    static const int px_env = [] { const char* e = getenv("VIP_B200_SUB_PX"); return e ? atoi(e) : 2; }();
+    const bool two = px_env == 2 && (p % 2 == 0) && (reinterpret_cast<uintptr_t>(M) % 8 == 0) &&
+                     (reinterpret_cast<uintptr_t>(V) % 8 == 0) && (reinterpret_cast<uintptr_t>(R) % 8 == 0);
+    const unsigned grid = (unsigned)ceil_div(p, (size_t)PT);      // PT pixels per CTA for both variants
     int nl = 0;
     for (int k0 = 0; k0 < k; k0 += KCMAX) {
         const int kc = (k - k0 < KCMAX) ? k - k0 : KCMAX;
         const float* src = (k0 == 0) ? M : R;
-        if (kc <= 8)       subtract_kernel<8><<<grid, PT, 0, st>>>(src, C, ldc, V, n, p, k0, kc, R);
-        else if (kc <= 16) subtract_kernel<16><<<grid, PT, 0, st>>>(src, C, ldc, V, n, p, k0, kc, R);
-        else if (kc <= 20) subtract_kernel<20><<<grid, PT, 0, st>>>(src, C, ldc, V, n, p, k0, kc, R);
-        else if (kc <= 24) subtract_kernel<24><<<grid, PT, 0, st>>>(src, C, ldc, V, n, p, k0, kc, R);
-        else               subtract_kernel<32><<<grid, PT, 0, st>>>(src, C, ldc, V, n, p, k0, kc, R);
+#define VB_SUB_LAUNCH(KCV)                                                                                   \
+        do {                                                                                                 \
+            if (two) subtract_kernel<KCV, 2><<<grid, PT / 2, 0, st>>>(src, C, ldc, V, n, p, k0, kc, R);      \
+            else     subtract_kernel<KCV, 1><<<grid, PT, 0, st>>>(src, C, ldc, V, n, p, k0, kc, R);          \
+        } while (0)
+        if (kc <= 8)       VB_SUB_LAUNCH(8);
+        else if (kc <= 16) VB_SUB_LAUNCH(16);
+        else if (kc <= 20) VB_SUB_LAUNCH(20);
+        else if (kc <= 24) VB_SUB_LAUNCH(24);
+        else               VB_SUB_LAUNCH(32);
+#undef VB_SUB_LAUNCH
         VB_CHECK_LAUNCH();
         ++nl;
     }
