@@ -202,6 +202,40 @@ def test_collapse_median_multipass_kernel_still_bit_exact(vb, monkeypatch):
     np.testing.assert_array_equal(vb.cube_collapse(cube, "median"), np.nanmedian(cube, axis=0))
 
 
+@pytest.mark.parametrize("algo", ["radix", "range"])
+@pytest.mark.parametrize("cfg", [None, "4,40", "8,24", "16,24", "32,8"])
+def test_collapse_median_both_kernels_and_tiles(vb, monkeypatch, algo, cfg):
+    """The 4-bit radix kernel (VIP_B200_MEDIAN_ALGO=radix) and the range-adaptive kernel (default), on forced
+    (lanes per pixel, tile) configurations: bit-exact vs numpy on NaNs, ties, signed zeros, wide exponent ranges,
+    clustered values (several refinement rounds) and denormals."""
+    rng = np.random.default_rng(11)
+    n = 500
+    cube = rng.normal(size=(n, 12, 21)).astype(np.float32)
+    cube[rng.uniform(size=cube.shape) < 0.03] = np.nan
+    cube[:, 0, 0] = 3.5
+    cube[:, 1, 1] = np.nan
+    cube[:, 2, 2] = np.round(cube[:, 2, 2])
+    cube[: n // 2, 3, 3] = -0.0
+    cube[n // 2:, 3, 3] = 0.0
+    cube[:, 0, 1] *= 1e30
+    cube[1:, 0, 2] = np.nan
+    cube[:, 4, 4] = 1.0 + 1e-6 * rng.normal(size=n).astype(np.float32)     # a few ulps around 1: >= 3 rounds
+    cube[:, 5, 5] = (1e-41 * rng.normal(size=n)).astype(np.float32)         # denormals
+    cube[:, 6, 6] = np.where(np.arange(n) % 2 == 0, np.float32(-1e38), np.float32(1e38))
+    cube[:, 7, 7] = np.inf
+    cube[::3, 7, 8] = -np.inf
+    monkeypatch.setenv("VIP_B200_MEDIAN_ALGO", algo)
+    if cfg:
+        monkeypatch.setenv("VIP_B200_MEDIAN_CFG", cfg)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = np.nanmedian(cube, axis=0)
+        ref_even = np.nanmedian(cube[:-1], axis=0)
+    np.testing.assert_array_equal(vb.cube_collapse(cube, "median"), ref)
+    np.testing.assert_array_equal(vb.cube_collapse(cube[:-1], "median"), ref_even)
+
+
 def test_collapse_4d(vb):
     rng = np.random.default_rng(0)
     cube = rng.normal(size=(3, 11, 8, 8)).astype(np.float32)

@@ -119,18 +119,11 @@ __device__ __forceinline__ unsigned int group_min(unsigned int v) {
     return v;
 }
 
-template <int SUB>
-__global__ void __launch_bounds__(768)
-collapse_median_smem_kernel(const float* __restrict__ cube, int n, size_t p, int pxt, int stride,
-                            float* __restrict__ out) {
-    extern __shared__ unsigned int smem_keys[];
+// Load phase shared by the shared-memory median kernels: the n x pxt tile of order-preserving keys
+// (NaN -> 0xffffffff, larger than every real key), row pitch `stride` words.  Ends with a CTA barrier.
+__device__ __forceinline__ void median_load_tile(const float* __restrict__ cube, int n, size_t p, int pxt, int stride,
+                                                 size_t px0, unsigned int* __restrict__ K) {
     const int T = blockDim.x, tid = threadIdx.x;
-    unsigned int* K = smem_keys;
-    // two histogram copies ([16][T] each) so that consecutive keys update independent counters
-    unsigned short* __restrict__ H = reinterpret_cast<unsigned short*>(smem_keys + (size_t)n * stride);
-    unsigned short* __restrict__ H2 = H + 16 * T;
-    const size_t px0 = (size_t)blockIdx.x * pxt;
-
     // ---- load: every frame row of the tile is one contiguous pxt*4-byte segment
     if ((p & 3) == 0 && (pxt & 3) == 0 && px0 + pxt <= p) {
         const int q = pxt >> 2, total = n * q;
@@ -174,6 +167,22 @@ collapse_median_smem_kernel(const float* __restrict__ cube, int n, size_t p, int
         }
     }
     __syncthreads();
+
+}
+
+template <int SUB>
+__global__ void __launch_bounds__(768)
+collapse_median_smem_kernel(const float* __restrict__ cube, int n, size_t p, int pxt, int stride,
+                            float* __restrict__ out) {
+    extern __shared__ unsigned int smem_keys[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    unsigned int* K = smem_keys;
+    // two histogram copies ([16][T] each) so that consecutive keys update independent counters
+    unsigned short* __restrict__ H = reinterpret_cast<unsigned short*>(smem_keys + (size_t)n * stride);
+    unsigned short* __restrict__ H2 = H + 16 * T;
+    const size_t px0 = (size_t)blockIdx.x * pxt;
+
+    median_load_tile(cube, n, p, pxt, stride, px0, K);
 
     // ---- select
     const int px = tid / SUB, s = tid - px * SUB;
@@ -259,11 +268,152 @@ collapse_median_smem_kernel(const float* __restrict__ cube, int n, size_t p, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Range-adaptive variant (default).  The 4-bit radix passes above spend most of their instructions on per-pass
+// fixed costs (16 histogram rows to clear and to merge over the lanes, six passes for typical residuals whose
+// leading key bits -- sign and high exponent bits -- barely discriminate): 100 instructions per sample
+// (ncu r01l).  Here every round first takes min/max of the surviving candidates of a pixel and bins them on
+// (key - min) >> sh into 256 bins that span exactly that range (16-bit counters packed in pairs, one
+// shared-memory atomic per key); the lanes of the pixel scan the bins, the bin holding the wanted rank is
+// compacted in place and becomes the next candidate set.  A round divides the key range by 256, so typical
+// pixels finish in two rounds (500 -> a handful -> done) and at most four are ever needed.  Exact selection:
+// same results as the radix kernel, bit for bit.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHistPitch = 136;     // words per pixel: 128 packed counter pairs + 8 (bank spread between pixels)
+
+template <int SUB>
+__global__ void __launch_bounds__(768)
+collapse_median_range_kernel(const float* __restrict__ cube, int n, size_t p, int pxt, int stride,
+                             float* __restrict__ out) {
+    extern __shared__ unsigned int smem_keys[];
+    const int tid = threadIdx.x;
+    unsigned int* K = smem_keys;
+    unsigned int* Hs = smem_keys + (size_t)n * stride;
+    const size_t px0 = (size_t)blockIdx.x * pxt;
+    median_load_tile(cube, n, p, pxt, stride, px0, K);
+
+    constexpr unsigned int FULL = 0xffffffffu;
+    constexpr int W = 128 / SUB;                      // histogram words scanned per lane
+    const int px = tid / SUB, s = tid - px * SUB;
+    unsigned int* col = K + px;                       // candidate j of this thread: col[(s + SUB*j) * stride]
+    unsigned int* hist = Hs + (size_t)px * kHistPitch;
+    int ncand = (n - s + SUB - 1) / SUB;
+    if (ncand < 0) ncand = 0;
+    unsigned int r1 = 0, r2 = 0, m = 0, k1 = 0, k2 = 0;
+    bool done = false;
+#pragma unroll 1
+    for (int round = 0; round < 6; ++round) {
+        // (1) range of the candidates (NaN keys only exist in round 0: they never fall into a selected bin)
+        unsigned int kmin = FULL, kmax = 0u, nnan = 0u;
+        if (!done) {
+#pragma unroll 4
+            for (int j = 0; j < ncand; ++j) {
+                const unsigned int k = col[(size_t)(s + SUB * j) * stride];
+                if (k != FULL) { kmin = min(kmin, k); kmax = max(kmax, k); }
+                else ++nnan;
+            }
+        }
+        kmin = group_min<SUB>(kmin);
+        kmax = group_max<SUB>(kmax);
+        if (round == 0) {
+            m = (unsigned int)n - group_sum<SUB>(nnan);
+            if (m == 0) done = true;
+            r1 = (m - 1) >> 1;
+            r2 = m >> 1;
+        }
+        if (!done && kmin == kmax) { k1 = kmin; k2 = kmin; done = true; }
+        if (__all_sync(FULL, done)) break;
+        int sh = 24 - __clz(kmax - kmin);             // (32 - clz) - 8: (kmax - kmin) >> sh < 256
+        if (sh < 0) sh = 0;
+        // (2) clear, (3) fill the 256 bins of this pixel
+#pragma unroll
+        for (int w = 0; w < W; ++w) hist[s * W + w] = 0u;
+        __syncwarp();
+        if (!done) {
+#pragma unroll 4
+            for (int j = 0; j < ncand; ++j) {
+                const unsigned int k = col[(size_t)(s + SUB * j) * stride];
+                if (k != FULL) {
+                    const unsigned int d = (k - kmin) >> sh;
+                    atomicAdd(&hist[d >> 1], 1u << ((d & 1u) << 4));
+                }
+            }
+        }
+        __syncwarp();
+        // (4) bins of the two wanted ranks: lane s scans bins [2 W s, 2 W (s+1))
+        unsigned int hw[W];
+        unsigned int loc = 0u;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            hw[w] = hist[s * W + w];
+            loc += (hw[w] & 0xffffu) + (hw[w] >> 16);
+        }
+        unsigned int incl = loc;
+#pragma unroll
+        for (int o = 1; o < SUB; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(FULL, incl, o, SUB);
+            if (s >= o) incl += t;
+        }
+        const unsigned int excl = incl - loc;
+        unsigned int pb = 0u, pc = 0u;                // owner lanes fill: pb = b1 | b2 << 8 | flags, pc = c1 | t1 << 16
+        if (!done) {
+            const bool own1 = r1 >= excl && r1 < incl, own2 = r2 >= excl && r2 < incl;
+            if (own1 || own2) {
+                unsigned int cum = excl;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const unsigned int c = h ? (hw[w] >> 16) : (hw[w] & 0xffffu);
+                        const unsigned int bin = (unsigned int)(2 * (s * W + w) + h);
+                        if (own1 && r1 >= cum && r1 < cum + c) { pb |= bin; pc = cum | (c << 16); }
+                        if (own2 && r2 >= cum && r2 < cum + c) { pb |= bin << 8; }
+                        cum += c;
+                    }
+                }
+            }
+        }
+        pb = group_sum<SUB>(pb);                      // exactly one lane contributes each field
+        pc = group_sum<SUB>(pc);
+        const unsigned int b1 = pb & 0xffu, b2 = (pb >> 8) & 0xffu, c1 = pc & 0xffffu, t1 = pc >> 16;
+        // (5) keep bin b1 (compaction in place), max over bin b1, min over bin b2
+        unsigned int mx = 0u, mn = FULL;
+        if (!done) {
+            int w = 0;
+#pragma unroll 4
+            for (int j = 0; j < ncand; ++j) {
+                const unsigned int k = col[(size_t)(s + SUB * j) * stride];
+                if (k == FULL) continue;
+                const unsigned int d = (k - kmin) >> sh;
+                if (d == b1) { col[(size_t)(s + SUB * w) * stride] = k; ++w; mx = max(mx, k); }
+                if (d == b2) mn = min(mn, k);
+            }
+            ncand = w;
+        }
+        mx = group_max<SUB>(mx);
+        mn = group_min<SUB>(mn);
+        if (!done) {
+            if (b1 != b2) { k1 = mx; k2 = mn; done = true; }
+            else if (t1 == 1u || sh == 0) { k1 = mx; k2 = mx; done = true; }
+            else { r1 -= c1; r2 -= c1; }
+        }
+        __syncwarp();
+        if (__all_sync(FULL, done)) break;
+    }
+    if (s == 0 && px < pxt && px0 + px < p) {
+        float r;
+        if (m == 0) r = __uint_as_float(0x7fc00000u);
+        else if (m & 1u) r = key2f(k1);
+        else r = (key2f(k1) + key2f(k2)) * 0.5f;
+        out[px0 + px] = r;
+    }
+}
+
 struct MedianCfg { int sub, pxt, stride, threads; size_t smem; };
 
 // Pick (SUB, pixel tile, padded stride) maximising resident threads per SM; returns false when n is too
 // large for a shared-memory tile (the multi-pass kernel handles those).
-static bool pick_median_cfg(int n, MedianCfg* best) {
+static bool pick_median_cfg(int n, MedianCfg* best, int range_variant) {
     const size_t smem_max = 227 * 1024 - 1024;
     // lanes per pixel: the per-pass histogram merge costs 16*log2(SUB) shuffles per lane, the scan
     // n/SUB keys -- keep the scan the larger part (about 64 keys per lane) unless n forces more lanes
@@ -276,7 +426,8 @@ static bool pick_median_cfg(int n, MedianCfg* best) {
             const int g = 32 / sub;
             const int stride = ((pxt / g) & 1) ? pxt : pxt + g;
             const int threads = pxt * sub;
-            const size_t smem = (size_t)n * stride * 4 + (size_t)64 * threads;
+            const size_t smem = (size_t)n * stride * 4 +
+                                (range_variant ? (size_t)pxt * kHistPitch * 4 : (size_t)64 * threads);
             if (pxt % g == 0 && threads <= 768 && (threads & 31) == 0 && smem <= smem_max) {
                 *best = MedianCfg{sub, pxt, stride, threads, smem};
                 return true;
@@ -290,7 +441,8 @@ static bool pick_median_cfg(int n, MedianCfg* best) {
             const int stride = ((pxt / g) & 1) ? pxt : pxt + g;
             const int threads = pxt * sub;
             if (threads > 768 || (threads & 31)) continue;
-            const size_t smem = (size_t)n * stride * 4 + (size_t)64 * threads;
+            const size_t smem = (size_t)n * stride * 4 +
+                                (range_variant ? (size_t)pxt * kHistPitch * 4 : (size_t)64 * threads);
             if (smem > smem_max) continue;
             int ctas = (int)((227 * 1024) / (smem + 1024));
             if (ctas * threads > 2048) ctas = 2048 / threads;
@@ -306,17 +458,23 @@ static bool pick_median_cfg(int n, MedianCfg* best) {
     return best_score > 0.0;
 }
 
-static int launch_median_smem(const float* cube, int n, size_t p, float* out, const MedianCfg& c, cudaStream_t st) {
+static int launch_median_smem(const float* cube, int n, size_t p, float* out, const MedianCfg& c, int range_variant,
+                              cudaStream_t st) {
     const unsigned grid = (unsigned)ceil_div(p, (size_t)c.pxt);
 #define VB_MEDIAN_CASE(S)                                                                              \
     case S: {                                                                                          \
-        static size_t configured = 0;                                                                  \
-        if (c.smem > configured) {                                                                     \
+        static bool configured = false;                                                                \
+        if (!configured) {                                                                             \
             VB_CHECK_CUDA(cudaFuncSetAttribute(collapse_median_smem_kernel<S>,                         \
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))); \
-            configured = 227 * 1024;                                                                   \
+            VB_CHECK_CUDA(cudaFuncSetAttribute(collapse_median_range_kernel<S>,                        \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))); \
+            configured = true;                                                                         \
         }                                                                                              \
-        collapse_median_smem_kernel<S><<<grid, c.threads, c.smem, st>>>(cube, n, p, c.pxt, c.stride, out); \
+        if (range_variant)                                                                             \
+            collapse_median_range_kernel<S><<<grid, c.threads, c.smem, st>>>(cube, n, p, c.pxt, c.stride, out); \
+        else                                                                                           \
+            collapse_median_smem_kernel<S><<<grid, c.threads, c.smem, st>>>(cube, n, p, c.pxt, c.stride, out);  \
         break;                                                                                         \
     }
     switch (c.sub) {
@@ -420,7 +578,11 @@ int collapse_f32(const float* cube, int n, size_t p, int mode, const double* w, 
         case kMedian: {
             MedianCfg cfg;
             const char* e = getenv("VIP_B200_MEDIAN_MULTIPASS");
-            if (!(e && atoi(e)) && pick_median_cfg(n, &cfg)) return launch_median_smem(cube, n, p, fo, cfg, st);
+            // VIP_B200_MEDIAN_ALGO=radix selects the 4-bit radix kernel; default: range-adaptive 256-bin rounds
+            const char* a = getenv("VIP_B200_MEDIAN_ALGO");
+            const int range_variant = (a && strcmp(a, "radix") == 0) ? 0 : 1;
+            if (!(e && atoi(e)) && pick_median_cfg(n, &cfg, range_variant))
+                return launch_median_smem(cube, n, p, fo, cfg, range_variant, st);
             collapse_median_kernel<<<(unsigned)ceil_div(p, (size_t)CT), CT, 0, st>>>(cube, n, p, fo);
             break;
         }
