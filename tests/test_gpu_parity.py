@@ -327,6 +327,30 @@ def test_eigh_topk_matches_lapack(n, k):
     assert np.max(np.abs(E.T @ E - v[:, :k] @ v[:, :k].T)) < 1e-8
 
 
+@pytest.mark.parametrize("n,k", [(150, 10), (500, 20), (333, 24), (64, 5)])
+@pytest.mark.parametrize("env", [{"VIP_B200_TOPK_CHOL": "1"}, {"VIP_B200_TOPK_RR": "0"},
+                                 {"VIP_B200_TOPK_CHOL": "1", "VIP_B200_TOPK_RR": "0"},
+                                 {"VIP_B200_TOPK_CHOL": "0", "VIP_B200_TOPK_RR": "4"}])
+def test_eigh_topk_solver_variants(n, k, env, monkeypatch):
+    """Fused subspace solver with the right-looking Cholesky / reciprocal pivots (VIP_B200_TOPK_CHOL=1) and the
+    adaptive Ritz schedule (VIP_B200_TOPK_RR=0), against LAPACK; the last entry pins the original kernel."""
+    import torch
+    from vip_b200 import kernels
+    for kk, vv in env.items():
+        monkeypatch.setenv(kk, vv)
+    cube, _ = adi_cube(n, 48, k, 60.0, seed=n + k)
+    M = cube.reshape(n, -1).astype(np.float64)
+    G = M @ M.T
+    evals, evecs, info = kernels.eigh_topk(torch.from_numpy(G).cuda(), k)
+    assert info["converged"], info
+    w, v = np.linalg.eigh(G)
+    w, v = w[::-1], v[:, ::-1]
+    np.testing.assert_allclose(evals.cpu().numpy(), w[:k], rtol=1e-10)
+    E = evecs.cpu().numpy()
+    np.testing.assert_allclose(E @ E.T, np.eye(k), atol=1e-10)
+    assert np.max(np.abs(E.T @ E - v[:, :k] @ v[:, :k].T)) < 1e-8
+
+
 def test_decomposition_falls_back_to_jacobi_when_subspace_iteration_stalls():
     """700 frames of 48x48 with 24 weak modes right above the noise bulk: the gap after k is ~1 %, plain
     subspace iteration does not reach the tolerance within its iteration cap and must say so; the

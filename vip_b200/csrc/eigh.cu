@@ -346,7 +346,9 @@ struct TopkState {
     int iters;
     int converged;
     double worst;     // max residual / theta_k at the last check
-    double pad;
+    double prev_worst;   // adaptive Ritz schedule (fused kernel, rr_every = 0): previous check and its iteration
+    int prev_it;
+    int next_rr;         // iteration index of the next Rayleigh-Ritz step
 };
 
 
@@ -674,12 +676,12 @@ struct FusedSmem {
 template <int B>
 __global__ void __launch_bounds__(512, 1)
 topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int max_iter, double jthr, int rr_every,
-                  double* X, double* T, double* S, double* Qm, double* R, double* theta, double* res, double* dinv,
+                  int chol_mode, int rr0, double* X, double* T, double* S, double* Qm, double* R, double* theta, double* res, double* dinv,
                   TopkState* st, unsigned int* bar) {
     using FS = FusedSmem<B>;
     constexpr int RPC = FS::RPC, TJ = FS::TJ;
     __shared__ typename FS::U u;
-    __shared__ double Ys[RPC][B + 1], Xm[RPC][B + 1], Qs[B][B + 1], dv[B];
+    __shared__ double Ys[RPC][B + 1], Xm[RPC][B + 1], Qs[B][B + 1], dv[B], rq[B];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tr = tid / B, tc = tid % B;
     const int r0 = blockIdx.x * RPC, r = r0 + tr;
@@ -696,7 +698,7 @@ topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int ma
         }
     };
     // phase D on CTA 0 / warp 0
-    auto cholesky_phase = [&](int check, int count_iter) {
+    auto cholesky_phase = [&](int check, int count_iter, int it_now) {
         if (blockIdx.x == 0 && warp == 0) {
             if (lane == 0) {
                 if (count_iter) st->iters += 1;
@@ -704,8 +706,25 @@ topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int ma
                     double worst = 0.0;
                     for (int q = 0; q < k; ++q) worst = fmax(worst, sqrt(__ldcg(&res[q])));
                     const double ref = __ldcg(&theta[k - 1]);
-                    st->worst = ref > 0.0 ? worst / ref : 0.0;
+                    const double rho = ref > 0.0 ? worst / ref : 0.0;
                     if (worst <= tol * ref) st->converged = 1;
+                    else if (rr_every == 0) {
+                        // adaptive schedule: convergence is geometric, so two checks give the rate and the number of
+                        // iterations still needed; the next Ritz step is placed there (2..8 ahead: the step before
+                        // it must be the CholeskyQR2 one) instead of every 4th iteration
+                        int step = 4;
+                        const double prho = st->prev_worst;
+                        const int pit = st->prev_it;
+                        if (pit > 0 && prho > 0.0 && rho > 0.0 && rho < prho) {
+                            const double lr = log(rho / prho) / (double)(it_now - pit);     // log rate per iteration (< 0)
+                            const double need = ceil(log(tol / rho) / lr);
+                            step = (need < 2.0) ? 2 : (need > 8.0 ? 8 : (int)need);
+                        }
+                        st->prev_worst = rho;
+                        st->prev_it = it_now;
+                        st->next_rr = it_now + step;
+                    }
+                    st->worst = rho;
                 }
             }
             __syncwarp();
@@ -714,6 +733,38 @@ topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int ma
                 dv[c] = d > 0.0 ? rsqrt(d) : 0.0;
             }
             __syncwarp();
+            if (chol_mode == 1) {
+                // Right-looking Cholesky, lane c owns column c of the (column-normalised) Gram matrix in shared memory
+                // (pitch B + 1: conflict-free): step j scales row j by a reciprocal square root and every lane
+                // updates its own column with INDEPENDENT FMAs.  The left-looking loop below recomputes, in every
+                // step and on every lane, a length-j dependent chain for the pivot and another for the row, with
+                // sqrt + division on the critical path: ~8-17 us per factorisation, 21 factorisations per solve.
+                const int c = lane;
+                for (int e = lane; e < B * B; e += 32) u.d.Sn[e / B][e % B] = __ldcg(&S[e]) * dv[e / B] * dv[e % B];
+                __syncwarp();
+#pragma unroll 1
+                for (int j = 0; j < B; ++j) {
+                    const double ajj = u.d.Sn[j][j];
+                    double d, rd;
+                    if (ajj > 1e-300) { rd = rsqrt(ajj); d = ajj * rd; } else { d = 1e-150; rd = 1e150; }
+                    double rjc = 0.0;
+                    if (c < B && c >= j) {
+                        rjc = (c == j) ? d : u.d.Sn[j][c] * rd;
+                        u.d.Rm[j][c] = rjc;
+                    }
+                    __syncwarp();
+                    if (c < B) {
+#pragma unroll 4
+                        for (int i = j + 1; i <= c; ++i) u.d.Sn[i][c] = fma(-u.d.Rm[j][i], rjc, u.d.Sn[i][c]);
+                    }
+                    __syncwarp();
+                }
+                for (int e = lane; e < B * B; e += 32) {
+                    R[e] = (e / B <= e % B) ? u.d.Rm[e / B][e % B] : 0.0;
+                    S[e] = 0.0;
+                    T[e] = 0.0;
+                }
+            } else {
             for (int e = lane; e < B * B; e += 32) u.d.Sn[e / B][e % B] = __ldcg(&S[e]) * dv[e / B] * dv[e % B];
             __syncwarp();
             for (int j = 0; j < B; ++j) {
@@ -732,13 +783,17 @@ topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int ma
                 S[e] = 0.0;
                 T[e] = 0.0;
             }
+            }
             for (int c = lane; c < B; c += 32) { dinv[c] = dv[c]; res[c] = 0.0; }
         }
     };
     // phase E: own rows  X = src D^-1 R^-1  (one thread per row), result to global X and to Xm
     auto solve_phase = [&](double (*src)[B + 1]) {
         for (int e = tid; e < B * B; e += 512) Qs[e / B][e % B] = __ldcg(&R[e]);
-        if (tid < B) dv[tid] = __ldcg(&dinv[tid]);
+        if (tid < B) {
+            dv[tid] = __ldcg(&dinv[tid]);
+            rq[tid] = 1.0 / __ldcg(&R[tid * B + tid]);     // chol_mode 1: reciprocal pivots, no division in the chain
+        }
         __syncthreads();
         if (tid < RPC) {
             double x[B];
@@ -747,7 +802,7 @@ topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int ma
                 double v = src[tid][c] * dv[c];
 #pragma unroll
                 for (int m = 0; m < c; ++m) v -= x[m] * Qs[m][c];
-                x[c] = v / Qs[c][c];
+                x[c] = chol_mode ? v * rq[c] : v / Qs[c][c];
             }
 #pragma unroll
             for (int c = 0; c < B; ++c) {
@@ -759,9 +814,19 @@ topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int ma
     };
 
     for (int it = 0; it < max_iter; ++it) {
-        const int ph = it % rr_every;
-        const bool rr = ph == rr_every - 1;
-        const bool qr2 = !rr && ph == rr_every - 2;
+        bool rr, qr2;
+        if (rr_every > 0) {
+            const int ph = it % rr_every;
+            rr = ph == rr_every - 1;
+            qr2 = !rr && ph == rr_every - 2;
+        } else {
+            // adaptive: first Ritz step at iteration rr0 - 1, then where phase D of the last one placed it (the value
+            // was published before the grid barrier that ended that iteration)
+            int nxt = __ldcg(&st->next_rr);
+            if (nxt < rr0 - 1) nxt = rr0 - 1;
+            rr = it == nxt || it == max_iter - 1;
+            qr2 = !rr && (it + 1 == nxt || it + 2 == max_iter);
+        }
 
         // ---- A: Y rows = G rows . X
         double acc0 = 0.0, acc1 = 0.0;
@@ -889,7 +954,7 @@ topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int ma
         }
 
         // ---- D: Cholesky (+ convergence test after a Ritz step)
-        cholesky_phase(rr ? 1 : 0, 1);
+        cholesky_phase(rr ? 1 : 0, 1, it);
         grid_barrier(bar, epoch);
         if (rr && __ldcg(&st->converged)) break;
 
@@ -899,7 +964,7 @@ topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int ma
             // second Cholesky-QR pass on the freshly orthogonalised block
             partial_gram(Xm, Xm, S);
             grid_barrier(bar, epoch);
-            cholesky_phase(0, 0);
+            cholesky_phase(0, 0, it);
             grid_barrier(bar, epoch);
             for (int e = tid; e < RPC * B; e += 512) Ys[e / B][e % B] = Xm[e / B][e % B];
             __syncthreads();
@@ -944,12 +1009,17 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
     const int fused_grid = ceil_div(n, 512 / B);
     if ((fe ? atoi(fe) : 1) && fused_grid <= kNumSMs) {
         const char* re = getenv("VIP_B200_TOPK_RR");
-        int rr_every = re ? atoi(re) : 4;
-        if (rr_every < 1) rr_every = 1;
+        int rr_every = re ? atoi(re) : 4;        // 0 = adaptive schedule (first Ritz step at iteration rr0)
+        if (rr_every < 0) rr_every = 1;
+        const char* r0e = getenv("VIP_B200_TOPK_RR0");
+        int rr0 = r0e ? atoi(r0e) : 8;
+        if (rr0 < 2) rr0 = 2;
         unsigned int* bar = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(state) + 64);
-        int fmax = ceil_div(max_iter, rr_every) * rr_every;
+        int fmax = rr_every > 0 ? ceil_div(max_iter, rr_every) * rr_every : max_iter;
+        const char* ce_ = getenv("VIP_B200_TOPK_CHOL");
+        int chol_mode = ce_ ? atoi(ce_) : 0;          // 1: register-resident right-looking Cholesky (see phase D)
         void* args[] = {(void*)&G, (void*)&n, (void*)&k, (void*)&tol, (void*)&fmax, (void*)&jthr, (void*)&rr_every,
-                        (void*)&X, (void*)&T, (void*)&S, (void*)&Qm, (void*)&R, (void*)&theta, (void*)&res,
+                        (void*)&chol_mode, (void*)&rr0, (void*)&X, (void*)&T, (void*)&S, (void*)&Qm, (void*)&R, (void*)&theta, (void*)&res,
                         (void*)&dinv, (void*)&state, (void*)&bar};
         const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)topk_fused_kernel<B>, dim3(fused_grid),
                                                            dim3(512), args, 0, st);
