@@ -715,8 +715,16 @@ topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int ma
                         int step = 4;
                         const double prho = st->prev_worst;
                         const int pit = st->prev_it;
+                        double lr = 0.0;                                   // log of the rate per iteration (< 0)
                         if (pit > 0 && prho > 0.0 && rho > 0.0 && rho < prho) {
-                            const double lr = log(rho / prho) / (double)(it_now - pit);     // log rate per iteration (< 0)
+                            lr = log(rho / prho) / (double)(it_now - pit);
+                        } else {
+                            // first check: subspace iteration converges like lambda_{B+1} / lambda_k, estimated by
+                            // the smallest Ritz value of the block over the k-th
+                            const double thb = __ldcg(&theta[B - 1]);
+                            if (thb > 0.0 && thb < ref) lr = log(thb / ref);
+                        }
+                        if (lr < 0.0 && rho > 0.0) {
                             const double need = ceil(log(tol / rho) / lr);
                             step = (need < 2.0) ? 2 : (need > 8.0 ? 8 : (int)need);
                         }
