@@ -205,7 +205,7 @@ def test_collapse_median_multipass_kernel_still_bit_exact(vb, monkeypatch):
 @pytest.mark.parametrize("algo", ["radix", "range"])
 @pytest.mark.parametrize("cfg", [None, "4,40", "8,24", "16,24", "32,8"])
 def test_collapse_median_both_kernels_and_tiles(vb, monkeypatch, algo, cfg):
-    """The 4-bit radix kernel (VIP_B200_MEDIAN_ALGO=radix) and the range-adaptive kernel (default), on forced
+    """The 4-bit radix kernel (default) and the range-adaptive kernel (VIP_B200_MEDIAN_ALGO=range), on forced
     (lanes per pixel, tile) configurations: bit-exact vs numpy on NaNs, ties, signed zeros, wide exponent ranges,
     clustered values (several refinement rounds) and denormals."""
     rng = np.random.default_rng(11)
@@ -328,12 +328,14 @@ def test_eigh_topk_matches_lapack(n, k):
 
 
 @pytest.mark.parametrize("n,k", [(150, 10), (500, 20), (333, 24), (64, 5)])
-@pytest.mark.parametrize("env", [{"VIP_B200_TOPK_CHOL": "1"}, {"VIP_B200_TOPK_RR": "0"},
+@pytest.mark.parametrize("env", [{"VIP_B200_TOPK_CHOL": "1", "VIP_B200_TOPK_RR": "4"},
+                                 {"VIP_B200_TOPK_CHOL": "0", "VIP_B200_TOPK_RR": "0"},
                                  {"VIP_B200_TOPK_CHOL": "1", "VIP_B200_TOPK_RR": "0"},
                                  {"VIP_B200_TOPK_CHOL": "0", "VIP_B200_TOPK_RR": "4"}])
 def test_eigh_topk_solver_variants(n, k, env, monkeypatch):
-    """Fused subspace solver with the right-looking Cholesky / reciprocal pivots (VIP_B200_TOPK_CHOL=1) and the
-    adaptive Ritz schedule (VIP_B200_TOPK_RR=0), against LAPACK; the last entry pins the original kernel."""
+    """Fused subspace solver: right-looking Cholesky / reciprocal pivots (VIP_B200_TOPK_CHOL=1, default) and the
+    adaptive Ritz schedule (VIP_B200_TOPK_RR=0, default), one at a time and together, against LAPACK; the last
+    entry pins the original phases and the fixed every-4th schedule."""
     import torch
     from vip_b200 import kernels
     for kk, vv in env.items():

@@ -269,7 +269,8 @@ collapse_median_smem_kernel(const float* __restrict__ cube, int n, size_t p, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// Range-adaptive variant (default).  The 4-bit radix passes above spend most of their instructions on per-pass
+// Range-adaptive variant (experiment, VIP_B200_MEDIAN_ALGO=range; NOT faster: 0.64 ms vs 0.55 ms at config 2, the
+// shared-memory atomics and the two extra scans per round cost more than the saved passes).  The 4-bit radix passes above spend most of their instructions on per-pass
 // fixed costs (16 histogram rows to clear and to merge over the lanes, six passes for typical residuals whose
 // leading key bits -- sign and high exponent bits -- barely discriminate): 100 instructions per sample
 // (ncu r01l).  Here every round first takes min/max of the surviving candidates of a pixel and bins them on
@@ -578,9 +579,10 @@ int collapse_f32(const float* cube, int n, size_t p, int mode, const double* w, 
         case kMedian: {
             MedianCfg cfg;
             const char* e = getenv("VIP_B200_MEDIAN_MULTIPASS");
-            // VIP_B200_MEDIAN_ALGO=radix selects the 4-bit radix kernel; default: range-adaptive 256-bin rounds
+            // default: 4-bit radix kernel; VIP_B200_MEDIAN_ALGO=range selects the range-adaptive 256-bin rounds
+            // (measured slower on config 2: 0.64 vs 0.55 ms, profiles/r01o_ab.md -- kept as a tested experiment)
             const char* a = getenv("VIP_B200_MEDIAN_ALGO");
-            const int range_variant = (a && strcmp(a, "radix") == 0) ? 0 : 1;
+            const int range_variant = (a && strcmp(a, "range") == 0) ? 1 : 0;
             if (!(e && atoi(e)) && pick_median_cfg(n, &cfg, range_variant))
                 return launch_median_smem(cube, n, p, fo, cfg, range_variant, st);
             collapse_median_kernel<<<(unsigned)ceil_div(p, (size_t)CT), CT, 0, st>>>(cube, n, p, fo);

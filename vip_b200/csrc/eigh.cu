@@ -1017,7 +1017,7 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
     const int fused_grid = ceil_div(n, 512 / B);
     if ((fe ? atoi(fe) : 1) && fused_grid <= kNumSMs) {
         const char* re = getenv("VIP_B200_TOPK_RR");
-        int rr_every = re ? atoi(re) : 4;        // 0 = adaptive schedule (first Ritz step at iteration rr0)
+        int rr_every = re ? atoi(re) : 0;        // 0 = adaptive schedule (default; first Ritz step at iteration rr0), 4 = r01n
         if (rr_every < 0) rr_every = 1;
         const char* r0e = getenv("VIP_B200_TOPK_RR0");
         int rr0 = r0e ? atoi(r0e) : 8;
@@ -1025,7 +1025,7 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
         unsigned int* bar = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(state) + 64);
         int fmax = rr_every > 0 ? ceil_div(max_iter, rr_every) * rr_every : max_iter;
         const char* ce_ = getenv("VIP_B200_TOPK_CHOL");
-        int chol_mode = ce_ ? atoi(ce_) : 0;          // 1: register-resident right-looking Cholesky (see phase D)
+        int chol_mode = ce_ ? atoi(ce_) : 1;          // 1 (default): right-looking Cholesky + reciprocal pivots (phase D/E)
         void* args[] = {(void*)&G, (void*)&n, (void*)&k, (void*)&tol, (void*)&fmax, (void*)&jthr, (void*)&rr_every,
                         (void*)&chol_mode, (void*)&rr0, (void*)&X, (void*)&T, (void*)&S, (void*)&Qm, (void*)&R, (void*)&theta, (void*)&res,
                         (void*)&dinv, (void*)&state, (void*)&bar};
