@@ -26,19 +26,37 @@ def circle_mask(shape, radius):
     return m
 
 
-def mask_circle(array, radius, fillwith=0):
-    """Copy of a numpy frame/cube with the centred disk set to ``fillwith`` (``var/shapes.py:38-113``)."""
+def mask_circle(array, radius, fillwith=0, mode="in", cy=None, cx=None, output="masked_arr"):
+    """Copy of a numpy frame/cube with the pixels inside (``mode='in'``) or outside (``'out'``) the disk set to
+    ``fillwith``, or the boolean keep-mask of the disk (``output='bool_mask'``) (``var/shapes.py:38-113``).
+    Cubes are indexed with the disk indices swapped, as the reference does (:101, :109)."""
     if not isinstance(fillwith, (int, float)):
         raise ValueError("`fillwith` must be integer, float or np.nan")
     shape = (array.shape[-2], array.shape[-1])
-    if radius == 0:
-        return array * True
-    out = array.copy()
-    if array.ndim == 2:
+    if cy is None or cx is None:
         cy, cx = frame_center(shape)
-        out[disk_indices(cy, cx, radius, shape)] = fillwith
+    if radius == 0:
+        keep_all = mode == "in"
+        if output == "bool_mask":
+            return np.full(shape, keep_all, dtype=bool)
+        return array * keep_all
+    rows, cols = disk_indices(cy, cx, radius, shape)
+    if output == "bool_mask":
+        keep = np.ones(shape, dtype=bool)
+        keep[rows, cols] = False
+        return keep
+    if output != "masked_arr":
+        raise ValueError("`output` not recognized")
+    # 2-d frames use (rows, cols); cubes use the swapped pair on their last two axes
+    sel = (rows, cols) if array.ndim == 2 else (Ellipsis, cols, rows)
+    if mode == "in":
+        out = array.copy()
+        out[sel] = fillwith
+    elif mode == "out":
+        out = np.full_like(array, fillwith)
+        out[sel] = array[sel]
     else:
-        out[..., circle_mask(shape, radius)] = fillwith
+        raise ValueError("`mode` not recognized")
     return out
 
 
