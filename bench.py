@@ -55,6 +55,7 @@ class ClockSampler:
     def __init__(self, index=0):
         self.index = index
         self.samples = []
+        self.marks = []
         self.stop = threading.Event()
         self.thread = None
 
@@ -69,7 +70,7 @@ class ClockSampler:
             line = proc.stdout.readline()
             if not line:
                 break
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
         proc.terminate()
 
     def __enter__(self):
@@ -81,10 +82,22 @@ class ClockSampler:
         self.stop.set()
         self.thread.join(timeout=2)
 
+    def mark(self):
+        """Host time stamp: call at the start and at the end of a timed region (pairs)."""
+        self.marks.append(time.time())
+
     def summary(self):
+        """Clocks / throttle reasons of the samples taken INSIDE the marked timed regions (nvidia-smi needs a few
+        hundred ms to start streaming, so the sampler is started before the warm-up steps, which run the same
+        load); if a region was too short to catch one, the samples of the whole run under load are used and
+        ``in_timed_region`` says 0."""
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        regions = list(zip(self.marks[0::2], self.marks[1::2]))
+        inside = [s for t, s in self.samples if any(a <= t <= b + 0.1 for a, b in regions)]
+        n_inside = len(inside)
+        use = inside if inside else [s for _, s in self.samples]
+        for s in use:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 7:
                 continue
@@ -97,9 +110,9 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "in_timed_region": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "in_timed_region": n_inside}
 
 
 # --------------------------------------------------------------------------------------------
@@ -297,15 +310,19 @@ def run_gpu(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(3, args.warmup)):
-        step_dev()
-    n0 = _cabi.launch_count()
     with ClockSampler(local) as clk:
+        for _ in range(max(3, args.warmup)):
+            step_dev()
+        n0 = _cabi.launch_count()
+        clk.mark()
         ms_dev = timed(step_dev, args.steps)
+        clk.mark()
         launches = (_cabi.launch_count() - n0) // args.steps
         for _ in range(2):
             step_e2e()
+        clk.mark()
         ms_e2e = timed(step_e2e, args.steps)
+        clk.mark()
     clocks = clk.summary()
 
     frames_total = n          # one cube per step, whatever the number of GPUs
