@@ -5,7 +5,7 @@ their known-answer arrays stay in the reference tree (last 
 
 Substituted (all host numpy code, no GPU): ``vip_b200.var`` (frame_center, dist, mask_circle,
 get_annulus_segments, reshape_matrix), ``vip_b200.preproc`` (_find_indices_adi, _define_annuli,
-check_scal_vector) and, where the product computes on the GPU, the oracle's restatement
+check_scal_vector, _find_indices_sdi) and, where the product computes on the GPU, the oracle's restatement
 (matrix_scaling, cube_rescaling_wavelengths, get_square).
 """
 import importlib.util
@@ -142,6 +142,23 @@ def test_rescaling_known_answers():
     mod = _load("pre_3_10/test_preproc_rescaling.py")
     mod.check_scal_vector = r.check_scal_vector
     _run(mod, "test_check_scal_vector")
+    ref_sdi = mod._find_indices_sdi
+    mod._find_indices_sdi = r._find_indices_sdi
+    assert _run(mod, "test_find_indices_sdi") == 7            # :152-169, seven known-answer index lists
+    # beyond the reference's vectors: random wavelength grids, separations and `nframes` windows, same lists / errors
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        z = int(rng.integers(3, 40))
+        wl = np.sort(rng.uniform(0.9, 2.4, z))
+        args = (wl.max() / wl, float(rng.uniform(2, 120)), int(rng.integers(0, z)), float(rng.uniform(2, 6)))
+        kw = {"delta_sep": float(rng.choice([0.1, 0.5, 1.0])), "nframes": rng.choice([None, 2, 4, 8])}
+        try:
+            want = ref_sdi(*args, **kw)
+        except RuntimeError:
+            with pytest.raises(RuntimeError):
+                r._find_indices_sdi(*args, **kw)
+            continue
+        np.testing.assert_array_equal(r._find_indices_sdi(*args, **kw), want)
 
     def rescale(cube, scal_list, full_output=True, inverse=False, y_in=None, x_in=None, imlib="vip-fft",
                 interpolation=None, **kw):

@@ -4,3 +4,4 @@ from .derotation import (cube_derotate, frame_rotate, _find_indices_adi, _comput
 from .subsampling import cube_collapse          # noqa: F401
 from .parangles import check_pa_vector          # noqa: F401
 from .recentering import frame_shift, cube_shift    # noqa: F401
+from .rescaling import check_scal_vector, _find_indices_sdi    # noqa: F401

@@ -1,7 +1,7 @@
 """SDI wavelength (de)scaling with the FFT method, as separable linear operators on the GPU.
 
 Reference: ``src/vip_hci/preproc/rescaling.py`` -- ``cube_rescaling_wavelengths`` :324-475,
-``frame_rescaling`` (vip-fft branch) :641-673, ``scale_fft`` :1114-1217, ``check_scal_vector`` :767-794.
+``frame_rescaling`` (vip-fft branch) :641-673, ``scale_fft`` :1114-1217, ``check_scal_vector`` :767-794, ``_find_indices_sdi`` :916-988.
 
 ``scale_fft`` is a fixed linear map per (frame size, scale): zero-pad to N+2kd, FFT, crop/pad the
 spectrum to N+2kf, inverse FFT, crop/embed back to N -- the same 1-d complex operator L along both
@@ -24,6 +24,33 @@ def check_scal_vector(scal_vec):
     if scal_vec.min() != 1:
         scal_vec = scal_vec / scal_vec.min()
     return scal_vec
+
+
+def _find_indices_sdi(scal, dist, index_ref, fwhm, delta_sep=1, nframes=None, debug=False):
+    """Spectral channels usable as PSF-model library for channel ``index_ref`` at separation ``dist`` px: those whose
+    radial motion after rescaling is at least ``delta_sep`` mean FWHM, on either side of the reference wavelength
+    (``rescaling.py:916-988``).  Integer index logic, kept on the host in fp64 with the reference's expressions so
+    that the lists are bit-exact; ``nframes`` keeps a window of adjacent channels around the reference one."""
+    scal = np.asarray(scal)
+    ref = scal[index_ref]
+    # motion (in FWHM) of a companion at dist +/- one resolution element, for shorter / longer wavelengths
+    shorter = (ref - scal) / ref * ((dist + fwhm * delta_sep) / fwhm) >= delta_sep
+    longer = (scal - ref) / ref * ((dist - fwhm * delta_sep) / fwhm) >= delta_sep
+    indices = np.nonzero(shorter | longer)[0]
+    if debug:
+        print("dist: {}, index_ref: {}, indices: {}".format(dist, index_ref, indices))
+    if indices.size == 0:
+        raise RuntimeError("No frames left after radial motion threshold. Try decreasing the value of `delta_sep`")
+    if nframes is not None:
+        n_short = int(shorter.sum())
+        half = nframes // 2
+        if n_short - half < 0 or n_short + half > indices[-1]:
+            half = nframes
+        indices = indices[max(0, n_short - half):min(scal.size, n_short + half)]
+        if indices.size < 2:
+            raise RuntimeError("No frames left after radial motion threshold. Try decreasing the value of "
+                               "`delta_sep` or `nframes`")
+    return indices
 
 
 def _scale_fft_1d_operator(dim, scale):
