@@ -109,7 +109,7 @@ def _worker(rank, world, port, collapse, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,collapse", [(2, "median"), (3, "mean")])
+@pytest.mark.parametrize("world,collapse", [(2, "median"), (3, "mean"), (8, "median")])
 def test_sharded_pca_matches_single_process(tmp_path, world, collapse):
     out = str(tmp_path / "frame.npy")
     mp.spawn(_worker, args=(world, _free_port(), collapse, out), nprocs=world, join=True)
