@@ -6,7 +6,6 @@
 import ctypes as C
 import os
 import sys
-import time
 
 import numpy as np
 import torch

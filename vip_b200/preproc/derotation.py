@@ -10,7 +10,6 @@ import torch
 
 from .. import kernels
 from .._device import to_device_f32, to_host
-from ..var.coords import frame_center
 
 
 def _center1d(n):
