@@ -1,0 +1,137 @@
+"""TEST INFRASTRUCTURE: a CPU stand-in for the ``vb_*`` kernels, so that the HOST orchestration of the drop-in
+callables (argument parsing, branch selection, library bookkeeping, return layouts) can be exercised in the build
+container, which has no GPU.  Every function mirrors the contract of its namesake in ``vip_b200/kernels.py`` with
+plain torch-CPU / numpy arithmetic (fp64 where the kernels accumulate in fp64) or the oracle's restatement.
+
+Only tests install it (``install(monkeypatch)``); the product never imports this module and still refuses to run
+without CUDA (``tests/test_host_logic.py::test_no_cpu_fallback_without_cuda``).  GPU parity of the real kernels is
+``tests/test_gpu_parity.py``.
+"""
+import numpy as np
+import torch
+
+from oracle import vip_oracle as O
+
+CPU = torch.device("cpu")
+
+
+def gram(M, deflate=False):
+    Md = M.double()
+    return Md @ Md.T
+
+
+def cross_gram(A, B):
+    return A.double() @ B.double().T
+
+
+def eigh(G, max_sweeps=0, tol=0.0):
+    w, v = torch.linalg.eigh(G.double())
+    w = w.abs()                                   # the one-sided Jacobi kernel returns column norms
+    order = torch.argsort(w, descending=True, stable=True)
+    return w[order].contiguous(), v[:, order].T.contiguous(), {"sweeps": 1, "converged": True}
+
+
+def eigh_topk(G, k, tol=0.0, max_iter=0):
+    w, E, _ = eigh(G)
+    return w[:k].contiguous(), E[:k].contiguous(), {"iters": 1, "converged": True}
+
+
+def topk_supported(n, k):
+    return False                                   # always the synchronous full solver: no CUDA stream needed
+
+
+def pcs(Wt, M):
+    return (Wt.double() @ M.double()).float()
+
+
+def project_subtract(M, Cm, V, out=None):
+    R = M - Cm.float() @ V
+    if out is not None:
+        out.copy_(R)
+        return out
+    return R
+
+
+def sub(a, b):
+    return a - b
+
+
+def derotate(cube, krot, a, b, S, N, y0, mask_val=float("nan"), zero_masked=False, force_direct=False,
+             scratch_max=None):
+    """Rotation from the per-frame scalars: angle = 90 krot + residual, residual = -asin(b) (b = -sin(residual))."""
+    arr = cube.numpy()
+    out = np.empty_like(arr)
+    for i in range(arr.shape[0]):
+        angle = 90.0 * int(krot[i]) + float(np.rad2deg(-np.arcsin(b[i])))
+        out[i] = O.frame_rotate(arr[i], angle, mask_val=mask_val, interp_zeros=bool(zero_masked))
+    return torch.from_numpy(out)
+
+
+def collapse(cube2d, mode="median", w=None, trim_k=0, trim_n=0):
+    import warnings
+    a = cube2d.numpy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if mode == "median":
+            r = np.nanmedian(a, axis=0)
+        elif mode == "mean":
+            r = np.nanmean(a, axis=0)
+        elif mode == "sum":
+            r = np.nansum(a, axis=0)
+        elif mode == "max":
+            r = np.nanmax(a, axis=0)
+        elif mode == "absmean":
+            r = np.nanmean(np.abs(a), axis=0)
+        elif mode == "wmean":
+            r = np.inner(np.asarray(w, dtype=np.float64), np.moveaxis(np.nan_to_num(a).astype(np.float64), 0, -1))
+        elif mode == "trimmean":
+            r = np.nanmean(np.sort(a, axis=0)[trim_k:trim_k + trim_n], axis=0)
+        else:
+            raise KeyError(mode)
+    return torch.from_numpy(np.ascontiguousarray(r))
+
+
+def upload_and_gram(host2d, device, nslabs=8):
+    M = torch.from_numpy(np.array(host2d, dtype=np.float32, copy=True))
+    return M, gram(M)
+
+
+def upload_columns(host2d, c0, c1, device):
+    return torch.from_numpy(np.ascontiguousarray(host2d[:, c0:c1]))
+
+
+def gather_columns(M, cols):
+    return M[:, cols.long()].contiguous()
+
+
+def scatter_columns(src, cols, dst):
+    dst[:, cols.long()] = src
+    return dst
+
+
+def gemm(A, B, C, trans_b=False, alpha=1.0, beta=0.0, a_mod=0, b_mod=0):
+    for i in range(C.shape[0]):
+        a = A[i % a_mod if a_mod else i]
+        b = B[i % b_mod if b_mod else i]
+        prod = a.double() @ (b.double().T if trans_b else b.double())
+        C[i] = (alpha * prod + beta * C[i].double()).float()
+    return C
+
+
+_NAMES = ("gram", "cross_gram", "eigh", "eigh_topk", "topk_supported", "pcs", "project_subtract", "sub", "derotate",
+          "collapse", "upload_and_gram", "upload_columns", "gather_columns", "scatter_columns", "gemm")
+
+
+def install(monkeypatch):
+    """Route ``vip_b200`` through the stand-ins above for the duration of one test."""
+    import vip_b200
+    from vip_b200 import kernels, _device
+    from vip_b200.psfsub import pca_fullfr, annular, sdi
+    g = globals()
+    for name in _NAMES:
+        monkeypatch.setattr(kernels, name, g[name])
+    monkeypatch.setattr(_device, "require_cuda", lambda: CPU)
+    for mod in (pca_fullfr, annular, sdi):
+        if hasattr(mod, "require_cuda"):
+            monkeypatch.setattr(mod, "require_cuda", lambda: CPU)
+    return vip_b200

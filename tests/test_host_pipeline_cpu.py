@@ -1,0 +1,107 @@
+"""Host orchestration of the drop-in callables on CPU: ``vip_b200.pca`` / ``median_sub`` / ``cube_derotate`` /
+``cube_collapse`` run end to end with the kernels replaced by the CPU stand-ins of ``tests/kernel_double.py`` and
+are compared with the golden outputs of the unmodified reference and with the oracle.  This pins everything that
+is NOT a kernel -- parameter parsing, branch selection, scaling / masking / library assembly, return layouts and
+dtypes -- in the container that has no GPU; the kernels themselves are pinned on the GPU (test_gpu_parity.py).
+"""
+import numpy as np
+import pytest
+
+import kernel_double
+from oracle import vip_oracle as O
+from tools.synth import adi_cube
+from conftest import rel_err
+
+TOL = 2e-5       # stand-ins are fp64-accurate; the slack is the reference's own fp32 arithmetic
+
+
+@pytest.fixture
+def vb(monkeypatch):
+    return kernel_double.install(monkeypatch)
+
+
+def test_pca_c1_layouts_and_values(vb, golden, golden_inputs):
+    g = golden["pca_fullframe"]
+    cube, angs = golden_inputs["c1"]
+    fr, pcs, recon, res, res_ = vb.pca(cube, angs, ncomp=5, verbose=False, full_output=True)
+    assert fr.dtype == np.float32 and fr.shape == (101, 101)
+    assert pcs.shape == (5, 101, 101) and recon.shape == res.shape == res_.shape == cube.shape
+    scale = np.max(np.abs(g["c1_res_frame7"]))
+    assert np.max(np.abs(res[7] - g["c1_res_frame7"])) < 1e-4 * scale
+    assert np.max(np.abs(res_[7] - g["c1_resder_frame7"])) < 1e-4 * scale
+    assert rel_err(fr, g["c1_frame"]) < 3e-4
+    P = pcs.reshape(5, -1)
+    assert np.max(np.abs((P.T @ P)[::97, ::89] - g["c1_proj"])) < 1e-5
+    assert rel_err(vb.pca(cube, angs, ncomp=5, verbose=False), g["c1_frame"]) < 3e-4
+
+
+def test_pca_options(vb, golden, golden_inputs):
+    g = golden["pca_fullframe"]
+    cube, angs = golden_inputs["small"]
+    for mode in ("lapack", "eigen", "arpack"):
+        assert rel_err(vb.pca(cube, angs, ncomp=4, svd_mode=mode, verbose=False), g["small_lapack"]) < 3e-4
+    for sc in ("temp-mean", "spat-mean", "temp-standard", "spat-standard"):
+        assert rel_err(vb.pca(cube, angs, ncomp=3, scaling=sc, verbose=False), g[f"small_{sc}"]) < 3e-4, sc
+    for col in ("mean", "sum"):
+        assert rel_err(vb.pca(cube, angs, ncomp=3, collapse=col, verbose=False), g[f"small_{col}"]) < 3e-4
+    ref = adi_cube(20, 41, 4, 60.0, seed=6)[0]
+    c64, r64 = cube.astype(np.float64), ref.astype(np.float64)
+    assert rel_err(vb.pca(cube, angs, cube_ref=ref, ncomp=4, verbose=False),
+                   O.pca_fullframe(c64, angs, ncomp=4, cube_ref=r64)) < 1e-4
+    assert rel_err(vb.pca(cube, angs, cube_ref=ref, ncomp=4, ref_strategy="ARDI", verbose=False),
+                   O.pca_fullframe(c64, angs, ncomp=4, cube_ref=np.concatenate((c64, r64)))) < 1e-4
+    assert rel_err(vb.pca(cube, angs, ncomp=0.9995, verbose=False), g["small_cevr"]) < 3e-4
+    fr = vb.pca(cube, angs, None, None, 4, "lapack", verbose=False)          # positional, dataclass order
+    assert rel_err(fr, g["small_lapack"]) < 3e-4
+    from vip_b200.psfsub import PCA_Params
+    fr = vb.pca(algo_params=PCA_Params(cube=cube, angle_list=angs, ncomp=4, verbose=False))
+    assert rel_err(fr, g["small_lapack"]) < 3e-4
+
+
+def test_pca_mask_sig_grid_4d(vb, golden, golden_inputs):
+    cube, angs = golden_inputs["small"]
+    assert rel_err(vb.pca(cube, angs, ncomp=3, mask_center_px=4, verbose=False),
+                   O.pca_fullframe(cube, angs, ncomp=3, mask_center_px=4)) < 3e-4
+    sig = np.zeros_like(cube)
+    sig[:, 30:34, 20:24] = 5.0
+    assert rel_err(vb.pca(cube, angs, ncomp=3, cube_sig=sig, verbose=False),
+                   O.pca_fullframe(cube, angs, ncomp=3, cube_sig=sig)) < 3e-4
+    g = golden["pca_grid4d"]
+    fr, pcl = vb.pca(cube, angs, ncomp=(1, 4), verbose=False, full_output=True)
+    assert pcl == list(g["grid_range_pclist"]) and fr.dtype == np.float32
+    for i in range(len(pcl)):
+        assert rel_err(fr[i], g["grid_range"][i]) < 3e-4, i
+    assert rel_err(vb.pca(cube, angs, ncomp=[2, 4], verbose=False), g["grid_list"]) < 3e-4
+    assert rel_err(vb.pca(cube, angs, ncomp=(1, 5, 2), med_of_npcs=True, verbose=False), g["grid_step_med"]) < 3e-4
+    cube4, angs4, _ = golden_inputs["ifs"]
+    r = vb.pca(cube4, angs4, ncomp=2, verbose=False, full_output=True)
+    assert len(r) == 6 and r[0].dtype == np.float64 and r[5].dtype == np.float64 and r[1].dtype == np.float32
+    assert rel_err(r[0], g["ch_frame"]) < 3e-4 and rel_err(r[5], g["ch_ifs"]) < 3e-4
+    final, pcl4, ifs = vb.pca(cube4, angs4, ncomp=[1, 3], verbose=False, full_output=True)
+    assert pcl4 == [[1, 3]] * 6
+    assert rel_err(final, g["ch_grid"]) < 3e-4 and rel_err(ifs, g["ch_grid_ifs"]) < 3e-4
+
+
+def test_pca_errors_and_clamp(vb):
+    cube, angs = adi_cube(8, 16, 2, 30.0, seed=1)
+    with pytest.raises(ValueError):
+        vb.pca(cube, angs[:-1], ncomp=2, verbose=False)
+    with pytest.raises(ValueError):
+        vb.pca(cube, angs, ncomp=0, verbose=False)
+    assert vb.pca(cube, angs, ncomp=50, verbose=False).shape == (16, 16)
+
+
+def test_derotate_collapse_median_sub(vb, golden, golden_inputs):
+    cube, angs = golden_inputs["derot33"]
+    out = vb.cube_derotate(cube, angs)
+    assert out.dtype == cube.dtype and rel_err(out, golden["derotate"]["derot33"]) < TOL
+    small = golden_inputs["small"][0].copy()
+    small[3, 5, 5] = np.nan
+    small[:, 7, 7] = np.nan
+    for m in ("median", "mean", "sum", "max", "absmean"):
+        np.testing.assert_array_equal(vb.cube_collapse(small, m), golden["collapse"][m], err_msg=m)
+    cube, angs = golden_inputs["small"]
+    co, cd, fr = vb.median_sub(cube, angs, full_output=True, verbose=False)
+    oo, od, of = O.median_sub_fullframe(cube, angs, full_output=True)
+    np.testing.assert_array_equal(co, oo)
+    assert rel_err(cd, od) < TOL and rel_err(fr, of) < TOL
