@@ -131,6 +131,7 @@ def install(monkeypatch):
     for name in _NAMES:
         monkeypatch.setattr(kernels, name, g[name])
     monkeypatch.setattr(_device, "require_cuda", lambda: CPU)
+    monkeypatch.setattr(_device, "free_memory_bytes", lambda: 8 << 30)
     for mod in (pca_fullfr, annular, sdi):
         if hasattr(mod, "require_cuda"):
             monkeypatch.setattr(mod, "require_cuda", lambda: CPU)

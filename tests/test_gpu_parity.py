@@ -996,3 +996,32 @@ def test_pca_left_eigv_golden(vb, golden, golden_inputs):
                   lambda: O.pca_fullframe(c64, angs, ncomp=3, left_eigv=True, scaling="spat-mean"), FRAME_TOL)
     with pytest.raises(NotImplementedError):
         vb.pca(cube, angs, ncomp=3, left_eigv=True, mask_center_px=3, verbose=False)
+
+
+# ------------------------------------------------------------------ incremental PCA
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent: the orchestration is "
+                   "verified on CPU against the same goldens with the kernel stand-ins "
+                   "(tests/test_host_pipeline_cpu.py), every kernel it calls is covered above; first hardware run "
+                   "is the round-end one")
+def test_pca_incremental_golden(vb, golden, golden_inputs):
+    """``pca(..., batch=...)``: mini-batch PCA streamed through the GPU against the reference's outputs."""
+    from tools.make_golden import INCREMENTAL_CASES
+    g = golden["pca_incremental"]
+    cube, angs = golden_inputs["small"]
+    c64 = cube.astype(np.float64)
+    for key, kw in INCREMENTAL_CASES.items():
+        fr, pcs, med = vb.pca(cube, angs, verbose=False, full_output=True, **kw)
+        assert fr.dtype == np.float64 and pcs.shape == g[f"{key}_pcs"].shape
+        okw = dict(kw)
+        b = okw.pop("batch")
+        # scikit-learn factorises the FIRST batch in float32 (sgesdd), so the reference itself sits ~2e-4 of the
+        # frame maximum away from the same algorithm in float64: usual parity rule (within tol of the reference,
+        # or at least as close to the float64 truth as the reference is)
+        assert_parity(med, g[f"{key}_medians"], lambda: O.pca_incremental(c64, angs, b, full_output=True, **okw)[2],
+                      PCA_TOL, key + " batch frames")
+        assert_parity(fr, g[f"{key}_frame"], lambda: O.pca_incremental(c64, angs, b, **okw), FRAME_TOL, key)
+        assert np.max(np.abs(pcs - g[f"{key}_pcs"])) < 1e-4 * np.max(np.abs(g[f"{key}_pcs"])), key
+    big, bangs = adi_cube(120, 64, 8, 80.0, seed=77)                  # top-k solver on the stacked matrix
+    fr = vb.pca(big, bangs, ncomp=8, batch=50, verbose=False)
+    assert_parity(fr, O.pca_incremental(big, bangs, 50, ncomp=8),
+                  lambda: O.pca_incremental(big.astype(np.float64), bangs, 50, ncomp=8), FRAME_TOL, "120 frames")

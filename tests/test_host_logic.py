@@ -54,7 +54,9 @@ def test_pca_validation_errors_before_any_gpu_work():
     with pytest.raises(NotImplementedError):
         vip_b200.pca(cube, angs, imlib="opencv")
     with pytest.raises(NotImplementedError):
-        vip_b200.pca(cube, angs, batch=2)
+        vip_b200.pca(np.zeros((2, 5, 8, 8), np.float32), angs, batch=2)      # incremental PCA: 3-d cubes only
+    with pytest.raises(ValueError):
+        vip_b200.pca(cube, angs, batch=2, cube_ref=cube)                     # "RDI not compatible with batch mode"
     with pytest.raises(TypeError):
         vip_b200.pca(cube, angs, cube_ref=cube, ref_strategy="XYZ")
     with pytest.raises(TypeError):

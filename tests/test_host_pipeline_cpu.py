@@ -105,3 +105,39 @@ def test_derotate_collapse_median_sub(vb, golden, golden_inputs):
     oo, od, of = O.median_sub_fullframe(cube, angs, full_output=True)
     np.testing.assert_array_equal(co, oo)
     assert rel_err(cd, od) < TOL and rel_err(fr, of) < TOL
+
+
+def test_pca_incremental_vs_oracle(vb):
+    """``pca(..., batch=...)``: the mini-batch model (mean update, stacked-matrix SVD through the Gramian route,
+    sign convention), the second pass and the median of the batch frames, against the oracle (= scikit-learn's
+    IncrementalPCA, bit-identical to the reference: tests/test_oracle_vs_reference.py)."""
+    cube, angs = adi_cube(23, 33, 3, 60.0, seed=11)
+    for batch in (6, 10, 23):
+        fr, pcs, med = vb.pca(cube, angs, ncomp=3, batch=batch, verbose=False, full_output=True)
+        ofr, opcs, omed = O.pca_incremental(cube, angs, batch, ncomp=3, full_output=True)
+        assert fr.dtype == pcs.dtype == med.dtype == np.float64
+        assert fr.shape == ofr.shape and pcs.shape == opcs.shape and med.shape == omed.shape
+        assert rel_err(med, omed) < 1e-4, batch
+        assert rel_err(fr, ofr) < 3e-4, batch          # frame ~1e-3 of the batch frames: fp32 residuals vs float64
+        assert np.max(np.abs(pcs - opcs)) < 1e-4 * np.max(np.abs(opcs)), batch     # same signs (svd_flip rule)
+    assert rel_err(vb.pca(cube, angs, ncomp=2, batch=8, collapse="mean", verbose=False),
+                   O.pca_incremental(cube, angs, 8, ncomp=2, collapse="mean")) < 1e-4
+    assert vb.pca(cube, angs, ncomp=2, batch=0.5, verbose=False).shape == (33, 33)     # memory-sized: one batch
+    res = vb.psfsub.pca_incremental(cube, angs, batch=7, ncomp=3, verbose=False, return_residuals=True)
+    assert rel_err(res, O.pca_incremental(cube, angs, 7, ncomp=3, return_residuals=True)) < 1e-4
+    with pytest.raises(ValueError):
+        vb.pca(cube, angs, ncomp=3, batch=2, verbose=False)            # first batch smaller than ncomp
+    with pytest.raises(ValueError):
+        vb.pca(cube, angs, cube_ref=cube, ncomp=3, batch=6, verbose=False)
+    with pytest.raises(TypeError):
+        vb.pca(cube, angs, ncomp=3, batch="6", verbose=False)
+
+
+def test_pca_incremental_golden(vb, golden, golden_inputs):
+    from tools.make_golden import INCREMENTAL_CASES
+    g = golden["pca_incremental"]
+    cube, angs = golden_inputs["small"]
+    for key, kw in INCREMENTAL_CASES.items():
+        fr, pcs, med = vb.pca(cube, angs, verbose=False, full_output=True, **kw)
+        assert rel_err(med, g[f"{key}_medians"]) < 1e-4 and rel_err(fr, g[f"{key}_frame"]) < 3e-4, key
+        assert np.max(np.abs(pcs - g[f"{key}_pcs"])) < 1e-4 * np.max(np.abs(g[f"{key}_pcs"])), key

@@ -79,3 +79,19 @@ def test_shift_and_median_sub_bit_identical(ref):
         o = O.median_sub_fullframe(cube, angs, full_output=True, **kw)
         for x, y in zip(r, o):
             np.testing.assert_array_equal(x, y)
+
+
+def test_pca_incremental_bit_identical(ref):
+    """``pca(..., batch=...)`` (incremental PCA, utils_pca.py:431-614): frame, PCs and per-batch frames."""
+    psfsub, _ = ref
+    cube, angs = adi_cube(23, 33, 3, 60.0, seed=11)
+    for batch in (6, 23, 10):
+        r = psfsub.pca(cube, angs, ncomp=3, batch=batch, verbose=False, full_output=True)
+        o = O.pca_incremental(cube, angs, batch, ncomp=3, full_output=True)
+        assert len(r) == len(o) == 3
+        for a, b in zip(r, o):
+            np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(psfsub.pca(cube, angs, ncomp=2, batch=8, collapse="mean", verbose=False),
+                                  O.pca_incremental(cube, angs, 8, ncomp=2, collapse="mean"))
+    with pytest.raises(ValueError):
+        O.pca_incremental(cube, angs, 2, ncomp=3)          # first batch smaller than ncomp (scikit-learn's check)

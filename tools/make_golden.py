@@ -125,6 +125,7 @@ def main():
     make_shift_medsub(inp)
     make_source_xy(inp, pca)
     make_grid_4d(inp, pca)
+    make_incremental(inp, pca)
     make_sdi_single(inp, pca)
     make_annular_4d(inp, pca_annular)
     for f in sorted(os.listdir(OUT)):
@@ -191,6 +192,19 @@ def make_source_xy(inp, pca):
     np.savez_compressed(os.path.join(OUT, "pca_source_xy.npz"), **out)
 
 
+INCREMENTAL_CASES = {"b12": dict(batch=12, ncomp=4), "b17_mean": dict(batch=17, ncomp=3, collapse="mean")}
+
+
+def make_incremental(inp, pca):
+    """pca(..., batch=...): incremental PCA in mini-batches (scikit-learn IncrementalPCA), median of batch frames."""
+    cube, angs = inp["small"]
+    out = {}
+    for key, kw in INCREMENTAL_CASES.items():
+        fr, pcs, med = pca(cube, angs, verbose=False, full_output=True, **kw)
+        out[f"{key}_frame"], out[f"{key}_pcs"], out[f"{key}_medians"] = fr, pcs, med
+    np.savez_compressed(os.path.join(OUT, "pca_incremental.npz"), **out)
+
+
 def make_annular_4d(inp, pca_annular):
     """pca_annular on a 4-d cube without scale_list (per-channel annular ADI + collapse_ifs)."""
     cube4, angs4, _ = inp["ifs"]
@@ -245,6 +259,10 @@ if __name__ == "__main__":
         ref_loader.load()
         from vip_hci.psfsub import pca as _pca
         make_left_eigv(golden_inputs(), _pca)
+    elif len(sys.argv) > 1 and sys.argv[1] == "incremental":
+        ref_loader.load()
+        from vip_hci.psfsub import pca as _pca
+        make_incremental(golden_inputs(), _pca)
     elif len(sys.argv) > 1 and sys.argv[1] == "source_xy":
         ref_loader.load()
         from vip_hci.psfsub import pca as _pca

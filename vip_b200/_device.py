@@ -9,6 +9,12 @@ def require_cuda():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def free_memory_bytes():
+    """Free device memory in bytes (sizing of mini-batches that must fit in HBM)."""
+    require_cuda()
+    return int(torch.cuda.mem_get_info()[0])
+
+
 def stream_ptr():
     return int(torch.cuda.current_stream().cuda_stream)
 

@@ -580,7 +580,21 @@ def pca(*all_args: List, **all_kwargs: dict):
         raise TypeError(msg.format(p.ref_strategy))
 
     if p.batch is not None:
-        _unsupported("incremental PCA (`batch`)")
+        # incremental PCA in mini-batches (pca_fullfr.py:838-856 -> utils_pca.py:431-614)
+        if isinstance(p.cube, str):
+            _unsupported("`batch` with a FITS path (FITS I/O is outside the hot path)")
+        if p.scale_list is not None or p.cube.ndim == 4:
+            _unsupported("`batch` with 4-d / ADI+mSDI cubes")
+        if p.cube_ref is not None:
+            raise ValueError("RDI not compatible with batch mode")
+        from .incremental import pca_incremental
+        res = pca_incremental(p.cube, p.angle_list, batch=p.batch, ncomp=p.ncomp, collapse=p.collapse,
+                              verbose=p.verbose, full_output=p.full_output, weights=p.weights, nproc=p.nproc,
+                              imlib=p.imlib, interpolation=p.interpolation, **rot_options)
+        if p.full_output:
+            frame, _, pcs, medians = res
+            return frame, pcs, medians                                                  # pca_fullfr.py:762-763
+        return res
     if p.scale_list is not None:
         return _pca_adimsdi(p, rot_options)
     if p.cube.ndim == 4:
