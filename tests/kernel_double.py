@@ -114,11 +114,26 @@ def gemm(A, B, C, trans_b=False, alpha=1.0, beta=0.0, a_mod=0, b_mod=0):
         a = A[i % a_mod if a_mod else i]
         b = B[i % b_mod if b_mod else i]
         prod = a.double() @ (b.double().T if trans_b else b.double())
-        C[i] = (alpha * prod + beta * C[i].double()).float()
+        C[i] = (alpha * prod + (beta * C[i].double() if beta != 0.0 else 0.0)).float()   # beta = 0: C is not read
     return C
 
 
-_NAMES = ("gram", "cross_gram", "eigh", "eigh_topk", "topk_supported", "pcs", "project_subtract", "sub", "derotate",
+def annular_weights(G, idx, lens, frames, ncomp, tol=0.0, max_iter=40, direct_fallback=True, force_direct=False):
+    """Per-problem projection weights from the library Gramian (contract of ``kernels.annular_weights``):
+    W[q, I] = X diag(1/theta) X^T G[I, frame_q] with (theta, X) the leading eigenpairs of G[I, I]."""
+    Gn = G.double().numpy()
+    nprob = idx.shape[0]
+    W = np.zeros((nprob, Gn.shape[0]), dtype=np.float32)
+    for q in range(nprob):
+        I = idx[q, :int(lens[q])].numpy().astype(np.int64)
+        w_, v_ = np.linalg.eigh(Gn[np.ix_(I, I)])
+        kk = min(int(ncomp), len(I))
+        X, th = v_[:, ::-1][:, :kk], w_[::-1][:kk]
+        W[q, I] = X @ ((X.T @ Gn[I, int(frames[q])]) / th)
+    return torch.from_numpy(W), torch.ones(nprob, dtype=torch.int32)
+
+
+_NAMES = ("annular_weights", "gram", "cross_gram", "eigh", "eigh_topk", "topk_supported", "pcs", "project_subtract", "sub", "derotate",
           "collapse", "upload_and_gram", "upload_columns", "gather_columns", "scatter_columns", "gemm")
 
 

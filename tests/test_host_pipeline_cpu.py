@@ -141,3 +141,53 @@ def test_pca_incremental_golden(vb, golden, golden_inputs):
         fr, pcs, med = vb.pca(cube, angs, verbose=False, full_output=True, **kw)
         assert rel_err(med, g[f"{key}_medians"]) < 1e-4 and rel_err(fr, g[f"{key}_frame"]) < 3e-4, key
         assert np.max(np.abs(pcs - g[f"{key}_pcs"])) < 1e-4 * np.max(np.abs(g[f"{key}_pcs"])), key
+
+
+def test_pca_annular_layouts_and_values(vb, golden, golden_inputs):
+    g = golden["pca_annular"]
+    cube, angs = golden_inputs["ann"]
+    co, cd, fr = vb.pca_annular(cube, angs, ncomp=3, asize=6, verbose=False, full_output=True)
+    assert co.shape == cd.shape == cube.shape and co.dtype == np.float32
+    scale = np.max(np.abs(g["ann_cube_out5"]))
+    assert np.max(np.abs(co[5] - g["ann_cube_out5"])) < 1e-4 * scale
+    assert rel_err(fr, g["ann_frame"]) < 3e-4
+    fr = vb.pca_annular(cube, angs, ncomp=2, asize=6, n_segments=3, delta_rot=0.5, radius_int=4, verbose=False)
+    assert rel_err(fr, g["ann_seg_frame"]) < 3e-4
+    co4, cd4, frl = vb.pca_annular(cube, angs, ncomp=[1, 3], asize=6, verbose=False, full_output=True)
+    assert co4.shape == (2,) + cube.shape and co4.dtype == np.float64 and isinstance(frl, list) and len(frl) == 2
+    for i in range(2):
+        assert rel_err(frl[i], g["ann_list_frames"][i]) < 3e-4
+    ref = adi_cube(12, 48, 3, 80.0, seed=10)[0]
+    sig = np.zeros_like(cube)
+    sig[:, 30:33, 10:13] = 4.0
+    for kw in (dict(ncomp=(1, 2, 3, 2), asize=6), dict(ncomp=2, asize=6, cube_sig=sig), dict(ncomp=2, asize=6, cube_ref=ref),
+               dict(ncomp=2, asize=6, scaling="temp-mean"), dict(ncomp=2, asize=8, max_frames_lib=12)):
+        o = O.pca_annular(cube, angs, full_output=True, **kw)
+        r = vb.pca_annular(cube, angs, full_output=True, verbose=False, **kw)
+        assert np.max(np.abs(r[0] - o[0])) < 1e-4 * np.max(np.abs(o[0])), kw
+        assert rel_err(r[2], o[2]) < 3e-4, kw
+    with pytest.raises(TypeError):
+        vb.pca_annular(cube, angs[:-1], ncomp=2, asize=6, verbose=False)
+    with pytest.raises(RuntimeError):
+        vb.pca_annular(cube, angs, ncomp=2, asize=6, delta_rot=500, verbose=False)
+    g4 = golden["pca_annular_4d"]
+    cube4, angs4, _ = golden_inputs["ifs"]
+    co, cd, fr = vb.pca_annular(cube4[:3], angs4, ncomp=2, asize=5, delta_rot=(0.05, 0.2), verbose=False, full_output=True)
+    assert co.dtype == np.float32 and fr.dtype == np.float64 and rel_err(fr, g4["ann4d_frame"]) < 3e-4
+
+
+def test_pca_sdi_layouts_and_values(vb, golden, golden_inputs):
+    g = golden["pca_sdi"]
+    cube, angs, sl = golden_inputs["ifs"]
+    tol = 5e-6 * float(np.max(np.abs(cube)))
+    fr, rc, rd = vb.pca(cube, angs, scale_list=sl, adimsdi="double", ncomp=(2, 3), verbose=False, full_output=True)
+    assert fr.dtype == np.float64 and rc.shape == (cube.shape[1],) + cube.shape[2:]
+    assert np.max(np.abs(rc - g["double_res_channels"])) < tol and np.max(np.abs(fr - g["double_frame"])) < tol
+    fr = vb.pca(cube, angs, scale_list=sl, adimsdi="double", ncomp=(2, None), verbose=False)
+    assert np.max(np.abs(fr - g["double_skipadi"])) < tol
+    with pytest.raises(TypeError):
+        vb.pca(cube, angs, scale_list=sl, adimsdi="double", ncomp=3, verbose=False)
+    gs = golden["pca_sdi_single"]
+    fr, allfr, desc, resadi = vb.pca(cube, angs, scale_list=sl, adimsdi="single", ncomp=3, verbose=False, full_output=True)
+    assert fr.dtype == np.float64 and allfr.shape == (84, 32, 32) and desc.shape == cube.shape
+    assert np.max(np.abs(desc[2] - gs["single_desc_ch2"])) < tol and np.max(np.abs(fr - gs["single_frame"])) < tol
