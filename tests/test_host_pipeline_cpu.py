@@ -191,3 +191,24 @@ def test_pca_sdi_layouts_and_values(vb, golden, golden_inputs):
     fr, allfr, desc, resadi = vb.pca(cube, angs, scale_list=sl, adimsdi="single", ncomp=3, verbose=False, full_output=True)
     assert fr.dtype == np.float64 and allfr.shape == (84, 32, 32) and desc.shape == cube.shape
     assert np.max(np.abs(desc[2] - gs["single_desc_ch2"])) < tol and np.max(np.abs(fr - gs["single_frame"])) < tol
+
+
+def test_pca_source_xy_and_left_eigv(vb, golden, golden_inputs):
+    """Frame-by-frame PCA with PA-rejection libraries (one Gramian, per-frame sub-problems) and ``left_eigv``."""
+    from tools.make_golden import SOURCE_XY_CASES
+    g = golden["pca_source_xy"]
+    cube, angs = golden_inputs["small"]
+    ref = adi_cube(20, 41, 4, 60.0, seed=6)[0]
+    for key, kw in SOURCE_XY_CASES.items():
+        extra = dict(cube_ref=ref) if key == "rdi" else {}
+        fr, recon, res, res_ = vb.pca(cube, angs, verbose=False, full_output=True, **kw, **extra)
+        assert fr.dtype == np.float32 and recon.shape == cube.shape and res_.shape == cube.shape
+        assert rel_err(res, g[f"{key}_res"]) < 1e-4, key
+        c64 = cube.astype(np.float64)
+        e64 = {k: v.astype(np.float64) for k, v in extra.items()}
+        truth = O.pca_fullframe(c64, angs, **kw, **e64)
+        assert rel_err(fr, g[f"{key}_frame"]) < 3e-4 or rel_err(fr, truth) < 1.5 * rel_err(g[f"{key}_frame"], truth) + 2e-5
+    gl = golden["pca_left_eigv"]
+    fr, pcs, recon, res, _ = vb.pca(cube, angs, ncomp=4, left_eigv=True, verbose=False, full_output=True)
+    assert pcs.shape == gl["left_pcs"].shape
+    assert rel_err(res, gl["left_res"]) < 1e-4 and rel_err(fr, gl["left_frame"]) < 3e-4
