@@ -109,6 +109,35 @@ def _worker(rank, world, port, collapse, out):
         dist.destroy_process_group()
 
 
+def _worker_shard(rank, world, port, out):
+    """Every rank hands over only its own pixel shard (no rank ever sees the whole cube in pca_sharded)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        NumpyOps.stall_once = False
+        cube, angs = adi_cube(11, 20, 3, 70.0, seed=2)
+        pb = shard_bounds(400, world)
+        mine = np.ascontiguousarray(cube.reshape(11, 400)[:, pb[rank]:pb[rank + 1]])
+        frame = pca_sharded(None, angs, 3, ops=NumpyOps(), device=torch.device("cpu"), host_shard=mine,
+                            shape=cube.shape)
+        if rank == 0:
+            np.save(out, frame)
+        with pytest.raises(ValueError):
+            pca_sharded(None, angs, 3, ops=NumpyOps(), device=torch.device("cpu"), host_shard=mine[:, :-1],
+                        shape=cube.shape)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_pca_from_host_shards(tmp_path):
+    out = str(tmp_path / "frame.npy")
+    mp.spawn(_worker_shard, args=(3, _free_port(), out), nprocs=3, join=True)
+    cube, angs = adi_cube(11, 20, 3, 70.0, seed=2)
+    ref = O.pca_fullframe(cube, angs, ncomp=3)
+    assert np.max(np.abs(np.load(out) - ref)) < 3e-4 * np.max(np.abs(ref))
+
+
 @pytest.mark.parametrize("world,collapse", [(2, "median"), (3, "mean"), (8, "median")])
 def test_sharded_pca_matches_single_process(tmp_path, world, collapse):
     out = str(tmp_path / "frame.npy")

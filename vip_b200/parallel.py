@@ -173,7 +173,8 @@ def _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, o
 
 
 def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None, device=None,
-                full_output=False, resident_shard=None, svd_mode="lapack", random_state=None, _defer_check=True):
+                full_output=False, resident_shard=None, svd_mode="lapack", random_state=None, _defer_check=True,
+                host_shard=None, shape=None):
     """Full-frame ADI PCA of ONE cube, sharded over the ranks of ``group``.
 
     ``cube`` (n,H,W) is the host array, visible on every rank (each rank uploads only its pixel
@@ -186,12 +187,22 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
     (BASELINE config 5): scikit-learn's randomized SVD on pixel shards, whose only communication is
     the all-reduce of the (ncomp+10) x n sketches and (ncomp+10)^2 Gramians
     (``psfsub.svd.randomized_pcs``); the Gaussian test matrix is drawn on rank 0 from
-    ``random_state`` (default: numpy's global RandomState, as the reference does) and broadcast."""
-    if cube.ndim != 3:
-        raise TypeError("Input array is not a cube or 3d array")
+    ``random_state`` (default: numpy's global RandomState, as the reference does) and broadcast.
+
+    ``host_shard`` + ``shape``: for cubes that no single host buffer should hold (BASELINE config 5 is 16.8 GB),
+    every rank may pass ONLY its own pixel shard -- a C-contiguous fp32 (n, p_g) host array with
+    p_g = ``shard_bounds(H*W, world)`` of this rank -- together with ``shape=(n, H, W)``; ``cube`` is then ignored
+    (pass None) and the upload is one contiguous copy."""
+    if host_shard is not None and (shape is None or len(shape) != 3):
+        raise TypeError("pca_sharded: `host_shard` needs `shape=(n, H, W)`")
+    if shape is not None and (host_shard is not None or resident_shard is not None):
+        n, H, W = (int(v) for v in shape)
+    else:
+        if cube.ndim != 3:
+            raise TypeError("Input array is not a cube or 3d array")
+        n, H, W = cube.shape
     ops = ops or CudaOps()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    n, H, W = cube.shape
     p = H * W
     angle_list = check_pa_vector(np.asarray(angle_list))
     if n != angle_list.shape[0]:
@@ -208,7 +219,14 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
     f0, f1 = int(fb[rank]), int(fb[rank + 1])
 
     # ---- pixel-sharded PCA ------------------------------------------------------------------
-    M = resident_shard if resident_shard is not None else ops.upload_pixels(cube.reshape(n, p), p0, p1, device)
+    if resident_shard is not None:
+        M = resident_shard
+    elif host_shard is not None:
+        if host_shard.shape != (n, p1 - p0) or host_shard.dtype != np.float32 or not host_shard.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"pca_sharded: rank {rank} needs a C-contiguous fp32 host shard of shape {(n, p1 - p0)}")
+        M = torch.from_numpy(host_shard).to(device, non_blocking=True)
+    else:
+        M = ops.upload_pixels(cube.reshape(n, p), p0, p1, device)
     src = dist.get_global_rank(group, 0) if group is not None else 0
     record = None
     mode = str(getattr(svd_mode, "value", svd_mode))
@@ -263,7 +281,7 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
             # rare: the subspace iteration stalled -> redo with the synchronous solver (Jacobi fallback)
             return pca_sharded(cube, angle_list, ncomp, collapse=collapse, group=group, ops=ops, device=device,
                                full_output=full_output, resident_shard=resident_shard, svd_mode=svd_mode,
-                               random_state=random_state, _defer_check=False)
+                               random_state=random_state, _defer_check=False, host_shard=host_shard, shape=shape)
     if full_output:
         return frame, der, (f0, f1)
     return frame
