@@ -20,6 +20,8 @@ The arithmetic goes through an ``ops`` object: :class:`CudaOps` (the CUDA kernel
 default.  The CPU tests of the communication logic (``tests/test_parallel_gloo.py``, gloo backend,
 world_size 2) pass a numpy test double instead -- the product never computes on the CPU.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -125,6 +127,34 @@ def _all_to_all(send, recv, group):
             r.wait()
 
 
+class _Exchange:
+    """Handle of an all-to-all in flight (``wait()`` orders the caller's stream after it)."""
+
+    def __init__(self, works):
+        self.works = works
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+
+
+def _all_to_all_async(send, recv, group):
+    """``_all_to_all`` that returns while the exchange is in flight: NCCL runs it on its own stream, ordered after
+    the work already enqueued on the caller's stream, so kernels launched afterwards overlap with the transfer."""
+    try:
+        return _Exchange([dist.all_to_all(recv, send, group=group, async_op=True)])
+    except (RuntimeError, NotImplementedError):
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        recv[rank].copy_(send[rank])
+        reqs = []
+        for peer in range(world):
+            if peer != rank:
+                g = dist.get_global_rank(group, peer) if group else peer
+                reqs.append(dist.isend(send[peer], dst=g, group=group))
+                reqs.append(dist.irecv(recv[peer], src=g, group=group))
+        return _Exchange(reqs)
+
+
 def _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, ops, device):
     """Tail of the sharded paths: this rank's residual frames ``mine`` (f1-f0, H, W) -> derotation (local) ->
     temporal collapse across the ranks.  'mean' / 'sum' are reducible (partial sums + one NCCL reduce of an
@@ -174,7 +204,7 @@ def _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, o
 
 def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None, device=None,
                 full_output=False, resident_shard=None, svd_mode="lapack", random_state=None, _defer_check=True,
-                host_shard=None, shape=None):
+                host_shard=None, shape=None, overlap_exchange=None):
     """Full-frame ADI PCA of ONE cube, sharded over the ranks of ``group``.
 
     ``cube`` (n,H,W) is the host array, visible on every rank (each rank uploads only its pixel
@@ -229,6 +259,9 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
         M = ops.upload_pixels(cube.reshape(n, p), p0, p1, device)
     src = dist.get_global_rank(group, 0) if group is not None else 0
     record = None
+    raw_exchange = None
+    if overlap_exchange is None:
+        overlap_exchange = os.environ.get("VIP_B200_SHARD_OVERLAP", "0") == "1"      # off until measured on hardware
     mode = str(getattr(svd_mode, "value", svd_mode))
     if mode in ("randsvd", "randcupy", "randpytorch"):
         def reduce(t):                                                   # exchange step 0: sketches
@@ -250,6 +283,15 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
     else:
         G = ops.gram(M)
         dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)           # exchange step 0: n x n fp64
+        if overlap_exchange:
+            # R = M - C V is row-local once V is known everywhere: the all-to-all to frame shards can move the RAW
+            # cube while the (replicated, latency-bound) eigensolver runs; V (k x p, 21 MB at config 2) is
+            # all-gathered afterwards and the subtraction happens on the frame shards.  Same kernels on the same
+            # values: bit-identical to the default order.
+            raw_send = [M[int(fb[h]):int(fb[h + 1])] for h in range(world)]          # contiguous row blocks
+            raw_recv = [torch.empty((f1 - f0, int(pb[h + 1] - pb[h])), dtype=M.dtype, device=device)
+                        for h in range(world)]
+            raw_exchange = _all_to_all_async(raw_send, raw_recv, group)
         # the convergence record of the subspace solver is read once, after the whole pipeline has been
         # enqueued (no host stall behind the eigensolver); see the check before the return
         deferred = ops.leading_eig_async(G, ncomp) if (_defer_check and hasattr(ops, "leading_eig_async")) else None
@@ -264,13 +306,29 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
         Wt = (evecs / S[:, None]).contiguous()
         Cm = (evecs * S[:, None]).t().to(torch.float32).contiguous()
         V = ops.pcs(Wt, M)
-    R = ops.project_subtract(M, Cm, V)                                   # (n, p_g)
+    if raw_exchange is not None:
+        # all-gather of the PCs (pixel shards of uneven width are padded to the widest)
+        k = V.shape[0]
+        pmax = int(np.max(np.diff(pb)))
+        padded = torch.zeros((k, pmax), dtype=V.dtype, device=device)
+        padded[:, : p1 - p0] = V
+        parts = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(parts, padded, group=group)
+        V_full = torch.cat([parts[h][:, : int(pb[h + 1] - pb[h])] for h in range(world)], dim=1).contiguous()
+        raw_exchange.wait()
+        mine_raw = torch.cat(raw_recv, dim=1).contiguous()                  # my frames, all pixels, raw
+        if f1 > f0:
+            mine = ops.project_subtract(mine_raw, Cm[f0:f1].contiguous(), V_full).reshape(f1 - f0, H, W)
+        else:
+            mine = mine_raw.reshape(0, H, W)
+    else:
+        R = ops.project_subtract(M, Cm, V)                                   # (n, p_g)
 
-    # ---- exchange 1: pixel shards -> frame shards ---------------------------------------------
-    send = [R[int(fb[h]):int(fb[h + 1])].contiguous() for h in range(world)]
-    recv = [torch.empty((f1 - f0, int(pb[h + 1] - pb[h])), dtype=R.dtype, device=device) for h in range(world)]
-    _all_to_all(send, recv, group)
-    mine = torch.cat(recv, dim=1).reshape(f1 - f0, H, W)                # my frames, all pixels
+        # ---- exchange 1: pixel shards -> frame shards ---------------------------------------------
+        send = [R[int(fb[h]):int(fb[h + 1])].contiguous() for h in range(world)]
+        recv = [torch.empty((f1 - f0, int(pb[h + 1] - pb[h])), dtype=R.dtype, device=device) for h in range(world)]
+        _all_to_all(send, recv, group)
+        mine = torch.cat(recv, dim=1).reshape(f1 - f0, H, W)                # my frames, all pixels
     frame, der = _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, ops, device)
     if record is not None:
         if device.type == "cuda":
@@ -281,7 +339,8 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
             # rare: the subspace iteration stalled -> redo with the synchronous solver (Jacobi fallback)
             return pca_sharded(cube, angle_list, ncomp, collapse=collapse, group=group, ops=ops, device=device,
                                full_output=full_output, resident_shard=resident_shard, svd_mode=svd_mode,
-                               random_state=random_state, _defer_check=False, host_shard=host_shard, shape=shape)
+                               random_state=random_state, _defer_check=False, host_shard=host_shard, shape=shape,
+                               overlap_exchange=overlap_exchange)
     if full_output:
         return frame, der, (f0, f1)
     return frame
