@@ -166,3 +166,15 @@ def test_rescaling_known_answers():
                                             y_in=y_in, x_in=x_in)
     mod.cube_rescaling_wavelengths = rescale
     _run(mod, "test_cube_rescaling_wavelengths", select=lambda a: a[0] == "vip-fft")
+
+
+def test_svd_wrapper_reference_test_through_kernel_standins(monkeypatch):
+    """tests/pre_3_10/test_pca_svd.py:10-21 (``U S V`` of the lapack mode reconstructs a 20 x 100 Gaussian matrix)
+    run verbatim against ``vip_b200.psfsub.svd_wrapper``: the host logic (mode dispatch, ``full_output`` orientation
+    of the lapack mode, dtype handling) is the product's, the kernels are the CPU stand-ins of
+    tests/kernel_double.py (their GPU parity: tests/test_gpu_parity.py)."""
+    import kernel_double
+    vb = kernel_double.install(monkeypatch)
+    mod = _load("pre_3_10/test_pca_svd.py")
+    mod.svd_wrapper = vb.psfsub.svd_wrapper
+    _run(mod, "test_svd_recons")
