@@ -212,3 +212,17 @@ def test_pca_source_xy_and_left_eigv(vb, golden, golden_inputs):
     fr, pcs, recon, res, _ = vb.pca(cube, angs, ncomp=4, left_eigv=True, verbose=False, full_output=True)
     assert pcs.shape == gl["left_pcs"].shape
     assert rel_err(res, gl["left_res"]) < 1e-4 and rel_err(fr, gl["left_frame"]) < 3e-4
+
+
+def test_pca_check_memory(vb, monkeypatch):
+    """``check_memory`` (pca_fullfr.py:438-455): an input larger than the available (device) memory raises
+    RuntimeError pointing at ``batch``; ``check_memory=False`` and ``batch`` bypass the check."""
+    from vip_b200 import _device
+    from vip_b200.psfsub import pca_fullfr
+    cube, angs = adi_cube(12, 16, 2, 40.0, seed=5)
+    monkeypatch.setattr(pca_fullfr, "_MEMCHECK_MIN_BYTES", 0)      # the query is skipped for inputs below 8 GiB
+    monkeypatch.setattr(_device, "free_memory_bytes", lambda: cube.nbytes - 1)
+    with pytest.raises(RuntimeError, match="batch"):
+        vb.pca(cube, angs, ncomp=2, verbose=False)
+    assert vb.pca(cube, angs, ncomp=2, verbose=False, check_memory=False).shape == (16, 16)
+    assert vb.pca(cube, angs, ncomp=2, batch=6, verbose=False).shape == (16, 16)

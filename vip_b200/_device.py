@@ -10,9 +10,11 @@ def require_cuda():
 
 
 def free_memory_bytes():
-    """Free device memory in bytes (sizing of mini-batches that must fit in HBM)."""
+    """Device memory this process can still use, in bytes: free at the driver plus the blocks PyTorch's caching
+    allocator holds but has not handed out (sizing of mini-batches, ``check_memory``)."""
     require_cuda()
-    return int(torch.cuda.mem_get_info()[0])
+    free = int(torch.cuda.mem_get_info()[0])
+    return free + int(torch.cuda.memory_reserved()) - int(torch.cuda.memory_allocated())
 
 
 def stream_ptr():

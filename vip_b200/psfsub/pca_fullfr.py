@@ -542,6 +542,23 @@ def _pca_adimsdi(p, rot_options):
     raise ValueError(f"ADIMSDI value should only be {Adimsdi.SINGLE} or {Adimsdi.DOUBLE}.")
 
 
+_MEMCHECK_MIN_BYTES = 8 << 30
+
+
+def _check_device_memory(p):
+    """``check_memory`` (``pca_fullfr.py:438-455``, ``config/mem.py:34-65``) against DEVICE memory: the cube (or the
+    reference cube) has to fit in HBM; larger inputs are pointed at ``batch`` (incremental PCA)."""
+    if not (p.check_memory and p.batch is None and isinstance(p.cube, np.ndarray)):
+        return
+    from .. import _device
+    input_bytes = p.cube_ref.nbytes if p.cube_ref is not None else p.cube.nbytes
+    if input_bytes < _MEMCHECK_MIN_BYTES:        # small inputs always fit: no driver query on the common path
+        return
+    if input_bytes > _device.free_memory_bytes():
+        raise RuntimeError("Input is larger than available device memory. Set check_memory=False to override "
+                           "this memory check or set `batch` to run incremental PCA (valid for ADI)")
+
+
 def pca(*all_args: List, **all_kwargs: dict):
     """Full-frame PCA speckle subtraction: drop-in for ``vip_hci.psfsub.pca``.
 
@@ -639,6 +656,7 @@ def pca(*all_args: List, **all_kwargs: dict):
             algo_params.cube_ref = cube_ref        # the reference overwrites the attribute too (:670-672)
         elif p.ref_strategy != "RDI":
             raise TypeError("ref_strategy argument not recognized.Should be 'RDI' or 'ARDI'")
+    _check_device_memory(p)
 
     if isinstance(p.ncomp, (tuple, list)):
         # PCA grid: one residual frame per number of components (pca_fullfr.py:1010-1035, returns :766-790)
