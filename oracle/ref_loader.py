@@ -8,6 +8,13 @@ vip_hci imports astropy / scikit-image / photutils / matplotlib / hciplot / ... 
 scope, none of which is installed here and none of which is *called* on the default
 ``pca`` / ``pca_annular`` / ``cube_derotate`` path.  A ``sys.meta_path`` finder serves
 empty stand-ins for exactly the top-level packages that are missing.
+
+One stand-in is not empty: ``skimage.draw.disk``, which ``var/shapes.py:88`` (``mask_circle``) calls on the
+``mask_center_px`` / ``radius_int`` paths.  scikit-image is not installed, so the loader serves scikit-image's
+published rule (``skimage/draw/draw.py`` ``ellipse`` -> ``_ellipse_in_shape``: bounding box
+ceil(c - R) .. floor(c + R) clipped to ``shape``, pixels with ((r-cy)/R)^2 + ((c-cx)/R)^2 < 1).  The resulting
+index sets are checked against the reference's own ``test_mask_circle`` known answers
+(``tests/test_reference_own_tests.py``).
 """
 import importlib.abc
 import importlib.machinery
@@ -21,6 +28,24 @@ _OPTIONAL = ["astropy", "skimage", "photutils", "matplotlib", "hciplot", "emcee"
              "corner", "dataclass_builder", "pyds9", "munch", "ultranest"]
 
 
+def _disk(center, radius, *, shape=None):
+    """scikit-image ``draw.disk`` (see the module docstring)."""
+    import numpy as np
+    center = np.array(center, dtype=float)
+    radii = np.array([radius, radius], dtype=float)
+    upper_left = np.ceil(center - radii).astype(int)
+    lower_right = np.floor(center + radii).astype(int)
+    if shape is not None:
+        upper_left = np.maximum(upper_left, np.array([0, 0]))
+        lower_right = np.minimum(lower_right, np.array(shape[:2]) - 1)
+    shifted = center - upper_left
+    bshape = lower_right - upper_left + 1
+    r_lim, c_lim = np.ogrid[0:float(bshape[0]), 0:float(bshape[1])]
+    r, c = (r_lim - shifted[0]), (c_lim - shifted[1])
+    rr, cc = np.nonzero((r / radius) ** 2 + (c / radius) ** 2 < 1)
+    return rr + upper_left[0], cc + upper_left[1]
+
+
 class _Stub(types.ModuleType):
     __path__ = []
 
@@ -28,6 +53,8 @@ class _Stub(types.ModuleType):
         if name.startswith("__"):
             raise AttributeError(name)
         modname = self.__name__
+        if modname == "skimage.draw" and name == "disk":
+            return _disk
 
         class _Missing(Warning):
             def __init__(self, *a, **k):

@@ -1,0 +1,42 @@
+"""Multi-rank NCCL parity: the sharded paths of ``vip_b200/parallel.py`` at world sizes
+2 / 4 / 8 (whatever the box has) against the single-GPU result.  Spawns ``torch.distributed.run`` with one rank per
+GPU; skipped on boxes with a single GPU (the host logic is covered under gloo in test_parallel_gloo.py)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_paths_match_single_gpu_over_nccl(world, tmp_path):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs, this box has {_ngpu()}")
+    out = tmp_path / "res.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world),
+           os.path.join(ROOT, "tests", "nccl_worker.py"), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = json.load(open(out))
+    print("[parity] NCCL world", world, json.dumps(res))
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"parity_nccl_world{world}.json"), "w") as f:
+            json.dump(res, f)
+    except OSError:
+        pass
+    assert res["world"] == world
+    for key, tol in (("exact_median", 1e-5), ("exact_mean", 1e-5), ("exact_sum", 1e-5), ("exact_max", 1e-5),
+                     ("exact_overlap_0", 1e-5), ("exact_overlap_1", 1e-5), ("exact_512", 1e-5), ("randsvd", 1e-4),
+                     ("sdi_double_median", 1e-4), ("sdi_double_mean", 1e-4)):
+        assert res[key] < tol, (key, res[key])

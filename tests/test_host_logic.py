@@ -128,3 +128,30 @@ def test_bench_reference_arm_contract():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_standard_scaling_zero_variance_rule_is_sklearns():
+    """'*-standard' scaling on low-flux data: sklearn treats a std below 10*eps(dtype) -- an ABSOLUTE threshold,
+    1.2e-6 for float32 cubes -- as zero variance and leaves the column unscaled (var/shapes.py:740-781 ->
+    sklearn.preprocessing.scale -> _handle_zeros_in_scale).  Pure torch host logic: runs on CPU tensors."""
+    import torch
+    import warnings
+    from oracle import vip_oracle as O
+    from vip_b200.psfsub.pca_fullfr import scale_matrix_device
+    rng = np.random.default_rng(3)
+    n = 40
+    M = np.empty((n, 6), dtype=np.float64)
+    for j, sd in enumerate((0.0, 1e-7, 5e-7, 3e-6, 1e-3, 2.0)):       # around the 1.19e-6 threshold
+        M[:, j] = rng.standard_normal(n) * sd
+    M32 = M.astype(np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for mode in ("temp-standard", "spat-standard", "temp-mean", "spat-mean"):
+            ref = O.matrix_scaling(M32, mode)
+            out = scale_matrix_device(torch.from_numpy(M32), mode, np.float32).numpy()
+            np.testing.assert_allclose(out, ref, rtol=2e-5, atol=1e-9)
+        # a float64 cube: the threshold follows the input dtype (2.2e-15), so the 1e-7 column IS scaled
+        ref64 = O.matrix_scaling(M, "temp-standard")
+        out64 = scale_matrix_device(torch.from_numpy(M32), "temp-standard", np.float64).numpy()
+        assert abs(np.std(ref64[:, 1]) - 1) < 1e-6 and abs(np.std(out64[:, 1]) - 1) < 1e-3
+        assert np.std(O.matrix_scaling(M32, "temp-standard")[:, 1]) < 1e-6

@@ -79,6 +79,15 @@ def test_shift_and_median_sub_bit_identical(ref):
         o = O.median_sub_fullframe(cube, angs, full_output=True, **kw)
         for x, y in zip(r, o):
             np.testing.assert_array_equal(x, y)
+    # radius_int > 0 with an ODD number of frames: np.median returns an actual sample, so one residual per pixel
+    # is exactly 0 and the reference's default rot_options (mask_val=0, interp_zeros=True; medsub.py:226-229)
+    # resets it after the rotation
+    cube, angs = adi_cube(11, 32, 3, 60.0, seed=4)
+    for kw in (dict(radius_int=3), dict(radius_int=2, collapse="mean"), dict(radius_int=3, mask_val=np.nan)):
+        r = median_sub(cube, angs, verbose=False, full_output=True, **kw)
+        o = O.median_sub_fullframe(cube, angs, full_output=True, **kw)
+        for x, y in zip(r, o):
+            np.testing.assert_array_equal(x, y)
 
 
 def test_pca_incremental_bit_identical(ref):

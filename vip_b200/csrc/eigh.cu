@@ -898,6 +898,7 @@ topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int ma
                                     u.b.Tm[i][a] = c * x - sn * y;
                                     u.b.Tm[i][b] = sn * x + c * y;
                                 }
+                                __syncwarp();          // every lane has read th[a], th[b] (racecheck, round 2)
                                 if (lane == 0) {
                                     u.b.th[a] = al - t * ga;
                                     u.b.th[b] = be + t * ga;

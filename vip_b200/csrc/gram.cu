@@ -11,6 +11,7 @@
 // callers that want it; it is not needed for accuracy any more.
 #include "common.cuh"
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 namespace vb {
@@ -390,13 +391,26 @@ int upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, voi
                     int nslabs, int* launches, cudaStream_t st) {
     VB_REQUIRE(n > 0 && p > 0, "upload_gram: empty matrix");
     VB_REQUIRE(ws_bytes >= gram_workspace_bytes(n, p), "upload_gram: workspace too small");
-    static cudaStream_t copy_stream = nullptr;
-    static cudaEvent_t ev[64], start_ev;
-    if (!copy_stream) {
-        VB_CHECK_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 64; ++i) VB_CHECK_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-        VB_CHECK_CUDA(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
+    // one private copy stream + event set PER DEVICE (a process may drive several GPUs), created under a lock
+    struct CopyCtx { cudaStream_t stream = nullptr; cudaEvent_t ev[64]; cudaEvent_t start; bool ready = false; };
+    static CopyCtx ctxs[64];
+    static std::mutex ctx_mutex;
+    int dev = 0;
+    VB_CHECK_CUDA(cudaGetDevice(&dev));
+    VB_REQUIRE(dev >= 0 && dev < 64, "upload_gram: device index %d out of range", dev);
+    CopyCtx& cx = ctxs[dev];
+    {
+        std::lock_guard<std::mutex> lock(ctx_mutex);
+        if (!cx.ready) {
+            VB_CHECK_CUDA(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 64; ++i) VB_CHECK_CUDA(cudaEventCreateWithFlags(&cx.ev[i], cudaEventDisableTiming));
+            VB_CHECK_CUDA(cudaEventCreateWithFlags(&cx.start, cudaEventDisableTiming));
+            cx.ready = true;
+        }
     }
+    cudaStream_t copy_stream = cx.stream;
+    cudaEvent_t* ev = cx.ev;
+    cudaEvent_t start_ev = cx.start;
     if (nslabs <= 0) nslabs = 8;
     if (nslabs > 64) nslabs = 64;
     if (gram_tc_eligible(n, p)) {

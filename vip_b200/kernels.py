@@ -84,8 +84,9 @@ def eigh_topk(G, k, tol=0.0, max_iter=0):
 
 def eigh_topk_async(G, k, tol=0.0, max_iter=0):
     """``eigh_topk`` without the host synchronisation.  Returns (evals, evecs, info) where ``info`` is a pinned
-    int32[2] tensor {iterations, converged} that is valid once the current stream has been synchronised;
-    the workspace is returned inside ``info.ws`` to keep it alive until then."""
+    int32[2] tensor {iterations, converged} that is valid once the current stream has been synchronised.
+    The workspace of the cooperative kernel is attached to the record (``info.ws``) so that it lives at least
+    as long as the caller holds the record, whatever stream later allocations are made on."""
     lib = _cabi.lib()
     n = G.shape[0]
     evals = empty((k,), torch.float64, G.device)
@@ -95,6 +96,7 @@ def eigh_topk_async(G, k, tol=0.0, max_iter=0):
     info = torch.zeros(2, dtype=torch.int32).pin_memory()
     _cabi.check(lib.vb_eigh_topk_async_f64(ptr(G), n, int(k), float(tol), int(max_iter), ptr(evals), ptr(evecs),
                                            ptr(ws), nb, info.data_ptr(), stream_ptr()), "vb_eigh_topk_async_f64")
+    info.ws = ws
     return evals, evecs, info
 
 

@@ -97,6 +97,11 @@ def median_sub(*all_args: List, **all_kwargs: dict):
     p = rot_options.pop(ALGO_KEY, None)
     if p is None:
         p = MEDIAN_SUB_Params(*all_args, **class_params)
+    # by default the masked centre is derotated as zeros (medsub.py:226-229)
+    if p.radius_int and len(rot_options) == 0:
+        rot_options["mask_val"] = 0
+        rot_options["ker"] = 1
+        rot_options["interp_zeros"] = True
     if not isinstance(p.cube, np.ndarray) or p.cube.ndim not in (3, 4):
         raise TypeError("Input array is not a 3d or 4d array")
     if p.cube.ndim == 4 or p.scale_list is not None:

@@ -77,10 +77,27 @@ def _unsupported(what):
 # --------------------------------------------------------------------------------------------------
 
 
-def scale_matrix_device(M, scaling):
+def _in_eps(in_dtype):
+    """10 * machine epsilon of the dtype the REFERENCE would scale in (the caller's cube dtype; integer cubes are
+    promoted to float64 by ``sklearn.preprocessing.scale``)."""
+    dt = np.dtype(in_dtype) if in_dtype is not None else np.dtype(np.float32)
+    if not np.issubdtype(dt, np.floating):
+        dt = np.dtype(np.float64)
+    return 10.0 * float(np.finfo(dt).eps)
+
+
+def _np_dtype_of(a):
+    """numpy dtype of a numpy array or torch tensor (the dtype the reference would compute in)."""
+    if isinstance(a, torch.Tensor):
+        return np.dtype(str(a.dtype).replace("torch.", ""))
+    return np.asarray(a).dtype
+
+
+def scale_matrix_device(M, scaling, in_dtype=np.float32):
     """``matrix_scaling`` (``var/shapes.py:740-781``): sklearn ``scale`` semantics on the device --
     mean removed along time ('temp-*', axis 0) or space ('spat-*', axis 1); '*-standard' also
-    divides by the population std, a zero std being replaced by 1."""
+    divides by the population std; a std below ``10 * finfo(in_dtype).eps`` (ABSOLUTE threshold, sklearn's
+    ``_handle_zeros_in_scale``: about 1.2e-6 for float32 cubes) counts as zero variance and is replaced by 1."""
     if scaling is None:
         return M
     scaling = _mode_name(scaling)
@@ -92,14 +109,12 @@ def scale_matrix_device(M, scaling):
     out = M64 - mean
     if scaling.endswith("standard"):
         std = torch.sqrt((out * out).mean(dim=axis, keepdim=True))
-        # sklearn: scales smaller than 10*eps*|mean| are treated as zero variance -> 1
-        std = torch.where(std < 10 * np.finfo(np.float64).eps * mean.abs().clamp(min=1e-300), torch.ones_like(std), std)
-        std = torch.where(std == 0, torch.ones_like(std), std)
+        std = torch.where(std < _in_eps(in_dtype), torch.ones_like(std), std)
         out = out / std
     return out.to(torch.float32).contiguous()
 
 
-def prepare_matrix_device(cube_dev, scaling=None, mask_center_px=None):
+def prepare_matrix_device(cube_dev, scaling=None, mask_center_px=None, in_dtype=np.float32):
     """``prepare_matrix(mode='fullfr')`` (``var/shapes.py:857-873``): optional central mask, flatten to
     (n, H*W), optional scaling.  Returns a new tensor when anything is modified."""
     n, H, W = cube_dev.shape
@@ -107,12 +122,12 @@ def prepare_matrix_device(cube_dev, scaling=None, mask_center_px=None):
     if mask_center_px:
         mask = torch.as_tensor(circle_mask((H, W), mask_center_px).reshape(-1)).to(M.device)
         M = M.masked_fill(mask[None, :], 0.0)
-    return scale_matrix_device(M, scaling)
+    return scale_matrix_device(M, scaling, in_dtype)
 
 
 def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, svd_mode="lapack",
                             cube_ref_dev=None, cube_sig_dev=None, full_output=False, verbose=False,
-                            random_state=None, gram=None, pending=None):
+                            random_state=None, gram=None, pending=None, in_dtype=np.float32):
     """Whole-matrix branch of ``_project_subtract`` (``pca_fullfr.py:1552-1737``) on the device.
 
     Returns residuals (n,H,W) or (residuals, reconstructed (n,p), V (k,p))."""
@@ -121,12 +136,12 @@ def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, 
     if not isinstance(ncomp, (int, np.integer, float, np.floating)):
         raise TypeError("Type not recognized for ncomp, should be int or float")
 
-    matrix = prepare_matrix_device(cube_dev, scaling, mask_center_px)
+    matrix = prepare_matrix_device(cube_dev, scaling, mask_center_px, in_dtype)
     if cube_sig_dev is None:
         matrix_emp = matrix
     else:
         matrix_emp = matrix - cube_sig_dev.reshape(cube_sig_dev.shape[0], -1)
-    ref_lib = (prepare_matrix_device(cube_ref_dev, scaling, mask_center_px)
+    ref_lib = (prepare_matrix_device(cube_ref_dev, scaling, mask_center_px, in_dtype)
                if cube_ref_dev is not None else matrix_emp)
 
     dec = None
@@ -135,7 +150,7 @@ def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, 
         # reference decomposes the *cube* itself for this (SVDecomposer(cube, ...))
         if not 1 > ncomp > 0:
             raise ValueError("if `ncomp` is float, it must lie in the interval (0,1]")
-        dec_cube = Decomposition(prepare_matrix_device(cube_dev, scaling, None))
+        dec_cube = Decomposition(prepare_matrix_device(cube_dev, scaling, None, in_dtype))
         ncomp = int(np.searchsorted(dec_cube.cevr(), ncomp) + 1)
         if verbose:
             print("Components used : {}".format(ncomp))
@@ -221,7 +236,7 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
     if source_xy is not None:
         residuals_cube, recon, nfrslib = pa_rejection_residuals_device(
             cube_dev, ref_dev, sig_dev, angle_list, ncomp, scaling, mask_center_px, svd_mode, source_xy,
-            delta_rot, fwhm, min_frames_pca, max_frames_pca, full_output)
+            delta_rot, fwhm, min_frames_pca, max_frames_pca, full_output, in_dtype=_np_dtype_of(cube))
         V = None
         if verbose:
             print("Size LIB: min={:.1f} / 10th perc.={:.1f} / median={:.1f} / 90th perc.={:.1f} / max={:.1f}".format(
@@ -234,7 +249,7 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
         pending = [] if _defer_check else None
         res = project_subtract_device(cube_dev, ncomp, scaling, mask_center_px, svd_mode, ref_dev, sig_dev,
                                       full_output=full_output, verbose=verbose, random_state=random_state,
-                                      gram=gram, pending=pending)
+                                      gram=gram, pending=pending, in_dtype=_np_dtype_of(cube))
         if full_output:
             residuals_cube, recon, V = res
         else:
@@ -262,7 +277,8 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
         # `left_eigv` projects on the temporal (left) singular vectors U_k: U_k U_k^T M = M V_k^T V_k, the same
         # reconstruction as the pixel-space projection (pca_fullfr.py:1697-1700, 1723-1726); only the returned
         # "pcs" differ: V.T of the reference = U_k^T, shape (k, n) (:905).  U_k S_k = M_emp V_k^T.
-        US = kernels.cross_gram(V, scale_matrix_device(cube_dev.reshape(n, y * x), scaling))   # (k, n) = S_k U_k^T
+        US = kernels.cross_gram(V, scale_matrix_device(cube_dev.reshape(n, y * x), scaling,
+                                                       _np_dtype_of(cube)))                   # (k, n) = S_k U_k^T
         pcs_left = (US / torch.linalg.vector_norm(US, dim=1, keepdim=True)).to(torch.float32)
         out = (pcs_left, recon.reshape(n, y, x), residuals_cube, residuals_cube_, frame)
     elif full_output:
@@ -274,7 +290,7 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
 
 def pa_rejection_residuals_device(cube_dev, ref_dev, sig_dev, angle_list, ncomp, scaling, mask_center_px,
                                   svd_mode, source_xy, delta_rot, fwhm, min_frames_pca, max_frames_pca,
-                                  full_output=False):
+                                  full_output=False, in_dtype=np.float32):
     """The ``source_xy`` branch of ``_adi_rdi_pca`` (``pca_fullfr.py:911-965``) with ``_project_subtract``'s
     frame-by-frame mode (:1640-1710): frame f is projected on the PCs of the library of frames whose
     parallactic angle differs from PA_f by more than the threshold set by ``delta_rot`` x ``fwhm`` at the
@@ -298,15 +314,18 @@ def pa_rejection_residuals_device(cube_dev, ref_dev, sig_dev, angle_list, ncomp,
                         "library")
     if not isinstance(ncomp, (int, np.integer, float, np.floating)):
         raise TypeError("Type not recognized for ncomp, should be int or float")
-    matrix = prepare_matrix_device(cube_dev, scaling, mask_center_px)
+    matrix = prepare_matrix_device(cube_dev, scaling, mask_center_px, in_dtype)
     if isinstance(ncomp, (float, np.floating)):
-        # CEVR of the whole cube -> ncomp (pca_fullfr.py:1624-1637)
+        # CEVR of the whole cube -> ncomp (pca_fullfr.py:1624-1637): SVDecomposer(cube, scaling) sees the cube
+        # WITHOUT the central mask
         if not 1 > ncomp > 0:
             raise ValueError("if `ncomp` is float, it must lie in the interval (0,1]")
-        ncomp = int(np.searchsorted(Decomposition(matrix, None).cevr(), ncomp) + 1)
+        unmasked = matrix if not mask_center_px else prepare_matrix_device(cube_dev, scaling, None, in_dtype)
+        ncomp = int(np.searchsorted(Decomposition(unmasked, None).cevr(), ncomp) + 1)
     ncomp = int(ncomp)
     matrix_emp = matrix if sig_dev is None else matrix - sig_dev.reshape(sig_dev.shape[0], -1)
-    matrix_ref = prepare_matrix_device(ref_dev, scaling, mask_center_px) if ref_dev is not None else None
+    matrix_ref = (prepare_matrix_device(ref_dev, scaling, mask_center_px, in_dtype)
+                  if ref_dev is not None else None)
     nref = 0 if matrix_ref is None else matrix_ref.shape[0]
 
     yc, xc = frame_center((y, x))
@@ -407,8 +426,9 @@ def _pca_grid_device(cube, cube_ref, rot_angles, range_pcs, scaling, mask_center
     _check_rot_options(rot_options.get("imlib", "vip-fft"), rot_options.get("cxy"),
                        rot_options.get("border_mode", "constant"), rot_options.get("edge_blend"), cube.shape)
     dev = require_cuda()
-    matrix = prepare_matrix_device(to_device_f32(cube, dev), scaling, mask_center_px)
-    ref_lib = (prepare_matrix_device(to_device_f32(cube_ref, dev), scaling, mask_center_px)
+    in_dtype = _np_dtype_of(cube)
+    matrix = prepare_matrix_device(to_device_f32(cube, dev), scaling, mask_center_px, in_dtype)
+    ref_lib = (prepare_matrix_device(to_device_f32(cube_ref, dev), scaling, mask_center_px, in_dtype)
                if cube_ref is not None else matrix)
     nr, p = ref_lib.shape
     if pcmax > min(nr, p):
