@@ -11,10 +11,15 @@ N=1 workload: BASELINE configs[1]  (500x512x512 fp32 ADI cube, full-frame PCA, n
 JSON line keys (see the task contract): value = device-resident throughput (cube already in HBM),
 e2e = the same metric through the public call ``vip_b200.pca(numpy_cube, ...)`` with the host->device
 copy of the cube (pinned) and the device->host read of the frame inside the timed region;
-roofline = derotation stage against the measured HBM peak (it is FFT-arithmetic bound, see DESIGN.md);
-cpu_baseline = the numpy oracle (port of the reference algorithm) on a bounded sample.
+roofline = derotation stage against the measured HBM peak (it is FFT-arithmetic bound; the second
+object ``roofline_fft`` measures it against the FP32 FMA rate measured in the same run);
+cpu_baseline = the reference's CPU path on a bounded sample: the UNMODIFIED reference (``baseline/_ref/vip_hci``,
+installed from /root/reference with pip --no-deps, git-ignored, shipped with the snapshot; ``kind: "reference"``)
+when it is there, else the numpy oracle port (``kind: "port"``).
 
-``--impl reference`` times the CPU oracle port only (bounded sample per step), no GPU needed.
+``--impl reference`` times that CPU path only (one bounded sample per step), no GPU needed.
+N > 1: ONE cube sharded over the ranks (vip_b200/parallel.py); the line carries ``parity_vs_single`` (the sharded
+frame against the single-GPU frame computed once outside the timed region) and the per-stage split ``stage_ms``.
 """
 import argparse
 import json
@@ -118,27 +123,88 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU baseline (oracle port), bounded sample extrapolated to the full workload
 # --------------------------------------------------------------------------------------------
-def cpu_sample(cube, angs, ncomp, n_rot=2, strip=8):
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def cpu_impl():
+    """(kind, project_subtract, cube_derotate, cube_collapse) of the CPU arm: the unmodified reference when
+    ``baseline/_ref/vip_hci`` exists (loaded through oracle/ref_loader.py, which stubs the optional packages that
+    are not installed), else the oracle port.  Both are test / measurement infrastructure, never the product."""
+    if os.path.isdir(os.path.join(REF_DIR, "vip_hci")):
+        try:
+            os.environ.setdefault("VIP_REFERENCE_SRC", REF_DIR)
+            from oracle import ref_loader
+            ref_loader.REFERENCE_SRC = REF_DIR
+            ref_loader.load()
+            from vip_hci.psfsub.pca_fullfr import _project_subtract
+            from vip_hci.preproc import cube_derotate, cube_collapse
+
+            def ps(cube, ncomp):
+                return _project_subtract(cube, None, ncomp, None, None, "lapack", False, False)
+
+            def rot(cube, angs):
+                return cube_derotate(cube, angs, imlib="vip-fft", nproc=1)
+
+            return "reference", ps, rot, (lambda c: cube_collapse(c, "median"))
+        except Exception as exc:                              # noqa: BLE001 - fall back to the port, say why
+            sys.stderr.write(f"bench: baseline/_ref present but not importable ({exc!r}); using the oracle port\n")
+    from oracle import vip_oracle as O
+    return "port", (lambda c, k: O.project_subtract(c, k)), O.cube_derotate, (lambda c: O.cube_collapse(c, "median"))
+
+
+def set_blas_threads():
+    """torchrun exports OMP_NUM_THREADS=1: give the CPU arm all the host cores it can use."""
+    ncpu = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=ncpu)
+    except Exception:
+        pass
+    return ncpu
+
+
+def cpu_sample(cube, angs, ncomp, impl, n_rot=2, strip=8):
     """One bounded sample of the reference algorithm on the host: PCA projection/subtraction and the
     median on a 1/strip pixel strip of ALL frames (both scale linearly with pixels), derotation of
-    n_rot full frames (per-frame independent).  Returns extrapolated seconds for the whole cube."""
-    from oracle import vip_oracle as O
+    n_rot full frames (per-frame independent).  Returns (measured seconds of the sample, extrapolated seconds
+    for the whole cube, per-stage extrapolations)."""
+    _, ps, rot, col = impl
     n, H, W = cube.shape
     rows = max(1, H // strip)
     sub = np.ascontiguousarray(cube[:, :rows, :])
+    t_all = time.perf_counter()
     t0 = time.perf_counter()
-    res = O.project_subtract(sub, ncomp)
+    res = ps(sub, ncomp)
     t_ps = time.perf_counter() - t0
     t0 = time.perf_counter()
-    O.cube_collapse(res, "median")
+    col(res)
     t_col = time.perf_counter() - t0
     fr = np.ascontiguousarray(cube[:n_rot] - cube[:n_rot].mean(0))
     t0 = time.perf_counter()
-    O.cube_derotate(fr, angs[:n_rot])
+    rot(fr, angs[:n_rot])
     t_rot = time.perf_counter() - t0
+    measured = time.perf_counter() - t_all
     total = (t_ps + t_col) * (H / rows) + t_rot * (n / n_rot)
-    return total, {"project_subtract_s": t_ps * H / rows, "collapse_s": t_col * H / rows,
-                   "derotate_s": t_rot * n / n_rot}
+    return measured, total, {"project_subtract_s": t_ps * H / rows, "collapse_s": t_col * H / rows,
+                             "derotate_s": t_rot * n / n_rot}
+
+
+def sample_text(n, kind):
+    who = ("the unmodified reference (vip_hci 2.0.1 from baseline/_ref: _project_subtract, cube_derotate, "
+           "cube_collapse)") if kind == "reference" else "numpy oracle port of the reference algorithm"
+    return (f"per step: PCA project/subtract + median on a 1/8 pixel strip of all {n} frames (x8), vip-fft "
+            f"derotation of 2 full frames (x{n // 2}); {who}; value = {n} frames / extrapolated seconds")
+
+
+def config_dict(cfg, world):
+    """The ``config`` object of the JSON line -- identical in both arms."""
+    n, size, _, _, _ = CONFIGS[cfg]
+    return {"workload": workload_name(cfg),
+            "l2_policy": (f"inputs larger than L2 ({n * size * size * 4 / 1e6:.0f} MB cube vs 126 MB L2)"
+                          if n * size * size * 4 > 126e6 else "small test configuration (fits L2; not a bench line)"),
+            "multi_gpu": ("one cube sharded over the ranks: pixel shards -> all-reduce(Gramian) -> all-to-all to "
+                          "frame shards (overlapped with the eigensolver) -> derotate -> all-to-all to pixel shards "
+                          "-> median -> all-gather (NCCL)") if world > 1 else "single GPU"}
 
 
 def n_tiles_upper(n, tile=128):
@@ -155,33 +221,38 @@ def cpu_threads():
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure Python and
-    /root/reference does not travel to the GPU box) on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (the unmodified
+    reference from baseline/_ref when present, else the oracle port; /root/reference does not travel to the GPU
+    box).  Each step is one bounded sample; ``ms_per_step`` is the MEASURED time of a sample, ``value`` the
+    frames/s of the whole workload extrapolated from it (``extrapolation`` says how)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = set_blas_threads()
     from tools.synth import adi_cube
     n, size, k, delta, seed = CONFIGS[args.config]
     cube, angs = adi_cube(n, size, k, delta, seed=seed)
     import warnings
     warnings.simplefilter("ignore")
+    impl = cpu_impl()
     for _ in range(args.warmup):
-        cpu_sample(cube, angs, k)
-    times = []
+        cpu_sample(cube, angs, k, impl)
+    meas, totals = [], []
     for _ in range(args.steps):
-        t, parts = cpu_sample(cube, angs, k)
-        times.append(t)
-    sec = float(np.mean(times))
+        m, t, parts = cpu_sample(cube, angs, k, impl)
+        meas.append(m)
+        totals.append(t)
+    sec = float(np.mean(totals))
     value = n / sec
-    sample = (f"per step: PCA project/subtract + nanmedian on a 1/8 pixel strip of all {n} frames (x8), "
-              f"vip-fft derotation of 2 full frames (x{n // 2}); numpy/LAPACK/pocketfft oracle port")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32 (fp64 FFT/SVD inside numpy)", "data": "synthetic",
-            "impl": "reference",
-            "config": {"workload": workload_name(args.config), "extrapolated_from_sample": True},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-                             "sample": sample, "stage_seconds_full_cube": parts},
+            "warmup": args.warmup, "ms_per_step": float(np.mean(meas)) * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp64 FFT/SVD inside numpy)",
+            "data": "synthetic", "impl": "reference", "config": config_dict(args.config, args.gpus),
+            "extrapolation": {"ms_per_step_is": "measured wall time of one bounded sample",
+                              "full_workload_seconds": sec, "stage_seconds_full_cube": parts,
+                              "rule": "strip stages x8 (linear in pixels), derotation x n/2 (per frame)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "blas_threads": cpu_threads(),
+                             "kind": impl[0], "sample": sample_text(n, impl[0])},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -244,6 +315,50 @@ def stage_times(cube_dev, angs, ncomp, reps=3):
     return out
 
 
+def fp32_peak_measured(device):
+    """FP32 FMA rate of this GPU right now (TFLOP/s), from the register-only FFMA probe of the library."""
+    import torch
+    from vip_b200 import _cabi
+    from vip_b200._device import ptr, stream_ptr
+    lib = _cabi.lib()
+    blocks, iters = 148 * 8, 4096
+    out = torch.empty(blocks * 256, dtype=torch.float32, device=device)
+    lib.vb_fp32_probe(ptr(out), blocks, 16, stream_ptr())
+    best = None
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        lib.vb_fp32_probe(ptr(out), blocks, iters, stream_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return 2.0 * blocks * 256 * iters * 32 / (best * 1e-3) / 1e12
+
+
+def golden_parity(frame, cfg):
+    """The frame of this run against the committed golden frames of the UNMODIFIED reference for the same seeded
+    cube (tests/golden/big_c2.npz = vip_hci.psfsub.pca on the fp32 cube, big_c2t.npz = the same call on the
+    float64-cast cube, i.e. the fp64 truth); max |diff| / max |reference frame|."""
+    if cfg != "c2":
+        return None
+    out = {}
+    gdir = os.path.join(ROOT, "tests", "golden")
+    try:
+        g32 = np.load(os.path.join(gdir, "big_c2.npz"))["frame"].astype(np.float64)
+        out["vs_reference_fp32"] = float(np.max(np.abs(frame - g32)) / np.max(np.abs(g32)))
+        tpath = os.path.join(gdir, "big_c2t.npz")
+        if os.path.exists(tpath):
+            g64 = np.load(tpath)["frame"].astype(np.float64)
+            out["vs_reference_on_float64_cube"] = float(np.max(np.abs(frame - g64)) / np.max(np.abs(g64)))
+            out["reference_fp32_vs_its_float64_run"] = float(np.max(np.abs(g32 - g64)) / np.max(np.abs(g64)))
+        out["source"] = "tests/golden/big_c2*.npz (tools/make_golden_big.py, unmodified vip_hci)"
+    except Exception as exc:                                                       # noqa: BLE001
+        out["unavailable"] = repr(exc)
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -256,22 +371,22 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
 
     n, size, k, delta, seed = CONFIGS[args.config]
     # N > 1: ONE cube, sharded over the ranks (vip_b200/parallel.py): total work fixed -> strong scaling
-    cube, angs = adi_cube(n, size, k, delta, seed=seed)
+    cube, angs = adi_cube(n, size, k, delta, seed=seed)          # pageable host array: what a drop-in caller has
     pinned = torch.from_numpy(cube).pin_memory()
     cube_pinned_np = pinned.numpy()
     if world == 1:
         cube_dev = pinned.cuda()
     else:
-        from vip_b200.parallel import pca_sharded, shard_bounds
+        from vip_b200.parallel import pca_sharded, shard_bounds, StageTimer
         from vip_b200 import kernels
         pb = shard_bounds(size * size, world)
-        shard = kernels.upload_columns(cube_pinned_np.reshape(n, -1), int(pb[rank]), int(pb[rank + 1]),
-                                       torch.device("cuda", local))
+        shard = kernels.upload_columns(cube_pinned_np.reshape(n, -1), int(pb[rank]), int(pb[rank + 1]), dev)
         cube_dev = None
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -285,10 +400,10 @@ def run_gpu(args):
             return _adi_rdi_pca_device(cube_dev, None, angs, k, None, None, "lapack", "median", False, False)
         return pca_sharded(cube_pinned_np, angs, k, resident_shard=shard)
 
-    def step_e2e():
+    def step_e2e(host=cube_pinned_np):
         if world == 1:
-            return vip_b200.pca(cube_pinned_np, angs, ncomp=k, verbose=False)
-        return pca_sharded(cube_pinned_np, angs, k)
+            return vip_b200.pca(host, angs, ncomp=k, verbose=False)
+        return pca_sharded(host, angs, k)
 
     def barrier():
         if world > 1:
@@ -319,10 +434,15 @@ def run_gpu(args):
         clk.mark()
         launches = (_cabi.launch_count() - n0) // args.steps
         for _ in range(2):
-            step_e2e()
+            frame_e2e = step_e2e()
         clk.mark()
         ms_e2e = timed(step_e2e, args.steps)
         clk.mark()
+        # the same public call on the caller's PAGEABLE numpy array (what a drop-in user passes): reported beside
+        # the pinned number, not used for `value`
+        step_e2e(cube)
+        ms_page = timed(lambda: step_e2e(cube), max(2, args.steps // 2))
+        ms_page_step = ms_page / max(2, args.steps // 2)
     clocks = clk.summary()
 
     frames_total = n          # one cube per step, whatever the number of GPUs
@@ -335,18 +455,47 @@ def run_gpu(args):
             "vs_baseline": None,
             "dtype": "f32 (Gramian/eigensolve in f64)",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.config),
-                       "l2_policy": f"inputs larger than L2 ({cube.nbytes / 1e6:.0f} MB cube vs 126 MB L2)",
-                       "multi_gpu": ("one cube sharded over the ranks: pixel shards -> all-reduce(Gramian) -> "
-                                     "all-to-all to frame shards -> derotate -> all-to-all to pixel shards -> "
-                                     "median -> gather (NCCL)") if world > 1 else "single GPU"},
+            "config": config_dict(args.config, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(cube.nbytes),
-                    "d2h_bytes_per_step": int(size * size * 4), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(size * size * 4), "ms_per_step": ms_e2e / args.steps,
+                    "host_buffer": "pinned"},
+            "e2e_pageable": {"value": frames_total / (ms_page_step * 1e-3), "unit": UNIT, "ms_per_step": ms_page_step,
+                             "host_buffer": "pageable numpy array (torch stages it through its own pinned buffer)"},
             "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
             "clocks": clocks}
 
-    if rank == 0 and world > 1:
-        print(json.dumps(line))
+    if world > 1:
+        # ---- correctness of what was timed: the sharded frame against the single-GPU frame, outside the timed region
+        parity = None
+        if rank == 0:
+            ref = _adi_rdi_pca_device(torch.from_numpy(cube).to(dev), None, angs, k, None, None, "lapack", "median",
+                                      False, False).cpu().numpy()
+            parity = {"rel_err": float(np.max(np.abs(frame_e2e - ref)) / np.max(np.abs(ref))), "tol": 1e-5,
+                      "what": "max|sharded frame - single-GPU frame| / max|single-GPU frame|, same cube"}
+            parity["ok"] = bool(parity["rel_err"] < parity["tol"])
+            gp = golden_parity(frame_e2e.astype(np.float64), args.config)
+            if gp:
+                parity["golden"] = gp
+            del ref
+        # ---- per-stage split (CUDA events between the stages, max over ranks), two extra untimed steps
+        agg = None
+        for _ in range(2):
+            barrier()
+            tm = StageTimer(dev)
+            pca_sharded(cube_pinned_np, angs, k, resident_shard=shard, timer=tm)
+            st = tm.summary()
+            names = sorted(st)
+            t = torch.tensor([st[nm] for nm in names], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cur = dict(zip(names, [float(v) for v in t.tolist()]))
+            agg = cur if agg is None else {nm: min(agg[nm], cur[nm]) for nm in names}
+        if rank == 0:
+            line["parity_vs_single"] = parity
+            line["stage_ms"] = agg
+            line["stage_ms_note"] = ("CUDA events after each stage of pca_sharded, max over ranks, best of 2 untimed "
+                                     "steps; exchange1_wait = what is left of the overlapped all-to-all after the "
+                                     "eigensolver + PCs")
+            print(json.dumps(line))
     if rank == 0 and world == 1:
         st = stage_times(cube_dev, angs, k)
         p = size * size
@@ -358,24 +507,40 @@ def run_gpu(args):
             fft_flop = n * (2 * size + 1 + N) * 2 * 5 * N * lg   # (rows p1 + cols p2 + rows p3) x (fwd+inv)
         alg_bytes = 8.0 * p * n       # read residual cube + write derotated cube
         achieved = alg_bytes / (derot_ms * 1e-3) / 1e9
-        # DRAM bytes of the three shear kernels for one 500x512x512 step, from the committed ncu --set full
-        # capture of the packed real-plane kernels (profiles/r01k_ncu_pk.md, 100 frames, scaled x5): the real
-        # planes T1/T2 between the passes (the transposition of the 3-shear algorithm) make it 9x the
-        # algorithmic 8p bytes/frame (18.3 GB with the complex planes of r01j)
-        traffic = 9.45e9 if (n, size) == (500, 512) else None
+        # DRAM bytes of the derotation kernels per step: read from the committed ncu --set full summary of this round
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                ent = tj.get(f"{n}x{size}x{size}")
+                if ent:
+                    traffic, traffic_src = float(ent["derotate_dram_bytes_per_step"]), ent["source"]
+            except Exception:                                                      # noqa: BLE001
+                pass
+        fp32_peak = fp32_peak_measured(dev)
+        line["fp32_tflops_measured"] = fp32_peak
         line["roofline"] = {
             "kernel": ("vb_derotate_f32 = shear_rows_first_pk_loop + shear_cols_pk + shear_rows_last_pk (+ two "
                        "per-frame scalar kernels), one launch each per chunk; two real lines per complex transform"),
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": traffic, "peak_source": peak_kind,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": derot_ms,
             "note": ("stage is fp32-FFT-arithmetic bound, not HBM bound (DESIGN.md): ~330 flop per algorithmic byte; "
-                     "fft_gflop counts the reference's pruned complex transforms (2S+1+N per frame, forward + "
-                     "inverse), the kernels run half as many by packing two real lines per transform"),
-            "fft_gflop": None if fft_flop is None else fft_flop / 1e9,
-            "fft_tflops_achieved": None if fft_flop is None else fft_flop / (derot_ms * 1e-3) / 1e12,
-            "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,
+                     "see roofline_fft for the bound that applies"),
         }
+        if fft_flop is not None:
+            # the kernels run HALF of the reference's complex transforms (two real lines per transform), so the
+            # executed flop count is fft_flop / 2; both rates are given against the FP32 FMA peak measured above
+            line["roofline_fft"] = {
+                "kernel": "vb_derotate_f32 (same launches as `roofline`)", "bound": "fp32",
+                "achieved": 0.5 * fft_flop / (derot_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": 0.5 * fft_flop / (derot_ms * 1e-3) / 1e12 / fp32_peak,
+                "peak_source": "measured in this run: vb_fp32_probe (register-only FFMA stream), CUDA events",
+                "executed_gflop": 0.5 * fft_flop / 1e9, "reference_gflop": fft_flop / 1e9,
+                "reference_flop_rate_tflops": fft_flop / (derot_ms * 1e-3) / 1e12,
+                "note": ("flop = 5 N log2 N per complex transform; reference count = (2S+1+N) pruned lines per "
+                         "frame, forward + inverse; FADD/FMUL count as one flop per lane against an FMA peak of two")}
         gram_ms = st["gram_ms"]
         tf_peak = float(peaks.get("bf16_tflops", 1590.0))
         gram_flop = float(n) * n * p                 # symmetric half of the 2 n^2 p SYRK
@@ -395,15 +560,18 @@ def run_gpu(args):
                                              "achieved": 8.0 * p * n / (ps_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                              "unit": "GB/s", "frac": 8.0 * p * n / (ps_ms * 1e-3) / 1e9 / hbm_peak}
         line["stage_ms"] = st
-        if world == 1 and not args.no_cpu:
+        gp = golden_parity(np.asarray(frame_e2e, dtype=np.float64), args.config)
+        if gp:
+            line["parity_vs_reference_golden"] = gp
+        if not args.no_cpu:
             import warnings
             warnings.simplefilter("ignore")
-            sec, parts = cpu_sample(cube, angs, k)
+            cores = set_blas_threads()
+            impl = cpu_impl()
+            _, sec, parts = cpu_sample(cube, angs, k, impl)
             line["cpu_baseline"] = {
-                "value": n / sec, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-                "sample": (f"PCA project/subtract + nanmedian on a 1/8 pixel strip of all {n} frames (x8), vip-fft "
-                           f"derotation of 2 full frames (x{n // 2}); numpy oracle port of the reference algorithm"),
-                "stage_seconds_full_cube": parts}
+                "value": n / sec, "unit": UNIT, "cores": cores, "blas_threads": cpu_threads(), "kind": impl[0],
+                "sample": sample_text(n, impl[0]), "stage_seconds_full_cube": parts}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -153,6 +153,12 @@ int vb_checker_correct_f32(const float* in, float* out, int nframes, int ny, int
 int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitch, size_t width_bytes,
                     size_t height, void* stream);
 
+/* ---- measurement aid (bench.py) -------------------------------------------------------------
+ * Register-only FFMA stream: blocks x 256 threads x iters x 32 fused multiply-adds; `out` receives
+ * blocks*256 floats.  Timed by the caller with CUDA events to report the FP32 FMA peak of this GPU at its
+ * current clocks (the yardstick of the FFT-bound derotation; no reference counterpart). */
+int vb_fp32_probe(float* out, int blocks, int iters, void* stream);
+
 /* ---- measurement hook (bench.py) ----------------------------------------------------------
  * vb_profile_enable(1): CUDA events are recorded around each of the three shear kernels of
  * vb_derotate_f32 on its stream; vb_profile_read(out4_host) synchronises on them and returns the

@@ -23,7 +23,12 @@ import os
 import sys
 import types
 
-REFERENCE_SRC = os.environ.get("VIP_REFERENCE_SRC", "/root/reference/src")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# where the unmodified reference is looked for: the read-only checkout of the build container, else the offline pip
+# install under baseline/_ref (git-ignored, shipped to the GPU box with the snapshot; bench.py's CPU arm uses it)
+_CANDIDATES = ["/root/reference/src", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+REFERENCE_SRC = os.environ.get("VIP_REFERENCE_SRC") or next(
+    (c for c in _CANDIDATES if os.path.isdir(os.path.join(c, "vip_hci"))), _CANDIDATES[0])
 _OPTIONAL = ["astropy", "skimage", "photutils", "matplotlib", "hciplot", "emcee", "nestle",
              "corner", "dataclass_builder", "pyds9", "munch", "ultranest"]
 

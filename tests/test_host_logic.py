@@ -122,7 +122,12 @@ def test_bench_reference_arm_contract():
                 "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    have_ref = os.path.isdir(os.path.join(root, "baseline", "_ref", "vip_hci"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    # ms_per_step is the MEASURED time of a sample (it has to fit in the driver's wall clock around the run)
+    assert d["ms_per_step"] * 1e-3 < 120 and d["extrapolation"]["full_workload_seconds"] > 0
+    assert set(d["config"]) == {"workload", "l2_policy", "multi_gpu"}      # same object as the GPU arm's
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")

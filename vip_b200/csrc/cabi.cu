@@ -58,6 +58,7 @@ int annular_direct_weights(const double*, const double*, int, const int*, const 
 int gather_columns(const float*, int, size_t, const int*, int, float*, cudaStream_t);
 int scatter_columns(const float*, int, int, const int*, size_t, float*, cudaStream_t);
 int profile_read(float* out);
+int fp32_probe(float*, int, int, cudaStream_t);
 
 // exp(-2 pi i j / N) tables for the FFT path, one per (device, N), built in fp64 on the host
 static const float2* twiddle_table(int N) {
@@ -261,6 +262,11 @@ int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitc
     VB_CHECK_CUDA(cudaMemcpy2DAsync(dst, dpitch, src_host, spitch, width_bytes, height, cudaMemcpyHostToDevice,
                                     (cudaStream_t)stream));
     return 0;
+}
+
+int vb_fp32_probe(float* out, int blocks, int iters, void* stream) {
+    g_launches += 1;
+    return fp32_probe(out, blocks, iters, (cudaStream_t)stream);
 }
 
 void vb_profile_enable(int on) { profile_enable(on); }

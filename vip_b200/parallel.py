@@ -108,6 +108,57 @@ class CudaOps:
         return collapse_device(cube2d.reshape(n, 1, p), mode).reshape(p)
 
 
+class StageTimer:
+    """CUDA-event marks between the stages of a sharded call (``stage_ms`` of bench.py for N > 1).
+
+    ``mark(name)`` records an event on the current stream AFTER the stage ``name`` has been enqueued; NCCL
+    collectives issued through ``torch.distributed`` order the current stream behind them, so the interval between
+    two marks is the device time of the stage in between (including its exchange).  ``summary()`` synchronises."""
+
+    def __init__(self, device):
+        self.cuda = device.type == "cuda"
+        self.marks = []
+        self.mark("start")
+
+    def mark(self, name):
+        if self.cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+        else:
+            import time
+            self.marks.append((name, time.perf_counter()))
+
+    def summary(self):
+        out = {}
+        if self.cuda:
+            torch.cuda.synchronize()
+        for (_, a), (name, b) in zip(self.marks[:-1], self.marks[1:]):
+            ms = a.elapsed_time(b) if self.cuda else (b - a) * 1e3
+            out[name + "_ms"] = out.get(name + "_ms", 0.0) + ms
+        return out
+
+
+def _mark(timer, name):
+    if timer is not None:
+        timer.mark(name)
+
+
+def _exchange_single(send_flat, send_counts, recv_counts, group, async_op=False):
+    """ONE preallocated all-to-all: ``send_flat`` (1-d, contiguous) holds the blocks for peers 0..world-1 back to
+    back (``send_counts`` elements each); returns (recv_flat, handle) with the blocks of the peers back to back
+    (``recv_counts``).  Uneven splits are fine (1-d element counts).  No per-peer tensors, no repacking."""
+    recv_flat = torch.empty(int(sum(recv_counts)), dtype=send_flat.dtype, device=send_flat.device)
+    work = dist.all_to_all_single(recv_flat, send_flat, output_split_sizes=[int(c) for c in recv_counts],
+                                  input_split_sizes=[int(c) for c in send_counts], group=group, async_op=async_op)
+    return recv_flat, work
+
+
+def _single_ok():
+    """all_to_all_single is NCCL-native; the gloo backend of the CPU tests lacks it on some builds."""
+    return os.environ.get("VIP_B200_SHARD_A2A", "single") == "single"
+
+
 def _all_to_all(send, recv, group):
     """Exchange lists of tensors (uneven sizes allowed)."""
     try:
@@ -155,7 +206,82 @@ def _all_to_all_async(send, recv, group):
         return _Exchange(reqs)
 
 
-def _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, ops, device):
+def _rows_to_frames(block, fb, pb, rank, group, device, timer=None, async_op=False):
+    """Exchange 1: ``block`` (n, p_g) -- every frame, this rank's pixel shard, row-major -- to this rank's frame
+    shard with all pixels, (f_g, p).  Row blocks of ``block`` are already contiguous per destination, so the send
+    side is zero-copy; the receive side is one flat buffer [peer h][f_g][p_h] that is stitched into (f_g, p) with
+    one strided copy per peer (no list of temporaries, no ``cat``).  Returns a callable producing the tensor
+    (it waits for the exchange when ``async_op``)."""
+    world = dist.get_world_size(group)
+    n, pg = block.shape
+    f0, f1 = int(fb[rank]), int(fb[rank + 1])
+    fg = f1 - f0
+    p = int(pb[-1])
+    widths = [int(pb[h + 1] - pb[h]) for h in range(world)]
+    if _single_ok() and block.is_contiguous():
+        try:
+            recv_flat, work = _exchange_single(block.reshape(-1), [int(fb[h + 1] - fb[h]) * pg for h in range(world)],
+                                               [fg * w for w in widths], group, async_op=async_op)
+        except (RuntimeError, NotImplementedError):
+            recv_flat = None
+        if recv_flat is not None:
+            def finish():
+                if async_op and work is not None:
+                    work.wait()
+                if world == 1:
+                    return recv_flat.reshape(fg, p)
+                out = torch.empty((fg, p), dtype=block.dtype, device=device)
+                off = 0
+                for h in range(world):
+                    out[:, int(pb[h]):int(pb[h + 1])] = recv_flat[off:off + fg * widths[h]].reshape(fg, widths[h])
+                    off += fg * widths[h]
+                return out
+            return finish
+    send = [block[int(fb[h]):int(fb[h + 1])].contiguous() for h in range(world)]
+    recv = [torch.empty((fg, widths[h]), dtype=block.dtype, device=device) for h in range(world)]
+    if async_op:
+        ex = _all_to_all_async(send, recv, group)
+
+        def finish_list():
+            ex.wait()
+            return torch.cat(recv, dim=1)
+        return finish_list
+    _all_to_all(send, recv, group)
+    return lambda: torch.cat(recv, dim=1)
+
+
+def _frames_to_pixels(der2, fb, pb, rank, group, device):
+    """Exchange 2: this rank's derotated frames (f_g, p) -> every frame of this rank's pixel shard, (n, p_g).
+    The send buffer is packed per destination with one strided copy per peer into ONE flat buffer; the flat
+    receive buffer [peer h][f_h][p_g] IS the (n, p_g) matrix (frame shards are contiguous, in rank order)."""
+    world = dist.get_world_size(group)
+    fg, p = der2.shape
+    n = int(fb[-1])
+    p0, p1 = int(pb[rank]), int(pb[rank + 1])
+    pg = p1 - p0
+    widths = [int(pb[h + 1] - pb[h]) for h in range(world)]
+    if _single_ok():
+        if world == 1:
+            send_flat = der2.reshape(-1)
+        else:
+            send_flat = torch.empty(fg * p, dtype=der2.dtype, device=device)
+            off = 0
+            for h in range(world):
+                send_flat[off:off + fg * widths[h]].reshape(fg, widths[h]).copy_(der2[:, int(pb[h]):int(pb[h + 1])])
+                off += fg * widths[h]
+        try:
+            recv_flat, _ = _exchange_single(send_flat, [fg * w for w in widths],
+                                            [int(fb[h + 1] - fb[h]) * pg for h in range(world)], group)
+            return recv_flat.reshape(n, pg)
+        except (RuntimeError, NotImplementedError):
+            pass
+    send = [der2[:, int(pb[h]):int(pb[h + 1])].contiguous() for h in range(world)]
+    recv = [torch.empty((int(fb[h + 1] - fb[h]), pg), dtype=der2.dtype, device=device) for h in range(world)]
+    _all_to_all(send, recv, group)
+    return torch.cat(recv, dim=0)
+
+
+def _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, ops, device, timer=None):
     """Tail of the sharded paths: this rank's residual frames ``mine`` (f1-f0, H, W) -> derotation (local) ->
     temporal collapse across the ranks.  'mean' / 'sum' are reducible (partial sums + one NCCL reduce of an
     (H,W) frame); the other modes need every frame of a pixel on one rank: all-to-all to pixel shards, local
@@ -168,6 +294,7 @@ def _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, o
     p0, p1 = int(pb[rank]), int(pb[rank + 1])
     f0, f1 = int(fb[rank]), int(fb[rank + 1])
     der = ops.derotate(mine, -angle_list[f0:f1]) if f1 > f0 else mine
+    _mark(timer, "derotate")
 
     if collapse in ("mean", "sum"):
         # ---- reducible collapse: partial sums over the own frames, one NCCL reduce of an (H,W) frame ------
@@ -176,6 +303,7 @@ def _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, o
         part = ops.collapse(der.reshape(f1 - f0, p), "sum") if f1 > f0 else torch.zeros(p, device=device)
         part = part.to(torch.float32).contiguous()
         dist.reduce(part, dst=src, op=dist.ReduceOp.SUM, group=group)
+        _mark(timer, "collapse_reduce")
         frame = None
         if rank == 0:
             if collapse == "mean":
@@ -184,18 +312,30 @@ def _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, o
         return frame, der
 
     # ---- exchange 2: frame shards -> pixel shards, collapse, gather --------------------------------
-    der2 = der.reshape(f1 - f0, p)
-    send = [der2[:, int(pb[h]):int(pb[h + 1])].contiguous() for h in range(world)]
-    recv = [torch.empty((int(fb[h + 1] - fb[h]), p1 - p0), dtype=der2.dtype, device=device) for h in range(world)]
-    _all_to_all(send, recv, group)
-    slab = ops.collapse(torch.cat(recv, dim=0).contiguous(), collapse)  # (p_g,)
+    slab_in = _frames_to_pixels(der.reshape(f1 - f0, p), fb, pb, rank, group, device)      # (n, p_g)
+    _mark(timer, "exchange2")
+    slab = ops.collapse(slab_in, collapse)                                                   # (p_g,)
+    _mark(timer, "collapse")
 
+    frame = None
+    if p % world == 0 and _single_ok():
+        # equal shards: the slabs land back to back in one (H*W) buffer, no padding / repacking
+        full = torch.empty(p, dtype=slab.dtype, device=device)
+        try:
+            dist.all_gather_into_tensor(full, slab.contiguous(), group=group)
+        except (RuntimeError, NotImplementedError, AttributeError):
+            full = None
+        if full is not None:
+            _mark(timer, "gather")
+            if rank == 0:
+                frame = full.reshape(H, W).cpu().numpy()
+            return frame, der
     pmax = int(np.max(np.diff(pb)))
     padded = torch.zeros(pmax, dtype=slab.dtype, device=device)
     padded[: p1 - p0] = slab
     gathered = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(gathered, padded, group=group)
-    frame = None
+    _mark(timer, "gather")
     if rank == 0:
         frame = torch.cat([gathered[h][: int(pb[h + 1] - pb[h])] for h in range(world)]).reshape(H, W)
         frame = frame.cpu().numpy()
@@ -204,7 +344,7 @@ def _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, o
 
 def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None, device=None,
                 full_output=False, resident_shard=None, svd_mode="lapack", random_state=None, _defer_check=True,
-                host_shard=None, shape=None, overlap_exchange=None):
+                host_shard=None, shape=None, overlap_exchange=None, timer=None):
     """Full-frame ADI PCA of ONE cube, sharded over the ranks of ``group``.
 
     ``cube`` (n,H,W) is the host array, visible on every rank (each rank uploads only its pixel
@@ -222,7 +362,9 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
     ``host_shard`` + ``shape``: for cubes that no single host buffer should hold (BASELINE config 5 is 16.8 GB),
     every rank may pass ONLY its own pixel shard -- a C-contiguous fp32 (n, p_g) host array with
     p_g = ``shard_bounds(H*W, world)`` of this rank -- together with ``shape=(n, H, W)``; ``cube`` is then ignored
-    (pass None) and the upload is one contiguous copy."""
+    (pass None) and the upload is one contiguous copy.
+
+    ``timer``: a :class:`StageTimer`; when given, a CUDA event is recorded after every stage (bench.py ``stage_ms``)."""
     if host_shard is not None and (shape is None or len(shape) != 3):
         raise TypeError("pca_sharded: `host_shard` needs `shape=(n, H, W)`")
     if shape is not None and (host_shard is not None or resident_shard is not None):
@@ -258,10 +400,13 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
     else:
         M = ops.upload_pixels(cube.reshape(n, p), p0, p1, device)
     src = dist.get_global_rank(group, 0) if group is not None else 0
+    _mark(timer, "upload")
     record = None
-    raw_exchange = None
+    raw_frames = None
     if overlap_exchange is None:
-        overlap_exchange = os.environ.get("VIP_B200_SHARD_OVERLAP", "0") == "1"      # off until measured on hardware
+        # default ON since round 2 (measured on NVLink: profiles/r02_scaling.md); VIP_B200_SHARD_OVERLAP=0 restores
+        # the subtract-then-exchange order
+        overlap_exchange = os.environ.get("VIP_B200_SHARD_OVERLAP", "1") == "1"
     mode = str(getattr(svd_mode, "value", svd_mode))
     if mode in ("randsvd", "randcupy", "randpytorch"):
         def reduce(t):                                                   # exchange step 0: sketches
@@ -279,19 +424,20 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
             omega = torch.empty((n, ell), dtype=torch.float64, device=device)
         dist.broadcast(omega, src=src, group=group)
         V = ops.randomized_pcs(M, ncomp, omega.cpu().numpy(), reduce)
+        _mark(timer, "randsvd")
         Cm = ops.coeffs(M, V, reduce)
+        _mark(timer, "coeffs")
     else:
         G = ops.gram(M)
+        _mark(timer, "gram")
         dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)           # exchange step 0: n x n fp64
-        if overlap_exchange:
-            # R = M - C V is row-local once V is known everywhere: the all-to-all to frame shards can move the RAW
+        _mark(timer, "allreduce_gram")
+        if overlap_exchange and world > 1:
+            # R = M - C V is row-local once V is known everywhere: the all-to-all to frame shards moves the RAW
             # cube while the (replicated, latency-bound) eigensolver runs; V (k x p, 21 MB at config 2) is
             # all-gathered afterwards and the subtraction happens on the frame shards.  Same kernels on the same
             # values: bit-identical to the default order.
-            raw_send = [M[int(fb[h]):int(fb[h + 1])] for h in range(world)]          # contiguous row blocks
-            raw_recv = [torch.empty((f1 - f0, int(pb[h + 1] - pb[h])), dtype=M.dtype, device=device)
-                        for h in range(world)]
-            raw_exchange = _all_to_all_async(raw_send, raw_recv, group)
+            raw_frames = _rows_to_frames(M, fb, pb, rank, group, device, async_op=True)
         # the convergence record of the subspace solver is read once, after the whole pipeline has been
         # enqueued (no host stall behind the eigensolver); see the check before the return
         deferred = ops.leading_eig_async(G, ncomp) if (_defer_check and hasattr(ops, "leading_eig_async")) else None
@@ -299,37 +445,49 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
             evals, evecs, record = deferred
         else:
             evals, evecs = ops.leading_eig(G, ncomp)
-        # replicate the eigenpairs bit-identically (atomics make the solver order-dependent at 1e-16)
-        dist.broadcast(evals, src=src, group=group)
-        dist.broadcast(evecs, src=src, group=group)
+        _mark(timer, "eigensolver")
+        if os.environ.get("VIP_B200_SHARD_BCAST", "0") == "1":
+            # optional: bit-identical eigenpairs on every rank.  Not needed for the residuals: every rank projects
+            # its pixel shard on ITS OWN (E, S) pair consistently (R_g = M_g - E E^T M_g is invariant to the sign
+            # and order of the vectors), and all ranks start from the same all-reduced G, so the subspaces agree
+            # to the solver's tolerance (1e-9 of lambda_k) -- two latency-bound broadcasts saved per call.
+            dist.broadcast(evals, src=src, group=group)
+            dist.broadcast(evecs, src=src, group=group)
         S = torch.sqrt(torch.clamp(evals, min=0.0))
         Wt = (evecs / S[:, None]).contiguous()
         Cm = (evecs * S[:, None]).t().to(torch.float32).contiguous()
         V = ops.pcs(Wt, M)
-    if raw_exchange is not None:
-        # all-gather of the PCs (pixel shards of uneven width are padded to the widest)
+        _mark(timer, "pcs")
+    if raw_frames is not None:
+        # all-gather of the PCs
         k = V.shape[0]
-        pmax = int(np.max(np.diff(pb)))
-        padded = torch.zeros((k, pmax), dtype=V.dtype, device=device)
-        padded[:, : p1 - p0] = V
-        parts = [torch.empty_like(padded) for _ in range(world)]
-        dist.all_gather(parts, padded, group=group)
-        V_full = torch.cat([parts[h][:, : int(pb[h + 1] - pb[h])] for h in range(world)], dim=1).contiguous()
-        raw_exchange.wait()
-        mine_raw = torch.cat(raw_recv, dim=1).contiguous()                  # my frames, all pixels, raw
+        if p % world == 0 and _single_ok():
+            parts_flat = torch.empty((world * k, p // world), dtype=V.dtype, device=device)
+            dist.all_gather_into_tensor(parts_flat, V.contiguous(), group=group)
+            V_full = parts_flat.reshape(world, k, p // world).permute(1, 0, 2).reshape(k, p)
+        else:
+            pmax = int(np.max(np.diff(pb)))
+            padded = torch.zeros((k, pmax), dtype=V.dtype, device=device)
+            padded[:, : p1 - p0] = V
+            parts = [torch.empty_like(padded) for _ in range(world)]
+            dist.all_gather(parts, padded, group=group)
+            V_full = torch.cat([parts[h][:, : int(pb[h + 1] - pb[h])] for h in range(world)], dim=1)
+        V_full = V_full.contiguous()
+        _mark(timer, "allgather_pcs")
+        mine_raw = raw_frames()                                             # my frames, all pixels, raw
+        _mark(timer, "exchange1_wait")
         if f1 > f0:
             mine = ops.project_subtract(mine_raw, Cm[f0:f1].contiguous(), V_full).reshape(f1 - f0, H, W)
         else:
             mine = mine_raw.reshape(0, H, W)
+        _mark(timer, "subtract")
     else:
         R = ops.project_subtract(M, Cm, V)                                   # (n, p_g)
-
+        _mark(timer, "subtract")
         # ---- exchange 1: pixel shards -> frame shards ---------------------------------------------
-        send = [R[int(fb[h]):int(fb[h + 1])].contiguous() for h in range(world)]
-        recv = [torch.empty((f1 - f0, int(pb[h + 1] - pb[h])), dtype=R.dtype, device=device) for h in range(world)]
-        _all_to_all(send, recv, group)
-        mine = torch.cat(recv, dim=1).reshape(f1 - f0, H, W)                # my frames, all pixels
-    frame, der = _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, ops, device)
+        mine = _rows_to_frames(R, fb, pb, rank, group, device)().reshape(f1 - f0, H, W)   # my frames, all pixels
+        _mark(timer, "exchange1")
+    frame, der = _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, ops, device, timer)
     if record is not None:
         if device.type == "cuda":
             torch.cuda.current_stream().synchronize()
@@ -340,7 +498,7 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
             return pca_sharded(cube, angle_list, ncomp, collapse=collapse, group=group, ops=ops, device=device,
                                full_output=full_output, resident_shard=resident_shard, svd_mode=svd_mode,
                                random_state=random_state, _defer_check=False, host_shard=host_shard, shape=shape,
-                               overlap_exchange=overlap_exchange)
+                               overlap_exchange=overlap_exchange, timer=timer)
     if full_output:
         return frame, der, (f0, f1)
     return frame
