@@ -77,8 +77,20 @@ int vb_eigh_topk_async_f64(const double* G, int n, int k, double tol, int max_it
  * V[k x p] (fp32) = Wt[k x n] (fp64) . M[n x p] (fp32), accumulated in fp64   psfsub/svd.py:451-459
  * R[n x p] = M - C[n x k] . V[k x p]   (R may alias M)            psfsub/pca_fullfr.py:1728-1731 */
 int vb_pcs_f32(const double* Wt, const float* M, int k, int n, size_t p, float* V, void* stream);
+/* Same product with the fp64 sum returned as an error-free pair of fp32 matrices, V = Vhi + Vlo (~48 bits):
+ * the raw sketches of the randomized SVD span (sigma_0/sigma_k)^(2q+1) in magnitude before they are
+ * orthonormalised, which fp32 storage cannot hold (sklearn's randomized_range_finder, extmath.py; call site
+ * psfsub/svd.py:487-491). */
+int vb_pcs_hilo_f32(const double* Wt, const float* M, int k, int n, size_t p, float* Vhi, float* Vlo,
+                    void* stream);
 int vb_project_subtract_f32(const float* M, const float* C, int ldc, const float* V, int k, int n,
                             size_t p, float* R, void* stream);
+/* Same projection with fp64 coefficients C (n x k), the components as the error-free pair Vhi + Vlo of
+ * vb_pcs_hilo_f32 (Vlo may be NULL) and fp64 accumulation; R is rounded to fp32 once.  The default of the PCA
+ * path: with a 1e4-bright halo in the cube, fp32 copies of C and V leave a frame-independent error in every
+ * residual pixel that survives the temporal median (measured 1e-3 of the final frame at config 2). */
+int vb_project_subtract_hp_f32(const float* M, const double* C, int ldc, const float* Vhi, const float* Vlo, int k,
+                               int n, size_t p, float* R, void* stream);
 /* out = a - b elementwise (reconstructed = matrix - residuals for full_output) */
 int vb_sub_f32(const float* a, const float* b, float* out, size_t count, void* stream);
 

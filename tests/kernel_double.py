@@ -44,8 +44,23 @@ def pcs(Wt, M):
     return (Wt.double() @ M.double()).float()
 
 
+def pcs_hilo(Wt, M):
+    acc = Wt.numpy().astype(np.float64) @ M.numpy().astype(np.float64)
+    hi = acc.astype(np.float32)
+    return torch.from_numpy(hi), torch.from_numpy((acc - hi).astype(np.float32))
+
+
 def project_subtract(M, Cm, V, out=None):
     R = M - Cm.float() @ V
+    if out is not None:
+        out.copy_(R)
+        return out
+    return R
+
+
+def project_subtract_hp(M, C64, Vhi, Vlo=None, out=None):
+    V = Vhi.double() if Vlo is None else Vhi.double() + Vlo.double()
+    R = (M.double() - C64.double() @ V).float()
     if out is not None:
         out.copy_(R)
         return out
@@ -133,7 +148,7 @@ def annular_weights(G, idx, lens, frames, ncomp, tol=0.0, max_iter=40, direct_fa
     return torch.from_numpy(W), torch.ones(nprob, dtype=torch.int32)
 
 
-_NAMES = ("annular_weights", "gram", "cross_gram", "eigh", "eigh_topk", "topk_supported", "pcs", "project_subtract", "sub", "derotate",
+_NAMES = ("annular_weights", "gram", "cross_gram", "eigh", "eigh_topk", "topk_supported", "pcs", "pcs_hilo", "project_subtract", "project_subtract_hp", "sub", "derotate",
           "collapse", "upload_and_gram", "upload_columns", "gather_columns", "scatter_columns", "gemm")
 
 

@@ -92,7 +92,7 @@ def test_c2_final_frame_vs_reference_golden(vb):
     assert e_res < PCA_TOL or ours_r < 1.5 * ref_r + 2e-5
     assert e_der < 2 * PCA_TOL or ours_d < 1.5 * ref_d + 2e-5
     assert e_fr < FRAME_TOL or ours_f < 1.5 * ref_f + 2e-5
-    assert ours_r < PCA_TOL and ours_f < FRAME_TOL       # and we ARE within tolerance of the truth
+    assert ours_r < PCA_TOL and ours_f < FRAME_TOL       # and we ARE within tolerance of the truth (hp projection)
     # the plain call (no full_output) returns the same frame bits
     np.testing.assert_array_equal(vb.pca(cube, angs, ncomp=20, verbose=False), frame)
 
@@ -107,20 +107,24 @@ def test_c2_randsvd_vs_reference_golden(vb):
     frame, pcs, recon, res, res_ = vb.pca(cube, angs, ncomp=20, svd_mode="randsvd", verbose=False, full_output=True)
     e_res = float(np.max(np.abs(res[123] - g["res_frame_123"])) / np.max(np.abs(g["res_frame_123"])))
     e_fr = rel_err(frame, g["frame"])
-    report(f"C2 randsvd (global RandomState seeded like the reference) vs unmodified reference: residual frame "
-           f"{e_res:.2e}, final frame {e_fr:.2e}")
-    # same rule as above: the reference's fp32 sgemm noise at this size exceeds the tolerance, so the exact PCA of the
-    # float64-cast cube (big_c2t; the spectrum is gapped at ncomp, so the randomized subspace equals the exact one to
-    # far below the tolerance) arbitrates
-    t = _big("c2t")
-    scale_r = float(np.max(np.abs(t["res_frame_123"])))
-    ours_r = float(np.max(np.abs(res[123] - t["res_frame_123"])) / scale_r)
-    ref_r = float(np.max(np.abs(g["res_frame_123"].astype(np.float64) - t["res_frame_123"])) / scale_r)
-    ours_f, ref_f = rel_err(frame, t["frame"]), rel_err(g["frame"], t["frame"])
-    report(f"C2 randsvd vs fp64 truth (exact PCA of the float64 cube): residual frame ours {ours_r:.2e} / reference "
-           f"{ref_r:.2e}; final frame ours {ours_f:.2e} / reference {ref_f:.2e}")
-    assert e_res < PCA_TOL or ours_r < 1.5 * ref_r + 2e-5
-    assert e_fr < FRAME_TOL or ours_f < 1.5 * ref_f + 2e-5
+    report(f"C2 randsvd (global RandomState seeded like the reference) vs the unmodified reference's fp32 run: "
+           f"residual frame {e_res:.2e}, final frame {e_fr:.2e}")
+    # The reference's fp32 randsvd is rounding noise on a halo-dominated fp32 cube (see
+    # test_c5_randsvd_seeded_vs_oracle), so the stable float64 evaluation of the same algorithm with the same Omega
+    # (O.randsvd_stable) arbitrates: residual frame 123 and the span of the 20 components.
+    M64 = cube.reshape(500, -1).astype(np.float64)
+    np.random.seed(int(g["seed"][0]))
+    omega = np.random.mtrand._rand.normal(size=(500, 30))
+    V_or = O.randsvd_stable(cube.reshape(500, -1), 20, omega)
+    o123 = M64[123] - (M64[123] @ V_or.T) @ V_or
+    scale = float(np.max(np.abs(o123)))
+    ours_r = float(np.max(np.abs(res[123].reshape(-1) - o123)) / scale)
+    ref_r = float(np.max(np.abs(g["res_frame_123"].reshape(-1).astype(np.float64) - o123)) / scale)
+    ang = _projector_distance(pcs.reshape(20, -1), V_or)
+    report(f"C2 randsvd vs the stable float64 evaluation, same Omega: residual frame ours {ours_r:.2e} / the "
+           f"reference's fp32 run {ref_r:.2e}; sin(largest principal angle) of the PC spans {ang:.2e}")
+    assert e_res < PCA_TOL or ours_r < PCA_TOL
+    assert ang < 1e-3
 
 
 # ------------------------------------------------------------------ config 3: 1000 x 512 x 512 pca_annular
@@ -211,27 +215,64 @@ def _projector_distance(V1, V2):
 
 @pytest.mark.parametrize("n,size,k", [(1000, 512, 50), (4000, 128, 50)])
 def test_c5_randsvd_seeded_vs_oracle(vb, n, size, k):
-    """``svd_mode='randsvd'`` with ncomp=50 (config 5) and the SAME Gaussian test matrix as scikit-learn: the residual
-    cube of the PCA stage against ``O.project_subtract(svd_mode='randsvd', random_state=RandomState(s))``
-    (``svd.py:487-491``, ``pca_fullfr.py:1727-1731``) at 1e-4, plus the principal angle between the two sets of
-    PCs.  (1000, 512): >= 1000 x 512^2 as the verdict asks; (4000, 128): the n = 4000 sketches of config 5."""
+    """``svd_mode='randsvd'`` with ncomp=50 (config 5) and the SAME Gaussian test matrix as scikit-learn
+    (``svd.py:487-491``, ``pca_fullfr.py:1727-1731``).  (1000, 512): >= 1000 x 512^2 as the verdict asks; (4000, 128):
+    the n = 4000 sketches of config 5.
+
+    scikit-learn computes in the dtype of its input and skips the normalisation of its two power iterations
+    (n_iter=2 => normaliser 'none'): the sketch holds (sigma_0/sigma_k)^5 of dynamic range, so on a cube that still
+    contains the stellar halo (sigma_0/sigma_k ~ 600 here) its fp32 run is rounding noise beyond the first components
+    and even its float64 run is only good to ~1e-2.  ``randomized_pcs`` evaluates the same algorithm stably (the
+    result in exact arithmetic).  Hence two comparisons:
+      (a) temporal mean removed (sigma_0/sigma_k ~ 50: the reference's float64 arithmetic is sound): residual cube
+          against ``O.project_subtract(float64 cube, svd_mode='randsvd', same RandomState)`` at 1e-4 + principal angle;
+      (b) the raw cube: against ``O.randsvd_stable`` (the same algorithm with a QR after every multiplication, float64;
+          pinned against scikit-learn in tests/test_oracle_known_answers.py) with the same Omega, the distance of the
+          reference's own fp32 run printed beside it."""
     import torch
     from vip_b200.psfsub.pca_fullfr import project_subtract_device
     cube, _ = adi_cube(n, size, 50, 90.0, seed=20260105, decay=0.97)      # spectrum gapped after 50 modes
     dev = torch.device("cuda")
-    res, _, V = project_subtract_device(torch.from_numpy(cube).to(dev), k, svd_mode="randsvd", full_output=True,
-                                        random_state=np.random.RandomState(11))
-    res = res.cpu().numpy()
-    V = V.cpu().numpy()
-    torch.cuda.empty_cache()
-    o_res, _, o_V = O.project_subtract(cube, k, svd_mode="randsvd", full_output=True,
+
+    def ours(c):
+        res, _, V = project_subtract_device(torch.from_numpy(c).to(dev), k, svd_mode="randsvd", full_output=True,
+                                            random_state=np.random.RandomState(11))
+        out = res.cpu().numpy(), V.cpu().numpy()
+        del res, V
+        torch.cuda.empty_cache()
+        return out
+
+    # (a) mean-removed cube, identical Omega, reference arithmetic in float64
+    cm = cube - cube.mean(axis=0, keepdims=True)
+    res, V = ours(cm)
+    o_res, _, o_V = O.project_subtract(cm.astype(np.float64), k, svd_mode="randsvd", full_output=True,
                                        random_state=np.random.RandomState(11))
     e = float(np.max(np.abs(res - o_res)) / np.max(np.abs(o_res)))
     ang = _projector_distance(V, o_V)
-    report(f"C5 randsvd n={n} {size}x{size} ncomp={k}, identical Omega: residual cube {e:.2e} (tol {PCA_TOL:.0e}), "
-           f"sin(largest principal angle) between the PC spans {ang:.2e}")
+    report(f"C5 randsvd n={n} {size}x{size} ncomp={k}, mean-removed cube, identical Omega, reference in float64: "
+           f"residual cube {e:.2e} (tol {PCA_TOL:.0e}), sin(largest principal angle) of the PC spans {ang:.2e}")
     assert e < PCA_TOL
-    assert ang < 2e-3
+    assert ang < 1e-3
+    del o_res, o_V, cm
+    # (b) raw (halo-dominated) cube against the stable float64 evaluation of the same algorithm, same Omega
+    res, V = ours(cube)
+    M64 = cube.reshape(n, -1).astype(np.float64)
+    omega = np.random.RandomState(11).normal(size=(n, k + 10))
+    V_or = O.randsvd_stable(cube.reshape(n, -1), k, omega)
+    sel = [0, n // 2, n - 1]
+    o_sel = M64[sel] - (M64[sel] @ V_or.T) @ V_or
+    scale = float(np.max(np.abs(o_sel)))
+    e_b = float(np.max(np.abs(res.reshape(n, -1)[sel] - o_sel)) / scale)
+    ang_b = _projector_distance(V, V_or)
+    msg = (f"C5 randsvd n={n} RAW cube vs the stable float64 evaluation (O.randsvd_stable), same Omega: residual frames "
+           f"{sel} {e_b:.2e} (tol {PCA_TOL:.0e}), sin(largest principal angle) {ang_b:.2e}")
+    if n <= 1000:
+        o32 = O.project_subtract(cube, k, svd_mode="randsvd", random_state=np.random.RandomState(11))
+        msg += (f"; the reference's own fp32 run on these frames: "
+                f"{float(np.max(np.abs(o32.reshape(n, -1)[sel] - o_sel)) / scale):.2e}")
+    report(msg)
+    assert e_b < PCA_TOL
+    assert ang_b < 1e-3
 
 
 def test_zz_report():

@@ -789,25 +789,35 @@ def test_randsvd_restatement_on_gpu():
 
 def test_pca_randsvd_seeded_matches_oracle(vb, golden_inputs):
     """``pca(svd_mode='randsvd')`` end to end with the reference's own source of randomness (numpy's global
-    RandomState, seeded identically on both sides => identical Omega): residual cube at 1e-4, final frame by the
-    fp32 parity rule.  (Round 1 only compared with the exact PCA at 5e-3.)"""
+    RandomState, seeded identically on both sides => identical Omega): residual cube at 1e-4 and final frame at
+    3e-4 against the oracle run on the FLOAT64-CAST cube.  scikit-learn computes in the dtype of its input and does
+    not normalise its two power iterations, so its fp32 run on a cube that still contains the stellar halo is
+    rounding noise after the first components (the two seeds below differ by O(1) of max|residual| in fp32 and by
+    1e-8 in float64); the CUDA path accumulates in fp64.  (Round 1 only compared with the exact PCA at 5e-3.)"""
     cube, angs = golden_inputs["small"]
+    c64 = cube.astype(np.float64)
     np.random.seed(1)
     frame, pcs, recon, res, res_ = vb.pca(cube, angs, ncomp=4, svd_mode="randsvd", verbose=False, full_output=True)
     np.random.seed(1)
-    o_frame, o_pcs, o_recon, o_res, o_res_ = O.pca_fullframe(cube, angs, ncomp=4, svd_mode="randsvd",
-                                                              full_output=True)
+    o_frame, o_pcs, o_recon, o_res, o_res_ = O.pca_fullframe(c64, angs, ncomp=4, svd_mode="randsvd", full_output=True)
     e_res = float(np.max(np.abs(res - o_res)) / np.max(np.abs(o_res)))
-    print(f"[parity] randsvd seeded, 30x41x41 ncomp=4: residual cube {e_res:.2e}, frame {rel_err(frame, o_frame):.2e}")
+    e_fr = rel_err(frame, o_frame)
+    np.random.seed(1)
+    o32 = O.project_subtract(cube, 4, svd_mode="randsvd")
+    e_ref32 = float(np.max(np.abs(o32 - o_res)) / np.max(np.abs(o_res)))
+    print(f"[parity] randsvd seeded, 30x41x41 ncomp=4 vs the float64 reference run: residual cube {e_res:.2e}, frame "
+          f"{e_fr:.2e}; the reference's fp32 run vs its float64 run: {e_ref32:.2e}")
     assert e_res < PCA_TOL
-
-    def truth():
-        np.random.seed(1)
-        return O.pca_fullframe(cube.astype(np.float64), angs, ncomp=4, svd_mode="randsvd")
-    assert_parity(frame, o_frame, truth, FRAME_TOL, "randsvd frame")
-    # and the randomized PCs span the exact leading subspace of this gapped cube
-    ref = O.pca_fullframe(cube, angs, ncomp=4, svd_mode="lapack")
-    assert rel_err(frame, ref) < 5e-3
+    assert e_fr < FRAME_TOL
+    # mildly conditioned input (temporal mean removed): here the reference's fp32 arithmetic is sound, direct comparison
+    cm = cube - cube.mean(axis=0)
+    np.random.seed(3)
+    fr = vb.pca(cm, angs, ncomp=4, svd_mode="randsvd", verbose=False)
+    np.random.seed(3)
+    ref = O.pca_fullframe(cm, angs, ncomp=4, svd_mode="randsvd")
+    print(f"[parity] randsvd seeded, mean-removed cube, vs the fp32 reference run: frame {rel_err(fr, ref):.2e}")
+    assert_parity(fr, ref, lambda: O.pca_fullframe(cm.astype(np.float64), angs, ncomp=4, svd_mode="lapack"), 5e-3,
+                  "randsvd frame, mean-removed cube")
 
 
 # ------------------------------------------------------------------ ADI+mSDI (4-d IFS cubes)

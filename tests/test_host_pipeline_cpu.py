@@ -226,3 +226,28 @@ def test_pca_check_memory(vb, monkeypatch):
         vb.pca(cube, angs, ncomp=2, verbose=False)
     assert vb.pca(cube, angs, ncomp=2, verbose=False, check_memory=False).shape == (16, 16)
     assert vb.pca(cube, angs, ncomp=2, batch=6, verbose=False).shape == (16, 16)
+
+
+def test_randsvd_is_the_exact_arithmetic_result_of_sklearns_algorithm(vb, golden_inputs):
+    """``svd_mode='randsvd'`` (psfsub/svd.py randomized_pcs) through the stand-ins: with identical Omega the
+    residuals equal those of scikit-learn's ``randomized_svd`` evaluated in float64 (where its unnormalised power
+    iterations are still accurate on this cube), for a halo-dominated fp32 cube on which the reference's OWN fp32
+    run is rounding noise (checked here too: O(1) away from its float64 run)."""
+    cube, angs = golden_inputs["small"]
+    import torch
+    from vip_b200.psfsub.pca_fullfr import project_subtract_device
+    res = project_subtract_device(torch.from_numpy(cube), 4, svd_mode="randsvd",
+                                  random_state=np.random.RandomState(11)).numpy()
+    o64 = O.project_subtract(cube.astype(np.float64), 4, svd_mode="randsvd", random_state=np.random.RandomState(11))
+    o32 = O.project_subtract(cube, 4, svd_mode="randsvd", random_state=np.random.RandomState(11))
+    scale = np.max(np.abs(o64))
+    assert np.max(np.abs(res - o64)) / scale < 1e-5
+    assert np.max(np.abs(o32 - o64)) / scale > 0.1            # the reference's fp32 arithmetic has lost the subspace
+    # a spectrum gapped at ncomp: the randomized subspace is the exact one
+    exact = O.project_subtract(cube.astype(np.float64), 4, svd_mode="lapack")
+    assert np.max(np.abs(res - exact)) / scale < 1e-5
+    # end to end (global RandomState like the reference), frame against the float64 reference run
+    np.random.seed(3)
+    fr = vb.pca(cube, angs, ncomp=4, svd_mode="randsvd", verbose=False)
+    np.random.seed(3)
+    assert rel_err(fr, O.pca_fullframe(cube.astype(np.float64), angs, ncomp=4, svd_mode="randsvd")) < 1e-4

@@ -158,3 +158,33 @@ def test_vectorised_library_indices_match_reference_rule():
             for f in range(len(angs)):
                 np.testing.assert_array_equal(lists[f], O.find_indices_adi(angs, f, thr, truncate=True,
                                                                             max_frames=mf))
+
+
+def test_randsvd_stable_is_sklearns_algorithm_in_exact_arithmetic():
+    """``O.randsvd_stable`` (QR after every multiplication) against scikit-learn's ``randomized_svd`` itself and the
+    literal restatement ``O.randsvd_restated``, identical Omega, float64, on a mildly conditioned matrix where the
+    unnormalised iterations are accurate: same components (sign convention included).  On a halo-dominated fp32 cube
+    scikit-learn's own fp32 run has lost the subspace (O(1) away) while the stable evaluation still equals the exact
+    PCA of a spectrum gapped at ncomp."""
+    from sklearn.utils.extmath import randomized_svd
+    from tools.synth import adi_cube
+    cube, _ = adi_cube(60, 40, 6, 60.0, seed=21)
+    M = cube.reshape(60, -1).astype(np.float64)
+    M = M - M.mean(axis=0)
+    k = 6
+    rs = np.random.RandomState(4)
+    omega = rs.normal(size=(60, k + 10))
+    _, _, V_sk = randomized_svd(M, n_components=k, n_iter=2, transpose="auto", random_state=np.random.RandomState(4))
+    V_st = O.randsvd_stable(M, k, omega)
+    V_re = O.randsvd_restated(M, k, omega)
+    np.testing.assert_allclose(V_st, V_sk, atol=1e-9)
+    np.testing.assert_allclose(V_re, V_sk, atol=1e-9)
+    # halo-dominated fp32 input
+    M32 = cube.reshape(60, -1)
+    U, s, Vt = np.linalg.svd(M32.astype(np.float64), full_matrices=False)
+    P_exact = Vt[:k].T @ Vt[:k]
+    V_st32 = O.randsvd_stable(M32, k, omega)
+    _, _, V_sk32 = randomized_svd(M32, n_components=k, n_iter=2, transpose="auto",
+                                  random_state=np.random.RandomState(4))
+    assert np.max(np.abs(V_st32.T @ V_st32 - P_exact)) < 1e-6
+    assert np.max(np.abs(V_sk32.T.astype(np.float64) @ V_sk32 - P_exact)) > 1e-2

@@ -30,7 +30,9 @@ SIGNATURES = {
     "vb_eigh_topk_f64": (_i, [_vp, _i, _i, _d, _i, _vp, _vp, _vp, _sz, C.POINTER(_i), _vp]),
     "vb_eigh_topk_async_f64": (_i, [_vp, _i, _i, _d, _i, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vb_pcs_f32": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp]),
+    "vb_pcs_hilo_f32": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _vp]),
     "vb_project_subtract_f32": (_i, [_vp, _vp, _i, _vp, _i, _i, _sz, _vp, _vp]),
+    "vb_project_subtract_hp_f32": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _sz, _vp, _vp]),
     "vb_sub_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "vb_derotate_scratch_bytes": (_sz, [_i, _i, _i, _sz]),
     "vb_derotate_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _sz, _i, _vp]),

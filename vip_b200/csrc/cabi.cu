@@ -30,9 +30,11 @@ int eigh_f64(const double*, int, double*, double*, int, double, void*, size_t, i
 size_t eigh_topk_workspace_bytes(int n, int B);
 int eigh_topk_f64(const double*, int, int, double, int, double*, double*, void*, size_t, int*, int*, cudaStream_t,
                   int* async_info = nullptr);
-int pcs_f32(const double*, const float*, int, int, size_t, float*, int*, cudaStream_t);
+int pcs_f32(const double*, const float*, int, int, size_t, float*, float*, int*, cudaStream_t);
 int project_subtract_f32(const float*, const float*, int, const float*, int, int, size_t, float*, int*,
                          cudaStream_t);
+int project_subtract_hp_f32(const float*, const double*, int, const float*, const float*, int, int, size_t, float*,
+                            int*, cudaStream_t);
 int sub_f32(const float*, const float*, float*, size_t, cudaStream_t);
 struct RotParams { int S; int N; int y0; int zero_masked; int mask_is_nan; float mask_val; };
 size_t derotate_scratch_bytes_per_frame(int S, int N);
@@ -156,7 +158,16 @@ int vb_eigh_topk_async_f64(const double* G, int n, int k, double tol, int max_it
 
 int vb_pcs_f32(const double* Wt, const float* M, int k, int n, size_t p, float* V, void* stream) {
     int nl = 0;
-    const int rc = pcs_f32(Wt, M, k, n, p, V, &nl, (cudaStream_t)stream);
+    const int rc = pcs_f32(Wt, M, k, n, p, V, nullptr, &nl, (cudaStream_t)stream);
+    g_launches += nl;
+    return rc;
+}
+
+int vb_pcs_hilo_f32(const double* Wt, const float* M, int k, int n, size_t p, float* Vhi, float* Vlo,
+                    void* stream) {
+    VB_REQUIRE(Vlo != nullptr, "pcs_hilo: Vlo is required");
+    int nl = 0;
+    const int rc = pcs_f32(Wt, M, k, n, p, Vhi, Vlo, &nl, (cudaStream_t)stream);
     g_launches += nl;
     return rc;
 }
@@ -165,6 +176,14 @@ int vb_project_subtract_f32(const float* M, const float* C, int ldc, const float
                             float* R, void* stream) {
     int nl = 0;
     const int rc = project_subtract_f32(M, C, ldc, V, k, n, p, R, &nl, (cudaStream_t)stream);
+    g_launches += nl;
+    return rc;
+}
+
+int vb_project_subtract_hp_f32(const float* M, const double* C, int ldc, const float* Vhi, const float* Vlo, int k,
+                               int n, size_t p, float* R, void* stream) {
+    int nl = 0;
+    const int rc = project_subtract_hp_f32(M, C, ldc, Vhi, Vlo, k, n, p, R, &nl, (cudaStream_t)stream);
     g_launches += nl;
     return rc;
 }

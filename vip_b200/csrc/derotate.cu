@@ -23,7 +23,9 @@
 //     with the closed-form Dirichlet kernel  D(t) = e^{-i pi t/N} sin(pi t) / (N sin(pi t/N)),
 //     evaluated directly on the non-zero support.
 #include "common.cuh"
+#include "fft_packed.cuh"
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 namespace vb {
@@ -556,6 +558,257 @@ struct ShearFft {
     }
 };
 
+// =====================================================================================
+// The same transforms on PACKED fp32 pairs (FFMA2 / FADD2 / FMUL2, csrc/fft_packed.cuh): one complex number per
+// aligned register pair.  Identical data flow, shared-memory layout, twiddles and phase arithmetic as ShearFft
+// above -- only the instruction selection of the complex arithmetic changes (a complex add is one instruction, a
+// complex multiply two, +-i a free operand modifier), which halves the FP32 instruction count of kernels that are
+// instruction-issue bound.  Selected at run time (VIP_B200_FFT_F32X2, default 1) so both can be timed and tested.
+// =====================================================================================
+struct Twiddle6P {
+    float2 b1, b2, b3, a1, a2, a3;        // w^1, w^2, w^3, w^4, w^8, w^12
+    template <int N, bool CONJ>
+    __device__ __forceinline__ void load(const float2* __restrict__ tw, int m) {
+        const float2 w1 = __ldg(tw + (m & (N - 1)));
+        const float2 w2 = __ldg(tw + ((2 * m) & (N - 1)));
+        const float2 w4 = __ldg(tw + ((4 * m) & (N - 1)));
+        const float2 w8 = __ldg(tw + ((8 * m) & (N - 1)));
+        const float sg = CONJ ? -1.f : 1.f;
+        b1 = make_float2(w1.x, sg * w1.y);
+        b2 = make_float2(w2.x, sg * w2.y);
+        a1 = make_float2(w4.x, sg * w4.y);
+        a2 = make_float2(w8.x, sg * w8.y);
+        b3 = pk::cmul2(b1, b2);
+        a3 = pk::cmul2(a1, a2);
+    }
+    __device__ __forceinline__ void apply(int k, float2& x) const {
+        const int a = k >> 2, b = k & 3;
+        if (b == 1)      x = pk::cmul2(x, b1);
+        else if (b == 2) x = pk::cmul2(x, b2);
+        else if (b == 3) x = pk::cmul2(x, b3);
+        if (a == 1)      x = pk::cmul2(x, a1);
+        else if (a == 2) x = pk::cmul2(x, a2);
+        else if (a == 3) x = pk::cmul2(x, a3);
+    }
+};
+
+// x * w16^(-e) for e in [0, 16): exponents above 7 are the negated lower half
+__device__ __forceinline__ float2 mul_w16n(int e, float2 x) {
+    if (e < 8) return pk::mul_w16<-1>(e, x);
+    const float2 y = pk::mul_w16<-1>(e - 8, x);
+    return make_float2(-y.x, -y.y);
+}
+__device__ __forceinline__ float2 mul_w16p(int e, float2 x) {
+    if (e < 8) return pk::mul_w16<+1>(e, x);
+    const float2 y = pk::mul_w16<+1>(e - 8, x);
+    return make_float2(-y.x, -y.y);
+}
+
+// forward radix-16 DFT with inputs 0..3 only (see dft16_in4)
+__device__ __forceinline__ void dft16_in4_p(float2 (&z)[16]) {
+    const float2 x0 = z[0], x1 = z[1], x2 = z[2], x3 = z[3];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        float2 y0 = x0, y1 = mul_w16n(b, x1), y2 = mul_w16n(2 * b, x2), y3 = mul_w16n(3 * b, x3);
+        pk::dft4<-1>(y0, y1, y2, y3);
+        z[b] = y0; z[4 + b] = y1; z[8 + b] = y2; z[12 + b] = y3;
+    }
+}
+// inverse radix-16 DFT with outputs 0..3 only (see dft16_out4)
+__device__ __forceinline__ void dft16_out4_p(float2 (&z)[16]) {
+    float2 o0 = make_float2(0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        float2 u0 = z[b], u1 = z[4 + b], u2 = z[8 + b], u3 = z[12 + b];
+        pk::dft4<+1>(u0, u1, u2, u3);
+        o0 = pk::add2(o0, u0);
+        o1 = pk::add2(o1, mul_w16p(b, u1));
+        o2 = pk::add2(o2, mul_w16p(2 * b, u2));
+        o3 = pk::add2(o3, mul_w16p(3 * b, u3));
+    }
+    z[0] = o0; z[1] = o1; z[2] = o2; z[3] = o3;
+}
+
+// PAD = false: the XOR-swizzled buffer layout of ShearFft (bank-conflict free, but every access pays a LOP3 + an
+// address add).  PAD = true: a PADDED layout with the same conflict-freedom in which every shared-memory access of a
+// thread is `base register + compile-time offset`:
+//   exchange A (stage 1 -> 2): element (row k1, column x)      at  k1 * PITCH + x
+//   exchange B (stage 2 -> 3): element (block k1p, q in [0,L1)) at  k1p * PITCH + q + (q >> 4)
+// with PITCH = 17 * R3 = L1 + L1/16: the 16 contiguous points a thread owns in stage 3 sit at pitch 17 (bank =
+// (tt + e) mod 16 over the lanes), and PITCH = R3 mod 16 puts the R3-thread groups of adjacent blocks on disjoint
+// banks for the stride-R3 accesses of stage 2 (checked for R3 = 2, 4, 8, 16 in tools/fft_pad_model.py).
+template <int N, bool PAD>
+struct ShearFftP {
+    using B = ShearFft<N>;
+    static constexpr int T = B::T, R3 = B::R3, L1 = B::L1, L2 = B::L2, LOG_R3 = B::LOG_R3, G3 = B::G3;
+    static constexpr int LOG_L1 = B::LOG_L1;
+    static constexpr int PITCH = 17 * R3;
+    static constexpr int BUF = PAD ? 16 * PITCH + 4 : B::BUF;
+
+    // exchange A: row k1 (compile-time at the call sites), column x
+    __device__ __forceinline__ static int iA(int k1, int x) { return PAD ? k1 * PITCH + x : B::sw1(k1 * L1 + x); }
+    // exchange B, stage-2 side: block k1p, element k2 * L2 + npp (k2 compile-time, npp < L2 <= 16, L2 | 16)
+    __device__ __forceinline__ static int iB2(int k1p, int k2, int npp) {
+        return PAD ? k1p * PITCH + npp + k2 * L2 + ((k2 * L2) >> 4) : B::sw2(k1p * L1 + k2 * L2 + npp);
+    }
+    // exchange B, stage-3 side: flat element 16 t + e
+    __device__ __forceinline__ static int iB3(int t, int e) {
+        return PAD ? (t >> LOG_R3) * PITCH + 17 * (t & (R3 - 1)) + e : B::sw2(16 * t + e);
+    }
+    // exchange-B position of an arbitrary flat element P (base a multiple of R3, i < R3 added by the caller)
+    __device__ __forceinline__ static int iBflat(int P) {
+        if (!PAD) return B::sw2(P);
+        const int q = P & (L1 - 1);
+        return (P >> LOG_L1) * PITCH + q + (q >> 4);
+    }
+
+    template <bool IN4>
+    __device__ __forceinline__ static void forward(float2 (&z)[16], float2* buf, const float2* __restrict__ tw,
+                                                   int t, int tr, float2 x4) {
+        const int npp = t & (L2 - 1), k1p = t >> LOG_R3;
+        Twiddle6P w;
+        if (IN4) {
+            dft16_in4_p(z);
+            if (t == 0) {   // the lone sample at n' = 4T adds x4 * (-i)^k1 to every output of thread 0
+                const float2 c1 = make_float2(x4.y, -x4.x), c2 = make_float2(-x4.x, -x4.y), c3 = make_float2(-x4.y, x4.x);
+#pragma unroll
+                for (int k1 = 0; k1 < 16; ++k1) {
+                    const int q = k1 & 3;
+                    z[k1] = pk::add2(z[k1], (q == 0) ? x4 : (q == 1) ? c1 : (q == 2) ? c2 : c3);
+                }
+            }
+        } else {
+            pk::dif<16, -1, 0>(z);
+        }
+        w.template load<N, false>(tw, t);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) {
+            const int r = IN4 ? k1 : brev(k1, 4);
+            w.apply(k1, z[r]);
+            buf[iA(k1, t)] = z[r];
+        }
+        transform_sync<T>(tr);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = buf[iA(k1p, j * L2 + npp)];
+        pk::dif<16, -1, 0>(z);
+        w.template load<N, false>(tw, npp * 16);
+        B::group_sync();
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+            const int r = brev(k2, 4);
+            w.apply(k2, z[r]);
+            buf[iB2(k1p, k2, npp)] = z[r];
+        }
+        B::group_sync();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) z[e] = buf[iB3(t, e)];
+        pk::GroupFft<R3, -1, G3>::fwd(z);
+    }
+
+    template <bool OUT4>
+    __device__ __forceinline__ static void inverse(float2 (&z)[16], float2* buf, const float2* __restrict__ tw,
+                                                   int t, int tr) {
+        const int npp = t & (L2 - 1), k1p = t >> LOG_R3;
+        Twiddle6P w;
+        pk::GroupFft<R3, +1, G3>::inv(z);
+        B::group_sync();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) buf[iB3(t, e)] = z[e];
+        w.template load<N, true>(tw, npp * 16);
+        B::group_sync();
+        {
+            float2 y[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float2 v = buf[iB2(k1p, j, npp)];
+                w.apply(j, v);
+                y[brev(j, 4)] = v;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = y[j];
+        }
+        pk::dit<16, +1, 0>(z);
+        B::group_sync();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) buf[iA(k1p, j * L2 + npp)] = z[j];
+        w.template load<N, true>(tw, t);
+        transform_sync<T>(tr);
+        {
+            float2 y[16];
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) {
+                float2 v = buf[iA(k1, t)];
+                w.apply(k1, v);
+                y[OUT4 ? k1 : brev(k1, 4)] = v;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = y[j];
+        }
+        if (OUT4) dft16_out4_p(z);
+        else pk::dit<16, +1, 0>(z);
+    }
+
+    // two real lines per complex transform: see ShearFft::run_pair (same bookkeeping, packed arithmetic)
+    template <bool IN4, bool OUT4>
+    __device__ __forceinline__ static void run_pair(float (&re)[16], float (&im)[16], float2* buf, float2* zbuf,
+                                                    float2* ph3, const float2* __restrict__ tw, int t, int tr,
+                                                    int sa_int, float sa_frac, int sb_int, float sb_frac,
+                                                    float x4r, float x4i, float& nyq_a, float& nyq_b) {
+        float2 z[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = make_float2(re[j], im[j]);
+        if (t < 2 * R3) {
+            const bool second = t >= R3;
+            ph3[t] = B::phase3(second ? t - R3 : t, second ? sb_int : sa_int, second ? sb_frac : sa_frac,
+                               0.5f / N);
+        }
+        forward<IN4>(z, buf, tw, t, tr, make_float2(x4r, x4i));
+#pragma unroll
+        for (int e = 0; e < 16; ++e) zbuf[iB3(t, e)] = z[e];
+        transform_sync<T>(tr);
+        nyq_a = 0.f; nyq_b = 0.f;
+#pragma unroll
+        for (int g = 0; g < G3; ++g) {
+            const int q = t * G3 + g;
+            const int kb = (q >> 4) + 16 * (q & 15);
+            float2 ea, eb;
+            phase_of<N>(sa_int, sa_frac, kb, ea.x, ea.y);
+            phase_of<N>(sb_int, sb_frac, kb, eb.x, eb.y);
+            const int kbp = (256 - kb) & 255;
+            const int basep = R3 * (((kbp & 15) << 4) | (kbp >> 4));
+            const float2* zmir = zbuf + (PAD ? iBflat(basep) : 0);     // PAD: + i below; swizzled: full index below
+#pragma unroll
+            for (int k3 = 0; k3 < R3; ++k3) {
+                const int r = g * R3 + brev(k3, LOG_R3);
+                const int i1 = brev(R3 - 1 - k3, LOG_R3), i0 = brev((R3 - k3) & (R3 - 1), LOG_R3);
+                const int isel = (kb != 0 ? i1 : i0);
+                const float2 zp = PAD ? zmir[isel] : zbuf[B::sw2(basep + isel)];
+                float2 pa = pk::cmul2(ea, ph3[k3]);
+                float2 pb = pk::cmul2(eb, ph3[R3 + k3]);
+                if (k3 == R3 / 2 && kb == 0) {      // Nyquist bin (thread 0 only)
+                    nyq_a = 2.f * z[r].x * pa.y;
+                    nyq_b = 2.f * z[r].y * pb.y;
+                    pa.y = 0.f; pb.y = 0.f;
+                }
+                const float2 hs = pk::add2(pa, pb), hd = pk::sub2(pa, pb);
+                // z * hs + conj(zp) * hd
+                float2 acc = pk::cmul2(z[r], hs);
+                acc = pk::fma2(pk::bc(zp.x), hd, acc);
+                acc = pk::fma2(pk::bc(zp.y), make_float2(hd.y, -hd.x), acc);
+                z[r] = acc;
+            }
+        }
+        inverse<OUT4>(z, buf, tw, t, tr);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { re[j] = z[j].x; im[j] = z[j].y; }
+    }
+};
+
+// transform class of a kernel: MODE 0 = scalar arithmetic (round 1), 1 = packed fp32x2, 2 = packed + padded layout
+template <int N, int MODE> struct FftSel { using type = ShearFft<N>; };
+template <int N> struct FftSel<N, 1> { using type = ShearFftP<N, false>; };
+template <int N> struct FftSel<N, 2> { using type = ShearFftP<N, true>; };
+
 // Column label n' of the re-indexed planes T1/T2 <-> physical plane column (n' + y0) mod N.
 
 // ---- pass 1: rows [y0, y0+S], real gathered input -> T1[(S+1) x N] complex (re-indexed columns)
@@ -892,12 +1145,12 @@ __device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gsrc
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
 
-template <int N, int NT, int MINB, int PP>
+template <int N, int NT, int MINB, int PP, int P2 = 0>
 __global__ void __launch_bounds__(NT * N / 16, MINB)
 shear_rows_first_pk_loop(const float* __restrict__ in, float* __restrict__ T1, float* __restrict__ aux,
                          RotParams g, const int* __restrict__ krot, const double* __restrict__ a_coef,
                          const float2* __restrict__ tw, int frame0) {
-    using F = ShearFft<N>;
+    using F = typename FftSel<N, P2>::type;
     constexpr int T = F::T;
     extern __shared__ float2 smem2[];
     __shared__ float2 ph3s[NT][32];
@@ -1017,11 +1270,11 @@ shear_aux_beta(float* __restrict__ aux, RotParams g, const double* __restrict__ 
 // The (S+1) x NC real slab is loaded with 16-byte vectors (NC*4-byte segments per row), kept column-major
 // in shared memory (pitch = 4 mod 32 words: conflict-free fill and column reads); results overwrite their
 // inputs and the S x NC output slab leaves the same way.
-template <int N, int NC, int MINB>
+template <int N, int NC, int MINB, int P2 = 0>
 __global__ void __launch_bounds__(N / 16, MINB)
 shear_cols_pk(const float* __restrict__ T1, float* __restrict__ T2, float* __restrict__ aux, RotParams g,
               const double* __restrict__ b_coef, const float2* __restrict__ tw, int frame0, int pitch) {
-    using F = ShearFft<N>;
+    using F = typename FftSel<N, P2>::type;
     constexpr int T = F::T;
     constexpr int V = NC / 4;               // float4 vectors per row
     extern __shared__ float2 smem2[];
@@ -1119,12 +1372,12 @@ shear_aux_gamma(float* __restrict__ aux, RotParams g, const double* __restrict__
 }
 
 // ---- pass 3 (packed): rows 2m, 2m+1 of [0, S); columns n' in [0, S) -> out, mask restored
-template <int N, int NT, int MINB>
+template <int N, int NT, int MINB, int P2 = 0>
 __global__ void __launch_bounds__(NT * N / 16, MINB)
 shear_rows_last_pk(const float* __restrict__ T2, const float* __restrict__ aux, const float* __restrict__ in,
                    float* __restrict__ out, RotParams g, const double* __restrict__ a_coef,
                    const float2* __restrict__ tw, int frame0) {
-    using F = ShearFft<N>;
+    using F = typename FftSel<N, P2>::type;
     extern __shared__ float2 smem2[];
     __shared__ float2 ph3s[NT][32];
     const int tr = threadIdx.x / F::T, t = threadIdx.x % F::T;
@@ -1497,38 +1750,56 @@ static int fft_cols_variant() {
     return v;
 }
 
-template <int N, int NC, int MINB>
+// transforms of the packed-plane kernels: 0 = scalar arithmetic (round 1), 1 = packed fp32x2 (FFMA2 / FADD2 /
+// FMUL2) on the swizzled buffers, 2 = packed fp32x2 on the padded buffers (VIP_B200_FFT_F32X2; A/B runs)
+static int fft_f32x2() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VIP_B200_FFT_F32X2");
+        v = e ? atoi(e) : 2;       // measured at C2 (r02e): derotation 8.47 / 8.41 / 7.72 ms for 0 / 1 / 2
+        if (v < 0 || v > 2) v = 2;
+    }
+    return v;
+}
+
+template <int N, int NC, int MINB, int MODE = 0>
 static int launch_cols_pk(const float* T1, float* T2, float* aux, const RotParams& g, const double* b,
                           const float2* tw, int frame0, int nf, cudaStream_t st) {
-    using F = ShearFft<N>;
+    using F = typename FftSel<N, MODE>::type;
     // conflict-free vector fill: a warp covers 32/(NC/4) rows x NC/4 vectors -> pitch = 4 (NC=8) or 2 (NC=16) mod 32
     const int pitch = ((g.S + 1 + 31) / 32) * 32 + (NC == 16 ? 2 : 4);
     const size_t smem_cols = (size_t)2 * F::BUF * sizeof(float2) + (size_t)NC * pitch * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_cols_pk<N, NC, MINB>,
+        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_cols_pk<N, NC, MINB, MODE>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    shear_cols_pk<N, NC, MINB><<<dim3(N / NC, nf), F::T, smem_cols, st>>>(T1, T2, aux, g, b, tw, frame0, pitch);
+    shear_cols_pk<N, NC, MINB, MODE><<<dim3(N / NC, nf), F::T, smem_cols, st>>>(T1, T2, aux, g, b, tw, frame0, pitch);
     VB_CHECK_LAUNCH();
     return 0;
 }
 
-template <int N, int NT, int MINB>
-static int launch_fft_chunk_pk(const float* in, float* out, float* T1, float* T2, float* aux, const RotParams& g,
-                               const int* krot, const double* a, const double* b, const float2* tw,
-                               int frame0, int nf, cudaStream_t st) {
-    using F = ShearFft<N>;
+// MODE 0: scalar transforms with every round-1 variant switch; MODE 1 / 2: packed fp32x2 transforms (swizzled /
+// padded buffers) on the default variants (looped pass 1, 16-column pass 2, one-shot pass 3)
+template <int N, int NT, int MINB, int MODE>
+static int launch_fft_chunk_pk_mode(const float* in, float* out, float* T1, float* T2, float* aux, const RotParams& g,
+                                    const int* krot, const double* a, const double* b, const float2* tw,
+                                    int frame0, int nf, cudaStream_t st) {
+    using F = typename FftSel<N, MODE>::type;
+    using F0 = ShearFft<N>;
     const size_t smem_rows = (size_t)NT * 2 * F::BUF * sizeof(float2);
-    const size_t smem_aux = (size_t)F::BUF * sizeof(float2);
+    const size_t smem_aux = (size_t)F0::BUF * sizeof(float2);
+    constexpr int PP = 4;
     static bool configured = false;
     if (!configured) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_first_pk<N, NT, MINB>,
+        if (MODE == 0) {
+            VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_first_pk<N, NT, MINB>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        }
+        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_first_pk_loop<N, NT, MINB, PP, MODE>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
-        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_first_pk_loop<N, NT, MINB, 4>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
-        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_last_pk<N, NT, MINB>,
+        VB_CHECK_CUDA(cudaFuncSetAttribute(shear_rows_last_pk<N, NT, MINB, MODE>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
         VB_CHECK_CUDA(cudaFuncSetAttribute(shear_aux_beta<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem_aux));
@@ -1537,31 +1808,34 @@ static int launch_fft_chunk_pk(const float* in, float* out, float* T1, float* T2
     const int threads = NT * F::T;
     const int pairs1 = (g.S + 2) / 2, pairs3 = g.S / 2;
     g_timer.mark(st);
-    if (fft_rows_loop()) {
-        constexpr int PP = 4;
-        shear_rows_first_pk_loop<N, NT, MINB, PP><<<dim3(ceil_div(pairs1, NT * PP), nf), threads, smem_rows, st>>>(
-            in, T1, aux, g, krot, a, tw, frame0);
-    } else {
+    if (MODE != 0 || fft_rows_loop()) {
+        shear_rows_first_pk_loop<N, NT, MINB, PP, MODE>
+            <<<dim3(ceil_div(pairs1, NT * PP), nf), threads, smem_rows, st>>>(in, T1, aux, g, krot, a, tw, frame0);
+    } else if (MODE == 0) {
         shear_rows_first_pk<N, NT, MINB><<<dim3(ceil_div(pairs1, NT), nf), threads, smem_rows, st>>>(
             in, T1, aux, g, krot, a, tw, frame0);
     }
     VB_CHECK_LAUNCH();
     g_timer.mark(st);
-    shear_aux_beta<N><<<nf, F::T, smem_aux, st>>>(aux, g, b, tw, frame0);
+    shear_aux_beta<N><<<nf, F0::T, smem_aux, st>>>(aux, g, b, tw, frame0);
     VB_CHECK_LAUNCH();
     {
         constexpr int MC = MINB > 1 ? MINB - 1 : 1;
-        const int cv = fft_cols_variant();
-        const int rc = cv == 2 ? launch_cols_pk<N, 16, MC>(T1, T2, aux, g, b, tw, frame0, nf, st)
-                     : cv == 1 ? launch_cols_pk<N, 8, MC>(T1, T2, aux, g, b, tw, frame0, nf, st)
-                               : launch_cols_pk<N, 8, MINB>(T1, T2, aux, g, b, tw, frame0, nf, st);
+        int rc;
+        if (MODE != 0) {
+            rc = launch_cols_pk<N, 16, MC, MODE>(T1, T2, aux, g, b, tw, frame0, nf, st);
+        } else {
+            const int cv = fft_cols_variant();
+            rc = cv == 2 ? launch_cols_pk<N, 16, MC>(T1, T2, aux, g, b, tw, frame0, nf, st)
+               : cv == 1 ? launch_cols_pk<N, 8, MC>(T1, T2, aux, g, b, tw, frame0, nf, st)
+                         : launch_cols_pk<N, 8, MINB>(T1, T2, aux, g, b, tw, frame0, nf, st);
+        }
         if (rc) return rc;
     }
     g_timer.mark(st);
     shear_aux_gamma<<<nf, 256, 0, st>>>(aux, g, a, frame0);
     VB_CHECK_LAUNCH();
-    if (fft_rows_loop() >= 2) {
-        constexpr int PP = 4;
+    if (MODE == 0 && fft_rows_loop() >= 2) {
         const size_t smem_last = smem_rows + (size_t)NT * 32 * F::T * sizeof(float);
         static bool cfg_last = false;
         if (!cfg_last) {
@@ -1572,12 +1846,23 @@ static int launch_fft_chunk_pk(const float* in, float* out, float* T1, float* T2
         shear_rows_last_pk_loop<N, NT, MINB, PP><<<dim3(ceil_div(pairs3, NT * PP), nf), threads, smem_last, st>>>(
             T2, aux, in, out, g, a, tw, frame0);
     } else {
-        shear_rows_last_pk<N, NT, MINB><<<dim3(ceil_div(pairs3, NT), nf), threads, smem_rows, st>>>(
+        shear_rows_last_pk<N, NT, MINB, MODE><<<dim3(ceil_div(pairs3, NT), nf), threads, smem_rows, st>>>(
             T2, aux, in, out, g, a, tw, frame0);
     }
     VB_CHECK_LAUNCH();
     g_timer.mark(st);
     return 0;
+}
+
+template <int N, int NT, int MINB>
+static int launch_fft_chunk_pk(const float* in, float* out, float* T1, float* T2, float* aux, const RotParams& g,
+                               const int* krot, const double* a, const double* b, const float2* tw,
+                               int frame0, int nf, cudaStream_t st) {
+    switch (fft_f32x2()) {
+        case 0: return launch_fft_chunk_pk_mode<N, NT, MINB, 0>(in, out, T1, T2, aux, g, krot, a, b, tw, frame0, nf, st);
+        case 1: return launch_fft_chunk_pk_mode<N, NT, MINB, 1>(in, out, T1, T2, aux, g, krot, a, b, tw, frame0, nf, st);
+        default: return launch_fft_chunk_pk_mode<N, NT, MINB, 2>(in, out, T1, T2, aux, g, krot, a, b, tw, frame0, nf, st);
+    }
 }
 
 static int launch_direct_chunk(const float* in, float* out, float2* T1, float2* T2, const RotParams& g,

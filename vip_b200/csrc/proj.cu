@@ -30,7 +30,7 @@ constexpr int PT = 256;       // threads (= pixels) per CTA
 template <int KC, int PX>
 __global__ void __launch_bounds__(PT / PX)
 pcs_kernel(const double* __restrict__ Wt, const float* __restrict__ M, int n, size_t p, int k0, int kc,
-           float* __restrict__ V) {
+           float* __restrict__ V, float* __restrict__ Vlo) {
     constexpr int WROWS = 128;
     constexpr int NT = PT / PX;
     __shared__ __align__(16) double Ws[WROWS][KC];
@@ -94,6 +94,16 @@ pcs_kernel(const double* __restrict__ Wt, const float* __restrict__ M, int n, si
                         make_float2((float)acc[0][q], (float)acc[PX - 1][q]);
                 else
                     V[(size_t)(k0 + q) * p + j] = (float)acc[0][q];
+                // optional low part: V + Vlo carries the fp64 sum to ~48 bits (error-free split), for sketches whose
+                // rows span a dynamic range that fp32 cannot hold (randomized SVD before orthonormalisation)
+                if (Vlo != nullptr) {
+                    if (PX == 2)
+                        *reinterpret_cast<float2*>(Vlo + (size_t)(k0 + q) * p + j) =
+                            make_float2((float)(acc[0][q] - (double)(float)acc[0][q]),
+                                        (float)(acc[PX - 1][q] - (double)(float)acc[PX - 1][q]));
+                    else
+                        Vlo[(size_t)(k0 + q) * p + j] = (float)(acc[0][q] - (double)(float)acc[0][q]);
+                }
             }
         }
     }
@@ -179,6 +189,88 @@ subtract_kernel(const float* Src, const float* __restrict__ C, int ldc, const fl
     }
 }
 
+// High-precision variant:  R[i][j] = fl32( Src[i][j] - sum_k C[i][k] * (Vhi[k][j] + Vlo[k][j]) )  with fp64 coefficients,
+// the principal components as an error-free fp32 pair and fp64 accumulation.  Why (measured at BASELINE config 2,
+// tests/test_gpu_configs.py): the cube holds the stellar halo (1e4) while the residuals are O(10); rounding V and C
+// to fp32 leaves an error of ~6e-8 * 1e4 in every residual pixel that is THE SAME in every frame (V does not depend
+// on the frame, C[:,0] hardly does), so it survives the temporal median: 1.0e-3 of the final frame's peak against the
+// reference run in float64, where the fp32 kernel above is 8.7e-5 on a single residual frame.  The pass stays
+// HBM-bound: KC DFMA per pixel and frame (2.6 GFLOP at config 2) hide under the 1 GB stream.
+template <int KC, int PX>
+__global__ void __launch_bounds__(PT / PX)
+subtract_hp_kernel(const float* Src, const double* __restrict__ C, int ldc, const float* __restrict__ Vhi,
+                   const float* __restrict__ Vlo, int n, size_t p, int k0, int kc, float* R) {  // Src may alias R
+    constexpr int NT = PT / PX;
+    constexpr int HROWS = 128;
+    __shared__ __align__(16) double Cs[HROWS][KC];
+    const size_t j = ((size_t)blockIdx.x * NT + threadIdx.x) * PX;
+    const bool jin = j < p;
+    double v[PX][KC];
+#pragma unroll
+    for (int q = 0; q < KC; ++q) {
+#pragma unroll
+        for (int x = 0; x < PX; ++x) {
+            double t = 0.0;
+            if (jin && q < kc) {
+                t = (double)Vhi[(size_t)(k0 + q) * p + j + x];
+                if (Vlo != nullptr) t += (double)Vlo[(size_t)(k0 + q) * p + j + x];
+            }
+            v[x][q] = t;
+        }
+    }
+    for (int i0 = 0; i0 < n; i0 += HROWS) {
+        const int ni = (n - i0 < HROWS) ? n - i0 : HROWS;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < ni * KC; idx += NT) {
+            const int i = idx / KC, q = idx % KC;
+            Cs[i][q] = (q < kc) ? C[(size_t)(i0 + i) * ldc + k0 + q] : 0.0;
+        }
+        __syncthreads();
+        if (jin) {
+            const float* src = Src + (size_t)i0 * p + j;
+            float* dst = R + (size_t)i0 * p + j;
+            for (int ib = 0; ib < ni; ib += 8) {
+                float mv[8][PX];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (PX == 2) {
+                        const float2 t = (ib + u < ni) ? *reinterpret_cast<const float2*>(src + (size_t)(ib + u) * p)
+                                                       : make_float2(0.f, 0.f);
+                        mv[u][0] = t.x;
+                        mv[u][PX - 1] = t.y;
+                    } else {
+                        mv[u][0] = (ib + u < ni) ? src[(size_t)(ib + u) * p] : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (ib + u < ni) {
+                        double s[PX][2];
+#pragma unroll
+                        for (int x = 0; x < PX; ++x) s[x][0] = s[x][1] = 0.0;
+#pragma unroll
+                        for (int q2 = 0; q2 < KC; q2 += 2) {
+                            const double2 c = *reinterpret_cast<const double2*>(&Cs[ib + u][q2]);
+#pragma unroll
+                            for (int x = 0; x < PX; ++x) {
+                                s[x][0] = fma(c.x, v[x][q2 + 0], s[x][0]);
+                                s[x][1] = fma(c.y, v[x][q2 + 1], s[x][1]);
+                            }
+                        }
+                        const float r0 = (float)((double)mv[u][0] - (s[0][0] + s[0][1]));
+                        if (PX == 2) {
+                            const float r1 = (float)((double)mv[u][PX - 1] - (s[PX - 1][0] + s[PX - 1][1]));
+                            *reinterpret_cast<float2*>(dst + (size_t)(ib + u) * p) = make_float2(r0, r1);
+                        } else {
+                            dst[(size_t)(ib + u) * p] = r0;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // out = a - b (elementwise), used for `reconstructed = matrix - residuals` when full_output asks for it
 __global__ void sub_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                            size_t count) {
@@ -187,19 +279,20 @@ __global__ void sub_kernel(const float* __restrict__ a, const float* __restrict_
 }
 
 // V (k x p, fp32) = Wt (k x n, row-major, fp64) . M (n x p, fp32), fp64 accumulation
-int pcs_f32(const double* Wt, const float* M, int k, int n, size_t p, float* V, int* launches, cudaStream_t st) {
+int pcs_f32(const double* Wt, const float* M, int k, int n, size_t p, float* V, float* Vlo, int* launches,
+            cudaStream_t st) {
     VB_REQUIRE(k > 0 && n > 0 && p > 0, "pcs: empty problem");
     static const int px_env = [] { const char* e = getenv("VIP_B200_PCS_PX"); return e ? atoi(e) : 2; }();
     const bool two = px_env == 2 && (p % 2 == 0) && (reinterpret_cast<uintptr_t>(M) % 8 == 0) &&
-                     (reinterpret_cast<uintptr_t>(V) % 8 == 0);
+                     (reinterpret_cast<uintptr_t>(V) % 8 == 0) && (reinterpret_cast<uintptr_t>(Vlo) % 8 == 0);
     const unsigned grid = (unsigned)ceil_div(p, (size_t)PT);      // PT pixels per CTA for both variants
     int nl = 0;
     for (int k0 = 0; k0 < k; k0 += KCMAX) {
         const int kc = (k - k0 < KCMAX) ? k - k0 : KCMAX;
 #define VB_PCS_LAUNCH(KCV)                                                                           \
         do {                                                                                         \
-            if (two) pcs_kernel<KCV, 2><<<grid, PT / 2, 0, st>>>(Wt, M, n, p, k0, kc, V);            \
-            else     pcs_kernel<KCV, 1><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V);                \
+            if (two) pcs_kernel<KCV, 2><<<grid, PT / 2, 0, st>>>(Wt, M, n, p, k0, kc, V, Vlo);           \
+            else     pcs_kernel<KCV, 1><<<grid, PT, 0, st>>>(Wt, M, n, p, k0, kc, V, Vlo);           \
         } while (0)
         if (kc <= 8)       VB_PCS_LAUNCH(8);
         else if (kc <= 16) VB_PCS_LAUNCH(16);
@@ -237,6 +330,35 @@ int project_subtract_f32(const float* M, const float* C, int ldc, const float* V
         else if (kc <= 24) VB_SUB_LAUNCH(24);
         else               VB_SUB_LAUNCH(32);
 #undef VB_SUB_LAUNCH
+        VB_CHECK_LAUNCH();
+        ++nl;
+    }
+    if (launches) *launches = nl;
+    return 0;
+}
+
+// R (n x p) = M - C (n x k fp64, leading dimension ldc) . (Vhi + Vlo) (k x p), fp64 accumulation; Vlo may be null.
+int project_subtract_hp_f32(const float* M, const double* C, int ldc, const float* Vhi, const float* Vlo, int k, int n,
+                            size_t p, float* R, int* launches, cudaStream_t st) {
+    VB_REQUIRE(k > 0 && n > 0 && p > 0, "project_subtract_hp: empty problem");
+    const bool al = (p % 2 == 0) && (reinterpret_cast<uintptr_t>(M) % 8 == 0) && (reinterpret_cast<uintptr_t>(R) % 8 == 0);
+    const unsigned grid = (unsigned)ceil_div(p, (size_t)PT);
+    int nl = 0;
+    for (int k0 = 0; k0 < k; k0 += KCMAX) {
+        const int kc = (k - k0 < KCMAX) ? k - k0 : KCMAX;
+        const float* src = (k0 == 0) ? M : R;
+        // two pixels per thread while 2 * KC fp64 components fit the register file comfortably
+#define VB_SUBHP_LAUNCH(KCV, TWO)                                                                               \
+        do {                                                                                                    \
+            if (TWO && al) subtract_hp_kernel<KCV, 2><<<grid, PT / 2, 0, st>>>(src, C, ldc, Vhi, Vlo, n, p, k0, kc, R); \
+            else           subtract_hp_kernel<KCV, 1><<<grid, PT, 0, st>>>(src, C, ldc, Vhi, Vlo, n, p, k0, kc, R);     \
+        } while (0)
+        if (kc <= 8)       VB_SUBHP_LAUNCH(8, true);
+        else if (kc <= 16) VB_SUBHP_LAUNCH(16, true);
+        else if (kc <= 20) VB_SUBHP_LAUNCH(20, true);
+        else if (kc <= 24) VB_SUBHP_LAUNCH(24, true);
+        else               VB_SUBHP_LAUNCH(32, false);
+#undef VB_SUBHP_LAUNCH
         VB_CHECK_LAUNCH();
         ++nl;
     }

@@ -117,6 +117,20 @@ def pcs(Wt, M):
     return V
 
 
+def pcs_hilo(Wt, M):
+    """(Vhi, Vlo) fp32 (k,p) with Vhi + Vlo = Wt (k,n) . M (n,p) carried to ~48 bits (fp64 accumulation, error-free
+    split): for products whose rows span more dynamic range than fp32 holds (raw randomized-SVD sketches)."""
+    lib = _cabi.lib()
+    Wt = Wt.to(torch.float64).contiguous()
+    k, n = Wt.shape
+    n2, p = M.shape
+    assert n == n2
+    Vhi = empty((k, p), torch.float32, M.device)
+    Vlo = empty((k, p), torch.float32, M.device)
+    _cabi.check(lib.vb_pcs_hilo_f32(ptr(Wt), ptr(M), k, n, p, ptr(Vhi), ptr(Vlo), stream_ptr()), "vb_pcs_hilo_f32")
+    return Vhi, Vlo
+
+
 def project_subtract(M, Cm, V, out=None):
     """R (n,p) = M - Cm (n,k) . V (k,p), fp32."""
     lib = _cabi.lib()
@@ -126,6 +140,19 @@ def project_subtract(M, Cm, V, out=None):
     R = out if out is not None else empty((n, p), torch.float32, M.device)
     _cabi.check(lib.vb_project_subtract_f32(ptr(M), ptr(Cm), k, ptr(V), k, n, p, ptr(R), stream_ptr()),
                 "vb_project_subtract_f32")
+    return R
+
+
+def project_subtract_hp(M, C64, Vhi, Vlo=None, out=None):
+    """R (n,p) fp32 = M - C64 (n,k fp64) . (Vhi + Vlo) (k,p), fp64 accumulation, one final rounding."""
+    lib = _cabi.lib()
+    n, p = M.shape
+    k = Vhi.shape[0]
+    C64 = C64.to(torch.float64).contiguous()
+    assert C64.shape == (n, k) and Vhi.is_contiguous() and (Vlo is None or Vlo.is_contiguous())
+    R = out if out is not None else empty((n, p), torch.float32, M.device)
+    _cabi.check(lib.vb_project_subtract_hp_f32(ptr(M), ptr(C64), k, ptr(Vhi), ptr(Vlo), k, n, p, ptr(R), stream_ptr()),
+                "vb_project_subtract_hp_f32")
     return R
 
 

@@ -68,19 +68,26 @@ class CudaOps:
             return None
         return kernels.eigh_topk_async(G, k)
 
+    # The principal components travel as ONE stacked tensor [Vhi; Vlo] (2k, p_g): the error-free fp32 pair of the
+    # high-precision projection (kernels.project_subtract_hp; why: csrc/proj.cu).  The driver treats it as opaque.
+    high_precision = True
+
     def pcs(self, Wt, M):
-        return kernels.pcs(Wt, M)
+        return torch.cat(kernels.pcs_hilo(Wt, M))
 
     def randomized_pcs(self, M, ncomp, omega, reduce):
         from .psfsub.svd import randomized_pcs
-        return randomized_pcs(M, ncomp, omega, reduce=reduce)
+        return torch.cat(randomized_pcs(M, ncomp, omega, reduce=reduce, hilo=True))
 
     def coeffs(self, M, V, reduce):
-        """C (n,k) fp32 = M V^T, the pixel axis summed over the shards."""
-        return reduce(kernels.cross_gram(M, V)).to(torch.float32).contiguous()
+        """C (n,k) fp64 = M (Vhi + Vlo)^T, the pixel axis summed over the shards."""
+        k = V.shape[0] // 2
+        C2 = reduce(kernels.cross_gram(M, V))                      # (n, 2k)
+        return (C2[:, :k] + C2[:, k:]).contiguous()
 
     def project_subtract(self, M, Cm, V):
-        return kernels.project_subtract(M, Cm, V)
+        k = V.shape[0] // 2
+        return kernels.project_subtract_hp(M, Cm, V[:k], V[k:])
 
     def derotate(self, cube, angles):
         return derotate_device(cube, angles)
@@ -455,7 +462,9 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
             dist.broadcast(evecs, src=src, group=group)
         S = torch.sqrt(torch.clamp(evals, min=0.0))
         Wt = (evecs / S[:, None]).contiguous()
-        Cm = (evecs * S[:, None]).t().to(torch.float32).contiguous()
+        Cm = (evecs * S[:, None]).t().contiguous()                     # fp64 (n, k)
+        if not getattr(ops, "high_precision", False):
+            Cm = Cm.to(torch.float32)
         V = ops.pcs(Wt, M)
         _mark(timer, "pcs")
     if raw_frames is not None:

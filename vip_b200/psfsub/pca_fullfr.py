@@ -164,14 +164,17 @@ def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, 
         msg += " Increase the size of the patches or request less PCs"
         raise RuntimeError(msg.format(ncomp, nr, p))
 
+    # The projection runs in high precision (kernels.project_subtract_hp): fp64 coefficients, the components as an
+    # error-free fp32 pair, fp64 accumulation -- fp32 copies of C and V leave a frame-independent error in every
+    # residual pixel that survives the temporal median (csrc/proj.cu).  V (returned with full_output) is the hi part.
     if svd_mode in _EXACT_MODES:
         if dec is None:
             dec = Decomposition(ref_lib, ncomp, G=gram if ref_lib is matrix else None, pending=pending)
-        V = dec.pcs(ncomp)
+        V, Vlo = dec.pcs_hilo(ncomp)
         if ref_lib is matrix_emp:
-            Cm = dec.coeffs(ncomp)                # = matrix_emp . V^T from the eigenpairs
+            Cm = dec.coeffs64(ncomp)              # = matrix_emp . V^T from the eigenpairs
         else:
-            Cm = kernels.cross_gram(matrix_emp, V).to(torch.float32).contiguous()
+            Cm = kernels.cross_gram(matrix_emp, V) + kernels.cross_gram(matrix_emp, Vlo)
     elif svd_mode in _RAND_MODES:
         rs = random_state
         if rs is None:
@@ -179,14 +182,14 @@ def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, 
         elif not isinstance(rs, np.random.RandomState):
             rs = np.random.RandomState(rs)
         omega = rs.normal(size=(nr, ncomp + 10))
-        V = randomized_pcs(ref_lib, ncomp, omega)
-        Cm = kernels.cross_gram(matrix_emp, V).to(torch.float32).contiguous()
+        V, Vlo = randomized_pcs(ref_lib, ncomp, omega, hilo=True)
+        Cm = kernels.cross_gram(matrix_emp, V) + kernels.cross_gram(matrix_emp, Vlo)
     else:
         raise ValueError("The SVD `mode` is not recognized")
     if verbose:
         print("Done SVD/PCA on the GPU (vip_b200, svd_mode={})".format(svd_mode))
 
-    residuals = kernels.project_subtract(matrix, Cm, V)
+    residuals = kernels.project_subtract_hp(matrix, Cm, V, Vlo)
     residuals_cube = residuals.reshape(n, H, W)
     if full_output:
         return residuals_cube, kernels.sub(matrix, residuals), V
@@ -436,14 +439,14 @@ def _pca_grid_device(cube, cube_ref, rot_angles, range_pcs, scaling, mask_center
         msg += " Increase the size of the patches or request less PCs"
         raise RuntimeError(msg.format(pcmax, nr, p))
     dec = Decomposition(ref_lib, pcmax)
-    V = dec.pcs(pcmax)
+    V, Vlo = dec.pcs_hilo(pcmax)
     if ref_lib is matrix:
-        Cm = dec.coeffs(pcmax)
+        Cm = dec.coeffs64(pcmax)
     else:
-        Cm = kernels.cross_gram(matrix, V).to(torch.float32).contiguous()
+        Cm = kernels.cross_gram(matrix, V) + kernels.cross_gram(matrix, Vlo)
     frames = []
     for pc in pclist:
-        residuals = kernels.project_subtract(matrix, Cm[:, :pc].contiguous(), V[:pc])
+        residuals = kernels.project_subtract_hp(matrix, Cm[:, :pc].contiguous(), V[:pc], Vlo[:pc])
         der = derotate_device(residuals.reshape(n, y, x), rot_angles, mask_val=mask_val,
                               interp_zeros=interp_zeros)
         frames.append(collapse_device(der, mode=collapse, w=weights))

@@ -63,6 +63,18 @@ class Decomposition:
         Wt = (self.U[:ncomp] / s[:, None]).contiguous()          # fp64: see csrc/proj.cu
         return kernels.pcs(Wt, self.M)
 
+    def pcs_hilo(self, ncomp):
+        """(Vhi, Vlo): the same components carried as an error-free fp32 pair (~48 bits) for the high-precision
+        projection (``kernels.project_subtract_hp``); Vhi is what ``pcs`` returns."""
+        self.check_rank(ncomp)
+        s = self.S[:ncomp]
+        Wt = (self.U[:ncomp] / s[:, None]).contiguous()
+        return kernels.pcs_hilo(Wt, self.M)
+
+    def coeffs64(self, ncomp):
+        """C (n,ncomp) fp64 = U_k^T diag(s) (see ``coeffs``)."""
+        return (self.U[:ncomp] * self.S[:ncomp, None]).t().contiguous()
+
     def coeffs(self, ncomp):
         """C (n,ncomp) fp32 = M V^T = U_k^T diag(s): projection of M's own rows on its PCs."""
         return (self.U[:ncomp] * self.S[:ncomp, None]).t().to(torch.float32).contiguous()
@@ -74,10 +86,10 @@ class Decomposition:
         return np.cumsum(exp_var / np.sum(exp_var))
 
 
-def orthonormalize(Yt, reduce=None):
-    """Rows of Yt (l,p) -> orthonormal rows spanning the same space (two Gram/eigh passes).
+def orthonormalize(Yt, reduce=None, passes=2):
+    """Rows of Yt (l,p) -> orthonormal rows spanning the same space (Gram / eigh passes).
     ``reduce``: see :func:`randomized_pcs`."""
-    for _ in range(2):
+    for _ in range(passes):
         G = kernels.cross_gram(Yt, Yt)
         if reduce is not None:
             G = reduce(G)
@@ -88,27 +100,59 @@ def orthonormalize(Yt, reduce=None):
     return Yt
 
 
-def randomized_pcs(M, ncomp, omega, n_iter=2, reduce=None):
+def orthonormalize_hilo(hi, lo, reduce=None):
+    """Orthonormal basis (fp32, (l,p)) of the row space of the sketch ``hi + lo`` (error-free fp32 pair, see
+    ``kernels.pcs_hilo``).  The raw sketch is dominated by the leading singular direction -- its rows span
+    (sigma_0/sigma_k)^(2q+1) in magnitude -- so its Gramian is formed from the stacked pair in fp64
+    (G = S S^T summed over the four hi/lo blocks) and the first change of basis is applied to the pair; the result
+    has O(1) rows that are orthonormal to ~1e-4 and is safe in plain fp32, where a second ordinary pass finishes."""
+    l = hi.shape[0]
+    S = torch.cat((hi, lo))                                     # (2l, p)
+    G2 = kernels.cross_gram(S, S)
+    if reduce is not None:
+        G2 = reduce(G2)
+    G = G2[:l, :l] + G2[:l, l:] + G2[l:, :l] + G2[l:, l:]
+    G = (0.5 * (G + G.t())).contiguous()
+    evals, evecs, _ = kernels.eigh(G)
+    keep = evals > evals[0] * 1e-30
+    Wt = (evecs / torch.sqrt(torch.clamp(evals, min=1e-300))[:, None])[keep]
+    Y1 = kernels.pcs(torch.cat((Wt, Wt), dim=1).contiguous(), S)
+    return orthonormalize(Y1, reduce, passes=2)
+
+
+def randomized_pcs(M, ncomp, omega, n_iter=2, reduce=None, hilo=False):
     """scikit-learn ``randomized_svd(M, ncomp, n_iter=2, transpose='auto')`` for n < p
     (``svd.py:487-491``): with the Gaussian test matrix ``omega`` (n, ncomp+10) supplied
     by the caller,  Y = M^T (M M^T)^n_iter omega,  Q = orth(Y),  B = Q^T M^T,  PCs = (Q U_B)[:, :k]^T.
-    Any orthonormal basis of range(Y) gives the same PCs, so orth() is Gram-based here.
+
+    What is computed is the result of that algorithm IN EXACT ARITHMETIC: the sketch is re-orthonormalised after
+    every application of M^T M (the row space, hence Q's span and the PCs, is unchanged by a change of basis), the
+    raw sketches are carried as error-free fp32 pairs and every reduction runs in fp64.  scikit-learn itself computes
+    in the dtype of its input and -- for n_iter = 2 -- without any normalisation, so on a cube that still contains
+    the stellar halo (sigma_0/sigma_k ~ 1e3) the reference's fp32 components beyond the first few are rounding noise
+    (its residuals differ from one seed to the next by more than their own size) and even its
+    float64 run only holds them to ~1e-16 (sigma_0/sigma_k)^5.  On inputs where the reference's arithmetic is sound
+    the two agree to 1e-4 with identical ``omega`` (tests/test_gpu_configs.py).
 
     Pixel-sharded use (``vip_b200/parallel.py``): ``M`` is this rank's column block and
     ``reduce`` sums a small fp64 matrix over the ranks in place (NCCL all-reduce).  Every product
-    with the pixel axis contracted -- the (l,n) sketches ``Y^T M^T``, ``Q^T M^T`` and the (l,l) Gramians
-    of the orthonormalisation -- is a sum over pixel shards; everything else is local."""
+    with the pixel axis contracted -- the (l,n) sketches ``Q M^T`` and the Gramians of the orthonormalisation --
+    is a sum over pixel shards; everything else is local.  ``hilo``: return the PCs as the error-free pair
+    (Vhi, Vlo) for the high-precision projection."""
     n, p = M.shape
     red = reduce if reduce is not None else (lambda t: t)
-    Om = torch.as_tensor(np.asarray(omega, dtype=np.float32)).to(M.device)
-    Yt = kernels.pcs(Om.t().contiguous(), M)                    # (l,p) = omega^T M
+    Om = torch.as_tensor(np.asarray(omega, dtype=np.float32)).to(M.device)      # sklearn casts Omega to M's dtype
+    hi, lo = kernels.pcs_hilo(Om.t().contiguous(), M)            # (l,p) = omega^T M
+    Qt = orthonormalize_hilo(hi, lo, reduce)
     for _ in range(n_iter):
-        Z = red(kernels.cross_gram(Yt, M))                       # (l,n) = Y^T M^T
-        Yt = kernels.pcs(Z.contiguous(), M)                      # (l,p)
-    Qt = orthonormalize(Yt, reduce)
+        Z = red(kernels.cross_gram(Qt, M))                       # (l,n) = Q^T M^T
+        hi, lo = kernels.pcs_hilo(Z.contiguous(), M)             # (l,p) = (Q^T M^T) M
+        Qt = orthonormalize_hilo(hi, lo, reduce)
     B = red(kernels.cross_gram(Qt, M))                           # (l,n) fp64
     evals, evecs, _ = kernels.eigh((B @ B.t()).contiguous())
     Wt = evecs[:ncomp].contiguous()                              # rows = leading left vectors of B
+    if hilo:
+        return kernels.pcs_hilo(Wt, Qt)
     return kernels.pcs(Wt, Qt)
 
 
