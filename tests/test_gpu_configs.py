@@ -93,8 +93,8 @@ def test_c2_final_frame_vs_reference_golden(vb):
     assert e_der < 2 * PCA_TOL or ours_d < 1.5 * ref_d + 2e-5
     assert e_fr < FRAME_TOL or ours_f < 1.5 * ref_f + 2e-5
     assert ours_r < PCA_TOL and ours_f < FRAME_TOL       # and we ARE within tolerance of the truth (hp projection)
-    # the plain call (no full_output) returns the same frame bits
-    np.testing.assert_array_equal(vb.pca(cube, angs, ncomp=20, verbose=False), frame)
+    # the plain call (no full_output) takes the pipelined upload + Gramian (slab-wise summation order): same frame to 1e-5
+    assert rel_err(vb.pca(cube, angs, ncomp=20, verbose=False), frame) < 1e-5
 
 
 def test_c2_randsvd_vs_reference_golden(vb):

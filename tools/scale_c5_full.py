@@ -25,7 +25,7 @@ from tools.synth import pa_track                          # noqa: E402
 from vip_b200.parallel import pca_sharded, shard_bounds, StageTimer   # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
-size, k, K, NBLK = 1024, 50, 20, 8
+size, k, K, NBLK = 1024, 50, 50, 8        # K = ncomp speckle modes: spectrum gapped at ncomp
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -45,7 +45,7 @@ ar = np.empty((n, K))
 ar[0] = rng.standard_normal(K)
 for t in range(1, n):
     ar[t] = 0.9 * ar[t - 1] + np.sqrt(1 - 0.81) * rng.standard_normal(K)
-coef = torch.from_numpy((0.05 * (0.88 ** np.arange(K))[None, :] * (0.5 + ar)).astype(np.float32)).to(dev)
+coef = torch.from_numpy((0.05 * (0.97 ** np.arange(K))[None, :] * (0.5 + ar)).astype(np.float32)).to(dev)
 g_all = torch.Generator(device=dev).manual_seed(1234)              # identical on every rank
 yy, xx = torch.meshgrid(torch.arange(size, device=dev), torch.arange(size, device=dev), indexing="ij")
 halo = 1e4 / (1.0 + ((yy - size // 2) ** 2 + (xx - size // 2) ** 2).float() / 16.0)

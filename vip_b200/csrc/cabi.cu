@@ -28,6 +28,7 @@ int upload_gram_f32(const float*, int, size_t, float*, double*, void*, size_t, i
 size_t eigh_workspace_bytes(int n);
 int eigh_f64(const double*, int, double*, double*, int, double, void*, size_t, int*, int*, cudaStream_t);
 size_t eigh_topk_workspace_bytes(int n, int B);
+int topk_block_width(int k);
 int eigh_topk_f64(const double*, int, int, double, int, double*, double*, void*, size_t, int*, int*, cudaStream_t,
                   int* async_info = nullptr);
 int pcs_f32(const double*, const float*, int, int, size_t, float*, float*, int*, cudaStream_t);
@@ -134,7 +135,7 @@ int vb_eigh_f64(const double* G, int n, double* evals, double* evecs, int max_sw
 }
 
 size_t vb_eigh_topk_workspace_bytes(int n, int k) {
-    return eigh_topk_workspace_bytes(n, (k <= 10) ? 16 : 32);
+    return eigh_topk_workspace_bytes(n, topk_block_width(k));
 }
 
 int vb_eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, double* evals, double* evecs,

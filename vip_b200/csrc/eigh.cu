@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256)
 topk_matvec_kernel(const double* __restrict__ G, int n, const double* __restrict__ X, double* __restrict__ Y,
                    const TopkState* __restrict__ st) {
     if (st->converged) return;
-    constexpr int TJ = 128, RPC = 256 / B;
+    constexpr int TJ = (B <= 32) ? 128 : 64, RPC = 256 / B;     // 64-wide blocks: 32 KB of X per step
     __shared__ double Gs[RPC][TJ + 1];
     __shared__ double Xs[TJ][B];
     const int r0 = blockIdx.x * RPC;
@@ -497,6 +497,9 @@ topk_ritz_kernel(double* __restrict__ T, double* __restrict__ Qm, double* __rest
     if (tid < B) { theta[tid] = th[order[tid]]; res[tid] = 0.0; }
 }
 
+// rows per CTA of the rotation kernel: static shared memory holds Q (B x B) and two row slabs
+__host__ __device__ constexpr int topk_rot_rows(int B) { return B <= 32 ? 64 : 8; }
+
 // rows: Yr = Y Q, Xr = X Q (in place); S += Yr^T Yr; res[r] += ||Yr[:,r] - theta_r Xr[:,r]||^2
 template <int B>
 __global__ void __launch_bounds__(256)
@@ -504,7 +507,7 @@ topk_rotate_kernel(double* __restrict__ X, double* __restrict__ Y, int n, const 
                    const double* __restrict__ theta, double* __restrict__ S, double* __restrict__ res,
                    const TopkState* __restrict__ st) {
     if (st->converged) return;
-    constexpr int RCH = 64;
+    constexpr int RCH = topk_rot_rows(B);
     __shared__ double Qs[B][B];
     __shared__ double Ys[RCH][B], Xs[RCH][B];
     const int tid = threadIdx.x, r0 = blockIdx.x * RCH;
@@ -564,7 +567,7 @@ __global__ void topk_chol_kernel(double* __restrict__ S, double* __restrict__ re
                                  const double* __restrict__ theta, int k, double tol, double* __restrict__ R,
                                  double* __restrict__ dinv, TopkState* __restrict__ st, int check) {
     if (st->converged) return;
-    __shared__ double Sn[B][B + 1], Rm[B][B + 1], dv[B];
+    __shared__ double Sn[B][B + 1], dv[B];       // factorised IN PLACE (upper triangle becomes R): one B x B matrix
     const int lane = threadIdx.x;
     if (lane == 0) {
         st->iters += 1;
@@ -582,17 +585,19 @@ __global__ void topk_chol_kernel(double* __restrict__ S, double* __restrict__ re
     for (int e = lane; e < B * B; e += 32) Sn[e / B][e % B] = S[e] * dv[e / B] * dv[e % B];
     __syncwarp();
     for (int j = 0; j < B; ++j) {
+        // rows m < j of Sn already hold R; row j still holds the (normalised) Gram entries
         double d = Sn[j][j];
-        for (int m = 0; m < j; ++m) d -= Rm[m][j] * Rm[m][j];
+        for (int m = 0; m < j; ++m) d -= Sn[m][j] * Sn[m][j];
         d = (d > 1e-300) ? sqrt(d) : 1e-150;
+        __syncwarp();
         for (int c = j + lane; c < B; c += 32) {
             double v = Sn[j][c];
-            for (int m = 0; m < j; ++m) v -= Rm[m][j] * Rm[m][c];
-            Rm[j][c] = (c == j) ? d : v / d;
+            for (int m = 0; m < j; ++m) v -= Sn[m][j] * Sn[m][c];
+            Sn[j][c] = (c == j) ? d : v / d;
         }
         __syncwarp();
     }
-    for (int e = lane; e < B * B; e += 32) R[e] = (e / B <= e % B) ? Rm[e / B][e % B] : 0.0;
+    for (int e = lane; e < B * B; e += 32) R[e] = (e / B <= e % B) ? Sn[e / B][e % B] : 0.0;
     for (int c = lane; c < B; c += 32) dinv[c] = dv[c];
     // leave the atomic accumulators clean for the next iteration (RR or plain orthogonalisation)
     for (int e = lane; e < B * B; e += 32) { S[e] = 0.0; T[e] = 0.0; }
@@ -983,6 +988,10 @@ topk_fused_kernel(const double* __restrict__ G, int n, int k, double tol, int ma
     }
 }
 
+// block width of the subspace solver for k wanted pairs: 16 (k <= 10), 32 (k <= 24: the fused single-launch kernel),
+// 64 (k <= 56: per-phase kernels; BASELINE config 5's ncomp = 50 on the exact path, psfsub/svd.py:466-475 takes any k)
+int topk_block_width(int k) { return (k <= 10) ? 16 : (k <= 24) ? 32 : 64; }
+
 size_t eigh_topk_workspace_bytes(int n, int B) {
     return ((size_t)2 * n * B + 4 * (size_t)B * B + 4 * B) * sizeof(double) + 512;
 }
@@ -1016,6 +1025,7 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
     // fused persistent kernel: all iterations in one cooperative launch (grid = ceil(n / rows-per-CTA) <= #SMs)
     const char* fe = getenv("VIP_B200_TOPK_FUSED");
     const int fused_grid = ceil_div(n, 512 / B);
+    if constexpr (B <= 32) {
     if ((fe ? atoi(fe) : 1) && fused_grid <= kNumSMs) {
         const char* re = getenv("VIP_B200_TOPK_RR");
         int rr_every = re ? atoi(re) : 0;        // 0 = adaptive schedule (default; first Ritz step at iteration rr0), 4 = r01n
@@ -1049,6 +1059,7 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
         }
         (void)cudaGetLastError();     // cooperative launch unavailable (e.g. MPS): use the per-phase kernels below
     }
+    }
     // Rayleigh-Ritz every iteration: without it the columns of G X all tilt towards the dominant
     // eigenvector (lambda_0 / lambda_B ~ 1e5) and the Cholesky-QR of Y^T Y (condition number squared)
     // loses the trailing directions -- measured: no convergence in 400 steps with RR every 4th step.
@@ -1056,7 +1067,7 @@ static int topk_run(const double* G, int n, int k, double tol, int max_iter, dou
         topk_matvec_kernel<B><<<ceil_div(n, 256 / B), 256, 0, st>>>(G, n, X, Y, state);
         topk_xty_kernel<B><<<grows, 256, 0, st>>>(X, Y, n, T, state);
         topk_ritz_kernel<B><<<1, 16 * B, 0, st>>>(T, Qm, theta, S, res, state, jthr);
-        topk_rotate_kernel<B><<<ceil_div(n, 64), 256, 0, st>>>(X, Y, n, Qm, theta, S, res, state);
+        topk_rotate_kernel<B><<<ceil_div(n, topk_rot_rows(B)), 256, 0, st>>>(X, Y, n, Qm, theta, S, res, state);
         topk_chol_kernel<B><<<1, 32, 0, st>>>(S, res, T, theta, k, tol, R, dinv, state, 1);
         nl += 2;
         topk_solve_kernel<B><<<ceil_div(n, 128), 128, 0, st>>>(X, Y, n, R, dinv, state);
@@ -1084,12 +1095,13 @@ int eigh_topk_f64(const double* G, int n, int k, double tol, int max_iter, doubl
     VB_REQUIRE(n >= 1 && k >= 1 && k <= n, "eigh_topk: need 1 <= k <= n");
     if (tol <= 0) tol = 1e-9;    // residual / lambda_k; eigenvector error ~ tol / relative gap
     if (max_iter <= 0) max_iter = 400;   // beyond this the caller is better off with the Jacobi solver
-    const int B = (k <= 10) ? 16 : 32;
-    VB_REQUIRE(k <= 24, "eigh_topk: k=%d too large for the subspace solver (use the Jacobi solver)", k);
+    const int B = topk_block_width(k);
+    VB_REQUIRE(k <= 56, "eigh_topk: k=%d too large for the subspace solver (use the Jacobi solver)", k);
     VB_REQUIRE(n >= B, "eigh_topk: n=%d smaller than the block width %d (use the Jacobi solver)", n, B);
     VB_REQUIRE(ws_bytes >= eigh_topk_workspace_bytes(n, B), "eigh_topk: workspace too small");
     if (B == 16) return topk_run<16>(G, n, k, tol, max_iter, evals, evecs, ws, info, launches, st, async_info);
-    return topk_run<32>(G, n, k, tol, max_iter, evals, evecs, ws, info, launches, st, async_info);
+    if (B == 32) return topk_run<32>(G, n, k, tol, max_iter, evals, evecs, ws, info, launches, st, async_info);
+    return topk_run<64>(G, n, k, tol, max_iter, evals, evecs, ws, info, launches, st, async_info);
 }
 
 }  // namespace vb

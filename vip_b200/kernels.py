@@ -101,8 +101,9 @@ def eigh_topk_async(G, k, tol=0.0, max_iter=0):
 
 
 def topk_supported(n, k):
-    """The subspace solver handles k <= 24 with a block (16 or 32 vectors) no wider than the matrix."""
-    return k <= 24 and n >= (16 if k <= 10 else 32) and n > 2 * k
+    """The subspace solver handles k <= 56 with a block (16, 32 or 64 vectors) no wider than the matrix
+    (k <= 24: one fused cooperative launch; 25..56: per-phase kernels, block 64)."""
+    return k <= 56 and n >= (16 if k <= 10 else 32 if k <= 24 else 64) and n > 2 * k
 
 
 def pcs(Wt, M):
