@@ -495,6 +495,11 @@ def run_gpu(args):
             cur = dict(zip(names, [float(v) for v in t.tolist()]))
             agg = cur if agg is None else {nm: min(agg[nm], cur[nm]) for nm in names}
         if rank == 0:
+            from vip_b200.parallel import PeerExchange, CudaOps
+            fused = PeerExchange.eligible(CudaOps(), world, n, size, size, "median", False) and \
+                PeerExchange.get(n, size, size, world, rank, shard_bounds(n, world), pb, dev, None) is not None
+            line["exchange"] = ("fused into the projection / last shear pass over peer memory (symmetric memory, "
+                                "NVLink)" if fused else "NCCL all_to_all_single")
             line["parity_vs_single"] = parity
             line["stage_ms"] = agg
             line["stage_ms_note"] = ("CUDA events after each stage of pca_sharded, max over ranks, best of 2 untimed "

@@ -91,6 +91,13 @@ int vb_project_subtract_f32(const float* M, const float* C, int ldc, const float
  * residual pixel that survives the temporal median (measured 1e-3 of the final frame at config 2). */
 int vb_project_subtract_hp_f32(const float* M, const double* C, int ldc, const float* Vhi, const float* Vlo, int k,
                                int n, size_t p, float* R, void* stream);
+/* Scattered output: row i of the result is written to Rrows[i][0..p) (device array of n row pointers, each 8-byte
+ * aligned) instead of R + i p.  The rows may live in PEER memory mapped into this process (NVLink): in the sharded
+ * path every rank subtracts on its pixel shard and writes each residual row straight into the frame shard of the
+ * rank that will derotate it -- the pixel->frame exchange rides on the projection pass, no separate all-to-all.
+ * Rscratch (n x p) is only used by the intermediate passes when k > 32 and may be NULL otherwise. */
+int vb_project_subtract_hp_rows_f32(const float* M, const double* C, int ldc, const float* Vhi, const float* Vlo,
+                                    int k, int n, size_t p, float* Rscratch, float* const* Rrows, void* stream);
 /* out = a - b elementwise (reconstructed = matrix - residuals for full_output) */
 int vb_sub_f32(const float* a, const float* b, float* out, size_t count, void* stream);
 
@@ -108,6 +115,16 @@ size_t vb_derotate_scratch_bytes(int nframes, int S, int N, size_t max_bytes);
 int vb_derotate_f32(const float* in, float* out, int nframes, int S, int N, int y0, const int* krot,
                     const double* a, const double* b, float mask_val, int mask_is_nan, int zero_masked,
                     void* scratch, size_t scratch_bytes, int force_direct, void* stream);
+/* The same rotation with a SCATTERED output for the sharded path: output row r of local frame f goes to
+ *   out_bases[r / rows_per_shard] + (frame_offset + f) * frame_stride + (r % rows_per_shard) * S      (floats)
+ * i.e. straight into the (n_frames_total x pixels_of_shard) slab of the rank that owns those image rows; the
+ * bases may be PEER allocations mapped into this process (NVLink), so the frame->pixel exchange that precedes the
+ * temporal median needs no separate all-to-all.  out_bases_host: HOST array of `nshards` (<= 8) device pointers;
+ * rows_per_shard even, rows_per_shard * nshards == S; power-of-two frames only (N = 4S). */
+int vb_derotate_scatter_f32(const float* in, int nframes, int S, int N, int y0, const int* krot, const double* a,
+                            const double* b, float mask_val, int mask_is_nan, int zero_masked, void* scratch,
+                            size_t scratch_bytes, void* const* out_bases_host, int nshards, int rows_per_shard,
+                            long long frame_stride, int frame_offset, void* stream);
 
 /* ---- temporal collapse ---------------------------------------------------------------------
  * cube[n x p] -> out[p].  mode: 0 median, 1 mean, 2 sum, 3 max, 4 absmean, 5 wmean (w: n

@@ -24,7 +24,7 @@ def cross_gram(A, B):
     return A.double() @ B.double().T
 
 
-def eigh(G, max_sweeps=0, tol=0.0):
+def eigh(G, max_sweeps=0, tol=0.0, check=True):
     w, v = torch.linalg.eigh(G.double())
     w = w.abs()                                   # the one-sided Jacobi kernel returns column norms
     order = torch.argsort(w, descending=True, stable=True)

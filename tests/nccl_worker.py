@@ -14,6 +14,7 @@ sys.path.insert(0, ROOT)
 from tools.synth import adi_cube                                            # noqa: E402
 from tools.make_golden import ifs_cube                                      # noqa: E402
 import vip_b200                                                              # noqa: E402
+import vip_b200.parallel                                                     # noqa: E402
 from vip_b200.parallel import pca_sharded, pca_adimsdi_double_sharded        # noqa: E402
 
 
@@ -32,15 +33,31 @@ def main(out_path):
         fr = pca_sharded(cube, angs, 10, collapse=collapse)
         if rank == 0:
             res[f"exact_{collapse}"] = rel(fr, vip_b200.pca(cube, angs, ncomp=10, collapse=collapse, verbose=False))
+    # the three exchange variants: NCCL all-to-alls (subtract first / raw cube overlapped with the eigensolver) and the
+    # exchanges fused into the kernels over peer memory (default when symmetric memory is available)
+    os.environ["VIP_B200_SHARD_FUSED"] = "0"
     for overlap in (False, True):
         fr = pca_sharded(cube, angs, 10, overlap_exchange=overlap)
         if rank == 0:
             res[f"exact_overlap_{int(overlap)}"] = rel(fr, vip_b200.pca(cube, angs, ncomp=10, verbose=False))
-    # the tcgen05 Gramian + 2048-point shears on pixel / frame shards (n p >= 2^22)
     cube2, angs2 = adi_cube(130, 512, 8, 70.0, seed=78)
     fr = pca_sharded(cube2, angs2, 8)
     if rank == 0:
-        res["exact_512"] = rel(fr, vip_b200.pca(cube2, angs2, ncomp=8, verbose=False))
+        ref512 = vip_b200.pca(cube2, angs2, ncomp=8, verbose=False)
+        res["exact_512_nccl"] = rel(fr, ref512)
+    os.environ["VIP_B200_SHARD_FUSED"] = "1"
+    from vip_b200.parallel import PeerExchange
+    res["fused_available"] = bool(PeerExchange.eligible(vip_b200.parallel.CudaOps(), world, 130, 512, 512, "median", False)
+                                  and PeerExchange.get(130, 512, 512, world, rank, vip_b200.parallel.shard_bounds(130, world),
+                                                       vip_b200.parallel.shard_bounds(512 * 512, world),
+                                                       torch.device("cuda", local), None) is not None)
+    for it in range(2):                                   # twice: the second step reuses the peer buffers
+        fr = pca_sharded(cube2, angs2, 8)
+    if rank == 0:
+        res["exact_512"] = rel(fr, ref512)
+    fr = pca_sharded(cube2, angs2, 8, collapse="mean")
+    if rank == 0:
+        res["exact_512_mean"] = rel(fr, vip_b200.pca(cube2, angs2, ncomp=8, collapse="mean", verbose=False))
     # BASELINE config 5's mode: randomized SVD on pixel shards (sketch all-reduces), same omega
     fr = pca_sharded(cube, angs, 10, svd_mode="randsvd", random_state=5)
     if rank == 0:

@@ -33,9 +33,12 @@ SIGNATURES = {
     "vb_pcs_hilo_f32": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _vp]),
     "vb_project_subtract_f32": (_i, [_vp, _vp, _i, _vp, _i, _i, _sz, _vp, _vp]),
     "vb_project_subtract_hp_f32": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _sz, _vp, _vp]),
+    "vb_project_subtract_hp_rows_f32": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _sz, _vp, _vp, _vp]),
     "vb_sub_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "vb_derotate_scratch_bytes": (_sz, [_i, _i, _i, _sz]),
     "vb_derotate_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _sz, _i, _vp]),
+    "vb_derotate_scatter_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _i, _vp, _sz, _vp, _i, _i,
+                                    C.c_longlong, _i, _vp]),
     "vb_collapse_f32": (_i, [_vp, _i, _sz, _i, _vp, _i, _i, _vp, _vp]),
     "vb_annular_weights_f64": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _d, _i, _vp, _vp, _vp]),
     "vb_annular_direct_f64": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),

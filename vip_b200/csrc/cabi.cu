@@ -35,9 +35,10 @@ int pcs_f32(const double*, const float*, int, int, size_t, float*, float*, int*,
 int project_subtract_f32(const float*, const float*, int, const float*, int, int, size_t, float*, int*,
                          cudaStream_t);
 int project_subtract_hp_f32(const float*, const double*, int, const float*, const float*, int, int, size_t, float*,
-                            int*, cudaStream_t);
+                            float* const*, int*, cudaStream_t);
 int sub_f32(const float*, const float*, float*, size_t, cudaStream_t);
-struct RotParams { int S; int N; int y0; int zero_masked; int mask_is_nan; float mask_val; };
+struct OutMap { float* base[8]; int nshards; int rows_per; long long fstride; int fofs; };
+struct RotParams { int S; int N; int y0; int zero_masked; int mask_is_nan; float mask_val; OutMap om; };
 size_t derotate_scratch_bytes_per_frame(int S, int N);
 size_t derotate_scratch_bytes_min(int S, int N);
 int shift_operators(const double*, const int*, int, int, float*, cudaStream_t);
@@ -184,7 +185,16 @@ int vb_project_subtract_f32(const float* M, const float* C, int ldc, const float
 int vb_project_subtract_hp_f32(const float* M, const double* C, int ldc, const float* Vhi, const float* Vlo, int k,
                                int n, size_t p, float* R, void* stream) {
     int nl = 0;
-    const int rc = project_subtract_hp_f32(M, C, ldc, Vhi, Vlo, k, n, p, R, &nl, (cudaStream_t)stream);
+    const int rc = project_subtract_hp_f32(M, C, ldc, Vhi, Vlo, k, n, p, R, nullptr, &nl, (cudaStream_t)stream);
+    g_launches += nl;
+    return rc;
+}
+
+int vb_project_subtract_hp_rows_f32(const float* M, const double* C, int ldc, const float* Vhi, const float* Vlo,
+                                    int k, int n, size_t p, float* Rscratch, float* const* Rrows, void* stream) {
+    VB_REQUIRE(Rrows != nullptr, "project_subtract_hp_rows: Rrows is required");
+    int nl = 0;
+    const int rc = project_subtract_hp_f32(M, C, ldc, Vhi, Vlo, k, n, p, Rscratch, Rrows, &nl, (cudaStream_t)stream);
     g_launches += nl;
     return rc;
 }
@@ -212,7 +222,7 @@ int vb_derotate_f32(const float* in, float* out, int nframes, int S, int N, int 
     VB_REQUIRE(nframes > 0 && S > 0, "derotate: empty cube");
     VB_REQUIRE(N % 2 == 0 && N > S && y0 >= 0 && y0 + S + 1 <= N, "derotate: bad geometry S=%d N=%d y0=%d", S,
                N, y0);
-    RotParams g{S, N, y0, zero_masked, mask_is_nan, mask_val};
+    RotParams g{S, N, y0, zero_masked, mask_is_nan, mask_val, OutMap{}};
     const float2* tw = nullptr;
     const bool pow2 = (N & (N - 1)) == 0 && N >= 512 && N <= 4096 && N == 4 * S;
     if (pow2 && !force_direct) {
@@ -222,6 +232,33 @@ int vb_derotate_f32(const float* in, float* out, int nframes, int S, int N, int 
     int nl = 0;
     const int rc = derotate_run(in, out, nframes, g, krot, a, b, tw, scratch, scratch_bytes, force_direct,
                                 &nl, (cudaStream_t)stream);
+    g_launches += nl;
+    return rc;
+}
+
+int vb_derotate_scatter_f32(const float* in, int nframes, int S, int N, int y0, const int* krot, const double* a,
+                            const double* b, float mask_val, int mask_is_nan, int zero_masked, void* scratch,
+                            size_t scratch_bytes, void* const* out_bases_host, int nshards, int rows_per_shard,
+                            long long frame_stride, int frame_offset, void* stream) {
+    VB_REQUIRE(nframes > 0 && S > 0, "derotate_scatter: empty cube");
+    VB_REQUIRE(N % 2 == 0 && N > S && y0 >= 0 && y0 + S + 1 <= N, "derotate_scatter: bad geometry S=%d N=%d y0=%d",
+               S, N, y0);
+    VB_REQUIRE(out_bases_host != nullptr && nshards >= 1 && nshards <= 8, "derotate_scatter: 1..8 output shards");
+    VB_REQUIRE(rows_per_shard > 0 && rows_per_shard % 2 == 0 && rows_per_shard * nshards == S,
+               "derotate_scatter: rows_per_shard must be even and rows_per_shard * nshards == S");
+    const bool pow2 = (N & (N - 1)) == 0 && N >= 512 && N <= 4096 && N == 4 * S;
+    VB_REQUIRE(pow2, "derotate_scatter: needs power-of-two frames (N = 4S, 512 <= N <= 4096)");
+    RotParams g{S, N, y0, zero_masked, mask_is_nan, mask_val, OutMap{}};
+    for (int h = 0; h < nshards; ++h) g.om.base[h] = reinterpret_cast<float*>(out_bases_host[h]);
+    g.om.nshards = nshards;
+    g.om.rows_per = rows_per_shard;
+    g.om.fstride = frame_stride;
+    g.om.fofs = frame_offset;
+    const float2* tw = twiddle_table(N);
+    VB_REQUIRE(tw != nullptr, "derotate_scatter: could not build the twiddle table");
+    int nl = 0;
+    const int rc = derotate_run(in, nullptr, nframes, g, krot, a, b, tw, scratch, scratch_bytes, 0, &nl,
+                                (cudaStream_t)stream);
     g_launches += nl;
     return rc;
 }

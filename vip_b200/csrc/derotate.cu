@@ -30,6 +30,19 @@
 
 namespace vb {
 
+// Scattered output of the last pass (sharded path): row r of local frame f is written to
+//   base[r / rows_per] + (fofs + f) * fstride + (r % rows_per) * S
+// i.e. straight into the pixel-shard slab (n x p_g) of the rank that owns those rows -- local or PEER memory over
+// NVLink -- so the frame->pixel exchange before the temporal collapse rides on the derotation.  nshards = 0: plain
+// (n, S, S) output.
+struct OutMap {
+    float* base[8];
+    int nshards;
+    int rows_per;
+    long long fstride;
+    int fofs;
+};
+
 struct RotParams {
     int S;        // frame size (square frames)
     int N;        // working plane size (even)
@@ -37,7 +50,15 @@ struct RotParams {
     int zero_masked;   // 1: pixels equal to mask_val enter the rotation as 0 (interp_zeros with a numeric mask)
     int mask_is_nan;   // 1: masked pixels are the NaNs of the input; 0: pixels == mask_val
     float mask_val;
+    OutMap om;
 };
+
+// address of output row `row` of local frame f (see OutMap)
+__device__ __forceinline__ float* out_row_ptr(float* out, const RotParams& g, int f, int row) {
+    if (g.om.nshards == 0) return out + ((size_t)f * g.S + row) * g.S;
+    const int h = row / g.om.rows_per;
+    return g.om.base[h] + (size_t)(g.om.fofs + f) * (size_t)g.om.fstride + (size_t)(row - h * g.om.rows_per) * g.S;
+}
 
 // Value at (i, j) of the zero-padded plane after np.rot90(plane, k) and dropping the last
 // row/column (derotation.py:577-599).  P is the (N+1)^2 plane holding the frame at [y0, y0+S)^2.
@@ -1410,7 +1431,7 @@ shear_rows_last_pk(const float* __restrict__ T2, const float* __restrict__ aux, 
         const float sgn_t = (t & 1) ? -1.f : 1.f;      // (-1)^n' for n' = t + j*T
         const float ca = sgn_t * corr[row], cb = sgn_t * corr[row + 1];
         const float* src = in + ((size_t)f * g.S + row) * g.S;
-        float* dst = out + ((size_t)f * g.S + row) * g.S;
+        float* dst = out_row_ptr(out, g, f, row);      // rows row, row + 1 share a shard (rows_per is even)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int x = t + j * F::T;     // < S = 4T
@@ -1926,6 +1947,8 @@ int derotate_run(const float* in, float* out, int nframes, const RotParams& g, c
                  size_t scratch_bytes, int force_direct, int* launches, cudaStream_t st) {
     const bool use_fft = fft_path(g.S, g.N) && !force_direct;
     const bool packed = use_fft && fft_packed();
+    VB_REQUIRE(g.om.nshards == 0 || (packed && fft_rows_loop() < 2),
+               "derotate: scattered output needs the packed FFT path (power-of-two frames, N = 4S)");
     const size_t per_frame = packed ? packed_bytes_per_frame(g.S, g.N) : complex_bytes_per_frame(g.S, g.N);
     VB_REQUIRE(scratch_bytes >= per_frame, "derotate: scratch too small (%zu < %zu)", scratch_bytes,
                per_frame);

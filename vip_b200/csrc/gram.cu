@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include <cstdlib>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace vb {
@@ -383,6 +384,68 @@ int gram_f32(const float* A, int n, size_t p, int deflate, double* G, void* ws, 
     return 0;
 }
 
+// ---- pageable host arrays: multi-threaded staging through a pinned double buffer ------------------------------
+// cudaMemcpy2DAsync from PAGEABLE memory is staged by the driver on one thread (~10 GB/s: 50 ms for the 524 MB cube of
+// config 2, against 9.5 ms of PCIe time).  A drop-in caller passes a plain numpy array, so the upload path copies each
+// pixel slab into pinned memory with a few host threads (memcpy bandwidth adds up across cores) while the previous
+// slab is in flight on the DMA engine.
+struct Stager {
+    void* buf[2] = {nullptr, nullptr};
+    size_t cap = 0;
+    cudaEvent_t done[2];
+    bool ev_ready = false;
+};
+
+static bool host_is_pinned(const void* ptr) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+static int stager_threads() {
+    static const int v = [] {
+        const char* e = getenv("VIP_B200_STAGE_THREADS");
+        int t = e ? atoi(e) : 8;
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && t > hw) t = hw;
+        return t < 1 ? 1 : t;
+    }();
+    return v;
+}
+
+// rows [0, n) x columns [c0, c1) of the row-major host matrix (row pitch p floats) -> contiguous dst (n x (c1-c0))
+static void stage_slab(const float* host, int n, size_t p, size_t c0, size_t c1, float* dst) {
+    const int nt = stager_threads();
+    const size_t w = c1 - c0;
+    auto work = [&](int t) {
+        const int r0 = (int)((long long)n * t / nt), r1 = (int)((long long)n * (t + 1) / nt);
+        for (int r = r0; r < r1; ++r) memcpy(dst + (size_t)r * w, host + (size_t)r * p + c0, w * sizeof(float));
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
+
+// one pixel slab to the device on `copy_stream`: direct strided DMA from pinned memory, or staged (buffer s % 2)
+static int upload_slab(const float* host, int n, size_t p, size_t c0, size_t c1, float* M, Stager* staged, int s,
+                       cudaStream_t copy_stream) {
+    const size_t w = c1 - c0;
+    if (staged == nullptr) {
+        VB_CHECK_CUDA(cudaMemcpy2DAsync(M + c0, p * sizeof(float), host + c0, p * sizeof(float), w * sizeof(float), n,
+                                        cudaMemcpyHostToDevice, copy_stream));
+        return 0;
+    }
+    const int b = s & 1;
+    if (s >= 2) VB_CHECK_CUDA(cudaEventSynchronize(staged->done[b]));      // the DMA that last used this buffer
+    float* sb = reinterpret_cast<float*>(staged->buf[b]);
+    stage_slab(host, n, p, c0, c1, sb);
+    VB_CHECK_CUDA(cudaMemcpy2DAsync(M + c0, p * sizeof(float), sb, w * sizeof(float), w * sizeof(float), n,
+                                    cudaMemcpyHostToDevice, copy_stream));
+    VB_CHECK_CUDA(cudaEventRecord(staged->done[b], copy_stream));
+    return 0;
+}
+
 // Host cube -> device matrix M (n x p) AND G = M M^T, pipelined: the cube is uploaded in `nslabs` pixel
 // slabs (strided 2-D DMAs on a private copy stream) and the Gramian of each slab is accumulated on
 // `st` as soon as that slab has landed, so the fp64 SYRK hides behind the PCIe transfer.
@@ -413,6 +476,32 @@ int upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, voi
     cudaEvent_t start_ev = cx.start;
     if (nslabs <= 0) nslabs = 8;
     if (nslabs > 64) nslabs = 64;
+    // pageable source: staged through this device's pinned double buffer (see Stager above)
+    static Stager stagers[64];
+    Stager* staged = nullptr;
+    if (!host_is_pinned(host) && stager_threads() > 0 && getenv("VIP_B200_NO_STAGING") == nullptr) {
+        staged = &stagers[dev];
+        const size_t slab_w = ceil_div(ceil_div(p, (size_t)nslabs), (size_t)64) * 64 + 128;
+        const size_t need = (size_t)n * slab_w * sizeof(float);
+        std::lock_guard<std::mutex> lock(ctx_mutex);
+        if (!staged->ev_ready) {
+            for (int i = 0; i < 2; ++i) VB_CHECK_CUDA(cudaEventCreateWithFlags(&staged->done[i], cudaEventDisableTiming));
+            staged->ev_ready = true;
+        }
+        if (staged->cap < need) {
+            for (int i = 0; i < 2; ++i) {
+                if (staged->buf[i]) cudaFreeHost(staged->buf[i]);
+                staged->buf[i] = nullptr;
+                if (cudaHostAlloc(&staged->buf[i], need, cudaHostAllocDefault) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    staged = nullptr;            // no pinned memory to spare: let the driver stage the copy
+                    break;
+                }
+            }
+            if (staged) staged->cap = need;
+            else stagers[dev].cap = 0;
+        }
+    }
     if (gram_tc_eligible(n, p)) {
         // tensor-core SYRK per slab (split pass + tcgen05 kernel), same copy/compute pipeline
         int ntiles = 0, nl = 0;
@@ -423,8 +512,7 @@ int upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, voi
         int s = 0;
         for (size_t c0 = 0; c0 < p; c0 += slab, ++s) {
             const size_t c1 = (c0 + slab < p) ? c0 + slab : p;
-            VB_CHECK_CUDA(cudaMemcpy2DAsync(M + c0, p * sizeof(float), host + c0, p * sizeof(float),
-                                            (c1 - c0) * sizeof(float), n, cudaMemcpyHostToDevice, copy_stream));
+            if (int rc = upload_slab(host, n, p, c0, c1, M, staged, s, copy_stream)) return rc;
             VB_CHECK_CUDA(cudaEventRecord(ev[s], copy_stream));
             VB_CHECK_CUDA(cudaStreamWaitEvent(st, ev[s], 0));
             if (int rc = gram_tc_accumulate(M, n, p, p, c0, c1, ws, ntiles, &nl, st)) return rc;
@@ -454,8 +542,7 @@ int upload_gram_f32(const float* host, int n, size_t p, float* M, double* G, voi
     int nl = 0, s = 0;
     for (size_t c0 = 0; c0 < p; c0 += slab, ++s) {
         const size_t c1 = (c0 + slab < p) ? c0 + slab : p;
-        VB_CHECK_CUDA(cudaMemcpy2DAsync(M + c0, p * sizeof(float), host + c0, p * sizeof(float),
-                                        (c1 - c0) * sizeof(float), n, cudaMemcpyHostToDevice, copy_stream));
+        if (int rc = upload_slab(host, n, p, c0, c1, M, staged, s, copy_stream)) return rc;
         VB_CHECK_CUDA(cudaEventRecord(ev[s], copy_stream));
         VB_CHECK_CUDA(cudaStreamWaitEvent(st, ev[s], 0));
         const int kchunk = 1024;

@@ -199,7 +199,8 @@ subtract_kernel(const float* Src, const float* __restrict__ C, int ldc, const fl
 template <int KC, int PX>
 __global__ void __launch_bounds__(PT / PX)
 subtract_hp_kernel(const float* Src, const double* __restrict__ C, int ldc, const float* __restrict__ Vhi,
-                   const float* __restrict__ Vlo, int n, size_t p, int k0, int kc, float* R) {  // Src may alias R
+                   const float* __restrict__ Vlo, int n, size_t p, int k0, int kc, float* R,
+                   float* const* __restrict__ Rrows) {  // Src may alias R; Rrows: see project_subtract_hp_f32
     constexpr int NT = PT / PX;
     constexpr int HROWS = 128;
     __shared__ __align__(16) double Cs[HROWS][KC];
@@ -245,6 +246,9 @@ subtract_hp_kernel(const float* Src, const double* __restrict__ C, int ldc, cons
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     if (ib + u < ni) {
+                        // row i of the result goes to R + i p, or -- scattered output -- to the row pointer the caller
+                        // supplied (possibly PEER memory over NVLink: the exchange to frame shards rides on this pass)
+                        float* drow = (Rrows != nullptr) ? Rrows[i0 + ib + u] + j : dst + (size_t)(ib + u) * p;
                         double s[PX][2];
 #pragma unroll
                         for (int x = 0; x < PX; ++x) s[x][0] = s[x][1] = 0.0;
@@ -260,9 +264,9 @@ subtract_hp_kernel(const float* Src, const double* __restrict__ C, int ldc, cons
                         const float r0 = (float)((double)mv[u][0] - (s[0][0] + s[0][1]));
                         if (PX == 2) {
                             const float r1 = (float)((double)mv[u][PX - 1] - (s[PX - 1][0] + s[PX - 1][1]));
-                            *reinterpret_cast<float2*>(dst + (size_t)(ib + u) * p) = make_float2(r0, r1);
+                            *reinterpret_cast<float2*>(drow) = make_float2(r0, r1);
                         } else {
-                            dst[(size_t)(ib + u) * p] = r0;
+                            *drow = r0;
                         }
                     }
                 }
@@ -338,20 +342,25 @@ int project_subtract_f32(const float* M, const float* C, int ldc, const float* V
 }
 
 // R (n x p) = M - C (n x k fp64, leading dimension ldc) . (Vhi + Vlo) (k x p), fp64 accumulation; Vlo may be null.
+// Rrows (optional): device array of n row pointers; when given, row i of the FINAL result is written to Rrows[i][0..p)
+// instead of R + i p (rows may live in peer memory; each must be 8-byte aligned).  R is then only the scratch of the
+// intermediate passes (k > 32) and may be null for k <= 32.
 int project_subtract_hp_f32(const float* M, const double* C, int ldc, const float* Vhi, const float* Vlo, int k, int n,
-                            size_t p, float* R, int* launches, cudaStream_t st) {
+                            size_t p, float* R, float* const* Rrows, int* launches, cudaStream_t st) {
     VB_REQUIRE(k > 0 && n > 0 && p > 0, "project_subtract_hp: empty problem");
+    VB_REQUIRE(R != nullptr || (Rrows != nullptr && k <= KCMAX), "project_subtract_hp: R is required");
     const bool al = (p % 2 == 0) && (reinterpret_cast<uintptr_t>(M) % 8 == 0) && (reinterpret_cast<uintptr_t>(R) % 8 == 0);
     const unsigned grid = (unsigned)ceil_div(p, (size_t)PT);
     int nl = 0;
     for (int k0 = 0; k0 < k; k0 += KCMAX) {
         const int kc = (k - k0 < KCMAX) ? k - k0 : KCMAX;
         const float* src = (k0 == 0) ? M : R;
+        float* const* rows = (k0 + KCMAX >= k) ? Rrows : nullptr;       // only the last pass scatters
         // two pixels per thread while 2 * KC fp64 components fit the register file comfortably
 #define VB_SUBHP_LAUNCH(KCV, TWO)                                                                               \
         do {                                                                                                    \
-            if (TWO && al) subtract_hp_kernel<KCV, 2><<<grid, PT / 2, 0, st>>>(src, C, ldc, Vhi, Vlo, n, p, k0, kc, R); \
-            else           subtract_hp_kernel<KCV, 1><<<grid, PT, 0, st>>>(src, C, ldc, Vhi, Vlo, n, p, k0, kc, R);     \
+            if (TWO && al) subtract_hp_kernel<KCV, 2><<<grid, PT / 2, 0, st>>>(src, C, ldc, Vhi, Vlo, n, p, k0, kc, R, rows); \
+            else           subtract_hp_kernel<KCV, 1><<<grid, PT, 0, st>>>(src, C, ldc, Vhi, Vlo, n, p, k0, kc, R, rows);     \
         } while (0)
         if (kc <= 8)       VB_SUBHP_LAUNCH(8, true);
         else if (kc <= 16) VB_SUBHP_LAUNCH(16, true);

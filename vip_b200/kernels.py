@@ -48,16 +48,23 @@ def cross_gram(A, B):
     return Cm
 
 
-def eigh(G, max_sweeps=0, tol=0.0):
+def eigh(G, max_sweeps=0, tol=0.0, check=True):
     """Eigen-decomposition of a symmetric PSD fp64 matrix.
 
-    Returns (evals[n] descending, evecs[n,n] with row j = eigenvector j, info dict)."""
+    Returns (evals[n] descending, evecs[n,n] with row j = eigenvector j, info dict).  ``check=False`` skips the
+    read-back of the convergence record -- and with it the host synchronisation -- for matrices the single-launch
+    solver handles (n <= 128): used for the many small whitening problems of the randomized SVD, whose 30 sweeps
+    are far more than a 60 x 60 Gramian ever needs."""
     lib = _cabi.lib()
     n = G.shape[0]
     evals = empty((n,), torch.float64, G.device)
     evecs = empty((n, n), torch.float64, G.device)
     nb = lib.vb_eigh_workspace_bytes(n)
     ws = _bytes(nb, G.device)
+    if not check and n <= 128:
+        _cabi.check(lib.vb_eigh_f64(ptr(G), n, ptr(evals), ptr(evecs), int(max_sweeps), float(tol), ptr(ws), nb,
+                                    None, stream_ptr()), "vb_eigh_f64")
+        return evals, evecs, {"sweeps": None, "converged": None}
     info = (C.c_int * 2)()
     _cabi.check(lib.vb_eigh_f64(ptr(G), n, ptr(evals), ptr(evecs), int(max_sweeps), float(tol), ptr(ws), nb,
                                 info, stream_ptr()), "vb_eigh_f64")
@@ -182,6 +189,39 @@ def derotate(cube, krot, a, b, S, N, y0, mask_val=float("nan"), zero_masked=Fals
                                     float(mask_val), mask_is_nan, int(bool(zero_masked)), ptr(scratch),
                                     nbytes, int(bool(force_direct)), stream_ptr()), "vb_derotate_f32")
     return out
+
+
+def derotate_scatter(cube, krot, a, b, S, N, y0, out_bases, rows_per_shard, frame_stride, frame_offset,
+                     mask_val=float("nan"), zero_masked=False, scratch_max=None):
+    """``derotate`` whose output rows go straight into the pixel-shard slabs ``out_bases`` (list of device pointers,
+    local or peer; see ``vb_derotate_scatter_f32``).  Returns nothing: the slabs are the output."""
+    lib = _cabi.lib()
+    n = cube.shape[0]
+    dev = cube.device
+    d_k = torch.as_tensor(np.asarray(krot, dtype=np.int32)).to(dev)
+    d_a = torch.as_tensor(np.asarray(a, dtype=np.float64)).to(dev)
+    d_b = torch.as_tensor(np.asarray(b, dtype=np.float64)).to(dev)
+    nbytes = lib.vb_derotate_scratch_bytes(n, S, N, scratch_max or _DEROT_SCRATCH_MAX)
+    scratch = _bytes(nbytes, dev)
+    bases = (C.c_void_p * len(out_bases))(*[int(x) for x in out_bases])
+    _cabi.check(lib.vb_derotate_scatter_f32(ptr(cube), n, S, N, y0, ptr(d_k), ptr(d_a), ptr(d_b), float(mask_val),
+                                            int(np.isnan(mask_val)), int(bool(zero_masked)), ptr(scratch), nbytes,
+                                            bases, len(out_bases), int(rows_per_shard), int(frame_stride),
+                                            int(frame_offset), stream_ptr()), "vb_derotate_scatter_f32")
+
+
+def project_subtract_hp_rows(M, C64, Vhi, Vlo, row_ptrs, scratch=None):
+    """``project_subtract_hp`` with row i of the result written to the address ``row_ptrs[i]`` (int64 CUDA tensor of
+    n device pointers, local or peer memory).  ``scratch`` (n,p) fp32 is needed when k > 32."""
+    lib = _cabi.lib()
+    n, p = M.shape
+    k = Vhi.shape[0]
+    C64 = C64.to(torch.float64).contiguous()
+    assert C64.shape == (n, k) and row_ptrs.dtype == torch.int64 and row_ptrs.numel() == n
+    if k > 32 and scratch is None:
+        scratch = empty((n, p), torch.float32, M.device)
+    _cabi.check(lib.vb_project_subtract_hp_rows_f32(ptr(M), ptr(C64), k, ptr(Vhi), ptr(Vlo), k, n, p, ptr(scratch),
+                                                    ptr(row_ptrs), stream_ptr()), "vb_project_subtract_hp_rows_f32")
 
 
 def collapse(cube2d, mode="median", w=None, trim_k=0, trim_n=0):

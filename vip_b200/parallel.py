@@ -76,8 +76,10 @@ class CudaOps:
         return torch.cat(kernels.pcs_hilo(Wt, M))
 
     def randomized_pcs(self, M, ncomp, omega, reduce):
+        """(V stacked, C): the coefficients M V^T come for free from the sketch (psfsub.svd.randomized_pcs)."""
         from .psfsub.svd import randomized_pcs
-        return torch.cat(randomized_pcs(M, ncomp, omega, reduce=reduce, hilo=True))
+        V, Cm = randomized_pcs(M, ncomp, omega, reduce=reduce, hilo=True, coeffs=True)
+        return torch.cat(V), Cm
 
     def coeffs(self, M, V, reduce):
         """C (n,k) fp64 = M (Vhi + Vlo)^T, the pixel axis summed over the shards."""
@@ -91,6 +93,19 @@ class CudaOps:
 
     def derotate(self, cube, angles):
         return derotate_device(cube, angles)
+
+    # ---- exchanges fused into the kernels over peer memory (NVLink), see PeerExchange below
+    def project_subtract_rows(self, M, Cm, V, row_ptrs):
+        k = V.shape[0] // 2
+        kernels.project_subtract_hp_rows(M, Cm, V[:k], V[k:], row_ptrs)
+
+    def derotate_scatter(self, cube, angles, out_bases, rows_per_shard, frame_stride, frame_offset):
+        from .preproc.derotation import rotation_geometry, rotation_scalars
+        S = cube.shape[-1]
+        N, y0 = rotation_geometry(S)
+        krot, a, b = rotation_scalars(angles)
+        kernels.derotate_scatter(cube.contiguous(), krot, a, b, S, N, y0, out_bases, rows_per_shard, frame_stride,
+                                 frame_offset)
 
     def sdi_stage1(self, cube4d, frames, scale_list, ncomp_ifs, collapse_ifs, device):
         """Stage 1 of the ADI+mSDI double PCA for the ADI frames ``frames`` of a host (z,n,H,W) cube:
@@ -164,6 +179,70 @@ def _exchange_single(send_flat, send_counts, recv_counts, group, async_op=False)
 def _single_ok():
     """all_to_all_single is NCCL-native; the gloo backend of the CPU tests lacks it on some builds."""
     return os.environ.get("VIP_B200_SHARD_A2A", "single") == "single"
+
+
+class PeerExchange:
+    """Symmetric (peer-mapped) buffers for the two exchanges of ``pca_sharded``, so that they can be FUSED into the
+    kernels that produce the data instead of running as separate NCCL all-to-alls:
+
+      * ``frames`` (f_max, p) per rank -- every rank's projection kernel writes residual row i of its pixel shard
+        directly into the frame shard of the rank that derotates frame i (``vb_project_subtract_hp_rows_f32``);
+      * ``slab`` (n, p_g) per rank -- the last shear pass of every rank writes each derotated image row directly into
+        the pixel-shard slab of the rank that takes that pixel's temporal median (``vb_derotate_scatter_f32``).
+
+    The buffers come from ``torch.distributed._symmetric_memory`` (CUDA VMM allocations exchanged between the
+    processes of the node, peer access over NVLink / NVSwitch) and are cached per geometry: allocation and rendezvous
+    are collective and slow, the steps reuse them.  ``barrier()`` is a device-side barrier on the current stream
+    (signal pads in the same allocations): peers have finished writing before a rank reads its buffer, and have
+    finished reading before the next step overwrites it.  Measured on 2 x B200 (tools/symm_probe.py): plain peer
+    writes move data at 2x the rate of ``all_to_all_single``; fused, the transfer also overlaps the kernel's math."""
+
+    _cache = {}
+
+    def __init__(self, n, H, W, world, rank, fb, pb, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        g = group if group is not None else dist.group.WORLD
+        p = H * W
+        self.world, self.rank = world, rank
+        fmax = int(np.max(np.diff(fb)))
+        pg = p // world
+        self.frames = symm_mem.empty((fmax, p), dtype=torch.float32, device=device)
+        self.frames_h = symm_mem.rendezvous(self.frames, g)
+        self.slab = symm_mem.empty((n, pg), dtype=torch.float32, device=device)
+        self.slab_h = symm_mem.rendezvous(self.slab, g)
+        p0 = int(pb[rank])
+        ptrs = np.empty(n, dtype=np.int64)
+        for h in range(world):
+            base = int(self.frames_h.buffer_ptrs[h])
+            i = np.arange(int(fb[h]), int(fb[h + 1]), dtype=np.int64)
+            ptrs[int(fb[h]):int(fb[h + 1])] = base + ((i - int(fb[h])) * p + p0) * 4
+        self.row_ptrs = torch.from_numpy(ptrs).to(device)
+        self.slab_bases = [int(self.slab_h.buffer_ptrs[h]) for h in range(world)]
+
+    def barrier(self):
+        self.frames_h.barrier()
+
+    @classmethod
+    def eligible(cls, ops, world, n, H, W, collapse, full_output):
+        if os.environ.get("VIP_B200_SHARD_FUSED", "1") != "1" or getattr(ops, "name", "") != "cuda":
+            return False
+        if world < 2 or world > 8 or full_output or H != W:
+            return False
+        N = 4 * H
+        pow2 = (N & (N - 1)) == 0 and 512 <= N <= 4096
+        return pow2 and H % world == 0 and (H // world) % 2 == 0 and (H * W) % world == 0 and (H * W // world) % 2 == 0
+
+    @classmethod
+    def get(cls, n, H, W, world, rank, fb, pb, device, group):
+        key = (n, H, W, world, rank, str(device), id(group))
+        if key not in cls._cache:
+            try:
+                cls._cache[key] = cls(n, H, W, world, rank, fb, pb, device, group)
+            except Exception as exc:                                       # noqa: BLE001
+                cls._cache[key] = None
+                import warnings
+                warnings.warn(f"vip_b200: symmetric memory unavailable ({exc!r}); NCCL exchanges are used")
+        return cls._cache[key]
 
 
 def _all_to_all(send, recv, group):
@@ -410,6 +489,9 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
     _mark(timer, "upload")
     record = None
     raw_frames = None
+    peer = None
+    if PeerExchange.eligible(ops, world, n, H, W, collapse, full_output):
+        peer = PeerExchange.get(n, H, W, world, rank, fb, pb, device, group)
     if overlap_exchange is None:
         # default ON since round 2 (measured on NVLink: profiles/r02_scaling.md); VIP_B200_SHARD_OVERLAP=0 restores
         # the subtract-then-exchange order
@@ -430,16 +512,20 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
         else:
             omega = torch.empty((n, ell), dtype=torch.float64, device=device)
         dist.broadcast(omega, src=src, group=group)
-        V = ops.randomized_pcs(M, ncomp, omega.cpu().numpy(), reduce)
+        out = ops.randomized_pcs(M, ncomp, omega if getattr(ops, "name", "") == "cuda" else omega.cpu().numpy(), reduce)
         _mark(timer, "randsvd")
-        Cm = ops.coeffs(M, V, reduce)
-        _mark(timer, "coeffs")
+        if isinstance(out, tuple):
+            V, Cm = out                                                  # coefficients for free (B^T Wt^T)
+        else:
+            V = out
+            Cm = ops.coeffs(M, V, reduce)
+            _mark(timer, "coeffs")
     else:
         G = ops.gram(M)
         _mark(timer, "gram")
         dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)           # exchange step 0: n x n fp64
         _mark(timer, "allreduce_gram")
-        if overlap_exchange and world > 1:
+        if overlap_exchange and world > 1 and peer is None:
             # R = M - C V is row-local once V is known everywhere: the all-to-all to frame shards moves the RAW
             # cube while the (replicated, latency-bound) eigensolver runs; V (k x p, 21 MB at config 2) is
             # all-gathered afterwards and the subtraction happens on the frame shards.  Same kernels on the same
@@ -467,7 +553,30 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
             Cm = Cm.to(torch.float32)
         V = ops.pcs(Wt, M)
         _mark(timer, "pcs")
-    if raw_frames is not None:
+    if peer is not None:
+        # ---- fused exchanges over peer memory: the projection writes every residual row into the frame shard of its
+        # owner, the last shear pass writes every derotated image row into the pixel slab of its owner
+        peer.barrier()                                   # nobody still reads the buffers of the previous step
+        ops.project_subtract_rows(M, Cm, V, peer.row_ptrs)
+        peer.barrier()                                   # every rank's rows have landed in my frame shard
+        _mark(timer, "subtract_scatter")
+        mine = peer.frames[: f1 - f0].reshape(f1 - f0, H, W)
+        if collapse in ("mean", "sum"):
+            # reducible collapse: partial sums over the own frames + one NCCL reduce (collective: every rank calls it)
+            frame, _ = _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, ops, device, timer)
+        else:
+            if f1 > f0:
+                ops.derotate_scatter(mine, -angle_list[f0:f1], peer.slab_bases, H // world, p // world, f0)
+            peer.barrier()                               # every rank's image rows have landed in my pixel slab
+            _mark(timer, "derotate_scatter")
+            slab = ops.collapse(peer.slab, collapse)
+            _mark(timer, "collapse")
+            full = torch.empty(p, dtype=slab.dtype, device=device)
+            dist.all_gather_into_tensor(full, slab.contiguous(), group=group)
+            _mark(timer, "gather")
+            frame = full.reshape(H, W).cpu().numpy() if rank == 0 else None
+        der = None
+    elif raw_frames is not None:
         # all-gather of the PCs
         k = V.shape[0]
         if p % world == 0 and _single_ok():
@@ -496,7 +605,8 @@ def pca_sharded(cube, angle_list, ncomp, collapse="median", group=None, ops=None
         # ---- exchange 1: pixel shards -> frame shards ---------------------------------------------
         mine = _rows_to_frames(R, fb, pb, rank, group, device)().reshape(f1 - f0, H, W)   # my frames, all pixels
         _mark(timer, "exchange1")
-    frame, der = _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, ops, device, timer)
+    if peer is None:
+        frame, der = _derotate_collapse_frame_shards(mine, angle_list, fb, pb, collapse, group, ops, device, timer)
     if record is not None:
         if device.type == "cuda":
             torch.cuda.current_stream().synchronize()

@@ -182,8 +182,9 @@ def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, 
         elif not isinstance(rs, np.random.RandomState):
             rs = np.random.RandomState(rs)
         omega = rs.normal(size=(nr, ncomp + 10))
-        V, Vlo = randomized_pcs(ref_lib, ncomp, omega, hilo=True)
-        Cm = kernels.cross_gram(matrix_emp, V) + kernels.cross_gram(matrix_emp, Vlo)
+        (V, Vlo), Cm = randomized_pcs(ref_lib, ncomp, omega, hilo=True, coeffs=True)
+        if ref_lib is not matrix_emp:
+            Cm = kernels.cross_gram(matrix_emp, V) + kernels.cross_gram(matrix_emp, Vlo)
     else:
         raise ValueError("The SVD `mode` is not recognized")
     if verbose:

@@ -93,34 +93,50 @@ def orthonormalize(Yt, reduce=None, passes=2):
         G = kernels.cross_gram(Yt, Yt)
         if reduce is not None:
             G = reduce(G)
-        evals, evecs, _ = kernels.eigh(G)
-        keep = evals > evals[0] * 1e-30
-        Wt = (evecs / torch.sqrt(torch.clamp(evals, min=1e-300))[:, None])[keep]
-        Yt = kernels.pcs(Wt.contiguous(), Yt)
+        Yt = kernels.pcs(_whitening(G), Yt)
     return Yt
 
 
-def orthonormalize_hilo(hi, lo, reduce=None):
-    """Orthonormal basis (fp32, (l,p)) of the row space of the sketch ``hi + lo`` (error-free fp32 pair, see
-    ``kernels.pcs_hilo``).  The raw sketch is dominated by the leading singular direction -- its rows span
-    (sigma_0/sigma_k)^(2q+1) in magnitude -- so its Gramian is formed from the stacked pair in fp64
-    (G = S S^T summed over the four hi/lo blocks) and the first change of basis is applied to the pair; the result
-    has O(1) rows that are orthonormal to ~1e-4 and is safe in plain fp32, where a second ordinary pass finishes."""
-    l = hi.shape[0]
-    S = torch.cat((hi, lo))                                     # (2l, p)
+def _gram_of_pair(S, l, reduce):
+    """Gramian (l,l) fp64 of the rows of ``hi + lo`` from the stacked pair S = [hi; lo] (2l, p)."""
     G2 = kernels.cross_gram(S, S)
     if reduce is not None:
         G2 = reduce(G2)
     G = G2[:l, :l] + G2[:l, l:] + G2[l:, :l] + G2[l:, l:]
-    G = (0.5 * (G + G.t())).contiguous()
-    evals, evecs, _ = kernels.eigh(G)
-    keep = evals > evals[0] * 1e-30
-    Wt = (evecs / torch.sqrt(torch.clamp(evals, min=1e-300))[:, None])[keep]
-    Y1 = kernels.pcs(torch.cat((Wt, Wt), dim=1).contiguous(), S)
-    return orthonormalize(Y1, reduce, passes=2)
+    return (0.5 * (G + G.t())).contiguous()
 
 
-def randomized_pcs(M, ncomp, omega, n_iter=2, reduce=None, hilo=False):
+def _whitening(G):
+    """Rows of Wt: eigenvectors of the Gramian scaled by 1/sqrt(eigenvalue) (numerically null directions dropped)."""
+    evals, evecs, _ = kernels.eigh(G, check=False)
+    # numerically null directions are zeroed, not dropped: no data-dependent shapes, hence no host synchronisation
+    # (a zero row of Wt gives a zero row of the basis, which contributes nothing to any later product)
+    scale = torch.where(evals > evals[0] * 1e-30, torch.rsqrt(torch.clamp(evals, min=1e-300)), torch.zeros_like(evals))
+    return (evecs * scale[:, None]).contiguous()
+
+
+def orthonormalize_hilo(hi, lo, reduce=None, final=False):
+    """Orthonormal basis of the row space of the sketch ``hi + lo`` (error-free fp32 pair, ``kernels.pcs_hilo``).
+
+    The raw sketch is dominated by the leading singular direction -- its rows span (sigma_0/sigma_k)^(2q+1) in
+    magnitude -- so its Gramian is formed from the stacked pair in fp64 and the change of basis is applied to the
+    pair.  Intermediate bases of the power iteration (``final=False``) are then rounded to plain fp32 (O(1) rows,
+    orthonormal to ~1e-4 after the first pass; one ordinary pass finishes): rounding an ITERATE only perturbs a
+    self-correcting iteration.  The LAST basis (``final=True``) is returned as a pair (Qhi, Qlo): its span is what the
+    principal components inherit, and an fp32 copy would leave 6e-8 of the 1e4-bright halo in every residual."""
+    l = hi.shape[0]
+    S = torch.cat((hi, lo))                                     # (2l, p)
+    Wt = _whitening(_gram_of_pair(S, l, reduce))
+    if not final:
+        Y1 = kernels.pcs(torch.cat((Wt, Wt), dim=1).contiguous(), S)
+        return orthonormalize(Y1, reduce, passes=1)
+    l1 = Wt.shape[0]
+    S = torch.cat(kernels.pcs_hilo(torch.cat((Wt, Wt), dim=1).contiguous(), S))
+    Wt = _whitening(_gram_of_pair(S, l1, reduce))
+    return kernels.pcs_hilo(torch.cat((Wt, Wt), dim=1).contiguous(), S)
+
+
+def randomized_pcs(M, ncomp, omega, n_iter=2, reduce=None, hilo=False, coeffs=False):
     """scikit-learn ``randomized_svd(M, ncomp, n_iter=2, transpose='auto')`` for n < p
     (``svd.py:487-491``): with the Gaussian test matrix ``omega`` (n, ncomp+10) supplied
     by the caller,  Y = M^T (M M^T)^n_iter omega,  Q = orth(Y),  B = Q^T M^T,  PCs = (Q U_B)[:, :k]^T.
@@ -138,22 +154,32 @@ def randomized_pcs(M, ncomp, omega, n_iter=2, reduce=None, hilo=False):
     ``reduce`` sums a small fp64 matrix over the ranks in place (NCCL all-reduce).  Every product
     with the pixel axis contracted -- the (l,n) sketches ``Q M^T`` and the Gramians of the orthonormalisation --
     is a sum over pixel shards; everything else is local.  ``hilo``: return the PCs as the error-free pair
-    (Vhi, Vlo) for the high-precision projection."""
+    (Vhi, Vlo) for the high-precision projection.  ``coeffs``: additionally return C (n,k) fp64 = M V^T, the projection
+    of M's own rows on the PCs -- it costs nothing: V = Wt Q, so M V^T = (Q M^T)^T Wt^T = B^T Wt^T with the (l,n)
+    matrix B the algorithm has already formed (the reference spends a full pass over M on it, pca_fullfr.py:1728)."""
     n, p = M.shape
     red = reduce if reduce is not None else (lambda t: t)
-    Om = torch.as_tensor(np.asarray(omega, dtype=np.float32)).to(M.device)      # sklearn casts Omega to M's dtype
+    if isinstance(omega, torch.Tensor):                          # sklearn casts Omega to M's dtype (fp32)
+        Om = omega.to(device=M.device, dtype=torch.float32)
+    else:
+        Om = torch.as_tensor(np.asarray(omega, dtype=np.float32)).to(M.device)
     hi, lo = kernels.pcs_hilo(Om.t().contiguous(), M)            # (l,p) = omega^T M
-    Qt = orthonormalize_hilo(hi, lo, reduce)
-    for _ in range(n_iter):
+    for it in range(n_iter):
+        Qt = orthonormalize_hilo(hi, lo, reduce)
         Z = red(kernels.cross_gram(Qt, M))                       # (l,n) = Q^T M^T
         hi, lo = kernels.pcs_hilo(Z.contiguous(), M)             # (l,p) = (Q^T M^T) M
-        Qt = orthonormalize_hilo(hi, lo, reduce)
-    B = red(kernels.cross_gram(Qt, M))                           # (l,n) fp64
-    evals, evecs, _ = kernels.eigh((B @ B.t()).contiguous())
+    Qhi, Qlo = orthonormalize_hilo(hi, lo, reduce, final=True)
+    Qs = torch.cat((Qhi, Qlo))                                   # stacked pair (2l, p)
+    l = Qhi.shape[0]
+    B2 = red(kernels.cross_gram(Qs, M))                          # (2l,n) fp64
+    B = (B2[:l] + B2[l:]).contiguous()                           # (l,n) = Q^T M^T
+    evals, evecs, _ = kernels.eigh((B @ B.t()).contiguous(), check=False)
     Wt = evecs[:ncomp].contiguous()                              # rows = leading left vectors of B
-    if hilo:
-        return kernels.pcs_hilo(Wt, Qt)
-    return kernels.pcs(Wt, Qt)
+    Wt2 = torch.cat((Wt, Wt), dim=1).contiguous()
+    V = kernels.pcs_hilo(Wt2, Qs) if hilo else kernels.pcs(Wt2, Qs)
+    if coeffs:
+        return V, (B.t() @ Wt.t()).contiguous()
+    return V
 
 
 def svd_wrapper(matrix, mode, ncomp, verbose=False, full_output=False, random_state=None, to_numpy=True,
