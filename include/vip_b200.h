@@ -59,6 +59,12 @@ size_t vb_eigh_workspace_bytes(int n);
 int vb_eigh_f64(const double* G, int n, double* evals, double* evecs, int max_sweeps, double tol,
                 void* ws, size_t ws_bytes, int* info_host, void* stream);
 
+/* Cholesky whitening of a small SPD Gramian (n <= 128): Wt (n x n fp64, lower triangular) = R^-T with G = R^T R,
+ * so that Wt G Wt^T = I (CholeskyQR).  Rows whose pivot is numerically zero are dropped (zero row/column of Wt).
+ * Asynchronous.  Used by the orthonormalisation passes of the randomized SVD (scikit-learn's QR in
+ * randomized_range_finder; call site psfsub/svd.py:487-491). */
+int vb_chol_whiten_f64(const double* G, int n, double* Wt, void* stream);
+
 /* Leading k (<= 24, block width <= n) eigenpairs only, by fp64 block subspace iteration with Rayleigh-Ritz
  * (O(n^2 B) per step instead of a full decomposition).  evals[k] descending, evecs[k x n] row j =
  * eigenvector j.  Iterates until max_j ||G x_j - theta_j x_j|| <= tol * theta_k.  info_host

@@ -31,6 +31,13 @@ def eigh(G, max_sweeps=0, tol=0.0, check=True):
     return w[order].contiguous(), v[:, order].T.contiguous(), {"sweeps": 1, "converged": True}
 
 
+def chol_whiten(G):
+    g = G.double().numpy()
+    g = 0.5 * (g + g.T)
+    R = np.linalg.cholesky(g).T                       # G = R^T R
+    return torch.from_numpy(np.ascontiguousarray(np.linalg.inv(R).T))
+
+
 def eigh_topk(G, k, tol=0.0, max_iter=0):
     w, E, _ = eigh(G)
     return w[:k].contiguous(), E[:k].contiguous(), {"iters": 1, "converged": True}
@@ -148,7 +155,7 @@ def annular_weights(G, idx, lens, frames, ncomp, tol=0.0, max_iter=40, direct_fa
     return torch.from_numpy(W), torch.ones(nprob, dtype=torch.int32)
 
 
-_NAMES = ("annular_weights", "gram", "cross_gram", "eigh", "eigh_topk", "topk_supported", "pcs", "pcs_hilo", "project_subtract", "project_subtract_hp", "sub", "derotate",
+_NAMES = ("annular_weights", "gram", "cross_gram", "eigh", "chol_whiten", "eigh_topk", "topk_supported", "pcs", "pcs_hilo", "project_subtract", "project_subtract_hp", "sub", "derotate",
           "collapse", "upload_and_gram", "upload_columns", "gather_columns", "scatter_columns", "gemm")
 
 

@@ -1047,3 +1047,29 @@ def test_pca_incremental_golden(vb, golden, golden_inputs):
     fr = vb.pca(big, bangs, ncomp=8, batch=50, verbose=False)
     assert_parity(fr, O.pca_incremental(big, bangs, 50, ncomp=8),
                   lambda: O.pca_incremental(big.astype(np.float64), bangs, 50, ncomp=8), FRAME_TOL, "120 frames")
+
+
+@pytest.mark.parametrize("n", [1, 5, 60, 100, 120, 128])
+def test_chol_whiten_kernel(n):
+    """``vb_chol_whiten_f64``: Wt G Wt^T = I for SPD Gramians with the dynamic range of a raw randomized-SVD sketch
+    (condition number ~1e10), lower-triangular Wt equal to numpy's R^-T; a numerically dependent row is dropped."""
+    import torch
+    from vip_b200 import kernels
+    rng = np.random.default_rng(n)
+    Y = rng.normal(size=(n, 4 * n + 8)) * np.logspace(0, -5, n)[:, None]
+    Y[0] += 50.0 * rng.normal(size=Y.shape[1])
+    G = Y @ Y.T
+    Wt = kernels.chol_whiten(torch.from_numpy(G).cuda()).cpu().numpy()
+    assert np.allclose(Wt, np.tril(Wt))
+    R = np.linalg.cholesky(G).T
+    np.testing.assert_allclose(Wt, np.linalg.inv(R).T, rtol=1e-6, atol=1e-12 * np.abs(np.linalg.inv(R)).max())
+    Q = Wt @ Y
+    np.testing.assert_allclose(Q @ Q.T, np.eye(n), atol=1e-5)
+    if n >= 5:
+        Y2 = Y.copy()
+        Y2[3] = 0.0                                     # dependent (null) row
+        W2 = kernels.chol_whiten(torch.from_numpy(Y2 @ Y2.T).cuda()).cpu().numpy()
+        assert np.all(W2[3] == 0) and np.all(W2[:, 3] == 0)
+        Q2 = W2 @ Y2
+        keep = np.arange(n) != 3
+        np.testing.assert_allclose((Q2 @ Q2.T)[np.ix_(keep, keep)], np.eye(n - 1), atol=1e-5)

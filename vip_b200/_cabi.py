@@ -26,6 +26,7 @@ SIGNATURES = {
     "vb_cross_gram_f32": (_i, [_vp, _i, _vp, _i, _sz, _vp, _vp, _sz, _vp]),
     "vb_eigh_workspace_bytes": (_sz, [_i]),
     "vb_eigh_f64": (_i, [_vp, _i, _vp, _vp, _i, _d, _vp, _sz, C.POINTER(_i), _vp]),
+    "vb_chol_whiten_f64": (_i, [_vp, _i, _vp, _vp]),
     "vb_eigh_topk_workspace_bytes": (_sz, [_i, _i]),
     "vb_eigh_topk_f64": (_i, [_vp, _i, _i, _d, _i, _vp, _vp, _vp, _sz, C.POINTER(_i), _vp]),
     "vb_eigh_topk_async_f64": (_i, [_vp, _i, _i, _d, _i, _vp, _vp, _vp, _sz, _vp, _vp]),

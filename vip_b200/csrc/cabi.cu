@@ -29,6 +29,7 @@ size_t eigh_workspace_bytes(int n);
 int eigh_f64(const double*, int, double*, double*, int, double, void*, size_t, int*, int*, cudaStream_t);
 size_t eigh_topk_workspace_bytes(int n, int B);
 int topk_block_width(int k);
+int chol_whiten_f64(const double*, int, double*, cudaStream_t);
 int eigh_topk_f64(const double*, int, int, double, int, double*, double*, void*, size_t, int*, int*, cudaStream_t,
                   int* async_info = nullptr);
 int pcs_f32(const double*, const float*, int, int, size_t, float*, float*, int*, cudaStream_t);
@@ -133,6 +134,11 @@ int vb_eigh_f64(const double* G, int n, double* evals, double* evecs, int max_sw
                             (cudaStream_t)stream);
     g_launches += nl;
     return rc;
+}
+
+int vb_chol_whiten_f64(const double* G, int n, double* Wt, void* stream) {
+    g_launches += 1;
+    return chol_whiten_f64(G, n, Wt, (cudaStream_t)stream);
 }
 
 size_t vb_eigh_topk_workspace_bytes(int n, int k) {

@@ -268,6 +268,84 @@ static int jacobi_sweeps(double* W, int n, int max_sweeps, double tol, JacobiSta
 
 // G: n x n symmetric fp64 (not modified).  evals[n] descending, evecs[n x n] row j = eigenvector j.
 // info (host, optional): [0] sweeps executed, [1] converged flag  -- reading it synchronises the stream.
+// ---------------------------------------------------------------------------------------------------------------
+// Cholesky whitening of a small SPD Gramian:  G = R^T R  (R upper triangular),  Wt = R^-T  (lower triangular), so that
+// Wt G Wt^T = I: the rows of Wt Y are orthonormal when G = Y Y^T (CholeskyQR).  One CTA, the matrix in shared memory,
+// right-looking factorisation (one barrier pair per column), then one thread per column of the inverse.  Replaces the
+// eigen-decomposition in the orthonormalisation passes of the randomized SVD, where a 60 x 60 one-sided Jacobi cost
+// 1.5 ms per call (7 calls = the fixed 10 ms that did not shrink with the number of GPUs, profiles/r02k_launches_c5.md).
+// A pivot below 1e-30 of the largest diagonal entry marks a numerically dependent row: its row/column of Wt is zeroed
+// (that direction is dropped), as the eigen-based whitening did for null eigenvalues.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+chol_whiten_kernel(const double* __restrict__ G, int n, double* __restrict__ Wt) {
+    extern __shared__ double cw_smem[];
+    double* A = cw_smem;                       // n x (n + 1), upper triangle becomes R
+    __shared__ double dmax_s;
+    __shared__ int dead[128];
+    const int ld = n + 1, tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < n * n; e += nt) {
+        const int i = e / n, j = e % n;
+        A[i * ld + j] = 0.5 * (G[i * n + j] + G[j * n + i]);
+    }
+    if (tid < 128) dead[tid] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        for (int i = 0; i < n; ++i) m = fmax(m, A[i * ld + i]);
+        dmax_s = m;
+    }
+    __syncthreads();
+    const double thr = dmax_s * 1e-30;
+    for (int j = 0; j < n; ++j) {
+        const double ajj = A[j * ld + j];
+        const bool ok = ajj > thr && ajj > 0.0;
+        const double rd = ok ? rsqrt(ajj) : 0.0;
+        __syncthreads();                       // everyone has read the pivot before row j is scaled
+        // row j of R:  R[j][c] = A[j][c] / sqrt(ajj)
+        for (int c = j + tid; c < n; c += nt) A[j * ld + c] = ok ? A[j * ld + c] * rd : 0.0;
+        if (tid == 0) { dead[j] = ok ? 0 : 1; if (!ok) A[j * ld + j] = 1.0; }
+        __syncthreads();
+        // trailing update: A[i][c] -= R[j][i] R[j][c]  for j < i <= c
+        const int m = n - j - 1;
+        for (int e = tid; e < m * m; e += nt) {
+            const int i = j + 1 + e / m, c = j + 1 + e % m;
+            if (c >= i) A[i * ld + c] = fma(-A[j * ld + i], A[j * ld + c], A[i * ld + c]);
+        }
+    }
+    __syncthreads();
+    // Wt = R^-T: column q of R^-1 solves R x = e_q (back substitution); Wt[q][i]... we need Wt = (R^-1)^T, i.e.
+    // Wt[r][c] = (R^-1)[c][r].  Thread q computes x = R^-1 e_q (non-zero for rows <= q) and writes Wt[q][0..q].
+    for (int q = tid; q < n; q += nt) {
+        // x_q = 1 / R[q][q]; for i = q-1 .. 0: x_i = -(sum_{m=i+1..q} R[i][m] x_m) / R[i][i]
+        double* x = Wt + (size_t)q * n;        // row q of Wt used as the work vector
+        for (int i = 0; i < n; ++i) x[i] = 0.0;
+        if (!dead[q]) {
+            x[q] = 1.0 / A[q * ld + q];
+            for (int i = q - 1; i >= 0; --i) {
+                double sacc = 0.0;
+                for (int mm = i + 1; mm <= q; ++mm) sacc = fma(A[i * ld + mm], x[mm], sacc);
+                x[i] = dead[i] ? 0.0 : -sacc / A[i * ld + i];
+            }
+        }
+    }
+}
+
+// Wt (n x n fp64, lower triangular) with Wt G Wt^T = I for the SPD matrix G (n <= 128).  Asynchronous on `st`.
+int chol_whiten_f64(const double* G, int n, double* Wt, cudaStream_t st) {
+    VB_REQUIRE(n >= 1 && n <= 128, "chol_whiten: 1 <= n <= 128");
+    const size_t smem = (size_t)n * (n + 1) * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        VB_CHECK_CUDA(cudaFuncSetAttribute(chol_whiten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           128 * 129 * (int)sizeof(double)));
+        attr = true;
+    }
+    chol_whiten_kernel<<<1, 256, smem, st>>>(G, n, Wt);
+    VB_CHECK_LAUNCH();
+    return 0;
+}
+
 int eigh_f64(const double* G, int n, double* evals, double* evecs, int max_sweeps, double tol, void* ws,
              size_t ws_bytes, int* info, int* launches, cudaStream_t st) {
     VB_REQUIRE(n >= 1, "eigh: n must be >= 1");

@@ -73,6 +73,16 @@ def eigh(G, max_sweeps=0, tol=0.0, check=True):
     return evals, evecs, {"sweeps": int(info[0]), "converged": bool(info[1])}
 
 
+def chol_whiten(G):
+    """Wt (n,n) fp64, lower triangular, with Wt G Wt^T = I for a small SPD Gramian (n <= 128); no host sync."""
+    lib = _cabi.lib()
+    n = G.shape[0]
+    G = G.contiguous()
+    Wt = empty((n, n), torch.float64, G.device)
+    _cabi.check(lib.vb_chol_whiten_f64(ptr(G), n, ptr(Wt), stream_ptr()), "vb_chol_whiten_f64")
+    return Wt
+
+
 def eigh_topk(G, k, tol=0.0, max_iter=0):
     """Leading k eigenpairs of a symmetric PSD fp64 matrix by block subspace iteration.
 

@@ -107,10 +107,11 @@ def _gram_of_pair(S, l, reduce):
 
 
 def _whitening(G):
-    """Rows of Wt: eigenvectors of the Gramian scaled by 1/sqrt(eigenvalue) (numerically null directions dropped)."""
+    """Wt with Wt G Wt^T = I (numerically dependent directions zeroed): Cholesky whitening for the small Gramians of
+    the sketches (one 150 us launch, no host synchronisation), eigen-based above 128 rows."""
+    if G.shape[0] <= 128:
+        return kernels.chol_whiten(G)
     evals, evecs, _ = kernels.eigh(G, check=False)
-    # numerically null directions are zeroed, not dropped: no data-dependent shapes, hence no host synchronisation
-    # (a zero row of Wt gives a zero row of the basis, which contributes nothing to any later product)
     scale = torch.where(evals > evals[0] * 1e-30, torch.rsqrt(torch.clamp(evals, min=1e-300)), torch.zeros_like(evals))
     return (evecs * scale[:, None]).contiguous()
 
