@@ -188,6 +188,20 @@ int vb_checker_correct_f32(const float* in, float* out, int nframes, int ny, int
 int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitch, size_t width_bytes,
                     size_t height, void* stream);
 
+/* ---- S/N of test resolution elements, S/N map ------------------------------------------
+ * Exact circular-aperture sums: out[a] = sum over pixels of area(circle(xs[a], ys[a], r) ∩ unit pixel) * img.
+ * Replaces: photutils CircularAperture + aperture_photometry(method='exact')   metrics/snr_source.py:393-397 */
+int vb_aperture_sums_f64(const float* img, int H, int W, const double* xs, const double* ys, int nap, double r,
+                         double* out, void* stream);
+/* S/N (Mawet et al. 2014 small-sample penalty) at npts integer pixel positions (px, py): one warp per position sums
+ * the non-overlapping apertures of its ring.  img2 (optional second frame, e.g. opposite derotation) adds its
+ * apertures to the noise sample, use2alone keeps only those; flux_out (optional) receives the source fluxes.
+ * (cy, cx) = frame centre.  Replaces: snr() per pixel forked over processes by snrmap()
+ * metrics/snr_source.py:32-204, 229-318, 321-455 */
+int vb_snr_points_f64(const float* img, const float* img2, int H, int W, const int* px, const int* py, int npts,
+                      double fwhm, double cy, double cx, int exclude_negative_lobes, int use2alone, double* snr_out,
+                      double* flux_out, void* stream);
+
 /* ---- measurement aid (bench.py) -------------------------------------------------------------
  * Register-only FFMA stream: blocks x 256 threads x iters x 32 fused multiply-adds; `out` receives
  * blocks*256 floats.  Timed by the caller with CUDA events to report the FP32 FMA peak of this GPU at its

@@ -14,7 +14,9 @@ One stand-in is not empty: ``skimage.draw.disk``, which ``var/shapes.py:88`` (``
 published rule (``skimage/draw/draw.py`` ``ellipse`` -> ``_ellipse_in_shape``: bounding box
 ceil(c - R) .. floor(c + R) clipped to ``shape``, pixels with ((r-cy)/R)^2 + ((c-cx)/R)^2 < 1).  The resulting
 index sets are checked against the reference's own ``test_mask_circle`` known answers
-(``tests/test_reference_own_tests.py``).
+(``tests/test_reference_own_tests.py``).  Likewise ``photutils.aperture.CircularAperture`` /
+``aperture_photometry(method='exact')`` (``metrics/snr_source.py:393-397``) are served from the oracle's restatement
+of the exact circle-pixel overlap, so that the reference's own ``snr`` / ``snrmap`` can run.
 """
 import importlib.abc
 import importlib.machinery
@@ -51,6 +53,28 @@ def _disk(center, radius, *, shape=None):
     return rr + upper_left[0], cc + upper_left[1]
 
 
+class _CircularAperture:
+    """Stand-in for ``photutils.aperture.CircularAperture`` (positions as (x, y) pairs, radius r)."""
+
+    def __init__(self, positions, r):
+        self.positions = [tuple(p) for p in positions]
+        self.r = float(r)
+
+
+def _aperture_photometry(data, apertures, method="exact", **kwargs):
+    """Stand-in for ``photutils.aperture.aperture_photometry(..., method='exact')``: photutils is not installed, so
+    the exact circle-pixel overlap sums come from the oracle's restatement (``vip_oracle.aperture_sums_exact``,
+    pinned by photutils' documented known answer).  Lets the reference's own ``snr`` / ``snrmap`` run, which pins
+    everything AROUND the aperture sums (centres, statistics, masks)."""
+    if method != "exact":
+        raise ImportError("photutils stand-in: only method='exact' is available")
+    import numpy as np
+    from . import vip_oracle
+    xs = [p[0] for p in apertures.positions]
+    ys = [p[1] for p in apertures.positions]
+    return {"aperture_sum": vip_oracle.aperture_sums_exact(np.asarray(data), xs, ys, apertures.r)}
+
+
 class _Stub(types.ModuleType):
     __path__ = []
 
@@ -60,6 +84,10 @@ class _Stub(types.ModuleType):
         modname = self.__name__
         if modname == "skimage.draw" and name == "disk":
             return _disk
+        if modname == "photutils.aperture" and name == "CircularAperture":
+            return _CircularAperture
+        if modname == "photutils.aperture" and name == "aperture_photometry":
+            return _aperture_photometry
 
         class _Missing(Warning):
             def __init__(self, *a, **k):

@@ -159,6 +159,20 @@ _NAMES = ("annular_weights", "gram", "cross_gram", "eigh", "chol_whiten", "eigh_
           "collapse", "upload_and_gram", "upload_columns", "gather_columns", "scatter_columns", "gemm")
 
 
+def aperture_sums_device(frame_dev, xs, ys, r):
+    from oracle import vip_oracle as O
+    return torch.from_numpy(O.aperture_sums_exact(frame_dev.numpy().astype(np.float64), xs, ys, r))
+
+
+def snr_points_device(frame_dev, xs, ys, fwhm, frame2_dev=None, use2alone=False, exclude_negative_lobes=False):
+    from oracle import vip_oracle as O
+    a = frame_dev.numpy()
+    b = None if frame2_dev is None else frame2_dev.numpy()
+    res = [O.snr(a, (int(x), int(y)), fwhm, True, b, use2alone, exclude_negative_lobes) for x, y in zip(xs, ys)]
+    return (torch.tensor([r[-1] for r in res], dtype=torch.float64),
+            torch.tensor([r[2] for r in res], dtype=torch.float64))
+
+
 def install(monkeypatch):
     """Route ``vip_b200`` through the stand-ins above for the duration of one test."""
     import vip_b200
@@ -169,7 +183,10 @@ def install(monkeypatch):
         monkeypatch.setattr(kernels, name, g[name])
     monkeypatch.setattr(_device, "require_cuda", lambda: CPU)
     monkeypatch.setattr(_device, "free_memory_bytes", lambda: 8 << 30)
-    for mod in (pca_fullfr, annular, sdi):
+    from vip_b200.metrics import snr_source
+    monkeypatch.setattr(snr_source, "aperture_sums_device", aperture_sums_device)
+    monkeypatch.setattr(snr_source, "snr_points_device", snr_points_device)
+    for mod in (pca_fullfr, annular, sdi, snr_source):
         if hasattr(mod, "require_cuda"):
             monkeypatch.setattr(mod, "require_cuda", lambda: CPU)
     return vip_b200

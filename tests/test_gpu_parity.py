@@ -1073,3 +1073,80 @@ def test_chol_whiten_kernel(n):
         Q2 = W2 @ Y2
         keep = np.arange(n) != 3
         np.testing.assert_allclose((Q2 @ Q2.T)[np.ix_(keep, keep)], np.eye(n - 1), atol=1e-5)
+
+
+# ------------------------------------------------------------------ S/N and S/N maps
+def test_snr_and_aperture_sums_vs_oracle(vb):
+    """``vip_b200.snr`` (exact circular-aperture sums on the GPU) against the oracle, every option of the reference
+    (``metrics/snr_source.py:321-455``); aperture sums also against pi r^2 on an image of ones."""
+    import torch
+    from vip_b200.metrics.snr_source import aperture_sums_device
+    rng = np.random.default_rng(5)
+    a = rng.normal(size=(40, 41)).astype(np.float32)
+    a2 = rng.normal(size=(40, 41)).astype(np.float32)
+    for xy in ((30, 22), (12.5, 9.25), (33, 5)):
+        for kw in (dict(), dict(exclude_negative_lobes=True), dict(array2=a2), dict(array2=a2, use2alone=True),
+                   dict(exclude_theta_range=(20, 70))):
+            r = vb.snr(a, xy, 4.0, full_output=True, **kw)
+            o = O.snr(a, xy, 4.0, full_output=True, **kw)
+            assert r[0] == o[0] and r[1] == o[1]
+            np.testing.assert_allclose(r[2], o[2], rtol=1e-10, atol=1e-10)
+            np.testing.assert_allclose(r[3], o[3], rtol=1e-10, atol=1e-10)
+            np.testing.assert_allclose(r[4], o[4], rtol=1e-8)
+    with pytest.raises(RuntimeError):
+        vb.snr(a, (20.5, 20.2), 4.0)
+    with pytest.raises(TypeError):
+        vb.snr(a, [30, 22], 4.0)
+    ones = torch.ones((64, 64), device="cuda")
+    xs, ys = rng.uniform(10, 50, 50), rng.uniform(10, 50, 50)
+    for r in (0.3, 1.0, 2.0, 4.75):
+        np.testing.assert_allclose(aperture_sums_device(ones, xs, ys, r).cpu().numpy(), np.pi * r * r, rtol=1e-12)
+    bad = a.copy()
+    bad[22, 30] = np.nan
+    assert np.isnan(vb.snr(bad, (30, 22), 4.0))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(exclude_negative_lobes=True), dict(with2=True), dict(with2=True, use2alone=True)])
+def test_snrmap_vs_oracle(vb, kw):
+    """``vip_b200.snrmap`` (one warp per pixel) against the oracle's per-pixel loop (``snr_source.py:32-204``): every
+    pixel of the annulus, zero pixels excluded, the other pixels exactly 0."""
+    kw = dict(kw)
+    rng = np.random.default_rng(9)
+    a = rng.normal(size=(41, 44)).astype(np.float32)
+    a[7, 30] = 0.0
+    a2 = rng.normal(size=(41, 44)).astype(np.float32) if kw.pop("with2", False) else None
+    m = vb.snrmap(a, 3.5, array2=a2, verbose=False, nproc=4, **kw)
+    ref = O.snrmap(a, 3.5, array2=a2, **kw)
+    assert m.dtype == a.dtype and m.shape == a.shape
+    assert np.array_equal(m == 0, ref == 0)
+    np.testing.assert_allclose(m, ref, rtol=2e-5, atol=2e-6)          # the map is stored in the frame's dtype (fp32)
+    with pytest.raises(NotImplementedError):
+        vb.snrmap(a, 3.5, approximated=True)
+    with pytest.raises(NotImplementedError):
+        vb.snrmap(a, 3.5, known_sources=(20, 20))
+
+
+def test_snrmap_finds_the_injected_planet_and_pca_snr_grid(vb):
+    """The reference's own acceptance test of the S/N map (tests/pre_3_10/test_metrics_snr.py): the map of a PCA
+    final frame peaks within 2 px of the injected companion -- here on the synthetic cube -- and
+    ``pca(source_xy=, ncomp=(lo, hi))`` (S/N-optimised number of components, ``utils_pca.py:242-418``) returns the
+    reference's (cube, optimal frame, table) with the same S/Ns, fluxes and choice as the oracle."""
+    cube, angs = adi_cube(40, 64, 4, 70.0, seed=12, planet_peak=400.0)
+    cy = cx = 32
+    # derotation aligns the companion at PA = 0 of the generator's convention: find it in the oracle-free way
+    frame = vb.pca(cube, angs, ncomp=4, verbose=False)
+    m = vb.snrmap(frame, 4.0, verbose=False)
+    y1, x1 = np.unravel_index(np.nanargmax(m), m.shape)
+    sub = np.nan_to_num(frame.copy(), nan=-np.inf)
+    y0, x0 = np.unravel_index(np.argmax(sub), sub.shape)
+    assert abs(int(y1) - int(y0)) <= 2 and abs(int(x1) - int(x0)) <= 2 and m[y1, x1] > 5
+    res = vb.pca(cube, angs, ncomp=(1, 6), source_xy=(int(x0), int(y0)), fwhm=4, verbose=False, full_output=True)
+    cubeout, optfr, table = res
+    o_cube, o_fr, o_tab, o_npc = O.pca_grid_snr(cube, angs, (1, 6), (int(x0), int(y0)), 4)
+    assert list(table["PCs"]) == o_tab["PCs"]
+    np.testing.assert_allclose(np.asarray(table["S/Ns"]), o_tab["S/Ns"], rtol=2e-3)
+    np.testing.assert_allclose(np.asarray(table["fluxes"]), o_tab["fluxes"], rtol=2e-3)
+    assert int(table["PCs"][int(np.argmax(table["S/Ns"]))]) == o_npc
+    assert rel_err(optfr, o_fr) < FRAME_TOL and cubeout.shape == o_cube.shape
+    only = vb.pca(cube, angs, ncomp=(1, 6), source_xy=(int(x0), int(y0)), fwhm=4, verbose=False)
+    np.testing.assert_array_equal(only, optfr)

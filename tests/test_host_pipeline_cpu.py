@@ -251,3 +251,26 @@ def test_randsvd_is_the_exact_arithmetic_result_of_sklearns_algorithm(vb, golden
     fr = vb.pca(cube, angs, ncomp=4, svd_mode="randsvd", verbose=False)
     np.random.seed(3)
     assert rel_err(fr, O.pca_fullframe(cube.astype(np.float64), angs, ncomp=4, svd_mode="randsvd")) < 1e-4
+
+
+def test_snr_snrmap_and_snr_optimised_grid_host_logic(vb):
+    """Host side of ``vip_b200.snr`` / ``snrmap`` and of ``pca(source_xy=, ncomp=(lo, hi))`` (return layouts, masks,
+    option handling) through the stand-ins, against the oracle."""
+    rng = np.random.default_rng(5)
+    a = rng.normal(size=(40, 41)).astype(np.float32)
+    a[5, 20] = 0.0
+    for kw in (dict(), dict(exclude_negative_lobes=True), dict(exclude_theta_range=(20, 70))):
+        r = vb.snr(a, (30, 22), 4.0, full_output=True, **kw)
+        o = O.snr(a, (30, 22), 4.0, full_output=True, **kw)
+        assert len(r) == 5
+        for x, y in zip(r, o):
+            np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(vb.snrmap(a, 4.0, verbose=False), O.snrmap(a, 4.0))
+    cube, angs = adi_cube(20, 40, 3, 60.0, seed=12, planet_peak=300.0)
+    cubeout, fr, table = vb.pca(cube, angs, ncomp=(1, 4), source_xy=(28, 24), fwhm=4, verbose=False, full_output=True)
+    o_cube, o_fr, o_tab, o_npc = O.pca_grid_snr(cube, angs, (1, 4), (28, 24), 4)
+    assert cubeout.shape == o_cube.shape == (4, 40, 40) and list(table.columns) == ["PCs", "S/Ns", "fluxes"]
+    np.testing.assert_allclose(np.asarray(table["S/Ns"]), o_tab["S/Ns"], rtol=5e-3)
+    assert int(table["PCs"][int(np.argmax(table["S/Ns"]))]) == o_npc
+    assert rel_err(fr, o_fr) < 3e-4
+    np.testing.assert_array_equal(vb.pca(cube, angs, ncomp=(1, 4), source_xy=(28, 24), fwhm=4, verbose=False), fr)

@@ -188,3 +188,33 @@ def test_randsvd_stable_is_sklearns_algorithm_in_exact_arithmetic():
                                   random_state=np.random.RandomState(4))
     assert np.max(np.abs(V_st32.T @ V_st32 - P_exact)) < 1e-6
     assert np.max(np.abs(V_sk32.T.astype(np.float64) @ V_sk32 - P_exact)) > 1e-2
+
+
+def test_exact_aperture_sums_known_answers():
+    """The restated exact circular-aperture sum (photutils is not installed): photutils' documented example -- a
+    radius-3 aperture on an image of ones sums to 28.274333882308138 -- and geometric identities: area pi r^2 for any
+    sub-pixel centre, linearity, clipping at the image edge, NaN propagation, single-pixel weights against a fine
+    numerical quadrature."""
+    ones = np.ones((60, 60))
+    s = O.aperture_sums_exact(ones, [30, 40], [30, 40], 3.0)
+    np.testing.assert_allclose(s, 28.274333882308138, rtol=1e-13)
+    rng = np.random.default_rng(1)
+    xs, ys = rng.uniform(10, 50, 20), rng.uniform(10, 50, 20)
+    for r in (0.3, 1.0, 2.0, 4.75):
+        np.testing.assert_allclose(O.aperture_sums_exact(ones, xs, ys, r), np.pi * r * r, rtol=1e-12)
+    img = rng.normal(size=(60, 60))
+    np.testing.assert_allclose(O.aperture_sums_exact(3.0 * img + ones, xs, ys, 2.0),
+                               3.0 * O.aperture_sums_exact(img, xs, ys, 2.0) + np.pi * 4.0, rtol=1e-11, atol=1e-11)
+    # half of a disc hangs over the edge
+    np.testing.assert_allclose(O.aperture_sums_exact(ones, [-0.5], [30.0], 3.0), 0.5 * np.pi * 9.0, rtol=1e-12)
+    bad = img.copy()
+    bad[30, 30] = np.nan
+    assert np.isnan(O.aperture_sums_exact(bad, [30.2], [29.9], 2.0)[0])
+    assert np.isfinite(O.aperture_sums_exact(bad, [40.0], [40.0], 2.0)[0])
+    # weight of one pixel against a 2000 x 2000 sub-pixel quadrature
+    g = (np.arange(2000) + 0.5) / 2000 - 0.5
+    for (dx, dy, r) in ((1.3, 0.4, 1.5), (0.0, 0.0, 0.45), (2.1, 1.9, 3.0), (0.2, 2.6, 2.5)):
+        X, Y = np.meshgrid(dx + g, dy + g)
+        quad = np.mean(X * X + Y * Y <= r * r)
+        w = O.circle_rect_area(np.array(dx - 0.5), np.array(dy - 0.5), np.array(dx + 0.5), np.array(dy + 0.5), r)
+        assert abs(float(w) - quad) < 2e-3

@@ -104,3 +104,28 @@ def test_pca_incremental_bit_identical(ref):
                                   O.pca_incremental(cube, angs, 8, ncomp=2, collapse="mean"))
     with pytest.raises(ValueError):
         O.pca_incremental(cube, angs, 2, ncomp=3)          # first batch smaller than ncomp (scikit-learn's check)
+
+
+def test_snr_and_snrmap_logic_bit_identical(ref):
+    """``metrics.snr`` / ``snrmap`` of the unmodified reference (with the photutils stand-in of oracle/ref_loader.py
+    supplying the exact aperture sums) against the oracle: aperture centres, small-sample statistics, the
+    exclude_negative_lobes / array2 / use2alone options and the pixel mask of the map."""
+    from vip_hci.metrics.snr_source import snr, snrmap, indep_ap_centers
+    rng = np.random.default_rng(5)
+    a = rng.normal(size=(40, 41))
+    a2 = rng.normal(size=(40, 41))
+    a[3, 7] = 0.0                                   # a zero pixel drops out of the map
+    for xy in ((30, 22), (12.5, 9.25), (33, 5)):
+        for kw in (dict(), dict(exclude_negative_lobes=True), dict(array2=a2), dict(array2=a2, use2alone=True)):
+            r = snr(a, xy, 4.0, full_output=True, **kw)
+            o = O.snr(a, xy, 4.0, full_output=True, **kw)
+            for x, y in zip(r, o):
+                np.testing.assert_array_equal(x, y)
+        np.testing.assert_array_equal(np.array(indep_ap_centers(a, xy, 4.0, exclude_theta_range=(20, 70))),
+                                      np.array(O.indep_ap_centers(a, xy, 4.0, exclude_theta_range=(20, 70))))
+    with pytest.raises(RuntimeError):
+        O.snr(a, (20.5, 20.2), 4.0)
+    m_ref = snrmap(a, 4.0, nproc=1, verbose=False)
+    np.testing.assert_array_equal(m_ref, O.snrmap(a, 4.0))
+    m_ref = snrmap(a, 3.0, nproc=1, verbose=False, array2=a2, exclude_negative_lobes=True)
+    np.testing.assert_array_equal(m_ref, O.snrmap(a, 3.0, array2=a2, exclude_negative_lobes=True))

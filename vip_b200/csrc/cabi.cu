@@ -64,6 +64,9 @@ int gather_columns(const float*, int, size_t, const int*, int, float*, cudaStrea
 int scatter_columns(const float*, int, int, const int*, size_t, float*, cudaStream_t);
 int profile_read(float* out);
 int fp32_probe(float*, int, int, cudaStream_t);
+int aperture_sums(const float*, int, int, const double*, const double*, int, double, double*, cudaStream_t);
+int snr_points(const float*, const float*, int, int, const int*, const int*, int, double, double, double, int, int,
+               double*, double*, cudaStream_t);
 
 // exp(-2 pi i j / N) tables for the FFT path, one per (device, N), built in fp64 on the host
 static const float2* twiddle_table(int N) {
@@ -325,6 +328,20 @@ int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitc
     VB_CHECK_CUDA(cudaMemcpy2DAsync(dst, dpitch, src_host, spitch, width_bytes, height, cudaMemcpyHostToDevice,
                                     (cudaStream_t)stream));
     return 0;
+}
+
+int vb_aperture_sums_f64(const float* img, int H, int W, const double* xs, const double* ys, int nap, double r,
+                         double* out, void* stream) {
+    g_launches += 1;
+    return aperture_sums(img, H, W, xs, ys, nap, r, out, (cudaStream_t)stream);
+}
+
+int vb_snr_points_f64(const float* img, const float* img2, int H, int W, const int* px, const int* py, int npts,
+                      double fwhm, double cy, double cx, int exclude_negative_lobes, int use2alone, double* snr_out,
+                      double* flux_out, void* stream) {
+    g_launches += 1;
+    return snr_points(img, img2, H, W, px, py, npts, fwhm, cy, cx, exclude_negative_lobes, use2alone, snr_out,
+                      flux_out, (cudaStream_t)stream);
 }
 
 int vb_fp32_probe(float* out, int blocks, int iters, void* stream) {

@@ -203,6 +203,7 @@ subtract_hp_kernel(const float* Src, const double* __restrict__ C, int ldc, cons
                    float* const* __restrict__ Rrows) {  // Src may alias R; Rrows: see project_subtract_hp_f32
     constexpr int NT = PT / PX;
     constexpr int HROWS = 128;
+    constexpr int U = 8;                       // rows per batch; the NEXT batch is loaded while this one is computed
     __shared__ __align__(16) double Cs[HROWS][KC];
     const size_t j = ((size_t)blockIdx.x * NT + threadIdx.x) * PX;
     const bool jin = j < p;
@@ -219,6 +220,19 @@ subtract_hp_kernel(const float* Src, const double* __restrict__ C, int ldc, cons
             v[x][q] = t;
         }
     }
+    auto load_batch = [&](const float* src, int ib, int ni, float (&mv)[U][PX]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (PX == 2) {
+                const float2 t = (ib + u < ni) ? *reinterpret_cast<const float2*>(src + (size_t)(ib + u) * p)
+                                               : make_float2(0.f, 0.f);
+                mv[u][0] = t.x;
+                mv[u][PX - 1] = t.y;
+            } else {
+                mv[u][0] = (ib + u < ni) ? src[(size_t)(ib + u) * p] : 0.f;
+            }
+        }
+    };
     for (int i0 = 0; i0 < n; i0 += HROWS) {
         const int ni = (n - i0 < HROWS) ? n - i0 : HROWS;
         __syncthreads();
@@ -230,21 +244,12 @@ subtract_hp_kernel(const float* Src, const double* __restrict__ C, int ldc, cons
         if (jin) {
             const float* src = Src + (size_t)i0 * p + j;
             float* dst = R + (size_t)i0 * p + j;
-            for (int ib = 0; ib < ni; ib += 8) {
-                float mv[8][PX];
+            float mv[U][PX], nx[U][PX];
+            load_batch(src, 0, ni, mv);
+            for (int ib = 0; ib < ni; ib += U) {
+                if (ib + U < ni) load_batch(src, ib + U, ni, nx);       // in flight during the DFMA chains below
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (PX == 2) {
-                        const float2 t = (ib + u < ni) ? *reinterpret_cast<const float2*>(src + (size_t)(ib + u) * p)
-                                                       : make_float2(0.f, 0.f);
-                        mv[u][0] = t.x;
-                        mv[u][PX - 1] = t.y;
-                    } else {
-                        mv[u][0] = (ib + u < ni) ? src[(size_t)(ib + u) * p] : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < U; ++u) {
                     if (ib + u < ni) {
                         // row i of the result goes to R + i p, or -- scattered output -- to the row pointer the caller
                         // supplied (possibly PEER memory over NVLink: the exchange to frame shards rides on this pass)
@@ -270,6 +275,10 @@ subtract_hp_kernel(const float* Src, const double* __restrict__ C, int ldc, cons
                         }
                     }
                 }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int x = 0; x < PX; ++x) mv[u][x] = nx[u][x];
             }
         }
     }

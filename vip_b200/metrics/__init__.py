@@ -1,0 +1,2 @@
+"""S/N of test resolution elements and S/N maps on the GPU (drop-ins for ``vip_hci.metrics``)."""
+from .snr_source import snr, snrmap, indep_ap_centers      # noqa: F401

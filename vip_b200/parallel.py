@@ -236,6 +236,7 @@ class PeerExchange:
     def get(cls, n, H, W, world, rank, fb, pb, device, group):
         key = (n, H, W, world, rank, str(device), id(group))
         if key not in cls._cache:
+            cls._cache.clear()               # one geometry at a time: the buffers are as large as the cube shard
             try:
                 cls._cache[key] = cls(n, H, W, world, rank, fb, pb, device, group)
             except Exception as exc:                                       # noqa: BLE001

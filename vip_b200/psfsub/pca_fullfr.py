@@ -664,8 +664,6 @@ def pca(*all_args: List, **all_kwargs: dict):
                      "randomized SVD")
     if p.mask_rdi is not None:
         _unsupported("`mask_rdi` (data imputation)")
-    if p.source_xy is not None and isinstance(p.ncomp, (tuple, list)):
-        _unsupported("`source_xy` with a tuple/list `ncomp` (S/N-optimised number of components)")
     if p.smooth is not None:
         _unsupported("`smooth`")
     imlib = _mode_name(p.imlib)
@@ -691,6 +689,34 @@ def pca(*all_args: List, **all_kwargs: dict):
             raise ValueError("`angle_list` vector has wrong length. It must equal the number of frames in the cube")
         cubeout, pclist = _pca_grid_device(p.cube, cube_ref, -angs, p.ncomp, p.scaling, p.mask_center_px,
                                            p.svd_mode, p.collapse, weights=p.weights, **rot_options)
+        if p.source_xy is not None:
+            # S/N-optimised number of components (pca_grid with source_xy, utils_pca.py:242-275, 352-418): for every
+            # frame of the grid the mean S/N and mean aperture flux over the pixels of the FWHM disc around the
+            # source (fmerit='mean'), all S/N evaluations on the GPU; returns (:778) (cube, optimal frame, table)
+            # with full_output, the optimal frame otherwise
+            if p.fwhm is None:
+                raise ValueError("if source_xy is provided, so should fwhm")
+            from ..metrics.snr_source import snr_points_device
+            from ..var.shapes import disk_indices
+            import pandas as pd
+            x, y = p.source_xy
+            yy, xx = disk_indices(y, x, p.fwhm / 2.0, cubeout.shape[1:])
+            snrlist, fluxlist = [], []
+            for i in range(cubeout.shape[0]):
+                sv, fl = snr_points_device(cubeout[i].contiguous(), xx, yy, p.fwhm)
+                snr_value = float(sv.mean().item())
+                snrlist.append(0 if np.isnan(snr_value) else snr_value)
+                fluxlist.append(float(fl.mean().item()))
+            argmax = int(np.argmax(snrlist))
+            final = _to_numpy_like(cubeout, p.cube.dtype)
+            table = pd.DataFrame({"PCs": pclist, "S/Ns": snrlist, "fluxes": fluxlist})
+            if p.verbose:
+                print("Number of steps", len(pclist))
+                print("Optimal number of PCs = {}, for S/N={:.3f}".format(pclist[argmax], snrlist[argmax]))
+            frame = final[argmax]
+            if p.med_of_npcs:
+                final = np.median(final, axis=0)
+            return (final, frame, table) if p.full_output else frame
         final = _to_numpy_like(cubeout, p.cube.dtype)
         if p.med_of_npcs:
             final = np.median(final, axis=0)
