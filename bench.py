@@ -380,7 +380,9 @@ def run_gpu(args):
     n, size, k, delta, seed = CONFIGS[args.config]
     # N > 1: ONE cube, sharded over the ranks (vip_b200/parallel.py): total work fixed -> strong scaling
     cube, angs = adi_cube(n, size, k, delta, seed=seed)          # pageable host array: what a drop-in caller has
-    pinned = torch.from_numpy(cube).pin_memory()
+    from vip_b200._device import gpu_local_cpus
+    with gpu_local_cpus(local):                                  # pinned pages next to this rank's GPU (NUMA)
+        pinned = torch.from_numpy(cube).pin_memory()
     cube_pinned_np = pinned.numpy()
     if world == 1:
         cube_dev = pinned.cuda()

@@ -187,6 +187,10 @@ int vb_checker_correct_f32(const float* in, float* out, int nframes, int ny, int
  * dst[r][0..width) = src_host[r][0..width) for r < height, pitches in bytes (cudaMemcpy2DAsync). */
 int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitch, size_t width_bytes,
                     size_t height, void* stream);
+/* Contiguous host -> device copy.  A PAGEABLE source (a plain numpy array) is staged through a pinned double buffer by
+ * several host threads while the previous chunk is on the DMA engine (the driver's own staging is single-threaded,
+ * ~10 GB/s); a pinned source is one cudaMemcpyAsync.  The source may be reused when the call returns. */
+int vb_memcpy_h2d_staged(void* dst, const void* src_host, size_t nbytes, void* stream);
 
 /* ---- S/N of test resolution elements, S/N map ------------------------------------------
  * Exact circular-aperture sums: out[a] = sum over pixels of area(circle(xs[a], ys[a], r) ∩ unit pixel) * img.

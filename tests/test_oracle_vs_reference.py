@@ -129,3 +129,20 @@ def test_snr_and_snrmap_logic_bit_identical(ref):
     np.testing.assert_array_equal(m_ref, O.snrmap(a, 4.0))
     m_ref = snrmap(a, 3.0, nproc=1, verbose=False, array2=a2, exclude_negative_lobes=True)
     np.testing.assert_array_equal(m_ref, O.snrmap(a, 3.0, array2=a2, exclude_negative_lobes=True))
+
+
+def test_pca_annular_adimsdi_bit_identical(ref):
+    """``pca_annular(cube4d, ..., scale_list=, ncomp=(k_ifs, k_adi))`` (``pca_local.py:332-462``, ``_pca_sdi_fr``
+    :470-591) of the unmodified reference against the oracle: both passes, and the single-pass variant (k_adi None)."""
+    psfsub, _ = ref
+    from tools.make_golden import ifs_cube
+    cube, angs, sl = ifs_cube(z=5, n=8, size=24, seed=7)
+    for ncomp, kw in (((2, 2), dict(asize=4, delta_sep=(0.1, 0.3))), ((1, None), dict(asize=6, delta_sep=0.1)),
+                      ((2, 2), dict(asize=4, delta_sep=(0.05, 0.15), n_segments=2, collapse_ifs="median",
+                                    scaling="temp-mean"))):
+        r = psfsub.pca_annular(cube, angs, scale_list=sl, ncomp=ncomp, fwhm=3, verbose=False, full_output=True,
+                               nproc=1, **kw)
+        o = O.pca_annular_sdi(cube, angs, sl, ncomp, fwhm=3, full_output=True, **kw)
+        assert len(r) == len(o) == 3
+        for a, b in zip(r, o):
+            np.testing.assert_array_equal(a, b)

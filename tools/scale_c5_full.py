@@ -70,8 +70,10 @@ for s0 in range(0, n, 256):                                        # chunked: bo
         blk[:, c0:c0 + bw] += 3.0 * torch.randn((s1 - s0, bw), device=dev, generator=gens[b])
     shard[s0:s1] = blk
 del blk
-host = torch.empty((n, p1 - p0), dtype=torch.float32).pin_memory()
-host.copy_(shard)
+from vip_b200._device import gpu_local_cpus                # noqa: E402
+with gpu_local_cpus(local):                                # pinned pages on the NUMA node of this rank's GPU
+    host = torch.empty((n, p1 - p0), dtype=torch.float32).pin_memory()
+    host.copy_(shard)
 host_np = host.numpy()
 torch.cuda.synchronize()
 shape = (n, size, size)

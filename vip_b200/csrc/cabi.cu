@@ -64,6 +64,7 @@ int gather_columns(const float*, int, size_t, const int*, int, float*, cudaStrea
 int scatter_columns(const float*, int, int, const int*, size_t, float*, cudaStream_t);
 int profile_read(float* out);
 int fp32_probe(float*, int, int, cudaStream_t);
+int memcpy_h2d_staged(void*, const void*, size_t, cudaStream_t);
 int aperture_sums(const float*, int, int, const double*, const double*, int, double, double*, cudaStream_t);
 int snr_points(const float*, const float*, int, int, const int*, const int*, int, double, double, double, int, int,
                double*, double*, cudaStream_t);
@@ -347,6 +348,10 @@ int vb_snr_points_f64(const float* img, const float* img2, int H, int W, const i
 int vb_fp32_probe(float* out, int blocks, int iters, void* stream) {
     g_launches += 1;
     return fp32_probe(out, blocks, iters, (cudaStream_t)stream);
+}
+
+int vb_memcpy_h2d_staged(void* dst, const void* src_host, size_t nbytes, void* stream) {
+    return memcpy_h2d_staged(dst, src_host, nbytes, (cudaStream_t)stream);
 }
 
 void vb_profile_enable(int on) { profile_enable(on); }

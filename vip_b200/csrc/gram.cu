@@ -427,6 +427,66 @@ static void stage_slab(const float* host, int n, size_t p, size_t c0, size_t c1,
     for (auto& x : th) x.join();
 }
 
+// Contiguous host -> device copy of `nbytes` on stream `st`, staged through a pinned double buffer by several host
+// threads when the source is pageable (plain numpy arrays): ~3-4x the rate of the driver's own single-threaded
+// staging.  Returns after the last chunk has been QUEUED (the pinned buffers belong to the library); the caller's
+// source may be reused as soon as the call returns.  Pinned sources take one plain cudaMemcpyAsync.
+int memcpy_h2d_staged(void* dst, const void* src_host, size_t nbytes, cudaStream_t st) {
+    if (nbytes == 0) return 0;
+    if (host_is_pinned(src_host) || getenv("VIP_B200_NO_STAGING") != nullptr) {
+        VB_CHECK_CUDA(cudaMemcpyAsync(dst, src_host, nbytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    static Stager stagers[64];
+    static std::mutex mu;
+    int dev = 0;
+    VB_CHECK_CUDA(cudaGetDevice(&dev));
+    VB_REQUIRE(dev >= 0 && dev < 64, "memcpy_h2d_staged: device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(mu);              // one staged copy per process at a time (shared buffers)
+    Stager& sg = stagers[dev];
+    const size_t chunk = (size_t)32 << 20;
+    if (!sg.ev_ready) {
+        for (int i = 0; i < 2; ++i) VB_CHECK_CUDA(cudaEventCreateWithFlags(&sg.done[i], cudaEventDisableTiming));
+        sg.ev_ready = true;
+    }
+    if (sg.cap < chunk) {
+        for (int i = 0; i < 2; ++i) {
+            if (sg.buf[i]) cudaFreeHost(sg.buf[i]);
+            sg.buf[i] = nullptr;
+            if (cudaHostAlloc(&sg.buf[i], chunk, cudaHostAllocDefault) != cudaSuccess) {
+                (void)cudaGetLastError();
+                sg.cap = 0;
+                VB_CHECK_CUDA(cudaMemcpyAsync(dst, src_host, nbytes, cudaMemcpyHostToDevice, st));
+                return 0;
+            }
+        }
+        sg.cap = chunk;
+    }
+    const int nt = stager_threads();
+    const char* src = reinterpret_cast<const char*>(src_host);
+    char* d = reinterpret_cast<char*>(dst);
+    int s = 0;
+    for (size_t off = 0; off < nbytes; off += chunk, ++s) {
+        const size_t len = (nbytes - off < chunk) ? nbytes - off : chunk;
+        const int b = s & 1;
+        if (s >= 2) VB_CHECK_CUDA(cudaEventSynchronize(sg.done[b]));
+        char* sb = reinterpret_cast<char*>(sg.buf[b]);
+        auto work = [&](int t) {
+            const size_t a0 = len * t / nt, a1 = len * (t + 1) / nt;
+            memcpy(sb + a0, src + off + a0, a1 - a0);
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+        VB_CHECK_CUDA(cudaMemcpyAsync(d + off, sb, len, cudaMemcpyHostToDevice, st));
+        VB_CHECK_CUDA(cudaEventRecord(sg.done[b], st));
+    }
+    // the pinned buffers must not be refilled by the next call before these DMAs are done
+    for (int b = 0; b < 2 && b < s; ++b) VB_CHECK_CUDA(cudaEventSynchronize(sg.done[b]));
+    return 0;
+}
+
 // one pixel slab to the device on `copy_stream`: direct strided DMA from pinned memory, or staged (buffer s % 2)
 static int upload_slab(const float* host, int n, size_t p, size_t c0, size_t c1, float* M, Stager* staged, int s,
                        cudaStream_t copy_stream) {

@@ -113,7 +113,19 @@ class CudaOps:
         from ._device import to_device_f32
         from .psfsub.sdi import RescaleOps, _stage1_frames, _CHUNK_BYTES
         z, n, H, W = cube4d.shape
-        sub = to_device_f32(np.ascontiguousarray(cube4d[:, frames]), device)      # (z, F, H, W)
+        if (len(frames) > 0 and frames == list(range(frames[0], frames[-1] + 1)) and cube4d.dtype == np.float32
+                and cube4d.flags["C_CONTIGUOUS"]):
+            # own frames of channel c are one contiguous block of the host cube: z staged copies straight into the
+            # device tensor, no host-side gather
+            from . import _cabi
+            from ._device import stream_ptr
+            sub = torch.empty((z, len(frames), H, W), dtype=torch.float32, device=device)
+            for c in range(z):
+                blk = cube4d[c, frames[0]:frames[-1] + 1]
+                _cabi.check(_cabi.lib().vb_memcpy_h2d_staged(int(sub[c].data_ptr()), int(blk.ctypes.data),
+                                                              int(blk.nbytes), stream_ptr()), "vb_memcpy_h2d_staged")
+        else:
+            sub = to_device_f32(np.ascontiguousarray(cube4d[:, frames]), device)      # (z, F, H, W)
         rops = RescaleOps(scale_list, H, device)
         per_frame = 4 * z * rops.big * rops.big * 4 * 2
         chunk = max(1, int(_CHUNK_BYTES // per_frame))
