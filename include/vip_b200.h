@@ -157,6 +157,16 @@ int vb_annular_weights_f64(const double* G, const double* Gt, int n, const int* 
 int vb_annular_direct_f64(const double* G, const double* Gt, int n, const int* idx, const int* len,
                           const int* frame, int nprob, int Lmax, int ncomp, const int* plist, int nlist, float* W,
                           int* iters, double* ws, void* stream);
+/* ncomp='auto' of pca_annular: the direct solver with `kmax` (<= 24) eigenpairs per problem; the number of components
+ * used for problem q is chosen by the reference's noise-decay rule -- smallest m >= 2 whose step
+ * std(res_{m-1}) - std(res_m) of the LIBRARY residuals falls below `noise_tol` -- evaluated from the eigenpairs and the
+ * row sums `rowsum[n]` of the library matrix (npx pixels per row), and returned in ncomp_out[q] (negative: the rule
+ * wanted more than kmax components; |value| were used).
+ * Replaces: get_eigenvectors(ncomp='auto', mode='noise')          psfsub/svd.py:622-672 */
+int vb_annular_auto_f64(const double* G, const double* Gt, int n, const int* idx, const int* len,
+                        const int* frame, int nprob, int Lmax, int kmax, const double* rowsum, double npx,
+                        double noise_tol, const int* plist, int nlist, float* W, int* iters, int* ncomp_out,
+                        double* ws, void* stream);
 /* dst[n x npx] = src[n x p][:, cols]  and the inverse scatter (matrix_segm = array[:, yy, xx],
  * cube_out[fr][yy, xx] = residuals[fr];  psfsub/pca_local.py:713, 786-787) */
 int vb_gather_columns_f32(const float* src, int n, size_t p, const int* cols, int npx, float* dst, void* stream);

@@ -155,7 +155,43 @@ def annular_weights(G, idx, lens, frames, ncomp, tol=0.0, max_iter=40, direct_fa
     return torch.from_numpy(W), torch.ones(nprob, dtype=torch.int32)
 
 
-_NAMES = ("annular_weights", "gram", "cross_gram", "eigh", "chol_whiten", "eigh_topk", "topk_supported", "pcs", "pcs_hilo", "project_subtract", "project_subtract_hp", "sub", "derotate",
+def annular_weights_auto(G, idx, lens, frames, rowsum, npx, noise_tol, kmax=24):
+    """Contract of ``kernels.annular_weights_auto``: the noise-decay rule evaluated from the eigenpairs of the
+    library Gramian and the row sums of the library matrix (no access to the matrix itself, like the kernel)."""
+    Gn = G.double().numpy()
+    rs = rowsum.double().numpy()
+    nprob = idx.shape[0]
+    W = np.zeros((nprob, Gn.shape[0]), dtype=np.float32)
+    used = np.zeros(nprob, dtype=np.int32)
+    for q in range(nprob):
+        I = idx[q, :int(lens[q])].numpy().astype(np.int64)
+        L = len(I)
+        w_, v_ = np.linalg.eigh(Gn[np.ix_(I, I)])
+        lam, X = w_[::-1], v_[:, ::-1]
+        tot = L * float(npx)
+        max_evs = int(min(L, npx))
+        k = min(int(kmax), L)
+        s2, sr, prev, decay, m, clipped = np.trace(Gn[np.ix_(I, I)]), rs[I].sum(), 0.0, 1.0, 0, False
+        while decay >= noise_tol:
+            m += 1
+            if m <= max_evs:
+                if m > k:
+                    clipped = True
+                    break
+                s2 -= lam[m - 1]
+                sr -= X[:, m - 1].sum() * (X[:, m - 1] @ rs[I])
+            noise = np.sqrt(max(s2 / tot - (sr / tot) ** 2, 0.0))
+            if m > 1:
+                decay = prev - noise
+            prev = noise
+        m = k if clipped else min(m, max_evs)
+        used[q] = -m if clipped else m
+        Xm, th = X[:, :m], lam[:m]
+        W[q, I] = Xm @ ((Xm.T @ Gn[I, int(frames[q])]) / th)
+    return torch.from_numpy(W), torch.from_numpy(used)
+
+
+_NAMES = ("annular_weights_auto", "annular_weights", "gram", "cross_gram", "eigh", "chol_whiten", "eigh_topk", "topk_supported", "pcs", "pcs_hilo", "project_subtract", "project_subtract_hp", "sub", "derotate",
           "collapse", "upload_and_gram", "upload_columns", "gather_columns", "scatter_columns", "gemm")
 
 

@@ -732,14 +732,88 @@ def test_pca_annular_4d_golden(vb, golden, golden_inputs):
     assert rel_err(fr, g["ann4d_list_median"]) < FRAME_TOL
 
 
+def test_pca_annular_adimsdi_vs_oracle(vb):
+    """Annular ADI+mSDI (``pca_local.py:332-462``, ``_pca_sdi_fr`` :470-591): spectral pass with per-channel
+    libraries (grouped Gramians + batched eigen-kernel), then the annular ADI pass, against the oracle (bit-identical
+    to the unmodified reference on these cases, ``test_oracle_vs_reference.py``).  Tolerance: a multiple of
+    max|cube| like the full-frame ADI+mSDI tests -- residuals are differences of halo-level fp32 samples
+    (eps32 * max|cube| = 5.6e-4 here)."""
+    from tools.make_golden import ifs_cube
+    cube, angs, sl = ifs_cube(z=5, n=8, size=24, seed=7)
+    tol = 1e-6 * float(np.max(np.abs(cube)))
+    for ncomp, kw in (((2, 2), dict(asize=4, delta_sep=(0.1, 0.3))), ((1, None), dict(asize=6, delta_sep=0.1)),
+                      ((2, 2), dict(asize=4, delta_sep=(0.05, 0.15), n_segments=2, collapse_ifs="median",
+                                    scaling="temp-mean"))):
+        o = O.pca_annular_sdi(cube, angs, sl, ncomp, fwhm=3, full_output=True, **kw)
+        r = vb.pca_annular(cube, angs, scale_list=sl, ncomp=ncomp, fwhm=3, verbose=False, full_output=True, **kw)
+        e0 = float(np.max(np.abs(r[0] - o[0])))
+        m = ~np.isnan(o[2])
+        e2 = float(np.max(np.abs(r[2][m] - o[2][m])))
+        print(f"annular ADI+mSDI {ncomp} {kw}: cube_out {e0:.2e}, frame {e2:.2e} (tol {tol:.2e})")
+        assert np.array_equal(np.isnan(r[2]), ~m)
+        assert e0 < tol and e2 < tol, (ncomp, kw)
+    # a larger IFS cube: 10 channels, 12 frames of 48x48 (several frame groups per Gramian, ragged channel libraries)
+    cube, angs, sl = ifs_cube(z=10, n=12, size=48, seed=3)
+    tol = 1e-6 * float(np.max(np.abs(cube)))
+    o = O.pca_annular_sdi(cube, angs, sl, (3, 2), fwhm=4, asize=6, delta_sep=(0.1, 0.5), full_output=True)
+    r = vb.pca_annular(cube, angs, scale_list=sl, ncomp=(3, 2), fwhm=4, asize=6, delta_sep=(0.1, 0.5), verbose=False,
+                       full_output=True)
+    m = ~np.isnan(o[2])
+    assert float(np.max(np.abs(r[0] - o[0]))) < tol and float(np.max(np.abs(r[2][m] - o[2][m]))) < tol
+
+
 def test_pca_annular_errors(vb, golden_inputs):
     cube, angs = golden_inputs["ann"]
     with pytest.raises(TypeError):
         vb.pca_annular(cube, angs[:-1], ncomp=2, asize=6, verbose=False)
     with pytest.raises(RuntimeError):      # PA threshold so large that no frame is left in the library
         vb.pca_annular(cube, angs, ncomp=2, asize=6, delta_rot=500, verbose=False)
-    with pytest.raises(NotImplementedError):
-        vb.pca_annular(cube, angs, ncomp="auto", asize=6, verbose=False)
+    with pytest.raises(TypeError):
+        vb.pca_annular(cube, angs, ncomp="automatic", asize=6, verbose=False)
+
+
+def test_pca_annular_ncomp_auto_vs_oracle(vb):
+    """``pca_annular(ncomp='auto', tol=)`` (``get_eigenvectors``, ``psfsub/svd.py:622-672``): number of components
+    per patch chosen INSIDE the direct eigen-kernel (``vb_annular_auto_f64``) by the reference's noise-decay rule.
+    The oracle (bit-identical to the unmodified reference on these cases) picks 6 ... 24 components; with that many
+    its fp32 arithmetic is 1.2e-4 ... 3e-4 away from its own float64 run, so 1e-4 is asserted against the float64 run."""
+    import torch
+    from vip_b200 import kernels
+    cube, angs = adi_cube(24, 40, 4, 80.0, seed=5)
+    for kw in (dict(ncomp="auto", tol=0.1, asize=5, delta_rot=(0.1, 0.4)),
+               dict(ncomp="auto", tol=0.5, asize=6, n_segments=2, delta_rot=0.3),
+               dict(ncomp="auto", tol=0.02, asize=5, delta_rot=0.2),
+               dict(ncomp=("auto", 2, "auto", 1), tol=0.1, asize=5, delta_rot=0.2),
+               dict(ncomp="auto", tol=0.1, asize=5, delta_rot=0)):
+        o = O.pca_annular(cube, angs, full_output=True, **kw)
+        o64 = O.pca_annular(cube.astype(np.float64), angs, full_output=True, **kw)
+        r = vb.pca_annular(cube, angs, full_output=True, verbose=False, **kw)
+        scale = np.max(np.abs(o64[0]))
+        e64, e32 = np.max(np.abs(r[0] - o64[0])) / scale, np.max(np.abs(r[0] - o[0])) / scale
+        print(f"pca_annular auto {kw}: vs float64 oracle {e64:.2e}, vs fp32 oracle {e32:.2e}")
+        assert e64 < PCA_TOL and e32 < 5e-4, kw
+        assert rel_err(r[2], o64[2]) < FRAME_TOL, kw
+    # the rule itself: chosen numbers of components of one segment against the rule on the residual matrix (numpy)
+    rng = np.random.default_rng(2)
+    n, npx = 30, 400
+    w = np.array([40, 20, 10, 5, 2.5, 1.2, 0.6, 0.3])
+    A = ((rng.normal(size=(n, 8)) * w[None, :]) @ rng.normal(size=(8, npx))
+         + 0.05 * rng.normal(size=(n, npx))).astype(np.float32)
+    lists = [np.array([j for j in range(n) if abs(j - f) > 2], dtype=np.int32) for f in range(n)]
+    Lmax = max(len(l) for l in lists)
+    idx = np.zeros((n, Lmax), dtype=np.int32)
+    lens = np.array([len(l) for l in lists], dtype=np.int32)
+    for f, l in enumerate(lists):
+        idx[f, :len(l)] = l
+    dev = torch.device("cuda")
+    At = torch.from_numpy(A).to(dev)
+    for tol in (2.0, 0.5, 0.1):                 # -> 0, 7 and 8-9 components per problem
+        _, used = kernels.annular_weights_auto(kernels.gram(At), torch.from_numpy(idx).to(dev),
+                                               torch.from_numpy(lens).to(dev),
+                                               torch.arange(n, dtype=torch.int32, device=dev),
+                                               At.double().sum(dim=1), npx, tol)
+        want = [O.get_eigenvectors_auto(A[l].astype(np.float64), "lapack", tol).shape[0] for l in lists]
+        assert used.cpu().tolist() == want, (tol, used.cpu().tolist(), want)
 
 
 # ------------------------------------------------------------------ sharded driver on one GPU

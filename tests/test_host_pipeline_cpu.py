@@ -274,3 +274,57 @@ def test_snr_snrmap_and_snr_optimised_grid_host_logic(vb):
     assert int(table["PCs"][int(np.argmax(table["S/Ns"]))]) == o_npc
     assert rel_err(fr, o_fr) < 3e-4
     np.testing.assert_array_equal(vb.pca(cube, angs, ncomp=(1, 4), source_xy=(28, 24), fwhm=4, verbose=False), fr)
+
+
+def test_pca_annular_adimsdi_vs_oracle(vb):
+    """``pca_annular(cube4d, scale_list=, ncomp=(k_ifs, k_adi))`` (``pca_local.py:332-462``, ``_pca_sdi_fr``
+    :470-591): host orchestration (channel libraries per annulus, grouped Gramians, both passes, single-pass variant)
+    against the oracle, which is bit-identical to the unmodified reference on these very cases
+    (``test_oracle_vs_reference.py::test_pca_annular_adimsdi_bit_identical``)."""
+    from tools.make_golden import ifs_cube
+    cube, angs, sl = ifs_cube(z=5, n=8, size=24, seed=7)
+    for ncomp, kw in (((2, 2), dict(asize=4, delta_sep=(0.1, 0.3))), ((1, None), dict(asize=6, delta_sep=0.1)),
+                      ((2, 2), dict(asize=4, delta_sep=(0.05, 0.15), n_segments=2, collapse_ifs="median",
+                                    scaling="temp-mean"))):
+        o = O.pca_annular_sdi(cube, angs, sl, ncomp, fwhm=3, full_output=True, **kw)
+        r = vb.pca_annular(cube, angs, scale_list=sl, ncomp=ncomp, fwhm=3, verbose=False, full_output=True, **kw)
+        assert len(r) == 3 and r[0].shape == o[0].shape
+        # the cube is float64 here and the product computes in fp32: the floor is the fp32 rounding of halo-level
+        # samples through the two rescalings, eps32 * max|cube| = 5.6e-4 (measured 2.8e-4 ... 1.1e-3); the same
+        # rule as the full-frame ADI+mSDI tests (a multiple of max|cube|), ten times tighter
+        tol = 5e-7 * float(np.max(np.abs(cube)))
+        assert np.max(np.abs(r[0] - o[0])) < tol, (ncomp, kw)
+        m = ~np.isnan(o[2])
+        assert np.array_equal(np.isnan(r[2]), ~m) and np.max(np.abs(r[2][m] - o[2][m])) < tol, (ncomp, kw)
+    fr = vb.pca_annular(cube, angs, scale_list=sl, ncomp=(1, None), fwhm=3, asize=6, delta_sep=0.1, verbose=False)
+    assert fr.shape == cube.shape[2:]
+    with pytest.raises(TypeError):
+        vb.pca_annular(cube, angs, scale_list=sl, ncomp=2, fwhm=3, verbose=False)
+    with pytest.raises(ValueError):
+        vb.pca_annular(cube, angs, scale_list=sl[:-1], ncomp=(1, 1), fwhm=3, verbose=False)
+    with pytest.raises(RuntimeError):                      # no channel moved by 50 FWHM
+        vb.pca_annular(cube, angs, scale_list=sl, ncomp=(1, 1), fwhm=3, delta_sep=50.0, verbose=False)
+
+
+def test_pca_annular_ncomp_auto_vs_oracle(vb):
+    """``pca_annular(ncomp='auto')``: the noise-decay rule evaluated from Gramian eigenpairs + library row sums (what
+    the kernel sees) picks the same number of components per patch as the reference's rule on the residual matrix
+    (oracle pinned bit-identically: ``test_pca_annular_ncomp_auto_bit_identical``)."""
+    cube, angs = adi_cube(24, 40, 4, 80.0, seed=5)
+    for kw in (dict(ncomp="auto", tol=0.1, asize=5, delta_rot=(0.1, 0.4)),
+               dict(ncomp="auto", tol=0.5, asize=6, n_segments=2, delta_rot=0.3),
+               dict(ncomp="auto", tol=0.02, asize=5, delta_rot=0.2),
+               dict(ncomp=("auto", 2, "auto", 1), tol=0.1, asize=5, delta_rot=0.2),
+               dict(ncomp="auto", tol=0.1, asize=5, delta_rot=0)):
+        # the rule picks 6 ... 24 components here: with that many the reference's fp32 arithmetic is itself
+        # 1.2e-4 ... 3e-4 away from its own float64 evaluation, so the 1e-4 bound is taken against the float64 run
+        # (measured 1e-5 ... 5e-5) and the fp32 run bounds the distance the reference's own rounding allows
+        used32, used64 = [], []
+        o = O.pca_annular(cube, angs, full_output=True, ncomp_out=used32, **kw)
+        o64 = O.pca_annular(cube.astype(np.float64), angs, full_output=True, ncomp_out=used64, **kw)
+        assert used32 == used64                     # the choice itself is not borderline on these cases
+        r = vb.pca_annular(cube, angs, full_output=True, verbose=False, **kw)
+        scale = np.max(np.abs(o64[0]))
+        assert np.max(np.abs(r[0] - o64[0])) < 1e-4 * scale, kw
+        assert np.max(np.abs(r[0] - o[0])) < 5e-4 * scale, kw
+        assert rel_err(r[2], o64[2]) < 3e-4, kw

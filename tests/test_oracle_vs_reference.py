@@ -146,3 +146,20 @@ def test_pca_annular_adimsdi_bit_identical(ref):
         assert len(r) == len(o) == 3
         for a, b in zip(r, o):
             np.testing.assert_array_equal(a, b)
+
+
+def test_pca_annular_ncomp_auto_bit_identical(ref):
+    """``pca_annular(ncomp='auto', tol=)``: the noise-decay rule of ``get_eigenvectors`` (``psfsub/svd.py:622-672``)
+    through ``do_pca_patch``, for two tolerances (different numbers of components per patch) and a tuple mixing
+    'auto' with fixed numbers."""
+    psfsub, _ = ref
+    cube, angs = adi_cube(24, 40, 4, 80.0, seed=5)
+    for kw in (dict(ncomp="auto", tol=0.1, asize=5, delta_rot=(0.1, 0.4)),
+               dict(ncomp="auto", tol=0.5, asize=6, n_segments=2, delta_rot=0.3),
+               dict(ncomp="auto", tol=0.02, asize=5, delta_rot=0.2)):
+        r = psfsub.pca_annular(cube, angs, verbose=False, full_output=True, nproc=1, **kw)
+        used = []
+        o = O.pca_annular(cube, angs, full_output=True, ncomp_out=used, **kw)
+        for a, b in zip(r, o):
+            np.testing.assert_array_equal(a, b)
+        assert len(set(used)) > 1 or kw["tol"] == 0.5, (kw, sorted(set(used)))

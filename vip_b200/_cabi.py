@@ -43,6 +43,7 @@ SIGNATURES = {
     "vb_collapse_f32": (_i, [_vp, _i, _sz, _i, _vp, _i, _i, _vp, _vp]),
     "vb_annular_weights_f64": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _d, _i, _vp, _vp, _vp]),
     "vb_annular_direct_f64": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "vb_annular_auto_f64": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _d, _d, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "vb_gather_columns_f32": (_i, [_vp, _i, _sz, _vp, _i, _vp, _vp]),
     "vb_scatter_columns_f32": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp]),
     "vb_gemm_f32": (_i, [_vp, C.c_longlong, C.c_longlong, _i, _vp, C.c_longlong, C.c_longlong, _i, _i, _vp,

@@ -39,6 +39,12 @@ struct AnnularArgs {
     int max_iter;
     float* W;               // (nprob, n) output weights, row q = problem q; must be zero-initialised
     int* iters;             // (nprob) iterations used (negative: not converged)
+    // ncomp='auto' (direct solver only; get_eigenvectors, psfsub/svd.py:640-672): when rowsum != nullptr the number
+    // of components of problem q is chosen by the reference's noise-decay rule among the ncomp computed eigenpairs
+    const double* rowsum = nullptr;   // (n) sum over the pixels of every library row
+    double npx = 0.0;                 // pixels per row
+    double noise_tol = 0.0;           // `tol` of pca_annular
+    int* ncomp_out = nullptr;         // (nprob) chosen number of components; negative: the rule wanted more than ncomp
 };
 
 // symmetric B x B eigenproblem in shared memory: one-sided Jacobi on the columns of Tm (PSD).
@@ -632,13 +638,63 @@ annular_direct_kernel(AnnularArgs p, const int* __restrict__ plist, double* __re
     }
     __syncthreads();
 
+    // ---- ncomp='auto': noise-decay rule of get_eigenvectors (svd.py:640-672) on the library itself.
+    // Residual of the library D (L x npx) after m components = sum_{i>m} sigma_i u_i v_i^T, so
+    //   mean(res^2) = (trace(G_II) - sum_{i<=m} lambda_i) / (L npx),
+    //   mean(res)   = (sum_i r_i - sum_{i<=m} (1.x_i)(x_i.r)) / (L npx)      with r = D 1 (row sums),
+    // and np.std(res) = sqrt(mean(res^2) - mean(res)^2): only the leading eigenpairs are needed.
+    int kuse = k;
+    if (p.rowsum != nullptr) {
+        double* ca = blo;                 // 1 . x_r
+        double* cb = bhi;                 // x_r . r
+        if (tid < 32) { ca[tid] = 0.0; cb[tid] = 0.0; }
+        __syncthreads();
+        const double rs = (tid < L) ? __ldg(p.rowsum + Is[tid]) : 0.0;
+        for (int r = 0; r < k; ++r) {
+            const double z = (tid < L) ? Z[(size_t)r * Lmax + tid] : 0.0;
+            const double va = warp_sum(z), vb2 = warp_sum(z * rs);
+            if (lane == 0) { atomicAdd(&ca[r], va); atomicAdd(&cb[r], vb2); }
+        }
+        const double srs = block_sum_256(rs, red);
+        __syncthreads();
+        if (tid == 0) {
+            double trace = 0.0;
+            for (int i = 0; i < L; ++i) trace += d[i];
+            const double tot = (double)L * p.npx;
+            const int max_evs = ((double)L < p.npx) ? L : (int)p.npx;
+            double s2 = trace, sr = srs, prev = 0.0, decay = 1.0;
+            int m = 0, clipped = 0;
+            while (decay >= p.noise_tol) {
+                ++m;
+                if (m <= max_evs) {
+                    if (m > k) { clipped = 1; break; }         // the rule wants more eigenpairs than were computed
+                    s2 -= lam[m - 1];
+                    sr -= ca[m - 1] * cb[m - 1];
+                }
+                const double mean = sr / tot;
+                const double var = s2 / tot - mean * mean;
+                const double noise = (var > 0.0) ? sqrt(var) : 0.0;
+                if (m > 1) decay = prev - noise;
+                prev = noise;
+                if (m > max_evs + 1) break;                     // tol <= 0: the reference would not terminate
+            }
+            if (m > max_evs) m = max_evs;                       // V_big[:ncomp] holds max_evs rows at most
+            if (clipped) m = k;
+            reinterpret_cast<int*>(scal)[0] = m;
+            p.ncomp_out[q] = clipped ? -m : m;
+        }
+        __syncthreads();
+        kuse = reinterpret_cast<int*>(scal)[0];
+        __syncthreads();
+    }
+
     // ---- weights  w = sum_r x_r (x_r . g) / lam_r
     double* coef = blo;                   // (bisection intervals are no longer needed)
     if (tid < 32) coef[tid] = 0.0;
     __syncthreads();
     {
         const double g = (tid < L) ? __ldg(p.Gt + (size_t)f * n + Is[tid]) : 0.0;
-        for (int r = 0; r < k; ++r) {
+        for (int r = 0; r < kuse; ++r) {
             const double v = warp_sum((tid < L) ? Z[(size_t)r * Lmax + tid] * g : 0.0);
             if (lane == 0) atomicAdd(&coef[r], v);
         }
@@ -646,7 +702,7 @@ annular_direct_kernel(AnnularArgs p, const int* __restrict__ plist, double* __re
     __syncthreads();
     if (tid < L) {
         double w = 0.0;
-        for (int r = 0; r < k; ++r)
+        for (int r = 0; r < kuse; ++r)
             if (lam[r] > 0.0) w = fma(Z[(size_t)r * Lmax + tid], coef[r] / lam[r], w);
         p.W[(size_t)q * n + Is[tid]] = (float)w;
     }
@@ -664,6 +720,20 @@ int annular_direct_weights(const double* G, const double* Gt, int n, const int* 
                            int* iters, double* ws, cudaStream_t st) {
     VB_REQUIRE(nlist > 0 && nlist <= nprob, "annular_direct: bad problem list");
     AnnularArgs a{G, Gt ? Gt : G, n, idx, len, frame, Lmax, ncomp, 0.0, 0, W, iters};
+    return annular_direct(a, plist, nlist, ws, st);
+}
+
+// ncomp='auto': every listed problem solved directly with `kmax` eigenpairs, the number used chosen per problem by
+// the noise-decay rule (see the kernel).  ncomp_out[q] < 0: the rule asked for more than kmax components.
+int annular_auto_weights(const double* G, const double* Gt, int n, const int* idx, const int* len, const int* frame,
+                         int nprob, int Lmax, int kmax, const double* rowsum, double npx, double noise_tol,
+                         const int* plist, int nlist, float* W, int* iters, int* ncomp_out, double* ws,
+                         cudaStream_t st) {
+    VB_REQUIRE(nlist > 0 && nlist <= nprob, "annular_auto: bad problem list");
+    VB_REQUIRE(rowsum != nullptr && ncomp_out != nullptr && npx >= 1.0, "annular_auto: missing row sums");
+    VB_REQUIRE(noise_tol > 0.0, "annular_auto: `tol` must be positive");
+    AnnularArgs a{G, Gt ? Gt : G, n, idx, len, frame, Lmax, kmax, 0.0, 0, W, iters};
+    a.rowsum = rowsum; a.npx = npx; a.noise_tol = noise_tol; a.ncomp_out = ncomp_out;
     return annular_direct(a, plist, nlist, ws, st);
 }
 

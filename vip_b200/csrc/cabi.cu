@@ -58,6 +58,8 @@ struct GemmArgs {
 int gemm_f32(const GemmArgs&, int, int, cudaStream_t);
 int annular_weights(const double*, const double*, int, const int*, const int*, const int*, int, int, int, double,
                     int, float*, int*, cudaStream_t);
+int annular_auto_weights(const double*, const double*, int, const int*, const int*, const int*, int, int, int,
+                         const double*, double, double, const int*, int, float*, int*, int*, double*, cudaStream_t);
 int annular_direct_weights(const double*, const double*, int, const int*, const int*, const int*, int, int, int,
                            const int*, int, float*, int*, double*, cudaStream_t);
 int gather_columns(const float*, int, size_t, const int*, int, float*, cudaStream_t);
@@ -304,6 +306,15 @@ int vb_annular_direct_f64(const double* G, const double* Gt, int n, const int* i
     g_launches += 1;
     return annular_direct_weights(G, Gt, n, idx, len, frame, nprob, Lmax, ncomp, plist, nlist, W, iters, ws,
                                   (cudaStream_t)stream);
+}
+
+int vb_annular_auto_f64(const double* G, const double* Gt, int n, const int* idx, const int* len,
+                        const int* frame, int nprob, int Lmax, int kmax, const double* rowsum, double npx,
+                        double noise_tol, const int* plist, int nlist, float* W, int* iters, int* ncomp_out,
+                        double* ws, void* stream) {
+    g_launches += 1;
+    return annular_auto_weights(G, Gt, n, idx, len, frame, nprob, Lmax, kmax, rowsum, npx, noise_tol, plist, nlist, W,
+                                iters, ncomp_out, ws, (cudaStream_t)stream);
 }
 
 int vb_gather_columns_f32(const float* src, int n, size_t p, const int* cols, int npx, float* dst, void* stream) {

@@ -303,6 +303,31 @@ def annular_weights(G, idx, lens, frames, ncomp, tol=0.0, max_iter=40, direct_fa
     return W, iters
 
 
+def annular_weights_auto(G, idx, lens, frames, rowsum, npx, noise_tol, kmax=24):
+    """``annular_weights`` with the number of components of every problem chosen by the reference's noise-decay rule
+    (``get_eigenvectors(ncomp='auto')``, ``psfsub/svd.py:622-672``) among ``kmax`` eigenpairs (direct solver).
+    ``rowsum`` (nlib,) fp64 = sum over the pixels of every row of the library matrix, ``npx`` its width.
+    Returns (W (nprob,nlib) fp32, ncomp (nprob,) int32; negative = clipped at kmax)."""
+    lib = _cabi.lib()
+    n = G.shape[0]
+    nprob, Lmax = idx.shape
+    dev = G.device
+    W = torch.zeros((nprob, n), dtype=torch.float32, device=dev)
+    iters = torch.zeros((nprob,), dtype=torch.int32, device=dev)
+    ncomp = torch.zeros((nprob,), dtype=torch.int32, device=dev)
+    rowsum = rowsum.to(torch.float64).contiguous()
+    todo = torch.arange(nprob, dtype=torch.int32, device=dev)
+    chunk = max(1, min(1024, (1 << 30) // (Lmax * Lmax * 8)))
+    for s in range(0, nprob, chunk):
+        part = todo[s:s + chunk].contiguous()
+        ws = torch.empty(part.numel() * Lmax * Lmax, dtype=torch.float64, device=dev)
+        _cabi.check(lib.vb_annular_auto_f64(ptr(G), 0, n, ptr(idx), ptr(lens), ptr(frames), nprob, Lmax, int(kmax),
+                                            ptr(rowsum), float(npx), float(noise_tol), ptr(part), part.numel(),
+                                            ptr(W), ptr(iters), ptr(ncomp), ptr(ws), stream_ptr()),
+                    "vb_annular_auto_f64")
+    return W, ncomp
+
+
 def upload_columns(host2d, c0, c1, device):
     """Columns [c0, c1) of a C-contiguous fp32 host matrix -> contiguous (n, c1-c0) CUDA tensor (one 2-D DMA)."""
     lib = _cabi.lib()

@@ -143,14 +143,17 @@ def library_indices(angle_list, pa_thr, max_frames):
 
 
 def _segment_residuals(A, A_lib, angle_list, pa_thr, ncomp, min_frames_lib, max_frames_lib, A_ref=None,
-                       lists=None):
+                       lists=None, tol=1e-1):
     """Residuals of every frame of one segment matrix ``A`` (n,npx) on the device.
 
     ``A_lib`` = matrix the libraries are drawn from (A, or A - A_sig); ``A_ref`` = optional RDI rows
     stacked in front of every library (``pca_local.py:880-885``)."""
     n, npx = A.shape
     dev = A.device
-    if pa_thr == 0:
+    auto = isinstance(ncomp, str)
+    if auto and pa_thr == 0:
+        lists = [np.arange(n, dtype=np.int32)] * n          # every frame: the whole segment matrix as library
+    if pa_thr == 0 and not auto:
         # every frame uses the whole segment matrix as library: one decomposition (pca_local.py:874-878)
         lib = A_lib if A_ref is None else torch.cat((A_ref, A_lib))
         k = min(ncomp, min(lib.shape))
@@ -181,6 +184,22 @@ def _segment_residuals(A, A_lib, angle_list, pa_thr, ncomp, min_frames_lib, max_
             idx_host[f, :nref] = np.arange(nref)
         idx_host[f, nref:L] = idx + nref
     lib = A_lib if A_ref is None else torch.cat((A_ref, A_lib))
+    if auto:
+        # ncomp='auto' (get_eigenvectors, svd.py:622-672): per frame, components are added until the pixel noise of
+        # the library residuals decays by less than `tol`; evaluated inside the direct eigen-kernel from the
+        # eigenpairs of the library Gramian and the row sums of the library matrix
+        G = kernels.gram(lib)
+        t0 = _tick("gram", t0)
+        W, used = kernels.annular_weights_auto(
+            G, torch.from_numpy(idx_host).to(dev), torch.from_numpy(lens).to(dev),
+            torch.arange(nref, nref + n, dtype=torch.int32, device=dev), lib.double().sum(dim=1), npx, float(tol))
+        if bool((used < 0).any()):
+            _unsupported("ncomp='auto' choosing more than 24 principal components (decrease `tol`-sensitivity: "
+                         "the noise-decay rule did not stop within 24 components)")
+        t0 = _tick("weights (batched eigenproblems, auto)", t0)
+        R = A.clone()
+        kernels.gemm(W.unsqueeze(0), lib.unsqueeze(0), R.unsqueeze(0), alpha=-1.0, beta=1.0)
+        return R, used
     k = min(ncomp, npx)                      # get_eigenvectors clamps to min(shape) (svd.py:694)
     if k > 24:
         _unsupported("more than 24 principal components per annulus")
@@ -252,8 +271,8 @@ def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segme
         if full_output:
             return cube_out, cube_der, frames
         return frames
-    if isinstance(ncomp, str):
-        _unsupported("ncomp='auto'")
+    if isinstance(ncomp, str) and ncomp != "auto":
+        raise TypeError("`ncomp` must be an int, a tuple/array of ints, a list or 'auto'")
     if left_eigv:
         _unsupported("`left_eigv`")
     _check_rot_options(imlib, rot_options.get("cxy"), rot_options.get("border_mode", "constant"),
@@ -261,7 +280,10 @@ def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segme
 
     t0 = time.perf_counter()
     dev = require_cuda()
-    cube_dev = to_device_f32(array, dev).reshape(n, y * x)
+    if isinstance(array, torch.Tensor):              # stage-1 output of the ADI+mSDI branch: already on the device
+        cube_dev = array.to(torch.float32).contiguous().reshape(n, y * x)
+    else:
+        cube_dev = to_device_f32(array, dev).reshape(n, y * x)
     ref_dev = to_device_f32(cube_ref, dev).reshape(cube_ref.shape[0], y * x) if cube_ref is not None else None
     sig_dev = to_device_f32(cube_sig, dev).reshape(n, y * x) if cube_sig is not None else None
     cube_out = torch.zeros_like(cube_dev)
@@ -281,7 +303,7 @@ def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segme
         if isinstance(ncomp, (tuple, np.ndarray)):
             if len(ncomp) != n_annuli:
                 raise TypeError("If `ncomp` is a tuple, its length must match the number of annuli")
-            ncompann = int(ncomp[ann])
+            ncompann = ncomp[ann] if isinstance(ncomp[ann], str) else int(ncomp[ann])
         else:
             ncompann = ncomp
         pa_thr, inner_radius, _ = _define_annuli(angle_list, ann, n_annuli, fwhm, radius_int, asize,
@@ -296,7 +318,7 @@ def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segme
                      if ref_dev is not None else None)
             A_lib = A - kernels.gather_columns(sig_dev, cols) if sig_dev is not None else A
             R, _ = _segment_residuals(A, A_lib, angle_list, pa_thr, ncompann, min_frames_lib,
-                                      max_frames_lib, A_ref, lists=all_lists[ann])
+                                      max_frames_lib, A_ref, lists=all_lists[ann], tol=tol)
             kernels.scatter_columns(R, cols, cube_out)
         if verbose == 1:
             print("Done PCA with {} for current annulus".format(_mode_name(svd_mode)))
@@ -316,6 +338,159 @@ def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segme
     if full_output:
         return cube_out, cube_der, frame
     return frame
+
+
+def _sdi_library_indices(scal, ann_center, fwhm, delta_sep):
+    """``_find_indices_sdi(scal, ann_center, j, fwhm, delta_sep)`` for every channel j (``rescaling.py:916-988``)."""
+    from ..preproc.rescaling import _find_indices_sdi
+    return [np.asarray(_find_indices_sdi(scal, ann_center, j, fwhm, delta_sep), dtype=np.int32)
+            for j in range(len(scal))]
+
+
+def _pca_sdi_frames_device(cube_dev, scal, radius_int, fwhm, asize, n_segments, delta_sep, ncomp, svd_mode,
+                           scaling, collapse_ifs, ifs_collapse_range, theta_init):
+    """``_pca_sdi_fr`` (``pca_local.py:470-591``) for ALL ADI frames of a (z, n, H, W) device cube -> (n, H, W).
+
+    Per multi-spectral frame the reference rescales the z channels, then per annular segment and per channel j runs a
+    PCA of channel j against the channels that moved radially by at least ``delta_sep`` FWHM
+    (``_find_indices_sdi``).  The channel libraries depend on the annulus only, not on the ADI frame: the segment
+    matrices of a group of ADI frames are stacked ((F z) x npx), ONE Gramian serves the group (its diagonal z x z
+    blocks are the per-frame Gramians), the batched eigen-kernel solves the F z library problems on index lists
+    offset into the blocks, and one GEMM applies the weights."""
+    from ..preproc.rescaling import check_scal_vector
+    from .sdi import RescaleOps, _CHUNK_BYTES
+    z, n, H, W = cube_dev.shape
+    dev = cube_dev.device
+    if H != W:
+        raise ValueError("FFT scaling only supports square input arrays")
+    scal = np.asarray(scal)
+    scale_list = check_scal_vector(scal)
+    ops = RescaleOps(scale_list, H, dev)
+    S = ops.big
+    fwhm = int(np.round(np.mean(fwhm)))
+    n_annuli = int((H / 2 - radius_int) / asize)
+    if isinstance(n_segments, int):
+        n_segments = [n_segments for _ in range(n_annuli)]
+    elif isinstance(n_segments, str) and n_segments == "auto":
+        n_segments = [2, 3]
+        ld = 2 * np.tan(360 / 4 / 2) * asize
+        for i in range(2, n_annuli):
+            ang = np.rad2deg(2 * np.arctan(ld / (2 * i * asize)))
+            n_segments.append(int(np.ceil(360 / ang)))
+    if isinstance(delta_sep, (tuple, list)):
+        delta_sep_vec = np.linspace(delta_sep[0], delta_sep[1], n_annuli)
+    elif np.isscalar(delta_sep):
+        delta_sep_vec = [delta_sep] * n_annuli
+    else:
+        if len(delta_sep) != n_annuli:
+            raise TypeError("If delta_sep is a list it should have n_annuli elements.")
+        delta_sep_vec = delta_sep
+    if _mode_name(svd_mode) not in _EXACT_MODES:
+        _unsupported(f"svd_mode={_mode_name(svd_mode)!r}")
+    if isinstance(ncomp, str):
+        _unsupported("ncomp='auto' in the spectral pass")
+    if min(int(ncomp), z) > 24:
+        _unsupported("more than 24 principal components per annulus")
+    i0, i1 = (0, z) if ifs_collapse_range == "all" else (int(ifs_collapse_range[0]), int(ifs_collapse_range[1]))
+
+    # geometry and channel libraries of every segment (host integer logic, shared by all ADI frames)
+    plan = []
+    for ann in range(n_annuli):
+        inner_radius = radius_int + (ann * asize - 1) if ann == n_annuli - 1 else radius_int + ann * asize
+        ann_center = inner_radius + (asize / 2)
+        lists = _sdi_library_indices(scal, ann_center, fwhm, delta_sep_vec[ann])
+        for yy, xx in get_annulus_segments((S, S), inner_radius, asize, n_segments[ann], theta_init):
+            if yy.size:
+                plan.append((torch.from_numpy((yy * S + xx).astype(np.int32)).to(dev), lists))
+
+    group = max(1, 256 // z)                                   # ADI frames per Gramian: (group z) <= 256 rows
+    per_frame = 4 * z * S * S * 4 * 2
+    chunk = max(1, min(n, int(_CHUNK_BYTES // per_frame)))
+    out = torch.empty((n, ops.out, ops.out), dtype=torch.float32, device=dev)
+    for f0 in range(0, n, chunk):
+        f1 = min(n, f0 + chunk)
+        F = f1 - f0
+        ms = cube_dev[:, f0:f1].permute(1, 0, 2, 3).contiguous()               # (F, z, H, W)
+        if ops.pad:
+            ms = torch.nn.functional.pad(ms, (ops.pad,) * 4, mode="reflect")
+        resc = RescaleOps.apply(ms.reshape(F * z, S, S), ops.Wf, z).reshape(F * z, S * S)
+        res = torch.zeros_like(resc)
+        for cols, lists in plan:
+            npx = cols.numel()
+            A = kernels.gather_columns(resc, cols)                              # (F z, npx)
+            if scaling is not None:
+                A = torch.cat([scale_matrix_device(A[f * z:(f + 1) * z], scaling) for f in range(F)])
+            Lmax = max(len(l) for l in lists)
+            k = min(int(ncomp), npx)
+            for g0 in range(0, F, group):
+                g1 = min(F, g0 + group)
+                Fg = g1 - g0
+                Ag = A[g0 * z:g1 * z]
+                idx_host = np.zeros((Fg * z, Lmax), dtype=np.int32)
+                lens = np.zeros(Fg * z, dtype=np.int32)
+                for f in range(Fg):
+                    for j, l in enumerate(lists):
+                        idx_host[f * z + j, :len(l)] = l + f * z
+                        lens[f * z + j] = len(l)
+                G = kernels.gram(Ag)
+                Wt, iters = kernels.annular_weights(
+                    G, torch.from_numpy(idx_host).to(dev), torch.from_numpy(lens).to(dev),
+                    torch.arange(Fg * z, dtype=torch.int32, device=dev), k)
+                if bool((iters < 0).any()):
+                    raise RuntimeError("vip_b200.pca_annular: spectral eigenproblems did not converge")
+                R = Ag.clone()
+                kernels.gemm(Wt.unsqueeze(0), Ag.unsqueeze(0), R.unsqueeze(0), alpha=-1.0, beta=1.0)
+                kernels.scatter_columns(R, cols, res[g0 * z:g1 * z])
+        desc = RescaleOps.apply(res.reshape(F * z, S, S), ops.Wi, z).reshape(F, z, ops.out, ops.out)
+        for f in range(F):
+            out[f0 + f] = collapse_device(desc[f, i0:i1], collapse_ifs).float()
+    return out
+
+
+def _pca_annular_adimsdi(p, rot_options):
+    """ADI+mSDI branch of ``pca_annular`` (``pca_local.py:332-462``): spectral pass per ADI frame with ``ncomp[0]``,
+    then the annular ADI pass with ``ncomp[1]`` (or derotation + collapse only when it is None)."""
+    cube = p.cube
+    z, n, y_in, x_in = cube.shape
+    fwhm = int(np.round(np.mean(p.fwhm)))
+    scale_list = np.asarray(p.scale_list)
+    if scale_list.ndim > 1:
+        raise ValueError("Scaling factors vector is not 1d")
+    if not scale_list.shape[0] == z:
+        raise ValueError("Scaling factors vector has wrong length")
+    if not isinstance(p.ncomp, tuple):
+        raise TypeError("`ncomp` must be a tuple of two integers when `cube` is a 4d array")
+    ncomp1, ncomp2 = p.ncomp[0], p.ncomp[1]
+    if p.cube_ref is not None and ncomp2 is not None:
+        _unsupported("`cube_ref` with a 4-d cube and `scale_list`")
+    _check_rot_options(p.imlib, rot_options.get("cxy"), rot_options.get("border_mode", "constant"),
+                       rot_options.get("edge_blend"), cube.shape[1:])
+    dev = require_cuda()
+    cube_dev = to_device_f32(cube, dev)
+    if p.verbose:
+        print("First PCA subtraction exploiting the spectral variability")
+        print("{} spectral channels per IFS frame".format(z))
+        print("N annuli = {}, mean FWHM = {:.3f}".format(int((y_in / 2 - p.radius_int) / p.asize), fwhm))
+    res_channels = _pca_sdi_frames_device(cube_dev, scale_list, p.radius_int, fwhm, p.asize, p.n_segments,
+                                          p.delta_sep, ncomp1, p.svd_mode, p.scaling, p.collapse_ifs,
+                                          p.ifs_collapse_range, p.theta_init)
+    del cube_dev
+    angle_list = np.asarray(p.angle_list)
+    if ncomp2 is None:
+        if p.verbose:
+            print("Skipping the second PCA subtraction")
+        mask_val = float(rot_options.get("mask_val", np.nan))
+        interp_zeros = bool(rot_options.get("interp_zeros", False))
+        cube_out = res_channels
+        # the reference passes the angles as they are here (no check_pa_vector; cube_derotate negates)
+        cube_der = derotate_device(cube_out, -angle_list, mask_val=mask_val, interp_zeros=interp_zeros)
+        frame = collapse_device(cube_der, mode=p.collapse, w=p.weights)
+        return cube_out, cube_der, frame
+    if p.verbose:
+        print("Second PCA subtraction exploiting angular variability")
+    func_params = setup_parameters(params_obj=p, fkt=_pca_adi_rdi_device, cube=res_channels, ncomp=ncomp2,
+                                   fwhm=fwhm, cube_ref=None, full_output=True)
+    return _pca_adi_rdi_device(**func_params, **rot_options)
 
 
 def pca_annular(*all_args: List, **all_kwargs: dict):
@@ -344,8 +519,6 @@ def pca_annular(*all_args: List, **all_kwargs: dict):
 
     if not isinstance(p.cube, np.ndarray):
         raise TypeError("Input array is not a cube or 3d array")
-    if p.cube.ndim == 4 and p.scale_list is not None:
-        _unsupported("4-d input with `scale_list` (annular ADI+mSDI)")
     if p.cube.ndim not in (3, 4):
         raise TypeError("Input array is not a 4d or 3d array")
     dt = p.cube.dtype
@@ -355,6 +528,12 @@ def pca_annular(*all_args: List, **all_kwargs: dict):
         if a.dtype == np.float32 and dt != np.float32 and np.issubdtype(dt, np.floating):
             a = a.astype(dt)
         return a
+
+    if p.cube.ndim == 4 and p.scale_list is not None:
+        cube_out, cube_der, frame = _pca_annular_adimsdi(p, rot_options)
+        if p.full_output:
+            return host(cube_out), host(cube_der), host(frame)
+        return host(frame)
 
     if p.cube.ndim == 4:
         # 4-d cube without mSDI: annular ADI/RDI per spectral channel, channel frames combined with
