@@ -236,6 +236,48 @@ def test_collapse_median_both_kernels_and_tiles(vb, monkeypatch, algo, cfg):
     np.testing.assert_array_equal(vb.cube_collapse(cube[:-1], "median"), ref_even)
 
 
+@pytest.mark.parametrize("n", [64, 65, 96, 127, 128, 129, 255, 256, 257, 500, 512, 513, 1000, 1024])
+def test_collapse_median_warp_kernel(vb, n):
+    """The warp-per-pixel bracket-search median (default for 64 <= n <= 1024; keys in registers, sample-guided
+    pivots, exact counts -- ``tools/median_bracket_model.py`` is the same logic in numpy): every register-tile width
+    and both pixel tiles, ragged frame counts, and the columns that stress the search -- NaN-ragged, all ties, all NaN,
+    signed zeros, 1e30 range, one valid sample, a few ulps around 1, denormals, two alternating huge values, +-inf,
+    60 % exact zeros, integer-valued data (ties beyond the 32-key finish), a sorted column, NaNs in the 32 sampled
+    frames: bit-exact vs numpy for odd and even counts."""
+    rng = np.random.default_rng(n)
+    cube = rng.normal(size=(n, 13, 35)).astype(np.float32)       # 455 pixels: ragged last tile, p % 4 != 0
+    cube[rng.uniform(size=cube.shape) < 0.03] = np.nan
+    cube[:, 0, 0] = 3.5
+    cube[:, 1, 1] = np.nan
+    cube[:, 2, 2] = np.round(cube[:, 2, 2])
+    cube[: n // 2, 3, 3] = -0.0
+    cube[n // 2:, 3, 3] = 0.0
+    cube[:, 0, 1] *= 1e30
+    cube[1:, 0, 2] = np.nan
+    cube[:, 4, 4] = 1.0 + 1e-6 * rng.normal(size=n).astype(np.float32)
+    cube[:, 5, 5] = (1e-41 * rng.normal(size=n)).astype(np.float32)
+    cube[:, 6, 6] = np.where(np.arange(n) % 2 == 0, np.float32(-1e38), np.float32(1e38))
+    cube[:, 7, 7] = np.inf
+    cube[::3, 7, 8] = -np.inf
+    cube[:, 8, 8] = np.where(rng.uniform(size=n) < 0.6, 0.0, cube[:, 8, 8])
+    cube[:, 9, 9] = np.round(3 * rng.normal(size=n))
+    cube[:, 10, 10] = np.sort(rng.normal(size=n)).astype(np.float32)
+    cube[:32, 11, 11] = np.nan
+    cube[:, 12, 12] = np.sort(rng.normal(size=n))[::-1].astype(np.float32)
+    cube[:, 12, 13] = np.where(np.arange(n) < 40, 1e20, 1.0)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = np.nanmedian(cube, axis=0)
+        ref_even = np.nanmedian(cube[:-1], axis=0)
+    np.testing.assert_array_equal(vb.cube_collapse(cube, "median"), ref)
+    if n > 64:
+        np.testing.assert_array_equal(vb.cube_collapse(cube[:-1], "median"), ref_even)
+    # a frame-sized cube with smooth statistics (the production case): 64 x 128 pixels
+    cube = (rng.normal(size=(n, 64, 128)) * rng.uniform(0.1, 30, size=(1, 64, 128))).astype(np.float32)
+    np.testing.assert_array_equal(vb.cube_collapse(cube, "median"), np.median(cube, axis=0))
+
+
 def test_collapse_4d(vb):
     rng = np.random.default_rng(0)
     cube = rng.normal(size=(3, 11, 8, 8)).astype(np.float32)

@@ -12,6 +12,7 @@
 // (selection is exact; the mean of the two middle values is a single fp32 add and halving).
 #include "common.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace vb {
 
@@ -20,8 +21,9 @@ enum CollapseMode { kMedian = 0, kMean = 1, kSum = 2, kMax = 3, kAbsMean = 4, kW
 constexpr int CT = 128;  // threads per CTA
 
 __device__ __forceinline__ unsigned int f2key(float v) {
+    // negative: ~u, positive: u | 0x80000000 -- as one shift and one three-input logic op
     const unsigned int u = __float_as_uint(v);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return u ^ ((unsigned int)((int)u >> 31) | 0x80000000u);
 }
 __device__ __forceinline__ float key2f(unsigned int k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
@@ -410,6 +412,216 @@ collapse_median_range_kernel(const float* __restrict__ cube, int n, size_t p, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-per-pixel median (round 2, default for 64 <= n <= 1024): keys of a pixel live in REGISTERS.
+// The radix kernels above spend ~100 instructions per sample (ncu r01l/r02k: issue-bound, 14 % of the HBM rate):
+// every 4-bit pass re-reads the surviving keys from shared memory, updates 16-bit histogram cells with
+// read-modify-write sequences and merges 16 bins over the lanes, and the leading key bits (sign, high exponent) hardly
+// discriminate, so about three passes touch every key.  Here a warp owns one pixel: lane l holds frames l, l + 32, ...
+// (KPL registers), read once from the shared-memory tile, and the two middle ranks are BRACKETED by counting:
+//   * a 32-key sample (one per lane) is sorted across the warp (bitonic, shuffles); its median is the first pivot and
+//     its order statistics guide the next ones: idx += (r - c) * 32 / m, overshooting by 1..3 sample ranks so that
+//     the target gets bracketed from both sides;
+//   * a pass counts the keys below the pivot (compare + predicated add per key, one REDUX for the warp) and moves the
+//     lower or the upper end of the bracket [lo, hi) -- counts (clo, chi) are exact, so the search never loses the
+//     ranks; once both ends come from counts the pivot is interpolated between them in VALUE space;
+//   * when at most 32 keys are left inside the bracket they are compacted (ballot + popc) into one key per lane,
+//     sorted, and ranks r1 - clo, r2 - clo are read off with a shuffle;
+//   * exactness does not depend on the guesses: every pivot lies strictly inside (lo, hi) so the bracket shrinks on
+//     every pass, every third pass after the sixth halves it in KEY space (<= 32 such passes to one key), heavy ties
+//     end at hi - lo == 1 or at the first pass (which also counts keys <= pivot when the sample has ties).
+// Pass counts of this logic on 500-sample columns (tools/median_bracket_model.py, the same code in numpy checked bit
+// for bit against np.nanmedian): 3.4 on Gaussian / heavy-tailed / outlier-ridden data, 2 with 60 % zeros.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int warp_sort32(unsigned int v, int lane) {
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+            const unsigned int o = __shfl_xor_sync(0xffffffffu, v, jj);
+            const bool keep_min = ((lane & jj) == 0) == ((lane & kk) == 0);
+            v = keep_min ? min(v, o) : max(v, o);
+        }
+    }
+    return v;
+}
+
+// c += (k < pv) as compare + predicated add (what the loop is meant to cost: ncu r02z showed the C++ form compiled to
+// 4.75 instructions per key -- the compiler also packed every compare result into a bit mask for later reuse)
+__device__ __forceinline__ void count_below(unsigned int& c, unsigned int k, unsigned int pv) {
+    asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %1, %2;\n\t@q add.u32 %0, %0, 1;\n\t}" : "+r"(c) : "r"(k), "r"(pv));
+}
+
+template <int KPL, int PXT>
+__global__ void __launch_bounds__(256, (KPL <= 16) ? 3 : 2)
+collapse_median_warp_kernel(const float* __restrict__ cube, int n, size_t p, float* __restrict__ out) {
+    constexpr int STRIDE = PXT + 1, ROWS = KPL * 32, Q = PXT / 4, RSTEP = 256 / Q;
+    constexpr unsigned int PAD = 0xffffffffu, FULL = 0xffffffffu;
+    extern __shared__ unsigned int smem_keys[];
+    unsigned int* K = smem_keys;                                       // [ROWS][STRIDE], rows >= n hold PAD
+    unsigned int* cand_all = smem_keys + (size_t)ROWS * STRIDE;        // [8 warps][32]
+    int* nanflag = reinterpret_cast<int*>(cand_all + 8 * 32);         // [PXT]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t px0 = (size_t)blockIdx.x * PXT;
+
+    if (tid < PXT) nanflag[tid] = 0;
+    for (int e = tid; e < (ROWS - n) * PXT; e += 256) K[(size_t)(n + e / PXT) * STRIDE + e % PXT] = PAD;
+    if ((p & 3) == 0 && px0 + PXT <= p && (reinterpret_cast<size_t>(cube) & 15) == 0) {
+        // fast path: thread = (row group r, float4 column c4); rows r, r + RSTEP, ...; 8 loads in flight
+        __syncthreads();
+        const int c4 = tid % Q, r = tid / Q;
+        const float* src = cube + px0 + 4 * c4;
+        bool anynan = false;
+        for (int row0 = r; row0 < n; row0 += 8 * RSTEP) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int row = row0 + u * RSTEP;
+                if (row < n) v[u] = ld_stream_f4(reinterpret_cast<const float4*>(src + (size_t)row * p));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int row = row0 + u * RSTEP;
+                if (row < n) {
+                    unsigned int* dst = K + (size_t)row * STRIDE + 4 * c4;
+                    const bool n0 = v[u].x != v[u].x, n1 = v[u].y != v[u].y, n2 = v[u].z != v[u].z,
+                               n3 = v[u].w != v[u].w;
+                    dst[0] = n0 ? PAD : f2key(v[u].x);
+                    dst[1] = n1 ? PAD : f2key(v[u].y);
+                    dst[2] = n2 ? PAD : f2key(v[u].z);
+                    dst[3] = n3 ? PAD : f2key(v[u].w);
+                    anynan |= n0 | n1 | n2 | n3;
+                }
+            }
+        }
+        if (anynan) {                                 // conservative: the flag only selects the NaN-counting path
+#pragma unroll
+            for (int t = 0; t < 4; ++t) nanflag[4 * c4 + t] = 1;
+        }
+        __syncthreads();
+    } else {
+        __syncthreads();
+        if (tid < PXT) nanflag[tid] = 1;                              // generic path: count NaNs for every pixel
+        median_load_tile(cube, n, p, PXT, STRIDE, px0, K);
+    }
+
+    unsigned int* cand = cand_all + warp * 32;
+    for (int px = warp; px < PXT; px += 8) {
+        if (px0 + px >= p) break;
+        const unsigned int* col = K + px + (size_t)lane * STRIDE;
+        unsigned int k[KPL];
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) k[j] = col[(size_t)(32 * j) * STRIDE];
+        auto count_lt = [&](unsigned int pv) {
+            unsigned int c0 = 0, c1 = 0;
+#pragma unroll
+            for (int j = 0; j < KPL; j += 2) { count_below(c0, k[j], pv); count_below(c1, k[j + 1], pv); }
+            return __reduce_add_sync(FULL, c0 + c1);
+        };
+        unsigned int m = (unsigned int)n;
+        if (nanflag[px]) {                                 // NaNs in this pixel (border of the rotated frames)
+            unsigned int nn = 0;
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) nn += (k[j] == PAD && lane + 32 * j < n) ? 1u : 0u;
+            m -= __reduce_add_sync(FULL, nn);
+        }
+        float result;
+        if (m == 0) {
+            result = __uint_as_float(0x7fc00000u);
+        } else {
+            const unsigned int r1 = (m - 1) >> 1, r2 = m >> 1;
+            const unsigned int s = warp_sort32(k[0], lane);            // n >= 64: row `lane` is a real frame
+            const int ns = __popc(__ballot_sync(FULL, s != PAD));
+            unsigned int lo = 0u, hi = PAD, clo = 0u, chi = m, k1 = 0u, k2 = 0u;
+            bool have_lo = false, have_hi = false, first = true;
+            int idx = ns >> 1, it = 0, guard = 0;
+            unsigned int pv = (ns > 0) ? __shfl_sync(FULL, s, idx) : (PAD >> 1);
+            for (;;) {
+                if (++guard > 400) __trap();                            // impossible by construction: fail loudly
+                const unsigned int c = count_lt(pv);
+                if (first && ns > 1) {
+                    const unsigned int sa = __shfl_sync(FULL, s, min(idx + 1, ns - 1));
+                    const unsigned int sb = __shfl_sync(FULL, s, max(idx - 1, 0));
+                    if (sa == pv || sb == pv) {                         // ties around the sample median
+                        const unsigned int cle = count_lt(pv + 1u);
+                        if (c <= r1 && r2 < cle) { k1 = k2 = pv; break; }
+                    }
+                }
+                first = false;
+                if (c <= r1) { lo = pv; clo = c; have_lo = true; }
+                else if (c > r2) { hi = pv; chi = c; have_hi = true; }
+                else {
+                    // c == r2 == r1 + 1: the pivot separates the two middle ranks
+                    // (compared with pv - 1 on purpose: written as `k < pv` the assembler keeps all KPL compare results
+                    // of every counting pass alive in a bit mask for this rarely taken block -- 2 extra instructions
+                    // per key and pass, ncu r02z)
+                    unsigned int a = 0u, b = PAD;
+                    const unsigned int pm = pv - 1u;                    // pv > 0: c >= 1 keys lie below it
+#pragma unroll
+                    for (int j = 0; j < KPL; ++j) {
+                        if (k[j] <= pm) a = max(a, k[j]); else b = min(b, k[j]);
+                    }
+                    k1 = __reduce_max_sync(FULL, a);
+                    k2 = __reduce_min_sync(FULL, b);
+                    break;
+                }
+                if (chi - clo <= 32u) {
+                    // the keys of [lo, hi): per-lane count, exclusive scan over the lanes, compacted into one key per
+                    // lane, sorted; the two ranks are read off with a shuffle
+                    const unsigned int width = hi - lo;
+                    unsigned int cnt = 0;
+#pragma unroll
+                    for (int j = 0; j < KPL; ++j) count_below(cnt, k[j] - lo, width);
+                    unsigned int off = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned int o = __shfl_up_sync(FULL, off, d);
+                        if (lane >= d) off += o;
+                    }
+                    off -= cnt;
+                    if (cnt) {
+#pragma unroll
+                        for (int j = 0; j < KPL; ++j)
+                            if ((k[j] - lo) < width) cand[off++] = k[j];
+                    }
+                    __syncwarp();
+                    unsigned int v = ((unsigned int)lane < chi - clo) ? cand[lane] : PAD;
+                    __syncwarp();
+                    v = warp_sort32(v, lane);
+                    k1 = __shfl_sync(FULL, v, (int)(r1 - clo));
+                    k2 = __shfl_sync(FULL, v, (int)(r2 - clo));
+                    break;
+                }
+                if (hi - lo <= 1u) { k1 = k2 = lo; break; }              // every key left equals lo
+                ++it;
+                const bool use_mid = it >= 6 && (it % 3) == 0;
+                unsigned int pn = 0u;
+                bool ok = false;
+                if (!use_mid && !(have_lo && have_hi) && ns > 0) {
+                    const int up = c <= r1;
+                    const int d = up ? (int)(((r1 - c) * (unsigned int)ns) / m)
+                                     : -(int)(((c - r1) * (unsigned int)ns) / m);
+                    const int g = min(it, 3);
+                    idx = min(max(idx + (up ? d + g : d - g), 0), ns - 1);
+                    pn = __shfl_sync(FULL, s, idx);
+                    ok = true;
+                } else if (!use_mid && have_lo && have_hi) {
+                    const float flo = key2f(lo), fhi = key2f(hi);
+                    float t = ((float)r1 + 0.5f - (float)clo) / (float)(chi - clo);
+                    t = fminf(fmaxf(t, 0.15f), 0.85f);
+                    const float pf = flo + (fhi - flo) * t;
+                    ok = pf == pf;
+                    pn = f2key(pf);
+                }
+                pv = (ok && pn > lo && pn < hi) ? pn : lo + ((hi - lo) >> 1);
+            }
+            const float a = key2f(k1), b = key2f(k2);
+            result = (m & 1u) ? a : (a + b) * 0.5f;
+        }
+        if (lane == 0) out[px0 + px] = result;
+    }
+}
+
 struct MedianCfg { int sub, pxt, stride, threads; size_t smem; };
 
 // Pick (SUB, pixel tile, padded stride) maximising resident threads per SM; returns false when n is too
@@ -486,6 +698,32 @@ static int launch_median_smem(const float* cube, int n, size_t p, float* out, co
         default: VB_REQUIRE(false, "collapse: bad median configuration");
     }
 #undef VB_MEDIAN_CASE
+    VB_CHECK_LAUNCH();
+    return 0;
+}
+
+static int launch_median_warp(const float* cube, int n, size_t p, float* out, cudaStream_t st) {
+    // pixel tile: 32 pixels (128-byte row segments, KPL <= 16) or 16 (n > 512: 32 keys per lane); the row pitch
+    // PXT + 1 is odd = conflict-free column reads (lane l reads row l + 32 j: bank (l + px) mod 32); the tile is
+    // padded to KPL * 32 rows so that key loads need no bounds test
+#define VB_MEDIAN_WARP_CASE(KPL, PXT)                                                                         \
+    {                                                                                                         \
+        const size_t smem = (size_t)(KPL * 32) * (PXT + 1) * 4 + 8 * 32 * 4 + PXT * 4;                        \
+        static bool configured = false;                                                                       \
+        if (!configured) {                                                                                    \
+            VB_CHECK_CUDA(cudaFuncSetAttribute(collapse_median_warp_kernel<KPL, PXT>,                         \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+            VB_CHECK_CUDA(cudaFuncSetAttribute(collapse_median_warp_kernel<KPL, PXT>,                         \
+                                               cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
+            configured = true;                                                                                \
+        }                                                                                                     \
+        collapse_median_warp_kernel<KPL, PXT><<<(unsigned)ceil_div(p, (size_t)PXT), 256, smem, st>>>(cube, n, p, out); \
+    }
+    if (n <= 128) VB_MEDIAN_WARP_CASE(4, 32)
+    else if (n <= 256) VB_MEDIAN_WARP_CASE(8, 32)
+    else if (n <= 512) VB_MEDIAN_WARP_CASE(16, 32)
+    else VB_MEDIAN_WARP_CASE(32, 16)
+#undef VB_MEDIAN_WARP_CASE
     VB_CHECK_LAUNCH();
     return 0;
 }
@@ -583,6 +821,11 @@ int collapse_f32(const float* cube, int n, size_t p, int mode, const double* w, 
             // (measured slower on config 2: 0.64 vs 0.55 ms, profiles/r01o_ab.md -- kept as a tested experiment)
             const char* a = getenv("VIP_B200_MEDIAN_ALGO");
             const int range_variant = (a && strcmp(a, "range") == 0) ? 1 : 0;
+            // default for 64 <= n <= 1024: warp-per-pixel bracket search on register-resident keys
+            // (VIP_B200_MEDIAN_ALGO=radix keeps the 4-bit radix kernel)
+            if (!(e && atoi(e)) && !(a && (strcmp(a, "radix") == 0 || strcmp(a, "range") == 0)) && n >= 64 &&
+                n <= 1024)
+                return launch_median_warp(cube, n, p, fo, st);
             if (!(e && atoi(e)) && pick_median_cfg(n, &cfg, range_variant))
                 return launch_median_smem(cube, n, p, fo, cfg, range_variant, st);
             collapse_median_kernel<<<(unsigned)ceil_div(p, (size_t)CT), CT, 0, st>>>(cube, n, p, fo);
