@@ -202,6 +202,18 @@ int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitc
  * ~10 GB/s); a pinned source is one cudaMemcpyAsync.  The source may be reused when the call returns. */
 int vb_memcpy_h2d_staged(void* dst, const void* src_host, size_t nbytes, void* stream);
 
+/* ---- blob detection and FITS decode ------------------------------------------------------
+ * mask[y][x] = 1 where img[y][x] is the maximum of its (2 d + 1)^2 neighbourhood (edge-replicated), exceeds
+ * `threshold` and lies more than d pixels from the border; NaNs never are peaks and never hide one.
+ * Replaces: skimage.feature.peak_local_max as called by detection      metrics/detection.py:277-279 */
+int vb_local_max_mask_f32(const float* img, int H, int W, int min_distance, float threshold, unsigned char* mask,
+                          void* stream);
+/* Data unit of a FITS image HDU on the device: `count` big-endian samples of type BITPIX (8, 16, 32, 64, -32, -64)
+ * at `raw` (device) -> out[i] = fp32(BSCALE * sample + BZERO).
+ * Replaces: the host-side conversion of open_fits (astropy + np.array(data, dtype))      fits/fits.py:119-146 */
+int vb_fits_decode_f32(const void* raw, int bitpix, size_t count, double bscale, double bzero, float* out,
+                       void* stream);
+
 /* ---- S/N of test resolution elements, S/N map ------------------------------------------
  * Exact circular-aperture sums: out[a] = sum over pixels of area(circle(xs[a], ys[a], r) ∩ unit pixel) * img.
  * Replaces: photutils CircularAperture + aperture_photometry(method='exact')   metrics/snr_source.py:393-397 */

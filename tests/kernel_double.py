@@ -209,6 +209,11 @@ def snr_points_device(frame_dev, xs, ys, fwhm, frame2_dev=None, use2alone=False,
             torch.tensor([r[2] for r in res], dtype=torch.float64))
 
 
+def local_max_mask_device(frame_dev, min_distance, threshold):
+    from oracle import vip_oracle as O
+    return torch.from_numpy(O.local_max_mask(frame_dev.numpy(), int(min_distance), float(threshold)))
+
+
 def install(monkeypatch):
     """Route ``vip_b200`` through the stand-ins above for the duration of one test."""
     import vip_b200
@@ -222,6 +227,10 @@ def install(monkeypatch):
     from vip_b200.metrics import snr_source
     monkeypatch.setattr(snr_source, "aperture_sums_device", aperture_sums_device)
     monkeypatch.setattr(snr_source, "snr_points_device", snr_points_device)
+    import importlib
+    detection_mod = importlib.import_module("vip_b200.metrics.detection")
+    monkeypatch.setattr(detection_mod, "local_max_mask_device", local_max_mask_device)
+    monkeypatch.setattr(detection_mod, "require_cuda", lambda: CPU)
     for mod in (pca_fullfr, annular, sdi, snr_source):
         if hasattr(mod, "require_cuda"):
             monkeypatch.setattr(mod, "require_cuda", lambda: CPU)

@@ -1288,3 +1288,71 @@ def test_snrmap_finds_the_injected_planet_and_pca_snr_grid(vb):
     assert rel_err(optfr, o_fr) < FRAME_TOL and cubeout.shape == o_cube.shape
     only = vb.pca(cube, angs, ncomp=(1, 6), source_xy=(int(x0), int(y0)), fwhm=4, verbose=False)
     np.testing.assert_array_equal(only, optfr)
+
+
+# ------------------------------------------------------------------ detection, FITS decode
+def test_local_max_mask_kernel_vs_oracle(vb):
+    """``vb_local_max_mask_f32`` against the oracle's restatement of scikit-image's peak mask (maximum filter with
+    edge replication, threshold, border exclusion): random frames with NaNs, plateaus and odd sizes, several window
+    radii; exact equality of the masks."""
+    import torch
+    from vip_b200.metrics.detection import local_max_mask_device
+    rng = np.random.default_rng(5)
+    for (H, W), d in (((64, 64), 4), ((37, 91), 1), ((101, 100), 7), ((16, 16), 0), ((300, 257), 5)):
+        img = rng.normal(size=(H, W)).astype(np.float32)
+        img[rng.uniform(size=img.shape) < 0.02] = np.nan
+        img[H // 2, W // 2] = img[H // 2, W // 2 + 1] = 9.0              # plateau: both are maxima of their window
+        img[0, 3] = 20.0                                                   # border
+        got = local_max_mask_device(torch.from_numpy(img).cuda(), d, 0.5).cpu().numpy()
+        np.testing.assert_array_equal(got, O.local_max_mask(img, d, 0.5), err_msg=str((H, W, d)))
+    img1 = np.zeros((7, 7), dtype=np.float32)                              # the example of skimage's docstring
+    img1[3, 4] = 1
+    img1[3, 2] = 1.5
+    np.testing.assert_array_equal(vb.metrics.peak_local_max(img1, min_distance=1), [[3, 2], [3, 4]])
+    np.testing.assert_array_equal(vb.metrics.peak_local_max(img1, min_distance=2), [[3, 2]])
+
+
+def test_detection_vs_oracle_and_reference_criterion(vb):
+    """``vip_b200.detection`` end to end on the GPU (S/N map, peak mask and aperture S/N in kernels) against the oracle,
+    and the reference's own acceptance criterion (``tests/helpers.py:38-77``): the companion injected at
+    (y, x) = (32, 51) is recovered within 3 px by ``mode='lpeaks'`` -- and by ``'snrmap'``."""
+    cube, gen_angs = adi_cube(40, 64, 4, 120.0, seed=12, planet_peak=60.0)
+    frame = np.nan_to_num(vb.pca(cube, -gen_angs, ncomp=4, verbose=False))
+    for mode in ("lpeaks", "snrmap"):
+        want = O.detection(frame, fwhm=4, mode=mode, snr_thresh=5, full_output=True)
+        tab = vb.detection(frame, fwhm=4, mode=mode, snr_thresh=5, full_output=True, plot=False, verbose=False)
+        assert list(tab.columns) == ["y", "x", "px_snr"] and len(tab) == len(want["y"])
+        np.testing.assert_allclose(tab.y, want["y"], atol=1e-4)
+        np.testing.assert_allclose(tab.x, want["x"], atol=1e-4)
+        np.testing.assert_allclose(tab.px_snr, want["px_snr"], rtol=1e-6)
+        assert any(abs(y - 32) <= 3 and abs(x - 51) <= 3 for y, x in zip(tab.y, tab.x)), (mode, tab)
+
+
+@pytest.mark.parametrize("bitpix", [8, 16, 32, 64, -32, -64])
+def test_fits_decode_on_device(vb, bitpix, tmp_path):
+    """``open_fits_device``: raw big-endian data unit uploaded and decoded on the GPU (``vb_fits_decode_f32``) equals
+    the host reader for every image BITPIX, with and without BSCALE / BZERO."""
+    from vip_b200.fits import fits as F
+    rng = np.random.default_rng(abs(bitpix))
+    shape = (5, 33, 47)
+    if bitpix > 0:
+        info = {8: (0, 255, ">u1"), 16: (-32768, 32767, ">i2"), 32: (-2**31, 2**31 - 1, ">i4"),
+                64: (-2**40, 2**40, ">i8")}[bitpix]
+        vals = rng.integers(info[0], info[1], size=shape, endpoint=True).astype(info[2])
+    else:
+        vals = (rng.normal(size=shape) * 1e3).astype(">f4" if bitpix == -32 else ">f8")
+        vals[0, 0, 0] = np.nan
+    for scaled in (False, True):
+        cards = ["SIMPLE  =                    T", f"BITPIX  = {bitpix:20d}", "NAXIS   =                    3",
+                 "NAXIS1  =                   47", "NAXIS2  =                   33", "NAXIS3  =                    5"]
+        if scaled:
+            cards += ["BSCALE  =                 0.25", "BZERO   =               1000.5"]
+        head = "".join(f"{c:<80s}" for c in cards + ["END"]).encode()
+        head += b" " * (-len(head) % 2880)
+        data = vals.tobytes()
+        name = str(tmp_path / f"f{bitpix}_{int(scaled)}.fits")
+        open(name, "wb").write(head + data + b"\0" * (-len(data) % 2880))
+        host = F.open_fits(name, verbose=False)
+        dev, hdr = F.open_fits_device(name, header=True)
+        assert dev.is_cuda and dev.dtype.is_floating_point and tuple(dev.shape) == shape and hdr["BITPIX"] == bitpix
+        np.testing.assert_array_equal(dev.cpu().numpy(), host)

@@ -328,3 +328,31 @@ def test_pca_annular_ncomp_auto_vs_oracle(vb):
         assert np.max(np.abs(r[0] - o64[0])) < 1e-4 * scale, kw
         assert np.max(np.abs(r[0] - o[0])) < 5e-4 * scale, kw
         assert rel_err(r[2], o64[2]) < 3e-4, kw
+
+
+def test_detection_host_logic_vs_oracle(vb):
+    """``vip_b200.detection`` (``metrics/detection.py:26-382``): mask, background level, peak ordering / spacing,
+    Gaussian-fit constraints, S/N filter and return layouts against the oracle, with the kernels replaced by their
+    stand-ins; the reference's ``check_detection`` criterion on the product's own PCA frame."""
+    import pandas as pn
+    cube, gen_angs = adi_cube(40, 64, 4, 120.0, seed=12, planet_peak=60.0)
+    frame = np.nan_to_num(vb.pca(cube, -gen_angs, ncomp=4, verbose=False))
+    for mode in ("lpeaks", "snrmap"):
+        want = O.detection(frame, fwhm=4, mode=mode, snr_thresh=5, full_output=True)
+        tab = vb.detection(frame, fwhm=4, mode=mode, snr_thresh=5, full_output=True, plot=False, verbose=False)
+        assert isinstance(tab, pn.DataFrame) and list(tab.columns) == ["y", "x", "px_snr"]
+        np.testing.assert_allclose(tab.y, want["y"], atol=1e-6)
+        np.testing.assert_allclose(tab.x, want["x"], atol=1e-6)
+        np.testing.assert_allclose(tab.px_snr, want["px_snr"], rtol=1e-6)
+        assert any(abs(y - 32) <= 3 and abs(x - 51) <= 3 for y, x in zip(tab.y, tab.x))
+        yy, xx = vb.detection(frame, fwhm=4, mode=mode, snr_thresh=5, plot=False, verbose=False)
+        np.testing.assert_allclose(yy, want["y"], atol=1e-6)
+    assert vb.detection(np.zeros((40, 40), dtype=np.float32), fwhm=4, plot=False, verbose=False) == (0, 0)
+    with pytest.raises(TypeError):
+        vb.detection(cube, fwhm=4, plot=False)
+    with pytest.raises(ValueError):
+        vb.detection(frame, fwhm=4, matched_filter=True, plot=False)
+    with pytest.raises(ValueError):
+        vb.detection(frame, fwhm=4, mode="blobs", plot=False)
+    with pytest.raises(NotImplementedError):
+        vb.detection(frame, fwhm=4, mode="log", plot=False)

@@ -218,3 +218,54 @@ def test_exact_aperture_sums_known_answers():
         quad = np.mean(X * X + Y * Y <= r * r)
         w = O.circle_rect_area(np.array(dx - 0.5), np.array(dy - 0.5), np.array(dx + 0.5), np.array(dy + 0.5), r)
         assert abs(float(w) - quad) < 2e-3
+
+
+def test_detection_pieces_known_answers():
+    """The third-party pieces of ``detection`` (``metrics/detection.py``) restated in the oracle -- astropy and
+    scikit-image are not installed, so these are pinned on documented known answers and exact properties:
+    ``peak_local_max`` on the example of its own docstring, the sigma clipping on a sample with planted outliers,
+    the Gaussian2D Levenberg-Marquardt fit on an exact Gaussian and its analytic Jacobian against finite differences."""
+    # scikit-image, feature/peak.py docstring:  img1[3, 4] = 1; img1[3, 2] = 1.5
+    img1 = np.zeros((7, 7))
+    img1[3, 4] = 1
+    img1[3, 2] = 1.5
+    np.testing.assert_array_equal(O.peak_local_max(img1, min_distance=1), [[3, 2], [3, 4]])
+    np.testing.assert_array_equal(O.peak_local_max(img1, min_distance=2), [[3, 2]])
+    # border exclusion, threshold, NaN, plateau (two equal neighbours: the first in raster order survives the spacing)
+    img = np.zeros((12, 12))
+    img[0, 5] = 9.0                       # on the border: excluded
+    img[5, 5] = 2.0
+    img[5, 6] = 2.0                       # plateau
+    img[9, 2] = 0.5                       # below the threshold
+    img[8, 9] = np.nan
+    np.testing.assert_array_equal(O.peak_local_max(img, min_distance=2, threshold_abs=1.0), [[5, 5]])
+    # sigma clipping: 1000 standard normal samples + 10 samples at 50: the outliers go, the bulk stays
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.normal(size=1000), np.full(10, 50.0), [np.nan, np.inf]])
+    mean, med, std = O.sigma_clipped_stats(x, sigma=5, maxiters=None)
+    bulk = x[:1000]
+    assert mean == pytest.approx(bulk.mean(), abs=1e-12) and med == pytest.approx(np.median(bulk), abs=1e-12)
+    assert std == pytest.approx(bulk.std(), abs=1e-12)
+    # exact elliptical Gaussian: the fit returns its parameters
+    sy, sx = np.indices((13, 13))
+    p_true = (7.0, 6.3, 5.8, 1.9, 1.6, 0.0)
+    a, b = 0.5 / p_true[3] ** 2, 0.5 / p_true[4] ** 2
+    g = p_true[0] * np.exp(-(a * (sx - p_true[1]) ** 2 + b * (sy - p_true[2]) ** 2))
+    fit = O.fit_gaussian2d_lm(g, g.max(), 6.0, 6.0, 1.7, 1.7)
+    np.testing.assert_allclose(np.abs(fit[:5]), p_true[:5], rtol=1e-6)
+    assert abs(np.sin(2 * fit[5])) * abs(fit[3] - fit[4]) < 1e-5          # axes aligned up to the pi/2 ambiguity
+
+
+def test_detection_recovers_the_injected_companion():
+    """The reference's acceptance criterion (``tests/helpers.py:38-77``, ``check_detection``): the companion injected at
+    (y, x) = (32, 51) is among the sources ``detection(mode='lpeaks')`` returns, within 3 px -- on the oracle's own
+    PCA frame ('snrmap' mode: ``test_host_pipeline_cpu.py::test_detection_host_logic_vs_oracle``)."""
+    from tools.synth import adi_cube
+    cube, gen_angs = adi_cube(40, 64, 4, 120.0, seed=12, planet_peak=60.0)
+    frame = np.nan_to_num(O.pca_fullframe(cube, -gen_angs, ncomp=4))
+    for mode in ("lpeaks",):
+        tab = O.detection(frame, fwhm=4, mode=mode, snr_thresh=5, full_output=True)
+        assert any(abs(y - 32) <= 3 and abs(x - 51) <= 3 for y, x in zip(tab["y"], tab["x"])), (mode, tab)
+        assert max(tab["px_snr"]) > 8
+    assert O.detection(np.zeros((40, 40)) + 1e-3 * np.random.default_rng(0).normal(size=(40, 40)), fwhm=4,
+                       snr_thresh=50) == (0, 0)

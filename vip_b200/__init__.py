@@ -6,7 +6,8 @@ through the C ABI of ``libvipb200.so`` (``include/vip_b200.h``).  No CPU fallbac
 """
 __version__ = "0.1.0"
 
-from . import config, metrics, preproc, psfsub, var        # noqa: F401
+from . import config, fits, metrics, preproc, psfsub, var        # noqa: F401
 from .psfsub import pca, pca_annular, median_sub                        # noqa: F401
 from .preproc import cube_derotate, cube_collapse, cube_shift, frame_shift           # noqa: F401
-from .metrics import snr, snrmap                                                        # noqa: F401
+from .metrics import snr, snrmap, detection                                             # noqa: F401
+from .fits import open_fits, write_fits                                                 # noqa: F401

@@ -54,6 +54,8 @@ SIGNATURES = {
     "vb_aperture_sums_f64": (_i, [_vp, _i, _i, _vp, _vp, _i, _d, _vp, _vp]),
     "vb_snr_points_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _d, _d, _d, _i, _i, _vp, _vp, _vp]),
     "vb_fp32_probe": (_i, [_vp, _i, _i, _vp]),
+    "vb_local_max_mask_f32": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
+    "vb_fits_decode_f32": (_i, [_vp, _i, _sz, _d, _d, _vp, _vp]),
     "vb_memcpy_h2d_staged": (_i, [_vp, _vp, _sz, _vp]),
     "vb_profile_enable": (None, [_i]),
     "vb_profile_read": (_i, [C.POINTER(_f)]),

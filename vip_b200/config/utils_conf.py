@@ -25,3 +25,6 @@ def check_array(input_array, dim, msg=None):
     if not isinstance(input_array, np.ndarray) or input_array.ndim not in dims:
         kind = "list, tuple or a 1" if dim == 1 else label
         raise TypeError(name + " must be a " + kind + "d numpy ndarray")
+
+
+sep = "―" * 80          # section separator of the reference's console output (``config/utils_conf.py``)

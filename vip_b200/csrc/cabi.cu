@@ -67,6 +67,8 @@ int scatter_columns(const float*, int, int, const int*, size_t, float*, cudaStre
 int profile_read(float* out);
 int fp32_probe(float*, int, int, cudaStream_t);
 int memcpy_h2d_staged(void*, const void*, size_t, cudaStream_t);
+int local_max_mask(const float*, int, int, int, float, unsigned char*, cudaStream_t);
+int fits_decode(const void*, int, size_t, double, double, float*, cudaStream_t);
 int aperture_sums(const float*, int, int, const double*, const double*, int, double, double*, cudaStream_t);
 int snr_points(const float*, const float*, int, int, const int*, const int*, int, double, double, double, int, int,
                double*, double*, cudaStream_t);
@@ -340,6 +342,18 @@ int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitc
     VB_CHECK_CUDA(cudaMemcpy2DAsync(dst, dpitch, src_host, spitch, width_bytes, height, cudaMemcpyHostToDevice,
                                     (cudaStream_t)stream));
     return 0;
+}
+
+int vb_local_max_mask_f32(const float* img, int H, int W, int min_distance, float threshold, unsigned char* mask,
+                          void* stream) {
+    g_launches += 1;
+    return local_max_mask(img, H, W, min_distance, threshold, mask, (cudaStream_t)stream);
+}
+
+int vb_fits_decode_f32(const void* raw, int bitpix, size_t count, double bscale, double bzero, float* out,
+                       void* stream) {
+    g_launches += 1;
+    return fits_decode(raw, bitpix, count, bscale, bzero, out, (cudaStream_t)stream);
 }
 
 int vb_aperture_sums_f64(const float* img, int H, int W, const double* xs, const double* ys, int nap, double r,
