@@ -564,7 +564,7 @@ def run_gpu(args):
                      "(error-free bf16x3 split) on 10 of 16 tiles: 0.52 PFLOP of tensor work per step"),
             "issued_bf16_tflops": 6.0 * 2.0 * (n_tiles_upper(n) * 128.0 * 128.0) * p / (gram_ms * 1e-3) / 1e12}
         col_ms = st["collapse_median_ms"]
-        line["roofline_collapse"] = {"kernel": "collapse_median_smem_kernel", "bound": "hbm",
+        line["roofline_collapse"] = {"kernel": "collapse_median_warp_kernel<16,32>", "bound": "hbm",
                                      "achieved": 4.0 * p * n / (col_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                      "unit": "GB/s", "frac": 4.0 * p * n / (col_ms * 1e-3) / 1e9 / hbm_peak}
         ps_ms = st["project_subtract_ms"]

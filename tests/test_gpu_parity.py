@@ -826,6 +826,27 @@ def test_pca_annular_adimsdi_vs_oracle(vb):
     assert float(np.max(np.abs(r[0] - o[0]))) < tol and float(np.max(np.abs(r[2][m] - o[2][m]))) < tol
 
 
+def test_pca_annular_left_eigv_vs_oracle(vb):
+    """``pca_annular(left_eigv=True)`` (``pca_local.py:704-707, 755-779``): temporal singular vectors of the pixels
+    outside each segment from (full-frame Gramian - segment Gramian), against the oracle (bit-identical to the
+    unmodified reference on these cases)."""
+    cube, angs = adi_cube(16, 32, 3, 70.0, seed=8)
+    for kw in (dict(ncomp=2, asize=5), dict(ncomp=3, asize=4, n_segments=2, scaling="temp-mean"),
+               dict(ncomp=2, asize=5, scaling="spat-mean")):
+        o = O.pca_annular(cube, angs, left_eigv=True, full_output=True, **kw)
+        r = vb.pca_annular(cube, angs, left_eigv=True, verbose=False, full_output=True, **kw)
+        assert np.max(np.abs(r[0] - o[0])) < PCA_TOL * np.max(np.abs(o[0])), kw
+        assert rel_err(r[2], o[2]) < FRAME_TOL, kw
+    cube, angs = adi_cube(300, 64, 5, 80.0, seed=9)             # the subspace solver on the difference Gramian
+    o = O.pca_annular(cube, angs, left_eigv=True, ncomp=5, asize=8, full_output=True)
+    r = vb.pca_annular(cube, angs, left_eigv=True, ncomp=5, asize=8, verbose=False, full_output=True)
+    o64 = O.pca_annular(cube.astype(np.float64), angs, left_eigv=True, ncomp=5, asize=8, full_output=True)
+    scale = np.max(np.abs(o64[0]))
+    e32, e64 = np.max(np.abs(r[0] - o[0])) / scale, np.max(np.abs(r[0] - o64[0])) / scale
+    print(f"left_eigv 300x64x64: vs fp32 oracle {e32:.2e}, vs float64 oracle {e64:.2e}")
+    assert e32 < PCA_TOL or e64 < PCA_TOL
+
+
 def test_pca_annular_errors(vb, golden_inputs):
     cube, angs = golden_inputs["ann"]
     with pytest.raises(TypeError):

@@ -356,3 +356,24 @@ def test_detection_host_logic_vs_oracle(vb):
         vb.detection(frame, fwhm=4, mode="blobs", plot=False)
     with pytest.raises(NotImplementedError):
         vb.detection(frame, fwhm=4, mode="log", plot=False)
+
+
+def test_pca_annular_left_eigv_vs_oracle(vb):
+    """``pca_annular(left_eigv=True)``: Gramian of the outside pixels as (full-frame Gramian - segment Gramian) for the
+    per-pixel scalings, the outside matrix itself for 'spat-*'; against the oracle (bit-identical to the reference:
+    ``test_pca_annular_left_eigv_bit_identical``)."""
+    cube, angs = adi_cube(16, 32, 3, 70.0, seed=8)
+    for kw in (dict(ncomp=2, asize=5), dict(ncomp=3, asize=4, n_segments=2, scaling="temp-mean"),
+               dict(ncomp=2, asize=5, scaling="spat-mean"), dict(ncomp=[1, 3], asize=5)):
+        if isinstance(kw["ncomp"], list):
+            r = vb.pca_annular(cube, angs, left_eigv=True, verbose=False, full_output=True, **kw)
+            for i, k in enumerate(kw["ncomp"]):
+                o = O.pca_annular(cube, angs, left_eigv=True, full_output=True, **dict(kw, ncomp=k))
+                assert np.max(np.abs(r[0][i] - o[0])) < 1e-4 * np.max(np.abs(o[0])), kw
+            continue
+        o = O.pca_annular(cube, angs, left_eigv=True, full_output=True, **kw)
+        r = vb.pca_annular(cube, angs, left_eigv=True, verbose=False, full_output=True, **kw)
+        assert np.max(np.abs(r[0] - o[0])) < 1e-4 * np.max(np.abs(o[0])), kw
+        assert rel_err(r[2], o[2]) < 3e-4, kw
+    with pytest.raises(NotImplementedError):
+        vb.pca_annular(cube, angs, left_eigv=True, ncomp="auto", verbose=False)

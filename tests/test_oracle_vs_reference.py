@@ -163,3 +163,16 @@ def test_pca_annular_ncomp_auto_bit_identical(ref):
         for a, b in zip(r, o):
             np.testing.assert_array_equal(a, b)
         assert len(set(used)) > 1 or kw["tol"] == 0.5, (kw, sorted(set(used)))
+
+
+def test_pca_annular_left_eigv_bit_identical(ref):
+    """``pca_annular(left_eigv=True)``: projection of every segment on the temporal singular vectors of the pixels
+    outside it (``pca_local.py:704-707, 755-779``)."""
+    psfsub, _ = ref
+    cube, angs = adi_cube(16, 32, 3, 70.0, seed=8)
+    for kw in (dict(ncomp=2, asize=5), dict(ncomp=3, asize=4, n_segments=2, scaling="temp-mean"),
+               dict(ncomp=2, asize=5, scaling="spat-mean")):
+        r = psfsub.pca_annular(cube, angs, left_eigv=True, verbose=False, full_output=True, nproc=1, **kw)
+        o = O.pca_annular(cube, angs, left_eigv=True, full_output=True, **kw)
+        for a, b in zip(r, o):
+            np.testing.assert_array_equal(a, b)

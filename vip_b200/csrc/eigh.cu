@@ -1184,11 +1184,14 @@ topk_fused2_kernel(const double* __restrict__ G, int n, int k, double tol, int m
 #pragma unroll
                 for (int r = 0; r < NUPD; ++r) {
                     const int e = tid + 480 * r;
-                    const int i = (e / B) % B, c = e % B;            // e >= B*B: inactive (wrapped row, no store)
+                    // threads beyond the matrix read element (0, 0), which no step writes (racecheck: reading another
+                    // thread's element, even to discard it, is a hazard), and store nothing
+                    const bool valid = e < B * B;
+                    const int i = valid ? e / B : 0, c = valid ? e % B : 0;
                     const bool lower = i > j;
                     // the next pivot (j+1, j+1) is left alone: the look-ahead reads its pre-update value in this very
                     // step, and nothing reads it afterwards
-                    act[r] = e < B * B && (lower ? (c >= i && !(c == i && i == j + 1)) : (c > j));
+                    act[r] = valid && (lower ? (c >= i && !(c == i && i == j + 1)) : (c > j));
                     const double mult = lower ? Sn[j][i] : Wm[i][j];
                     dst[r] = lower ? &Sn[i][c] : &Wm[i][c];
                     val[r] = fma(-(mult * inv), Sn[j][c], *dst[r]);

@@ -273,8 +273,6 @@ def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segme
         return frames
     if isinstance(ncomp, str) and ncomp != "auto":
         raise TypeError("`ncomp` must be an int, a tuple/array of ints, a list or 'auto'")
-    if left_eigv:
-        _unsupported("`left_eigv`")
     _check_rot_options(imlib, rot_options.get("cxy"), rot_options.get("border_mode", "constant"),
                        rot_options.get("edge_blend"), array.shape)
 
@@ -288,6 +286,16 @@ def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segme
     sig_dev = to_device_f32(cube_sig, dev).reshape(n, y * x) if cube_sig is not None else None
     cube_out = torch.zeros_like(cube_dev)
     t0 = _tick("upload", t0)
+    G_full = M_full = None
+    if left_eigv:
+        # `left_eigv` (pca_local.py:704-707, 755-779): every segment is projected on the leading TEMPORAL singular
+        # vectors of the pixels outside it.  Their Gramian is the Gramian of the whole frame minus the Gramian of the
+        # segment -- one full-frame product (tensor cores) serves all segments -- whenever the scaling acts per pixel
+        # (none, temp-*); the per-frame scalings (spat-*) depend on the pixel set and take the outside matrix itself.
+        sc = None if scaling is None else _mode_name(scaling)
+        if sc is None or sc.startswith("temp"):
+            M_full = scale_matrix_device(cube_dev, scaling)
+            G_full = kernels.gram(M_full)
 
     verbose_ann = (int(verbose) + int(cube_ref is None)) if verbose else verbose
     # library index lists of every annulus (host integer logic, independent of the pixel data): computed
@@ -313,6 +321,29 @@ def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segme
             if yy.size == 0:
                 continue
             cols = torch.from_numpy((yy * x + xx).astype(np.int32)).to(dev)
+            if left_eigv:
+                if G_full is not None:
+                    A = kernels.gather_columns(M_full, cols)
+                    G_out = G_full - kernels.gram(A)
+                    p_out = y * x - cols.numel()
+                else:
+                    outside = np.ones(y * x, dtype=bool)
+                    outside[yy * x + xx] = False
+                    cols_out = torch.from_numpy(np.nonzero(outside)[0].astype(np.int32)).to(dev)
+                    A = scale_matrix_device(kernels.gather_columns(cube_dev, cols), scaling)
+                    G_out = kernels.gram(scale_matrix_device(kernels.gather_columns(cube_dev, cols_out), scaling))
+                    p_out = cols_out.numel()
+                kk = min(int(ncompann), n, p_out)
+                if kernels.topk_supported(n, kk):
+                    _, U, info = kernels.eigh_topk(G_out, kk)
+                    if not info["converged"]:
+                        U = kernels.eigh(G_out)[1][:kk]
+                else:
+                    U = kernels.eigh(G_out)[1][:kk]
+                V = kernels.pcs(U, A)                                            # (kk, npx) = U A
+                R = kernels.project_subtract(A, U.t().to(torch.float32).contiguous(), V)
+                kernels.scatter_columns(R, cols, cube_out)
+                continue
             A = scale_matrix_device(kernels.gather_columns(cube_dev, cols), scaling)
             A_ref = (scale_matrix_device(kernels.gather_columns(ref_dev, cols), scaling)
                      if ref_dev is not None else None)
