@@ -1164,8 +1164,9 @@ def test_pca_source_xy_large_libraries_and_errors(vb):
         vb.pca(small, a, source_xy=(30, 25), delta_rot=1, fwhm=4, ncomp=3, verbose=False)
     with pytest.raises(TypeError):
         vb.pca(small, a, source_xy=(30, 25), ncomp=3, verbose=False)          # delta_rot missing
-    with pytest.raises(NotImplementedError):
-        vb.pca(small, a, source_xy=(30, 25), delta_rot=0.5, ncomp=(1, 3), verbose=False)
+    # source_xy + tuple ncomp = the S/N-optimised grid (implemented since fb27c7d; it raised before): optimal frame
+    fr = vb.pca(small, a, source_xy=(30, 25), delta_rot=0.5, ncomp=(1, 3), fwhm=4, verbose=False)
+    assert fr.shape == small.shape[1:]
 
 
 def test_pca_left_eigv_golden(vb, golden, golden_inputs):
@@ -1308,7 +1309,9 @@ def test_snrmap_finds_the_injected_planet_and_pca_snr_grid(vb):
     assert int(table["PCs"][int(np.argmax(table["S/Ns"]))]) == o_npc
     assert rel_err(optfr, o_fr) < FRAME_TOL and cubeout.shape == o_cube.shape
     only = vb.pca(cube, angs, ncomp=(1, 6), source_xy=(int(x0), int(y0)), fwhm=4, verbose=False)
-    np.testing.assert_array_equal(only, optfr)
+    # two runs agree to an fp32 ulp, not bit for bit: the block Gramians of the eigensolver are accumulated with
+    # atomics (summation order varies at the 1e-16 level of the fp64 eigenvectors)
+    assert rel_err(only, optfr) < 1e-5
 
 
 # ------------------------------------------------------------------ detection, FITS decode

@@ -298,6 +298,15 @@ def test_pca_annular_adimsdi_vs_oracle(vb):
         assert np.array_equal(np.isnan(r[2]), ~m) and np.max(np.abs(r[2][m] - o[2][m])) < tol, (ncomp, kw)
     fr = vb.pca_annular(cube, angs, scale_list=sl, ncomp=(1, None), fwhm=3, asize=6, delta_sep=0.1, verbose=False)
     assert fr.shape == cube.shape[2:]
+    cref, _, _ = ifs_cube(z=5, n=6, size=24, seed=8)        # reference cube through the same spectral pass
+    o = O.pca_annular_sdi(cube, angs, sl, (2, 2), fwhm=3, asize=4, delta_sep=(0.1, 0.3), cube_ref=cref,
+                          full_output=True)
+    r = vb.pca_annular(cube, angs, scale_list=sl, ncomp=(2, 2), fwhm=3, asize=4, delta_sep=(0.1, 0.3), cube_ref=cref,
+                       verbose=False, full_output=True)
+    tol = 5e-7 * float(np.max(np.abs(cube)))
+    assert np.max(np.abs(r[0] - o[0])) < tol
+    with pytest.raises(TypeError):
+        vb.pca_annular(cube, angs, scale_list=sl, ncomp=(2, 2), fwhm=3, cube_ref=cref[0], verbose=False)
     with pytest.raises(TypeError):
         vb.pca_annular(cube, angs, scale_list=sl, ncomp=2, fwhm=3, verbose=False)
     with pytest.raises(ValueError):

@@ -282,7 +282,10 @@ def _pca_adi_rdi_device(cube, angle_list, radius_int=0, fwhm=4, asize=2, n_segme
         cube_dev = array.to(torch.float32).contiguous().reshape(n, y * x)
     else:
         cube_dev = to_device_f32(array, dev).reshape(n, y * x)
-    ref_dev = to_device_f32(cube_ref, dev).reshape(cube_ref.shape[0], y * x) if cube_ref is not None else None
+    if isinstance(cube_ref, torch.Tensor):
+        ref_dev = cube_ref.to(torch.float32).contiguous().reshape(cube_ref.shape[0], y * x)
+    else:
+        ref_dev = to_device_f32(cube_ref, dev).reshape(cube_ref.shape[0], y * x) if cube_ref is not None else None
     sig_dev = to_device_f32(cube_sig, dev).reshape(n, y * x) if cube_sig is not None else None
     cube_out = torch.zeros_like(cube_dev)
     t0 = _tick("upload", t0)
@@ -492,8 +495,9 @@ def _pca_annular_adimsdi(p, rot_options):
     if not isinstance(p.ncomp, tuple):
         raise TypeError("`ncomp` must be a tuple of two integers when `cube` is a 4d array")
     ncomp1, ncomp2 = p.ncomp[0], p.ncomp[1]
-    if p.cube_ref is not None and ncomp2 is not None:
-        _unsupported("`cube_ref` with a 4-d cube and `scale_list`")
+    if p.cube_ref is not None and (not isinstance(p.cube_ref, np.ndarray) or p.cube_ref.ndim != 4 or
+                                   p.cube_ref.shape[0] != z or p.cube_ref.shape[2:] != cube.shape[2:]):
+        raise TypeError("Ref cube has wrong format for 4d input cube")
     _check_rot_options(p.imlib, rot_options.get("cxy"), rot_options.get("border_mode", "constant"),
                        rot_options.get("edge_blend"), cube.shape[1:])
     dev = require_cuda()
@@ -519,8 +523,17 @@ def _pca_annular_adimsdi(p, rot_options):
         return cube_out, cube_der, frame
     if p.verbose:
         print("Second PCA subtraction exploiting angular variability")
+    res_ref = None
+    if p.cube_ref is not None:
+        # the same spectral pass on the reference cube (pca_local.py:407-432); its residual frames become the
+        # reference library of the ADI pass
+        if p.verbose:
+            print("First PCA subtraction (spectral) on REF cube")
+        res_ref = _pca_sdi_frames_device(to_device_f32(p.cube_ref, dev), scale_list, p.radius_int, fwhm, p.asize,
+                                         p.n_segments, p.delta_sep, ncomp1, p.svd_mode, p.scaling, p.collapse_ifs,
+                                         p.ifs_collapse_range, p.theta_init)
     func_params = setup_parameters(params_obj=p, fkt=_pca_adi_rdi_device, cube=res_channels, ncomp=ncomp2,
-                                   fwhm=fwhm, cube_ref=None, full_output=True)
+                                   fwhm=fwhm, cube_ref=res_ref, full_output=True)
     return _pca_adi_rdi_device(**func_params, **rot_options)
 
 
