@@ -51,11 +51,25 @@ struct AnnularArgs {
 // On exit Tm's columns are mutually orthogonal: column j = theta_j * q_j.
 template <int B>
 __device__ void small_jacobi(double (*Tm)[B + 1], int nb, int tid) {
+    // Round 2 (measured on the B200, tools/microbench/fp64_lat.cu: DFMA 9 cycles, but sqrt 100, divide 126, rsqrt 77
+    // cycles of dependent latency): the first version of this routine took three warp reductions (both squared norms
+    // and the inner product) and sqrt -> divide -> sqrt -> divide per rotation, ~900 cycles per round and ~80 % of an
+    // iteration of the kernel below.  Now the squared column norms are kept up to date analytically, a rotation needs
+    // ONE reduction and TWO rsqrt (1/h = rsqrt(d^2 + g^2), cos 2t = |d| / h, c^2 = (1 + cos 2t) / 2, s = sign(d) g /
+    // (2 h c)), and a sweep whose rotations all started from couplings below 1e-8 is known to be the last one
+    // (quadratic convergence) without a verification sweep.
     const int warp = tid >> 5, lane = tid & 31, nwarps = AT / 32;
     const int m = (nb + 1) & ~1;   // even number of players
+    __shared__ int rotated;
+    __shared__ double jn[B];
+    const double thr = (double)B * 1.1e-16;
     for (int sweep = 0; sweep < 30; ++sweep) {
-        __shared__ int rotated;
         if (tid == 0) rotated = 0;
+        if (tid < nb) {
+            double sq = 0.0;
+            for (int i = 0; i < nb; ++i) sq = fma(Tm[i][tid], Tm[i][tid], sq);
+            jn[tid] = sq;
+        }
         __syncthreads();
         for (int r = 0; r < m - 1; ++r) {
             for (int pr = warp; pr < m / 2; pr += nwarps) {
@@ -63,22 +77,29 @@ __device__ void small_jacobi(double (*Tm)[B + 1], int nb, int tid) {
                 const int mm = m - 1;
                 if (pr == 0) { a = mm; b = r % mm; } else { a = (r + pr) % mm; b = (r - pr + mm) % mm; }
                 if (a < nb && b < nb) {
-                    double al = 0, be = 0, ga = 0;
-                    for (int i = lane; i < nb; i += 32) {
-                        const double x = Tm[i][a], y = Tm[i][b];
-                        al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
-                    }
-                    al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
-                    if (al > 0 && be > 0 && fabs(ga) > 1e-15 * sqrt(al) * sqrt(be)) {
-                        const double zeta = (be - al) / (2.0 * ga);
-                        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                    double ga = 0;
+                    for (int i = lane; i < nb; i += 32) ga = fma(Tm[i][a], Tm[i][b], ga);
+                    ga = warp_sum(ga);
+                    const double al = jn[a], be = jn[b];
+                    if (al > 0 && be > 0 && ga * ga > thr * thr * al * be) {
+                        const double d = be - al, g2 = 2.0 * ga;
+                        const double rh = rsqrt(fma(d, d, g2 * g2));
+                        const double c2 = fma(0.5 * fabs(d), rh, 0.5);
+                        const double q = rsqrt(c2);
+                        const double c = c2 * q;
+                        const double s = copysign(0.5, d) * g2 * rh * q;
                         for (int i = lane; i < nb; i += 32) {
                             const double x = Tm[i][a], y = Tm[i][b];
                             Tm[i][a] = c * x - s * y;
                             Tm[i][b] = s * x + c * y;
                         }
-                        if (lane == 0) rotated = 1;
+                        __syncwarp();
+                        if (lane == 0) {
+                            const double cs2 = 2.0 * c * s * ga;
+                            jn[a] = fma(c * c, al, fma(s * s, be, -cs2));
+                            jn[b] = fma(s * s, al, fma(c * c, be, cs2));
+                            if (ga * ga > 1e-16 * al * be) rotated = 1;
+                        }
                     }
                 }
             }
@@ -115,6 +136,7 @@ annular_weights_kernel(AnnularArgs p) {
     int* order = reinterpret_cast<int*>(cres + B);      // [B]
     int* Is = order + B;                    // [Lmax]
     __shared__ int done;
+    __shared__ double hist;                 // worst residual four iterations ago (thread 0 only)
 
     for (int i = tid; i < L; i += AT) Is[i] = I[i];
     // start block: hashed pseudo-random entries (well conditioned), orthonormalised below
@@ -123,7 +145,7 @@ annular_weights_kernel(AnnularArgs p) {
         Y[e] = (c < nb) ? hash_unit((unsigned)i * 131u + 7u, (unsigned)c * 977u + 3u) : 0.0;
     }
     if (tid < B) { cnorm[tid] = 0.0; }
-    if (tid == 0) done = 0;
+    if (tid == 0) { done = 0; hist = 0.0; }
     __syncthreads();
 
     int it = 0;
@@ -139,42 +161,60 @@ annular_weights_kernel(AnnularArgs p) {
             if ((tid & 31) == 0) atomicAdd(&cnorm[c], v);
         }
         __syncthreads();
-        for (int e = tid; e < L * B; e += AT) {
-            const int c = e % B;
-            Y[e] = (c < nb && cnorm[c] > 0.0) ? Y[e] * rsqrt(cnorm[c]) : 0.0;
-        }
+        if (tid < B) cres[tid] = (tid < nb && cnorm[tid] > 0.0) ? rsqrt(cnorm[tid]) : 0.0;   // once per column
         __syncthreads();
-        for (int e = tid; e < B * B; e += AT) {       // S = Yn^T Yn
+        for (int e = tid; e < L * B; e += AT) Y[e] *= cres[e % B];
+        __syncthreads();
+        for (int e = tid; e < B * B; e += AT) {       // S = Yn^T Yn  (four independent chains: DFMA latency 9 cycles)
             const int a = e / B, b = e % B;
-            double s = 0.0;
-            if (a < nb && b < nb)
-                for (int i = 0; i < L; ++i) s = fma(Y[i * B + a], Y[i * B + b], s);
-            Tm[a][b] = s;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            if (a < nb && b < nb) {
+                int i = 0;
+                for (; i + 3 < L; i += 4) {
+                    s0 = fma(Y[i * B + a], Y[i * B + b], s0);
+                    s1 = fma(Y[(i + 1) * B + a], Y[(i + 1) * B + b], s1);
+                    s2 = fma(Y[(i + 2) * B + a], Y[(i + 2) * B + b], s2);
+                    s3 = fma(Y[(i + 3) * B + a], Y[(i + 3) * B + b], s3);
+                }
+                for (; i < L; ++i) s0 = fma(Y[i * B + a], Y[i * B + b], s0);
+            }
+            Tm[a][b] = (s0 + s1) + (s2 + s3);
+            Q[a][b] = (a == b) ? 1.0 : 0.0;
         }
         __syncthreads();
-        if (tid < 32) {                                // Cholesky S = R^T R (R upper, stored in Q), warp 0
+        if (tid < 32) {
+            // S = R^T R by elimination, with U (R^-1 before its column scaling) accumulated alongside: step j only
+            // needs 1 / a_jj (one divide, lane-uniform); lane c owns column c of S (rows > j) and of U (rows <= j).
+            // Replaces the left-looking factorisation (sqrt + divide per pivot) and the per-row triangular solve with
+            // one divide per element (16 dependent divides per row: ~2000 cycles per iteration).
+            const int c = tid;
             for (int j = 0; j < nb; ++j) {
-                double d = Tm[j][j];
-                for (int m2 = 0; m2 < j; ++m2) d -= Q[m2][j] * Q[m2][j];
-                d = (d > 1e-300) ? sqrt(d) : 1e-150;
-                for (int c = j + tid; c < nb; c += 32) {
-                    double v = Tm[j][c];
-                    for (int m2 = 0; m2 < j; ++m2) v -= Q[m2][j] * Q[m2][c];
-                    Q[j][c] = (c == j) ? d : v / d;
+                const double ajj = Tm[j][j];
+                const double inv = (ajj > 1e-300) ? 1.0 / ajj : 1e300;
+                if (c == 0) cnorm[j] = inv;                      // cnorm is free once the column scales are taken
+                if (c < nb && c > j) {
+                    const double sjc = Tm[j][c] * inv;
+                    for (int i = j + 1; i <= c; ++i) Tm[i][c] = fma(-Tm[j][i], sjc, Tm[i][c]);
+                    for (int i = 0; i <= j; ++i) Q[i][c] = fma(-Q[i][j], sjc, Q[i][c]);
                 }
                 __syncwarp();
             }
+            if (tid < nb) cnorm[tid] = sqrt(cnorm[tid]);         // 1 / R[j][j]
+            __syncwarp();
+            for (int e = tid; e < B * B; e += 32) {              // R^-1 = U diag(sqrt(1 / a_jj)), upper triangular
+                const int a = e / B, b = e % B;
+                Q[a][b] = (a <= b && b < nb) ? Q[a][b] * cnorm[b] : 0.0;
+            }
         }
         __syncthreads();
-        if (tid < L) {                                 // x^T R = yn^T  (forward substitution per row)
+        if (tid < L) {                                 // x = yn R^-1: 16 independent chains, no divide
             double xr[B];
 #pragma unroll
-            for (int c = 0; c < B; ++c) {
-                if (c < nb) {
-                    double v = Y[tid * B + c];
-                    for (int m2 = 0; m2 < c; ++m2) v -= xr[m2] * Q[m2][c];
-                    xr[c] = v / Q[c][c];
-                } else xr[c] = 0.0;
+            for (int c = 0; c < B; ++c) xr[c] = 0.0;
+            for (int m2 = 0; m2 < nb; ++m2) {
+                const double v = Y[tid * B + m2];
+#pragma unroll
+                for (int c = 0; c < B; ++c) xr[c] = fma(v, Q[m2][c], xr[c]);
             }
 #pragma unroll
             for (int c = 0; c < B; ++c) X[tid * B + c] = xr[c];
@@ -202,10 +242,18 @@ annular_weights_kernel(AnnularArgs p) {
         // ---- Rayleigh-Ritz: T = X^T Y (symmetrised), eig via one-sided Jacobi
         for (int e = tid; e < B * B; e += AT) {
             const int a = e / B, b = e % B;
-            double s = 0.0;
-            if (a < nb && b < nb)
-                for (int i = 0; i < L; ++i) s = fma(X[i * B + a], Y[i * B + b], s);
-            Q[a][b] = s;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            if (a < nb && b < nb) {
+                int i = 0;
+                for (; i + 3 < L; i += 4) {
+                    s0 = fma(X[i * B + a], Y[i * B + b], s0);
+                    s1 = fma(X[(i + 1) * B + a], Y[(i + 1) * B + b], s1);
+                    s2 = fma(X[(i + 2) * B + a], Y[(i + 2) * B + b], s2);
+                    s3 = fma(X[(i + 3) * B + a], Y[(i + 3) * B + b], s3);
+                }
+                for (; i < L; ++i) s0 = fma(X[i * B + a], Y[i * B + b], s0);
+            }
+            Q[a][b] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
         for (int e = tid; e < B * B; e += AT) {
@@ -263,9 +311,26 @@ annular_weights_kernel(AnnularArgs p) {
             double worst = 0.0;
             for (int r = 0; r < k; ++r) worst = fmax(worst, sqrt(cres[r]));
             const double ref = theta[order[k - 1]];
-            done = (worst <= p.tol * ref) || (nb == L);   // a full-width block is exact after one step
+            int dn = (worst <= p.tol * ref) || (nb == L);   // a full-width block is exact after one step
+            // Hopeless cases leave early (BASELINE config 3: in 5 of 8 annuli the spectra are flat, every problem ran
+            // all max_iter iterations -- 13 ms per annulus -- only to be solved again by the direct solver): the
+            // progress over the last 4 iterations predicts the iterations still needed.
+            if (!dn && (it & 3) == 0) {
+                if (it >= 8 && hist > 0.0) {
+                    const double r4 = worst / hist;
+                    if (!(r4 < 1.0)) dn = 2;
+                    else if (worst > 0.0 && ref > 0.0 &&
+                             (double)it + 4.0 * log(p.tol * ref / worst) / log(r4) > (double)p.max_iter) dn = 2;
+                }
+                hist = worst;
+            }
+            done = dn;
         }
         __syncthreads();
+        if (done == 2) {                                   // left to the direct solver
+            if (tid == 0) p.iters[q] = -it;
+            return;
+        }
         converged = done != 0;
         if (converged || it >= p.max_iter) {
             // X already holds the Ritz vectors (orthonormal up to the residual); finish below
@@ -377,10 +442,7 @@ __device__ __forceinline__ double block_sum_256(double v, double* red) {
     return t;
 }
 
-__global__ void __launch_bounds__(AT)
-annular_direct_kernel(AnnularArgs p, const int* __restrict__ plist, double* __restrict__ ws) {
-    extern __shared__ double sm[];
-    const int q = plist[blockIdx.x];
+__device__ void annular_direct_one(const AnnularArgs& p, int q, double* __restrict__ ws, double* sm) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = p.len[q];
     const int f = p.frame[q];
@@ -453,10 +515,17 @@ annular_direct_kernel(AnnularArgs p, const int* __restrict__ plist, double* __re
         // p = tau * A22 v   (A22 symmetric: column i of A22 read as row-major rows l, coalesced over i)
         const double* A22 = A + (size_t)(j + 1) * L + (j + 1);
         if (tid < m) {
-            double acc = 0.0;
-#pragma unroll 8
-            for (int l = 0; l < m; ++l) acc = fma(A22[(size_t)l * L + tid], vv[l], acc);
-            pp[tid] = tj * acc;
+            // four independent chains: a dependent DFMA costs 9 cycles on this part (fp64_lat.cu)
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int l = 0;
+            for (; l + 3 < m; l += 4) {
+                a0 = fma(A22[(size_t)l * L + tid], vv[l], a0);
+                a1 = fma(A22[(size_t)(l + 1) * L + tid], vv[l + 1], a1);
+                a2 = fma(A22[(size_t)(l + 2) * L + tid], vv[l + 2], a2);
+                a3 = fma(A22[(size_t)(l + 3) * L + tid], vv[l + 3], a3);
+            }
+            for (; l < m; ++l) a0 = fma(A22[(size_t)l * L + tid], vv[l], a0);
+            pp[tid] = tj * ((a0 + a1) + (a2 + a3));
         }
         __syncthreads();
         double pv = (tid < m) ? pp[tid] * vv[tid] : 0.0;
@@ -709,6 +778,24 @@ annular_direct_kernel(AnnularArgs p, const int* __restrict__ plist, double* __re
     if (tid == 0) p.iters[q] = 100000;      // marker: solved directly
 }
 
+// Persistent launch: three CTAs per SM (the register limit) work through the problem list, each with ONE workspace
+// slot, so the workspace is 444 x Lmax^2 doubles whatever the number of problems.  The solver is bound by the LATENCY
+// of its global workspace (ncu, BASELINE config 3: 64 MB of trailing-matrix traffic per 200-frame problem, long
+// scoreboard 20 and barrier 18 stalls per issue, 13 % issue-active): two CTAs per SM -- whose 95 MB of workspaces
+// would stay L2-resident -- ran 25 % SLOWER than three (157 vs 126 ms per config-3 call), i.e. concurrency, not DRAM
+// bandwidth, is what it lacks; the fix is a packed-symmetric matrix resident in shared memory (160 KB at L = 200).
+__global__ void __launch_bounds__(AT)
+annular_direct_kernel(AnnularArgs p, const int* __restrict__ plist, int nlist, double* __restrict__ ws) {
+    extern __shared__ double sm[];
+    for (int i = blockIdx.x; i < nlist; i += gridDim.x) {
+        annular_direct_one(p, plist[i], ws, sm);
+        __syncthreads();
+    }
+}
+
+
+int annular_direct_slots() { return 3 * kNumSMs; }      // workspace slots (= CTAs) of one launch: nslots * Lmax^2 doubles
+
 size_t annular_direct_smem_bytes(int k, int Lmax) {
     return ((size_t)5 * Lmax + 16 + 96 + (size_t)4 * k * Lmax) * sizeof(double) + ((size_t)AT + Lmax) * sizeof(int) + 16;
 }
@@ -744,7 +831,8 @@ int annular_direct(const AnnularArgs& a, const int* plist, int nlist, double* ws
     const size_t smem = annular_direct_smem_bytes(a.ncomp, a.Lmax);
     VB_REQUIRE(smem <= 220 * 1024, "annular_direct: %zu bytes of shared memory needed", smem);
     VB_CHECK_CUDA(cudaFuncSetAttribute(annular_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    annular_direct_kernel<<<nlist, AT, smem, st>>>(a, plist, ws);
+    const int grid = nlist < annular_direct_slots() ? nlist : annular_direct_slots();
+    annular_direct_kernel<<<grid, AT, smem, st>>>(a, plist, nlist, ws);
     VB_CHECK_LAUNCH();
     return 0;
 }
