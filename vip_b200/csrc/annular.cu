@@ -442,6 +442,28 @@ __device__ __forceinline__ double block_sum_256(double v, double* red) {
     return t;
 }
 
+// fp64 reciprocal from the 20-bit hardware seed and two Newton steps (4 dependent DFMA): ~70 cycles of latency
+// against 126 for the IEEE divide (tools/microbench/fp64_lat.cu); relative error ~1e-16 for NORMAL arguments, which
+// is all the Sturm recurrence and the pivots below feed it (|q| >= pivmin >= the smallest normal number).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// PACKED = true (round 2): the matrix lives in SHARED memory as its column-packed lower triangle (element (r, c),
+// r >= c, at c L - c (c - 1) / 2 + r - c: L (L + 1) / 2 doubles, 161 KB at L = 200; the trailing matrix of every
+// Householder step is again a packed triangle and reflector j -- column j below the diagonal -- is contiguous),
+// the eigenvectors Z stay in shared memory and only the LU factors of the inverse iteration (written once, read once
+// per round, off the dependency chain) go to the CTA's global slot.  With the full matrix in a global workspace
+// (PACKED = false: libraries too large for shared memory) the Householder steps move 64 MB of trailing-matrix traffic
+// per 200-frame problem through L2 / DRAM and the kernel idles on it (ncu, BASELINE config 3: long-scoreboard 20 and
+// barrier 18 stalls per issue, 13 % issue-active, 27 ms per 1000 problems).
+template <bool PACKED>
 __device__ void annular_direct_one(const AnnularArgs& p, int q, double* __restrict__ ws, double* sm) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = p.len[q];
@@ -450,7 +472,7 @@ __device__ void annular_direct_one(const AnnularArgs& p, int q, double* __restri
     const int* I = p.idx + (size_t)q * Lmax;
     if (L <= 0) { if (tid == 0) p.iters[q] = 0; return; }
     const int k = (p.ncomp < L) ? p.ncomp : L;
-    double* A = ws + (size_t)blockIdx.x * Lmax * Lmax;     // L x L, ld = L
+    double* slot = ws + (size_t)blockIdx.x * Lmax * Lmax;  // global workspace slot of this CTA (Lmax^2 doubles)
 
     // shared layout
     double* d = sm;                       // [Lmax]
@@ -463,85 +485,195 @@ __device__ void annular_direct_one(const AnnularArgs& p, int q, double* __restri
     double* lam = scal + 8;               // [32]
     double* blo = lam + 32;               // [32]
     double* bhi = blo + 32;               // [32]
-    double* Z = bhi + 32;                 // [k][Lmax]
-    double* U0 = Z + (size_t)p.ncomp * Lmax;
+    double* Z = bhi + 32;                 // [ncomp][Lmax]
+    // PACKED: A = packed lower triangle in shared memory behind Z, U0..U2 in the global slot (3 k Lmax <= Lmax^2,
+    //         checked by the launcher); else: A = full matrix in the global slot, U0..U2 in shared memory
+    double* zend = Z + (size_t)p.ncomp * Lmax;
+    double* A = PACKED ? zend : slot;
+    double* U0 = PACKED ? slot : zend;
     double* U1 = U0 + (size_t)p.ncomp * Lmax;
     double* U2 = U1 + (size_t)p.ncomp * Lmax;
-    int* cnt = reinterpret_cast<int*>(U2 + (size_t)p.ncomp * Lmax);   // [AT]
+    int* cnt = reinterpret_cast<int*>(PACKED ? A + ((size_t)Lmax * (Lmax + 1) / 2) : U2 + (size_t)p.ncomp * Lmax);   // [AT]
     int* Is = cnt + AT;                   // [Lmax]
 
     for (int i = tid; i < L; i += AT) Is[i] = I[i];
     __syncthreads();
-    for (int el = tid; el < L * L; el += AT) {
-        const int i = el / L, j = el % L;
-        A[el] = __ldg(p.G + (size_t)Is[i] * n + Is[j]);
+    if (PACKED) {
+        // column c of the triangle = G[I[c..L-1], I[c]] (symmetric: read as the row I[c], ascending indices)
+        for (int c = warp; c < L; c += AT / 32) {
+            const double* grow = p.G + (size_t)Is[c] * n;
+            double* col = A + (size_t)c * L - (size_t)c * (c - 1) / 2 - c;      // col[r] = A(r, c)
+            for (int r = c + lane; r < L; r += 32) col[r] = __ldg(grow + Is[r]);
+        }
+    } else {
+        for (int el = tid; el < L * L; el += AT) {
+            const int i = el / L, j = el % L;
+            A[el] = __ldg(p.G + (size_t)Is[i] * n + Is[j]);
+        }
     }
     __syncthreads();
 
-    // ---- Householder tridiagonalisation (both triangles kept up to date; reflector j stored in row j)
-    for (int j = 0; j < L - 1; ++j) {
-        const int m = L - 1 - j;
-        double* x = A + (size_t)j * L + (j + 1);
-        double part = 0.0;
-        for (int i = 1 + tid; i < m; i += AT) part = fma(x[i], x[i], part);
-        const double sigma = block_sum_256(part, red);
-        if (tid == 0) {
-            const double alpha = x[0];
-            d[j] = A[(size_t)j * L + j];
-            if (sigma == 0.0) {
-                tau[j] = 0.0; e[j] = alpha; scal[0] = 0.0; scal[1] = 0.0;
-            } else {
-                const double beta = -copysign(sqrt(alpha * alpha + sigma), alpha);
-                tau[j] = (beta - alpha) / beta;
-                e[j] = beta;
-                scal[0] = tau[j];
-                scal[1] = 1.0 / (alpha - beta);
+    // ---- Householder tridiagonalisation
+    if (PACKED) {
+        for (int j = 0; j < L - 1; ++j) {
+            const int m = L - 1 - j;
+            double* cj = A + (size_t)j * L - (size_t)j * (j - 1) / 2;      // column j: cj[0] = A(j, j), cj[1 + i] = x[i]
+            double* x = cj + 1;
+            double part = 0.0;
+            for (int i = 1 + tid; i < m; i += AT) part = fma(x[i], x[i], part);
+            const double sigma = block_sum_256(part, red);
+            if (tid == 0) {
+                const double alpha = x[0];
+                d[j] = cj[0];
+                if (sigma == 0.0) {
+                    tau[j] = 0.0; e[j] = alpha; scal[0] = 0.0; scal[1] = 0.0;
+                } else {
+                    const double beta = -copysign(sqrt(alpha * alpha + sigma), alpha);
+                    tau[j] = (beta - alpha) / beta;
+                    e[j] = beta;
+                    scal[0] = tau[j];
+                    scal[1] = 1.0 / (alpha - beta);
+                }
             }
-        }
-        __syncthreads();
-        const double tj = scal[0];
-        if (tj == 0.0) {            // nothing to eliminate: v = e_1
-            if (tid == 0) x[0] = 1.0;
             __syncthreads();
-            continue;
-        }
-        const double scale = scal[1];
-        for (int i = tid; i < m; i += AT) {
-            const double v = (i == 0) ? 1.0 : x[i] * scale;
-            vv[i] = v;
-            x[i] = v;
-        }
-        __syncthreads();
-        // p = tau * A22 v   (A22 symmetric: column i of A22 read as row-major rows l, coalesced over i)
-        const double* A22 = A + (size_t)(j + 1) * L + (j + 1);
-        if (tid < m) {
-            // four independent chains: a dependent DFMA costs 9 cycles on this part (fp64_lat.cu)
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int l = 0;
-            for (; l + 3 < m; l += 4) {
-                a0 = fma(A22[(size_t)l * L + tid], vv[l], a0);
-                a1 = fma(A22[(size_t)(l + 1) * L + tid], vv[l + 1], a1);
-                a2 = fma(A22[(size_t)(l + 2) * L + tid], vv[l + 2], a2);
-                a3 = fma(A22[(size_t)(l + 3) * L + tid], vv[l + 3], a3);
+            const double tj = scal[0];
+            if (tj == 0.0) {            // nothing to eliminate: v = e_1
+                if (tid == 0) x[0] = 1.0;
+                __syncthreads();
+                continue;
             }
-            for (; l < m; ++l) a0 = fma(A22[(size_t)l * L + tid], vv[l], a0);
-            pp[tid] = tj * ((a0 + a1) + (a2 + a3));
+            const double scale = scal[1];
+            for (int i = tid; i < m; i += AT) {
+                const double v = (i == 0) ? 1.0 : x[i] * scale;
+                vv[i] = v;
+                x[i] = v;
+            }
+            __syncthreads();
+            // trailing matrix B (m x m) = packed triangle behind column j: B(r, c) at c m - c (c - 1) / 2 + r - c
+            double* B = cj + (m + 1);
+            // p = tau * B v: thread i owns row i.  l <= i: B(i, l) sits i - l behind the head of column l (consecutive
+            // threads, consecutive words); l > i: B(l, i) inside the thread's own column i.
+            if (tid < m) {
+                const int i = tid;
+                const double* own = B + (size_t)i * m - (size_t)i * (i - 1) / 2 - i;    // own[l] = B(l, i), l >= i
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // four chains: a dependent DFMA costs 9 cycles
+                int head = i;                       // index of B(i, l) for the running l <= i: cb(l) + i - l
+                int l = 0;
+                for (; l + 3 < m; l += 4) {
+                    const double b0 = (l <= i) ? B[head] : own[l];
+                    head += m - 1 - l;
+                    const double b1 = (l + 1 <= i) ? B[head] : own[l + 1];
+                    head += m - 2 - l;
+                    const double b2 = (l + 2 <= i) ? B[head] : own[l + 2];
+                    head += m - 3 - l;
+                    const double b3 = (l + 3 <= i) ? B[head] : own[l + 3];
+                    head += m - 4 - l;
+                    a0 = fma(b0, vv[l], a0);
+                    a1 = fma(b1, vv[l + 1], a1);
+                    a2 = fma(b2, vv[l + 2], a2);
+                    a3 = fma(b3, vv[l + 3], a3);
+                }
+                for (; l < m; ++l) {
+                    a0 = fma((l <= i) ? B[head] : own[l], vv[l], a0);
+                    head += m - 1 - l;
+                }
+                pp[i] = tj * ((a0 + a1) + (a2 + a3));
+            }
+            __syncthreads();
+            double pv = (tid < m) ? pp[tid] * vv[tid] : 0.0;
+            const double K = -0.5 * tj * block_sum_256(pv, red);
+            if (tid < m) pp[tid] = fma(K, vv[tid], pp[tid]);      // w
+            __syncthreads();
+            // B -= v w^T + w v^T on the triangle, in 32 x 32 tiles dealt round-robin to the warps (row-indexed
+            // lanes: conflict-free; the tiles balance the triangular work over the warps)
+            {
+                const int nrb = (m + 31) >> 5;
+                int item = 0;
+                for (int rb = 0; rb < nrb; ++rb) {
+                    const int r = (rb << 5) + lane;
+                    for (int cbk = 0; cbk <= rb; ++cbk, ++item) {
+                        if ((item & (AT / 32 - 1)) != warp || r >= m) continue;
+                        const double wr = pp[r], vr = vv[r];
+                        const int c0 = cbk << 5;
+                        const int c1 = min(c0 + 31, r);
+                        double* el = B + (size_t)c0 * m - (size_t)c0 * (c0 - 1) / 2 + (r - c0);
+                        for (int c = c0; c <= c1; ++c) {
+                            *el -= fma(vv[c], wr, pp[c] * vr);
+                            el += m - 1 - c;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
         }
+        if (tid == 0) { d[L - 1] = A[(size_t)(L - 1) * L - (size_t)(L - 1) * (L - 2) / 2]; e[L - 1] = 0.0; tau[L - 1] = 0.0; }
         __syncthreads();
-        double pv = (tid < m) ? pp[tid] * vv[tid] : 0.0;
-        const double K = -0.5 * tj * block_sum_256(pv, red);
-        if (tid < m) pp[tid] = fma(K, vv[tid], pp[tid]);      // w
-        __syncthreads();
-        if (tid < m) {
-            const double wi = pp[tid], vi = vv[tid];
-            double* col = A + (size_t)(j + 1) * L + (j + 1) + tid;
-#pragma unroll 8
-            for (int l = 0; l < m; ++l) col[(size_t)l * L] -= vv[l] * wi + pp[l] * vi;
+    } else {
+        // ---- Householder tridiagonalisation (both triangles kept up to date; reflector j stored in row j)
+        for (int j = 0; j < L - 1; ++j) {
+            const int m = L - 1 - j;
+            double* x = A + (size_t)j * L + (j + 1);
+            double part = 0.0;
+            for (int i = 1 + tid; i < m; i += AT) part = fma(x[i], x[i], part);
+            const double sigma = block_sum_256(part, red);
+            if (tid == 0) {
+                const double alpha = x[0];
+                d[j] = A[(size_t)j * L + j];
+                if (sigma == 0.0) {
+                    tau[j] = 0.0; e[j] = alpha; scal[0] = 0.0; scal[1] = 0.0;
+                } else {
+                    const double beta = -copysign(sqrt(alpha * alpha + sigma), alpha);
+                    tau[j] = (beta - alpha) / beta;
+                    e[j] = beta;
+                    scal[0] = tau[j];
+                    scal[1] = 1.0 / (alpha - beta);
+                }
+            }
+            __syncthreads();
+            const double tj = scal[0];
+            if (tj == 0.0) {            // nothing to eliminate: v = e_1
+                if (tid == 0) x[0] = 1.0;
+                __syncthreads();
+                continue;
+            }
+            const double scale = scal[1];
+            for (int i = tid; i < m; i += AT) {
+                const double v = (i == 0) ? 1.0 : x[i] * scale;
+                vv[i] = v;
+                x[i] = v;
+            }
+            __syncthreads();
+            // p = tau * A22 v   (A22 symmetric: column i of A22 read as row-major rows l, coalesced over i)
+            const double* A22 = A + (size_t)(j + 1) * L + (j + 1);
+            if (tid < m) {
+                // four independent chains: a dependent DFMA costs 9 cycles on this part (fp64_lat.cu)
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int l = 0;
+                for (; l + 3 < m; l += 4) {
+                    a0 = fma(A22[(size_t)l * L + tid], vv[l], a0);
+                    a1 = fma(A22[(size_t)(l + 1) * L + tid], vv[l + 1], a1);
+                    a2 = fma(A22[(size_t)(l + 2) * L + tid], vv[l + 2], a2);
+                    a3 = fma(A22[(size_t)(l + 3) * L + tid], vv[l + 3], a3);
+                }
+                for (; l < m; ++l) a0 = fma(A22[(size_t)l * L + tid], vv[l], a0);
+                pp[tid] = tj * ((a0 + a1) + (a2 + a3));
+            }
+            __syncthreads();
+            double pv = (tid < m) ? pp[tid] * vv[tid] : 0.0;
+            const double K = -0.5 * tj * block_sum_256(pv, red);
+            if (tid < m) pp[tid] = fma(K, vv[tid], pp[tid]);      // w
+            __syncthreads();
+            if (tid < m) {
+                const double wi = pp[tid], vi = vv[tid];
+                double* col = A + (size_t)(j + 1) * L + (j + 1) + tid;
+    #pragma unroll 8
+                for (int l = 0; l < m; ++l) col[(size_t)l * L] -= vv[l] * wi + pp[l] * vi;
+            }
+            __syncthreads();
         }
+        if (tid == 0) { d[L - 1] = A[(size_t)(L - 1) * L + (L - 1)]; e[L - 1] = 0.0; tau[L - 1] = 0.0; }
         __syncthreads();
     }
-    if (tid == 0) { d[L - 1] = A[(size_t)(L - 1) * L + (L - 1)]; e[L - 1] = 0.0; tau[L - 1] = 0.0; }
-    __syncthreads();
 
     // ---- k largest eigenvalues of the tridiagonal: multisection with Sturm counts
     {
@@ -585,7 +717,7 @@ __device__ void annular_direct_one(const AnnularArgs& p, int q, double* __restri
             if (fabs(qv) < pivmin) qv = -pivmin;
             c = qv < 0.0;
             for (int i = 1; i < L; ++i) {
-                qv = d[i] - xs - e[i - 1] * e[i - 1] / qv;
+                qv = fma(-e[i - 1] * e[i - 1], fast_rcp(qv), d[i] - xs);
                 if (fabs(qv) < pivmin) qv = -pivmin;
                 c += qv < 0.0;
             }
@@ -627,43 +759,79 @@ __device__ void annular_direct_one(const AnnularArgs& p, int q, double* __restri
     for (int round = 0; round < 3; ++round) {
         if (tid < k) {
             const int r = tid;
-            double* u0 = U0 + (size_t)r * Lmax;
-            double* u1 = U1 + (size_t)r * Lmax;
-            double* u2 = U2 + (size_t)r * Lmax;
+            // factors of row i: UF[(3 i + {0, 1, 2}) K + r] = {1 / pivot, first, second super-diagonal}: the k active
+            // threads write and read consecutive words; the reads of the back substitution do not depend on its
+            // chain and are fetched PF rows ahead (PACKED: they come from the global slot)
+            const int K = p.ncomp;
+            double* UF = U0 + r;
             double* b = Z + (size_t)r * Lmax;
             const double lr = lam[r];
             // Gaussian elimination with partial pivoting of (T - lr I); sub-diagonal of row i+1 is e[i]
             double diag = d[0] - lr;              // current pivot-row candidates
             double sup = (L > 1) ? e[0] : 0.0;
+            double bi = b[0];
             for (int i = 0; i < L - 1; ++i) {
+                const double bn = b[i + 1];
                 const double sub = e[i];
                 const double nd = d[i + 1] - lr;                    // next row: [sub, nd, e[i+1]]
                 const double ns = (i + 2 < L) ? e[i + 1] : 0.0;
-                if (fabs(diag) >= fabs(sub)) {
-                    const double piv = (diag != 0.0) ? diag : 1e-300;
-                    const double mlt = sub / piv;
-                    u0[i] = piv; u1[i] = sup; u2[i] = 0.0;
-                    b[i + 1] -= mlt * b[i];
-                    diag = nd - mlt * sup;
+                double* uf = UF + (size_t)3 * i * K;
+                if (fabs(diag) >= fabs(sub) || fabs(sub) < 1e-300) {
+                    const double piv = (fabs(diag) >= 1e-300) ? diag : copysign(1e-300, diag);
+                    const double rinv = fast_rcp(piv);
+                    const double mlt = sub * rinv;
+                    uf[0] = rinv; uf[K] = sup; uf[2 * K] = 0.0;
+                    b[i] = bi;
+                    bi = fma(-mlt, bi, bn);
+                    diag = fma(-mlt, sup, nd);
                     sup = ns;
                 } else {
-                    const double mlt = diag / sub;
-                    u0[i] = sub; u1[i] = nd; u2[i] = ns;
-                    const double bi = b[i];
-                    b[i] = b[i + 1];
-                    b[i + 1] = bi - mlt * b[i + 1];
-                    diag = sup - mlt * nd;
+                    const double rinv = fast_rcp(sub);              // |sub| > |diag| >= 0: a normal number here
+                    const double mlt = diag * rinv;
+                    uf[0] = rinv; uf[K] = nd; uf[2 * K] = ns;
+                    b[i] = bn;
+                    bi = fma(-mlt, bn, bi);
+                    diag = fma(-mlt, nd, sup);
                     sup = -mlt * ns;
                 }
             }
-            u0[L - 1] = (diag != 0.0) ? diag : 1e-300;
-            // back substitution
-            b[L - 1] = b[L - 1] / u0[L - 1];
-            if (L > 1) b[L - 2] = (b[L - 2] - u1[L - 2] * b[L - 1]) / u0[L - 2];
-            for (int i = L - 3; i >= 0; --i) b[i] = (b[i] - u1[i] * b[i + 1] - u2[i] * b[i + 2]) / u0[i];
+            {
+                double* uf = UF + (size_t)3 * (L - 1) * K;
+                const double piv = (fabs(diag) >= 1e-300) ? diag : copysign(1e-300, diag);
+                uf[0] = fast_rcp(piv); uf[K] = 0.0; uf[2 * K] = 0.0;
+                b[L - 1] = bi;
+            }
+            // back substitution  b[i] = (b[i] - u1[i] b[i+1] - u2[i] b[i+2]) / u0[i], running maximum for the scaling
+            constexpr int PF = 4;
+            double q0[PF], q1[PF], q2[PF];
+#pragma unroll
+            for (int t = 0; t < PF; ++t) {
+                const int i = L - 1 - t;
+                const double* uf = UF + (size_t)3 * (i < 0 ? 0 : i) * K;
+                q0[t] = uf[0]; q1[t] = uf[K]; q2[t] = uf[2 * K];
+            }
+            double x1 = 0.0, x2 = 0.0, mx = 0.0;
+            for (int i0 = L - 1; i0 >= 0; i0 -= PF) {
+                double n0[PF], n1[PF], n2[PF];
+#pragma unroll
+                for (int t = 0; t < PF; ++t) {
+                    const int i = i0 - PF - t;
+                    const double* uf = UF + (size_t)3 * (i < 0 ? 0 : i) * K;
+                    n0[t] = uf[0]; n1[t] = uf[K]; n2[t] = uf[2 * K];
+                }
+#pragma unroll
+                for (int t = 0; t < PF; ++t) {
+                    const int i = i0 - t;
+                    if (i >= 0) {
+                        const double xi = fma(-q2[t], x2, fma(-q1[t], x1, b[i])) * q0[t];
+                        b[i] = xi;
+                        mx = fmax(mx, fabs(xi));
+                        x2 = x1; x1 = xi;
+                    }
+                    q0[t] = n0[t]; q1[t] = n1[t]; q2[t] = n2[t];
+                }
+            }
             // scale to avoid overflow in the next round
-            double mx = 0.0;
-            for (int i = 0; i < L; ++i) mx = fmax(mx, fabs(b[i]));
             const double inv = (mx > 0.0) ? 1.0 / mx : 1.0;
             for (int i = 0; i < L; ++i) b[i] *= inv;
         }
@@ -697,7 +865,7 @@ __device__ void annular_direct_one(const AnnularArgs& p, int q, double* __restri
             const double tj = tau[j];
             if (tj == 0.0) continue;
             const int m = L - 1 - j;
-            const double* v = A + (size_t)j * L + (j + 1);
+            const double* v = PACKED ? A + (size_t)j * L - (size_t)j * (j - 1) / 2 + 1 : A + (size_t)j * L + (j + 1);
             double dt = 0.0;
             for (int i = lane; i < m; i += 32) dt = fma(v[i], z[j + 1 + i], dt);
             dt = warp_sum(dt) * tj;
@@ -778,26 +946,30 @@ __device__ void annular_direct_one(const AnnularArgs& p, int q, double* __restri
     if (tid == 0) p.iters[q] = 100000;      // marker: solved directly
 }
 
-// Persistent launch: three CTAs per SM (the register limit) work through the problem list, each with ONE workspace
-// slot, so the workspace is 444 x Lmax^2 doubles whatever the number of problems.  The solver is bound by the LATENCY
-// of its global workspace (ncu, BASELINE config 3: 64 MB of trailing-matrix traffic per 200-frame problem, long
-// scoreboard 20 and barrier 18 stalls per issue, 13 % issue-active): two CTAs per SM -- whose 95 MB of workspaces
-// would stay L2-resident -- ran 25 % SLOWER than three (157 vs 126 ms per config-3 call), i.e. concurrency, not DRAM
-// bandwidth, is what it lacks; the fix is a packed-symmetric matrix resident in shared memory (160 KB at L = 200).
-__global__ void __launch_bounds__(AT)
+// Persistent launch: the CTAs work through the problem list, each with ONE workspace slot (Lmax^2 doubles), so the
+// workspace is bounded whatever the number of problems.  PACKED = false (matrix in the global slot) is bound by the
+// LATENCY of that workspace (ncu, BASELINE config 3: 64 MB of trailing-matrix traffic per 200-frame problem, long
+// scoreboard 20 and barrier 18 stalls per issue, 13 % issue-active; two CTAs per SM -- whose 95 MB of workspaces would
+// stay L2-resident -- ran 25 % SLOWER than three, i.e. concurrency, not DRAM bandwidth, is what it lacks);
+// PACKED = true keeps the matrix in shared memory (one CTA per SM at Lmax = 200, more for smaller libraries).
+template <bool PACKED>
+__global__ void __launch_bounds__(AT, PACKED ? 1 : 3)
 annular_direct_kernel(AnnularArgs p, const int* __restrict__ plist, int nlist, double* __restrict__ ws) {
     extern __shared__ double sm[];
     for (int i = blockIdx.x; i < nlist; i += gridDim.x) {
-        annular_direct_one(p, plist[i], ws, sm);
+        annular_direct_one<PACKED>(p, plist[i], ws, sm);
         __syncthreads();
     }
 }
 
-
-int annular_direct_slots() { return 3 * kNumSMs; }      // workspace slots (= CTAs) of one launch: nslots * Lmax^2 doubles
+int annular_direct_slots() { return 3 * kNumSMs; }      // upper bound of the workspace slots (= CTAs) of one launch
 
 size_t annular_direct_smem_bytes(int k, int Lmax) {
     return ((size_t)5 * Lmax + 16 + 96 + (size_t)4 * k * Lmax) * sizeof(double) + ((size_t)AT + Lmax) * sizeof(int) + 16;
+}
+size_t annular_direct_packed_smem_bytes(int k, int Lmax) {
+    return ((size_t)5 * Lmax + 16 + 96 + (size_t)k * Lmax + (size_t)Lmax * (Lmax + 1) / 2) * sizeof(double) +
+           ((size_t)AT + Lmax) * sizeof(int) + 16;
 }
 
 int annular_direct(const AnnularArgs& a, const int* plist, int nlist, double* ws, cudaStream_t st);
@@ -824,15 +996,29 @@ int annular_auto_weights(const double* G, const double* Gt, int n, const int* id
     return annular_direct(a, plist, nlist, ws, st);
 }
 
-// Solve the problems listed in plist (device, nlist entries) directly.  ws: nlist * Lmax^2 doubles.
+// Solve the problems listed in plist (device, nlist entries) directly.  ws: min(nlist, annular_direct_slots()) * Lmax^2
+// doubles.
+static int direct_mode() {       // VIP_B200_ANNULAR_DIRECT: 0 = matrix in the global slot (round 1), 1 = packed (default)
+    static const int v = [] { const char* e = getenv("VIP_B200_ANNULAR_DIRECT"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
 int annular_direct(const AnnularArgs& a, const int* plist, int nlist, double* ws, cudaStream_t st) {
     VB_REQUIRE(a.ncomp <= 24 && a.ncomp >= 1, "annular_direct: ncomp must be in 1..24");
     VB_REQUIRE(a.Lmax <= AT, "annular_direct: library too large");
-    const size_t smem = annular_direct_smem_bytes(a.ncomp, a.Lmax);
+    const size_t smem_p = annular_direct_packed_smem_bytes(a.ncomp, a.Lmax);
+    // packed: shared memory must hold the triangle and the slot the 3 k Lmax LU factors
+    const bool packed = direct_mode() != 0 && smem_p <= 220 * 1024 && 3 * a.ncomp <= a.Lmax;
+    const size_t smem = packed ? smem_p : annular_direct_smem_bytes(a.ncomp, a.Lmax);
     VB_REQUIRE(smem <= 220 * 1024, "annular_direct: %zu bytes of shared memory needed", smem);
-    VB_CHECK_CUDA(cudaFuncSetAttribute(annular_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = nlist < annular_direct_slots() ? nlist : annular_direct_slots();
-    annular_direct_kernel<<<grid, AT, smem, st>>>(a, plist, nlist, ws);
+    auto kern = packed ? annular_direct_kernel<true> : annular_direct_kernel<false>;
+    VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    VB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, AT, smem));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
+    const int slots = per_sm * kNumSMs;
+    const int grid = nlist < slots ? nlist : slots;
+    kern<<<grid, AT, smem, st>>>(a, plist, nlist, ws);
     VB_CHECK_LAUNCH();
     return 0;
 }
