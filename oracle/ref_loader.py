@@ -57,7 +57,10 @@ class _CircularAperture:
     """Stand-in for ``photutils.aperture.CircularAperture`` (positions as (x, y) pairs, radius r)."""
 
     def __init__(self, positions, r):
-        self.positions = [tuple(p) for p in positions]
+        import numpy as np
+        pos = np.asarray(positions if isinstance(positions, np.ndarray) else list(positions), dtype=float)
+        self.scalar = pos.ndim == 1                      # photutils also takes ONE (x, y) pair (frame_report)
+        self.positions = [tuple(p) for p in np.atleast_2d(pos)]
         self.r = float(r)
 
 

@@ -386,3 +386,62 @@ def test_pca_annular_left_eigv_vs_oracle(vb):
         assert rel_err(r[2], o[2]) < 3e-4, kw
     with pytest.raises(NotImplementedError):
         vb.pca_annular(cube, angs, left_eigv=True, ncomp="auto", verbose=False)
+
+
+def _ifs_small():
+    from tools.make_golden import ifs_cube
+    cube, angs, sl = ifs_cube(z=5, n=10, size=24, seed=43)
+    cref = ifs_cube(z=5, n=6, size=24, seed=47)[0]
+    return cube, angs, sl, cref
+
+
+def test_pca_adimsdi_fullframe_options(vb):
+    """Full-frame ADI+mSDI options added in the second half of round 2, against the oracle restatements that are
+    pinned bit-identically to the unmodified reference (tests/test_oracle_vs_reference.py): reference cube in both
+    modes, PA-rejection second pass (``source_xy``) with ``cube_sig``, single-pass PCA grid with / without
+    ``source_xy``.  Tolerance as for the other mSDI tests: 5e-6 * max|cube| (fp32 pipeline vs float64 reference)."""
+    cube, angs, sl, cref = _ifs_small()
+    tol = 5e-6 * float(np.max(np.abs(cube)))
+    kw = dict(scale_list=sl, verbose=False)
+    err = lambda a, b: float(np.max(np.abs(np.asarray(a, dtype=np.float64) - b)))      # noqa: E731
+    # double pass with a reference cube (RSDI): the first-pass frames of the reference come back too
+    fr, rc, rd = vb.pca(cube, angs, cube_ref=cref, adimsdi="double", ncomp=(2, 3), full_output=True, **kw)
+    ofr, orc, ord_ = O.pca_adimsdi_double(cube, angs, sl, (2, 3), cube_ref=cref, full_output=True)
+    assert fr.dtype == np.float64 and rc.shape == orc.shape == (16, 24, 24) and rd.shape == ord_.shape
+    assert err(rc, orc) < tol and err(fr, ofr) < tol
+    with pytest.raises(IndexError):
+        vb.pca(cube, angs, cube_ref=cref, adimsdi="double", ncomp=(2, 3), ref_strategy="ARDI", **kw)
+    # double pass, PA-rejection libraries in the second pass
+    sig = np.zeros(cube.shape[1:], dtype=np.float32)
+    sig[:, 12, 17] = 3.0
+    for extra in (dict(), dict(cube_ref=cref), dict(cube_sig=sig)):
+        opts = dict(source_xy=(17, 12), delta_rot=0.5, fwhm=3, min_frames_pca=2)
+        fr, rc, rd = vb.pca(cube, angs, adimsdi="double", ncomp=(2, 2), full_output=True, **opts, **kw, **extra)
+        ofr, orc, ord_ = O.pca_adimsdi_double(cube, angs, sl, (2, 2), full_output=True, **opts, **extra)
+        m = ~np.isnan(ord_)
+        assert err(rc, orc) < tol and err(rd[m], ord_[m]) < 4 * tol and err(fr, ofr) < 4 * tol, list(extra)
+    # single pass with a reference cube, both strategies
+    for strat, tag in (("RDI", "RSDI"), ("ARDI", "ARSDI")):
+        fr, allfr, desc, resadi = vb.pca(cube, angs, cube_ref=cref, adimsdi="single", ncomp=3, ref_strategy=strat,
+                                         full_output=True, **kw)
+        ofr, oall, odesc, oadi = O.pca_adimsdi_single(cube, angs, sl, 3, cube_ref=cref, ref_strategy=tag,
+                                                      full_output=True)
+        assert allfr.shape == oall.shape and desc.shape == odesc.shape and desc.dtype == np.float32
+        assert err(allfr, oall) < tol and err(resadi, oadi) < tol and err(fr, ofr) < tol, strat
+    # single-pass grid
+    out, pcl = vb.pca(cube, angs, adimsdi="single", ncomp=(1, 3), full_output=True, **kw)
+    oout, opcl = O.pca_adimsdi_single_grid(cube, angs, sl, (1, 3))
+    assert pcl == opcl and out.dtype == np.float64 and out.shape == oout.shape and err(out, oout) < tol
+    out = vb.pca(cube, angs, adimsdi="single", ncomp=[2, 4], ifs_collapse_range=(1, 4), collapse="mean", **kw)
+    assert err(out, O.pca_adimsdi_single_grid(cube, angs, sl, [2, 4], ifs_collapse_range=(1, 4), collapse="mean")[0]) < tol
+    out = vb.pca(cube, angs, adimsdi="single", ncomp=(1, 3), med_of_npcs=True, **kw)
+    assert out.shape == (24, 24) and err(out, np.median(oout, axis=0)) < tol
+    out, best, table = vb.pca(cube, angs, adimsdi="single", ncomp=(1, 3), source_xy=(17, 12), fwhm=3,
+                              full_output=True, **kw)
+    o = O.pca_adimsdi_single_grid(cube, angs, sl, (1, 3), source_xy=(17, 12), fwhm=3)
+    assert err(out, o[0]) < tol and list(table["PCs"]) == o[2]["PCs"]
+    assert np.allclose(table["S/Ns"], o[2]["S/Ns"], rtol=2e-3, atol=2e-4)
+    assert np.allclose(table["fluxes"], o[2]["fluxes"], rtol=1e-4, atol=10 * tol)
+    assert err(best, o[0][int(np.argmax(table["S/Ns"]))]) < tol
+    best2 = vb.pca(cube, angs, adimsdi="single", ncomp=(1, 3), source_xy=(17, 12), fwhm=3, **kw)
+    assert np.array_equal(best, best2)

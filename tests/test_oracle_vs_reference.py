@@ -184,3 +184,56 @@ def test_pca_annular_left_eigv_bit_identical(ref):
         o = O.pca_annular(cube, angs, left_eigv=True, full_output=True, **kw)
         for a, b in zip(r, o):
             np.testing.assert_array_equal(a, b)
+
+
+def _ifs_small():
+    from tools.make_golden import ifs_cube
+    cube, angs, sl = ifs_cube(z=5, n=10, size=24, seed=43)
+    cref = ifs_cube(z=5, n=6, size=24, seed=47)[0]
+    return cube, angs, sl, cref
+
+
+def test_pca_adimsdi_fullframe_options_bit_identical(ref):
+    """Full-frame ADI+mSDI options of round 2 (second half): reference cube in both modes (``pca_fullfr.py:499-510,
+    1099-1119, 1278-1282, 1392-1404``), PA-rejection second pass with ``source_xy`` and ``cube_sig`` (:1407-1460), and
+    the single-pass PCA grid with / without ``source_xy`` (:1205-1236 -> ``utils_pca.py:191-228``)."""
+    psfsub, _ = ref
+    cube, angs, sl, cref = _ifs_small()
+    kw = dict(scale_list=sl, verbose=False)
+    # double pass, RSDI
+    r = psfsub.pca(cube, angs, cube_ref=cref, adimsdi="double", ncomp=(2, 3), full_output=True, **kw)
+    o = O.pca_adimsdi_double(cube, angs, sl, (2, 3), cube_ref=cref, full_output=True)
+    for a, b in zip(r, o):
+        np.testing.assert_array_equal(a, b)
+    # double pass, source_xy (+ reference cube, + cube_sig)
+    sig = np.zeros(cube.shape[1:], dtype=np.float32)
+    sig[:, 12, 17] = 3.0
+    for extra in (dict(), dict(cube_ref=cref), dict(cube_sig=sig)):
+        r = psfsub.pca(cube, angs, adimsdi="double", ncomp=(2, 2), source_xy=(17, 12), delta_rot=0.5, fwhm=3,
+                       min_frames_pca=2, full_output=True, **kw, **extra)
+        o = O.pca_adimsdi_double(cube, angs, sl, (2, 2), source_xy=(17, 12), delta_rot=0.5, fwhm=3, min_frames_pca=2,
+                                 full_output=True, **extra)
+        for a, b in zip(r, o):
+            np.testing.assert_array_equal(a, b)
+    # single pass with a reference cube, both strategies
+    for strat, tag in (("RDI", "RSDI"), ("ARDI", "ARSDI")):
+        r = psfsub.pca(cube, angs, cube_ref=cref, adimsdi="single", ncomp=3, ref_strategy=strat, full_output=True, **kw)
+        o = O.pca_adimsdi_single(cube, angs, sl, 3, cube_ref=cref, ref_strategy=tag, full_output=True)
+        for a, b in zip(r, o):
+            np.testing.assert_array_equal(a, b)
+    # single-pass grid
+    r, pcl = psfsub.pca(cube, angs, adimsdi="single", ncomp=(1, 3), full_output=True, **kw)
+    o, opcl = O.pca_adimsdi_single_grid(cube, angs, sl, (1, 3))
+    assert list(pcl) == list(opcl)
+    np.testing.assert_array_equal(r, o)
+    r = psfsub.pca(cube, angs, adimsdi="single", ncomp=[2, 4], ifs_collapse_range=(1, 4), collapse="mean", **kw)
+    o, _ = O.pca_adimsdi_single_grid(cube, angs, sl, [2, 4], ifs_collapse_range=(1, 4), collapse="mean")
+    np.testing.assert_array_equal(r, o)
+    r = psfsub.pca(cube, angs, adimsdi="single", ncomp=(1, 3), source_xy=(17, 12), fwhm=3, full_output=True, **kw)
+    o = O.pca_adimsdi_single_grid(cube, angs, sl, (1, 3), source_xy=(17, 12), fwhm=3)
+    np.testing.assert_array_equal(r[0], o[0])
+    np.testing.assert_array_equal(r[1], o[1])
+    # the reference averages an OBJECT array (sequential Python sums), the oracle a float array (pairwise): 1 ulp
+    np.testing.assert_allclose(np.asarray(r[2]["S/Ns"], dtype=float), np.asarray(o[2]["S/Ns"], dtype=float), rtol=1e-13)
+    np.testing.assert_allclose(np.asarray(r[2]["fluxes"], dtype=float), np.asarray(o[2]["fluxes"], dtype=float),
+                               rtol=1e-13)

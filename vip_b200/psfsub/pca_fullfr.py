@@ -414,10 +414,12 @@ def _grid_pclist(range_pcs, n):
 
 
 def _pca_grid_device(cube, cube_ref, rot_angles, range_pcs, scaling, mask_center_px, svd_mode, collapse,
-                     weights=None, **rot_options):
+                     weights=None, residual_hook=None, **rot_options):
     """``pca_grid(mode='fullfr', source_xy=None)`` (``utils_pca.py:25-428``) as reached from
     ``_adi_rdi_pca`` (``pca_fullfr.py:1010-1035``): ONE decomposition with max(pclist) components, then
     for every entry of the list the truncated projection/subtraction, derotation and collapse.
+    ``residual_hook`` (ADI+mSDI single pass, ``utils_pca.py:201-223``): maps the residual cube of the z*n rescaled
+    frames to the (n, H, W) cube that is derotated (descaling + collapse over the channels of each ADI frame).
     Returns (cubeout (len(pclist),H,W) device tensor, pclist)."""
     n, y, x = cube.shape
     rot_angles = np.asarray(rot_angles)          # = -angle_list (cube_derotate convention)
@@ -447,11 +449,37 @@ def _pca_grid_device(cube, cube_ref, rot_angles, range_pcs, scaling, mask_center
         Cm = kernels.cross_gram(matrix, V) + kernels.cross_gram(matrix, Vlo)
     frames = []
     for pc in pclist:
-        residuals = kernels.project_subtract_hp(matrix, Cm[:, :pc].contiguous(), V[:pc], Vlo[:pc])
-        der = derotate_device(residuals.reshape(n, y, x), rot_angles, mask_val=mask_val,
-                              interp_zeros=interp_zeros)
+        residuals = kernels.project_subtract_hp(matrix, Cm[:, :pc].contiguous(), V[:pc], Vlo[:pc]).reshape(n, y, x)
+        if residual_hook is not None:
+            residuals = residual_hook(residuals)
+        der = derotate_device(residuals, rot_angles, mask_val=mask_val, interp_zeros=interp_zeros)
         frames.append(collapse_device(der, mode=collapse, w=weights))
     return torch.stack(frames), pclist
+
+
+def _grid_snr_table(cubeout, pclist, source_xy, fwhm, verbose=False):
+    """S/N-optimised number of components (``pca_grid`` with ``source_xy``, ``utils_pca.py:242-275, 352-418``): for
+    every frame of the grid the mean S/N and mean aperture flux over the pixels of the FWHM disc around the source
+    (fmerit='mean'), all S/N evaluations on the GPU.  Returns (index of the best frame, pandas table)."""
+    if fwhm is None:
+        raise ValueError("if source_xy is provided, so should fwhm")
+    from ..metrics.snr_source import snr_points_device
+    from ..var.shapes import disk_indices
+    import pandas as pd
+    x, y = source_xy
+    yy, xx = disk_indices(y, x, fwhm / 2.0, cubeout.shape[1:])
+    snrlist, fluxlist = [], []
+    for i in range(cubeout.shape[0]):
+        sv, fl = snr_points_device(cubeout[i].contiguous(), xx, yy, fwhm)
+        snr_value = float(sv.mean().item())
+        snrlist.append(0 if np.isnan(snr_value) else snr_value)
+        fluxlist.append(float(fl.mean().item()))
+    argmax = int(np.argmax(snrlist))
+    table = pd.DataFrame({"PCs": pclist, "S/Ns": snrlist, "fluxes": fluxlist})
+    if verbose:
+        print("Number of steps", len(pclist))
+        print("Optimal number of PCs = {}, for S/N={:.3f}".format(pclist[argmax], snrlist[argmax]))
+    return argmax, table
 
 
 def _pca_4d_channels(p, rot_options):
@@ -524,12 +552,12 @@ def _to_numpy_like(t, ref_dtype):
     return a
 
 
-def _pca_adimsdi(p, rot_options):
+def _pca_adimsdi(p, rot_options, algo_params=None):
     """ADI+mSDI branch of ``pca`` (``pca_fullfr.py:497-552``, returns :719-760)."""
-    from .sdi import adimsdi_doublepca_device
+    from .sdi import adimsdi_doublepca_device, adimsdi_singlepca_device, adimsdi_singlepca_grid_device
     if p.cube.ndim != 4:
         raise TypeError("Input cube is not a 4d array (required with `scale_list`)")
-    for name in ("cube_ref", "mask_rdi", "source_xy", "cube_sig", "smooth_first_pass", "smooth", "batch"):
+    for name in ("mask_rdi", "smooth_first_pass", "smooth", "batch"):
         if getattr(p, name) is not None:
             _unsupported(f"`{name}` with ADI+mSDI")
     if p.left_eigv:
@@ -538,25 +566,51 @@ def _pca_adimsdi(p, rot_options):
         if _mode_name(lib) != "vip-fft":
             _unsupported(f"imlib={_mode_name(lib)!r}")
     adimsdi = _mode_name(p.adimsdi)
+    # reference library (:499-510): 'ARSDI' -> the science cube joins the library (single pass: concatenated here)
+    cube_ref, ref_strategy = p.cube_ref, "RSDI"
+    if cube_ref is not None:
+        if np.ndim(cube_ref) != 4:
+            raise TypeError("Ref cube has wrong format for 4d input cube")
+        if "A" in str(p.ref_strategy):
+            ref_strategy = "ARSDI"
+            if adimsdi == "single":
+                cube_ref = np.concatenate((p.cube, cube_ref), axis=1)
     if adimsdi == "double":
         res_ch, res_der, frame = adimsdi_doublepca_device(
             p.cube, p.angle_list, p.scale_list, p.ncomp, scaling=p.scaling, mask_center_px=p.mask_center_px,
             svd_mode=p.svd_mode, collapse=p.collapse, collapse_ifs=p.collapse_ifs,
-            ifs_collapse_range=p.ifs_collapse_range, weights=p.weights, verbose=p.verbose, **rot_options)
+            ifs_collapse_range=p.ifs_collapse_range, weights=p.weights, verbose=p.verbose, cube_ref=cube_ref,
+            ref_strategy=ref_strategy, source_xy=p.source_xy, delta_rot=p.delta_rot, fwhm=p.fwhm,
+            min_frames_pca=p.min_frames_pca, max_frames_pca=p.max_frames_pca, cube_sig=p.cube_sig, **rot_options)
         # the reference's mSDI outputs are float64 (rescaling runs in fp64 there)
         if p.full_output:
             return (to_host(frame).astype(np.float64), to_host(res_ch).astype(np.float64),
                     to_host(res_der).astype(np.float64))
         return to_host(frame).astype(np.float64)
     if adimsdi == "single":
-        from .sdi import adimsdi_singlepca_device
+        # `cube_sig` and -- for a scalar ncomp -- `source_xy` are not forwarded to / used by _adimsdi_singlepca in the
+        # reference (setup_parameters drops what the function does not take): ignored here as well
         if isinstance(p.ncomp, (tuple, list)):
-            _unsupported("adimsdi='single' with a tuple/list `ncomp` (pca_grid on the rescaled cube)")
+            # PCA grid on the rescaled stack (:1205-1236, returns :740-751); `cube_ref` is ignored there upstream
+            cubeout, pclist = adimsdi_singlepca_grid_device(
+                p.cube, p.angle_list, p.scale_list, p.ncomp, scaling=p.scaling, mask_center_px=p.mask_center_px,
+                svd_mode=p.svd_mode, collapse=p.collapse, ifs_collapse_range=p.ifs_collapse_range,
+                crop_ifs=p.crop_ifs, weights=p.weights, verbose=p.verbose, **rot_options)
+            final = to_host(cubeout).astype(np.float64)
+            if p.source_xy is not None:
+                argmax, table = _grid_snr_table(cubeout, pclist, p.source_xy, p.fwhm, p.verbose)
+                frame = final[argmax]
+                if p.med_of_npcs:
+                    final = np.median(final, axis=0)
+                return (final, frame, table) if p.full_output else frame
+            if p.med_of_npcs:
+                final = np.median(final, axis=0)
+            return (final, pclist) if p.full_output else final
         allfr, desc, resadi, frame = adimsdi_singlepca_device(
             p.cube, p.angle_list, p.scale_list, p.ncomp, scaling=p.scaling, mask_center_px=p.mask_center_px,
             svd_mode=p.svd_mode, collapse=p.collapse, collapse_ifs=p.collapse_ifs,
             ifs_collapse_range=p.ifs_collapse_range, crop_ifs=p.crop_ifs, weights=p.weights, verbose=p.verbose,
-            **rot_options)
+            cube_ref=cube_ref, **rot_options)
         # reference dtypes: the rescaled cube and every np.zeros buffer are float64; cube_desc_residuals
         # is np.zeros_like(cube) (pca_fullfr.py:1159-1170)
         f64 = lambda t: to_host(t).astype(np.float64)
@@ -690,29 +744,10 @@ def pca(*all_args: List, **all_kwargs: dict):
         cubeout, pclist = _pca_grid_device(p.cube, cube_ref, -angs, p.ncomp, p.scaling, p.mask_center_px,
                                            p.svd_mode, p.collapse, weights=p.weights, **rot_options)
         if p.source_xy is not None:
-            # S/N-optimised number of components (pca_grid with source_xy, utils_pca.py:242-275, 352-418): for every
-            # frame of the grid the mean S/N and mean aperture flux over the pixels of the FWHM disc around the
-            # source (fmerit='mean'), all S/N evaluations on the GPU; returns (:778) (cube, optimal frame, table)
-            # with full_output, the optimal frame otherwise
-            if p.fwhm is None:
-                raise ValueError("if source_xy is provided, so should fwhm")
-            from ..metrics.snr_source import snr_points_device
-            from ..var.shapes import disk_indices
-            import pandas as pd
-            x, y = p.source_xy
-            yy, xx = disk_indices(y, x, p.fwhm / 2.0, cubeout.shape[1:])
-            snrlist, fluxlist = [], []
-            for i in range(cubeout.shape[0]):
-                sv, fl = snr_points_device(cubeout[i].contiguous(), xx, yy, p.fwhm)
-                snr_value = float(sv.mean().item())
-                snrlist.append(0 if np.isnan(snr_value) else snr_value)
-                fluxlist.append(float(fl.mean().item()))
-            argmax = int(np.argmax(snrlist))
+            # S/N-optimised number of components; returns (:778) (cube, optimal frame, table) with full_output, the
+            # optimal frame otherwise
+            argmax, table = _grid_snr_table(cubeout, pclist, p.source_xy, p.fwhm, p.verbose)
             final = _to_numpy_like(cubeout, p.cube.dtype)
-            table = pd.DataFrame({"PCs": pclist, "S/Ns": snrlist, "fluxes": fluxlist})
-            if p.verbose:
-                print("Number of steps", len(pclist))
-                print("Optimal number of PCs = {}, for S/N={:.3f}".format(pclist[argmax], snrlist[argmax]))
             frame = final[argmax]
             if p.med_of_npcs:
                 final = np.median(final, axis=0)

@@ -100,10 +100,22 @@ def _stage1_frames(cube_dev, frames, ops, ncomp_ifs, scaling, mask_center_px, sv
 
 def adimsdi_doublepca_device(cube, angle_list, scale_list, ncomp, scaling=None, mask_center_px=None,
                              svd_mode="lapack", collapse="median", collapse_ifs="mean",
-                             ifs_collapse_range="all", weights=None, verbose=False, **rot_options):
+                             ifs_collapse_range="all", weights=None, verbose=False, cube_ref=None,
+                             ref_strategy="RSDI", source_xy=None, delta_rot=None, fwhm=4, min_frames_pca=10,
+                             max_frames_pca=None, cube_sig=None, **rot_options):
     """``_adimsdi_doublepca`` (``pca_fullfr.py:1245-1475``) on the device.
-    Returns (res_cube_channels (n,H,W), residuals_cube_channels_ (n,H,W), frame (H,W)) as CUDA tensors."""
+
+    ``cube_ref`` (z, nr, H, W): its frames go through the same spectral first pass (:1278-1282, :1326) and form the
+    reference library of the second, rotational pass (``ref_strategy`` 'RSDI', :1392-1404).  ``source_xy``: second
+    pass frame by frame with a PA-rejection library (:1407-1460).  ``cube_sig`` (n, H, W): subtracted from the
+    first-pass frames before the second decomposition.
+    Returns (res_cube_channels (n+nr,H,W), residuals_cube_channels_ (n,H,W), frame (H,W)) as CUDA tensors."""
     z, n, y_in, x_in = cube.shape
+    nr = 0
+    if cube_ref is not None:
+        if np.ndim(cube_ref) != 4:
+            raise TypeError("Ref cube has wrong format for 4d input cube")
+        nr = cube_ref.shape[1]
     if not isinstance(ncomp, tuple):
         raise TypeError("`ncomp` must be a tuple when a double pass PCA is performed")
     ncomp_ifs, ncomp_adi = ncomp
@@ -128,12 +140,14 @@ def adimsdi_doublepca_device(cube, angle_list, scale_list, ncomp, scaling=None, 
 
     dev = require_cuda()
     cube_dev = to_device_f32(cube, dev)
+    if nr:
+        cube_dev = torch.cat((cube_dev, to_device_f32(cube_ref, dev)), dim=1)      # np.concatenate(..., axis=1)
     ops = RescaleOps(scale_list, y_in, dev)
     per_frame = 4 * z * ops.big * ops.big * 4 * 2          # rescaled + U + residuals + descaled (upper bound)
-    chunk = max(1, min(n, int(_CHUNK_BYTES // per_frame)))
+    chunk = max(1, min(n + nr, int(_CHUNK_BYTES // per_frame)))
     parts = []
-    for f0 in range(0, n, chunk):
-        frames = list(range(f0, min(n, f0 + chunk)))
+    for f0 in range(0, n + nr, chunk):
+        frames = list(range(f0, min(n + nr, f0 + chunk)))
         parts.append(_stage1_frames(cube_dev, frames, ops, ncomp_ifs, scaling[0], mask_center_px, svd_mode,
                                     collapse_ifs, ifs_range))
     res_channels = torch.cat(parts)                          # (n, H, W)
@@ -142,27 +156,103 @@ def adimsdi_doublepca_device(cube, angle_list, scale_list, ncomp, scaling=None, 
 
     mask_val = float(rot_options.get("mask_val", np.nan))
     interp_zeros = bool(rot_options.get("interp_zeros", False))
+    sci = res_channels[:n]
+    ref = res_channels[n:] if nr else None
+    sig_dev = to_device_f32(cube_sig, dev) if cube_sig is not None else None
     if ncomp_adi is None:
-        res2 = res_channels
+        res2 = sci
     else:
-        if ncomp_adi > n:
-            ncomp_adi = n
+        if ncomp_adi > n + nr:
+            ncomp_adi = n + nr
             print("Number of PCs too high, using  maximum of {} PCs instead".format(n))
-        res2 = project_subtract_device(res_channels, ncomp_adi, scaling[1], mask_center_px, svd_mode)
+        if source_xy is None and nr and "A" in str(ref_strategy):
+            # upstream decomposes the n + nr first-pass frames and then derotates all of them with the n angles
+            # (pca_fullfr.py:1379-1391, 1462: IndexError in cube_derotate): nothing to reproduce
+            raise IndexError("index {} is out of bounds for axis 0 with size {} (ref_strategy='ARSDI' with "
+                             "adimsdi='double' fails the same way in the reference)".format(n, n))
+        if source_xy is None:
+            res2 = project_subtract_device(sci, ncomp_adi, scaling[1], mask_center_px, svd_mode,
+                                           cube_ref_dev=ref, cube_sig_dev=sig_dev, in_dtype=np.float64)
+        else:
+            from .pca_fullfr import pa_rejection_residuals_device
+            res2, _, _ = pa_rejection_residuals_device(sci, ref, sig_dev, angle_list, ncomp_adi, scaling[1],
+                                                       mask_center_px, svd_mode, source_xy, delta_rot, fwhm,
+                                                       min_frames_pca, max_frames_pca, in_dtype=np.float64)
     res_der = derotate_device(res2, -angle_list, mask_val=mask_val, interp_zeros=interp_zeros)
     frame = collapse_device(res_der, mode=collapse, w=weights)
     return res_channels, res_der, frame
 
 
-def adimsdi_singlepca_device(cube, angle_list, scale_list, ncomp, scaling=None, mask_center_px=None,
-                             svd_mode="lapack", collapse="median", collapse_ifs="mean",
-                             ifs_collapse_range="all", crop_ifs=True, weights=None, verbose=False,
-                             **rot_options):
-    """``_adimsdi_singlepca`` (``pca_fullfr.py:1038-1242``) for a scalar ``ncomp`` on the device: every
-    channel of every ADI frame is rescaled (speckles aligned), ONE PCA runs over the z*n rescaled frames,
-    the residuals are descaled and collapsed over the channels of each ADI frame, then derotated and
-    collapsed over time.  Returns (cube_allfr_residuals (z*n,S,S), cube_desc_residuals (zr,n,H,W),
-    cube_adi_residuals (n,H,W), frame (H,W)) as CUDA tensors (frame index of the big cube = i*z + channel)."""
+class _SinglePass:
+    """Shared pieces of the single-pass ADI+mSDI PCA: the rescaled (and cropped) stack of all channels of all ADI
+    frames (``pca_fullfr.py:1083-1097``) and its inverse -- descaling of the selected channels of every ADI frame,
+    collapse over them, crop to the input size (``scwave(..., inverse=True)``, :1161-1175 / ``utils_pca.py:203-221``)."""
+
+    def __init__(self, z, n, y_in, scale_list, ifs_collapse_range, crop_ifs, dev):
+        self.z, self.n, self.y_in, self.dev = z, n, y_in, dev
+        self.scale_list = scale_list
+        self.i0, self.i1 = ((0, z) if ifs_collapse_range == "all"
+                            else (int(ifs_collapse_range[0]), int(ifs_collapse_range[1])))
+        self.ops = RescaleOps(scale_list, y_in, dev)
+        S = self.ops.big
+        # crop_ifs: cube_crop_frames(cube_resc, size=y_in) about the centre of the padded frame
+        if crop_ifs and S > y_in:
+            c = frame_center((S, S))[0]
+            self.c0, self.c1 = crop_window(S, y_in, c)
+        else:
+            self.c0, self.c1 = 0, S
+        self.Sc = self.c1 - self.c0
+        per_frame = 3 * z * S * S * 4 * 2
+        self.chunk = max(1, int(_CHUNK_BYTES // per_frame))
+        self._Wi = None
+
+    def rescaled_stack(self, cube_dev):
+        """(z, m, H, W) device cube -> (m*z, Sc, Sc), frame index = i*z + channel."""
+        z, m = cube_dev.shape[:2]
+        S, c0, c1 = self.ops.big, self.c0, self.c1
+        big = torch.empty((m * z, self.Sc, self.Sc), dtype=torch.float32, device=self.dev)
+        for f0 in range(0, m, self.chunk):
+            f1 = min(m, f0 + self.chunk)
+            ms = cube_dev[:, f0:f1].permute(1, 0, 2, 3).contiguous()                # (F, z, H, W)
+            if self.ops.pad:
+                ms = torch.nn.functional.pad(ms, (self.ops.pad,) * 4, mode="reflect")
+            resc = RescaleOps.apply(ms.reshape((f1 - f0) * z, S, S), self.ops.Wf, z)
+            big[f0 * z:f1 * z] = resc[:, c0:c1, c0:c1]
+        return big
+
+    def inverse_ops(self):
+        # inverse rescaling acts on the (possibly cropped) frames: operators of size Sc, crop to the input size
+        if self._Wi is None:
+            Sc, y_in = self.Sc, self.y_in
+            inv = [rescale_operator(Sc, float(1.0 / s)) for s in self.scale_list[self.i0:self.i1]]
+            if Sc > y_in:
+                c = frame_center((Sc, Sc))[0]
+                r0, r1 = crop_window(Sc, y_in, c)
+                inv = [L[r0:r1] for L in inv]
+            W = np.stack([np.concatenate((L.real, L.imag), axis=0) for L in inv]).astype(np.float32)
+            self._Wi = torch.from_numpy(W).to(self.dev)
+        return self._Wi
+
+    def descale_collapse(self, res_cube, collapse_mode, want_desc=False):
+        """Residuals of the stack (n*z, Sc, Sc) -> (cube_desc_residuals (zr, n, H, W) or None, (n, H, W))."""
+        z, n, y_in, Sc, i0, i1 = self.z, self.n, self.y_in, self.Sc, self.i0, self.i1
+        Wi = self.inverse_ops()
+        zr = i1 - i0
+        desc = torch.empty((zr, n, y_in, y_in), dtype=torch.float32, device=self.dev) if want_desc else None
+        resadi = torch.empty((n, y_in, y_in), dtype=torch.float32, device=self.dev)
+        for f0 in range(0, n, self.chunk):
+            f1 = min(n, f0 + self.chunk)
+            F = f1 - f0
+            sel = res_cube[f0 * z:f1 * z].reshape(F, z, Sc, Sc)[:, i0:i1].reshape(F * zr, Sc, Sc).contiguous()
+            d = RescaleOps.apply(sel, Wi, zr).reshape(F, zr, y_in, y_in)
+            if want_desc:
+                desc[:, f0:f1] = d.permute(1, 0, 2, 3)
+            for f in range(F):
+                resadi[f0 + f] = collapse_device(d[f], collapse_mode).float()
+        return desc, resadi
+
+
+def _check_single_inputs(cube, angle_list, scale_list):
     z, n, y_in, x_in = cube.shape
     angle_list = check_pa_vector(np.asarray(angle_list))
     if angle_list.shape[0] != n:
@@ -176,54 +266,34 @@ def adimsdi_singlepca_device(cube, angle_list, scale_list, ncomp, scaling=None, 
         raise ValueError("`scale_list` has wrong length")
     if y_in != x_in:
         raise ValueError("FFT scaling only supports square input arrays")
+    return angle_list, scale_list
+
+
+def adimsdi_singlepca_device(cube, angle_list, scale_list, ncomp, scaling=None, mask_center_px=None,
+                             svd_mode="lapack", collapse="median", collapse_ifs="mean",
+                             ifs_collapse_range="all", crop_ifs=True, weights=None, verbose=False, cube_ref=None,
+                             **rot_options):
+    """``_adimsdi_singlepca`` (``pca_fullfr.py:1038-1242``) for a scalar ``ncomp`` on the device: every
+    channel of every ADI frame is rescaled (speckles aligned), ONE PCA runs over the z*n rescaled frames,
+    the residuals are descaled and collapsed over the channels of each ADI frame, then derotated and
+    collapsed over time.  ``cube_ref`` (z, nr, H, W): rescaled the same way, its z*nr frames are the PCA library
+    (:1099-1119; for ``ref_strategy='ARSDI'`` the caller passes cube and reference concatenated, :504-508).
+    Returns (cube_allfr_residuals (z*n,S,S), cube_desc_residuals (zr,n,H,W),
+    cube_adi_residuals (n,H,W), frame (H,W)) as CUDA tensors (frame index of the big cube = i*z + channel)."""
+    z, n, y_in, x_in = cube.shape
+    angle_list, scale_list = _check_single_inputs(cube, angle_list, scale_list)
     if not np.isscalar(ncomp):
         raise TypeError("`ncomp` must be an int, float, tuple or list for single-pass PCA")
-    i0, i1 = (0, z) if ifs_collapse_range == "all" else (int(ifs_collapse_range[0]), int(ifs_collapse_range[1]))
-
     dev = require_cuda()
-    cube_dev = to_device_f32(cube, dev)
-    ops = RescaleOps(scale_list, y_in, dev)
-    S = ops.big
-    # crop_ifs: cube_crop_frames(cube_resc, size=y_in) about the centre of the padded frame
-    if crop_ifs and S > y_in:
-        c = frame_center((S, S))[0]
-        c0, c1 = crop_window(S, y_in, c)
-    else:
-        c0, c1 = 0, S
-    Sc = c1 - c0
-    big = torch.empty((n * z, Sc, Sc), dtype=torch.float32, device=dev)
-    per_frame = 3 * z * S * S * 4 * 2
-    chunk = max(1, min(n, int(_CHUNK_BYTES // per_frame)))
-    for f0 in range(0, n, chunk):
-        f1 = min(n, f0 + chunk)
-        ms = cube_dev[:, f0:f1].permute(1, 0, 2, 3).contiguous()                # (F, z, H, W)
-        if ops.pad:
-            ms = torch.nn.functional.pad(ms, (ops.pad,) * 4, mode="reflect")
-        resc = RescaleOps.apply(ms.reshape((f1 - f0) * z, S, S), ops.Wf, z)
-        big[f0 * z:f1 * z] = resc[:, c0:c1, c0:c1]
+    sp = _SinglePass(z, n, y_in, scale_list, ifs_collapse_range, crop_ifs, dev)
+    big = sp.rescaled_stack(to_device_f32(cube, dev))
+    big_ref = sp.rescaled_stack(to_device_f32(cube_ref, dev)) if cube_ref is not None else None
     if verbose:
         print("{} total frames".format(n * z))
         print("Performing single-pass PCA")
-    res_cube = project_subtract_device(big, ncomp, scaling, mask_center_px, svd_mode)
-
-    # inverse rescaling acts on the (possibly cropped) frames: operators of size Sc, crop to the input size
-    inv = [rescale_operator(Sc, float(1.0 / s)) for s in scale_list[i0:i1]]
-    if Sc > y_in:
-        c = frame_center((Sc, Sc))[0]
-        r0, r1 = crop_window(Sc, y_in, c)
-        inv = [L[r0:r1] for L in inv]
-    Wi = torch.from_numpy(np.stack([np.concatenate((L.real, L.imag), axis=0) for L in inv]).astype(np.float32)).to(dev)
-    zr = i1 - i0
-    desc = torch.empty((zr, n, y_in, x_in), dtype=torch.float32, device=dev)
-    resadi = torch.empty((n, y_in, x_in), dtype=torch.float32, device=dev)
-    for f0 in range(0, n, chunk):
-        f1 = min(n, f0 + chunk)
-        F = f1 - f0
-        sel = res_cube[f0 * z:f1 * z].reshape(F, z, Sc, Sc)[:, i0:i1].reshape(F * zr, Sc, Sc).contiguous()
-        d = RescaleOps.apply(sel, Wi, zr).reshape(F, zr, y_in, x_in)
-        desc[:, f0:f1] = d.permute(1, 0, 2, 3)
-        for f in range(F):
-            resadi[f0 + f] = collapse_device(d[f], collapse_ifs).float()
+    res_cube = project_subtract_device(big, ncomp, scaling, mask_center_px, svd_mode, cube_ref_dev=big_ref,
+                                       in_dtype=np.float64)
+    desc, resadi = sp.descale_collapse(res_cube, collapse_ifs, want_desc=True)
     mask_val = float(rot_options.get("mask_val", np.nan))
     interp_zeros = bool(rot_options.get("interp_zeros", False))
     der = derotate_device(resadi, -angle_list, mask_val=mask_val, interp_zeros=interp_zeros)
@@ -232,3 +302,26 @@ def adimsdi_singlepca_device(cube, angle_list, scale_list, ncomp, scaling=None, 
         der = der.masked_fill(mask[None], 0.0)
     frame = collapse_device(der, mode=collapse, w=weights)
     return res_cube, desc, resadi, frame
+
+
+def adimsdi_singlepca_grid_device(cube, angle_list, scale_list, range_pcs, scaling=None, mask_center_px=None,
+                                  svd_mode="lapack", collapse="median", ifs_collapse_range="all", crop_ifs=True,
+                                  weights=None, verbose=False, **rot_options):
+    """``_adimsdi_singlepca`` with a tuple / list ``ncomp`` (``pca_fullfr.py:1205-1236`` -> ``pca_grid`` with
+    ``scale_list`` and ``initial_4dshape``, ``utils_pca.py:191-228``): ONE decomposition of the rescaled stack with
+    max(pclist) components; for every entry of the list the truncated residuals are descaled, collapsed over the
+    channels of each ADI frame WITH THE TEMPORAL ``collapse`` MODE (that is what the reference passes to ``scwave``
+    there, not ``collapse_ifs``), derotated and combined.  The reference ignores ``cube_ref`` on this branch
+    (``cube_ref=None``, :1212).  Returns (cubeout (len(pclist), H, W) device tensor, pclist)."""
+    from .pca_fullfr import _pca_grid_device
+    z, n, y_in, x_in = cube.shape
+    angle_list, scale_list = _check_single_inputs(cube, angle_list, scale_list)
+    dev = require_cuda()
+    sp = _SinglePass(z, n, y_in, scale_list, ifs_collapse_range, crop_ifs, dev)
+    big = sp.rescaled_stack(to_device_f32(cube, dev))
+    if verbose:
+        print("{} total frames".format(n * z))
+        print("Performing single-pass PCA")
+    hook = lambda res: sp.descale_collapse(res, collapse)[1]             # noqa: E731
+    return _pca_grid_device(big, None, -angle_list, range_pcs, scaling, mask_center_px, svd_mode, collapse,
+                            weights=weights, residual_hook=hook, **rot_options)
