@@ -181,6 +181,21 @@ int vb_gemm_f32(const float* A, long long lda, long long strideA, int a_mod, con
                 long long strideB, int b_mod, int trans_b, float* C, long long ldc, long long strideC, int M,
                 int N, int K, float alpha, float beta, int batch, void* stream);
 
+/* ---- batched GEMM on the tensor cores (tcgen05, fp32-grade bf16x3 products) --------------------------
+ * vb_split3_bf16: fp32 rows (rows x K, row stride ldx) -> three bf16 planes (error-free split x = x1 + x2 + x3),
+ * plane p at planes + p * plane_stride, row stride ldp (elements; multiple of 8, >= K).
+ * vb_gemm_bf16x3_tc: C[b] (M x N) = A[b % a_mod] (M x K) . B[b] (N x K)^T, b < batch, from such planes (A planes hold
+ * a_mod * M rows, B planes batch * N rows; six cross products per K-block, fp32 accumulation in tensor memory).
+ * Output: fp32 C (ldc, strideC; planesC = NULL), or the bf16x3 planes of C (planesC != NULL, row stride ldpC) with
+ * the rows r >= msplit stored on row r - msplit at column offset N -- the layout in which  [Lr; Li] X^T  becomes the
+ * K-major operand of the second product of  Re(L X L^T) = [Lr | -Li] . [Lr X^T | Li X^T]^T.
+ * Replaces: the FFT zoom of scale_fft for IFS cubes              preproc/rescaling.py:1114-1217, 324-475 */
+int vb_split3_bf16(const float* X, long long rows, int K, long long ldx, void* planes, long long ldp,
+                   long long plane_stride, void* stream);
+int vb_gemm_bf16x3_tc(const void* planesA, long long ldpA, long long strideA, int a_mod, const void* planesB,
+                      long long ldpB, long long strideB, int M, int N, int K, int batch, float* C, long long ldc,
+                      long long strideC, void* planesC, long long ldpC, long long strideCp, int msplit, void* stream);
+
 /* ---- Fourier sub-pixel shift (frame recentring, fake-companion injection) -------------------------
  * The vip-fft shift of a frame is  out = Ty X Tx^T - checkerboard term  with real Toeplitz operators
  * T[m][n] = Re D_N(m - n - s) of the zero-padded even plane of N pixels (csrc/shift.cu).

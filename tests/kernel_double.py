@@ -140,6 +140,43 @@ def gemm(A, B, C, trans_b=False, alpha=1.0, beta=0.0, a_mod=0, b_mod=0):
     return C
 
 
+def split3(X):
+    """Contract of ``kernels.split3``: exact three-way bf16 split, planes (3, rows, ldp) with ldp = K rounded up to 8."""
+    from vip_b200.kernels import Planes3
+    rows, K = X.shape
+    ldp = (K + 7) // 8 * 8
+    data = torch.zeros((3, rows, ldp), dtype=torch.bfloat16)
+    r = X.float().clone()
+    for q in range(3):
+        h = r.to(torch.bfloat16)
+        data[q, :, :K] = h
+        r = r - h.float()
+    return Planes3(data, rows, K)
+
+
+def planes3_empty(rows, K, device):
+    from vip_b200.kernels import Planes3
+    return Planes3(torch.zeros((3, int(rows), (int(K) + 7) // 8 * 8), dtype=torch.bfloat16), rows, K)
+
+
+def gemm_tc(A, a_mod, B, M, N, batch, out=None, out_planes=None, msplit=0):
+    """Contract of ``kernels.gemm_tc`` (products in float64 of the summed planes)."""
+    Af = A.data.double().sum(0)[:, :A.K].reshape(a_mod, M, A.K)
+    Bf = B.data.double().sum(0)[:, :B.K].reshape(batch, N, B.K)
+    for b in range(batch):
+        Cb = (Af[b % a_mod] @ Bf[b].T).float()                  # (M, N)
+        if out_planes is None:
+            out[b] = Cb
+            continue
+        folded = torch.cat((Cb[:msplit], Cb[msplit:]), dim=1) if M > msplit else Cb      # (msplit, 2N)
+        r = folded.clone()
+        for q in range(3):
+            h = r.to(torch.bfloat16)
+            out_planes.data[q, b * msplit:(b + 1) * msplit, :folded.shape[1]] = h
+            r = r - h.float()
+    return out if out_planes is None else out_planes
+
+
 def annular_weights(G, idx, lens, frames, ncomp, tol=0.0, max_iter=40, direct_fallback=True, force_direct=False):
     """Per-problem projection weights from the library Gramian (contract of ``kernels.annular_weights``):
     W[q, I] = X diag(1/theta) X^T G[I, frame_q] with (theta, X) the leading eigenpairs of G[I, I]."""
@@ -192,7 +229,7 @@ def annular_weights_auto(G, idx, lens, frames, rowsum, npx, noise_tol, kmax=24):
 
 
 _NAMES = ("annular_weights_auto", "annular_weights", "gram", "cross_gram", "eigh", "chol_whiten", "eigh_topk", "topk_supported", "pcs", "pcs_hilo", "project_subtract", "project_subtract_hp", "sub", "derotate",
-          "collapse", "upload_and_gram", "upload_columns", "gather_columns", "scatter_columns", "gemm")
+          "collapse", "upload_and_gram", "upload_columns", "gather_columns", "scatter_columns", "gemm", "split3", "planes3_empty", "gemm_tc")
 
 
 def aperture_sums_device(frame_dev, xs, ys, r):

@@ -1121,6 +1121,59 @@ def test_pca_adimsdi_fullframe_options(vb):
     assert np.array_equal(best, best2)
 
 
+def test_gemm_tc_matches_fp64(vb):
+    """Batched tcgen05 GEMM with error-free bf16x3 operands (``vb_gemm_bf16x3_tc``) against float64 products: fp32
+    output and the folded bf16x3 plane output, tile-ragged extents (446 = 3 x 128 + 62), K not a multiple of 64,
+    operator index b % a_mod.  Error bound: fp32-grade products + fp32 accumulation over K."""
+    import torch
+    from vip_b200 import kernels
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for (amod, M, N, K, batch, msplit) in ((3, 150, 70, 90, 6, 75), (2, 892, 446, 446, 4, 446), (2, 446, 446, 892, 4, 446),
+                                           (1, 128, 128, 64, 1, 128)):
+        A = (torch.randn((amod, M, K), generator=g) * 3.0).to(dev)
+        B = (torch.randn((batch, N, K), generator=g) * 100.0 + 50.0).to(dev)
+        want = torch.stack([A[b % amod].double() @ B[b].double().T for b in range(batch)])
+        bound = torch.stack([A[b % amod].abs().double() @ B[b].abs().double().T for b in range(batch)])
+        Ap, Bp = kernels.split3(A.reshape(amod * M, K)), kernels.split3(B.reshape(batch * N, K))
+        assert torch.equal(Ap.data.double().sum(0)[:, :K], A.reshape(amod * M, K).double())      # the split is exact
+        out = torch.full((batch, M, N), float("nan"), device=dev)
+        kernels.gemm_tc(Ap, amod, Bp, M, N, batch, out=out)
+        err = float(((out.double() - want).abs() / bound).max())
+        print(f"gemm_tc M={M} N={N} K={K}: max err / sum|a||b| = {err:.2e}")
+        assert err < 6e-7, (M, N, K, err)
+        # plane output, rows >= msplit folded beside the first block
+        P = kernels.planes3_empty(batch * msplit, 2 * N if M > msplit else N, dev)
+        P.data.zero_()
+        kernels.gemm_tc(Ap, amod, Bp, M, N, batch, out_planes=P, msplit=msplit)
+        got = P.data.double().sum(0).reshape(batch, msplit, -1)
+        assert float(((got[:, :, :N] - want[:, :msplit]).abs() / bound[:, :msplit]).max()) < 6e-7
+        if M > msplit:
+            assert float(((got[:, :M - msplit, N:2 * N] - want[:, msplit:]).abs() / bound[:, msplit:]).max()) < 6e-7
+
+
+def test_rescale_tc_matches_cuda_core_path(vb, monkeypatch):
+    """``RescaleOps.apply`` on the tensor cores against the CUDA-core fp32 GEMM path (fp64 accumulation across
+    k-slabs) on a config-4-shaped problem: 39 channels, 256 -> 446 pixel planes, 2 frames."""
+    import torch
+    from vip_b200.psfsub.sdi import RescaleOps
+    dev = torch.device("cuda")
+    lam = np.linspace(0.95, 1.65, 39)
+    ops = RescaleOps(lam.max() / lam, 256, dev)
+    assert ops.big == 446
+    X = (torch.randn((2 * 39, 446, 446), generator=torch.Generator().manual_seed(1)) * 20 + 300).to(dev)
+    monkeypatch.setenv("VIP_B200_RESCALE_TC", "0")
+    ref_f = RescaleOps.apply(X, ops.Wf, 39)
+    ref_i = RescaleOps.apply(X, ops.Wi, 39)
+    monkeypatch.setenv("VIP_B200_RESCALE_TC", "1")
+    out_f = RescaleOps.apply(X, ops.Wf, 39)
+    out_i = RescaleOps.apply(X, ops.Wi, 39)
+    assert out_f.shape == ref_f.shape == (78, 446, 446) and out_i.shape == ref_i.shape == (78, 256, 256)
+    # two chained fp32-grade products (1.5e-7 of sum|a||b| each, operator rows with |.|-sums of a few units)
+    assert float((out_f - ref_f).abs().max()) < 4e-6 * float(ref_f.abs().max())
+    assert float((out_i - ref_i).abs().max()) < 4e-6 * float(ref_i.abs().max())
+
+
 # ------------------------------------------------------------------ Fourier shift, median subtraction
 SHIFT_TOL = 2e-5
 

@@ -48,6 +48,9 @@ SIGNATURES = {
     "vb_scatter_columns_f32": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp]),
     "vb_gemm_f32": (_i, [_vp, C.c_longlong, C.c_longlong, _i, _vp, C.c_longlong, C.c_longlong, _i, _i, _vp,
                         C.c_longlong, C.c_longlong, _i, _i, _i, _f, _f, _i, _vp]),
+    "vb_split3_bf16": (_i, [_vp, C.c_longlong, _i, C.c_longlong, _vp, C.c_longlong, C.c_longlong, _vp]),
+    "vb_gemm_bf16x3_tc": (_i, [_vp, C.c_longlong, C.c_longlong, _i, _vp, C.c_longlong, C.c_longlong, _i, _i, _i, _i,
+                              _vp, C.c_longlong, C.c_longlong, _vp, C.c_longlong, C.c_longlong, _i, _vp]),
     "vb_shift_operators_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "vb_checker_correct_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "vb_memcpy2d_h2d": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),

@@ -56,6 +56,9 @@ struct GemmArgs {
     float alpha, beta;
 };
 int gemm_f32(const GemmArgs&, int, int, cudaStream_t);
+int split3_bf16(const float*, long long, int, long long, void*, long long, long long, cudaStream_t);
+int gemm_bf16x3_tc(const void*, long long, long long, int, const void*, long long, long long, int, int, int, int,
+                   float*, long long, long long, void*, long long, long long, int, cudaStream_t);
 int annular_weights(const double*, const double*, int, const int*, const int*, const int*, int, int, int, double,
                     int, float*, int*, cudaStream_t);
 int annular_auto_weights(const double*, const double*, int, const int*, const int*, const int*, int, int, int,
@@ -335,6 +338,20 @@ int vb_gemm_f32(const float* A, long long lda, long long strideA, int a_mod, con
     GemmArgs g{A, lda, strideA, a_mod, B, ldb, strideB, b_mod, C, ldc, strideC, M, N, K, alpha, beta};
     g_launches += 1;
     return gemm_f32(g, trans_b, batch, (cudaStream_t)stream);
+}
+
+int vb_split3_bf16(const float* X, long long rows, int K, long long ldx, void* planes, long long ldp,
+                   long long plane_stride, void* stream) {
+    g_launches += 1;
+    return split3_bf16(X, rows, K, ldx, planes, ldp, plane_stride, (cudaStream_t)stream);
+}
+
+int vb_gemm_bf16x3_tc(const void* planesA, long long ldpA, long long strideA, int a_mod, const void* planesB,
+                      long long ldpB, long long strideB, int M, int N, int K, int batch, float* C, long long ldc,
+                      long long strideC, void* planesC, long long ldpC, long long strideCp, int msplit, void* stream) {
+    g_launches += 1;
+    return gemm_bf16x3_tc(planesA, ldpA, strideA, a_mod, planesB, ldpB, strideB, M, N, K, batch, C, ldc, strideC,
+                          planesC, ldpC, strideCp, msplit, (cudaStream_t)stream);
 }
 
 int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitch, size_t width_bytes,

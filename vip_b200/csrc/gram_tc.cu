@@ -354,6 +354,234 @@ slab_mean_kernel(const float* __restrict__ A, int n, size_t w, size_t ld, float*
     }
 }
 
+
+// =====================================================================================
+// Batched GEMM  C[b] = A[b % amod] . B[b]^T  on the same tcgen05 pipeline (round 2, second half)
+// =====================================================================================
+// Role in the reference: the two-sided separable resampling  Re(L X L^T)  that replaces the FFT zoom of scale_fft
+// (preproc/rescaling.py:1114-1217) for every (ADI frame, channel) of an IFS cube -- BASELINE config 4 spends 83 % of
+// its kernel time there on the CUDA-core GEMM of csrc/gemm.cu (profiles/r04c_launches_c4.md).  Both operands are
+// K-major bf16x3 planes (three-way error-free split of fp32, six cross products: fp32-grade products, fp32
+// accumulation over K <= 896 in TMEM); operators depend on the channel only (row block b % amod of the A planes),
+// frames on the batch index (row block b of the B planes).  One CTA per 128 x 128 output tile: warp 0 = TMA
+// producer, warp 1 = MMA issuer, warps 2..9 = epilogue.  The epilogue transposes the accumulator through the (by
+// then idle) pipeline buffers so that every store instruction writes one contiguous row segment, and writes either
+// fp32 C or -- OUT_PLANES -- the bf16x3 planes of C directly, in the layout the NEXT product reads as its K-major B
+// operand: rows r < msplit at row r, rows r >= msplit at row r - msplit shifted by N columns (the real and imaginary
+// halves of  [Lr; Li] X^T  side by side).
+struct GemmTcArgs {
+    int M, N, K;                 // per-batch extents (A: M x K, B: N x K)
+    int amod, nper;              // operator index = b % amod; nper = batch / amod (batches per operator)
+    int ntj;                     // column tiles per batch
+    float* C; long long ldc, strideC;                          // fp32 output (OUT_PLANES = false)
+    __nv_bfloat16* P; long long ldp, plane_stride; int msplit; // plane output (OUT_PLANES = true)
+};
+
+// Accuracy: the tensor core adds every MMA result to the fp32 accumulator with ONE truncating rounding (measured:
+// 0.5 ulp of systematic loss per MMA instruction on same-sign data, 1e-6 relative after 36 instructions), so
+//   * the leading product D1.D1 and the five small cross products (2^-8 ... 2^-16 of it) go to SEPARATE TMEM
+//     accumulators -- the corrections are then rounded relative to their own size, not to the sum's;
+//   * every CHUNK_KB K-blocks (128 values of k) both accumulators are drained and added to fp32 registers with
+//     round-to-nearest CUDA-core adds; the two accumulator pairs are double-buffered so the drain of chunk c overlaps
+//     the MMAs of chunk c + 1 (same protocol as gram_umma_kernel).
+constexpr int GEMM_CHUNK_KB = 2;
+constexpr int GEMM_TMEM_COLS = 4 * TN;      // (hi, lo) x 2 buffers
+
+template <bool OUT_PLANES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcArgs g) {
+    constexpr int BK = 64, NPIECE = 3;
+    using K = Cfg<BK, NPIECE>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[K::STAGES], bar_empty[K::STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // consecutive CTAs share the operator (L2 reuse of its planes): y -> b = (y % nper) * amod + y / nper
+    const int y = blockIdx.y;
+    const int b = (g.nper > 0) ? (y % g.nper) * g.amod + y / g.nper : y;
+    const int ti = blockIdx.x / g.ntj, tj = blockIdx.x % g.ntj;
+    const int rowA0 = (g.amod > 0 ? b % g.amod : b) * g.M + ti * TM;
+    const int rowB0 = b * g.N + tj * TN;
+    const int nkb = (g.K + BK - 1) / BK;
+    const int nchunks = (nkb + GEMM_CHUNK_KB - 1) / GEMM_CHUNK_KB;
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K::STAGES; ++s) {
+            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_empty[s]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&bar_tfull[i]), 1);
+            mbar_init(smem_u32(&bar_tempty[i]), NEPI);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_base_s)), "r"((uint32_t)GEMM_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % K::STAGES;
+                const uint32_t ph = (i / K::STAGES) & 1;
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+                const uint32_t full = smem_u32(&bar_full[s]);
+                mbar_expect_tx(full, 2 * NPIECE * K::PIECE_BYTES);
+                const uint32_t sa = smem0 + s * K::STAGE_BYTES;
+#pragma unroll
+                for (int pc = 0; pc < NPIECE; ++pc) tma_load_3d(sa + pc * K::PIECE_BYTES, &tmA, full, i * BK, rowA0, pc);
+#pragma unroll
+                for (int pc = 0; pc < NPIECE; ++pc)
+                    tma_load_3d(sa + (NPIECE + pc) * K::PIECE_BYTES, &tmB, full, i * BK, rowB0, pc);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr int PA[6] = {0, 0, 1, 0, 2, 1};
+            constexpr int PB[6] = {0, 1, 0, 2, 0, 1};
+            int i = 0;
+            for (int c = 0; c < nchunks; ++c) {
+                const int buf = c & 1;
+                mbar_wait(smem_u32(&bar_tempty[buf]), ((c >> 1) & 1) ^ 1);
+                fence_after();
+                const uint32_t thi = tmem_base + buf * 2 * TN, tlo = thi + TN;
+                const int iend = (i + GEMM_CHUNK_KB < nkb) ? i + GEMM_CHUNK_KB : nkb;
+                bool first_hi = true, first_lo = true;
+                for (; i < iend; ++i) {
+                    const int s = i % K::STAGES;
+                    const uint32_t ph = (i / K::STAGES) & 1;
+                    mbar_wait(smem_u32(&bar_full[s]), ph);
+                    fence_after();
+                    const uint32_t sa = smem0 + s * K::STAGE_BYTES;
+                    const uint32_t sb = sa + NPIECE * K::PIECE_BYTES;
+#pragma unroll
+                    for (int pr = 0; pr < 6; ++pr) {
+                        const uint64_t ad = smem_desc<K::SW>(sa + PA[pr] * K::PIECE_BYTES);
+                        const uint64_t bd = smem_desc<K::SW>(sb + PB[pr] * K::PIECE_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < BK / UK; ++kk) {
+                            if (pr == 0) { umma_bf16(thi, ad + 2 * kk, bd + 2 * kk, kInstrDesc, first_hi ? 0u : 1u); first_hi = false; }
+                            else { umma_bf16(tlo, ad + 2 * kk, bd + 2 * kk, kInstrDesc, first_lo ? 0u : 1u); first_lo = false; }
+                        }
+                    }
+                    umma_commit(smem_u32(&bar_empty[s]));
+                }
+                umma_commit(smem_u32(&bar_tfull[buf]));
+            }
+        }
+    } else {
+        // ===== epilogue: drain the chunks into fp32 registers, then registers -> shared (transpose) -> global =====
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;       // which 64 columns
+        constexpr int PITCH = 66;               // floats per staged row (even: float2 reads; 2-way conflicts on the fill)
+        float acc[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+            const int buf = c & 1;
+            mbar_wait(smem_u32(&bar_tfull[buf]), (c >> 1) & 1);
+            fence_after();
+            const uint32_t thi = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * TN + half * 64;
+            uint32_t vh[32], vl[32];
+            tmem_ld32(thi, vh);
+            tmem_ld32(thi + TN, vl);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(vh[j]) + __uint_as_float(vl[j]);
+            tmem_ld32(thi + 32, vh);
+            tmem_ld32(thi + TN + 32, vl);
+            tmem_ld_wait();
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[buf]));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[32 + j] += __uint_as_float(vh[j]) + __uint_as_float(vl[j]);
+        }
+        // every MMA has retired (the last tfull) and every TMA load was consumed: the pipeline buffers are free
+        float* stage = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw))) + (size_t)(warp - 2) * 32 * PITCH;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) stage[lane * PITCH + j] = acc[j];
+        __syncwarp();
+        const int col = tj * TN + half * 64 + 2 * lane;      // this lane's two columns of every row
+        if (col < g.N) {                                     // N is even: col + 1 < N as well
+            for (int rr = 0; rr < 32; ++rr) {
+                const int r = ti * TM + q * 32 + rr;
+                if (r >= g.M) break;
+                const float2 val = *reinterpret_cast<const float2*>(stage + rr * PITCH + 2 * lane);
+                if (!OUT_PLANES) {
+                    *reinterpret_cast<float2*>(g.C + (size_t)b * g.strideC + (size_t)r * g.ldc + col) = val;
+                } else {
+                    const int r_lo = (r >= g.msplit) ? r - g.msplit : r;
+                    const int shift = (r >= g.msplit) ? g.N : 0;
+                    __nv_bfloat16* dst = g.P + ((size_t)b * g.msplit + r_lo) * g.ldp + shift + col;
+                    float x0 = val.x, x1 = val.y;
+#pragma unroll
+                    for (int pc = 0; pc < NPIECE; ++pc) {
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                        x0 -= __bfloat162float(h0);
+                        x1 -= __bfloat162float(h1);
+                        __nv_bfloat162 h;
+                        h.x = h0; h.y = h1;
+                        *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)pc * g.plane_stride) = h;
+                    }
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)GEMM_TMEM_COLS) : "memory");
+    }
+}
+
+// fp32 rows (row stride ldx) -> three bf16 planes (row stride ldp, a multiple of 8), 8 consecutive elements per thread
+__global__ void __launch_bounds__(256)
+split3_rows_kernel(const float* __restrict__ X, long long rows, int Kc, long long ldx,
+                   __nv_bfloat16* __restrict__ planes, long long ldp, long long plane_stride, int tpr) {
+    const int rpb = 256 / tpr;                              // rows per block
+    const long long row = (long long)blockIdx.x * rpb + threadIdx.x / tpr;
+    const int k0 = (threadIdx.x % tpr) * 8;
+    if (row >= rows || threadIdx.x / tpr >= rpb || k0 >= Kc) return;
+    const float* src = X + row * ldx + k0;
+    float d[8];
+    if (k0 + 8 <= Kc && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(src));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        d[0] = a0.x; d[1] = a0.y; d[2] = a0.z; d[3] = a0.w;
+        d[4] = a1.x; d[5] = a1.y; d[6] = a1.z; d[7] = a1.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = (k0 + j < Kc) ? __ldg(src + j) : 0.f;
+    }
+    __align__(16) __nv_bfloat16 pc[3][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float r = d[j];
+#pragma unroll
+        for (int qq = 0; qq < 3; ++qq) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(r);
+            pc[qq][j] = h;
+            r -= __bfloat162float(h);
+        }
+    }
+    __nv_bfloat16* dst = planes + row * ldp + k0;
+#pragma unroll
+    for (int qq = 0; qq < 3; ++qq)
+        *reinterpret_cast<uint4*>(dst + qq * plane_stride) = *reinterpret_cast<const uint4*>(pc[qq]);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -554,6 +782,74 @@ int gram_tc_f32(const float* A, int n, size_t p, double* G, void* ws, size_t ws_
     if (int rc = gram_tc_accumulate(A, n, p, p, 0, p, ws, ntiles, &nl, st)) return rc;
     if (int rc = gram_tc_finish(n, p, ws, G, &nl, st)) return rc;
     if (launches) *launches = nl;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched bf16x3 GEMM on tcgen05 (SDI rescaling operators)
+// ------------------------------------------------------------------------------------------------
+int split3_bf16(const float* X, long long rows, int K, long long ldx, void* planes, long long ldp,
+                long long plane_stride, cudaStream_t st) {
+    VB_REQUIRE(rows > 0 && K > 0 && K <= 2048, "split3: bad extents (rows=%lld, K=%d; K <= 2048)", rows, K);
+    VB_REQUIRE(ldp % 8 == 0 && ldp >= (K + 7) / 8 * 8 && plane_stride % 8 == 0, "split3: plane pitch must be a multiple of 8 >= K");
+    VB_REQUIRE((reinterpret_cast<uintptr_t>(planes) & 15) == 0, "split3: planes must be 16-byte aligned");
+    int tpr = ((K + 7) / 8 + 31) / 32 * 32;
+    if (tpr > 256) tpr = 256;
+    const int rpb = 256 / tpr;
+    const long long blocks = (rows + rpb - 1) / rpb;
+    VB_REQUIRE(blocks < (1ll << 31), "split3: too many rows");
+    tc::split3_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, rows, K, ldx, reinterpret_cast<__nv_bfloat16*>(planes),
+                                                             ldp, plane_stride, tpr);
+    VB_CHECK_LAUNCH();
+    return 0;
+}
+
+// C[b] (M x N) = A[b % amod] (M x K) . B[b] (N x K)^T for b < batch.  A planes: (amod * M) rows, B planes: (batch * N)
+// rows, both three bf16 planes of pitch ldpA / ldpB.  Output: fp32 C (ldc, strideC) when planesC == nullptr, else the
+// bf16x3 planes of C with rows r >= msplit folded to row r - msplit at column offset N (pitch ldpC >= 2 N).
+int gemm_bf16x3_tc(const void* planesA, long long ldpA, long long strideA, int amod, const void* planesB,
+                   long long ldpB, long long strideB, int M, int N, int K, int batch, float* C, long long ldc,
+                   long long strideC, void* planesC, long long ldpC, long long strideCp, int msplit,
+                   cudaStream_t st) {
+    VB_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0 && amod > 0, "gemm_tc: empty problem");
+    VB_REQUIRE(batch <= 65535, "gemm_tc: at most 65535 batches per call (got %d)", batch);
+    VB_REQUIRE(N % 2 == 0, "gemm_tc: N must be even (got %d)", N);
+    VB_REQUIRE(ldpA % 8 == 0 && ldpB % 8 == 0 && strideA % 8 == 0 && strideB % 8 == 0, "gemm_tc: plane pitches must be multiples of 8");
+    VB_REQUIRE((long long)amod * M < (1ll << 31) && (long long)batch * N < (1ll << 31), "gemm_tc: too many rows");
+    const bool out_planes = planesC != nullptr;
+    if (out_planes) {
+        VB_REQUIRE(msplit > 0 && msplit <= M && ldpC % 2 == 0 && strideCp % 2 == 0 && ldpC >= (M > msplit ? 2 : 1) * N,
+                   "gemm_tc: bad plane output layout");
+        VB_REQUIRE((reinterpret_cast<uintptr_t>(planesC) & 3) == 0, "gemm_tc: output planes must be 4-byte aligned");
+    } else {
+        VB_REQUIRE(C != nullptr && ldc % 2 == 0 && strideC % 2 == 0 && (reinterpret_cast<uintptr_t>(C) & 7) == 0,
+                   "gemm_tc: fp32 output needs even ldc / strideC and an 8-byte aligned base");
+    }
+    CUtensorMap tmA, tmB;
+    if (int rc = tc::make_map(&tmA, reinterpret_cast<const __nv_bfloat16*>(planesA), (size_t)K, amod * M, 3,
+                              (size_t)ldpA, (size_t)strideA, 64)) return rc;
+    if (int rc = tc::make_map(&tmB, reinterpret_cast<const __nv_bfloat16*>(planesB), (size_t)K, batch * N, 3,
+                              (size_t)ldpB, (size_t)strideB, 64)) return rc;
+    using Kc = tc::Cfg<64, 3>;
+    static bool configured = false;
+    if (!configured) {
+        VB_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Kc::SMEM_BYTES));
+        VB_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Kc::SMEM_BYTES));
+        configured = true;
+    }
+    tc::GemmTcArgs g;
+    g.M = M; g.N = N; g.K = K;
+    g.amod = amod;
+    g.nper = (batch % amod == 0) ? batch / amod : 0;
+    g.ntj = ceil_div(N, tc::TN);
+    g.C = C; g.ldc = ldc; g.strideC = strideC;
+    g.P = reinterpret_cast<__nv_bfloat16*>(planesC); g.ldp = ldpC; g.plane_stride = strideCp; g.msplit = msplit;
+    const dim3 grid(ceil_div(M, tc::TM) * g.ntj, batch);
+    if (out_planes) tc::gemm_umma_kernel<true><<<grid, tc::NTHREADS, Kc::SMEM_BYTES, st>>>(tmA, tmB, g);
+    else tc::gemm_umma_kernel<false><<<grid, tc::NTHREADS, Kc::SMEM_BYTES, st>>>(tmA, tmB, g);
+    VB_CHECK_LAUNCH();
     return 0;
 }
 

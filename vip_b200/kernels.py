@@ -356,6 +356,56 @@ def gemm(A, B, C, trans_b=False, alpha=1.0, beta=0.0, a_mod=0, b_mod=0):
     return C
 
 
+class Planes3:
+    """fp32 matrix (rows, K) as three bf16 planes (3, rows, ldp) -- the K-major operand format of the tcgen05 kernels."""
+
+    def __init__(self, data, rows, K):
+        self.data, self.rows, self.K = data, int(rows), int(K)
+
+    @property
+    def ldp(self):
+        return int(self.data.shape[2])
+
+    @property
+    def plane_stride(self):
+        return int(self.data.stride(0))
+
+
+def planes3_empty(rows, K, device):
+    ldp = (int(K) + 7) // 8 * 8
+    return Planes3(torch.empty((3, int(rows), ldp), dtype=torch.bfloat16, device=device), rows, K)
+
+
+def split3(X):
+    """Error-free split of a contiguous fp32 matrix (rows, K) into three bf16 planes (``vb_split3_bf16``)."""
+    lib = _cabi.lib()
+    assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1
+    rows, K = X.shape
+    P = planes3_empty(rows, K, X.device)
+    _cabi.check(lib.vb_split3_bf16(ptr(X), rows, K, X.stride(0), ptr(P.data), P.ldp, P.plane_stride, stream_ptr()),
+                "vb_split3_bf16")
+    return P
+
+
+def gemm_tc(A, a_mod, B, M, N, batch, out=None, out_planes=None, msplit=0):
+    """Batched ``C[b] = A[b % a_mod] @ B[b]^T`` on the tensor cores (``vb_gemm_bf16x3_tc``): A, B are :class:`Planes3`
+    with a_mod * M and batch * N rows and the same K.  ``out`` (batch, M, N) fp32, or ``out_planes`` (:class:`Planes3`
+    with batch * msplit rows): the bf16x3 planes of C, rows r >= msplit folded to row r - msplit at column offset N."""
+    lib = _cabi.lib()
+    assert A.K == B.K and A.rows == a_mod * M and B.rows == batch * N
+    if out_planes is not None:
+        _cabi.check(lib.vb_gemm_bf16x3_tc(ptr(A.data), A.ldp, A.plane_stride, int(a_mod), ptr(B.data), B.ldp,
+                                          B.plane_stride, M, N, A.K, batch, 0, 0, 0, ptr(out_planes.data),
+                                          out_planes.ldp, out_planes.plane_stride, int(msplit), stream_ptr()),
+                    "vb_gemm_bf16x3_tc")
+        return out_planes
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (batch, M, N)
+    _cabi.check(lib.vb_gemm_bf16x3_tc(ptr(A.data), A.ldp, A.plane_stride, int(a_mod), ptr(B.data), B.ldp,
+                                      B.plane_stride, M, N, A.K, batch, ptr(out), N, M * N, 0, 0, 0, 0,
+                                      stream_ptr()), "vb_gemm_bf16x3_tc")
+    return out
+
+
 def shift_operators(shifts, nplane, L, device):
     """(nf, L, L) fp32 Toeplitz operators of the vip-fft shift: T[f][m][n] = Re D_N(m - n - shift[f])."""
     lib = _cabi.lib()

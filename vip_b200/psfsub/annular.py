@@ -473,7 +473,9 @@ def _pca_sdi_frames_device(cube_dev, scal, radius_int, fwhm, asize, n_segments, 
                 if bool((iters < 0).any()):
                     raise RuntimeError("vip_b200.pca_annular: spectral eigenproblems did not converge")
                 R = Ag.clone()
-                kernels.gemm(Wt.unsqueeze(0), Ag.unsqueeze(0), R.unsqueeze(0), alpha=-1.0, beta=1.0)
+                # Wt is block diagonal (libraries never leave their frame): apply the Fg diagonal z x z blocks as a batch
+                P = Wt.reshape(Fg, z, Fg, z).diagonal(dim1=0, dim2=2).permute(2, 0, 1).contiguous()
+                kernels.gemm(P, Ag.reshape(Fg, z, npx), R.reshape(Fg, z, npx), alpha=-1.0, beta=1.0)
                 kernels.scatter_columns(R, cols, res[g0 * z:g1 * z])
         desc = RescaleOps.apply(res.reshape(F * z, S, S), ops.Wi, z).reshape(F, z, ops.out, ops.out)
         for f in range(F):

@@ -32,9 +32,29 @@ class RescaleOps:
     """Forward / inverse rescaling operators of every channel, on the device.
 
     forward:  (z, S', S')  real and imaginary parts stacked as W = [Lr; Li] (z, 2S', S')
-    inverse:  rows restricted to the final crop window -> (z, 2H, S')"""
+    inverse:  rows restricted to the final crop window -> (z, 2H, S')
+
+    Instances are cached per (scale_list, frame size, device): building and uploading the 2 z operators (and, on
+    first use, their bf16x3 planes for the tensor-core products) costs more than a whole config-4 frame chunk."""
+
+    _cache = {}
+
+    def __new__(cls, scale_list, size, device):
+        key = (np.asarray(scale_list, dtype=np.float64).tobytes(), int(size), str(device))
+        hit = cls._cache.get(key)
+        if hit is not None:
+            return hit
+        self = super().__new__(cls)
+        self._build(scale_list, size, device)
+        if len(cls._cache) >= 4:
+            cls._cache.pop(next(iter(cls._cache)))
+        cls._cache[key] = self
+        return self
 
     def __init__(self, scale_list, size, device):
+        pass
+
+    def _build(self, scale_list, size, device):
         scale_list = np.asarray(scale_list, dtype=np.float64)
         self.z = scale_list.shape[0]
         self.size = size
@@ -61,9 +81,26 @@ class RescaleOps:
     @staticmethod
     def apply(X, W, z):
         """X (B, S, S) fp32 with B a multiple of z (channel = b % z); W (z, 2*So, S).
-        Returns Re(L X L^T) (B, So, So) with L = W[:So] + i W[So:]."""
+        Returns Re(L X L^T) (B, So, So) with L = W[:So] + i W[So:].
+
+        Default: two products on the tensor cores (``kernels.gemm_tc``, tcgen05 with fp32-grade bf16x3 operands):
+        U = [Lr; Li] X^T written by the first kernel's epilogue directly as the bf16x3 planes of
+        [Lr X^T | Li X^T] (So x 2S per frame), then  Y = [Lr | -Li] U^T  with K = 2S.  The CUDA-core fp32 GEMM
+        (``kernels.gemm``) remains for odd sizes and ``VIP_B200_RESCALE_TC=0``."""
         B, S, _ = X.shape
         So = W.shape[1] // 2
+        if _rescale_tc() and S % 2 == 0 and So % 2 == 0 and B % z == 0 and B <= 65535:
+            ops = getattr(W, "_vb_tc_planes", None)
+            if ops is None:
+                A1 = kernels.split3(W.reshape(z * 2 * So, S).contiguous())
+                A2 = kernels.split3(torch.cat((W[:, :So], -W[:, So:]), dim=2).reshape(z * So, 2 * S).contiguous())
+                ops = W._vb_tc_planes = (A1, A2)
+            A1, A2 = ops
+            Xp = kernels.split3(X.reshape(B * S, S))
+            U = kernels.planes3_empty(B * So, 2 * S, X.device)
+            kernels.gemm_tc(A1, z, Xp, 2 * So, S, B, out_planes=U, msplit=So)
+            Y = torch.empty((B, So, So), dtype=torch.float32, device=X.device)
+            return kernels.gemm_tc(A2, z, U, So, So, B, out=Y)
         U = torch.empty((B, S, 2 * So), dtype=torch.float32, device=X.device)
         kernels.gemm(X, W, U, trans_b=True, b_mod=z)                       # U = X [Lr; Li]^T
         Y = torch.empty((B, So, So), dtype=torch.float32, device=X.device)
@@ -72,9 +109,57 @@ class RescaleOps:
         return Y
 
 
+def _rescale_tc():
+    import os
+    return os.environ.get("VIP_B200_RESCALE_TC", "1") != "0"
+
+
+def _batched_channel_pca(resc, ncomp, mask_center_px):
+    """PCA across the z channels of every frame of a chunk, several frames per launch (the default configuration of
+    ``_adimsdi_doublepca_ifs``: integer ``ncomp``, no ``scaling``, exact SVD): with G_f = M_f M_f^T (z x z) and E_k its
+    k leading eigenvectors, the residuals of ``_project_subtract`` are R_f = (I - E_k E_k^T) M_f.  The channel
+    matrices of a group of frames are stacked ((g z) x p, g z <= 256): ONE Gramian on the tensor cores serves the
+    group (its diagonal z x z blocks; exact bf16x3 products, fp64 accumulation -- an fp32 Gramian would scramble the
+    noise-level eigenvectors), ONE launch of the batched sub-Gramian eigensolver of the annular path solves the g z
+    problems (problem (f, c) returns column c of E_k E_k^T = E diag(1/lambda) E^T G e_c) and one product applies
+    them -- the same scheme as the spectral pass of the annular ADI+mSDI (``annular.py``).  At BASELINE config 4 the
+    frame-by-frame route spent more time in launch latencies and Python than in its kernels
+    (profiles/r04_summary.md).  resc (F, z, S, S) -> residuals (F, z, S, S)."""
+    F, z, S, _ = resc.shape
+    p = S * S
+    M = resc.reshape(F * z, p)
+    if mask_center_px:
+        mask = torch.as_tensor(circle_mask((S, S), mask_center_px).reshape(-1)).to(M.device)
+        M = M.masked_fill(mask[None, :], 0.0)
+    k = int(ncomp)
+    if k > min(z, p):
+        msg = "{} PCs cannot be obtained from a matrix with size [{},{}]."
+        msg += " Increase the size of the patches or request less PCs"
+        raise RuntimeError(msg.format(k, z, p))
+    group = max(1, 256 // z)
+    R = M.clone()
+    ar = torch.arange(z, dtype=torch.int32, device=M.device)
+    for g0 in range(0, F, group):
+        g1 = min(F, g0 + group)
+        Fg = g1 - g0
+        Ag = M[g0 * z:g1 * z]
+        G = kernels.gram(Ag)
+        base = torch.arange(Fg, device=M.device, dtype=torch.int32).repeat_interleave(z) * z
+        idx = (base[:, None] + ar[None, :]).contiguous()                        # library of (f, c): block f
+        lens = torch.full((Fg * z,), z, dtype=torch.int32, device=M.device)
+        Wt, iters = kernels.annular_weights(G, idx, lens, torch.arange(Fg * z, dtype=torch.int32, device=M.device), k)
+        if bool((iters < 0).any()):
+            raise RuntimeError("vip_b200.pca: spectral eigenproblems did not converge")
+        # W is block diagonal (the library of (f, c) is frame f): apply the Fg diagonal z x z blocks as a batch
+        P = Wt.reshape(Fg, z, Fg, z).diagonal(dim1=0, dim2=2).permute(2, 0, 1).contiguous()      # (Fg, z, z)
+        kernels.gemm(P, Ag.reshape(Fg, z, p), R[g0 * z:g1 * z].reshape(Fg, z, p), alpha=-1.0, beta=1.0)   # R = M - P M
+    return R.reshape(F, z, S, S)
+
+
 def _stage1_frames(cube_dev, frames, ops, ncomp_ifs, scaling, mask_center_px, svd_mode, collapse_ifs,
                    ifs_range):
     """``_adimsdi_doublepca_ifs`` for a chunk of ADI frames: (z, n, H, W) device cube -> (F, H, W)."""
+    from .pca_fullfr import _EXACT_MODES, _mode_name
     z, n, H, W = cube_dev.shape
     F = len(frames)
     i0, i1 = ifs_range
@@ -85,17 +170,28 @@ def _stage1_frames(cube_dev, frames, ops, ncomp_ifs, scaling, mask_center_px, sv
         ms = torch.nn.functional.pad(ms, (ops.pad,) * 4, mode="reflect")   # np.pad(..., 'reflect')
     S = ops.big
     resc = RescaleOps.apply(ms.reshape(F * z, S, S), ops.Wf, z).reshape(F, z, S, S)
-    res = torch.empty_like(resc)
-    for f in range(F):                                                     # PCA across the z channels
-        res[f] = project_subtract_device(resc[f], ncomp_ifs, scaling, mask_center_px, svd_mode)
+    if (isinstance(ncomp_ifs, (int, np.integer)) and scaling is None and _mode_name(svd_mode) in _EXACT_MODES
+            and z <= 256 and ncomp_ifs <= 24 and _batched_stage1()):
+        res = _batched_channel_pca(resc, ncomp_ifs, mask_center_px)
+    else:
+        res = torch.empty_like(resc)
+        for f in range(F):                                                 # PCA across the z channels
+            res[f] = project_subtract_device(resc[f], ncomp_ifs, scaling, mask_center_px, svd_mode)
     desc = RescaleOps.apply(res.reshape(F * z, S, S), ops.Wi, z).reshape(F, z, ops.out, ops.out)
-    out = torch.stack([collapse_device(desc[f, i0:i1], collapse_ifs) for f in range(F)])
+    # collapse over the selected channels of every frame in one launch: (zr, F * out * out) along axis 0
+    sel = desc[:, i0:i1].permute(1, 0, 2, 3).reshape(i1 - i0, F * ops.out, ops.out)
+    out = collapse_device(sel.contiguous(), collapse_ifs).reshape(F, ops.out, ops.out)
     if out.dtype != torch.float32:
         out = out.float()
     if mask_center_px:
         mask = torch.as_tensor(circle_mask((ops.out, ops.out), mask_center_px)).to(out.device)
         out = out.masked_fill(mask[None], 0.0)
     return out
+
+
+def _batched_stage1():
+    import os
+    return os.environ.get("VIP_B200_SDI_BATCHED", "1") != "0"
 
 
 def adimsdi_doublepca_device(cube, angle_list, scale_list, ncomp, scaling=None, mask_center_px=None,
