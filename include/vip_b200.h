@@ -216,6 +216,11 @@ int vb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src_host, size_t spitc
  * several host threads while the previous chunk is on the DMA engine (the driver's own staging is single-threaded,
  * ~10 GB/s); a pinned source is one cudaMemcpyAsync.  The source may be reused when the call returns. */
 int vb_memcpy_h2d_staged(void* dst, const void* src_host, size_t nbytes, void* stream);
+/* The same for `height` strided rows of `width_bytes` (source pitch spitch) into a CONTIGUOUS device buffer: the
+ * frames [f0, f1) of every channel of a (z, n, H, W) IFS cube, uploaded chunk by chunk on a copy stream while the
+ * previous chunk is processed.  Returns after the last DMA has completed. */
+int vb_memcpy2d_h2d_staged(void* dst, const void* src_host, size_t spitch, size_t width_bytes, size_t height,
+                           void* stream);
 
 /* ---- blob detection and FITS decode ------------------------------------------------------
  * mask[y][x] = 1 where img[y][x] is the maximum of its (2 d + 1)^2 neighbourhood (edge-replicated), exceeds

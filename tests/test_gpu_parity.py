@@ -687,6 +687,36 @@ def test_annular_weights_kernel_vs_numpy():
         assert np.count_nonzero(W[q]) <= len(I)
 
 
+
+def test_annular_direct_solver_tiny_libraries():
+    """Direct solver with libraries of fewer than 8 frames (the channel PCA of a 6-channel IFS cube runs it with
+    Lmax = 6, k = 2): the per-warp scratch of its Gershgorin reduction used to overrun the Lmax-sized vectors."""
+    import torch
+    from vip_b200 import kernels
+    rng = np.random.default_rng(8)
+    n, npx, k, Lmax = 24, 500, 2, 6
+    A = rng.normal(size=(n, npx)) * 3 + 100.0 / (1 + (np.arange(npx) / 50.0) ** 2)
+    G = A @ A.T
+    nprob = 12
+    frames = rng.integers(0, n, nprob).astype(np.int32)
+    lens = np.array([6, 6, 6, 5, 4, 3, 2, 6, 6, 1, 6, 6], np.int32)
+    idx = np.zeros((nprob, Lmax), np.int32)
+    for q in range(nprob):
+        idx[q, :lens[q]] = np.sort(rng.choice(n, lens[q], replace=False))
+    W, iters = kernels.annular_weights(torch.from_numpy(G).cuda(), torch.from_numpy(idx).cuda(),
+                                       torch.from_numpy(lens).cuda(), torch.from_numpy(frames).cuda(), k,
+                                       force_direct=True)
+    W = W.cpu().numpy()
+    assert (iters.cpu().numpy() == 100000).all()
+    for q in range(nprob):
+        I = idx[q, :lens[q]]
+        w_, v_ = np.linalg.eigh(G[np.ix_(I, I)])
+        kk = min(k, len(I))
+        X, th = v_[:, ::-1][:, :kk], w_[::-1][:kk]
+        wref = X @ ((X.T @ G[I, frames[q]]) / th)
+        assert np.max(np.abs(W[q, I] - wref)) < 1e-5 * max(1.0, np.max(np.abs(wref))), q
+
+
 @pytest.mark.parametrize("flat", [False, True])
 def test_annular_direct_solver_vs_numpy(flat):
     """Direct (Householder + bisection + inverse iteration) solver, forced for every problem: gapped

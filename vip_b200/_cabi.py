@@ -60,6 +60,7 @@ SIGNATURES = {
     "vb_local_max_mask_f32": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
     "vb_fits_decode_f32": (_i, [_vp, _i, _sz, _d, _d, _vp, _vp]),
     "vb_memcpy_h2d_staged": (_i, [_vp, _vp, _sz, _vp]),
+    "vb_memcpy2d_h2d_staged": (_i, [_vp, _vp, _sz, _sz, _sz, _vp]),
     "vb_profile_enable": (None, [_i]),
     "vb_profile_read": (_i, [C.POINTER(_f)]),
 }

@@ -474,13 +474,15 @@ __device__ void annular_direct_one(const AnnularArgs& p, int q, double* __restri
     const int k = (p.ncomp < L) ? p.ncomp : L;
     double* slot = ws + (size_t)blockIdx.x * Lmax * Lmax;  // global workspace slot of this CTA (Lmax^2 doubles)
 
-    // shared layout
-    double* d = sm;                       // [Lmax]
-    double* e = d + Lmax;                 // [Lmax]   e[j] couples j and j+1
-    double* tau = e + Lmax;               // [Lmax]
-    double* vv = tau + Lmax;              // [Lmax]
-    double* pp = vv + Lmax;               // [Lmax]
-    double* red = pp + Lmax;              // [8]
+    // shared layout (the five vectors hold at least 8 entries: vv / pp double as per-warp scratch of the Gershgorin
+    // reduction -- with libraries of fewer than 8 frames they used to overrun into `red`)
+    const int Lv = Lmax < 8 ? 8 : Lmax;
+    double* d = sm;                       // [Lv]
+    double* e = d + Lv;                   // [Lv]   e[j] couples j and j+1
+    double* tau = e + Lv;                 // [Lv]
+    double* vv = tau + Lv;                // [Lv]
+    double* pp = vv + Lv;                 // [Lv]
+    double* red = pp + Lv;                // [8]
     double* scal = red + 8;               // [8]  broadcast scalars
     double* lam = scal + 8;               // [32]
     double* blo = lam + 32;               // [32]
@@ -965,10 +967,12 @@ annular_direct_kernel(AnnularArgs p, const int* __restrict__ plist, int nlist, d
 int annular_direct_slots() { return 3 * kNumSMs; }      // upper bound of the workspace slots (= CTAs) of one launch
 
 size_t annular_direct_smem_bytes(int k, int Lmax) {
-    return ((size_t)5 * Lmax + 16 + 96 + (size_t)4 * k * Lmax) * sizeof(double) + ((size_t)AT + Lmax) * sizeof(int) + 16;
+    const int Lv = Lmax < 8 ? 8 : Lmax;
+    return ((size_t)5 * Lv + 16 + 96 + (size_t)4 * k * Lmax) * sizeof(double) + ((size_t)AT + Lmax) * sizeof(int) + 16;
 }
 size_t annular_direct_packed_smem_bytes(int k, int Lmax) {
-    return ((size_t)5 * Lmax + 16 + 96 + (size_t)k * Lmax + (size_t)Lmax * (Lmax + 1) / 2) * sizeof(double) +
+    const int Lv = Lmax < 8 ? 8 : Lmax;
+    return ((size_t)5 * Lv + 16 + 96 + (size_t)k * Lmax + (size_t)Lmax * (Lmax + 1) / 2) * sizeof(double) +
            ((size_t)AT + Lmax) * sizeof(int) + 16;
 }
 

@@ -70,6 +70,7 @@ int scatter_columns(const float*, int, int, const int*, size_t, float*, cudaStre
 int profile_read(float* out);
 int fp32_probe(float*, int, int, cudaStream_t);
 int memcpy_h2d_staged(void*, const void*, size_t, cudaStream_t);
+int memcpy2d_h2d_staged(void*, const void*, size_t, size_t, size_t, cudaStream_t);
 int local_max_mask(const float*, int, int, int, float, unsigned char*, cudaStream_t);
 int fits_decode(const void*, int, size_t, double, double, float*, cudaStream_t);
 int aperture_sums(const float*, int, int, const double*, const double*, int, double, double*, cudaStream_t);
@@ -394,6 +395,11 @@ int vb_fp32_probe(float* out, int blocks, int iters, void* stream) {
 
 int vb_memcpy_h2d_staged(void* dst, const void* src_host, size_t nbytes, void* stream) {
     return memcpy_h2d_staged(dst, src_host, nbytes, (cudaStream_t)stream);
+}
+
+int vb_memcpy2d_h2d_staged(void* dst, const void* src_host, size_t spitch, size_t width_bytes, size_t height,
+                           void* stream) {
+    return memcpy2d_h2d_staged(dst, src_host, spitch, width_bytes, height, (cudaStream_t)stream);
 }
 
 void vb_profile_enable(int on) { profile_enable(on); }

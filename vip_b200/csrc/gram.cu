@@ -487,6 +487,76 @@ int memcpy_h2d_staged(void* dst, const void* src_host, size_t nbytes, cudaStream
     return 0;
 }
 
+// Strided rows of a host array -> contiguous device buffer (height rows of width bytes, source pitch spitch): the
+// same multi-threaded pinned staging as memcpy_h2d_staged, the worker threads gathering the rows.  Used to upload the
+// frames [f0, f1) of every spectral channel of a (z, n, H, W) IFS cube chunk by chunk on a copy stream while the
+// previous chunk is being processed (psfsub/sdi.py).  Returns after the last DMA has completed.
+int memcpy2d_h2d_staged(void* dst, const void* src_host, size_t spitch, size_t width, size_t height, cudaStream_t st) {
+    if (width == 0 || height == 0) return 0;
+    if (spitch == width) return memcpy_h2d_staged(dst, src_host, width * height, st);
+    if (host_is_pinned(src_host) || getenv("VIP_B200_NO_STAGING") != nullptr) {
+        VB_CHECK_CUDA(cudaMemcpy2DAsync(dst, width, src_host, spitch, width, height, cudaMemcpyHostToDevice, st));
+        VB_CHECK_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
+    static Stager stagers[64];
+    static std::mutex mu;
+    int dev = 0;
+    VB_CHECK_CUDA(cudaGetDevice(&dev));
+    VB_REQUIRE(dev >= 0 && dev < 64, "memcpy2d_h2d_staged: device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(mu);
+    Stager& sg = stagers[dev];
+    const size_t chunk = (size_t)32 << 20;
+    if (!sg.ev_ready) {
+        for (int i = 0; i < 2; ++i) VB_CHECK_CUDA(cudaEventCreateWithFlags(&sg.done[i], cudaEventDisableTiming));
+        sg.ev_ready = true;
+    }
+    if (sg.cap < chunk) {
+        for (int i = 0; i < 2; ++i) {
+            if (sg.buf[i]) cudaFreeHost(sg.buf[i]);
+            sg.buf[i] = nullptr;
+            if (cudaHostAlloc(&sg.buf[i], chunk, cudaHostAllocDefault) != cudaSuccess) {
+                (void)cudaGetLastError();
+                sg.cap = 0;
+                VB_CHECK_CUDA(cudaMemcpy2DAsync(dst, width, src_host, spitch, width, height, cudaMemcpyHostToDevice, st));
+                VB_CHECK_CUDA(cudaStreamSynchronize(st));
+                return 0;
+            }
+        }
+        sg.cap = chunk;
+    }
+    const int nt = stager_threads();
+    const char* src = reinterpret_cast<const char*>(src_host);
+    char* d = reinterpret_cast<char*>(dst);
+    const size_t nbytes = width * height;
+    int s = 0;
+    for (size_t off = 0; off < nbytes; off += chunk, ++s) {
+        const size_t len = (nbytes - off < chunk) ? nbytes - off : chunk;
+        const int b = s & 1;
+        if (s >= 2) VB_CHECK_CUDA(cudaEventSynchronize(sg.done[b]));
+        char* sb = reinterpret_cast<char*>(sg.buf[b]);
+        auto work = [&](int t) {
+            size_t a = off + len * t / nt;                      // destination-contiguous byte range [a, a1)
+            const size_t a1 = off + len * (t + 1) / nt;
+            while (a < a1) {
+                const size_t row = a / width, col = a % width;
+                size_t m = width - col;
+                if (m > a1 - a) m = a1 - a;
+                memcpy(sb + (a - off), src + row * spitch + col, m);
+                a += m;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+        VB_CHECK_CUDA(cudaMemcpyAsync(d + off, sb, len, cudaMemcpyHostToDevice, st));
+        VB_CHECK_CUDA(cudaEventRecord(sg.done[b], st));
+    }
+    for (int b = 0; b < 2 && b < s; ++b) VB_CHECK_CUDA(cudaEventSynchronize(sg.done[b]));
+    return 0;
+}
+
 // one pixel slab to the device on `copy_stream`: direct strided DMA from pinned memory, or staged (buffer s % 2)
 static int upload_slab(const float* host, int n, size_t p, size_t c0, size_t c1, float* M, Stager* staged, int s,
                        cudaStream_t copy_stream) {

@@ -147,9 +147,11 @@ def _batched_channel_pca(resc, ncomp, mask_center_px):
         base = torch.arange(Fg, device=M.device, dtype=torch.int32).repeat_interleave(z) * z
         idx = (base[:, None] + ar[None, :]).contiguous()                        # library of (f, c): block f
         lens = torch.full((Fg * z,), z, dtype=torch.int32, device=M.device)
-        Wt, iters = kernels.annular_weights(G, idx, lens, torch.arange(Fg * z, dtype=torch.int32, device=M.device), k)
-        if bool((iters < 0).any()):
-            raise RuntimeError("vip_b200.pca: spectral eigenproblems did not converge")
+        # the direct (tridiagonalisation) solver for every problem: 39 x 39 matrices cost it ~50 us each, it cannot
+        # fail to converge, and -- unlike the subspace iteration with its fallback list -- needs no host round trip,
+        # so the host keeps enqueueing (and uploading the next chunk) while the GPU works
+        Wt, _ = kernels.annular_weights(G, idx, lens, torch.arange(Fg * z, dtype=torch.int32, device=M.device), k,
+                                        force_direct=True)
         # W is block diagonal (the library of (f, c) is frame f): apply the Fg diagonal z x z blocks as a batch
         P = Wt.reshape(Fg, z, Fg, z).diagonal(dim1=0, dim2=2).permute(2, 0, 1).contiguous()      # (Fg, z, z)
         kernels.gemm(P, Ag.reshape(Fg, z, p), R[g0 * z:g1 * z].reshape(Fg, z, p), alpha=-1.0, beta=1.0)   # R = M - P M
@@ -187,6 +189,65 @@ def _stage1_frames(cube_dev, frames, ops, ncomp_ifs, scaling, mask_center_px, sv
         mask = torch.as_tensor(circle_mask((ops.out, ops.out), mask_center_px)).to(out.device)
         out = out.masked_fill(mask[None], 0.0)
     return out
+
+
+class _FrameFeeder:
+    """Frames [f0, f1) of every channel of a (z, n, H, W) host cube (a reference cube, if any, continues the frame
+    axis) -> (z, F, H, W) device tensors, uploaded on a copy stream ``depth`` chunks ahead of the chunk whose kernels
+    are being enqueued (``vb_memcpy2d_h2d_staged``: strided rows gathered into pinned buffers by worker threads).  At
+    BASELINE config 4 the 3.07 GB upload (110 ms from a pageable numpy array) disappears behind the first pass."""
+
+    def __init__(self, cube, cube_ref, chunks, dev, depth=3):
+        self.cubes = [cube] + ([cube_ref] if cube_ref is not None else [])
+        self.n = cube.shape[1]
+        self.chunks, self.dev, self.depth = chunks, dev, depth
+        self.pending = {}
+        self.issued = 0
+        self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+
+    def _upload_one(self, cube, f0, f1):
+        z, n, H, W = cube.shape
+        fast = (self.stream is not None and isinstance(cube, np.ndarray) and cube.dtype == np.float32
+                and cube.flags["C_CONTIGUOUS"])
+        if not fast:
+            part = cube[:, f0:f1]
+            return to_device_f32(np.ascontiguousarray(part) if isinstance(part, np.ndarray) else part, self.dev)
+        from .. import _cabi
+        from .._device import stream_ptr
+        out = torch.empty((z, f1 - f0, H, W), dtype=torch.float32, device=self.dev)
+        frame_bytes = H * W * 4
+        _cabi.check(_cabi.lib().vb_memcpy2d_h2d_staged(int(out.data_ptr()), int(cube.ctypes.data) + f0 * frame_bytes,
+                                                       n * frame_bytes, (f1 - f0) * frame_bytes, z, stream_ptr()),
+                    "vb_memcpy2d_h2d_staged")
+        return out
+
+    def _upload(self, i):
+        f0, f1 = self.chunks[i]
+        parts = []
+        if f0 < self.n:
+            parts.append(self._upload_one(self.cubes[0], f0, min(f1, self.n)))
+        if f1 > self.n:
+            parts.append(self._upload_one(self.cubes[1], max(f0, self.n) - self.n, f1 - self.n))
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+
+    def get(self, i):
+        """Device tensor of chunk i (ready on the current stream); keeps the uploads ``depth`` chunks ahead."""
+        while self.issued < min(len(self.chunks), i + self.depth):
+            j = self.issued
+            if self.stream is None:
+                self.pending[j] = (self._upload(j), None)
+            else:
+                with torch.cuda.stream(self.stream):
+                    t = self._upload(j)
+                    ev = torch.cuda.Event()
+                    ev.record(self.stream)
+                self.pending[j] = (t, ev)
+            self.issued += 1
+        t, ev = self.pending.pop(i)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            t.record_stream(torch.cuda.current_stream())
+        return t
 
 
 def _batched_stage1():
@@ -235,16 +296,15 @@ def adimsdi_doublepca_device(cube, angle_list, scale_list, ncomp, scaling=None, 
     ifs_range = (0, z) if ifs_collapse_range == "all" else (int(ifs_collapse_range[0]), int(ifs_collapse_range[1]))
 
     dev = require_cuda()
-    cube_dev = to_device_f32(cube, dev)
-    if nr:
-        cube_dev = torch.cat((cube_dev, to_device_f32(cube_ref, dev)), dim=1)      # np.concatenate(..., axis=1)
     ops = RescaleOps(scale_list, y_in, dev)
     per_frame = 4 * z * ops.big * ops.big * 4 * 2          # rescaled + U + residuals + descaled (upper bound)
     chunk = max(1, min(n + nr, int(_CHUNK_BYTES // per_frame)))
+    chunks = [(f0, min(n + nr, f0 + chunk)) for f0 in range(0, n + nr, chunk)]
+    feeder = _FrameFeeder(cube, cube_ref if nr else None, chunks, dev)      # the reference frames follow the cube's
     parts = []
-    for f0 in range(0, n + nr, chunk):
-        frames = list(range(f0, min(n + nr, f0 + chunk)))
-        parts.append(_stage1_frames(cube_dev, frames, ops, ncomp_ifs, scaling[0], mask_center_px, svd_mode,
+    for i, (f0, f1) in enumerate(chunks):
+        sub = feeder.get(i)                                                  # (z, F, H, W), uploaded ahead
+        parts.append(_stage1_frames(sub, list(range(f1 - f0)), ops, ncomp_ifs, scaling[0], mask_center_px, svd_mode,
                                     collapse_ifs, ifs_range))
     res_channels = torch.cat(parts)                          # (n, H, W)
     if verbose:
