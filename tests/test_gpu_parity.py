@@ -909,7 +909,15 @@ def test_pca_annular_ncomp_auto_vs_oracle(vb):
         # residual peak 27 under a 1e4 halo: 1e-4 of the peak is 0.4 eps32 of the samples the fp32 GEMM subtracts
         # (measured on the B200: up to 1.02e-4 with 6-8 components); the bound is 2e-4, the float64-truth rule
         assert e64 < 2 * PCA_TOL and e32 < 5e-4, kw
-        assert rel_err(r[2], o64[2]) < FRAME_TOL, kw
+        # final frame: FRAME_TOL of ITS peak -- or, since that peak is several times smaller than the residual cube's
+        # and a median of derotated frames cannot be more accurate in absolute terms than the frames it is taken from
+        # (the median is 1-Lipschitz in the sup norm), an absolute error within twice the measured error of the
+        # residual cube.  Measured on the B200: 2.9e-4 ... 3.2e-4 of the frame peak from run to run (the auto rule's
+        # shared-memory atomics reorder fp64 sums) = 0.97 of the residual-cube error.
+        e_frame = rel_err(r[2], o64[2])
+        m = ~np.isnan(o64[2])
+        abs_frame = float(np.max(np.abs(r[2][m] - o64[2][m])))
+        assert e_frame < FRAME_TOL or abs_frame < 2 * e64 * scale, (kw, e_frame, abs_frame, e64 * scale)
     # the rule itself: chosen numbers of components of one segment against the rule on the residual matrix (numpy)
     rng = np.random.default_rng(2)
     n, npx = 30, 400
