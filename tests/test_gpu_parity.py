@@ -1212,6 +1212,52 @@ def test_rescale_tc_matches_cuda_core_path(vb, monkeypatch):
     assert float((out_i - ref_i).abs().max()) < 4e-6 * float(ref_i.abs().max())
 
 
+def _rdi_masks(size):
+    yy, xx = O.get_annulus_segments((size, size), 3, 7)[0]
+    boat = np.zeros((size, size)); boat[yy, xx] = 1
+    yy, xx = O.get_annulus_segments((size, size), 8, 6)[0]
+    anchor = np.zeros((size, size)); anchor[yy, xx] = 1
+    return anchor, boat
+
+
+def test_pca_mask_rdi_data_imputation(vb):
+    """``pca(cube, angs, cube_ref=, mask_rdi=(anchor, boat) | anchor, ncomp=k)`` against the oracle restatement of
+    ``cube_subtract_sky_pca`` that is pinned bit-identically to the unmodified reference
+    (tests/test_oracle_vs_reference.py::test_pca_mask_rdi_bit_identical); the reference's fp32 arithmetic (sgemm
+    Gramian of a 1e4 halo, fp32 matrix inverse) is the noisy side, so the float64 run of the oracle is the truth."""
+    cube, angs = adi_cube(16, 33, 3, 60.0, seed=21)
+    cref = adi_cube(12, 33, 3, 60.0, seed=22)[0]
+    anchor, boat = _rdi_masks(33)
+    for masks in ((anchor, boat), anchor):
+        o64 = O.pca_fullframe(cube.astype(np.float64), angs, cube_ref=cref.astype(np.float64), mask_rdi=masks, ncomp=3,
+                              full_output=True)
+        fr, pcs, recon, res, res_ = vb.pca(cube, angs, cube_ref=cref, mask_rdi=masks, ncomp=3, verbose=False,
+                                           full_output=True)
+        assert fr.dtype == np.float32 and pcs.shape == o64[1].shape == (12, 33, 33) and recon.shape == cube.shape
+        assert np.max(np.abs(res - o64[3])) < 1e-4 * np.max(np.abs(o64[3]))
+        assert np.max(np.abs(recon - o64[2])) < 1e-5 * np.max(np.abs(o64[2]))
+        for j in range(3):                                   # boat components up to their sign
+            d = min(np.max(np.abs(pcs[j] - o64[1][j])), np.max(np.abs(pcs[j] + o64[1][j])))
+            assert d < 1e-4 * np.max(np.abs(o64[1][j])), j
+        assert rel_err(fr, o64[0]) < FRAME_TOL
+        assert np.array_equal(vb.pca(cube, angs, cube_ref=cref, mask_rdi=masks, ncomp=3, verbose=False), fr)
+    with pytest.raises(TypeError):
+        vb.pca(cube, angs, cube_ref=cref, mask_rdi=(anchor, boat), ncomp=3, ref_strategy="ARDI", verbose=False)
+    with pytest.raises(TypeError):
+        vb.pca(cube, angs, mask_rdi=(anchor, boat), ncomp=3, verbose=False)
+def test_pca_batch_from_fits_paths(vb, tmp_path):
+    """``pca(cube='cube.fits', angle_list='angs.fits', batch=...)`` (``utils_pca.py:508-519``): the mini-batches are
+    sliced from a memory map of the file's big-endian data unit; same result as with the arrays."""
+    cube, angs = adi_cube(23, 33, 3, 60.0, seed=11)
+    cpath, apath = str(tmp_path / "cube.fits"), str(tmp_path / "angs.fits")
+    vb.write_fits(cpath, cube, verbose=False)
+    vb.write_fits(apath, angs.astype(np.float32), verbose=False)
+    want = vb.pca(cube, angs.astype(np.float32).astype(np.float64), ncomp=3, batch=6, verbose=False, full_output=True)
+    got = vb.pca(cpath, apath, ncomp=3, batch=6, verbose=False, full_output=True)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+
+
 # ------------------------------------------------------------------ Fourier shift, median subtraction
 SHIFT_TOL = 2e-5
 

@@ -237,3 +237,34 @@ def test_pca_adimsdi_fullframe_options_bit_identical(ref):
     np.testing.assert_allclose(np.asarray(r[2]["S/Ns"], dtype=float), np.asarray(o[2]["S/Ns"], dtype=float), rtol=1e-13)
     np.testing.assert_allclose(np.asarray(r[2]["fluxes"], dtype=float), np.asarray(o[2]["fluxes"], dtype=float),
                                rtol=1e-13)
+
+
+def _rdi_masks(size):
+    from oracle import vip_oracle as O_
+    ones = np.ones((size, size))
+    yy, xx = O_.get_annulus_segments((size, size), 3, 7)[0]
+    boat = np.zeros((size, size)); boat[yy, xx] = 1
+    yy, xx = O_.get_annulus_segments((size, size), 8, 6)[0]
+    anchor = np.zeros((size, size)); anchor[yy, xx] = 1
+    return anchor, boat
+
+
+def test_pca_mask_rdi_bit_identical(ref):
+    """``pca(cube, angs, cube_ref=ref, mask_rdi=(anchor, boat), ncomp=k)``: PCA with data imputation
+    (``pca_fullfr.py:966-972`` -> ``cube_subtract_sky_pca``, ``preproc/skysubtraction.py:36-260``), two masks and one."""
+    psfsub, _ = ref
+    cube, angs = adi_cube(16, 33, 3, 60.0, seed=21)
+    cref = adi_cube(12, 33, 3, 60.0, seed=22)[0]
+    anchor, boat = _rdi_masks(33)
+    for masks in ((anchor, boat), anchor):
+        for dt in (np.float32, np.float64):
+            r = psfsub.pca(cube.astype(dt), angs, cube_ref=cref.astype(dt), mask_rdi=masks, ncomp=3, verbose=False,
+                           full_output=True)
+            o = O.pca_fullframe(cube.astype(dt), angs, cube_ref=cref.astype(dt), mask_rdi=masks, ncomp=3,
+                                full_output=True)
+            assert len(r) == len(o) == 5
+            for a, b in zip(r, o):
+                assert a.dtype == b.dtype and a.shape == b.shape
+                np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(psfsub.pca(cube, angs, cube_ref=cref, mask_rdi=(anchor, boat), ncomp=2, verbose=False),
+                                  O.pca_fullframe(cube, angs, cube_ref=cref, mask_rdi=(anchor, boat), ncomp=2))

@@ -109,13 +109,18 @@ class IncrementalModel:
 
 def pca_incremental(cube, angle_list, batch=0.25, ncomp=1, collapse="median", verbose=True, full_output=False,
                     return_residuals=False, start_time=None, weights=None, **rot_options):
-    """Drop-in for ``vip_hci.psfsub.utils_pca.pca_incremental`` with a numpy cube (FITS paths are outside the
-    hot path).  Returns ``frame``; with ``full_output`` ``(frame, model, pcs, medians)`` where ``model`` is the
+    """Drop-in for ``vip_hci.psfsub.utils_pca.pca_incremental``: ``cube`` / ``angle_list`` are numpy arrays or paths
+    of FITS files (``vip_b200.fits``, no astropy needed).  Returns ``frame``; with ``full_output`` ``(frame, model, pcs, medians)`` where ``model`` is the
     :class:`IncrementalModel` (the reference returns its scikit-learn object there); with ``return_residuals``
     the (n, y, x) residual cube."""
-    if isinstance(cube, str) or isinstance(angle_list, str):
-        raise NotImplementedError("vip_b200.pca_incremental: FITS paths are not implemented (FITS I/O is outside the "
-                                  "hot path); pass numpy arrays (np.memmap works)")
+    # FITS paths (utils_pca.py:508-519): the data unit of the first HDU as a (big-endian) memory map -- the mini-batches
+    # are sliced from it, converted and uploaded one at a time, the file is never read as a whole
+    if isinstance(cube, str):
+        from ..fits import open_fits
+        cube = open_fits(cube, n=0, return_memmap=True, verbose=False)
+    if isinstance(angle_list, str):
+        from ..fits import open_fits
+        angle_list = np.asarray(open_fits(angle_list, verbose=False))
     if not isinstance(cube, np.ndarray):
         raise TypeError("`cube` must be a str (full path on disk) or a numpy array")
     if not isinstance(angle_list, np.ndarray):

@@ -197,12 +197,62 @@ def project_subtract_device(cube_dev, ncomp, scaling=None, mask_center_px=None, 
     return residuals_cube
 
 
+def sky_pca_residuals_device(cube_dev, ref_dev, masks, ncomp, full_output=False):
+    """PCA with data imputation: ``cube_subtract_sky_pca(cube, cube_ref, mask_rdi, ncomp, full_output=True)``
+    (``preproc/skysubtraction.py:36-260``) as reached from ``_adi_rdi_pca`` (``pca_fullfr.py:966-972``).
+
+    The reference builds four masked copies of the cubes, the eigen-images of the reference ("sky") cube on the
+    ANCHOR mask (all of them, through an SVD of the nr x nr Gramian), projects the anchor-masked science frames on
+    them, inverts the nr x nr Gramian of the eigen-images and rebuilds the first ``ncomp`` terms on the BOAT mask.  In
+    exact arithmetic that Gramian is diag(lambda), so with (lambda_j, v_j) the leading eigenpairs of
+    G = S_a S_a^T (S_a: anchor-masked reference frames) the model of frame i is
+    ``sum_{j<ncomp} (v_j . (S_a C_a[i])) / lambda_j * (v_j^T S_b)``: one Gramian, one top-k eigensolve, one cross
+    Gramian ``C_a S_a^T``, the boat components ``v_j^T S_b`` as an error-free fp32 pair and the high-precision
+    projection kernel of the PCA path -- the sign of v_j cancels.
+    Returns residuals (n,H,W) or (residuals, sky_opt (n,H,W), sky_boat_cube (nr,H,W): ALL nr boat components)."""
+    n, y, x = cube_dev.shape
+    nr = ref_dev.shape[0]
+    if tuple(ref_dev.shape[1:]) != (y, x):
+        raise TypeError("Science and Sky frames sizes do not match")
+    if type(masks) not in (list, tuple):
+        mask_anchor = np.asarray(masks)
+        mask_boat = np.ones(mask_anchor.shape)
+    elif len(masks) != 2:
+        raise TypeError("Science and Reference frames sizes do not match")
+    else:
+        mask_anchor, mask_boat = np.asarray(masks[0]), np.asarray(masks[1])
+    if mask_anchor.shape != (y, x) or mask_boat.shape != (y, x):
+        raise IndexError("mask_rdi: masks must have the shape of a frame")
+    if not isinstance(ncomp, (int, np.integer)):
+        raise TypeError("'float' object cannot be interpreted as an integer")          # range(ncomp) in the reference
+    k = int(ncomp)
+    if k > nr:
+        raise IndexError("index {} is out of bounds for axis 0 with size {}".format(nr, nr))
+    dev = cube_dev.device
+    p = y * x
+    za = torch.as_tensor(mask_anchor == 0).reshape(-1).to(dev)
+    zb = torch.as_tensor(mask_boat == 0).reshape(-1).to(dev)
+    ref2, sci2 = ref_dev.reshape(nr, p), cube_dev.reshape(n, p)
+    Sa, Sb = ref2.masked_fill(za[None, :], 0.0), ref2.masked_fill(zb[None, :], 0.0)
+    Ca, Cb = sci2.masked_fill(za[None, :], 0.0), sci2.masked_fill(zb[None, :], 0.0)
+    dec = Decomposition(Sa, None if full_output else k)          # eigenpairs of S_a S_a^T (all of them for the pcs)
+    lam, Vk = dec.evals[:k], dec.U[:k].contiguous()
+    Bhi, Blo = kernels.pcs_hilo(Vk, Sb)                          # boat components v_j^T S_b, (k, p)
+    T = kernels.cross_gram(Ca, Sa)                               # (n, nr) fp64 = C_a S_a^T
+    Cm = ((T @ Vk.t()) / lam[None, :]).contiguous()              # (n, k) coefficients on the anchor
+    res = kernels.project_subtract_hp(Cb, Cm, Bhi, Blo)
+    if not full_output:
+        return res.reshape(n, y, x)
+    sky_opt = kernels.sub(Cb, res)
+    boat_all = kernels.pcs(dec.U.contiguous(), Sb)               # (nr, p)
+    return res.reshape(n, y, x), sky_opt.reshape(n, y, x), boat_all.reshape(nr, y, x)
+
+
 def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_px, svd_mode, collapse,
                         verbose, full_output, weights=None, cube_sig=None, random_state=None,
                         keep_on_device=False, source_xy=None, delta_rot=None, fwhm=4, min_frames_pca=10,
-                        max_frames_pca=None, left_eigv=False, _defer_check=True, **rot_options):
-    """``_adi_rdi_pca`` (``pca_fullfr.py:801-1035``) for scalar ``ncomp`` without ``batch`` /
-    ``mask_rdi``: PCA residuals (whole matrix, or frame by frame with a PA-rejection library when
+                        max_frames_pca=None, left_eigv=False, mask_rdi=None, _defer_check=True, **rot_options):
+    """``_adi_rdi_pca`` (``pca_fullfr.py:801-1035``) for scalar ``ncomp`` without ``batch``: PCA residuals (whole matrix, or frame by frame with a PA-rejection library when
     ``source_xy`` is given) -> derotation -> collapse."""
     n, y, x = cube.shape
     angle_list = check_pa_vector(np.asarray(angle_list))
@@ -225,6 +275,8 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
     dev = require_cuda()
     as_dev = (lambda a: a.to(dev).float()) if isinstance(cube, torch.Tensor) else (lambda a: to_device_f32(a, dev))
     gram = None
+    if mask_rdi is not None and cube_ref is None:
+        raise TypeError("`mask_rdi` (PCA with data imputation) needs a reference cube (`cube_ref`)")
     plain = (cube_ref is None and cube_sig is None and scaling is None and not mask_center_px
              and source_xy is None
              and _mode_name(svd_mode) in _EXACT_MODES and isinstance(ncomp, (int, np.integer)))
@@ -237,7 +289,12 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
     ref_dev = as_dev(cube_ref) if cube_ref is not None else None
     sig_dev = as_dev(cube_sig) if cube_sig is not None else None
 
-    if source_xy is not None:
+    pending = None
+    if mask_rdi is not None:
+        # PCA with data imputation (:966-972): pcs = boat components of the reference cube, recon = the sky model
+        out_rdi = sky_pca_residuals_device(cube_dev, ref_dev, mask_rdi, ncomp, full_output)
+        residuals_cube, recon, V = out_rdi if full_output else (out_rdi, None, None)
+    elif source_xy is not None:
         residuals_cube, recon, nfrslib = pa_rejection_residuals_device(
             cube_dev, ref_dev, sig_dev, angle_list, ncomp, scaling, mask_center_px, svd_mode, source_xy,
             delta_rot, fwhm, min_frames_pca, max_frames_pca, full_output, in_dtype=_np_dtype_of(cube))
@@ -264,7 +321,7 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
         mask = torch.as_tensor(circle_mask((y, x), mask_center_px)).to(dev)
         residuals_cube_ = residuals_cube_.masked_fill(mask[None], 0.0)
         frame = frame.masked_fill(mask, 0.0)
-    if source_xy is None and pending:
+    if source_xy is None and mask_rdi is None and pending:
         torch.cuda.current_stream().synchronize()
         if any(int(rec[1]) == 0 for rec in pending):
             # rare: subspace iteration stalled (flat spectrum) -> redo with the synchronous path, which falls
@@ -275,7 +332,9 @@ def _adi_rdi_pca_device(cube, cube_ref, angle_list, ncomp, scaling, mask_center_
                                        left_eigv=left_eigv, _defer_check=False, **rot_options)
     if verbose:
         print("Done de-rotating and combining")
-    if full_output and source_xy is not None:
+    if full_output and mask_rdi is not None:
+        out = (V, recon, residuals_cube, residuals_cube_, frame)       # pcs = sky_boat_cube, recon = sky_opt (:969-972)
+    elif full_output and source_xy is not None:
         out = (recon.reshape(n, y, x), residuals_cube, residuals_cube_, frame)       # pca_fullfr.py:996-1000
     elif full_output and left_eigv:
         # `left_eigv` projects on the temporal (left) singular vectors U_k: U_k U_k^T M = M V_k^T V_k, the same
@@ -676,9 +735,7 @@ def pca(*all_args: List, **all_kwargs: dict):
 
     if p.batch is not None:
         # incremental PCA in mini-batches (pca_fullfr.py:838-856 -> utils_pca.py:431-614)
-        if isinstance(p.cube, str):
-            _unsupported("`batch` with a FITS path (FITS I/O is outside the hot path)")
-        if p.scale_list is not None or p.cube.ndim == 4:
+        if p.scale_list is not None or (not isinstance(p.cube, str) and p.cube.ndim == 4):
             _unsupported("`batch` with 4-d / ADI+mSDI cubes")
         if p.cube_ref is not None:
             raise ValueError("RDI not compatible with batch mode")
@@ -716,8 +773,6 @@ def pca(*all_args: List, **all_kwargs: dict):
                         or p.cube_sig is not None or _mode_name(p.svd_mode) not in _EXACT_MODES):
         _unsupported("`left_eigv` together with mask_center_px / source_xy / cube_sig / tuple ncomp / "
                      "randomized SVD")
-    if p.mask_rdi is not None:
-        _unsupported("`mask_rdi` (data imputation)")
     if p.smooth is not None:
         _unsupported("`smooth`")
     imlib = _mode_name(p.imlib)
