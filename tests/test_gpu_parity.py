@@ -1258,6 +1258,29 @@ def test_pca_batch_from_fits_paths(vb, tmp_path):
         np.testing.assert_array_equal(a, b)
 
 
+def test_pca_annular_beyond_the_batched_solver_limits(vb):
+    """``pca_annular`` with more components (ncomp > 24) or larger libraries (> 256 frames) than the batched
+    sub-Gramian eigensolver takes: the frame-by-frame route through the full-size eigensolvers.  With 30 components
+    of a 36-frame library the trailing eigenvalues are at the noise floor of the data: the reference's own fp32 run is
+    3.8e-4 of the residual peak away from its float64 run, the CUDA path 1.9e-4 (measured on the B200,
+    tools/annular_fallback_probe.py: 1.85e-4 / 3.75e-4 at ncomp=30, 1.65e-4 / 3.41e-4 at ncomp=26, 5.6e-5 / 1.0e-4
+    with 270-frame libraries) -- the float64-truth rule of this file applies."""
+    cube, angs = adi_cube(40, 36, 3, 80.0, seed=9)
+    kw = dict(ncomp=30, asize=6, delta_rot=0.05, radius_int=2)
+    co, cd, fr = vb.pca_annular(cube, angs, verbose=False, full_output=True, **kw)
+    o32 = O.pca_annular(cube, angs, full_output=True, **kw)
+    assert co.shape == o32[0].shape and fr.shape == o32[2].shape and np.isfinite(fr).all()
+    assert_parity(co, o32[0], lambda: O.pca_annular(cube.astype(np.float64), angs, full_output=True, **kw)[0],
+                  PCA_TOL, "pca_annular ncomp=30")
+    # libraries of 270 frames
+    cube, angs = adi_cube(300, 20, 3, 170.0, seed=10)
+    kw = dict(ncomp=4, asize=5, delta_rot=0.1, max_frames_lib=270, radius_int=2)
+    co, cd, fr = vb.pca_annular(cube, angs, verbose=False, full_output=True, **kw)
+    oo, od, of = O.pca_annular(cube.astype(np.float64), angs, full_output=True, **kw)
+    assert np.max(np.abs(co - oo)) < 1e-4 * np.max(np.abs(oo))
+    assert rel_err(fr, of) < FRAME_TOL
+
+
 # ------------------------------------------------------------------ Fourier shift, median subtraction
 SHIFT_TOL = 2e-5
 

@@ -493,3 +493,23 @@ def test_pca_batch_from_fits_paths(vb, tmp_path):
     got = vb.pca(cpath, apath, ncomp=3, batch=6, verbose=False, full_output=True)
     for a, b in zip(got, want):
         np.testing.assert_array_equal(a, b)
+
+
+def test_pca_annular_beyond_the_batched_solver_limits(vb):
+    """``pca_annular`` with more components (ncomp > 24) or larger libraries (> 256 frames) than the batched
+    sub-Gramian eigensolver takes: the frame-by-frame route through the full-size eigensolvers, against the oracle
+    on the float64-cast cube (the reference's fp32 arithmetic with 30 components of a 36-frame library is the noisy
+    side)."""
+    cube, angs = adi_cube(40, 36, 3, 80.0, seed=9)
+    kw = dict(ncomp=30, asize=6, delta_rot=0.05, radius_int=2)
+    co, cd, fr = vb.pca_annular(cube, angs, verbose=False, full_output=True, **kw)
+    oo, od, of = O.pca_annular(cube.astype(np.float64), angs, full_output=True, **kw)
+    assert np.max(np.abs(co - oo)) < 1e-4 * np.max(np.abs(oo))
+    assert rel_err(fr, of) < 3e-4
+    # libraries of 270 frames
+    cube, angs = adi_cube(300, 20, 3, 170.0, seed=10)
+    kw = dict(ncomp=4, asize=5, delta_rot=0.1, max_frames_lib=270, radius_int=2)
+    co, cd, fr = vb.pca_annular(cube, angs, verbose=False, full_output=True, **kw)
+    oo, od, of = O.pca_annular(cube.astype(np.float64), angs, full_output=True, **kw)
+    assert np.max(np.abs(co - oo)) < 1e-4 * np.max(np.abs(oo))
+    assert rel_err(fr, of) < 3e-4

@@ -173,8 +173,9 @@ def _segment_residuals(A, A_lib, angle_list, pa_thr, ncomp, min_frames_lib, max_
             msg += "Try decreasing either delta_rot or min_frames_lib."
             raise RuntimeError(msg.format(len(idx), min_frames_lib))
     Lmax = max(len(i) for i in lists) + nref
-    if Lmax > 256:
-        _unsupported(f"libraries of more than 256 frames (got {Lmax}: max_frames_lib + reference frames)")
+    if Lmax > 256 and auto:
+        _unsupported(f"ncomp='auto' with libraries of more than 256 frames (got {Lmax}: max_frames_lib + reference "
+                     "frames)")
     idx_host = np.zeros((n, max(Lmax, 1)), dtype=np.int32)
     lens = np.zeros(n, dtype=np.int32)
     for f, idx in enumerate(lists):
@@ -201,10 +202,32 @@ def _segment_residuals(A, A_lib, angle_list, pa_thr, ncomp, min_frames_lib, max_
         kernels.gemm(W.unsqueeze(0), lib.unsqueeze(0), R.unsqueeze(0), alpha=-1.0, beta=1.0)
         return R, used
     k = min(ncomp, npx)                      # get_eigenvectors clamps to min(shape) (svd.py:694)
-    if k > 24:
-        _unsupported("more than 24 principal components per annulus")
     G = kernels.gram(lib)
     t0 = _tick("gram", t0)
+    if k > 24 or Lmax > 256:
+        # outside the batched kernel's limits (24 components, 256-frame libraries): the same weights
+        # w = E diag(1/lambda) E^T G[I, f] frame by frame through the full-size eigensolvers (functional, not fast:
+        # ~1 ms per frame and segment); get_eigenvectors clamps ncomp to the library size per frame (svd.py:694)
+        W = torch.zeros((n, lib.shape[0]), dtype=torch.float32, device=dev)
+        for f in range(n):
+            L = int(lens[f])
+            I = torch.from_numpy(idx_host[f, :L].astype(np.int64)).to(dev)
+            kk = min(k, L)
+            Gs = G.index_select(0, I).index_select(1, I).contiguous()
+            if kernels.topk_supported(L, kk):
+                lam, E, info = kernels.eigh_topk(Gs, kk)
+                if not info["converged"]:
+                    lam, E, _ = kernels.eigh(Gs)
+            else:
+                lam, E, _ = kernels.eigh(Gs)
+            lam, E = lam[:kk], E[:kk]                             # E rows = eigenvectors of G[I, I]
+            g = G[nref + f].index_select(0, I)                     # target (emptied) frame . library rows
+            W[f, I] = (E.t() @ ((E @ g) / lam)).to(torch.float32)
+        t0 = _tick("weights (frame-by-frame eigenproblems)", t0)
+        R = A.clone()
+        kernels.gemm(W.unsqueeze(0), lib.unsqueeze(0), R.unsqueeze(0), alpha=-1.0, beta=1.0)
+        _tick("apply W.A_lib and subtract", t0)
+        return R, k
     W, iters = kernels.annular_weights(
         G, torch.from_numpy(idx_host).to(dev), torch.from_numpy(lens).to(dev),
         torch.arange(nref, nref + n, dtype=torch.int32, device=dev), k)
