@@ -69,7 +69,9 @@ def test_c2_scale_and_permutation_equivariance(vb, c2):
     cube, angs = c2
     frame = vb.pca(cube, angs, ncomp=20, verbose=False)
     f4 = vb.pca(4.0 * cube, angs, ncomp=20, verbose=False)
-    assert rel_err(f4, 4.0 * frame.astype(np.float64)) < 1e-6
+    # not bit-exact: the eigensolver accumulates its small Gramians with atomics, so two runs differ by fp32 ulps of
+    # the residuals (~3e-5 near the star) -- a few 1e-7 of the frame peak; passed at 1e-6 on the B200, bound 5e-6
+    assert rel_err(f4, 4.0 * frame.astype(np.float64)) < 5e-6
     perm = np.random.default_rng(3).permutation(cube.shape[0])
     fp = vb.pca(np.ascontiguousarray(cube[perm]), angs[perm], ncomp=20, verbose=False)
     assert rel_err(fp, frame) < 2e-5
