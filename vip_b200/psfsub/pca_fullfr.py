@@ -611,7 +611,7 @@ def _to_numpy_like(t, ref_dtype):
     return a
 
 
-def _pca_adimsdi(p, rot_options, algo_params=None):
+def _pca_adimsdi(p, rot_options):
     """ADI+mSDI branch of ``pca`` (``pca_fullfr.py:497-552``, returns :719-760)."""
     from .sdi import adimsdi_doublepca_device, adimsdi_singlepca_device, adimsdi_singlepca_grid_device
     if p.cube.ndim != 4:
